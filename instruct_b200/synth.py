@@ -1,0 +1,173 @@
+"""Synthetic genotype generator for the InStruct hot path.
+
+The reference ships no example data, so every test and benchmark
+input comes from here.  The generative model is the one InStruct assumes: K clusters with
+allele frequencies ``P[k][l] ~ Dirichlet(1_A)``, individual ``i`` drawn mostly from cluster
+``i mod K``, a per-cluster selfing rate, a geometric number of selfing generations per
+individual, and per locus two allele copies that are forced identical with probability
+``1 - 2**-(G-1)``.  Missing genotypes are i.i.d. Bernoulli.
+
+Two products:
+  * :func:`make_dataset`   -- dense allele indices in the NEW packed layout
+    ``int16[L][N][ploid]`` (negative = missing), optionally on a CUDA device so that
+    config-4 sized inputs (4 GB) never exist as Python lists or text;
+  * :func:`write_reference_text` -- the same data in the reference's text format
+    (two lines per diploid individual, ``label pop a_1 .. a_L``; data_interface.c:133-245)
+    for the compiled reference in ``oracle/_ref``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+MISSING = -9  # the reference's in-memory code for a missing allele (data_interface.c:494)
+
+
+@dataclass
+class SynthData:
+    x: np.ndarray            # int16 [L][N][ploid]
+    allelenum: np.ndarray    # int32 [L]
+    K: int
+    S_true: np.ndarray       # [K] or [N]
+    G_true: np.ndarray       # [N]
+    Q_true: np.ndarray       # [N][K]
+    pop: np.ndarray          # [N] home cluster
+    P_true: np.ndarray       # [K][L][A]
+
+    @property
+    def L(self):
+        return self.x.shape[0]
+
+    @property
+    def N(self):
+        return self.x.shape[1]
+
+    @property
+    def ploid(self):
+        return self.x.shape[2]
+
+
+def make_dataset(N, L, K, A=2, miss=0.0, seed=0, pure=False, own=0.9, s_atoms=None,
+                 ploid=2) -> SynthData:
+    """Diploid synthetic data set (numpy, for tests and small benchmarks)."""
+    rng = np.random.default_rng(seed)
+    P = rng.dirichlet(np.ones(A), size=(K, L))                      # [K][L][A]
+    pop = np.arange(N) % K
+    if pure or K == 1:
+        Q = np.eye(K)[pop]
+    else:
+        Q = np.full((N, K), (1.0 - own) / (K - 1))
+        Q[np.arange(N), pop] = own
+    if s_atoms is None:
+        S_k = np.linspace(0.1, 0.9, K) if K > 1 else np.array([0.5])
+        s_i = S_k[pop]
+        S_true = S_k
+    else:                                                          # individual selfing rates (config 3)
+        s_i = rng.choice(np.asarray(s_atoms, dtype=float), size=N)
+        S_true = s_i
+    G = np.minimum(rng.geometric(1.0 - s_i), 50)                    # generations since outcrossing
+    x = np.empty((L, N, ploid), dtype=np.int16)
+    cumP = np.cumsum(P, axis=2)                                     # [K][L][A]
+    cumQ = np.cumsum(Q, axis=1)
+    for l in range(L):
+        u = rng.random((N, ploid))
+        anc = (rng.random((N, ploid))[:, :, None] > cumQ[:, None, :]).sum(axis=2)   # ancestry per copy
+        anc = np.minimum(anc, K - 1)
+        cp = cumP[anc, l, :]                                        # [N][ploid][A]
+        a = (u[:, :, None] > cp).sum(axis=2)
+        a = np.minimum(a, A - 1)
+        homo = rng.random(N) < (1.0 - 0.5 ** (G - 1))
+        a[homo, 1:] = a[homo, :1]
+        x[l] = a.astype(np.int16)
+    if miss > 0:
+        m = rng.random((L, N)) < miss
+        x[m] = MISSING
+    x, allelenum = recode_dense(x)
+    return SynthData(x=x, allelenum=allelenum, K=K, S_true=S_true, G_true=G, Q_true=Q, pop=pop, P_true=P)
+
+
+def recode_dense(x: np.ndarray):
+    """Renumber alleles per locus in order of first appearance scanning individuals then
+    copies, and drop monomorphic loci -- the rule of transform_data (data_interface.c:510-548).
+    Returns (x', allelenum)."""
+    L, N, ploid = x.shape
+    keep, nums = [], []
+    out = np.empty_like(x)
+    for l in range(L):
+        flat = x[l].reshape(-1)
+        valid = flat >= 0
+        vals = flat[valid]
+        if vals.size == 0:
+            continue
+        uniq, first = np.unique(vals, return_index=True)
+        if uniq.size < 2:
+            continue
+        order = uniq[np.argsort(first)]
+        lut = np.full(int(flat.max()) + 1, -1, dtype=np.int16)
+        lut[order] = np.arange(order.size, dtype=np.int16)
+        row = np.full(flat.shape, MISSING, dtype=np.int16)
+        row[valid] = lut[vals]
+        out[len(keep)] = row.reshape(N, ploid)
+        keep.append(l)
+        nums.append(order.size)
+    return np.ascontiguousarray(out[: len(keep)]), np.asarray(nums, dtype=np.int32)
+
+
+def make_dataset_torch(N, L, K, A=2, miss=0.0, seed=0, device="cuda", own=0.9, chunk=2048):
+    """Config-4 scale generator: same model, torch ops on ``device``, written straight into
+    an int16 [L][N][2] tensor in locus chunks.  Returns (x, allelenum) as torch tensors.
+    Loci are assumed polymorphic (true with overwhelming probability for N >= 1000)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    pop = torch.arange(N, device=device) % K
+    if K > 1:
+        Q = torch.full((N, K), (1.0 - own) / (K - 1), device=device)
+        Q[torch.arange(N, device=device), pop] = own
+    else:
+        Q = torch.ones((N, 1), device=device)
+    cumQ = torch.cumsum(Q, 1)
+    S_k = torch.linspace(0.1, 0.9, K, device=device) if K > 1 else torch.tensor([0.5], device=device)
+    s_i = S_k[pop]
+    u = torch.rand(N, generator=g, device=device).clamp_min(1e-12)
+    G = torch.clamp(torch.floor(torch.log(u) / torch.log(s_i)) + 1, 1, 50)
+    p_homo = 1.0 - torch.pow(0.5, G - 1)
+    x = torch.empty((L, N, 2), dtype=torch.int16, device=device)
+    for l0 in range(0, L, chunk):
+        l1 = min(L, l0 + chunk)
+        n = l1 - l0
+        e = -torch.log(torch.rand((K, n, A), generator=g, device=device).clamp_min(1e-12))
+        cumP = torch.cumsum(e / e.sum(2, keepdim=True), 2)            # Dirichlet(1_A) [K][n][A]
+        anc = (torch.rand((n, N, 2, 1), generator=g, device=device) > cumQ[None, :, None, :]).sum(3)
+        anc.clamp_(max=K - 1)
+        li = torch.arange(n, device=device)[:, None, None].expand(n, N, 2)
+        cp = cumP[anc, li]                                            # [n][N][2][A]
+        a = (torch.rand((n, N, 2, 1), generator=g, device=device) > cp).sum(3).clamp_(max=A - 1)
+        homo = torch.rand((n, N), generator=g, device=device) < p_homo[None, :]
+        a[:, :, 1] = torch.where(homo, a[:, :, 0], a[:, :, 1])
+        if miss > 0:
+            mm = torch.rand((n, N), generator=g, device=device) < miss
+            a[mm] = MISSING
+        x[l0:l1] = a.to(torch.int16)
+    allelenum = torch.full((L,), A, dtype=torch.int32, device=device)
+    return x, allelenum
+
+
+def write_reference_text(path, x: np.ndarray, labels=True, popdata=True, pop=None,
+                         allele_base=100, missing="-9"):
+    """Write a diploid data set in the reference's default format (-af 0): one line per
+    haploid copy, ``[label] [pop] a_1 ... a_L`` (read_data_from_file, data_interface.c:133)."""
+    L, N, ploid = x.shape
+    with open(path, "w") as fh:
+        for i in range(N):
+            for c in range(ploid):
+                tok = []
+                if labels:
+                    tok.append(f"ind{i}")
+                if popdata:
+                    tok.append(str(int(pop[i]) if pop is not None else 0))
+                col = x[:, i, c]
+                tok.extend(missing if v < 0 else str(allele_base + 2 * int(v)) for v in col)
+                fh.write(" ".join(tok) + "\n")
