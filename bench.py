@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the InStruct MCMC sweep on B200 (BASELINE.json metric).
+
+One "step" is one MCMC sweep (one pass of the for(step...) body, mcmc.c:208-235) over the
+resident genotype store.  The default workload is BASELINE.json configs[3]: the SNP-scale
+single chain K=8, N=10,000, L=100,000, diploid, mode 2 -- the configuration the roofline
+target is quoted on, and it fits one GPU (4 GB genotype store + 2 GB Z).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
+  python bench.py --impl reference ...                           the reference's CPU sweep
+
+N > 1 (torchrun, one rank per GPU): ``--shard individuals`` (default) shards the individuals
+of the ONE chain over the ranks -- strong scaling, one int32 NCCL all-reduce of n[L][A][K] and
+one all-gather of the per-individual records per sweep; ``--shard chains`` runs one
+independent chain per rank (weak scaling, no communication).
+
+Output: ONE JSON line on rank 0 (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, L, K, A, miss, mode)
+    "c4": (10_000, 100_000, 8, 2, 0.0, 2),      # BASELINE.json configs[3]
+    "c2": (2_000, 200, 5, 6, 0.05, 2),          # configs[1] (per chain)
+    "c1": (200, 10, 2, 8, 0.0, 2),              # configs[0]
+    "c3": (5_000, 1_000, 4, 4, 0.0, 3),         # configs[2] (DP prior)
+    "tiny": (600, 256, 8, 2, 0.0, 2),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's CPU sweep (oracle/_ref harness around the unmodified mcmc.c), bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_reference_sample(workload, steps, warmup, budget_s=20.0):
+    """Times refh_sweeps() -- the reference's own update_P / update_S_POP / update_G /
+    update_ZQ / update_alpha / cal_lkh in its own order -- on a bounded sample of the
+    workload (same K, A, missing rate and generative model; fewer individuals and loci so a
+    step takes ~1-2 s).  Single-threaded: one chain of the reference cannot use more cores."""
+    import numpy as np
+    from instruct_b200.synth import make_dataset
+    from oracle import pyoracle
+
+    N, L, K, A, miss, mode = WORKLOADS[workload]
+    # ~2.5 M allele copies per sweep at ~2.5 M copy-updates/s ~= 1 s per step
+    target = 1_250_000
+    n = min(N, 500)
+    l = max(8, min(L, target // n))
+    d = make_dataset(N=n, L=l, K=K, A=A, miss=miss, seed=4)
+    kind = "reference" if pyoracle.have_ref() else "port"
+    if kind == "reference":
+        eng = pyoracle.Reference(d.x, d.allelenum, K, mode=mode)
+        eng.setseeds(13, 4, 1972)
+        eng.set_self(np.linspace(0.2, 0.8, K if mode == 2 else n))
+        eng.set_gen(np.ones(n, dtype=np.int32))
+        eng.update_ZQ(1)
+    else:
+        eng = pyoracle.Oracle(d.x, d.allelenum, K, mode=mode)
+        eng.self_rates[...] = np.linspace(0.2, 0.8, eng.self_rates.size)
+        eng.update_ZQ(1)
+    copies = float((~(d.x < 0).any(axis=2)).sum() * 2)
+    eng.sweeps(max(warmup, 1))
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        eng.sweeps(1)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": copies * done / dt, "unit": "copy-updates/s", "cores": 1, "kind": kind,
+            "sample": f"N={d.N} L={d.L} K={K} A={A} miss={miss} mode={mode}: {done} sweeps in {dt:.2f} s "
+                      f"({done / dt:.3f} sweeps/s on the sample; one chain of the reference is single-threaded)",
+            "sweeps_per_sec_sample": done / dt, "ms_per_step": 1e3 * dt / done, "steps": done}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_sample(args.workload, args.steps, args.warmup, budget_s=120.0)
+    N, L, K, A, miss, mode = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "genotype_copy_updates_per_sec", "value": cb["value"], "unit": "copy-updates/s",
+        "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong" if args.shard == "individuals" else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} diploid mode {mode} (bounded sample, see cpu_baseline.sample)"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "copy-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from instruct_b200 import Sampler, SeqData, _lib
+    from instruct_b200.shard import shard_bounds, broadcast_unique_id
+    from instruct_b200.synth import make_dataset_torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    N, L, K, A, miss, mode = WORKLOADS[args.workload]
+    if args.N:
+        N = args.N
+    if args.L:
+        L = args.L
+    shard_ind = world > 1 and args.shard == "individuals"
+    if shard_ind:
+        b, e = shard_bounds(N, world, rank)
+        nloc, i0, count, srank, seed_data = e - b, b, world, rank, 4
+    else:
+        nloc, i0, count, srank, seed_data = N, 0, 1, 0, 4 + rank
+    x, an = make_dataset_torch(N, L, K, A=A, miss=miss, seed=seed_data, device=dev, i0=i0, n_local=nloc)
+    torch.cuda.synchronize()
+    usable = float((~(x < 0).any(dim=2)).sum().item())
+    copies_local = 2.0 * usable
+    # the genotype store is passed by device pointer (inputs resident in HBM); this SeqData only
+    # carries the flags and the (L, Nloc, ploid) shape, through a zero-strided placeholder
+    shape_only = np.lib.stride_tricks.as_strided(np.zeros(1, dtype=np.int16), shape=(L, nloc, 2), strides=(0, 0, 0))
+    sd = SeqData(shape_only, np.zeros(L, dtype=np.int32), K, mode=mode, prior_flag=1 if args.workload == "c3" else 0,
+                 alpha_dpm=2.0)
+    s = Sampler(sd, seed=args.seed, device=local, shard_rank=srank, shard_count=count, totalsize=N,
+                rng_rounds=args.rng_rounds, x_device_ptr=x.data_ptr(), allelenum_device_ptr=an.data_ptr())
+    if shard_ind:
+        uid = broadcast_unique_id(Sampler.unique_id, rank)
+        s.comm_init(uid)
+    s.chain_init(0 if shard_ind else rank, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
+    s.sweep(args.warmup)
+    s.sync()
+    s.profile(True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0, _, k0 = s.profile_read()
+    ms = s.time_sweeps(args.steps)               # CUDA events on the library's stream, sync both sides
+    torch.cuda.synchronize()
+    nz, zq_ms, k1 = s.profile_read()
+    if dist is not None:
+        t = torch.tensor([ms, copies_local if not shard_ind else 0.0], device=dev, dtype=torch.float64)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([copies_local], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ms = float(mx[0].item())
+        copies_total = float(tot[0].item())
+        dist.barrier()
+    else:
+        copies_total = copies_local
+    clk = clocks.stop() if rank == 0 else None
+    geo = s.geometry()
+    algo_bytes_launch = 4.0 * copies_local           # 4 B per allele copy x copies one launch processes
+    zq_avg_ms = zq_ms / max(nz, 1)
+    peak, peak_src = peaks()
+    achieved = algo_bytes_launch / (zq_avg_ms * 1e-3) / 1e9 if zq_avg_ms > 0 else 0.0
+    sweeps_per_s = args.steps / (ms * 1e-3)
+    value = copies_total * sweeps_per_s
+
+    # ---- e2e: the drop-in call with HOST buffers (H2D of the store + D2H of the moments inside)
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        from instruct_b200 import Init, mcmc_updating
+        xh = torch.empty(x.shape, dtype=torch.int16, pin_memory=True)
+        xh.copy_(x)
+        torch.cuda.synchronize()
+        sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, mode=mode, nstep_check_empty_cluster=10 ** 9)
+        upd = args.steps + args.warmup
+        t0 = time.perf_counter()
+        ch = mcmc_updating(sd_h, Init(update=upd, burnin=args.warmup if args.warmup > 0 else 1, thinning=1), 0, None,
+                           seed=args.seed, device=local)
+        dt = time.perf_counter() - t0
+        h2d = xh.numel() * 2 + an.numel() * 4
+        d2h = 8 * (nloc * (2 * K + 3) + 2 * K + 2)
+        e2e = {"value": copies_local * upd / dt, "unit": "copy-updates/s", "h2d_bytes_per_step": h2d / upd,
+               "d2h_bytes_per_step": d2h / upd, "sweeps": upd, "seconds": dt,
+               "note": "one ig_mcmc_updating() call: create + H2D of the pinned genotype store + all sweeps + D2H of CHAIN"}
+        del xh
+    s.close()
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu:
+            cb = cpu_reference_sample(args.workload, steps=12, warmup=1, budget_s=15.0)
+        line = {
+            "metric": "genotype_copy_updates_per_sec", "value": value, "unit": "copy-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if (shard_ind or world == 1) else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "sweeps_per_sec": sweeps_per_s,
+            "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} diploid mode {mode} miss={miss}",
+                       "parallelism": ("individual-sharded x%d" % world) if shard_ind else ("chains x%d" % world),
+                       "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel()) / 1e9),
+                       "geometry": geo, "rng": f"philox4x32-{args.rng_rounds or 10}"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
+                         "algorithmic_bytes_per_launch": algo_bytes_launch, "peak_source": peak_src,
+                         "share_of_step": zq_ms / ms if ms > 0 else None},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None,
+            "e2e": e2e, "gpu_launches": int(k1 - k0), "clocks": clk,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="individuals", choices=["individuals", "chains"])
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--rng-rounds", type=int, default=0)
+    ap.add_argument("--N", type=int, default=0)
+    ap.add_argument("--L", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1030 @@
+// ig_api.cu -- the C-ABI of include/instruct_b200.h: context, chain driver, multi-GPU exchange,
+// the host-side Dirichlet-process step, and the state hooks the parity tests use.
+//
+// The chain driver restates the control flow of mcmc_POP_selfing / mcmc_INDV_selfing
+// (mcmc.c:182-239, 297-383) around the kernels in ig_kernels.cu.  Nothing here falls back
+// to the CPU: every entry point needs a CUDA device.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "ig_internal.h"
+#include "philox.cuh"
+#include "samplers.cuh"
+
+using namespace ig;
+
+// --------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static ig_status fail(ig_status st, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return st;
+}
+#define CK(call)                                                                                           \
+	do {                                                                                               \
+		cudaError_t e_ = (call);                                                                       \
+		if (e_ != cudaSuccess) return fail(IG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+extern "C" const char *ig_last_error(void) { return g_err; }
+extern "C" const char *ig_version(void) { return "instruct_b200 0.1 (sm_100a)"; }
+extern "C" int ig_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+// --------------------------------------------------------------------------------------
+// NCCL, bound at run time (the library must load on a box without NCCL or a GPU)
+// --------------------------------------------------------------------------------------
+struct NcclApi {
+	void *h = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static ig_status nccl_load()
+{
+	if (g_nccl.h) return IG_OK;
+	void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) return fail(IG_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(f, name)                                                    \
+	*(void **)(&g_nccl.f) = dlsym(h, name);                             \
+	if (!g_nccl.f) return fail(IG_ERR_NCCL, "libnccl lacks %s", name)
+	SYM(GetUniqueId, "ncclGetUniqueId");
+	SYM(CommInitRank, "ncclCommInitRank");
+	SYM(CommDestroy, "ncclCommDestroy");
+	SYM(AllReduce, "ncclAllReduce");
+	SYM(AllGather, "ncclAllGather");
+	SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+	g_nccl.h = h;
+	return IG_OK;
+}
+#define NCK(call)                                                                                   \
+	do {                                                                                        \
+		ncclResult_t r_ = (call);                                                               \
+		if (r_ != ncclSuccess) return fail(IG_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r_)); \
+	} while (0)
+
+// --------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------
+struct DpCluster { double value; int num; int next; };
+
+struct ig_ctx {
+	ig_config cfg;
+	Geometry geo;
+	int ns;                    // length of S: K (mode 2) or N (mode 3)
+	int Npad;                  // records in ind: shard_count * shard_cap
+	int shard_cap;
+	cudaStream_t stream = nullptr;
+	bool loaded = false, chain_ready = false;
+	uint32_t iter = 0, key0 = 0, key1 = 0;
+	int rounds = 10;
+	// device buffers
+	int16_t *Xt = nullptr;
+	int8_t *Zt = nullptr;
+	float *P = nullptr;
+	double *P64 = nullptr;
+	int32_t *n = nullptr;
+	int32_t *allelenum = nullptr;
+	double *ind = nullptr;
+	float *Qf = nullptr;
+	int32_t *gprop = nullptr;
+	int2 *gpair = nullptr;
+	double *S = nullptr;
+	int32_t *state = nullptr;
+	DevScalars *sc = nullptr;
+	uint16_t *pcnt = nullptr;
+	double *plog = nullptr;
+	int32_t *cnt = nullptr;
+	double *llparts = nullptr;
+	float *initd_dev = nullptr;
+	double *scratch = nullptr;      // small device scratch (parity hooks)
+	Moments mom{};
+	// host mirrors
+	std::vector<int32_t> allelenum_h;
+	std::vector<double> ind_h, S_h;
+	// DP prior (host)
+	std::vector<DpCluster> dp;
+	std::vector<int> dp_of;
+	int dp_head = -1, dp_free = -1, dp_cnt = 0;
+	// NCCL
+	ncclComm_t comm = nullptr;
+	// profiling
+	bool profile = false;
+	std::vector<cudaEvent_t> ev;
+	int ev_used = 0;
+	int64_t launches = 0;
+};
+
+static uint32_t pad_k(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n)
+{
+	cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+	if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+	return e;
+}
+
+extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
+{
+	if (!cfg || !out) return fail(IG_ERR_ARG, "null argument");
+	*out = nullptr;
+	if (cfg->ploid != 2) return fail(IG_ERR_UNSUPPORTED, "ploid %d: only the diploid sampler is built in this library version", cfg->ploid);
+	if (cfg->mode != 2 && cfg->mode != 3) return fail(IG_ERR_UNSUPPORTED, "mode %d: only modes 2 and 3 are on the hot path", cfg->mode);
+	if (cfg->popnum < 1 || cfg->popnum > MAX_K) return fail(IG_ERR_UNSUPPORTED, "popnum %d outside 1..%d", cfg->popnum, MAX_K);
+	if (cfg->locinum < 1 || cfg->totalsize < 1) return fail(IG_ERR_ARG, "empty data set (N=%d, L=%d)", cfg->totalsize, cfg->locinum);
+	if (cfg->mode == 3 && cfg->prior_flag != 0 && cfg->prior_flag != 1) return fail(IG_ERR_ARG, "prior_flag must be 0 or 1");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(IG_ERR_CUDA, "no CUDA device: instruct_b200 has no CPU path");
+	}
+	if (cfg->device < 0 || cfg->device >= ndev) return fail(IG_ERR_ARG, "device %d of %d", cfg->device, ndev);
+	CK(cudaSetDevice(cfg->device));
+
+	ig_ctx *c = new ig_ctx();
+	c->cfg = *cfg;
+	const int count = cfg->shard_count > 1 ? cfg->shard_count : 1;
+	const int rank = count > 1 ? cfg->shard_rank : 0;
+	const int N = cfg->totalsize;
+	c->shard_cap = (N + count - 1) / count;
+	c->Npad = c->shard_cap * count;
+	Geometry &g = c->geo;
+	g.N = N;
+	g.i0 = rank * c->shard_cap;
+	g.Nloc = N - g.i0 < c->shard_cap ? N - g.i0 : c->shard_cap;
+	if (g.Nloc < 1) { delete c; return fail(IG_ERR_ARG, "shard %d of %d is empty for N=%d", rank, count, N); }
+	if (count > 1 && cfg->shard_size != 0 && (cfg->shard_size != g.Nloc || cfg->shard_begin != g.i0)) {
+		const int b = g.i0, e = g.i0 + g.Nloc;
+		delete c;
+		return fail(IG_ERR_ARG, "shard %d must be [%d,%d) (got begin %d size %d)", rank, b, e, cfg->shard_begin, cfg->shard_size);
+	}
+	g.L = cfg->locinum;
+	g.Lpad = (g.L + TILE - 1) / TILE * TILE;
+	g.LT = g.Lpad / TILE;
+	g.K = cfg->popnum;
+	g.KP = (int)pad_k(g.K);
+	g.A = 2;                   // fixed when the genotypes are loaded
+	g.REC = g.K + 3;
+	c->ns = (cfg->mode == 3) ? N : g.K;
+	c->rounds = (cfg->rng_rounds == 7) ? 7 : 10;
+	c->key0 = (uint32_t)cfg->seed;
+	c->key1 = (uint32_t)(cfg->seed >> 32);
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(IG_ERR_CUDA, "stream creation failed"); }
+	*out = c;
+	return IG_OK;
+}
+
+static void free_all(ig_ctx *c)
+{
+	cudaFree(c->Xt); cudaFree(c->Zt); cudaFree(c->P); cudaFree(c->P64); cudaFree(c->n); cudaFree(c->allelenum);
+	cudaFree(c->ind); cudaFree(c->Qf); cudaFree(c->gprop); cudaFree(c->gpair); cudaFree(c->S); cudaFree(c->state);
+	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
+	cudaFree(c->scratch);
+	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
+	cudaFree(c->mom.self2); cudaFree(c->mom.gen); cudaFree(c->mom.gen2); cudaFree(c->mom.freq); cudaFree(c->mom.freq2);
+	cudaFree(c->mom.convg);
+}
+
+extern "C" void ig_destroy(ig_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->cfg.device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+	for (auto e : c->ev) cudaEventDestroy(e);
+	free_all(c);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+// allocate everything that depends on allelenum_max, then tile the genotype store
+static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
+{
+	Geometry &g = c->geo;
+	int amax = 1;
+	for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] > amax) amax = c->allelenum_h[l];
+	if (amax > 32000) return fail(IG_ERR_ARG, "allelenum_max %d does not fit the int16 genotype store", amax);
+	g.A = amax < 2 ? 2 : amax;
+	CK(zq_configure(g, c->cfg.device));
+	const size_t tiles = (size_t)g.LT * g.Nloc * TILE * 2;
+	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
+	CK(dalloc(&c->Xt, tiles));
+	CK(dalloc(&c->Zt, tiles));
+	CK(dalloc(&c->P, pn));
+	CK(dalloc(&c->n, pn));
+	if (c->cfg.print_freq) CK(dalloc(&c->P64, (size_t)g.K * g.L * g.A));
+	CK(dalloc(&c->ind, (size_t)c->Npad * g.REC));
+	CK(dalloc(&c->Qf, (size_t)g.Nloc * g.KP));
+	CK(dalloc(&c->gprop, (size_t)c->Npad));
+	CK(dalloc(&c->gpair, (size_t)g.Nloc));
+	CK(dalloc(&c->S, (size_t)(c->ns > g.K ? c->ns : g.K)));
+	CK(dalloc(&c->state, (size_t)MAX_K));
+	CK(dalloc(&c->sc, 1));
+	CK(dalloc(&c->pcnt, (size_t)g.nchunks * g.Nloc * g.KP));
+	CK(dalloc(&c->plog, (size_t)g.nchunks * 4 * g.Nloc));
+	CK(dalloc(&c->cnt, (size_t)g.Nloc * g.K));
+	CK(dalloc(&c->llparts, (size_t)g.Nloc * 4));
+	CK(dalloc(&c->initd_dev, (size_t)MAX_K));
+	CK(dalloc(&c->scratch, (size_t)64));
+	CK(dalloc(&c->mom.tot, 2));
+	CK(dalloc(&c->mom.indvlkh, (size_t)g.N));
+	CK(dalloc(&c->mom.qq, (size_t)g.N * g.K));
+	CK(dalloc(&c->mom.qq2, (size_t)g.N * g.K));
+	CK(dalloc(&c->mom.self, (size_t)c->ns));
+	CK(dalloc(&c->mom.self2, (size_t)c->ns));
+	CK(dalloc(&c->mom.gen, (size_t)g.N));
+	CK(dalloc(&c->mom.gen2, (size_t)g.N));
+	CK(dalloc(&c->mom.convg, (size_t)(c->cfg.ckrep > 0 ? c->cfg.ckrep : 1)));
+	if (c->cfg.print_freq) {
+		CK(dalloc(&c->mom.freq, (size_t)g.K * g.L * g.A));
+		CK(dalloc(&c->mom.freq2, (size_t)g.K * g.L * g.A));
+	}
+	CK(launch_tile_x(x_dev_canon, c->Xt, c->allelenum, g, c->stream));
+	c->launches++;
+	CK(cudaStreamSynchronize(c->stream));
+	c->loaded = true;
+	return IG_OK;
+}
+
+extern "C" ig_status ig_load_genotypes(ig_ctx *c, const int16_t *x_host, const int32_t *allelenum_host)
+{
+	if (!c || !x_host || !allelenum_host) return fail(IG_ERR_ARG, "null argument");
+	if (c->loaded) return fail(IG_ERR_STATE, "genotypes already loaded");
+	CK(cudaSetDevice(c->cfg.device));
+	Geometry &g = c->geo;
+	c->allelenum_h.assign(allelenum_host, allelenum_host + g.L);
+	CK(dalloc(&c->allelenum, (size_t)g.Lpad));
+	CK(cudaMemcpyAsync(c->allelenum, allelenum_host, (size_t)g.L * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	int16_t *tmp = nullptr;
+	const size_t bytes = (size_t)g.L * g.Nloc * 2 * sizeof(int16_t);
+	CK(cudaMalloc((void **)&tmp, bytes));
+	cudaError_t e = cudaMemcpyAsync(tmp, x_host, bytes, cudaMemcpyHostToDevice, c->stream);
+	if (e != cudaSuccess) { cudaFree(tmp); CK(e); }
+	ig_status st = finish_load(c, tmp);
+	cudaFree(tmp);
+	return st;
+}
+
+extern "C" ig_status ig_load_genotypes_device(ig_ctx *c, const int16_t *x_dev, const int32_t *allelenum_dev)
+{
+	if (!c || !x_dev || !allelenum_dev) return fail(IG_ERR_ARG, "null argument");
+	if (c->loaded) return fail(IG_ERR_STATE, "genotypes already loaded");
+	CK(cudaSetDevice(c->cfg.device));
+	Geometry &g = c->geo;
+	c->allelenum_h.resize(g.L);
+	CK(cudaMemcpy(c->allelenum_h.data(), allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+	CK(dalloc(&c->allelenum, (size_t)g.Lpad));
+	CK(cudaMemcpy(c->allelenum, allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+	return finish_load(c, x_dev);
+}
+
+// --------------------------------------------------------------------------------------
+// multi-GPU
+// --------------------------------------------------------------------------------------
+extern "C" ig_status ig_comm_unique_id(void *id128)
+{
+	if (!id128) return fail(IG_ERR_ARG, "null argument");
+	ig_status st = nccl_load();
+	if (st != IG_OK) return st;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	NCK(g_nccl.GetUniqueId(&id));
+	memcpy(id128, &id, 128);
+	return IG_OK;
+}
+
+extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
+{
+	if (!c || !id128) return fail(IG_ERR_ARG, "null argument");
+	if (c->cfg.shard_count <= 1) return IG_OK;
+	ig_status st = nccl_load();
+	if (st != IG_OK) return st;
+	CK(cudaSetDevice(c->cfg.device));
+	ncclUniqueId id;
+	memcpy(&id, id128, 128);
+	NCK(g_nccl.CommInitRank(&c->comm, c->cfg.shard_count, id, c->cfg.shard_rank));
+	return IG_OK;
+}
+
+static ig_status exchange_tally(ig_ctx *c)
+{
+	// the one per-sweep reduction of the sharded mode: int32 n[L][A][K] summed over the shards
+	// (integer => identical on every rank and for every shard count)
+	if (!c->comm) return IG_OK;
+	const Geometry &g = c->geo;
+	NCK(g_nccl.AllReduce(c->n, c->n, (size_t)g.Lpad * g.A * g.KP, ncclInt32, ncclSum, c->comm, c->stream));
+	return IG_OK;
+}
+static ig_status exchange_individuals(ig_ctx *c)
+{
+	// (Q, indvlkh, sum log q, G) of every shard, so that the O(N*K) scalar updates run
+	// redundantly and identically on every rank
+	if (!c->comm) return IG_OK;
+	const Geometry &g = c->geo;
+	const size_t cnt = (size_t)c->shard_cap * g.REC;
+	NCK(g_nccl.AllGather(c->ind + (size_t)g.i0 * g.REC, c->ind, cnt, ncclDouble, c->comm, c->stream));
+	return IG_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// Dirichlet-process prior on the individual selfing rates -- host side (DPMM.c:124-398).
+// The step is a sequential Chinese-restaurant Gibbs scan over individuals; it reads only
+// G[0..N) and writes only S[0..N), i.e. N ints down and N doubles up per sweep.  Clusters
+// live in a value-sorted index-linked pool.  Randomness: Philox site (j, 0, iter, TAG_DP).
+// --------------------------------------------------------------------------------------
+static void dp_reset(ig_ctx *c)
+{
+	const int N = c->geo.N;
+	c->dp.assign(N + 1, DpCluster{0.0, 0, -1});
+	for (int s = 0; s <= N; s++) c->dp[s].next = s + 1;
+	c->dp[N].next = -1;
+	c->dp_free = 0; c->dp_head = -1; c->dp_cnt = 0;
+	c->dp_of.assign(N, -1);
+}
+static int dp_create(ig_ctx *c, double v)
+{
+	const int s = c->dp_free;
+	c->dp_free = c->dp[s].next;
+	c->dp[s].value = v; c->dp[s].num = 1;
+	if (c->dp_head < 0 || v <= c->dp[c->dp_head].value) { c->dp[s].next = c->dp_head; c->dp_head = s; return s; }
+	int q = c->dp_head, p = c->dp[q].next;
+	while (p >= 0 && c->dp[p].value <= v) { q = p; p = c->dp[p].next; }
+	c->dp[s].next = p;
+	c->dp[q].next = s;
+	return s;
+}
+static void dp_leave(ig_ctx *c, int j)
+{
+	const int s = c->dp_of[j];
+	if (--c->dp[s].num > 0) return;
+	if (c->dp_head == s) c->dp_head = c->dp[s].next;
+	else {
+		int q = c->dp_head;
+		while (c->dp[q].next != s) q = c->dp[q].next;
+		c->dp[q].next = c->dp[s].next;
+	}
+	c->dp[s].next = c->dp_free;
+	c->dp_free = s;
+	c->dp_cnt--;
+}
+// pick an index in [0, n) with probability proportional to w[i] (disc_unif, random.c:403)
+static int pick_weighted(const std::vector<double> &cum, int n, double u)
+{
+	const double t = u * cum[n - 1];
+	int k = 0;
+	while (k < n - 1 && t > cum[k]) k++;
+	return k;
+}
+static void dp_init(ig_ctx *c)                         // init_DP, DPMM.c:124-161
+{
+	const int N = c->geo.N;
+	const double a = c->cfg.alpha_dpm;
+	dp_reset(c);
+	c->S_h.assign(N, 0.0);
+	std::vector<double> cum(N + 1);
+	for (int j = 0; j < N; j++) {
+		Stream st((uint32_t)j, 0u, 0u, TAG_DP, c->key0, c->key1);
+		cum[0] = a / (a + j);
+		int n = 1;
+		for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++) cum[n] = cum[n - 1] + c->dp[p].num / (a + j);
+		const int pick = pick_weighted(cum, n, st.uniform());
+		if (pick == 0) { c->S_h[j] = st.uniform(); c->dp_of[j] = dp_create(c, c->S_h[j]); c->dp_cnt++; }
+		else {
+			int p = c->dp_head;
+			for (int k = 1; k < pick; k++) p = c->dp[p].next;
+			c->dp[p].num++; c->dp_of[j] = p; c->S_h[j] = c->dp[p].value;
+		}
+	}
+}
+static void dp_update(ig_ctx *c, const std::vector<double> &ind_h)   // update_DP, DPMM.c:165-199
+{
+	const Geometry &g = c->geo;
+	const int N = g.N;
+	std::vector<double> cum(N + 1);
+	for (int j = 0; j < N; j++) {
+		Stream st((uint32_t)j, 0u, c->iter, TAG_DP, c->key0, c->key1);
+		const int gen = (int)ind_h[(size_t)j * g.REC + g.K + 2];
+		dp_leave(c, j);
+		cum[0] = c->cfg.alpha_dpm / (gen + 1) / gen;                  // gen_post_prob, DPMM.c:369
+		int n = 1;
+		for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++) {
+			const double v = c->dp[p].value;
+			cum[n] = cum[n - 1] + c->dp[p].num * (pow(v, (double)(gen - 1)) * (1.0 - v));   // dgeom, mcmc.c:1602
+		}
+		const int pick = pick_weighted(cum, n, st.uniform());
+		if (pick == 0) {                                              // sample_poster, DPMM.c:395: Beta(G, 2)
+			c->S_h[j] = draw_beta(st, (double)gen, 2.0);
+			c->dp_of[j] = dp_create(c, c->S_h[j]);
+			c->dp_cnt++;
+		} else {
+			int p = c->dp_head;
+			for (int k = 1; k < pick; k++) p = c->dp[p].next;
+			c->dp[p].num++; c->dp_of[j] = p; c->S_h[j] = c->dp[p].value;
+		}
+	}
+}
+
+// --------------------------------------------------------------------------------------
+// sweep phases
+// --------------------------------------------------------------------------------------
+static ZQArgs zq_args(ig_ctx *c)
+{
+	ZQArgs a;
+	a.Xt = c->Xt; a.Zt = c->Zt; a.P = c->P; a.n = c->n; a.Qf = c->Qf; a.gpair = c->gpair;
+	a.pcnt = c->pcnt; a.plog = c->plog; a.geo = c->geo; a.iter = c->iter; a.key0 = c->key0; a.key1 = c->key1;
+	a.type_freq = c->cfg.type_freq;
+	return a;
+}
+
+static ig_status phase_update_P(ig_ctx *c)
+{
+	ig_status st = exchange_tally(c);
+	if (st != IG_OK) return st;
+	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1};
+	CK(launch_p_dirichlet(a, c->stream));
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status phase_update_S(ig_ctx *c)
+{
+	const Geometry &g = c->geo;
+	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1) {
+		c->ind_h.resize((size_t)c->Npad * g.REC);
+		CK(cudaMemcpyAsync(c->ind_h.data(), c->ind, c->ind_h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		dp_update(c, c->ind_h);
+		CK(cudaMemcpyAsync(c->S, c->S_h.data(), (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	}
+	PreArgs a{c->ind, c->S, c->state, c->gprop, c->gpair, c->sc, c->geo, c->iter, c->key0, c->key1,
+	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl};
+	CK(launch_pre_sweep(a, c->stream));
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status phase_zq(ig_ctx *c, int init)
+{
+	ZQArgs a = zq_args(c);
+	if (init) a.type_freq = 1;
+	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
+	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
+	CK(launch_zq_sweep(a, c->rounds, c->stream));
+	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
+	EpiArgs e{c->pcnt, c->plog, c->ind, c->Qf, c->cnt, c->llparts, c->gpair, c->sc, c->geo, c->iter, c->key0, c->key1, init};
+	CK(launch_epilogue(e, c->stream));
+	c->launches += 2;
+	return exchange_individuals(c);
+}
+
+static ig_status phase_alpha(ig_ctx *c)
+{
+	PostArgs a{c->ind, c->sc, c->geo, c->iter, c->key0, c->key1};
+	CK(launch_post_sweep(a, c->stream));
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status one_sweep(ig_ctx *c)
+{
+	ig_status st;
+	c->iter++;
+	if ((st = phase_update_P(c)) != IG_OK) return st;      // update_P            mcmc.c:210
+	if ((st = phase_update_S(c)) != IG_OK) return st;      // update_S_* + G proposal  :211-212
+	if ((st = phase_zq(c, 0)) != IG_OK) return st;         // update_G accept, update_ZQ, cal_lkh :212-215
+	return phase_alpha(c);                                 // update_alpha, totallkh    :214-215
+}
+
+extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *initd)
+{
+	if (!c) return fail(IG_ERR_ARG, "null context");
+	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
+	CK(cudaSetDevice(c->cfg.device));
+	const Geometry &g = c->geo;
+	c->key0 = (uint32_t)c->cfg.seed ^ (0x9E3779B9u * (uint32_t)(chain_id + 1));
+	c->key1 = (uint32_t)(c->cfg.seed >> 32) ^ (0x85EBCA6Bu * (uint32_t)(chain_id + 1));
+	c->iter = 0;
+	float init_h[MAX_K];
+	for (int k = 0; k < MAX_K; k++) init_h[k] = (initd && k < g.K) ? initd[k] : 0.5f;
+	if (c->cfg.mode == 2 && !initd) {
+		// read_init without an -i file draws the starting rates from U(0,1) (initial.c:52-58)
+		Stream st(0u, 2u, 0u, TAG_INIT, c->key0, c->key1);
+		for (int k = 0; k < g.K; k++) init_h[k] = (float)st.uniform();
+	}
+	CK(cudaMemcpyAsync(c->initd_dev, init_h, sizeof(init_h), cudaMemcpyHostToDevice, c->stream));
+	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1) {
+		dp_init(c);
+		CK(cudaMemcpyAsync(c->S, c->S_h.data(), (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	}
+	CK(launch_init_chain(c->ind, c->S, c->state, c->sc, c->initd_dev, c->gprop, c->gpair, g, c->cfg.mode, c->cfg.prior_flag,
+	                     c->cfg.back_refl, c->key0, c->key1, c->stream));
+	// initial assignment (update_ZQ with init_flag = 1, mcmc.c:206,1143-1144): uniform Z is the
+	// categorical draw with all weights equal, so the sweep kernel runs once with P = Q = 1
+	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
+	CK(launch_fill_f32(c->P, 1.0f, pn, c->stream));
+	CK(launch_fill_f32(c->Qf, 1.0f, (size_t)g.Nloc * g.KP, c->stream));
+	CK(cudaMemsetAsync(c->n, 0, pn * sizeof(int32_t), c->stream));
+	CK(cudaMemsetAsync(c->Zt, 0, (size_t)g.LT * g.Nloc * TILE * 2, c->stream));
+	c->launches += 3;
+	ig_status st = phase_zq(c, 1);
+	if (st != IG_OK) return st;
+	c->chain_ready = true;
+	return IG_OK;
+}
+
+extern "C" ig_status ig_sweep(ig_ctx *c, int32_t nsweeps)
+{
+	if (!c) return fail(IG_ERR_ARG, "null context");
+	if (!c->chain_ready) return fail(IG_ERR_STATE, "call ig_chain_init first");
+	CK(cudaSetDevice(c->cfg.device));
+	for (int s = 0; s < nsweeps; s++) {
+		ig_status st = one_sweep(c);
+		if (st != IG_OK) return st;
+	}
+	return IG_OK;
+}
+
+extern "C" ig_status ig_time_sweeps(ig_ctx *c, int32_t nsweeps, double *elapsed_ms)
+{
+	if (!c || !elapsed_ms) return fail(IG_ERR_ARG, "null argument");
+	if (!c->chain_ready) return fail(IG_ERR_STATE, "call ig_chain_init first");
+	CK(cudaSetDevice(c->cfg.device));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0));
+	CK(cudaEventCreate(&e1));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaEventRecord(e0, c->stream));
+	ig_status st = IG_OK;
+	for (int s = 0; s < nsweeps && st == IG_OK; s++) st = one_sweep(c);
+	cudaEventRecord(e1, c->stream);
+	cudaError_t e = cudaEventSynchronize(e1);
+	float ms = 0.f;
+	if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (st != IG_OK) return st;
+	CK(e);
+	*elapsed_ms = ms;
+	return IG_OK;
+}
+
+extern "C" ig_status ig_sync(ig_ctx *c)
+{
+	if (!c) return fail(IG_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaStreamSynchronize(c->stream));
+	return IG_OK;
+}
+
+extern "C" ig_status ig_run_phase(ig_ctx *c, int32_t mask)
+{
+	if (!c) return fail(IG_ERR_ARG, "null context");
+	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
+	CK(cudaSetDevice(c->cfg.device));
+	ig_status st;
+	if (mask & IG_PHASE_UPDATE_P) if ((st = phase_update_P(c)) != IG_OK) return st;
+	if (mask & IG_PHASE_UPDATE_S) if ((st = phase_update_S(c)) != IG_OK) return st;
+	if (mask & IG_PHASE_ZQ) if ((st = phase_zq(c, 0)) != IG_OK) return st;
+	if (mask & IG_PHASE_ALPHA) if ((st = phase_alpha(c)) != IG_OK) return st;
+	CK(cudaStreamSynchronize(c->stream));
+	return IG_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// the chain driver
+// --------------------------------------------------------------------------------------
+static ig_status download_result(ig_ctx *c, ig_chain_result *out, double *convg_ld, long stored)
+{
+	const Geometry &g = c->geo;
+	double tot[2];
+	CK(cudaMemcpyAsync(tot, c->mom.tot, sizeof(tot), cudaMemcpyDeviceToHost, c->stream));
+#define DL(dst, src, n) \
+	if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream))
+	DL(out->indvlkh, c->mom.indvlkh, g.N);
+	DL(out->qq, c->mom.qq, (size_t)g.N * g.K);
+	DL(out->qq2, c->mom.qq2, (size_t)g.N * g.K);
+	DL(out->self_rates, c->mom.self, c->ns);
+	DL(out->self_rates2, c->mom.self2, c->ns);
+	DL(out->gen, c->mom.gen, g.N);
+	DL(out->gen2, c->mom.gen2, g.N);
+	if (c->cfg.print_freq) {
+		DL(out->freq, c->mom.freq, (size_t)g.K * g.L * g.A);
+		DL(out->freq2, c->mom.freq2, (size_t)g.K * g.L * g.A);
+	}
+	if (convg_ld && c->cfg.ckrep > 0) {
+		const long nv = stored < c->cfg.ckrep ? stored : c->cfg.ckrep;
+		if (nv > 0) CK(cudaMemcpyAsync(convg_ld, c->mom.convg, (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	}
+#undef DL
+	CK(cudaStreamSynchronize(c->stream));
+	out->totallkh = tot[0];
+	out->totallkh2 = tot[1];
+	return IG_OK;
+}
+
+extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *initd, ig_chain_result *out, double *convg_ld)
+{
+	if (!c || !out) return fail(IG_ERR_ARG, "null argument");
+	const ig_config &cf = c->cfg;
+	if (cf.update < 1 || cf.burnin < 1 || cf.thinning < 1 || cf.burnin > cf.update)
+		return fail(IG_ERR_ARG, "need 1 <= burnin <= update and thinning >= 1 (InStruct.c:299-300)");
+	ig_status st = ig_chain_init(c, chain_id, initd);
+	if (st != IG_OK) return st;
+	const Geometry &g = c->geo;
+	out->steps = (cf.update - cf.burnin) / cf.thinning;              // mcmc.c:485
+	out->step = 0;
+	out->flag_empty_cluster = 0;
+	long cnt_step = 0;
+	MomArgs m{c->ind, c->S, c->sc, c->P, c->mom, g, c->ns, 0, -1, cf.print_freq};
+	const long print_every = cf.update >= 100 ? cf.update / 100 : 1;   // print_info, mcmc.c:1273 (guards the /0 of App. B #7)
+	for (long step = 0; step < cf.update; step++) {
+		if ((st = one_sweep(c)) != IG_OK) return st;
+		if (cf.print_iter == 1 && step % print_every == 0) {
+			DevScalars h;
+			CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaStreamSynchronize(c->stream));
+			fprintf(stdout, "\nStep=%ld\tlog_likelihood=%f\n", step + 1, h.totallkh);
+			if (cf.mode == 2) {
+				double sh[MAX_K];
+				CK(cudaMemcpy(sh, c->S, g.K * sizeof(double), cudaMemcpyDeviceToHost));
+				for (int k = 0; k < g.K; k++) fprintf(stdout, "s_%d=%f%s", k, sh[k], k < g.K - 1 ? " " : "");
+				fprintf(stdout, "\n");
+			}
+		}
+		if (step == cf.burnin - 1) {                                   // allocate_chn, mcmc.c:218-219
+			CK(launch_moments_reset(m, c->stream));
+			c->launches++;
+		}
+		if (step >= cf.burnin && (step + 1 - cf.burnin) % cf.thinning == 0) {    // mcmc.c:220-226
+			m.step = cnt_step;
+			m.convg_slot = (cnt_step < cf.ckrep) ? (int)cnt_step : -1;
+			CK(launch_moments(m, c->stream));
+			c->launches++;
+			cnt_step++;
+		}
+		if (cnt_step == cf.nstep_check_empty_cluster) {                // mcmc.c:227-234
+			DevScalars h;
+			CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaStreamSynchronize(c->stream));
+			int empty = 0;
+			for (int k = 0; k < g.K; k++) if (h.qcol[k] < 0.01) empty = 1;   // check_empty_cluster, mcmc.c:1963-1970
+			out->flag_empty_cluster = empty;
+			if (empty) break;
+		}
+	}
+	out->step = cnt_step;
+	st = download_result(c, out, convg_ld, cnt_step);
+	if (st != IG_OK) return st;
+	return out->flag_empty_cluster ? IG_EMPTY_CLUSTER : IG_OK;
+}
+
+extern "C" ig_status ig_mcmc_updating(const ig_config *cfg, const int16_t *x_host, const int32_t *allelenum_host,
+                                      int32_t chain_id, const float *initd, ig_chain_result *out, double *convg_ld)
+{
+	ig_ctx *c = nullptr;
+	ig_status st = ig_create(cfg, &c);
+	if (st != IG_OK) return st;
+	st = ig_load_genotypes(c, x_host, allelenum_host);
+	if (st == IG_OK) st = ig_run_chain(c, chain_id, initd, out, convg_ld);
+	ig_destroy(c);
+	return st;
+}
+
+// --------------------------------------------------------------------------------------
+// state hooks (parity tests): canonical host layouts <-> device layouts
+// --------------------------------------------------------------------------------------
+static ig_status need(size_t have, size_t want, const char *what)
+{
+	if (have != want) return fail(IG_ERR_ARG, "%s: expected %zu bytes, got %zu", what, want, have);
+	return IG_OK;
+}
+
+extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t bytes)
+{
+	if (!c || !host) return fail(IG_ERR_ARG, "null argument");
+	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
+	CK(cudaSetDevice(c->cfg.device));
+	const Geometry &g = c->geo;
+	ig_status st;
+	CK(cudaStreamSynchronize(c->stream));
+	switch (id) {
+	case IG_STATE_X:
+	case IG_STATE_Z: {
+		const size_t el = (size_t)g.L * g.Nloc * 2;
+		const size_t want = el * (id == IG_STATE_X ? 2 : 1);
+		if ((st = need(bytes, want, "X/Z")) != IG_OK) return st;
+		void *tmp = nullptr;
+		CK(cudaMalloc(&tmp, want));
+		cudaError_t e = (id == IG_STATE_X) ? launch_untile_x(c->Xt, (int16_t *)tmp, g, c->stream) : launch_untile_z(c->Zt, (int8_t *)tmp, g, c->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(host, tmp, want, cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		cudaFree(tmp);
+		CK(e);
+		return IG_OK;
+	}
+	case IG_STATE_MASK: {
+		if ((st = need(bytes, (size_t)g.L * g.Nloc, "MASK")) != IG_OK) return st;
+		std::vector<int16_t> x((size_t)g.L * g.Nloc * 2);
+		if ((st = ig_get_state(c, IG_STATE_X, x.data(), x.size() * 2)) != IG_OK) return st;
+		uint8_t *m = (uint8_t *)host;
+		for (size_t t = 0; t < (size_t)g.L * g.Nloc; t++) m[t] = (x[2 * t] < 0 || x[2 * t + 1] < 0) ? 1 : 0;
+		return IG_OK;
+	}
+	case IG_STATE_Q: {
+		if ((st = need(bytes, (size_t)g.N * g.K * 8, "Q")) != IG_OK) return st;
+		std::vector<double> r((size_t)c->Npad * g.REC);
+		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		double *q = (double *)host;
+		for (int i = 0; i < g.N; i++) for (int k = 0; k < g.K; k++) q[(size_t)i * g.K + k] = r[(size_t)i * g.REC + k];
+		return IG_OK;
+	}
+	case IG_STATE_G:
+	case IG_STATE_INDVLKH: {
+		std::vector<double> r((size_t)c->Npad * g.REC);
+		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		if (id == IG_STATE_G) {
+			if ((st = need(bytes, (size_t)g.N * 4, "G")) != IG_OK) return st;
+			for (int i = 0; i < g.N; i++) ((int32_t *)host)[i] = (int32_t)r[(size_t)i * g.REC + g.K + 2];
+		} else {
+			if ((st = need(bytes, (size_t)g.N * 8, "INDVLKH")) != IG_OK) return st;
+			for (int i = 0; i < g.N; i++) ((double *)host)[i] = r[(size_t)i * g.REC + g.K];
+		}
+		return IG_OK;
+	}
+	case IG_STATE_P:
+	case IG_STATE_TALLY: {
+		const size_t pn = (size_t)g.Lpad * g.A * g.KP;
+		const size_t el = (size_t)g.K * g.L * g.A;
+		if ((st = need(bytes, el * (id == IG_STATE_P ? 8 : 4), "P/TALLY")) != IG_OK) return st;
+		if (id == IG_STATE_P) {
+			std::vector<float> p(pn);
+			CK(cudaMemcpy(p.data(), c->P, pn * 4, cudaMemcpyDeviceToHost));
+			for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int a = 0; a < g.A; a++)
+				((double *)host)[((size_t)k * g.L + l) * g.A + a] = (double)p[((size_t)l * g.A + a) * g.KP + k];
+		} else {
+			std::vector<int32_t> p(pn);
+			CK(cudaMemcpy(p.data(), c->n, pn * 4, cudaMemcpyDeviceToHost));
+			for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int a = 0; a < g.A; a++)
+				((int32_t *)host)[((size_t)k * g.L + l) * g.A + a] = p[((size_t)l * g.A + a) * g.KP + k];
+		}
+		return IG_OK;
+	}
+	case IG_STATE_ALPHA:
+	case IG_STATE_TOTALLKH: {
+		if ((st = need(bytes, 8, "scalar")) != IG_OK) return st;
+		DevScalars h;
+		CK(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
+		*(double *)host = (id == IG_STATE_ALPHA) ? h.alpha : h.totallkh;
+		return IG_OK;
+	}
+	case IG_STATE_S:
+		if ((st = need(bytes, (size_t)c->ns * 8, "S")) != IG_OK) return st;
+		CK(cudaMemcpy(host, c->S, bytes, cudaMemcpyDeviceToHost));
+		return IG_OK;
+	case IG_STATE_STATE:
+		if ((st = need(bytes, (size_t)g.K * 4, "STATE")) != IG_OK) return st;
+		CK(cudaMemcpy(host, c->state, bytes, cudaMemcpyDeviceToHost));
+		return IG_OK;
+	case IG_STATE_CNT:
+		if ((st = need(bytes, (size_t)g.Nloc * g.K * 4, "CNT")) != IG_OK) return st;
+		CK(cudaMemcpy(host, c->cnt, bytes, cudaMemcpyDeviceToHost));
+		return IG_OK;
+	case IG_STATE_GPROP:
+		if ((st = need(bytes, (size_t)g.N * 4, "GPROP")) != IG_OK) return st;
+		CK(cudaMemcpy(host, c->gprop, bytes, cudaMemcpyDeviceToHost));
+		return IG_OK;
+	case IG_STATE_ITER:
+		if ((st = need(bytes, 8, "ITER")) != IG_OK) return st;
+		*(int64_t *)host = c->iter;
+		return IG_OK;
+	case 100:     /* debug: per-individual (d_old, c_new, a_new, b_new) of the last zq pass, double [Nloc][4] */
+		if ((st = need(bytes, (size_t)g.Nloc * 32, "LLPARTS")) != IG_OK) return st;
+		CK(cudaMemcpy(host, c->llparts, bytes, cudaMemcpyDeviceToHost));
+		return IG_OK;
+	case 101: {   /* debug: launch geometry int32[8] = TL, nchunks, nblk, subs_per_blk, R, smem, KP, A */
+		if ((st = need(bytes, 32, "GEOMETRY")) != IG_OK) return st;
+		int32_t *o = (int32_t *)host;
+		o[0] = g.TL; o[1] = g.nchunks; o[2] = g.nblk; o[3] = g.subs_per_blk; o[4] = g.R; o[5] = (int32_t)g.zq_smem; o[6] = g.KP; o[7] = g.A;
+		return IG_OK;
+	}
+	default:
+		return fail(IG_ERR_ARG, "unknown state id %d", id);
+	}
+}
+
+extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes)
+{
+	if (!c || !host) return fail(IG_ERR_ARG, "null argument");
+	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
+	CK(cudaSetDevice(c->cfg.device));
+	const Geometry &g = c->geo;
+	ig_status st;
+	CK(cudaStreamSynchronize(c->stream));
+	switch (id) {
+	case IG_STATE_Z: {
+		const size_t want = (size_t)g.L * g.Nloc * 2;
+		if ((st = need(bytes, want, "Z")) != IG_OK) return st;
+		void *tmp = nullptr;
+		CK(cudaMalloc(&tmp, want));
+		cudaError_t e = cudaMemcpyAsync(tmp, host, want, cudaMemcpyHostToDevice, c->stream);
+		if (e == cudaSuccess) e = launch_tile_z((const int8_t *)tmp, c->Zt, g, c->stream);
+		if (e == cudaSuccess) e = launch_tally(c->Xt, c->Zt, c->n, g, c->stream);    // n always mirrors Z
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		cudaFree(tmp);
+		CK(e);
+		return IG_OK;
+	}
+	case IG_STATE_Q: {
+		if ((st = need(bytes, (size_t)g.N * g.K * 8, "Q")) != IG_OK) return st;
+		std::vector<double> r((size_t)c->Npad * g.REC);
+		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		const double *q = (const double *)host;
+		for (int i = 0; i < g.N; i++) {
+			double slq = 0;
+			for (int k = 0; k < g.K; k++) { r[(size_t)i * g.REC + k] = q[(size_t)i * g.K + k]; slq += log(q[(size_t)i * g.K + k]); }
+			r[(size_t)i * g.REC + g.K + 1] = slq;
+		}
+		CK(cudaMemcpy(c->ind, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+		CK(launch_qf_from_ind(c->ind, c->Qf, g, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		return IG_OK;
+	}
+	case IG_STATE_G:
+	case IG_STATE_INDVLKH: {
+		std::vector<double> r((size_t)c->Npad * g.REC);
+		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		if (id == IG_STATE_G) {
+			if ((st = need(bytes, (size_t)g.N * 4, "G")) != IG_OK) return st;
+			for (int i = 0; i < g.N; i++) r[(size_t)i * g.REC + g.K + 2] = (double)((const int32_t *)host)[i];
+		} else {
+			if ((st = need(bytes, (size_t)g.N * 8, "INDVLKH")) != IG_OK) return st;
+			for (int i = 0; i < g.N; i++) r[(size_t)i * g.REC + g.K] = ((const double *)host)[i];
+		}
+		CK(cudaMemcpy(c->ind, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+		return IG_OK;
+	}
+	case IG_STATE_P: {
+		const size_t pn = (size_t)g.Lpad * g.A * g.KP;
+		if ((st = need(bytes, (size_t)g.K * g.L * g.A * 8, "P")) != IG_OK) return st;
+		std::vector<float> p(pn, 0.0f);
+		for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int a = 0; a < g.A; a++)
+			p[((size_t)l * g.A + a) * g.KP + k] = (float)((const double *)host)[((size_t)k * g.L + l) * g.A + a];
+		CK(cudaMemcpy(c->P, p.data(), pn * 4, cudaMemcpyHostToDevice));
+		return IG_OK;
+	}
+	case IG_STATE_ALPHA: {
+		if ((st = need(bytes, 8, "ALPHA")) != IG_OK) return st;
+		CK(cudaMemcpy(&c->sc->alpha, host, 8, cudaMemcpyHostToDevice));
+		return IG_OK;
+	}
+	case IG_STATE_S:
+		if ((st = need(bytes, (size_t)c->ns * 8, "S")) != IG_OK) return st;
+		CK(cudaMemcpy(c->S, host, bytes, cudaMemcpyHostToDevice));
+		return IG_OK;
+	case IG_STATE_STATE:
+		if ((st = need(bytes, (size_t)g.K * 4, "STATE")) != IG_OK) return st;
+		CK(cudaMemcpy(c->state, host, bytes, cudaMemcpyHostToDevice));
+		return IG_OK;
+	case IG_STATE_GPROP: {      /* also refreshes the (g, g') pairs the sweep kernel reads */
+		if ((st = need(bytes, (size_t)g.N * 4, "GPROP")) != IG_OK) return st;
+		CK(cudaMemcpy(c->gprop, host, bytes, cudaMemcpyHostToDevice));
+		std::vector<double> r((size_t)c->Npad * g.REC);
+		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		std::vector<int2> gp(g.Nloc);
+		for (int il = 0; il < g.Nloc; il++) gp[il] = make_int2((int)r[(size_t)(g.i0 + il) * g.REC + g.K + 2], ((const int32_t *)host)[g.i0 + il]);
+		CK(cudaMemcpy(c->gpair, gp.data(), gp.size() * sizeof(int2), cudaMemcpyHostToDevice));
+		return IG_OK;
+	}
+	case IG_STATE_ITER:
+		if ((st = need(bytes, 8, "ITER")) != IG_OK) return st;
+		c->iter = (uint32_t) * (const int64_t *)host;
+		c->chain_ready = true;
+		return IG_OK;
+	default:
+		return fail(IG_ERR_ARG, "state id %d cannot be set", id);
+	}
+}
+
+extern "C" ig_status ig_loglik(ig_ctx *c, const int32_t *gen, double *out)
+{
+	if (!c || !gen || !out) return fail(IG_ERR_ARG, "null argument");
+	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
+	CK(cudaSetDevice(c->cfg.device));
+	const Geometry &g = c->geo;
+	int32_t *gd = nullptr;
+	double *od = nullptr;
+	CK(cudaMalloc((void **)&gd, (size_t)g.Nloc * 4));
+	CK(cudaMalloc((void **)&od, (size_t)g.Nloc * 8));
+	cudaError_t e = cudaMemcpyAsync(gd, gen, (size_t)g.Nloc * 4, cudaMemcpyHostToDevice, c->stream);
+	if (e == cudaSuccess) e = launch_loglik(c->Xt, c->Zt, c->P, c->Qf, gd, od, g, c->cfg.type_freq, c->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out, od, (size_t)g.Nloc * 8, cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(gd);
+	cudaFree(od);
+	CK(e);
+	return IG_OK;
+}
+
+extern "C" ig_status ig_proposal_loglik(ig_ctx *c, const double *S, double *out)
+{
+	if (!c || !S || !out) return fail(IG_ERR_ARG, "null argument");
+	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
+	if (c->cfg.mode != 2) return fail(IG_ERR_ARG, "proposal() is the mode-2 likelihood (mcmc.c:1630)");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaMemcpyAsync(c->scratch, S, (size_t)c->geo.K * 8, cudaMemcpyHostToDevice, c->stream));
+	CK(launch_proposal_ll(c->ind, c->scratch, c->scratch + 32, c->geo, c->stream));
+	CK(cudaMemcpyAsync(out, c->scratch + 32, 8, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return IG_OK;
+}
+
+extern "C" ig_status ig_alpha_logratio(ig_ctx *c, double ralpha, double *out)
+{
+	if (!c || !out) return fail(IG_ERR_ARG, "null argument");
+	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
+	CK(cudaSetDevice(c->cfg.device));
+	// sum log q is maintained per individual in the record; reduce it with the same kernel the
+	// sweep uses, on a scratch copy of the scalars so that alpha itself is not advanced
+	DevScalars keep;
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpy(&keep, c->sc, sizeof(keep), cudaMemcpyDeviceToHost));
+	PostArgs a{c->ind, c->sc, c->geo, 0xFFFFFFFFu, c->key0, c->key1};
+	CK(launch_post_sweep(a, c->stream));
+	DevScalars h;
+	CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	*out = (ralpha - keep.alpha) * h.sumlogq;
+	CK(cudaMemcpy(c->sc, &keep, sizeof(keep), cudaMemcpyHostToDevice));
+	return IG_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// profiling
+// --------------------------------------------------------------------------------------
+extern "C" ig_status ig_profile(ig_ctx *c, int32_t enable)
+{
+	if (!c) return fail(IG_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->cfg.device));
+	c->profile = enable != 0;
+	c->ev_used = 0;
+	if (enable && c->ev.empty()) {
+		c->ev.resize(2 * 4096);
+		for (auto &e : c->ev) CK(cudaEventCreate(&e));
+	}
+	return IG_OK;
+}
+
+extern "C" ig_status ig_profile_read(ig_ctx *c, int32_t *launches, double *zq_ms_total, int64_t *kernels_launched)
+{
+	if (!c) return fail(IG_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaStreamSynchronize(c->stream));
+	double tot = 0.0;
+	for (int i = 0; i + 1 < c->ev_used; i += 2) {
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+		tot += ms;
+	}
+	if (launches) *launches = c->ev_used / 2;
+	if (zq_ms_total) *zq_ms_total = tot;
+	if (kernels_launched) *kernels_launched = c->launches;
+	c->ev_used = 0;
+	return IG_OK;
+}
+
+extern "C" ig_status ig_algorithmic_bytes(ig_ctx *c, double *bytes_per_sweep, double *copies_per_sweep)
+{
+	if (!c) return fail(IG_ERR_ARG, "null context");
+	const Geometry &g = c->geo;
+	// N*L*ploid*4 B (int16 x + int8 old z + int8 new z per allele copy)
+	//             + K*L*A*12 B (count write + count read + P write) + N*(16K+16) B (Q r/w, G, lkh)
+	double abar = 0.0;
+	for (int l = 0; l < g.L; l++) abar += c->allelenum_h.empty() ? g.A : c->allelenum_h[l];
+	const double b = (double)g.Nloc * g.L * 2 * 4.0 + (double)g.K * abar * 12.0 + (double)g.Nloc * (16.0 * g.K + 16.0);
+	if (bytes_per_sweep) *bytes_per_sweep = b;
+	if (copies_per_sweep) *copies_per_sweep = (double)g.Nloc * g.L * 2;
+	return IG_OK;
+}

@@ -1,0 +1,125 @@
+// ig_internal.h -- context layout and kernel launch interfaces shared by ig_api.cu and the
+// kernel translation units.  Not part of the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/instruct_b200.h"
+
+namespace ig {
+
+constexpr int TILE = 8;          // loci per micro-tile (one 128-bit Z vector, two 128-bit X vectors)
+constexpr int ZQ_THREADS = 256;  // individuals per CTA pass
+constexpr int MAX_K = 16;
+constexpr float P_FLOOR = 1e-18f;   // keeps f0*f1 a normal fp32 number in the product accumulators
+
+// device-resident scalars of one chain
+struct DevScalars {
+	double alpha;
+	double totallkh;
+	double sumlogq;          // sum_i sum_k log q_ik  (sufficient statistic of update_alpha)
+	double cur_prop_ll;      // proposal() at the current S, kept between update_S_POP steps
+	double qcol[MAX_K];      // column sums of Q (check_empty_cluster)
+	int32_t alpha_accepts;
+	int32_t s_accepts;
+	int32_t flags;
+	int32_t pad;
+};
+
+// running moments (store_chn, mcmc.c:1320) on the device
+struct Moments {
+	double *tot;       // [2] totallkh, totallkh2
+	double *indvlkh;   // [N]
+	double *qq, *qq2;  // [N][K]
+	double *self, *self2;
+	double *gen, *gen2;
+	double *freq, *freq2;   // [K][L][A] (print_freq)
+	double *convg;     // [ckrep]
+};
+
+struct Geometry {
+	int N, Nloc, i0;         // global individuals, local shard size and first global index
+	int L, Lpad, LT;         // loci, padded to TILE, micro-tiles
+	int K, KP, A;            // populations, padded populations, allelenum_max
+	int REC;                 // doubles per individual record: Q[K], lkh, slq, G
+	int TL;                  // loci per chunk (multiple of TILE)
+	int nchunks;             // ceil(Lpad / TL)
+	int nblk;                // individual blocks (grid.y)
+	int subs_per_blk;        // 256-individual passes per CTA
+	int R;                   // smem histogram replicas
+	size_t zq_smem;          // dynamic shared memory bytes of zq_sweep
+};
+
+struct ZQArgs {
+	const int16_t *Xt;       // [LT][Nloc][TILE][2]
+	int8_t *Zt;              // [LT][Nloc][TILE][2]
+	const float *P;          // [Lpad][A][KP]
+	int32_t *n;              // [Lpad][A][KP]
+	const float *Qf;         // [Nloc][KP]
+	const int2 *gpair;       // [Nloc] (g, g')
+	uint16_t *pcnt;          // [nchunks][Nloc][KP]
+	double *plog;            // [nchunks][4][Nloc]
+	Geometry geo;
+	uint32_t iter;
+	uint32_t key0, key1;
+	int type_freq;
+};
+
+// ---- launchers (ig_kernels.cu) -------------------------------------------------------
+cudaError_t launch_zq_sweep(const ZQArgs &a, int rounds, cudaStream_t s);
+cudaError_t zq_configure(Geometry &g, int device);
+
+struct EpiArgs {
+	const uint16_t *pcnt; const double *plog;
+	double *ind;             // [Npad][REC]
+	float *Qf;               // [Nloc][KP]
+	int32_t *cnt;            // [Nloc][K]
+	double *llparts;         // [Nloc][4]
+	const int2 *gpair;
+	const DevScalars *sc;
+	Geometry geo;
+	uint32_t iter, key0, key1;
+	int init;                // 1: initial assignment pass (no G accept, no likelihood)
+};
+cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s);
+
+struct PArgs {
+	int32_t *n; float *P; double *P64; const int32_t *allelenum;
+	Geometry geo; uint32_t iter, key0, key1;
+};
+cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s);
+
+struct PreArgs {
+	double *ind; double *S; int32_t *state; int32_t *gprop; int2 *gpair; DevScalars *sc;
+	Geometry geo; uint32_t iter, key0, key1; int mode, prior_flag, back_refl;
+};
+cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s);
+
+struct PostArgs {
+	const double *ind; DevScalars *sc; Geometry geo; uint32_t iter, key0, key1;
+};
+cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
+
+struct MomArgs {
+	const double *ind; const double *S; const DevScalars *sc; const float *P; Moments m;
+	Geometry geo; int ns; long step; int convg_slot; int print_freq;
+};
+cudaError_t launch_moments(const MomArgs &a, cudaStream_t s);
+cudaError_t launch_moments_reset(const MomArgs &a, cudaStream_t s);
+
+// layout transforms and stand-alone evaluators (tests, state injection)
+cudaError_t launch_tile_x(const int16_t *x_canon, int16_t *Xt, const int32_t *allelenum, Geometry g, cudaStream_t s);
+cudaError_t launch_untile_x(const int16_t *Xt, int16_t *x_canon, Geometry g, cudaStream_t s);
+cudaError_t launch_tile_z(const int8_t *z_canon, int8_t *Zt, Geometry g, cudaStream_t s);
+cudaError_t launch_untile_z(const int8_t *Zt, int8_t *z_canon, Geometry g, cudaStream_t s);
+cudaError_t launch_tally(const int16_t *Xt, const int8_t *Zt, int32_t *n, Geometry g, cudaStream_t s);
+cudaError_t launch_loglik(const int16_t *Xt, const int8_t *Zt, const float *P, const float *Qf, const int32_t *gen,
+                          double *out, Geometry g, int type_freq, cudaStream_t s);
+cudaError_t launch_fill_f32(float *p, float v, size_t n, cudaStream_t s);
+cudaError_t launch_init_chain(double *ind, double *S, int32_t *state, DevScalars *sc, const float *initd_dev,
+                              int32_t *gprop, int2 *gpair, Geometry g, int mode, int prior_flag, int back_refl,
+                              uint32_t key0, uint32_t key1, cudaStream_t s);
+cudaError_t launch_proposal_ll(const double *ind, const double *S, double *out, Geometry g, cudaStream_t s);
+cudaError_t launch_qf_from_ind(const double *ind, float *Qf, Geometry g, cudaStream_t s);
+
+}  // namespace ig

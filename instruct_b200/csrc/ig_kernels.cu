@@ -1,0 +1,1010 @@
+// ig_kernels.cu -- sm_100a kernels of the diploid InStruct sweep (modes 2 and 3).
+//
+// One sweep of the reference (mcmc.c:208-215 / :334-348) is
+//     update_P -> update_S_* -> update_G -> update_ZQ -> update_alpha -> cal_lkh
+// with three O(N*L) passes over the data (log_ld_indv twice in update_G, once in cal_lkh)
+// plus the O(N*L*A*K) tally at the top of update_P.  Here it is
+//     p_dirichlet   (L*K threads)       P | n            mcmc.c:846-857
+//     pre_sweep     (1 CTA)             S | G,Q  and the G proposals   mcmc.c:913-983,864-886,1062-1084
+//     zq_sweep      (the one big pass)  Z | P,Q ; per-individual K-counts ; n[l][a][k] for the
+//                                       NEXT update_P ; the four log-likelihood pieces that the
+//                                       G accept and cal_lkh need           mcmc.c:1122-1194,1726-1773,810-845
+//     indiv_epilogue(N threads)         G accept, Q | Z,alpha, indvlkh     mcmc.c:1085-1089,1196-1198,1931
+//     post_sweep    (1 CTA)             alpha | Q, totallkh, column sums   mcmc.c:1244-1263,1940,1954-1961
+//     moments       (N*K threads)       store_chn                         mcmc.c:1320-1456
+//
+// update_G reads the OLD Z and update_ZQ never reads G, so both can ride one pass over the
+// genotype store: the pass reads x (int16) and old z (int8), writes new z (int8) -- the
+// 4 bytes per allele copy of SURVEY.md section 8d.
+#include <math.h>
+#include <stdio.h>
+#include "ig_internal.h"
+#include "philox.cuh"
+#include "samplers.cuh"
+
+namespace ig {
+
+#define LN2_D 0.69314718055994530942
+
+// --------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP), cache-hinted
+// 128-bit global accesses.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "WAIT_LOOP:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@p bra DONE;\n\t"
+	    "bra WAIT_LOOP;\n\t"
+	    "DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	                 smem_addr(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+	             : "memory");
+}
+__device__ __forceinline__ int4 ldg_stream(const int4 *p)   // read-once data: bypass L1 allocation
+{
+	int4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ int4 ldg_rw(const int4 *p)       // data this kernel also writes: no .nc
+{
+	int4 r;
+	asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void stg_stream(int4 *p, const int4 &v)
+{
+	asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// --------------------------------------------------------------------------------------
+// Product accumulator: a log-likelihood is a sum of logs of per-locus probabilities; the
+// kernel keeps the PRODUCT instead, as an fp32 mantissa in [1,2^64) and an integer
+// exponent, and takes one logarithm per (individual, chunk).  Relative error of an n-term
+// product is <= n * 2^-24, i.e. an ABSOLUTE error <= 6e-8 * n on a log-likelihood of
+// magnitude ~n: relative ~1e-7, inside the 1e-6 gate of BASELINE.json.
+// --------------------------------------------------------------------------------------
+struct LogProd {
+	float m;
+	int e;
+	__device__ __forceinline__ void init() { m = 1.0f; e = 0; }
+	__device__ __forceinline__ void mul(float t)
+	{
+		int b = __float_as_int(t);
+		e += (b >> 23) - 127;
+		m *= __int_as_float((b & 0x007fffff) | 0x3f800000);
+	}
+	__device__ __forceinline__ void renorm()
+	{
+		int b = __float_as_int(m);
+		e += (b >> 23) - 127;
+		m = __int_as_float((b & 0x007fffff) | 0x3f800000);
+	}
+	__device__ __forceinline__ double value()
+	{
+		renorm();
+		return log((double)m) + (double)e * LN2_D;
+	}
+};
+
+// --------------------------------------------------------------------------------------
+// Per-individual ancestry counter (qqnum, mcmc.c:1176-1194): K counters that are bumped by
+// a data-dependent index twice per locus.  Registers cannot be indexed dynamically, so the
+// counters are nibble fields of one word (shift by 4z), spilled to byte fields every four
+// loci and to 16-bit fields every 15 micro-tiles.
+// --------------------------------------------------------------------------------------
+template <int KP>
+struct Counter {
+	static constexpr int NW = (KP + 7) / 8;     // nibble words
+	uint32_t n4[NW], blo[NW], bhi[NW];
+	uint32_t c16[KP / 2];                       // (pop 2j) | (pop 2j+1) << 16
+	__device__ __forceinline__ void init()
+	{
+#pragma unroll
+		for (int w = 0; w < NW; w++) { n4[w] = 0; blo[w] = 0; bhi[w] = 0; }
+#pragma unroll
+		for (int j = 0; j < KP / 2; j++) c16[j] = 0;
+	}
+	__device__ __forceinline__ void add(int z)
+	{
+		if (NW == 1) n4[0] += 1u << (4 * z);
+		else {
+#pragma unroll
+			for (int w = 0; w < NW; w++) n4[w] += ((z >> 3) == w) ? (1u << (4 * (z & 7))) : 0u;
+		}
+	}
+	__device__ __forceinline__ void flush_nibbles()      // after at most 4 loci (8 increments)
+	{
+#pragma unroll
+		for (int w = 0; w < NW; w++) {
+			blo[w] += n4[w] & 0x0F0F0F0Fu;
+			bhi[w] += (n4[w] >> 4) & 0x0F0F0F0Fu;
+			n4[w] = 0;
+		}
+	}
+	__device__ __forceinline__ void flush_bytes()        // after at most 30 nibble flushes
+	{
+#pragma unroll
+		for (int w = 0; w < NW; w++) {
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				int idx = w * 4 + j;
+				if (idx < KP / 2) c16[idx] += ((blo[w] >> (8 * j)) & 0xFFu) | (((bhi[w] >> (8 * j)) & 0xFFu) << 16);
+			}
+			blo[w] = 0; bhi[w] = 0;
+		}
+	}
+};
+
+// --------------------------------------------------------------------------------------
+// zq_sweep: grid (locus chunks, individual blocks), 256 threads, one thread = one
+// individual, marching over the chunk's micro-tiles of 8 loci.
+//   global  : X  int16 [LT][Nloc][8][2]  two 128-bit loads per thread per micro-tile
+//             Z  int8  [LT][Nloc][8][2]  one 128-bit load + one 128-bit store
+//   shared  : P chunk [TL][A][KP] fp32, landed by ONE TMA bulk copy on an mbarrier;
+//             n chunk [TL][A][KP][R] int32 histogram, R lane-replicas to thin out conflicts,
+//             reduced and pushed to global n with RED at the end of the CTA
+//   output  : per (chunk, individual) partials: K counts (u16) + 4 log-likelihood pieces
+// --------------------------------------------------------------------------------------
+template <int KP, int ROUNDS, bool TF0>
+__global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bar;
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x;
+	const int chunk = blockIdx.x;
+	const int l0 = chunk * g.TL;
+	const int nl = min(g.TL, g.Lpad - l0);
+	const int nmt = nl / TILE;
+	const int A = g.A;
+	const int rowsz = A * KP;                       // floats per locus
+	float *Psm = reinterpret_cast<float *>(smem_raw);
+	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);
+	const int nbins = nl * rowsz;
+	const int R = g.R;
+	const int rlane = tid & (R - 1);
+
+	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+	__syncthreads();
+	if (tid == 0) {
+		mbar_expect_tx(&bar, (uint32_t)nbins * 4u);
+		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
+	}
+	for (int j = tid; j < nbins * R; j += ZQ_THREADS) hist[j] = 0;
+	__syncthreads();
+	mbar_wait(&bar, 0);
+
+	const int Nloc = g.Nloc;
+	const int mt0 = l0 / TILE;
+	const int sub0 = blockIdx.y * g.subs_per_blk;
+	const int nsub_total = (Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
+	const int sub1 = min(sub0 + g.subs_per_blk, nsub_total);
+
+	for (int sub = sub0; sub < sub1; ++sub) {
+		const int il = sub * ZQ_THREADS + tid;
+		if (il < Nloc) {
+			float q[KP];
+			{
+				const float4 *qp = reinterpret_cast<const float4 *>(a.Qf + (size_t)il * KP);
+#pragma unroll
+				for (int v = 0; v < KP / 4; v++) {
+					float4 t = __ldg(qp + v);
+					q[4 * v] = t.x; q[4 * v + 1] = t.y; q[4 * v + 2] = t.z; q[4 * v + 3] = t.w;
+				}
+			}
+			const int2 gg = __ldg(a.gpair + il);
+			// 1 - h(g) = 2^-(g-1); exact in fp32 down to 2^-126, 0 beyond (g can start huge in mode 3)
+			const float omh_g = (gg.x <= 127) ? __int_as_float((128 - gg.x) << 23) : 0.0f;
+			const float omh_p = (gg.y <= 127) ? __int_as_float((128 - gg.y) << 23) : 0.0f;
+			const float h_g = 1.0f - omh_g, h_p = 1.0f - omh_p;
+
+			LogProd Cn, An, Bn, Ao, Bo;
+			Cn.init(); An.init(); Bn.init(); Ao.init(); Bo.init();
+			int nhet = 0, nsh_new = 0, nsh_old = 0;
+			Counter<KP> cnt;
+			cnt.init();
+
+			const int4 *xp = reinterpret_cast<const int4 *>(a.Xt) + ((size_t)mt0 * Nloc + il) * 2;
+			int4 *zp = reinterpret_cast<int4 *>(a.Zt) + ((size_t)mt0 * Nloc + il);
+			const size_t xstride = (size_t)Nloc * 2, zstride = (size_t)Nloc;
+			const uint32_t ig_global = (uint32_t)(g.i0 + il);
+
+			int4 xa_n = ldg_stream(xp), xb_n = ldg_stream(xp + 1), zz_n = ldg_rw(zp);
+			for (int mt = 0; mt < nmt; ++mt) {
+				const int4 xa = xa_n, xb = xb_n, zz = zz_n;
+				if (mt + 1 < nmt) {
+					xa_n = ldg_stream(xp + (size_t)(mt + 1) * xstride);
+					xb_n = ldg_stream(xp + (size_t)(mt + 1) * xstride + 1);
+					zz_n = ldg_rw(zp + (size_t)(mt + 1) * zstride);
+				}
+				const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+				const int zwo[4] = {zz.x, zz.y, zz.z, zz.w};
+				int zwn[4];
+#pragma unroll
+				for (int pr = 0; pr < 4; ++pr) {
+					const u32x4 rnd = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
+					const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+					int znew_word = zwo[pr];
+#pragma unroll
+					for (int h2 = 0; h2 < 2; ++h2) {
+						const int j = 2 * pr + h2;
+						const int x0 = (xw[j] << 16) >> 16, x1 = xw[j] >> 16;
+						if ((x0 | x1) >= 0) {
+							const int lj = mt * TILE + j;
+							const int row0 = (lj * A + x0) * KP, row1 = (lj * A + x1) * KP;
+							const bool het = (x0 != x1);
+							const int zo0 = (zwo[pr] >> (16 * h2)) & 0xFF, zo1 = (zwo[pr] >> (16 * h2 + 8)) & 0xFF;
+							// ---- cumulative weights w_k = sum_{m<=k} Q_im P_m,l,x (mcmc.c:1141-1149)
+							float p0[KP], p1[KP], c0[KP], c1[KP];
+#pragma unroll
+							for (int v = 0; v < KP / 4; v++) {
+								const float4 t0 = *reinterpret_cast<const float4 *>(Psm + row0 + 4 * v);
+								const float4 t1 = *reinterpret_cast<const float4 *>(Psm + row1 + 4 * v);
+								p0[4 * v] = t0.x; p0[4 * v + 1] = t0.y; p0[4 * v + 2] = t0.z; p0[4 * v + 3] = t0.w;
+								p1[4 * v] = t1.x; p1[4 * v + 1] = t1.y; p1[4 * v + 2] = t1.z; p1[4 * v + 3] = t1.w;
+							}
+							c0[0] = q[0] * p0[0];
+							c1[0] = q[0] * p1[0];
+#pragma unroll
+							for (int k = 1; k < KP; k++) { c0[k] = fmaf(q[k], p0[k], c0[k - 1]); c1[k] = fmaf(q[k], p1[k], c1[k - 1]); }
+							// ---- old-Z pieces of update_G's ratio (log_ld_indv, mcmc.c:1752-1759)
+							if (!TF0) {
+								const bool same_o = (zo0 == zo1);
+								const float fo = Psm[row0 + zo0];
+								const bool sh_o = same_o && !het;
+								Ao.mul(sh_o ? fmaf(fo, omh_g, h_g) : 1.0f);
+								Bo.mul(sh_o ? fmaf(fo, omh_p, h_p) : 1.0f);
+								nsh_old += (same_o && het) ? 1 : 0;
+							}
+							// ---- categorical draws (disc_unif, random.c:403-430)
+							const float t0 = u01f(rr[2 * h2]) * c0[KP - 1];
+							const float t1 = u01f(rr[2 * h2 + 1]) * c1[KP - 1];
+							int z0 = 0, z1 = 0;
+#pragma unroll
+							for (int k = 0; k < KP - 1; k++) { z0 += (t0 >= c0[k]) ? 1 : 0; z1 += (t1 >= c1[k]) ? 1 : 0; }
+							z0 = min(z0, g.K - 1);
+							z1 = min(z1, g.K - 1);
+							// ---- n[l][a][k] tally for the next update_P (mcmc.c:815-845)
+							atomicAdd(&hist[(row0 + z0) * R + rlane], 1);
+							atomicAdd(&hist[(row1 + z1) * R + rlane], 1);
+							cnt.add(z0);
+							cnt.add(z1);
+							// ---- new-Z likelihood pieces (cal_lkh and the accepted-G selection)
+							float f0, f1;
+							bool same_n;
+							if (TF0) { f0 = c0[KP - 1]; f1 = c1[KP - 1]; same_n = true; }   // mcmc.c:1739-1749
+							else { f0 = Psm[row0 + z0]; f1 = Psm[row1 + z1]; same_n = (z0 == z1); }
+							const bool sh_n = same_n && !het;
+							Cn.mul(f0 * (sh_n ? 1.0f : f1));
+							An.mul(sh_n ? fmaf(f0, omh_g, h_g) : 1.0f);
+							Bn.mul(sh_n ? fmaf(f0, omh_p, h_p) : 1.0f);
+							nhet += het ? 1 : 0;
+							nsh_new += (same_n && het) ? 1 : 0;
+							znew_word = (znew_word & ~(0xFFFF << (16 * h2))) | ((z0 | (z1 << 8)) << (16 * h2));
+						}
+					}
+					zwn[pr] = znew_word;
+					if (pr == 1 || pr == 3) cnt.flush_nibbles();
+				}
+				stg_stream(zp + (size_t)mt * zstride, make_int4(zwn[0], zwn[1], zwn[2], zwn[3]));
+				if ((mt & 7) == 7) { Cn.renorm(); An.renorm(); Bn.renorm(); Ao.renorm(); Bo.renorm(); }
+				if ((mt % 15) == 14) cnt.flush_bytes();
+			}
+			cnt.flush_bytes();
+			// ---- partials of this (chunk, individual)
+			{
+				uint32_t *pc = reinterpret_cast<uint32_t *>(a.pcnt + ((size_t)chunk * Nloc + il) * KP);
+#pragma unroll
+				for (int j = 0; j < KP / 2; j++) pc[j] = cnt.c16[j];
+				double *pl = a.plog + (size_t)chunk * 4 * Nloc + il;
+				const double la = An.value(), lb = Bn.value();
+				double d_old;
+				if (TF0) d_old = (lb - la) - (double)nsh_new * (double)(gg.y - gg.x) * LN2_D;
+				else d_old = (Bo.value() - Ao.value()) - (double)nsh_old * (double)(gg.y - gg.x) * LN2_D;
+				pl[0] = d_old;
+				pl[(size_t)Nloc] = Cn.value() + (double)nhet * LN2_D;
+				pl[(size_t)2 * Nloc] = la - (double)nsh_new * (double)(gg.x - 1) * LN2_D;
+				pl[(size_t)3 * Nloc] = lb - (double)nsh_new * (double)(gg.y - 1) * LN2_D;
+			}
+		}
+	}
+	__syncthreads();
+	// ---- reduce the replicas and push this CTA's tally into global n (RED, no return value)
+	int32_t *ng = a.n + (size_t)l0 * rowsz;
+	for (int b = tid; b < nbins; b += ZQ_THREADS) {
+		int s = 0;
+		for (int r = 0; r < R; r++) s += hist[b * R + r];
+		if (s) atomicAdd(ng + b, s);
+	}
+}
+
+template <int KP>
+static cudaError_t launch_zq_kp(const ZQArgs &a, int rounds, cudaStream_t s)
+{
+	dim3 grid(a.geo.nchunks, a.geo.nblk), block(ZQ_THREADS);
+	const size_t sm = a.geo.zq_smem;
+#define IG_LAUNCH(RND, TF)                                                                                   \
+	do {                                                                                                 \
+		cudaError_t e = cudaFuncSetAttribute(zq_sweep_kernel<KP, RND, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+		if (e != cudaSuccess) return e;                                                                  \
+		zq_sweep_kernel<KP, RND, TF><<<grid, block, sm, s>>>(a);                                          \
+	} while (0)
+	if (a.type_freq == 0) { if (rounds == 7) IG_LAUNCH(7, true); else IG_LAUNCH(10, true); }
+	else { if (rounds == 7) IG_LAUNCH(7, false); else IG_LAUNCH(10, false); }
+#undef IG_LAUNCH
+	return cudaGetLastError();
+}
+
+cudaError_t launch_zq_sweep(const ZQArgs &a, int rounds, cudaStream_t s)
+{
+	switch (a.geo.KP) {
+	case 4: return launch_zq_kp<4>(a, rounds, s);
+	case 8: return launch_zq_kp<8>(a, rounds, s);
+	case 16: return launch_zq_kp<16>(a, rounds, s);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+// Choose the decomposition: chunks of TL loci x blocks of individuals.  The tally of a chunk
+// is complete inside one CTA when nblk == 1 (no contention on global n); per-individual
+// pieces are always combined by indiv_epilogue in chunk order (deterministic).
+cudaError_t zq_configure(Geometry &g, int device)
+{
+	int sms = 148, smem_optin = 227 * 1024;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+	const int target_ctas = 4 * sms;                       // two resident CTAs per SM, two waves
+	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / 2 - 2048;   // two CTAs per SM
+	const size_t per_locus = (size_t)g.A * g.KP * 4;
+	const int nsub_total = (g.Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
+	int R = 8;
+	while (R > 1 && per_locus * (1 + R) * TILE > budget) R >>= 1;
+	if (per_locus * (1 + R) * TILE > (size_t)smem_optin - 2048) return cudaErrorInvalidConfiguration;
+	int tl_max = (int)(budget / (per_locus * (1 + R)));
+	if (tl_max < TILE) tl_max = (int)(((size_t)smem_optin - 2048) / (per_locus * (1 + R)));
+	tl_max = (tl_max / TILE) * TILE;
+	if (tl_max < TILE) return cudaErrorInvalidConfiguration;
+	if (tl_max > 1024) tl_max = 1024;
+	int tl = ((g.Lpad + target_ctas - 1) / target_ctas + TILE - 1) / TILE * TILE;
+	if (tl < TILE) tl = TILE;
+	if (tl > tl_max) tl = tl_max;
+	g.TL = tl;
+	g.nchunks = (g.Lpad + tl - 1) / tl;
+	int nblk = 1;
+	if (g.nchunks < target_ctas) nblk = min(nsub_total, (target_ctas + g.nchunks - 1) / g.nchunks);
+	if (nblk < 1) nblk = 1;
+	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
+	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
+	g.R = R;
+	g.zq_smem = (size_t)tl * per_locus * (1 + R);
+	return cudaSuccess;
+}
+
+// --------------------------------------------------------------------------------------
+// p_dirichlet: P[k][l][.] ~ Dirichlet(n[k][l][.] + 1)  (update_P, mcmc.c:846-857, lambda = 1).
+// One thread per (locus, population); writes fp32 P[l][a][k] and clears n for the next sweep.
+// --------------------------------------------------------------------------------------
+__global__ void p_dirichlet_kernel(const PArgs a)
+{
+	const Geometry &g = a.geo;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= g.Lpad * g.KP) return;
+	const int l = t / g.KP, k = t % g.KP;
+	const size_t base = (size_t)l * g.A * g.KP + k;
+	const int Al = (l < g.L) ? a.allelenum[l] : 0;
+	if (k >= g.K || Al <= 1) {
+		for (int al = 0; al < g.A; al++) { a.P[base + (size_t)al * g.KP] = 0.0f; a.n[base + (size_t)al * g.KP] = 0; }
+		return;
+	}
+	Stream st((uint32_t)l, (uint32_t)k, a.iter, TAG_P, a.key0, a.key1);
+	double sum = 0.0;
+	double gam[64];
+	// allelenum_max is small (2 for SNPs, tens for microsatellites); larger loci spill to a second pass
+	if (Al <= 64) {
+		for (int al = 0; al < Al; al++) { gam[al] = draw_gamma(st, (double)a.n[base + (size_t)al * g.KP] + 1.0); sum += gam[al]; }
+		for (int al = 0; al < g.A; al++) {
+			const double p = (al < Al) ? gam[al] / sum : 0.0;
+			a.P[base + (size_t)al * g.KP] = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;
+			if (a.P64) a.P64[((size_t)k * g.L + l) * g.A + al] = p;
+			a.n[base + (size_t)al * g.KP] = 0;
+		}
+	} else {
+		for (int al = 0; al < Al; al++) sum += draw_gamma(st, (double)a.n[base + (size_t)al * g.KP] + 1.0);
+		Stream st2((uint32_t)l, (uint32_t)k, a.iter, TAG_P, a.key0, a.key1);     // replay the same stream
+		for (int al = 0; al < g.A; al++) {
+			const double p = (al < Al) ? draw_gamma(st2, (double)a.n[base + (size_t)al * g.KP] + 1.0) / sum : 0.0;
+			a.P[base + (size_t)al * g.KP] = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;
+			if (a.P64) a.P64[((size_t)k * g.L + l) * g.A + al] = p;
+			a.n[base + (size_t)al * g.KP] = 0;
+		}
+	}
+}
+cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s)
+{
+	const int total = a.geo.Lpad * a.geo.KP;
+	p_dirichlet_kernel<<<(total + 127) / 128, 128, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// Deterministic block reduction (fixed blockDim => fixed summation tree => identical on
+// every rank and for every GPU count).
+// --------------------------------------------------------------------------------------
+constexpr int RED_THREADS = 1024;
+__device__ double block_sum(double v, double *sh)
+{
+	const int tid = threadIdx.x;
+	__syncthreads();
+	sh[tid] = v;
+	__syncthreads();
+	for (int s = RED_THREADS / 2; s > 0; s >>= 1) {
+		if (tid < s) sh[tid] += sh[tid + s];
+		__syncthreads();
+	}
+	const double r = sh[0];
+	__syncthreads();
+	return r;
+}
+
+// dt_stat, mcmc.c:1524-1546 (selfing rates are always inside [0,1] here)
+__device__ __forceinline__ int sel_state(double v)
+{
+	const double eps = 0.001;
+	if (v <= eps) return 0;
+	if (v >= 1.0 - eps) return 2;
+	return 1;
+}
+// log( s^(g-1) (1-s) ): the summand of proposal() (mcmc.c:1645) and log dgeom (mcmc.c:1602)
+__device__ __forceinline__ double log_geom(double s, int gen)
+{
+	const double l1 = log(1.0 - s);
+	return (gen > 1) ? (double)(gen - 1) * log(s) + l1 : l1;
+}
+// q(), mcmc.c:1566-1593
+__device__ __forceinline__ double trans_prob(int from, int to)
+{
+	if (from == 0) return (to == 0 || to == 1) ? 0.5 : 0.0;
+	if (from == 2) return (to == 2 || to == 1) ? 0.5 : 0.0;
+	return (to == 1) ? 0.90 : 0.05;
+}
+
+// --------------------------------------------------------------------------------------
+// pre_sweep (one CTA): selfing-rate update, then the generation proposals of update_G.
+//   mode 2: update_S_POP (mcmc.c:913-983): K sequential MH steps, each a block reduction of
+//           sum_i log( s_i^(G_i-1) (1-s_i) ), s_i = sum_k Q_ik S_k  (proposal, mcmc.c:1630)
+//   mode 3, uniform prior: update_S_IND (mcmc.c:864-886), independent per individual
+//   mode 3, DP prior: S was written by the host step (ig_api.cu) before this launch
+// Every rank of a sharded chain runs this redundantly on the all-gathered (Q, G): identical
+// inputs and a fixed reduction tree give identical S everywhere, so no broadcast is needed.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) pre_sweep_kernel(const PreArgs a)
+{
+	__shared__ double sh[RED_THREADS];
+	__shared__ double Ssh[MAX_K];
+	__shared__ int accept_sh;
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x;
+	const int K = g.K, REC = g.REC;
+
+	if (a.mode == 2) {
+		if (tid < K) Ssh[tid] = a.S[tid];
+		__syncthreads();
+		// proposal() at the current S
+		double cur = 0.0;
+		{
+			double part = 0.0;
+			for (int i = tid; i < g.N; i += RED_THREADS) {
+				const double *rec = a.ind + (size_t)i * REC;
+				double s = 0.0;
+				for (int k = 0; k < K; k++) s += rec[k] * Ssh[k];
+				part += log_geom(s, (int)rec[K + 2]);
+			}
+			cur = block_sum(part, sh);
+		}
+		for (int j = 0; j < K; j++) {
+			Stream st((uint32_t)j, 0u, a.iter, TAG_SPOP, a.key0, a.key1);
+			double prop;
+			int new_state = 1;
+			const double sj = Ssh[j];
+			if (a.back_refl == 1) {                         // mcmc.c:939-945
+				prop = sj + (st.uniform() * 2.0 * 0.05 - 0.05);
+				if (prop <= 0.0) prop = -prop;
+				else if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
+			} else {                                        // adpt_indp, mcmc.c:1461-1520
+				const int cs = a.state[j];
+				const double u = st.uniform();
+				if (cs == 0) { if (u < 0.5) { prop = 0.0; new_state = 0; } else { prop = st.uniform(); new_state = 1; } }
+				else if (cs == 2) { if (u < 0.5) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
+				else { if (u <= 0.05) { prop = 0.0; new_state = 0; } else if (u >= 0.95) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
+			}
+			double part = 0.0;
+			for (int i = tid; i < g.N; i += RED_THREADS) {
+				const double *rec = a.ind + (size_t)i * REC;
+				double s = 0.0;
+				for (int k = 0; k < K; k++) s += rec[k] * ((k == j) ? prop : Ssh[k]);
+				part += log_geom(s, (int)rec[K + 2]);
+			}
+			const double pl = block_sum(part, sh);
+			if (tid == 0) {
+				double ratio = exp(pl - cur);
+				if (a.back_refl == 0) ratio *= trans_prob(a.state[j], new_state) / trans_prob(new_state, a.state[j]);
+				const double u = st.uniform();
+				// MIN2(1, NaN) == 1 in the reference (mcmc.h:10): a NaN ratio accepts
+				accept_sh = (ratio != ratio) ? 1 : (u < fmin(1.0, ratio));
+			}
+			__syncthreads();
+			if (accept_sh) {
+				cur = pl;
+				if (tid == 0) { Ssh[j] = prop; a.S[j] = prop; if (a.back_refl == 0) a.state[j] = new_state; a.sc->s_accepts++; }
+			}
+			__syncthreads();
+		}
+		if (tid == 0) a.sc->cur_prop_ll = cur;
+	} else if (a.mode == 3 && a.prior_flag == 0) {
+		for (int i = tid; i < g.N; i += RED_THREADS) {
+			Stream st((uint32_t)i, 0u, a.iter, TAG_SIND, a.key0, a.key1);
+			const double s = a.S[i];
+			const int gen = (int)a.ind[(size_t)i * REC + K + 2];
+			double prop = s + (st.uniform() * 2.0 * 0.05 - 0.05);
+			if (prop <= 0.0) prop = -prop;
+			if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
+			const double ratio = exp(log_geom(prop, gen) - log_geom(s, gen));
+			const double u = st.uniform();
+			if ((ratio != ratio) || u < fmin(1.0, ratio)) a.S[i] = prop;
+		}
+	}
+	__syncthreads();
+	// ---- generation proposals (update_G, mcmc.c:1062-1084): independence proposal from Geom(1 - s_i)
+	for (int i = tid; i < g.N; i += RED_THREADS) {
+		const double *rec = a.ind + (size_t)i * REC;
+		double s = 0.0;
+		if (a.mode == 2) { for (int k = 0; k < K; k++) s += rec[k] * Ssh[k]; }
+		else s = a.S[i];
+		const int stt = sel_state(s);
+		int gp;
+		if (stt == 1) {
+			Stream st((uint32_t)i, 0u, a.iter, TAG_GPROP, a.key0, a.key1);
+			const double u = st.uniform();
+			const double v = floor(log(u) / log(s)) + 1.0;           // rgeom(1 - s), random.c:311-321
+			gp = (v < 1.0) ? 1 : (v > 50.0 ? 50 : (int)v);
+		} else gp = (stt == 0) ? 1 : 50;
+		a.gprop[i] = gp;
+		const int il = i - g.i0;
+		if (il >= 0 && il < g.Nloc) a.gpair[il] = make_int2((int)rec[K + 2], gp);
+	}
+}
+cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
+{
+	pre_sweep_kernel<<<1, RED_THREADS, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// indiv_epilogue: one thread per local individual.  Combines the per-chunk partials in
+// chunk order, takes the update_G accept decision (mcmc.c:1085-1089), draws
+// Q_i ~ Dirichlet(cnt_i + alpha) (mcmc.c:1196-1198) and writes the individual's record
+// (Q, indvlkh, sum_k log q, G) into the all-gatherable array.
+// --------------------------------------------------------------------------------------
+__global__ void indiv_epilogue_kernel(const EpiArgs a)
+{
+	const Geometry &g = a.geo;
+	const int il = blockIdx.x * blockDim.x + threadIdx.x;
+	if (il >= g.Nloc) return;
+	const int K = g.K, KP = g.KP;
+	int cnt[MAX_K];
+	for (int k = 0; k < K; k++) cnt[k] = 0;
+	double d_old = 0.0, c_new = 0.0, a_new = 0.0, b_new = 0.0;
+	for (int c = 0; c < g.nchunks; c++) {
+		const uint16_t *pc = a.pcnt + ((size_t)c * g.Nloc + il) * KP;
+		for (int k = 0; k < K; k++) cnt[k] += pc[k];
+		const double *pl = a.plog + (size_t)c * 4 * g.Nloc + il;
+		d_old += pl[0];
+		c_new += pl[(size_t)g.Nloc];
+		a_new += pl[(size_t)2 * g.Nloc];
+		b_new += pl[(size_t)3 * g.Nloc];
+	}
+	const int ig_global = g.i0 + il;
+	double *rec = a.ind + (size_t)ig_global * g.REC;
+	if (a.llparts) { double *lp = a.llparts + (size_t)il * 4; lp[0] = d_old; lp[1] = c_new; lp[2] = a_new; lp[3] = b_new; }
+	if (!a.init) {
+		const int2 gg = a.gpair[il];
+		Stream sa((uint32_t)ig_global, 0u, a.iter, TAG_GACC, a.key0, a.key1);
+		const double u = sa.uniform();
+		const double ratio = exp(d_old);
+		const bool acc = (ratio != ratio) || (u < fmin(1.0, ratio));
+		rec[K + 2] = (double)(acc ? gg.y : gg.x);
+		rec[K] = c_new + (acc ? b_new : a_new);
+	}
+	const double alpha = a.sc->alpha;
+	Stream sq((uint32_t)ig_global, 0u, a.iter, TAG_Q, a.key0, a.key1);
+	double qv[MAX_K], sum = 0.0;
+	for (int k = 0; k < K; k++) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
+	double slq = 0.0;
+	for (int k = 0; k < K; k++) {
+		const double qk = qv[k] / sum;
+		rec[k] = qk;
+		slq += log(qk);
+		a.Qf[(size_t)il * KP + k] = (float)qk;
+		a.cnt[(size_t)il * K + k] = cnt[k];
+	}
+	for (int k = K; k < KP; k++) a.Qf[(size_t)il * KP + k] = 0.0f;
+	rec[K + 1] = slq;
+}
+cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s)
+{
+	indiv_epilogue_kernel<<<(a.geo.Nloc + 127) / 128, 128, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// post_sweep (one CTA): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
+// (update_alpha, mcmc.c:1244-1263, in log form: (alpha'-alpha) * sum log q), and the
+// column sums of Q for check_empty_cluster (mcmc.c:1954-1961).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) post_sweep_kernel(const PostArgs a)
+{
+	__shared__ double sh[RED_THREADS];
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x, K = g.K, REC = g.REC;
+	double pl = 0.0, ps = 0.0;
+	for (int i = tid; i < g.N; i += RED_THREADS) { pl += a.ind[(size_t)i * REC + K]; ps += a.ind[(size_t)i * REC + K + 1]; }
+	const double tot = block_sum(pl, sh);
+	const double slq = block_sum(ps, sh);
+	for (int k = 0; k < K; k++) {
+		double pq = 0.0;
+		for (int i = tid; i < g.N; i += RED_THREADS) pq += a.ind[(size_t)i * REC + k];
+		const double cs = block_sum(pq, sh);
+		if (tid == 0) a.sc->qcol[k] = cs;
+	}
+	if (tid == 0) {
+		a.sc->totallkh = tot;
+		a.sc->sumlogq = slq;
+		Stream st(0u, 0u, a.iter, TAG_ALPHA, a.key0, a.key1);
+		const double alpha = a.sc->alpha;
+		const double ralpha = alpha + draw_normal(st);
+		if (ralpha > 0.0) {
+			const double ratio = exp((ralpha - alpha) * slq);
+			const double u = st.uniform();
+			if ((ratio != ratio) || u < fmin(1.0, ratio)) { a.sc->alpha = ralpha; a.sc->alpha_accepts++; }
+		}
+	}
+}
+cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s)
+{
+	post_sweep_kernel<<<1, RED_THREADS, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// moments: store_chn (mcmc.c:1320-1456).  mean_{n+1} = (n*mean_n + x)/(n+1), which is what
+// the reference's m*((step + x/m)/(1+step)) evaluates algebraically.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ void run_mean(double *m, double x, long step) { *m = (*m * (double)step + x) / (double)(step + 1); }
+
+__global__ void moments_kernel(const MomArgs a)
+{
+	const Geometry &g = a.geo;
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int K = g.K, REC = g.REC;
+	const long step = a.step;
+	if (t < (long)g.N * K) {
+		const int i = (int)(t / K), k = (int)(t % K);
+		const double q = a.ind[(size_t)i * REC + k];
+		run_mean(a.m.qq + t, q, step);
+		run_mean(a.m.qq2 + t, q * q, step);
+		if (k == 0) {
+			const double lk = a.ind[(size_t)i * REC + K], gen = a.ind[(size_t)i * REC + K + 2];
+			run_mean(a.m.indvlkh + i, lk, step);
+			run_mean(a.m.gen + i, gen, step);
+			run_mean(a.m.gen2 + i, gen * gen, step);
+		}
+	}
+	if (t < a.ns) {
+		const double s = a.S[t];
+		run_mean(a.m.self + t, s, step);
+		run_mean(a.m.self2 + t, s * s, step);
+	}
+	if (t == 0) {
+		const double tl = a.sc->totallkh;
+		run_mean(a.m.tot, tl, step);
+		run_mean(a.m.tot + 1, tl * tl, step);
+		if (a.convg_slot >= 0) a.m.convg[a.convg_slot] = tl;
+	}
+	if (a.print_freq && a.m.freq) {
+		const long tot = (long)K * g.L * g.A;
+		for (long e = t; e < tot; e += (long)gridDim.x * blockDim.x) {
+			const int al = (int)(e % g.A), l = (int)((e / g.A) % g.L), k = (int)(e / ((long)g.A * g.L));
+			const double p = (double)a.P[((size_t)l * g.A + al) * g.KP + k];
+			run_mean(a.m.freq + e, p, step);
+			run_mean(a.m.freq2 + e, p * p, step);
+		}
+	}
+}
+cudaError_t launch_moments(const MomArgs &a, cudaStream_t s)
+{
+	long n = (long)a.geo.N * a.geo.K;
+	if (a.ns > n) n = a.ns;
+	moments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// Layout transforms: canonical [L][Nloc][2] <-> tiled [LT][Nloc][8][2]; loci beyond L and
+// monomorphic loci are stored as missing so the sweep skips them (mcmc.c:817,1137).
+// --------------------------------------------------------------------------------------
+__global__ void tile_x_kernel(const int16_t *xc, int16_t *Xt, const int32_t *allelenum, Geometry g)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t total = (size_t)g.LT * g.Nloc * TILE;
+	if (t >= total) return;
+	const int j = (int)(t % TILE);
+	const int i = (int)((t / TILE) % g.Nloc);
+	const int mt = (int)(t / ((size_t)TILE * g.Nloc));
+	const int l = mt * TILE + j;
+	int16_t v0 = -9, v1 = -9;
+	if (l < g.L && allelenum[l] > 1) {
+		v0 = xc[((size_t)l * g.Nloc + i) * 2];
+		v1 = xc[((size_t)l * g.Nloc + i) * 2 + 1];
+		if (v0 < 0 || v1 < 0 || v0 >= g.A || v1 >= g.A) { v0 = -9; v1 = -9; }   // any copy missing drops the genotype (data_interface.c:828-832)
+	}
+	Xt[t * 2] = v0;
+	Xt[t * 2 + 1] = v1;
+}
+__global__ void untile_x_kernel(const int16_t *Xt, int16_t *xc, Geometry g)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t total = (size_t)g.L * g.Nloc;
+	if (t >= total) return;
+	const int i = (int)(t % g.Nloc), l = (int)(t / g.Nloc);
+	const size_t src = (((size_t)(l / TILE) * g.Nloc + i) * TILE + (l % TILE)) * 2;
+	xc[t * 2] = Xt[src];
+	xc[t * 2 + 1] = Xt[src + 1];
+}
+__global__ void tile_z_kernel(const int8_t *zc, int8_t *Zt, Geometry g)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t total = (size_t)g.LT * g.Nloc * TILE;
+	if (t >= total) return;
+	const int j = (int)(t % TILE);
+	const int i = (int)((t / TILE) % g.Nloc);
+	const int mt = (int)(t / ((size_t)TILE * g.Nloc));
+	const int l = mt * TILE + j;
+	int8_t v0 = 0, v1 = 0;
+	if (l < g.L) { v0 = zc[((size_t)l * g.Nloc + i) * 2]; v1 = zc[((size_t)l * g.Nloc + i) * 2 + 1]; }
+	Zt[t * 2] = v0;
+	Zt[t * 2 + 1] = v1;
+}
+__global__ void untile_z_kernel(const int8_t *Zt, int8_t *zc, Geometry g)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t total = (size_t)g.L * g.Nloc;
+	if (t >= total) return;
+	const int i = (int)(t % g.Nloc), l = (int)(t / g.Nloc);
+	const size_t src = (((size_t)(l / TILE) * g.Nloc + i) * TILE + (l % TILE)) * 2;
+	zc[t * 2] = Zt[src];
+	zc[t * 2 + 1] = Zt[src + 1];
+}
+static inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
+cudaError_t launch_tile_x(const int16_t *xc, int16_t *Xt, const int32_t *an, Geometry g, cudaStream_t s)
+{
+	tile_x_kernel<<<nblocks((size_t)g.LT * g.Nloc * TILE, 256), 256, 0, s>>>(xc, Xt, an, g);
+	return cudaGetLastError();
+}
+cudaError_t launch_untile_x(const int16_t *Xt, int16_t *xc, Geometry g, cudaStream_t s)
+{
+	untile_x_kernel<<<nblocks((size_t)g.L * g.Nloc, 256), 256, 0, s>>>(Xt, xc, g);
+	return cudaGetLastError();
+}
+cudaError_t launch_tile_z(const int8_t *zc, int8_t *Zt, Geometry g, cudaStream_t s)
+{
+	tile_z_kernel<<<nblocks((size_t)g.LT * g.Nloc * TILE, 256), 256, 0, s>>>(zc, Zt, g);
+	return cudaGetLastError();
+}
+cudaError_t launch_untile_z(const int8_t *Zt, int8_t *zc, Geometry g, cudaStream_t s)
+{
+	untile_z_kernel<<<nblocks((size_t)g.L * g.Nloc, 256), 256, 0, s>>>(Zt, zc, g);
+	return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// Stand-alone evaluators used by the parity hooks (ig_set_state(Z), ig_loglik).  They are
+// deliberately simple; the product path is zq_sweep.
+// --------------------------------------------------------------------------------------
+__global__ void tally_kernel(const int16_t *Xt, const int8_t *Zt, int32_t *n, Geometry g)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t total = (size_t)g.LT * g.Nloc * TILE;
+	if (t >= total) return;
+	const int j = (int)(t % TILE);
+	const int mt = (int)(t / ((size_t)TILE * g.Nloc));
+	const int l = mt * TILE + j;
+	const int x0 = Xt[t * 2], x1 = Xt[t * 2 + 1];
+	if (x0 < 0 || x1 < 0) return;
+	atomicAdd(&n[((size_t)l * g.A + x0) * g.KP + Zt[t * 2]], 1);
+	atomicAdd(&n[((size_t)l * g.A + x1) * g.KP + Zt[t * 2 + 1]], 1);
+}
+cudaError_t launch_tally(const int16_t *Xt, const int8_t *Zt, int32_t *n, Geometry g, cudaStream_t s)
+{
+	cudaError_t e = cudaMemsetAsync(n, 0, (size_t)g.Lpad * g.A * g.KP * sizeof(int32_t), s);
+	if (e != cudaSuccess) return e;
+	tally_kernel<<<nblocks((size_t)g.LT * g.Nloc * TILE, 256), 256, 0, s>>>(Xt, Zt, n, g);
+	return cudaGetLastError();
+}
+
+// log_ld_indv (mcmc.c:1726-1773) in double, one thread per individual
+__global__ void loglik_kernel(const int16_t *Xt, const int8_t *Zt, const float *P, const float *Qf, const int32_t *gen,
+                              double *out, Geometry g, int type_freq)
+{
+	const int il = blockIdx.x * blockDim.x + threadIdx.x;
+	if (il >= g.Nloc) return;
+	const int gi = gen[il];
+	const double h = 1.0 - exp2(-(double)(gi - 1));
+	double ll = 0.0;
+	for (int l = 0; l < g.Lpad; l++) {
+		const size_t src = (((size_t)(l / TILE) * g.Nloc + il) * TILE + (l % TILE)) * 2;
+		const int x0 = Xt[src], x1 = Xt[src + 1];
+		if (x0 < 0 || x1 < 0) continue;
+		const int z0 = Zt[src], z1 = Zt[src + 1];
+		double f0, f1;
+		bool same;
+		if (type_freq == 0) {
+			f0 = 0.0; f1 = 0.0;
+			for (int k = 0; k < g.K; k++) {
+				f0 += (double)Qf[(size_t)il * g.KP + k] * (double)P[((size_t)l * g.A + x0) * g.KP + k];
+				f1 += (double)Qf[(size_t)il * g.KP + k] * (double)P[((size_t)l * g.A + x1) * g.KP + k];
+			}
+			same = true;
+		} else {
+			f0 = (double)P[((size_t)l * g.A + x0) * g.KP + z0];
+			f1 = (double)P[((size_t)l * g.A + x1) * g.KP + z1];
+			same = (z0 == z1);
+		}
+		if (same) {
+			if (x0 == x1) ll += log(f0 * (h + f0 * (1.0 - h)));
+			else ll += log(2.0 * f0 * f1) - (double)(gi - 1) * LN2_D;
+		} else {
+			ll += log(f0) + log(f1);
+			if (x0 != x1) ll += LN2_D;
+		}
+	}
+	out[il] = ll;
+}
+cudaError_t launch_loglik(const int16_t *Xt, const int8_t *Zt, const float *P, const float *Qf, const int32_t *gen,
+                          double *out, Geometry g, int type_freq, cudaStream_t s)
+{
+	loglik_kernel<<<(g.Nloc + 63) / 64, 64, 0, s>>>(Xt, Zt, P, Qf, gen, out, g, type_freq);
+	return cudaGetLastError();
+}
+
+__global__ void fill_f32_kernel(float *p, float v, size_t n)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n) p[t] = v;
+}
+cudaError_t launch_fill_f32(float *p, float v, size_t n, cudaStream_t s)
+{
+	fill_f32_kernel<<<nblocks(n, 256), 256, 0, s>>>(p, v, n);
+	return cudaGetLastError();
+}
+
+__global__ void qf_from_ind_kernel(const double *ind, float *Qf, Geometry g)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= g.Nloc * g.KP) return;
+	const int il = t / g.KP, k = t % g.KP;
+	Qf[t] = (k < g.K) ? (float)ind[(size_t)(g.i0 + il) * g.REC + k] : 0.0f;
+}
+cudaError_t launch_qf_from_ind(const double *ind, float *Qf, Geometry g, cudaStream_t s)
+{
+	qf_from_ind_kernel<<<nblocks((size_t)g.Nloc * g.KP, 256), 256, 0, s>>>(ind, Qf, g);
+	return cudaGetLastError();
+}
+
+// Chain initialisation (mcmc.c:193-205 mode 2, :315-331 mode 3, initial_chn :479):
+// alpha ~ U(0,10); mode 2: G_i = min(rgeom(U), 50), S_k = initd[k]; mode 3 uniform prior:
+// S_i ~ U(0,1), G_i = rgeom(1 - S_i) capped at 50 (the reference forgets the cap, App. B #5;
+// harmless after burn-in).  With the DP prior S comes from the host (init_DP) beforehand.
+__global__ void init_chain_kernel(double *ind, double *S, int32_t *state, DevScalars *sc, const float *initd,
+                                  int32_t *gprop, int2 *gpair, Geometry g, int mode, int prior_flag, int back_refl,
+                                  uint32_t key0, uint32_t key1)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0) {
+		Stream st(0u, 1u, 0u, TAG_INIT, key0, key1);
+		sc->alpha = st.uniform() * 10.0;
+		sc->totallkh = 0.0; sc->sumlogq = 0.0; sc->alpha_accepts = 0; sc->s_accepts = 0; sc->flags = 0;
+		if (mode == 2)
+			for (int k = 0; k < g.K; k++) { S[k] = (double)initd[k]; if (back_refl == 0) state[k] = sel_state(S[k]); }
+	}
+	if (i >= g.N) return;
+	Stream st((uint32_t)i, 0u, 0u, TAG_INIT, key0, key1);
+	double *rec = ind + (size_t)i * g.REC;
+	int gen;
+	if (mode == 2) {
+		const double p = st.uniform(), u = st.uniform();
+		const double v = floor(log(u) / log(1.0 - p)) + 1.0;
+		gen = (v > 50.0) ? 50 : (v < 1.0 ? 1 : (int)v);
+	} else {
+		if (prior_flag == 0) S[i] = st.uniform();
+		const double s = S[i], u = st.uniform();
+		const double v = (s > 0.0 && s < 1.0) ? floor(log(u) / log(s)) + 1.0 : (s <= 0.0 ? 1.0 : 50.0);
+		gen = (v > 50.0) ? 50 : (v < 1.0 ? 1 : (int)v);
+	}
+	for (int k = 0; k < g.K; k++) rec[k] = 1.0 / g.K;
+	rec[g.K] = 0.0; rec[g.K + 1] = 0.0; rec[g.K + 2] = (double)gen;
+	gprop[i] = gen;
+	const int il = i - g.i0;
+	if (il >= 0 && il < g.Nloc) gpair[il] = make_int2(gen, gen);
+}
+cudaError_t launch_init_chain(double *ind, double *S, int32_t *state, DevScalars *sc, const float *initd_dev,
+                              int32_t *gprop, int2 *gpair, Geometry g, int mode, int prior_flag, int back_refl,
+                              uint32_t key0, uint32_t key1, cudaStream_t s)
+{
+	init_chain_kernel<<<(g.N + 127) / 128 + 1, 128, 0, s>>>(ind, S, state, sc, initd_dev, gprop, gpair, g, mode, prior_flag, back_refl, key0, key1);
+	return cudaGetLastError();
+}
+
+// proposal() (mcmc.c:1630-1648) at an arbitrary S, for the parity hook
+__global__ void __launch_bounds__(RED_THREADS) proposal_ll_kernel(const double *ind, const double *S, double *out, Geometry g)
+{
+	__shared__ double sh[RED_THREADS];
+	double part = 0.0;
+	for (int i = threadIdx.x; i < g.N; i += RED_THREADS) {
+		const double *rec = ind + (size_t)i * g.REC;
+		double s = 0.0;
+		for (int k = 0; k < g.K; k++) s += rec[k] * S[k];
+		part += log_geom(s, (int)rec[g.K + 2]);
+	}
+	const double r = block_sum(part, sh);
+	if (threadIdx.x == 0) *out = r;
+}
+cudaError_t launch_proposal_ll(const double *ind, const double *S, double *out, Geometry g, cudaStream_t s)
+{
+	proposal_ll_kernel<<<1, RED_THREADS, 0, s>>>(ind, S, out, g);
+	return cudaGetLastError();
+}
+
+__global__ void moments_reset_kernel(const MomArgs a)
+{
+	// initialize_chn (mcmc.c:644-738) seeds every moment with 1 and step = 0, which the first
+	// store overwrites with x; zeroing is equivalent for the (step*m + x)/(step+1) form.
+	const Geometry &g = a.geo;
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < (long)g.N * g.K) { a.m.qq[t] = 0; a.m.qq2[t] = 0; }
+	if (t < g.N) { a.m.indvlkh[t] = 0; a.m.gen[t] = 0; a.m.gen2[t] = 0; }
+	if (t < a.ns) { a.m.self[t] = 0; a.m.self2[t] = 0; }
+	if (t < 2) a.m.tot[t] = 0;
+	if (a.m.freq) {
+		const long tot = (long)g.K * g.L * g.A;
+		for (long e = t; e < tot; e += (long)gridDim.x * blockDim.x) { a.m.freq[e] = 0; a.m.freq2[e] = 0; }
+	}
+}
+cudaError_t launch_moments_reset(const MomArgs &a, cudaStream_t s)
+{
+	long n = (long)a.geo.N * a.geo.K;
+	if (a.ns > n) n = a.ns;
+	if (n < 2) n = 2;
+	moments_reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+}  // namespace ig

@@ -13,7 +13,7 @@ Two products:
     config-4 sized inputs (4 GB) never exist as Python lists or text;
   * :func:`write_reference_text` -- the same data in the reference's text format
     (two lines per diploid individual, ``label pop a_1 .. a_L``; data_interface.c:133-245)
-    for the compiled reference in ``oracle/_ref``.
+    for the compiled reference program.
 """
 from __future__ import annotations
 
@@ -114,41 +114,48 @@ def recode_dense(x: np.ndarray):
     return np.ascontiguousarray(out[: len(keep)]), np.asarray(nums, dtype=np.int32)
 
 
-def make_dataset_torch(N, L, K, A=2, miss=0.0, seed=0, device="cuda", own=0.9, chunk=2048):
+def make_dataset_torch(N, L, K, A=2, miss=0.0, seed=0, device="cuda", own=0.9, chunk=2048, i0=0, n_local=None):
     """Config-4 scale generator: same model, torch ops on ``device``, written straight into
-    an int16 [L][N][2] tensor in locus chunks.  Returns (x, allelenum) as torch tensors.
+    an int16 [L][n_local][2] tensor in locus chunks.  ``i0``/``n_local`` select a block of
+    individuals of the SAME global data set (allele frequencies come from a generator seeded
+    by ``seed`` alone, individual-level randomness from ``seed`` and ``i0``), so the shards
+    that several ranks generate fit together.  Returns (x, allelenum) as torch tensors.
     Loci are assumed polymorphic (true with overwhelming probability for N >= 1000)."""
     import torch
 
+    n_local = N - i0 if n_local is None else n_local
+    gP = torch.Generator(device=device)
+    gP.manual_seed(seed)
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    pop = torch.arange(N, device=device) % K
+    g.manual_seed(seed * 1000003 + 17 + i0)
+    idx = torch.arange(i0, i0 + n_local, device=device)
+    pop = idx % K
     if K > 1:
-        Q = torch.full((N, K), (1.0 - own) / (K - 1), device=device)
-        Q[torch.arange(N, device=device), pop] = own
+        Q = torch.full((n_local, K), (1.0 - own) / (K - 1), device=device)
+        Q[torch.arange(n_local, device=device), pop] = own
     else:
-        Q = torch.ones((N, 1), device=device)
+        Q = torch.ones((n_local, 1), device=device)
     cumQ = torch.cumsum(Q, 1)
     S_k = torch.linspace(0.1, 0.9, K, device=device) if K > 1 else torch.tensor([0.5], device=device)
     s_i = S_k[pop]
-    u = torch.rand(N, generator=g, device=device).clamp_min(1e-12)
+    u = torch.rand(n_local, generator=g, device=device).clamp_min(1e-12)
     G = torch.clamp(torch.floor(torch.log(u) / torch.log(s_i)) + 1, 1, 50)
     p_homo = 1.0 - torch.pow(0.5, G - 1)
-    x = torch.empty((L, N, 2), dtype=torch.int16, device=device)
+    x = torch.empty((L, n_local, 2), dtype=torch.int16, device=device)
     for l0 in range(0, L, chunk):
         l1 = min(L, l0 + chunk)
         n = l1 - l0
-        e = -torch.log(torch.rand((K, n, A), generator=g, device=device).clamp_min(1e-12))
+        e = -torch.log(torch.rand((K, n, A), generator=gP, device=device).clamp_min(1e-12))
         cumP = torch.cumsum(e / e.sum(2, keepdim=True), 2)            # Dirichlet(1_A) [K][n][A]
-        anc = (torch.rand((n, N, 2, 1), generator=g, device=device) > cumQ[None, :, None, :]).sum(3)
+        anc = (torch.rand((n, n_local, 2, 1), generator=g, device=device) > cumQ[None, :, None, :]).sum(3)
         anc.clamp_(max=K - 1)
-        li = torch.arange(n, device=device)[:, None, None].expand(n, N, 2)
-        cp = cumP[anc, li]                                            # [n][N][2][A]
-        a = (torch.rand((n, N, 2, 1), generator=g, device=device) > cp).sum(3).clamp_(max=A - 1)
-        homo = torch.rand((n, N), generator=g, device=device) < p_homo[None, :]
+        li = torch.arange(n, device=device)[:, None, None].expand(n, n_local, 2)
+        cp = cumP[anc, li]                                            # [n][n_local][2][A]
+        a = (torch.rand((n, n_local, 2, 1), generator=g, device=device) > cp).sum(3).clamp_(max=A - 1)
+        homo = torch.rand((n, n_local), generator=g, device=device) < p_homo[None, :]
         a[:, :, 1] = torch.where(homo, a[:, :, 0], a[:, :, 1])
         if miss > 0:
-            mm = torch.rand((n, N), generator=g, device=device) < miss
+            mm = torch.rand((n, n_local), generator=g, device=device) < miss
             a[mm] = MISSING
         x[l0:l1] = a.to(torch.int16)
     allelenum = torch.full((L,), A, dtype=torch.int32, device=device)

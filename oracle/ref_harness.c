@@ -20,7 +20,19 @@
  *
  * All entry points take flat, row-major C arrays so Python (ctypes) can drive them.
  */
+/* mcmc_INDV_selfing reads and may write generation[N], one element past its ivector
+ * (mcmc.c:329-331), which corrupts the heap of the test process.  The
+ * harness gives every ivector allocated from this TU eight ints of slack; the layout that
+ * free_ivector (nrutil.c) expects is unchanged.  Build-recipe fix, source untouched. */
+#define ivector refh_slack_ivector
 #include "mcmc.c"
+#undef ivector
+int *refh_slack_ivector(long nl, long nh)
+{
+	int *v = (int *)malloc((size_t)((nh - nl + 1 + 1 + 8) * sizeof(int)));
+	if (!v) nrerror("allocation failure in refh_slack_ivector()");
+	return v - nl + 1;
+}
 
 void ref_real_rdirich(double *alpha, int length, double **rand, double add);
 
@@ -69,7 +81,7 @@ REFH *refh_new(int N, int L, int K, int ploid, int mode, int prior_flag, int bac
 	d->nstep_check_empty_cluster = 1 << 30; d->print_iter = 0; d->print_freq = 0;
 	d->missingnum = -9; d->missingdata = "-9"; d->autopoly = 1;
 	d->seqdata = i3tensor(0, N - 1, 0, L - 1, 0, ploid - 1);
-	d->allelenum = ivector(0, L - 1);
+	d->allelenum = refh_slack_ivector(0, L - 1);
 	for (j = 0; j < L; j++) { d->allelenum[j] = allelenum[j]; if (allelenum[j] > amax) amax = allelenum[j]; }
 	d->allelenum_max = amax;
 	for (i = 0; i < N; i++)
@@ -250,7 +262,7 @@ int refh_mcmc_updating(REFH *h, long update, long burnin, int thinning, int ckre
 	init.chainnum = 1; init.update = update; init.burnin = burnin; init.thinning = thinning; init.popnum = d->popnum;
 	init.initd = matrix(0, 0, 0, d->popnum - 1);
 	for (k = 0; k < d->popnum; k++) init.initd[0][k] = initd ? initd[k] : 0.5f;
-	init.name_len = ivector(0, 0); init.chn_name = cmatrix(0, 0, 0, 99);
+	init.name_len = refh_slack_ivector(0, 0); init.chn_name = cmatrix(0, 0, 0, 99);
 	strcpy(init.chn_name[0], "Chain#1"); init.name_len[0] = 8;
 	cvg.n_chain = 1; cvg.ckrep = ckrep; cvg.convgfilename = NULL;
 	cvg.convg_ld = dvector(0, ckrep > 0 ? ckrep - 1 : 0);
