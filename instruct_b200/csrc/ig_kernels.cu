@@ -76,83 +76,69 @@ __device__ __forceinline__ void stg_stream(int4 *p, const int4 &v)
 }
 
 // --------------------------------------------------------------------------------------
-// Product accumulator: a log-likelihood is a sum of logs of per-locus probabilities; the
-// kernel keeps the PRODUCT instead, as an fp32 mantissa in [1,2^64) and an integer
-// exponent, and takes one logarithm per (individual, chunk).  Relative error of an n-term
-// product is <= n * 2^-24, i.e. an ABSOLUTE error <= 6e-8 * n on a log-likelihood of
-// magnitude ~n: relative ~1e-7, inside the 1e-6 gate of BASELINE.json.
+// Instruction-mix note (profiles/r1_zq_sweep_v1.md): the first version of this kernel was
+// bound by the ALU pipe (LOP3 / IADD / ISETP / FSETP / SHF, 16 lanes per SM sub-partition)
+// at 68 % while the FMA pipe (FFMA / FMUL / FADD / IMAD, twice as wide) idled at 35 %.  The
+// helpers below therefore phrase comparisons, shifts and index arithmetic as FMA-pipe work
+// wherever that is exact: saturating FFMA instead of FSETP+IADD for the categorical search,
+// IMAD.HI instead of SHF for exponent extraction, IMAD for index math, shared-memory RED
+// instead of register bit-field counters.
 // --------------------------------------------------------------------------------------
+
+// Product accumulator: a log-likelihood is a sum of logs of per-locus probabilities; the
+// kernel keeps the PRODUCT instead, as an fp32 mantissa in [1,2^64) and the integer sum of
+// the factors' biased exponents, and takes one logarithm per (individual, chunk).  Relative
+// error of an n-term product is <= n * 2^-24, i.e. an ABSOLUTE error <= 6e-8 * n on a
+// log-likelihood of magnitude ~n: relative ~1e-7, inside the 1e-6 gate of BASELINE.json.
 struct LogProd {
 	float m;
-	int e;
+	int e;        // sum of biased exponents; value() removes 127 per multiplication
 	__device__ __forceinline__ void init() { m = 1.0f; e = 0; }
 	__device__ __forceinline__ void mul(float t)
 	{
-		int b = __float_as_int(t);
-		e += (b >> 23) - 127;
-		m *= __int_as_float((b & 0x007fffff) | 0x3f800000);
+		const uint32_t b = __float_as_uint(t);
+		asm("mad.hi.u32 %0, %1, 512, %0;" : "+r"(e) : "r"(b));                // e += b >> 23 on the FMA pipe (IMAD.HI)
+		m *= __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
 	}
 	__device__ __forceinline__ void renorm()
 	{
-		int b = __float_as_int(m);
-		e += (b >> 23) - 127;
-		m = __int_as_float((b & 0x007fffff) | 0x3f800000);
+		const uint32_t b = __float_as_uint(m);
+		e += (int)(b >> 23) - 127;
+		m = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
 	}
-	__device__ __forceinline__ double value()
+	__device__ __forceinline__ double value(int nmul)
 	{
 		renorm();
-		return log((double)m) + (double)e * LN2_D;
+		return log((double)m) + (double)(e - 127 * nmul) * LN2_D;
 	}
 };
 
-// --------------------------------------------------------------------------------------
-// Per-individual ancestry counter (qqnum, mcmc.c:1176-1194): K counters that are bumped by
-// a data-dependent index twice per locus.  Registers cannot be indexed dynamically, so the
-// counters are nibble fields of one word (shift by 4z), spilled to byte fields every four
-// loci and to 16-bit fields every 15 micro-tiles.
-// --------------------------------------------------------------------------------------
+constexpr float BIG126 = 8.507059173023462e37f;          // 2^126
+constexpr float U_SCALE = 8.507059173023462e37f;         // (f - 1 + 2^-24) * 2^126, f in [1,2)
+constexpr float U_OFFS = -8.5070586659632355e37f;        // (-1 + 2^-24) * 2^126
+
+// uniform in (0,1) scaled by 2^126, from 23 random bits: ((r >> 9) + 0.5) * 2^-23 * 2^126.
+// One funnel shift builds the float 1.mantissa, one FFMA rescales it.
+__device__ __forceinline__ float uniform_big(uint32_t r)
+{
+	const float f = __uint_as_float(__funnelshift_r(r, 0x7Fu, 9));        // [1, 2)
+	return fmaf(f, U_SCALE, U_OFFS);
+}
+
+// index of the first cumulative weight that exceeds t:  #{k < KP-1 : t > c_k}, evaluated as a
+// sum of saturated differences (t - c_k) * 2^126 -- FFMA.SAT + FADD on the FMA pipe.  t and
+// c_k are fp32 values whose difference is either 0 or at least one ulp(t) >= 2^-126 in
+// magnitude (t >= 2^-24 * total, total >= P_FLOOR / K), so every term is exactly 0 or 1.
+// Padded populations have c_k = total > t and never count; no clamp is needed.
 template <int KP>
-struct Counter {
-	static constexpr int NW = (KP + 7) / 8;     // nibble words
-	uint32_t n4[NW], blo[NW], bhi[NW];
-	uint32_t c16[KP / 2];                       // (pop 2j) | (pop 2j+1) << 16
-	__device__ __forceinline__ void init()
-	{
+__device__ __forceinline__ int pick_category(const float (&c)[KP], float ub)
+{
+	const float tb = ub * c[KP - 1];                                      // t * 2^126, t = u * total
+	float zf = 0.0f;
 #pragma unroll
-		for (int w = 0; w < NW; w++) { n4[w] = 0; blo[w] = 0; bhi[w] = 0; }
-#pragma unroll
-		for (int j = 0; j < KP / 2; j++) c16[j] = 0;
-	}
-	__device__ __forceinline__ void add(int z)
-	{
-		if (NW == 1) n4[0] += 1u << (4 * z);
-		else {
-#pragma unroll
-			for (int w = 0; w < NW; w++) n4[w] += ((z >> 3) == w) ? (1u << (4 * (z & 7))) : 0u;
-		}
-	}
-	__device__ __forceinline__ void flush_nibbles()      // after at most 4 loci (8 increments)
-	{
-#pragma unroll
-		for (int w = 0; w < NW; w++) {
-			blo[w] += n4[w] & 0x0F0F0F0Fu;
-			bhi[w] += (n4[w] >> 4) & 0x0F0F0F0Fu;
-			n4[w] = 0;
-		}
-	}
-	__device__ __forceinline__ void flush_bytes()        // after at most 30 nibble flushes
-	{
-#pragma unroll
-		for (int w = 0; w < NW; w++) {
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				int idx = w * 4 + j;
-				if (idx < KP / 2) c16[idx] += ((blo[w] >> (8 * j)) & 0xFFu) | (((bhi[w] >> (8 * j)) & 0xFFu) << 16);
-			}
-			blo[w] = 0; bhi[w] = 0;
-		}
-	}
-};
+	for (int k = 0; k < KP - 1; k++) zf += __saturatef(fmaf(c[k], -BIG126, tb));
+	return __float2int_rn(zf);
+}
 
 // --------------------------------------------------------------------------------------
 // zq_sweep: grid (locus chunks, individual blocks), 256 threads, one thread = one
@@ -161,7 +147,8 @@ struct Counter {
 //             Z  int8  [LT][Nloc][8][2]  one 128-bit load + one 128-bit store
 //   shared  : P chunk [TL][A][KP] fp32, landed by ONE TMA bulk copy on an mbarrier;
 //             n chunk [TL][A][KP][R] int32 histogram, R lane-replicas to thin out conflicts,
-//             reduced and pushed to global n with RED at the end of the CTA
+//             reduced and pushed to global n with RED at the end of the CTA;
+//             per-thread ancestry counters [KP][256] int32 (column tid: conflict-free RED)
 //   output  : per (chunk, individual) partials: K counts (u16) + 4 log-likelihood pieces
 // --------------------------------------------------------------------------------------
 template <int KP, int ROUNDS, bool TF0>
@@ -179,9 +166,9 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 	const int rowsz = A * KP;                       // floats per locus
 	float *Psm = reinterpret_cast<float *>(smem_raw);
 	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);
+	int *cntsm = hist + (size_t)g.TL * rowsz * g.R;                 // [KP][ZQ_THREADS]
 	const int nbins = nl * rowsz;
 	const int R = g.R;
-	const int rlane = tid & (R - 1);
 
 	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 	__syncthreads();
@@ -190,6 +177,8 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
 	}
 	for (int j = tid; j < nbins * R; j += ZQ_THREADS) hist[j] = 0;
+#pragma unroll
+	for (int k = 0; k < KP; k++) cntsm[k * ZQ_THREADS + tid] = 0;
 	__syncthreads();
 	mbar_wait(&bar, 0);
 
@@ -198,6 +187,8 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 	const int sub0 = blockIdx.y * g.subs_per_blk;
 	const int nsub_total = (Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
 	const int sub1 = min(sub0 + g.subs_per_blk, nsub_total);
+	int *hist_t = hist + (tid & (R - 1));           // this lane's replica column
+	int *cnt_t = cntsm + tid;                       // this thread's counter column
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		const int il = sub * ZQ_THREADS + tid;
@@ -220,8 +211,6 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 			LogProd Cn, An, Bn, Ao, Bo;
 			Cn.init(); An.init(); Bn.init(); Ao.init(); Bo.init();
 			int nhet = 0, nsh_new = 0, nsh_old = 0;
-			Counter<KP> cnt;
-			cnt.init();
 
 			const int4 *xp = reinterpret_cast<const int4 *>(a.Xt) + ((size_t)mt0 * Nloc + il) * 2;
 			int4 *zp = reinterpret_cast<int4 *>(a.Zt) + ((size_t)mt0 * Nloc + il);
@@ -237,22 +226,24 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 					zz_n = ldg_rw(zp + (size_t)(mt + 1) * zstride);
 				}
 				const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-				const int zwo[4] = {zz.x, zz.y, zz.z, zz.w};
-				int zwn[4];
+				const uint32_t zwo[4] = {(uint32_t)zz.x, (uint32_t)zz.y, (uint32_t)zz.z, (uint32_t)zz.w};
+				uint32_t zwn[4];
 #pragma unroll
 				for (int pr = 0; pr < 4; ++pr) {
 					const u32x4 rnd = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
 					const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-					int znew_word = zwo[pr];
+					uint32_t pair[2];
 #pragma unroll
 					for (int h2 = 0; h2 < 2; ++h2) {
 						const int j = 2 * pr + h2;
-						const int x0 = (xw[j] << 16) >> 16, x1 = xw[j] >> 16;
-						if ((x0 | x1) >= 0) {
+						const uint32_t pold = h2 ? (zwo[pr] >> 16) : (zwo[pr] & 0xFFFFu);
+						pair[h2] = pold;
+						// the tiler stores a genotype with ANY missing copy as (-9,-9): one sign test
+						if (xw[j] >= 0) {
+							const int x0 = xw[j] & 0xFFFF, x1 = xw[j] >> 16;
 							const int lj = mt * TILE + j;
 							const int row0 = (lj * A + x0) * KP, row1 = (lj * A + x1) * KP;
 							const bool het = (x0 != x1);
-							const int zo0 = (zwo[pr] >> (16 * h2)) & 0xFF, zo1 = (zwo[pr] >> (16 * h2 + 8)) & 0xFF;
 							// ---- cumulative weights w_k = sum_{m<=k} Q_im P_m,l,x (mcmc.c:1141-1149)
 							float p0[KP], p1[KP], c0[KP], c1[KP];
 #pragma unroll
@@ -268,6 +259,7 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 							for (int k = 1; k < KP; k++) { c0[k] = fmaf(q[k], p0[k], c0[k - 1]); c1[k] = fmaf(q[k], p1[k], c1[k - 1]); }
 							// ---- old-Z pieces of update_G's ratio (log_ld_indv, mcmc.c:1752-1759)
 							if (!TF0) {
+								const int zo0 = pold & 0xFF, zo1 = pold >> 8;
 								const bool same_o = (zo0 == zo1);
 								const float fo = Psm[row0 + zo0];
 								const bool sh_o = same_o && !het;
@@ -276,18 +268,14 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 								nsh_old += (same_o && het) ? 1 : 0;
 							}
 							// ---- categorical draws (disc_unif, random.c:403-430)
-							const float t0 = u01f(rr[2 * h2]) * c0[KP - 1];
-							const float t1 = u01f(rr[2 * h2 + 1]) * c1[KP - 1];
-							int z0 = 0, z1 = 0;
-#pragma unroll
-							for (int k = 0; k < KP - 1; k++) { z0 += (t0 >= c0[k]) ? 1 : 0; z1 += (t1 >= c1[k]) ? 1 : 0; }
-							z0 = min(z0, g.K - 1);
-							z1 = min(z1, g.K - 1);
-							// ---- n[l][a][k] tally for the next update_P (mcmc.c:815-845)
-							atomicAdd(&hist[(row0 + z0) * R + rlane], 1);
-							atomicAdd(&hist[(row1 + z1) * R + rlane], 1);
-							cnt.add(z0);
-							cnt.add(z1);
+							const int z0 = pick_category<KP>(c0, uniform_big(rr[2 * h2]));
+							const int z1 = pick_category<KP>(c1, uniform_big(rr[2 * h2 + 1]));
+							// ---- n[l][a][k] tally for the next update_P (mcmc.c:815-845), and the
+							//      individual's ancestry counts (mcmc.c:1176-1194): shared-memory RED
+							atomicAdd(hist_t + (row0 + z0) * R, 1);
+							atomicAdd(hist_t + (row1 + z1) * R, 1);
+							atomicAdd(cnt_t + z0 * ZQ_THREADS, 1);
+							atomicAdd(cnt_t + z1 * ZQ_THREADS, 1);
 							// ---- new-Z likelihood pieces (cal_lkh and the accepted-G selection)
 							float f0, f1;
 							bool same_n;
@@ -299,29 +287,34 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 							Bn.mul(sh_n ? fmaf(f0, omh_p, h_p) : 1.0f);
 							nhet += het ? 1 : 0;
 							nsh_new += (same_n && het) ? 1 : 0;
-							znew_word = (znew_word & ~(0xFFFF << (16 * h2))) | ((z0 | (z1 << 8)) << (16 * h2));
+							pair[h2] = (uint32_t)(z1 * 256 + z0);
 						}
 					}
-					zwn[pr] = znew_word;
-					if (pr == 1 || pr == 3) cnt.flush_nibbles();
+					zwn[pr] = pair[1] * 65536u + pair[0];
 				}
-				stg_stream(zp + (size_t)mt * zstride, make_int4(zwn[0], zwn[1], zwn[2], zwn[3]));
+				stg_stream(zp + (size_t)mt * zstride, make_int4((int)zwn[0], (int)zwn[1], (int)zwn[2], (int)zwn[3]));
 				if ((mt & 7) == 7) { Cn.renorm(); An.renorm(); Bn.renorm(); Ao.renorm(); Bo.renorm(); }
-				if ((mt % 15) == 14) cnt.flush_bytes();
 			}
-			cnt.flush_bytes();
 			// ---- partials of this (chunk, individual)
 			{
+				int csum = 0;
 				uint32_t *pc = reinterpret_cast<uint32_t *>(a.pcnt + ((size_t)chunk * Nloc + il) * KP);
 #pragma unroll
-				for (int j = 0; j < KP / 2; j++) pc[j] = cnt.c16[j];
+				for (int j = 0; j < KP / 2; j++) {
+					const int ca = cnt_t[(2 * j) * ZQ_THREADS], cb = cnt_t[(2 * j + 1) * ZQ_THREADS];
+					cnt_t[(2 * j) * ZQ_THREADS] = 0;
+					cnt_t[(2 * j + 1) * ZQ_THREADS] = 0;
+					csum += ca + cb;
+					pc[j] = (uint32_t)ca | ((uint32_t)cb << 16);
+				}
+				const int nmul = csum >> 1;               // usable genotypes = multiplications per accumulator
 				double *pl = a.plog + (size_t)chunk * 4 * Nloc + il;
-				const double la = An.value(), lb = Bn.value();
+				const double la = An.value(nmul), lb = Bn.value(nmul);
 				double d_old;
 				if (TF0) d_old = (lb - la) - (double)nsh_new * (double)(gg.y - gg.x) * LN2_D;
-				else d_old = (Bo.value() - Ao.value()) - (double)nsh_old * (double)(gg.y - gg.x) * LN2_D;
+				else d_old = (Bo.value(nmul) - Ao.value(nmul)) - (double)nsh_old * (double)(gg.y - gg.x) * LN2_D;
 				pl[0] = d_old;
-				pl[(size_t)Nloc] = Cn.value() + (double)nhet * LN2_D;
+				pl[(size_t)Nloc] = Cn.value(nmul) + (double)nhet * LN2_D;
 				pl[(size_t)2 * Nloc] = la - (double)nsh_new * (double)(gg.x - 1) * LN2_D;
 				pl[(size_t)3 * Nloc] = lb - (double)nsh_new * (double)(gg.y - 1) * LN2_D;
 			}
@@ -373,14 +366,15 @@ cudaError_t zq_configure(Geometry &g, int device)
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
 	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 	const int target_ctas = 4 * sms;                       // two resident CTAs per SM, two waves
-	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / 2 - 2048;   // two CTAs per SM
+	const size_t cnt_bytes = (size_t)g.KP * ZQ_THREADS * sizeof(int);
+	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / 2 - 2048 - cnt_bytes;   // two CTAs per SM
 	const size_t per_locus = (size_t)g.A * g.KP * 4;
 	const int nsub_total = (g.Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
 	int R = 8;
 	while (R > 1 && per_locus * (1 + R) * TILE > budget) R >>= 1;
-	if (per_locus * (1 + R) * TILE > (size_t)smem_optin - 2048) return cudaErrorInvalidConfiguration;
+	if (per_locus * (1 + R) * TILE > (size_t)smem_optin - 2048 - cnt_bytes) return cudaErrorInvalidConfiguration;
 	int tl_max = (int)(budget / (per_locus * (1 + R)));
-	if (tl_max < TILE) tl_max = (int)(((size_t)smem_optin - 2048) / (per_locus * (1 + R)));
+	if (tl_max < TILE) tl_max = (int)(((size_t)smem_optin - 2048 - cnt_bytes) / (per_locus * (1 + R)));
 	tl_max = (tl_max / TILE) * TILE;
 	if (tl_max < TILE) return cudaErrorInvalidConfiguration;
 	if (tl_max > 1024) tl_max = 1024;
@@ -395,7 +389,7 @@ cudaError_t zq_configure(Geometry &g, int device)
 	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
 	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
 	g.R = R;
-	g.zq_smem = (size_t)tl * per_locus * (1 + R);
+	g.zq_smem = (size_t)tl * per_locus * (1 + R) + (size_t)g.KP * ZQ_THREADS * sizeof(int);
 	return cudaSuccess;
 }
 

@@ -26,8 +26,10 @@ constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 IG_HD void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
 {
 #if defined(__CUDA_ARCH__)
-	lo = a * b;
-	hi = __umulhi(a, b);
+	uint64_t p;
+	asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));     // one IMAD.WIDE.U32
+	lo = (uint32_t)p;
+	hi = (uint32_t)(p >> 32);
 #else
 	uint64_t p = (uint64_t)a * b;
 	lo = (uint32_t)p;

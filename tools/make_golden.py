@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures in tests/golden/ from the UNMODIFIED reference
+(the include-the-.c harness in oracle/_ref, built by oracle/Makefile from /root/reference).
+
+The reference ships no golden vectors of its own, so these are the
+"outputs of the reference itself run here" that pin the oracle and give the GPU path its
+statistical target.  Run in the authoring container only:
+
+    python tools/make_golden.py            # writes tests/golden/*.npz (small, committed)
+
+Fixtures
+  state_K{K}.npz      injected state + the reference's tally / missing mask / log_ld_indv /
+                      proposal / cal_lkh on it                       (parity levels 1 and 2)
+  chain_mode{m}.npz   CHAIN moments of one short chain from fixed Wichmann-Hill seeds through
+                      the reference's own mcmc_updating()            (whole-chain pin)
+  posterior_c1.npz    config-1 shaped data (K=2 N=200 L=10), posterior means of S, Q, log-lik
+                      from R independent reference chains            (parity level 3)
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from instruct_b200.synth import make_dataset  # noqa: E402
+from oracle.pyoracle import Reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def state_fixture(K, A, miss, seed):
+    d = make_dataset(N=48, L=29, K=K, A=A, miss=miss, seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    r = Reference(d.x, d.allelenum, K)
+    z = rng.integers(0, K, size=d.x.shape).astype(np.int8)
+    qq = rng.dirichlet(np.ones(K) * 0.7, size=d.N)
+    freq = rng.dirichlet(np.ones(r.Amax), size=(K, d.L))
+    gen = rng.integers(1, 9, size=d.N).astype(np.int32)
+    S = rng.uniform(0.1, 0.9, K)
+    r.set_z(z); r.set_qq(qq); r.set_freq(freq); r.set_gen(gen); r.set_self(S); r.set_alpha(0.8)
+    tally = r.update_P(want_tally=True)          # also redraws freq: restore it
+    r.set_freq(freq)
+    ll = np.array([[r.log_ld_indv(g, i) for g in (1, 2, 5, 50)] for i in range(d.N)])
+    r.cal_lkh()
+    indv, tot = r.get_lkh()
+    S2 = rng.uniform(0.1, 0.9, K)
+    np.savez_compressed(os.path.join(OUT, f"state_K{K}.npz"), x=d.x, allelenum=d.allelenum, K=K, z=z, qq=qq,
+                        freq=freq, gen=gen, S=S, S2=S2, tally=tally, missindx=r.missindx().astype(np.uint8),
+                        ll_g=np.array([1, 2, 5, 50]), ll=ll, indvlkh=indv, totallkh=tot,
+                        proposal_S=r.proposal(S), proposal_S2=r.proposal(S2))
+
+
+def chain_fixture(mode, prior):
+    K = 3
+    d = make_dataset(N=40, L=18, K=K, A=4, miss=0.05, seed=31, s_atoms=[0.1, 0.5, 0.9] if mode == 3 else None)
+    r = Reference(d.x, d.allelenum, K, mode=mode, prior_flag=prior, alpha_dpm=2.0)
+    r.setseeds(13, 4, 1972)
+    kw = dict(update=120, burnin=40, thinning=4, ckrep=6, nstep_check_empty=10, initd=[0.25, 0.5, 0.75])
+    c = r.mcmc_updating(**kw)
+    np.savez_compressed(os.path.join(OUT, f"chain_mode{mode}_prior{prior}.npz"), x=d.x, allelenum=d.allelenum, K=K,
+                        mode=mode, prior=prior, seeds=[13, 4, 1972], alpha_dpm=2.0, **{f"kw_{k}": v for k, v in kw.items()},
+                        **{k: np.asarray(v) for k, v in c.items()})
+
+
+def posterior_fixture(R=12):
+    """BASELINE.json configs[0] shape: K=2 N=200 L=10 microsatellite, mode 2, uniform prior."""
+    K = 2
+    d = make_dataset(N=200, L=10, K=K, A=8, miss=0.0, seed=1001, pure=True)
+    S, Qm, LL, G = [], [], [], []
+    for rep in range(R):
+        r = Reference(d.x, d.allelenum, K, mode=2)
+        r.setseeds(13 + 7 * rep, 4 + 3 * rep, 1972 + 11 * rep)
+        c = r.mcmc_updating(update=6000, burnin=2000, thinning=10, ckrep=5, nstep_check_empty=20,
+                            initd=[0.3 + 0.02 * rep, 0.6 - 0.02 * rep])
+        # label switching: order clusters by their mean selfing rate
+        o = np.argsort(c["self_rates"])
+        S.append(c["self_rates"][o]); Qm.append(c["qq"][:, o]); LL.append(c["totallkh"]); G.append(c["gen"])
+        print("posterior rep", rep, c["self_rates"][o], c["totallkh"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "posterior_c1.npz"), x=d.x, allelenum=d.allelenum, K=K, S=np.array(S),
+                        Q=np.array(Qm).astype(np.float32), LL=np.array(LL), G=np.array(G).astype(np.float32),
+                        S_true=d.S_true, pop=d.pop, update=6000, burnin=2000, thinning=10)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    state_fixture(2, 3, 0.0, 1)
+    state_fixture(5, 6, 0.06, 2)
+    state_fixture(8, 2, 0.1, 3)
+    chain_fixture(2, 0)
+    chain_fixture(3, 0)
+    chain_fixture(3, 1)
+    posterior_fixture()
