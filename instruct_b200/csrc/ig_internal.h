@@ -63,6 +63,7 @@ struct ZQArgs {
 	uint32_t iter;
 	uint32_t key0, key1;
 	int type_freq;
+	uint32_t k512;           // the constant 512, kept in a register on purpose (see LogProd::mul)
 };
 
 // ---- launchers (ig_kernels.cu) -------------------------------------------------------

@@ -94,10 +94,12 @@ struct LogProd {
 	float m;
 	int e;        // sum of biased exponents; value() removes 127 per multiplication
 	__device__ __forceinline__ void init() { m = 1.0f; e = 0; }
-	__device__ __forceinline__ void mul(float t)
+	// k512 is the constant 512 passed as a kernel argument: ptxas strength-reduces a literal
+	// power-of-two multiplier to LEA.HI (ALU pipe), a register operand stays an IMAD.HI
+	__device__ __forceinline__ void mul(float t, uint32_t k512)
 	{
 		const uint32_t b = __float_as_uint(t);
-		asm("mad.hi.u32 %0, %1, 512, %0;" : "+r"(e) : "r"(b));                // e += b >> 23 on the FMA pipe (IMAD.HI)
+		asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(e) : "r"(b), "r"(k512));       // e += b >> 23 on the FMA pipe
 		m *= __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
 	}
 	__device__ __forceinline__ void renorm()
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 	const int sub1 = min(sub0 + g.subs_per_blk, nsub_total);
 	int *hist_t = hist + (tid & (R - 1));           // this lane's replica column
 	int *cnt_t = cntsm + tid;                       // this thread's counter column
+	const uint32_t k512 = a.k512;
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		const int il = sub * ZQ_THREADS + tid;
@@ -263,8 +266,8 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 								const bool same_o = (zo0 == zo1);
 								const float fo = Psm[row0 + zo0];
 								const bool sh_o = same_o && !het;
-								Ao.mul(sh_o ? fmaf(fo, omh_g, h_g) : 1.0f);
-								Bo.mul(sh_o ? fmaf(fo, omh_p, h_p) : 1.0f);
+								Ao.mul(sh_o ? fmaf(fo, omh_g, h_g) : 1.0f, k512);
+								Bo.mul(sh_o ? fmaf(fo, omh_p, h_p) : 1.0f, k512);
 								nsh_old += (same_o && het) ? 1 : 0;
 							}
 							// ---- categorical draws (disc_unif, random.c:403-430)
@@ -282,9 +285,9 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 							if (TF0) { f0 = c0[KP - 1]; f1 = c1[KP - 1]; same_n = true; }   // mcmc.c:1739-1749
 							else { f0 = Psm[row0 + z0]; f1 = Psm[row1 + z1]; same_n = (z0 == z1); }
 							const bool sh_n = same_n && !het;
-							Cn.mul(f0 * (sh_n ? 1.0f : f1));
-							An.mul(sh_n ? fmaf(f0, omh_g, h_g) : 1.0f);
-							Bn.mul(sh_n ? fmaf(f0, omh_p, h_p) : 1.0f);
+							Cn.mul(f0 * (sh_n ? 1.0f : f1), k512);
+							An.mul(sh_n ? fmaf(f0, omh_g, h_g) : 1.0f, k512);
+							Bn.mul(sh_n ? fmaf(f0, omh_p, h_p) : 1.0f, k512);
 							nhet += het ? 1 : 0;
 							nsh_new += (same_n && het) ? 1 : 0;
 							pair[h2] = (uint32_t)(z1 * 256 + z0);

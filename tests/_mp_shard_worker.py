@@ -1,0 +1,86 @@
+"""Worker for the multi-process tests (launched by torch.distributed.run).
+
+mode "cpu"  (gloo, no GPU): the host-side sharding logic -- shard bounds tile the individuals,
+             the per-shard integer tallies all-reduce to the full tally (the exchange the
+             library issues over NCCL per sweep), traces gather, the id broadcast works.
+mode "gpu"  (nccl, >= 2 GPUs): a chain whose individuals are sharded over the ranks is
+             BIT-IDENTICAL to the same chain on one GPU (counter-based RNG keyed on global
+             indices + integer all-reduce + fixed-order reductions).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from instruct_b200.shard import (broadcast_unique_id, chains_of_rank, gather_traces, shard_bounds,  # noqa: E402
+                                 shard_genotypes)
+from instruct_b200.synth import make_dataset  # noqa: E402
+
+
+def cpu_mode():
+    from oracle.pyoracle import Oracle
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    K = 3
+    d = make_dataset(N=101, L=19, K=K, A=4, miss=0.05, seed=3)
+    o = Oracle(d.x, d.allelenum, K)
+    rng = np.random.default_rng(0)
+    o.z[...] = rng.integers(0, K, size=o.z.shape)
+    b, e = shard_bounds(d.N, world, rank)
+    spans = [None] * world
+    dist.all_gather_object(spans, (b, e))
+    assert spans[0][0] == 0 and spans[-1][1] == d.N and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    assert shard_genotypes(d.x, world, rank).shape[1] == e - b
+    part = torch.from_numpy(o.tally(b, e).astype(np.int32))
+    dist.all_reduce(part)
+    assert np.array_equal(part.numpy(), o.tally())
+    uid = broadcast_unique_id(lambda: bytes(range(128)), rank)
+    assert uid == bytes(range(128))
+    mine = {c: np.arange(5) + 10.0 * c for c in chains_of_rank(5, world, rank)}
+    tr = gather_traces(mine, 5, 5)
+    assert np.array_equal(tr, np.arange(5)[None, :] + 10.0 * np.arange(5)[:, None])
+    dist.barrier()
+    if rank == 0:
+        print("CPU_SHARD_OK")
+    dist.destroy_process_group()
+
+
+def gpu_mode():
+    from instruct_b200 import Sampler, SeqData, _lib
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K = 4
+    d = make_dataset(N=777, L=150, K=K, A=3, miss=0.04, seed=8)
+    kw = dict(update=25, burnin=10, thinning=3, ckrep=4, seed=99)
+    xs = shard_genotypes(d.x, world, rank)
+    s = Sampler(SeqData(xs, d.allelenum, K), device=local, shard_rank=rank, shard_count=world, totalsize=d.N, **kw)
+    s.comm_init(broadcast_unique_id(Sampler.unique_id, rank))
+    ch, cv = s.run_chain(0, initd=[0.2, 0.4, 0.6, 0.8])
+    zloc = s.get(_lib.STATE_Z)
+    s.close()
+    ok = True
+    if rank == 0:
+        s1 = Sampler(SeqData(d.x, d.allelenum, K), device=local, **kw)
+        c1, cv1 = s1.run_chain(0, initd=[0.2, 0.4, 0.6, 0.8])
+        z1 = s1.get(_lib.STATE_Z)
+        s1.close()
+        b, e = shard_bounds(d.N, world, 0)
+        for name in ("qq", "qq2", "self_rates", "self_rates2", "gen", "gen2", "indvlkh"):
+            ok &= bool(np.array_equal(getattr(ch, name), getattr(c1, name)))
+        ok &= ch.totallkh == c1.totallkh and ch.totallkh2 == c1.totallkh2 and bool(np.array_equal(cv, cv1))
+        ok &= bool(np.array_equal(zloc, z1[:, b:e, :]))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("GPU_SHARD_OK" if int(flag.item()) == 1 else "GPU_SHARD_MISMATCH")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    cpu_mode() if sys.argv[1] == "cpu" else gpu_mode()
