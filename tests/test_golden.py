@@ -1,0 +1,59 @@
+"""The oracle against the committed golden fixtures (tests/golden/*.npz), which
+tools/make_golden.py generated from the UNMODIFIED reference compiled in oracle/_ref.
+Runs anywhere (no reference, no GPU needed): this is what keeps the oracle pinned on the
+GPU box, where /root/reference does not exist."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "state_K*.npz"))))
+def test_state_fixture(path):
+    g = np.load(path)
+    K = int(g["K"])
+    o = Oracle(g["x"], g["allelenum"], K)
+    o.z[...] = g["z"]; o.qq[...] = g["qq"]; o.freq[...] = g["freq"]; o.gen[...] = g["gen"]
+    o.self_rates[...] = g["S"]; o.alpha = 0.8
+    assert np.array_equal(o.tally(), g["tally"])                      # integer: bit-exact
+    assert np.array_equal(o.missing_mask(), g["missindx"])
+    for j, gen in enumerate(g["ll_g"]):
+        got = np.array([o.log_ld_indv(int(gen), i) for i in range(o.N)])
+        np.testing.assert_allclose(got, g["ll"][:, j], rtol=1e-12, atol=0)
+    o.cal_lkh()
+    np.testing.assert_allclose(o.indvlkh, g["indvlkh"], rtol=1e-12)
+    assert abs(o.totallkh - float(g["totallkh"])) <= 1e-12 * abs(float(g["totallkh"]))
+    assert abs(o.proposal(g["S"]) - float(g["proposal_S"])) <= 1e-12 * abs(float(g["proposal_S"]))
+    assert abs(o.proposal(g["S2"]) - float(g["proposal_S2"])) <= 1e-12 * abs(float(g["proposal_S2"]))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "chain_mode*.npz"))))
+def test_chain_fixture_bit_exact(path):
+    """Whole chains from fixed Wichmann-Hill seeds reproduce the reference's CHAIN moments."""
+    g = np.load(path)
+    K = int(g["K"])
+    o = Oracle(g["x"], g["allelenum"], K, mode=int(g["mode"]), prior_flag=int(g["prior"]), alpha_dpm=float(g["alpha_dpm"]))
+    o.setseeds(*[int(v) for v in g["seeds"]])
+    c = o.run_chain(update=int(g["kw_update"]), burnin=int(g["kw_burnin"]), thinning=int(g["kw_thinning"]),
+                    ckrep=int(g["kw_ckrep"]), nstep_check_empty=int(g["kw_nstep_check_empty"]), initd=g["kw_initd"])
+    assert c["flag_empty_cluster"] == int(g["flag_empty_cluster"]) == 0
+    for k in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "gen", "gen2", "convg"]:
+        # libm differences between hosts could in principle move the last bit; allow 1e-12
+        np.testing.assert_allclose(np.asarray(c[k]), g[k], rtol=1e-12, atol=0, err_msg=k)
+
+
+def test_gelman_rubin_variants():
+    from oracle import pyoracle
+    from instruct_b200.converge import gelman_rubin, gelman_rubin_ref_compat
+    rng = np.random.default_rng(0)
+    tr = rng.normal(size=(4, 12)) + np.array([0, 0.5, 1.0, 1.5])[:, None]
+    flat = tr.reshape(-1)
+    assert abs(gelman_rubin(tr) - pyoracle.gelman_rubin(flat, 4, 12)) < 1e-12
+    # what the reference computes (check_converg.c:67): segments of chain 0 only
+    assert abs(gelman_rubin_ref_compat(flat, 4, 12) - pyoracle.gelman_rubin_ref(flat, 4, 12)) < 1e-12
+    assert gelman_rubin(tr) > 1.2      # four chains with shifted means do not look converged

@@ -1,0 +1,58 @@
+"""Parity level 3 (BASELINE.json north_star): posterior summaries of the GPU sampler agree
+with the reference within Monte-Carlo standard error across seeds.
+
+tests/golden/posterior_c1.npz holds, for a config-1 shaped data set (K=2 N=200 L=10
+microsatellite, mode 2, uniform prior), the posterior means of S, Q, log-likelihood and G
+from 12 independent chains of the compiled reference (tools/make_golden.py).  The same
+number of GPU chains, same length, must give means within 3 combined standard errors."""
+import os
+
+import numpy as np
+import pytest
+
+from instruct_b200 import Sampler, SeqData
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "posterior_c1.npz")
+
+
+def _z(a, b):
+    """difference of means over combined standard error, per component"""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    se = np.sqrt(a.var(axis=0, ddof=1) / len(a) + b.var(axis=0, ddof=1) / len(b))
+    return (a.mean(axis=0) - b.mean(axis=0)) / np.maximum(se, 1e-12)
+
+
+def test_posterior_matches_reference_within_mcse():
+    g = np.load(GOLD)
+    K = int(g["K"])
+    R = g["S"].shape[0]
+    sd = SeqData(g["x"], g["allelenum"], K, mode=2)
+    S, Qown, LL, G = [], [], [], []
+    pop = g["pop"]
+    for rep in range(R):
+        s = Sampler(sd, update=int(g["update"]), burnin=int(g["burnin"]), thinning=int(g["thinning"]), ckrep=5, seed=1000 + rep)
+        ch, _ = s.run_chain(rep, initd=[0.3 + 0.02 * rep, 0.6 - 0.02 * rep])
+        s.close()
+        assert ch.flag_empty_cluster == 0 and ch.step == ch.steps
+        o = np.argsort(ch.self_rates)                   # label switching: order clusters by selfing rate
+        S.append(ch.self_rates[o]); LL.append(ch.totallkh); G.append(ch.gen.mean())
+        Qown.append(ch.qq[:, o])
+    S, LL, G = np.array(S), np.array(LL), np.array(G)
+    Q = np.array(Qown)                                  # [R][N][K], clusters ordered by S
+    refQ = g["Q"].astype(np.float64)
+    zS = _z(S, g["S"])
+    zLL = _z(LL[:, None], g["LL"][:, None])
+    zG = _z(G[:, None], g["G"].mean(axis=1)[:, None])
+    # membership: mean over individuals of the cluster-0 proportion, per home population
+    m_gpu = np.stack([Q[:, pop == p, 0].mean(axis=1) for p in range(K)], axis=1)
+    m_ref = np.stack([refQ[:, pop == p, 0].mean(axis=1) for p in range(K)], axis=1)
+    zQ = _z(m_gpu, m_ref)
+    msg = f"zS={zS} zLL={zLL} zG={zG} zQ={zQ} S_gpu={S.mean(0)} S_ref={g['S'].mean(0)} LL_gpu={LL.mean()} LL_ref={g['LL'].mean()}"
+    assert np.all(np.abs(zS) < 3.5), msg
+    assert np.all(np.abs(zLL) < 3.5), msg
+    assert np.all(np.abs(zG) < 3.5), msg
+    assert np.all(np.abs(zQ) < 3.5), msg
+    # and absolute closeness, so that a huge variance cannot hide a bias
+    assert np.all(np.abs(S.mean(0) - g["S"].mean(0)) < 0.02), msg
+    assert abs(LL.mean() - g["LL"].mean()) < 3.0, msg
