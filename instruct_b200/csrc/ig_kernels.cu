@@ -679,9 +679,16 @@ __global__ void __launch_bounds__(RED_THREADS) post_sweep_kernel(const PostArgs 
 		const double alpha = a.sc->alpha;
 		const double ralpha = alpha + draw_normal(st);
 		if (ralpha > 0.0) {
+			// The reference multiplies pow(q, alpha'+n)/pow(q, n+alpha) over all (i,k) (mcmc.c:1258).
+			// A q that underflowed to exactly 0 makes one factor 0/0 = NaN, and MIN2(1, NaN) == 1
+			// (mcmc.h:10), so the proposal is accepted.  With near-pure ancestry alpha drifts
+			// towards 0 (the ratio has no Gamma normaliser) until this happens, so the rule is
+			// what sets alpha's long-run distribution there; it is reproduced: sum log q = -inf
+			// <=> some q == 0 <=> accept.
 			const double ratio = exp((ralpha - alpha) * slq);
 			const double u = st.uniform();
-			if ((ratio != ratio) || u < fmin(1.0, ratio)) { a.sc->alpha = ralpha; a.sc->alpha_accepts++; }
+			const bool nan_accept = (slq != slq) || (slq == -INFINITY);
+			if (nan_accept || u < fmin(1.0, ratio)) { a.sc->alpha = ralpha; a.sc->alpha_accepts++; }
 		}
 	}
 }

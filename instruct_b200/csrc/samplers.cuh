@@ -32,8 +32,9 @@ IG_HD double draw_gamma(Stream &st, double a)
 		v = v * v * v;
 		const double u = st.uniform();
 		if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
-			const double r = d * v * boost;
-			return r > 1e-300 ? r : 1e-300;      // keep log q finite (update_alpha's statistic)
+			// May underflow to exactly 0 for tiny shapes, like the reference's pow(x, 1/alpha)
+			// (random.c:187): update_alpha's behaviour at q == 0 is part of the chain (see post_sweep).
+			return d * v * boost;
 		}
 	}
 	return d;
