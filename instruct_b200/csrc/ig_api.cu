@@ -12,6 +12,7 @@
 #include <string.h>
 #include <math.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ig_internal.h"
@@ -120,6 +121,8 @@ struct ig_ctx {
 	double *llparts = nullptr;
 	float *initd_dev = nullptr;
 	double *scratch = nullptr;      // small device scratch (parity hooks)
+	double *gpart = nullptr;        // partials of the cooperative grid sums
+	int32_t *state2 = nullptr;      // double buffer of UPMCMC.state (-e 0)
 	Moments mom{};
 	// host mirrors
 	std::vector<int32_t> allelenum_h;
@@ -202,7 +205,7 @@ static void free_all(ig_ctx *c)
 	cudaFree(c->Xt); cudaFree(c->Zt); cudaFree(c->P); cudaFree(c->P64); cudaFree(c->n); cudaFree(c->allelenum);
 	cudaFree(c->ind); cudaFree(c->Qf); cudaFree(c->gprop); cudaFree(c->gpair); cudaFree(c->S); cudaFree(c->state);
 	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
-	cudaFree(c->scratch);
+	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2);
 	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
 	cudaFree(c->mom.self2); cudaFree(c->mom.gen); cudaFree(c->mom.gen2); cudaFree(c->mom.freq); cudaFree(c->mom.freq2);
 	cudaFree(c->mom.convg);
@@ -249,6 +252,8 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	CK(dalloc(&c->llparts, (size_t)g.Nloc * 4));
 	CK(dalloc(&c->initd_dev, (size_t)MAX_K));
 	CK(dalloc(&c->scratch, (size_t)64));
+	CK(dalloc(&c->gpart, (size_t)2 * SC_MAX_CTAS * 20));
+	CK(dalloc(&c->state2, (size_t)MAX_K));
 	CK(dalloc(&c->mom.tot, 2));
 	CK(dalloc(&c->mom.indvlkh, (size_t)g.N));
 	CK(dalloc(&c->mom.qq, (size_t)g.N * g.K));
@@ -480,9 +485,11 @@ static ig_status phase_update_S(ig_ctx *c)
 		dp_update(c, c->ind_h);
 		CK(cudaMemcpyAsync(c->S, c->S_h.data(), (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	}
-	PreArgs a{c->ind, c->S, c->state, c->gprop, c->gpair, c->sc, c->geo, c->iter, c->key0, c->key1,
+	// UPMCMC.state is read by every CTA and written by one: double-buffered
+	PreArgs a{c->ind, c->S, c->state, c->state2, c->gprop, c->gpair, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1,
 	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl};
 	CK(launch_pre_sweep(a, c->stream));
+	if (c->cfg.mode == 2 && c->cfg.back_refl == 0) std::swap(c->state, c->state2);
 	c->launches++;
 	return IG_OK;
 }
@@ -503,7 +510,7 @@ static ig_status phase_zq(ig_ctx *c, int init)
 
 static ig_status phase_alpha(ig_ctx *c)
 {
-	PostArgs a{c->ind, c->sc, c->geo, c->iter, c->key0, c->key1};
+	PostArgs a{c->ind, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1};
 	CK(launch_post_sweep(a, c->stream));
 	c->launches++;
 	return IG_OK;
@@ -972,7 +979,7 @@ extern "C" ig_status ig_alpha_logratio(ig_ctx *c, double ralpha, double *out)
 	DevScalars keep;
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpy(&keep, c->sc, sizeof(keep), cudaMemcpyDeviceToHost));
-	PostArgs a{c->ind, c->sc, c->geo, 0xFFFFFFFFu, c->key0, c->key1};
+	PostArgs a{c->ind, c->sc, c->gpart, c->geo, 0xFFFFFFFFu, c->key0, c->key1};
 	CK(launch_post_sweep(a, c->stream));
 	DevScalars h;
 	CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

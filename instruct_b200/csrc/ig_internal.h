@@ -11,6 +11,7 @@ namespace ig {
 constexpr int TILE = 8;          // loci per micro-tile (one 128-bit Z vector, two 128-bit X vectors)
 constexpr int ZQ_THREADS = 256;  // individuals per CTA pass
 constexpr int MAX_K = 16;
+constexpr int SC_MAX_CTAS = 592;   // cooperative scalar-update kernels: at most 4 CTAs per SM
 constexpr float P_FLOOR = 1e-18f;   // keeps f0*f1 a normal fp32 number in the product accumulators
 
 // device-resident scalars of one chain
@@ -91,13 +92,14 @@ struct PArgs {
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s);
 
 struct PreArgs {
-	double *ind; double *S; int32_t *state; int32_t *gprop; int2 *gpair; DevScalars *sc;
+	double *ind; double *S; const int32_t *state_in; int32_t *state_out; int32_t *gprop; int2 *gpair; DevScalars *sc;
+	double *gpart;           // [2][SC_MAX_CTAS][20] partials of the grid-wide sums
 	Geometry geo; uint32_t iter, key0, key1; int mode, prior_flag, back_refl;
 };
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s);
 
 struct PostArgs {
-	const double *ind; DevScalars *sc; Geometry geo; uint32_t iter, key0, key1;
+	const double *ind; DevScalars *sc; double *gpart; Geometry geo; uint32_t iter, key0, key1;
 };
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
 

@@ -20,7 +20,10 @@
 #include <stdio.h>
 #include "ig_internal.h"
 #include "philox.cuh"
+#include <cooperative_groups.h>
 #include "samplers.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ig {
 
@@ -485,139 +488,239 @@ __device__ __forceinline__ double trans_prob(int from, int to)
 }
 
 // --------------------------------------------------------------------------------------
-// pre_sweep (one CTA): selfing-rate update, then the generation proposals of update_G.
-//   mode 2: update_S_POP (mcmc.c:913-983): K sequential MH steps, each a block reduction of
-//           sum_i log( s_i^(G_i-1) (1-s_i) ), s_i = sum_k Q_ik S_k  (proposal, mcmc.c:1630)
+// Deterministic grid-wide sums for the scalar updates.  The kernels below are launched
+// cooperatively (all CTAs resident).  Each CTA reduces its threads' values with a fixed
+// shuffle/shared tree and writes one partial per value; after grid.sync() every CTA adds
+// the partials in CTA order.  Fixed launch shape => fixed summation order => bit-identical
+// on every rank of a sharded chain and for every GPU count.  Partials are double-buffered
+// so one grid.sync() per reduction suffices.
+// --------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_MAXV = 20;                     // values reduced at once (K + 2 <= 18)
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// reduce nv per-thread values over the whole grid; result in out[0..nv) for every thread
+__device__ void grid_sum(cg::grid_group &grid, const double *v, int nv, double *out, double *gpart, int &phase, double *sh /*[SC_MAXV][8]*/)
+{
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	for (int j = 0; j < nv; j++) {
+		const double w = warp_sum(v[j]);
+		if (lane == 0) sh[j * 8 + wid] = w;
+	}
+	__syncthreads();
+	double *buf = gpart + (size_t)(phase & 1) * gridDim.x * SC_MAXV;
+	if (tid < nv) {
+		double t = 0.0;
+		for (int w = 0; w < SC_THREADS / 32; w++) t += sh[tid * 8 + w];
+		buf[(size_t)blockIdx.x * SC_MAXV + tid] = t;
+	}
+	__threadfence();
+	grid.sync();
+	if (tid < nv) {
+		double t = 0.0;
+		for (unsigned b = 0; b < gridDim.x; b++) t += buf[(size_t)b * SC_MAXV + tid];
+		sh[SC_MAXV * 8 + tid] = t;
+	}
+	__syncthreads();
+	for (int j = 0; j < nv; j++) out[j] = sh[SC_MAXV * 8 + j];
+	__syncthreads();
+	phase++;
+}
+
+// --------------------------------------------------------------------------------------
+// pre_sweep (cooperative grid, one thread per individual, grid-stride beyond that):
+// selfing-rate update, then the generation proposals of update_G.
+//   mode 2: update_S_POP (mcmc.c:913-983): K sequential MH steps, each a grid-wide sum of
+//           log( s_i^(G_i-1) (1-s_i) ), s_i = sum_k Q_ik S_k  (proposal, mcmc.c:1630)
 //   mode 3, uniform prior: update_S_IND (mcmc.c:864-886), independent per individual
 //   mode 3, DP prior: S was written by the host step (ig_api.cu) before this launch
 // Every rank of a sharded chain runs this redundantly on the all-gathered (Q, G): identical
-// inputs and a fixed reduction tree give identical S everywhere, so no broadcast is needed.
+// inputs and a fixed reduction order give identical S everywhere, so no broadcast is needed.
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RED_THREADS) pre_sweep_kernel(const PreArgs a)
+__global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 {
-	__shared__ double sh[RED_THREADS];
+	cg::grid_group grid = cg::this_grid();
+	__shared__ double sh[SC_MAXV * 8 + SC_MAXV];
 	__shared__ double Ssh[MAX_K];
-	__shared__ int accept_sh;
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x;
 	const int K = g.K, REC = g.REC;
+	const int gstride = gridDim.x * SC_THREADS;
+	const int i_first = blockIdx.x * SC_THREADS + tid;
+	int phase = 0;
 
 	if (a.mode == 2) {
 		if (tid < K) Ssh[tid] = a.S[tid];
 		__syncthreads();
-		// proposal() at the current S
-		double cur = 0.0;
-		{
-			double part = 0.0;
-			for (int i = tid; i < g.N; i += RED_THREADS) {
-				const double *rec = a.ind + (size_t)i * REC;
-				double s = 0.0;
-				for (int k = 0; k < K; k++) s += rec[k] * Ssh[k];
-				part += log_geom(s, (int)rec[K + 2]);
-			}
-			cur = block_sum(part, sh);
+		double Sl[MAX_K];
+		for (int k = 0; k < K; k++) Sl[k] = Ssh[k];
+		double cur, part = 0.0;
+		for (int i = i_first; i < g.N; i += gstride) {
+			const double *rec = a.ind + (size_t)i * REC;
+			double s = 0.0;
+			for (int k = 0; k < K; k++) s += rec[k] * Sl[k];
+			part += log_geom(s, (int)rec[K + 2]);
 		}
+		grid_sum(grid, &part, 1, &cur, a.gpart, phase, sh);
+		int accepts = 0;
 		for (int j = 0; j < K; j++) {
 			Stream st((uint32_t)j, 0u, a.iter, TAG_SPOP, a.key0, a.key1);
 			double prop;
 			int new_state = 1;
-			const double sj = Ssh[j];
+			const int cs = (a.back_refl == 0) ? a.state_in[j] : 1;
+			const double sj = Sl[j];
 			if (a.back_refl == 1) {                         // mcmc.c:939-945
 				prop = sj + (st.uniform() * 2.0 * 0.05 - 0.05);
 				if (prop <= 0.0) prop = -prop;
 				else if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
 			} else {                                        // adpt_indp, mcmc.c:1461-1520
-				const int cs = a.state[j];
 				const double u = st.uniform();
 				if (cs == 0) { if (u < 0.5) { prop = 0.0; new_state = 0; } else { prop = st.uniform(); new_state = 1; } }
 				else if (cs == 2) { if (u < 0.5) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
 				else { if (u <= 0.05) { prop = 0.0; new_state = 0; } else if (u >= 0.95) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
 			}
-			double part = 0.0;
-			for (int i = tid; i < g.N; i += RED_THREADS) {
+			part = 0.0;
+			for (int i = i_first; i < g.N; i += gstride) {
 				const double *rec = a.ind + (size_t)i * REC;
 				double s = 0.0;
-				for (int k = 0; k < K; k++) s += rec[k] * ((k == j) ? prop : Ssh[k]);
+				for (int k = 0; k < K; k++) s += rec[k] * ((k == j) ? prop : Sl[k]);
 				part += log_geom(s, (int)rec[K + 2]);
 			}
-			const double pl = block_sum(part, sh);
-			if (tid == 0) {
-				double ratio = exp(pl - cur);
-				if (a.back_refl == 0) ratio *= trans_prob(a.state[j], new_state) / trans_prob(new_state, a.state[j]);
-				const double u = st.uniform();
-				// MIN2(1, NaN) == 1 in the reference (mcmc.h:10): a NaN ratio accepts
-				accept_sh = (ratio != ratio) ? 1 : (u < fmin(1.0, ratio));
-			}
-			__syncthreads();
-			if (accept_sh) {
+			double pl;
+			grid_sum(grid, &part, 1, &pl, a.gpart, phase, sh);
+			// every thread of every CTA takes the same decision from the same numbers
+			double ratio = exp(pl - cur);
+			if (a.back_refl == 0) ratio *= trans_prob(cs, new_state) / trans_prob(new_state, cs);
+			const double u = st.uniform();
+			// MIN2(1, NaN) == 1 in the reference (mcmc.h:10): a NaN ratio accepts
+			const bool acc = (ratio != ratio) || (u < fmin(1.0, ratio));
+			if (acc) {
 				cur = pl;
-				if (tid == 0) { Ssh[j] = prop; a.S[j] = prop; if (a.back_refl == 0) a.state[j] = new_state; a.sc->s_accepts++; }
-			}
-			__syncthreads();
+				Sl[j] = prop;
+				accepts++;
+				if (blockIdx.x == 0 && tid == 0) { a.S[j] = prop; if (a.back_refl == 0) a.state_out[j] = new_state; }
+			} else if (blockIdx.x == 0 && tid == 0 && a.back_refl == 0) a.state_out[j] = cs;
 		}
-		if (tid == 0) a.sc->cur_prop_ll = cur;
-	} else if (a.mode == 3 && a.prior_flag == 0) {
-		for (int i = tid; i < g.N; i += RED_THREADS) {
+		if (blockIdx.x == 0 && tid == 0) { a.sc->cur_prop_ll = cur; a.sc->s_accepts += accepts; }
+		// ---- generation proposals with the UPDATED S (update_G follows update_S_POP, mcmc.c:211-212)
+		for (int i = i_first; i < g.N; i += gstride) {
+			const double *rec = a.ind + (size_t)i * REC;
+			double s = 0.0;
+			for (int k = 0; k < K; k++) s += rec[k] * Sl[k];
+			const int stt = sel_state(s);
+			int gp;
+			if (stt == 1) {
+				Stream st((uint32_t)i, 0u, a.iter, TAG_GPROP, a.key0, a.key1);
+				const double v = floor(log(st.uniform()) / log(s)) + 1.0;    // rgeom(1 - s), random.c:311-321
+				gp = (v < 1.0) ? 1 : (v > 50.0 ? 50 : (int)v);
+			} else gp = (stt == 0) ? 1 : 50;
+			a.gprop[i] = gp;
+			const int il = i - g.i0;
+			if (il >= 0 && il < g.Nloc) a.gpair[il] = make_int2((int)rec[K + 2], gp);
+		}
+		return;
+	}
+	// ---- mode 3
+	for (int i = i_first; i < g.N; i += gstride) {
+		double s = a.S[i];
+		const int gen = (int)a.ind[(size_t)i * REC + K + 2];
+		if (a.prior_flag == 0) {                             // update_S_IND, mcmc.c:864-886
 			Stream st((uint32_t)i, 0u, a.iter, TAG_SIND, a.key0, a.key1);
-			const double s = a.S[i];
-			const int gen = (int)a.ind[(size_t)i * REC + K + 2];
 			double prop = s + (st.uniform() * 2.0 * 0.05 - 0.05);
 			if (prop <= 0.0) prop = -prop;
 			if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
 			const double ratio = exp(log_geom(prop, gen) - log_geom(s, gen));
 			const double u = st.uniform();
-			if ((ratio != ratio) || u < fmin(1.0, ratio)) a.S[i] = prop;
+			if ((ratio != ratio) || u < fmin(1.0, ratio)) { s = prop; a.S[i] = prop; }
 		}
-	}
-	__syncthreads();
-	// ---- generation proposals (update_G, mcmc.c:1062-1084): independence proposal from Geom(1 - s_i)
-	for (int i = tid; i < g.N; i += RED_THREADS) {
-		const double *rec = a.ind + (size_t)i * REC;
-		double s = 0.0;
-		if (a.mode == 2) { for (int k = 0; k < K; k++) s += rec[k] * Ssh[k]; }
-		else s = a.S[i];
 		const int stt = sel_state(s);
 		int gp;
 		if (stt == 1) {
 			Stream st((uint32_t)i, 0u, a.iter, TAG_GPROP, a.key0, a.key1);
-			const double u = st.uniform();
-			const double v = floor(log(u) / log(s)) + 1.0;           // rgeom(1 - s), random.c:311-321
+			const double v = floor(log(st.uniform()) / log(s)) + 1.0;
 			gp = (v < 1.0) ? 1 : (v > 50.0 ? 50 : (int)v);
 		} else gp = (stt == 0) ? 1 : 50;
 		a.gprop[i] = gp;
 		const int il = i - g.i0;
-		if (il >= 0 && il < g.Nloc) a.gpair[il] = make_int2((int)rec[K + 2], gp);
+		if (il >= 0 && il < g.Nloc) a.gpair[il] = make_int2(gen, gp);
 	}
 }
+
+static int coop_grid(const void *kernel, int n_items, int device)
+{
+	int per_sm = 1, sms = 148;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SC_THREADS, 0);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	int want = (n_items + SC_THREADS - 1) / SC_THREADS;
+	int cap = per_sm * sms;
+	if (cap > SC_MAX_CTAS) cap = SC_MAX_CTAS;
+	if (want < 1) want = 1;
+	return want < cap ? want : cap;
+}
+
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
 {
-	pre_sweep_kernel<<<1, RED_THREADS, 0, s>>>(a);
-	return cudaGetLastError();
+	static int grid_cache_n = -1, grid_cache = 0;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (grid_cache_n != a.geo.N) { grid_cache = coop_grid((const void *)pre_sweep_kernel, a.geo.N, dev); grid_cache_n = a.geo.N; }
+	void *args[] = {(void *)&a};
+	return cudaLaunchCooperativeKernel((const void *)pre_sweep_kernel, dim3(grid_cache), dim3(SC_THREADS), args, 0, s);
 }
 
 // --------------------------------------------------------------------------------------
-// indiv_epilogue: one thread per local individual.  Combines the per-chunk partials in
-// chunk order, takes the update_G accept decision (mcmc.c:1085-1089), draws
+// indiv_epilogue: CTA = 32 individuals (lanes) x 8 chunk groups (warps).  Warp w adds the
+// partials of chunks w, w+8, ... (coalesced across the 32 individuals), warp 0 then adds the
+// 8 group sums in group order, takes the update_G accept decision (mcmc.c:1085-1089), draws
 // Q_i ~ Dirichlet(cnt_i + alpha) (mcmc.c:1196-1198) and writes the individual's record
-// (Q, indvlkh, sum_k log q, G) into the all-gatherable array.
+// (Q, indvlkh, sum_k log q, G) into the all-gatherable array.  The summation order depends
+// only on the chunk decomposition, which depends only on (L, K, A): shard-invariant.
 // --------------------------------------------------------------------------------------
-__global__ void indiv_epilogue_kernel(const EpiArgs a)
+constexpr int EPI_GROUPS = 8;
+__global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const EpiArgs a)
 {
+	__shared__ int cnt_sh[EPI_GROUPS][MAX_K][32];
+	__shared__ double ll_sh[EPI_GROUPS][4][32];
 	const Geometry &g = a.geo;
-	const int il = blockIdx.x * blockDim.x + threadIdx.x;
-	if (il >= g.Nloc) return;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int il = blockIdx.x * 32 + lane;
 	const int K = g.K, KP = g.KP;
+	const bool live = il < g.Nloc;
 	int cnt[MAX_K];
-	for (int k = 0; k < K; k++) cnt[k] = 0;
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
 	double d_old = 0.0, c_new = 0.0, a_new = 0.0, b_new = 0.0;
-	for (int c = 0; c < g.nchunks; c++) {
-		const uint16_t *pc = a.pcnt + ((size_t)c * g.Nloc + il) * KP;
-		for (int k = 0; k < K; k++) cnt[k] += pc[k];
-		const double *pl = a.plog + (size_t)c * 4 * g.Nloc + il;
-		d_old += pl[0];
-		c_new += pl[(size_t)g.Nloc];
-		a_new += pl[(size_t)2 * g.Nloc];
-		b_new += pl[(size_t)3 * g.Nloc];
+	if (live) {
+		for (int c = w; c < g.nchunks; c += EPI_GROUPS) {
+			const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.pcnt + ((size_t)c * g.Nloc + il) * KP);
+#pragma unroll
+			for (int j = 0; j < MAX_K / 2; j++)
+				if (2 * j < KP) { const uint32_t v = pc[j]; cnt[2 * j] += v & 0xFFFFu; cnt[2 * j + 1] += v >> 16; }
+			const double *pl = a.plog + (size_t)c * 4 * g.Nloc + il;
+			d_old += pl[0];
+			c_new += pl[(size_t)g.Nloc];
+			a_new += pl[(size_t)2 * g.Nloc];
+			b_new += pl[(size_t)3 * g.Nloc];
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) cnt_sh[w][k][lane] = cnt[k];
+	ll_sh[w][0][lane] = d_old; ll_sh[w][1][lane] = c_new; ll_sh[w][2][lane] = a_new; ll_sh[w][3][lane] = b_new;
+	__syncthreads();
+	if (w != 0 || !live) return;
+	d_old = c_new = a_new = b_new = 0.0;
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
+	for (int ww = 0; ww < EPI_GROUPS; ww++) {
+#pragma unroll
+		for (int k = 0; k < MAX_K; k++) cnt[k] += cnt_sh[ww][k][lane];
+		d_old += ll_sh[ww][0][lane]; c_new += ll_sh[ww][1][lane]; a_new += ll_sh[ww][2][lane]; b_new += ll_sh[ww][3][lane];
 	}
 	const int ig_global = g.i0 + il;
 	double *rec = a.ind + (size_t)ig_global * g.REC;
@@ -634,68 +737,83 @@ __global__ void indiv_epilogue_kernel(const EpiArgs a)
 	const double alpha = a.sc->alpha;
 	Stream sq((uint32_t)ig_global, 0u, a.iter, TAG_Q, a.key0, a.key1);
 	double qv[MAX_K], sum = 0.0;
-	for (int k = 0; k < K; k++) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++)
+		if (k < K) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
 	double slq = 0.0;
-	for (int k = 0; k < K; k++) {
-		const double qk = qv[k] / sum;
-		rec[k] = qk;
-		slq += log(qk);
-		a.Qf[(size_t)il * KP + k] = (float)qk;
-		a.cnt[(size_t)il * K + k] = cnt[k];
-	}
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++)
+		if (k < K) {
+			const double qk = qv[k] / sum;
+			rec[k] = qk;
+			slq += log(qk);
+			a.Qf[(size_t)il * KP + k] = (float)qk;
+			a.cnt[(size_t)il * K + k] = cnt[k];
+		}
 	for (int k = K; k < KP; k++) a.Qf[(size_t)il * KP + k] = 0.0f;
 	rec[K + 1] = slq;
 }
 cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s)
 {
-	indiv_epilogue_kernel<<<(a.geo.Nloc + 127) / 128, 128, 0, s>>>(a);
+	indiv_epilogue_kernel<<<(a.geo.Nloc + 31) / 32, 32 * EPI_GROUPS, 0, s>>>(a);
 	return cudaGetLastError();
 }
 
 // --------------------------------------------------------------------------------------
-// post_sweep (one CTA): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
+// post_sweep (cooperative grid): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
 // (update_alpha, mcmc.c:1244-1263, in log form: (alpha'-alpha) * sum log q), and the
-// column sums of Q for check_empty_cluster (mcmc.c:1954-1961).
+// column sums of Q for check_empty_cluster (mcmc.c:1954-1961) -- one grid-wide sum of
+// K + 2 values.
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RED_THREADS) post_sweep_kernel(const PostArgs a)
+__global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a)
 {
-	__shared__ double sh[RED_THREADS];
+	cg::grid_group grid = cg::this_grid();
+	__shared__ double sh[SC_MAXV * 8 + SC_MAXV];
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x, K = g.K, REC = g.REC;
-	double pl = 0.0, ps = 0.0;
-	for (int i = tid; i < g.N; i += RED_THREADS) { pl += a.ind[(size_t)i * REC + K]; ps += a.ind[(size_t)i * REC + K + 1]; }
-	const double tot = block_sum(pl, sh);
-	const double slq = block_sum(ps, sh);
-	for (int k = 0; k < K; k++) {
-		double pq = 0.0;
-		for (int i = tid; i < g.N; i += RED_THREADS) pq += a.ind[(size_t)i * REC + k];
-		const double cs = block_sum(pq, sh);
-		if (tid == 0) a.sc->qcol[k] = cs;
+	const int gstride = gridDim.x * SC_THREADS;
+	double v[SC_MAXV], tot[SC_MAXV];
+#pragma unroll
+	for (int j = 0; j < SC_MAXV; j++) v[j] = 0.0;
+	for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) {
+		const double *rec = a.ind + (size_t)i * REC;
+		v[0] += rec[K];
+		v[1] += rec[K + 1];
+#pragma unroll
+		for (int k = 0; k < MAX_K; k++) if (k < K) v[2 + k] += rec[k];
 	}
-	if (tid == 0) {
-		a.sc->totallkh = tot;
-		a.sc->sumlogq = slq;
-		Stream st(0u, 0u, a.iter, TAG_ALPHA, a.key0, a.key1);
-		const double alpha = a.sc->alpha;
-		const double ralpha = alpha + draw_normal(st);
-		if (ralpha > 0.0) {
-			// The reference multiplies pow(q, alpha'+n)/pow(q, n+alpha) over all (i,k) (mcmc.c:1258).
-			// A q that underflowed to exactly 0 makes one factor 0/0 = NaN, and MIN2(1, NaN) == 1
-			// (mcmc.h:10), so the proposal is accepted.  With near-pure ancestry alpha drifts
-			// towards 0 (the ratio has no Gamma normaliser) until this happens, so the rule is
-			// what sets alpha's long-run distribution there; it is reproduced: sum log q = -inf
-			// <=> some q == 0 <=> accept.
-			const double ratio = exp((ralpha - alpha) * slq);
-			const double u = st.uniform();
-			const bool nan_accept = (slq != slq) || (slq == -INFINITY);
-			if (nan_accept || u < fmin(1.0, ratio)) { a.sc->alpha = ralpha; a.sc->alpha_accepts++; }
-		}
+	int phase = 0;
+	grid_sum(grid, v, K + 2, tot, a.gpart, phase, sh);
+	if (blockIdx.x != 0 || tid != 0) return;
+	const double slq = tot[1];
+	a.sc->totallkh = tot[0];
+	a.sc->sumlogq = slq;
+	for (int k = 0; k < K; k++) a.sc->qcol[k] = tot[2 + k];
+	if (a.iter == 0xFFFFFFFFu) return;                      // statistics only (parity hook)
+	Stream st(0u, 0u, a.iter, TAG_ALPHA, a.key0, a.key1);
+	const double alpha = a.sc->alpha;
+	const double ralpha = alpha + draw_normal(st);
+	if (ralpha > 0.0) {
+		// The reference multiplies pow(q, alpha'+n)/pow(q, n+alpha) over all (i,k) (mcmc.c:1258).
+		// A q that underflowed to exactly 0 makes one factor 0/0 = NaN, and MIN2(1, NaN) == 1
+		// (mcmc.h:10), so the proposal is accepted.  With near-pure ancestry alpha drifts
+		// towards 0 (the ratio has no Gamma normaliser) until this happens, so the rule is
+		// what sets alpha's long-run distribution there; it is reproduced: sum log q = -inf
+		// <=> some q == 0 <=> accept.
+		const double ratio = exp((ralpha - alpha) * slq);
+		const double u = st.uniform();
+		const bool nan_accept = (slq != slq) || (slq == -INFINITY);
+		if (nan_accept || u < fmin(1.0, ratio)) { a.sc->alpha = ralpha; a.sc->alpha_accepts++; }
 	}
 }
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s)
 {
-	post_sweep_kernel<<<1, RED_THREADS, 0, s>>>(a);
-	return cudaGetLastError();
+	static int grid_cache_n = -1, grid_cache = 0;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (grid_cache_n != a.geo.N) { grid_cache = coop_grid((const void *)post_sweep_kernel, a.geo.N, dev); grid_cache_n = a.geo.N; }
+	void *args[] = {(void *)&a};
+	return cudaLaunchCooperativeKernel((const void *)post_sweep_kernel, dim3(grid_cache), dim3(SC_THREADS), args, 0, s);
 }
 
 // --------------------------------------------------------------------------------------
