@@ -461,7 +461,7 @@ static ZQArgs zq_args(ig_ctx *c)
 	a.Xt = c->Xt; a.Zt = c->Zt; a.P = c->P; a.n = c->n; a.Qf = c->Qf; a.gpair = c->gpair;
 	a.pcnt = c->pcnt; a.plog = c->plog; a.geo = c->geo; a.iter = c->iter; a.key0 = c->key0; a.key1 = c->key1;
 	a.type_freq = c->cfg.type_freq;
-	a.k512 = 512u;
+	a.k512 = 512u; a.k_mant = 0x007fffffu; a.k_one = 0x3f800000u;
 	return a;
 }
 

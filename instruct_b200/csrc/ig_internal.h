@@ -64,7 +64,7 @@ struct ZQArgs {
 	uint32_t iter;
 	uint32_t key0, key1;
 	int type_freq;
-	uint32_t k512;           // the constant 512, kept in a register on purpose (see LogProd::mul)
+	uint32_t k512, k_mant, k_one;   // 512, 0x007fffff, 0x3f800000 kept in registers on purpose (see LogProd::mul)
 };
 
 // ---- launchers (ig_kernels.cu) -------------------------------------------------------

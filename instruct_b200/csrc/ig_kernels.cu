@@ -93,17 +93,23 @@ __device__ __forceinline__ void stg_stream(int4 *p, const int4 &v)
 // the factors' biased exponents, and takes one logarithm per (individual, chunk).  Relative
 // error of an n-term product is <= n * 2^-24, i.e. an ABSOLUTE error <= 6e-8 * n on a
 // log-likelihood of magnitude ~n: relative ~1e-7, inside the 1e-6 gate of BASELINE.json.
+// constants that must live in registers: ptxas turns a literal 512 into LEA.HI (ALU pipe) and
+// splits an and-or with two literals into two LOP3; kernel-argument values stay IMAD.HI / one LOP3
+struct LogProdConst { uint32_t k512, mant, one; };
+
 struct LogProd {
 	float m;
 	int e;        // sum of biased exponents; value() removes 127 per multiplication
 	__device__ __forceinline__ void init() { m = 1.0f; e = 0; }
 	// k512 is the constant 512 passed as a kernel argument: ptxas strength-reduces a literal
 	// power-of-two multiplier to LEA.HI (ALU pipe), a register operand stays an IMAD.HI
-	__device__ __forceinline__ void mul(float t, uint32_t k512)
+	__device__ __forceinline__ void mul(float t, const LogProdConst &k)
 	{
 		const uint32_t b = __float_as_uint(t);
-		asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(e) : "r"(b), "r"(k512));       // e += b >> 23 on the FMA pipe
-		m *= __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+		uint32_t mb;
+		asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(e) : "r"(b), "r"(k.k512));     // e += b >> 23 on the FMA pipe
+		asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mb) : "r"(b), "r"(k.mant), "r"(k.one));   // (b & mant) | one, one LOP3
+		m *= __uint_as_float(mb);
 	}
 	__device__ __forceinline__ void renorm()
 	{
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 	const int sub1 = min(sub0 + g.subs_per_blk, nsub_total);
 	int *hist_t = hist + (tid & (R - 1));           // this lane's replica column
 	int *cnt_t = cntsm + tid;                       // this thread's counter column
-	const uint32_t k512 = a.k512;
+	const LogProdConst k512{a.k512, a.k_mant, a.k_one};
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		const int il = sub * ZQ_THREADS + tid;
@@ -214,8 +220,10 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 			const float omh_p = (gg.y <= 127) ? __int_as_float((128 - gg.y) << 23) : 0.0f;
 			const float h_g = 1.0f - omh_g, h_p = 1.0f - omh_p;
 
-			LogProd Cn, An, Bn, Ao, Bo;
-			Cn.init(); An.init(); Bn.init(); Ao.init(); Bo.init();
+			// new Z: D_g = prod T_g, T_g = f (h_g + f (1-h_g)) for same-z homozygotes, f0 f1 otherwise
+			// old Z: only the ratio B/A over same-z homozygotes enters update_G's accept
+			LogProd An, Bn, Ao, Bo;
+			An.init(); Bn.init(); Ao.init(); Bo.init();
 			int nhet = 0, nsh_new = 0, nsh_old = 0;
 
 			const int4 *xp = reinterpret_cast<const int4 *>(a.Xt) + ((size_t)mt0 * Nloc + il) * 2;
@@ -223,14 +231,12 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 			const size_t xstride = (size_t)Nloc * 2, zstride = (size_t)Nloc;
 			const uint32_t ig_global = (uint32_t)(g.i0 + il);
 
-			int4 xa_n = ldg_stream(xp), xb_n = ldg_stream(xp + 1), zz_n = ldg_rw(zp);
+			// No software prefetch: a micro-tile is ~1300 instructions per warp, so with four
+			// resident warps per scheduler the ~1 us load latency of one warp hides behind the
+			// other three; rotating prefetch registers cost 7 instructions per genotype.
 			for (int mt = 0; mt < nmt; ++mt) {
-				const int4 xa = xa_n, xb = xb_n, zz = zz_n;
-				if (mt + 1 < nmt) {
-					xa_n = ldg_stream(xp + (size_t)(mt + 1) * xstride);
-					xb_n = ldg_stream(xp + (size_t)(mt + 1) * xstride + 1);
-					zz_n = ldg_rw(zp + (size_t)(mt + 1) * zstride);
-				}
+				const int4 xa = ldg_stream(xp + (size_t)mt * xstride), xb = ldg_stream(xp + (size_t)mt * xstride + 1);
+				const int4 zz = ldg_rw(zp + (size_t)mt * zstride);
 				const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 				const uint32_t zwo[4] = {(uint32_t)zz.x, (uint32_t)zz.y, (uint32_t)zz.z, (uint32_t)zz.w};
 				uint32_t zwn[4];
@@ -288,9 +294,8 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 							if (TF0) { f0 = c0[KP - 1]; f1 = c1[KP - 1]; same_n = true; }   // mcmc.c:1739-1749
 							else { f0 = Psm[row0 + z0]; f1 = Psm[row1 + z1]; same_n = (z0 == z1); }
 							const bool sh_n = same_n && !het;
-							Cn.mul(f0 * (sh_n ? 1.0f : f1), k512);
-							An.mul(sh_n ? fmaf(f0, omh_g, h_g) : 1.0f, k512);
-							Bn.mul(sh_n ? fmaf(f0, omh_p, h_p) : 1.0f, k512);
+							An.mul(f0 * (sh_n ? fmaf(f0, omh_g, h_g) : f1), k512);
+							Bn.mul(f0 * (sh_n ? fmaf(f0, omh_p, h_p) : f1), k512);
 							nhet += het ? 1 : 0;
 							nsh_new += (same_n && het) ? 1 : 0;
 							pair[h2] = (uint32_t)(z1 * 256 + z0);
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 					zwn[pr] = pair[1] * 65536u + pair[0];
 				}
 				stg_stream(zp + (size_t)mt * zstride, make_int4((int)zwn[0], (int)zwn[1], (int)zwn[2], (int)zwn[3]));
-				if ((mt & 7) == 7) { Cn.renorm(); An.renorm(); Bn.renorm(); Ao.renorm(); Bo.renorm(); }
+				if ((mt & 7) == 7) { An.renorm(); Bn.renorm(); Ao.renorm(); Bo.renorm(); }
 			}
 			// ---- partials of this (chunk, individual)
 			{
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
 				if (TF0) d_old = (lb - la) - (double)nsh_new * (double)(gg.y - gg.x) * LN2_D;
 				else d_old = (Bo.value(nmul) - Ao.value(nmul)) - (double)nsh_old * (double)(gg.y - gg.x) * LN2_D;
 				pl[0] = d_old;
-				pl[(size_t)Nloc] = Cn.value(nmul) + (double)nhet * LN2_D;
+				pl[(size_t)Nloc] = (double)nhet * LN2_D;
 				pl[(size_t)2 * Nloc] = la - (double)nsh_new * (double)(gg.x - 1) * LN2_D;
 				pl[(size_t)3 * Nloc] = lb - (double)nsh_new * (double)(gg.y - 1) * LN2_D;
 			}
