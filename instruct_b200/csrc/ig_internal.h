@@ -10,6 +10,7 @@ namespace ig {
 
 constexpr int TILE = 8;          // loci per micro-tile (one 128-bit Z vector, two 128-bit X vectors)
 constexpr int ZQ_THREADS = 256;  // individuals per CTA pass
+constexpr int ZQ_MIN_CTAS = 2;   // resident CTAs per SM the sweep kernel is compiled and sized for
 constexpr int MAX_K = 16;
 constexpr int SC_MAX_CTAS = 592;   // cooperative scalar-update kernels: at most 4 CTAs per SM
 constexpr float P_FLOOR = 1e-18f;   // keeps f0*f1 a normal fp32 number in the product accumulators

@@ -163,7 +163,7 @@ __device__ __forceinline__ int pick_category(const float (&c)[KP], float ub)
 //   output  : per (chunk, individual) partials: K counts (u16) + 4 log-likelihood pieces
 // --------------------------------------------------------------------------------------
 template <int KP, int ROUNDS, bool TF0>
-__global__ void __launch_bounds__(ZQ_THREADS, 2) zq_sweep_kernel(const ZQArgs a)
+__global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const ZQArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bar;
@@ -376,9 +376,9 @@ cudaError_t zq_configure(Geometry &g, int device)
 	int sms = 148, smem_optin = 227 * 1024;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
 	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-	const int target_ctas = 4 * sms;                       // two resident CTAs per SM, two waves
+	const int target_ctas = 2 * ZQ_MIN_CTAS * sms;         // ZQ_MIN_CTAS resident CTAs per SM, two waves
 	const size_t cnt_bytes = (size_t)g.KP * ZQ_THREADS * sizeof(int);
-	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / 2 - 2048 - cnt_bytes;   // two CTAs per SM
+	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / ZQ_MIN_CTAS - 2048 - cnt_bytes;
 	const size_t per_locus = (size_t)g.A * g.KP * 4;
 	const int nsub_total = (g.Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
 	int R = 8;
