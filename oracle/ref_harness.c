@@ -291,3 +291,42 @@ int refh_mcmc_updating(REFH *h, long update, long burnin, int thinning, int ckre
 	free_chain(&c, *d);
 	return 0;
 }
+
+/* ---- the reference's result writer on given CHAIN moments (result_analysis.c:34), for the
+ *      byte-parity test of instruct_b200/host/writer.c.  Labels are "ind<i>", pre-defined
+ *      populations "pop<p>". ------------------------------------------------------------- */
+double refh_chain_stat(REFH *h, const char *outfile, int label, int popdata, int distr_fmt, const int *popindx,
+                       int pop_count, const int *missvec, const char *chn_name, double tot, double tot2,
+                       const double *indvlkh, const double *qq, const double *qq2, const double *self,
+                       const double *self2, const double *gen, const double *gen2)
+{
+	SEQDATA d = h->data;
+	CHAIN c;
+	int i, k, ns = (d.mode == 3) ? d.totalsize : d.popnum;
+	double dic;
+	d.label = label; d.popdata = popdata; d.distr_fmt = distr_fmt; d.print_freq = 0; d.pop_count = pop_count;
+	d.indvname = cmatrix(0, d.totalsize, 0, 99);      /* one spare row: print_S_INDV reads indvname[N] (App. B #2) */
+	for (i = 0; i <= d.totalsize; i++) sprintf(d.indvname[i], "ind%d", i);
+	d.poptype = (char **)malloc((pop_count + 1) * sizeof(char *));
+	for (i = 0; i < pop_count; i++) { d.poptype[i] = (char *)malloc(32); sprintf(d.poptype[i], "pop%d", i); }
+	d.popindx = refh_slack_ivector(0, d.totalsize - 1);
+	d.missvec = refh_slack_ivector(0, d.totalsize - 1);
+	for (i = 0; i < d.totalsize; i++) { d.popindx[i] = popindx[i]; d.missvec[i] = missvec[i]; }
+	memset(&c, 0, sizeof(c));
+	c.name_len = (int)strlen(chn_name) + 1;
+	c.chn_name = cvector(0, c.name_len - 1);
+	memcpy(c.chn_name, chn_name, c.name_len);
+	c.steps = 10; c.totallkh = tot; c.totallkh2 = tot2;
+	c.indvlkh = dvector(0, d.totalsize - 1);
+	c.qq = dmatrix(0, d.totalsize - 1, 0, d.popnum - 1); c.qq2 = dmatrix(0, d.totalsize - 1, 0, d.popnum - 1);
+	c.self_rates = dvector(0, ns); c.self_rates2 = dvector(0, ns);
+	c.gen = dvector(0, d.totalsize - 1); c.gen2 = dvector(0, d.totalsize - 1);
+	for (i = 0; i < d.totalsize; i++) {
+		c.indvlkh[i] = indvlkh[i]; c.gen[i] = gen[i]; c.gen2[i] = gen2[i];
+		for (k = 0; k < d.popnum; k++) { c.qq[i][k] = qq[(long)i * d.popnum + k]; c.qq2[i][k] = qq2[(long)i * d.popnum + k]; }
+	}
+	for (i = 0; i < ns; i++) { c.self_rates[i] = self[i]; c.self_rates2[i] = self2[i]; }
+	c.self_rates[ns] = 0; c.self_rates2[ns] = 0;
+	dic = chain_stat((char *)outfile, c, d, 0);
+	return dic;
+}

@@ -1,0 +1,58 @@
+"""End-to-end drop-in check of the host program: `inbreed` (GPU) and the compiled reference
+`InStruct` (CPU) are run on the same file with the same flags; the result files must have
+the same banner bytes and the same table structure, and agree numerically within MCMC noise."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from instruct_b200.synth import make_dataset, write_reference_text
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INBREED = os.path.join(ROOT, "instruct_b200", "host", "inbreed")
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "InStruct")
+
+
+def _floats(line):
+    return [float(v) for v in re.findall(r"-?\d+\.\d+", line)]
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built")
+def test_cli_matches_reference_program(tmp_path):
+    assert os.path.exists(INBREED), "build the host program: make -C instruct_b200/host"
+    d = make_dataset(N=120, L=12, K=2, A=6, miss=0.03, seed=2024, pure=True)
+    data = str(tmp_path / "geno.txt")
+    write_reference_text(data, d.x, pop=d.pop)
+    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "2", "-u", "3000", "-b", "1000", "-t", "5", "-c", "2",
+             "-v", "2", "-f", "0", "-g", "1", "-r", "10", "-pi", "0", "-s", "13", "4", "1972"]
+    outs = {}
+    for name, exe, extra in (("ref", REFBIN, []), ("gpu", INBREED, ["--quiet-data"])):
+        out = str(tmp_path / f"{name}.out")
+        p = subprocess.run([exe, "-d", data, "-o", out] + flags + extra, capture_output=True, text=True, timeout=600,
+                           cwd=str(tmp_path))
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        assert "THE JOB IS SUCCESSFULLY FINISHED" in p.stdout
+        outs[name] = open(out, "rb").read()
+    # ---- banner: identical bytes apart from the echoed command line
+    def banner(t):
+        t = t[: t.index(b"Chain#1")]
+        return re.sub(rb"Command line arguments:\n.*\n", b"", t)
+    assert banner(outs["ref"]) == banner(outs["gpu"])
+    # ---- same sequence of section headers and the same number of table rows
+    def skeleton(t):
+        return [re.sub(rb"-?\d+\.\d+", b"#", ln) for ln in t[t.index(b"Chain#1"):].split(b"\n")
+                if not ln.startswith(b"The Gelman-Rubin")]
+    sr, sg = skeleton(outs["ref"]), skeleton(outs["gpu"])
+    assert len(sr) == len(sg)
+    assert sum(a == b for a, b in zip(sr, sg)) > 0.97 * len(sr)      # a few rows differ in a printed digit count only
+    # ---- numbers: selfing rates and log-likelihood of both chains agree with the reference's
+    def selfing(t):
+        rows = [ln for ln in t.decode(errors="ignore").split("\n") if ln.startswith("Cluster ")]
+        return np.array([_floats(r)[0] for r in rows]).reshape(2, 2)
+    def loglik(t):
+        return np.array([_floats(ln)[0] for ln in t.decode(errors="ignore").split("\n") if "Posterior Mean" in ln])
+    assert np.abs(selfing(outs["ref"]).mean(0) - selfing(outs["gpu"]).mean(0)).max() < 0.08
+    assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 15.0

@@ -1,0 +1,173 @@
+"""The C host side (instruct_b200/host): the packer against the reference's own text reader,
+and the result-file writer against the reference's own chain_stat(), byte for byte.
+CPU-only (the reference lives in oracle/_ref, built from /root/reference by oracle/Makefile)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from instruct_b200.synth import make_dataset
+from oracle import pyoracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "instruct_b200", "host")
+HOST_SO = os.path.join(HOST, "libinbreed_host.so")
+
+pytestmark = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+
+
+class GsOptions(C.Structure):
+    _fields_ = [("ploid", C.c_int), ("totalsize", C.c_int), ("locinum", C.c_int), ("missing", C.c_char_p),
+                ("label", C.c_int), ("popdata", C.c_int), ("n_extra_col", C.c_int), ("markername_flag", C.c_int),
+                ("datafmt", C.c_int), ("quiet", C.c_int)]
+
+
+class GsStore(C.Structure):
+    _fields_ = [("ploid", C.c_int), ("totalsize", C.c_int), ("locinum", C.c_int), ("locinum_file", C.c_int),
+                ("allelenum_max", C.c_int), ("x", C.POINTER(C.c_int16)), ("allelenum", C.POINTER(C.c_int32)),
+                ("alleletype", C.c_void_p), ("locus_of", C.POINTER(C.c_int)), ("marker_names", C.c_void_p),
+                ("indvname", C.POINTER(C.c_char_p)), ("popindx", C.POINTER(C.c_int)), ("poptype", C.POINTER(C.c_char_p)),
+                ("pop_count", C.c_int), ("extra_col", C.c_void_p), ("n_extra_col", C.c_int), ("missvec", C.POINTER(C.c_int))]
+
+
+class WrRun(C.Structure):
+    _fields_ = [("datafilename", C.c_char_p), ("initialfilename", C.c_char_p), ("missingdata", C.c_char_p)] + \
+               [(n, C.c_int) for n in ("chainnum", "thinning", "ploid", "autopoly", "totalsize", "locinum", "popnum", "mode",
+                                       "inf_K", "prior_flag", "back_refl", "print_freq", "GR_flag", "ckrep", "distr_fmt",
+                                       "label", "popdata", "markername_flag")] + \
+               [("update", C.c_long), ("burnin", C.c_long), ("siglevel", C.c_double), ("alpha_dpm", C.c_double)]
+
+
+class WrData(C.Structure):
+    _fields_ = [("indvname", C.POINTER(C.c_char_p)), ("poptype", C.POINTER(C.c_char_p)), ("marker_names", C.c_void_p),
+                ("alleletype", C.c_void_p), ("popindx", C.POINTER(C.c_int)), ("missvec", C.POINTER(C.c_int)),
+                ("allelenum", C.POINTER(C.c_int)), ("pop_count", C.c_int), ("allelenum_max", C.c_int)]
+
+
+class WrChain(C.Structure):
+    _fields_ = [("chn_name", C.c_char_p), ("name_len", C.c_int), ("totallkh", C.c_double), ("totallkh2", C.c_double)] + \
+               [(n, C.POINTER(C.c_double)) for n in ("indvlkh", "qq", "qq2", "self_rates", "self_rates2", "gen", "gen2",
+                                                      "freq", "freq2")]
+
+
+@pytest.fixture(scope="module")
+def host():
+    out = subprocess.run(["make", "-C", HOST, "libinbreed_host.so"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lib = C.CDLL(HOST_SO)
+    lib.gs_read.argtypes = [C.c_char_p, C.POINTER(GsOptions), C.POINTER(GsStore), C.c_char_p, C.c_int]
+    lib.gs_free.argtypes = [C.POINTER(GsStore)]
+    lib.wr_chain.argtypes = [C.c_char_p, C.POINTER(WrRun), C.POINTER(WrData), C.POINTER(WrChain), C.POINTER(C.c_double)]
+    lib.wr_gelman_rubin.restype = C.c_double
+    lib.wr_gelman_rubin.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
+    return lib
+
+
+def _write_text(path, x, pops, label, popdata, extra, fmt, markers, alleles):
+    L, N, _ = x.shape
+    with open(path, "w") as fh:
+        if markers:
+            fh.write(" ".join(f"m{l}" for l in range(L)) + "\n")
+        for i in range(N):
+            meta = ([f"id{i}"] if label else []) + ([f"P{pops[i]}"] if popdata else []) + [f"e{i}_{k}" for k in range(extra)]
+            tok = lambda l, c: "-9" if x[l, i, c] < 0 else alleles[l][x[l, i, c]]
+            if fmt == 0:
+                for c in range(2):
+                    fh.write("\t".join(meta + [tok(l, c) for l in range(L)]) + "\n")
+            else:
+                fh.write(" ".join(meta + [tok(l, c) for l in range(L) for c in range(2)]) + "\n")
+
+
+@pytest.mark.parametrize("label,popdata,extra,fmt,markers", [(1, 1, 0, 0, 0), (0, 0, 0, 0, 0), (1, 0, 2, 1, 0), (1, 1, 1, 0, 1)])
+def test_packer_matches_reference_reader(host, tmp_path, label, popdata, extra, fmt, markers):
+    rng = np.random.default_rng(label * 8 + popdata * 4 + extra * 2 + fmt)
+    d = make_dataset(N=23, L=14, K=3, A=5, miss=0.08, seed=77)
+    x = d.x.copy()
+    x[3] = np.where(x[3] >= 0, 0, x[3])                   # a monomorphic locus: both readers must drop it
+    x[9, :, :] = -9                                       # an all-missing locus
+    alleles = [[str(int(v)) for v in rng.permutation(np.arange(100, 100 + 40))[:8]] for _ in range(x.shape[0])]
+    p = str(tmp_path / "geno.txt")
+    _write_text(p, x, d.pop, label, popdata, extra, fmt, markers, alleles)
+    opt = GsOptions(2, 23, 14, b"-9", label, popdata, extra, markers, fmt, 1)
+    st = GsStore()
+    err = C.create_string_buffer(512)
+    assert host.gs_read(p.encode(), C.byref(opt), C.byref(st), err, 512) == 0, err.value
+    N, L = st.totalsize, st.locinum
+    mine = np.ctypeslib.as_array(st.x, (L, N, 2)).copy()
+    an = np.ctypeslib.as_array(st.allelenum, (L,)).copy()
+    rx, ran, rmiss, _ = pyoracle.ref_read_data(p, 2, 23, 3, 14, label=label, popdata=popdata, n_extra_col=extra,
+                                               markername_flag=markers, datafmt=fmt)
+    assert (L, N) == (rx.shape[0], rx.shape[1]) == (12, 23)
+    assert np.array_equal(an, ran)
+    assert np.array_equal(mine, rx)                       # same recoding, same missing code, same layout
+    mv = np.ctypeslib.as_array(st.missvec, (N,))
+    assert np.array_equal(mv, rmiss.sum(axis=0))
+    if popdata:
+        assert st.pop_count == 3
+        assert [st.poptype[i].decode() for i in range(3)] == ["P0", "P1", "P2"]
+    if label:
+        assert st.indvname[5].decode() == "id5"
+    host.gs_free(C.byref(st))
+
+
+@pytest.mark.parametrize("mode,label,popdata,distr", [(2, 1, 1, 1), (2, 0, 0, 0), (3, 0, 1, 1)])
+def test_result_file_bytes_match_reference_writer(host, tmp_path, mode, label, popdata, distr):
+    K, N = 3, 17
+    d = make_dataset(N=N, L=9, K=K, A=4, miss=0.1, seed=5)
+    rng = np.random.default_rng(3)
+    ns = N if mode == 3 else K
+    tot, tot2 = -1234.5678, 1234.5678 ** 2 + 33.3
+    indv = rng.normal(-70, 5, N)
+    qq = rng.dirichlet(np.ones(K), N); qq2 = qq ** 2 + rng.uniform(0, 0.01, (N, K))
+    s = rng.uniform(0.05, 0.95, ns); s2 = s ** 2 + rng.uniform(0, 0.01, ns)
+    g = rng.uniform(1, 6, N); g2 = g ** 2 + rng.uniform(0, 1, N)
+    pops = (np.arange(N) % 2).astype(np.int32)
+    missvec = (d.x < 0).any(axis=2).sum(axis=0).astype(np.int32)
+    ref = pyoracle.Reference(d.x, d.allelenum, K, mode=mode)
+    L = pyoracle.ref_lib()
+    L.refh_chain_stat.restype = C.c_double
+    L.refh_chain_stat.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, pyoracle.c_ip, C.c_int, pyoracle.c_ip,
+                                  C.c_char_p, C.c_double, C.c_double] + [pyoracle.c_dp] * 7
+    dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(pyoracle.c_dp)
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (indv, qq, qq2, s, s2, g, g2)]
+    f_ref = str(tmp_path / "ref.out")
+    dic_ref = L.refh_chain_stat(ref.h, f_ref.encode(), label, popdata, distr, pops.ctypes.data_as(pyoracle.c_ip), 2,
+                                missvec.ctypes.data_as(pyoracle.c_ip), b"Chain#1", tot, tot2,
+                                *[k.ctypes.data_as(pyoracle.c_dp) for k in keep])
+    # ---- ours
+    names = (C.c_char_p * N)(*[f"ind{i}".encode() for i in range(N)])
+    ptypes = (C.c_char_p * 2)(b"pop0", b"pop1")
+    run = WrRun()
+    run.ploid, run.totalsize, run.locinum, run.popnum, run.mode = 2, N, d.L, K, mode
+    run.label, run.popdata, run.distr_fmt, run.print_freq = label, popdata, distr, 0
+    wd = WrData(names, ptypes, None, None, pops.ctypes.data_as(C.POINTER(C.c_int)), missvec.ctypes.data_as(C.POINTER(C.c_int)),
+                None, 2, 4)
+    ch = WrChain(b"Chain#1", 8, tot, tot2, *[k.ctypes.data_as(C.POINTER(C.c_double)) for k in keep], None, None)
+    f_my = str(tmp_path / "my.out")
+    dic = C.c_double()
+    assert host.wr_chain(f_my.encode(), C.byref(run), C.byref(wd), C.byref(ch), C.byref(dic)) == 0
+    a, b = open(f_ref, "rb").read(), open(f_my, "rb").read()
+    assert abs(dic.value - dic_ref) < 1e-9
+    if mode == 3:
+        # the reference's mode-3 table is shifted by one individual and reads past the arrays
+        # (SURVEY.md App. B #2); everything outside that table must still match byte for byte
+        def strip(t):
+            i0 = t.index(b"The Posterior distribution of Selfing Rates:")
+            i1 = t.index(b"The Posterior distribution of Generations:")
+            return t[:i0] + t[i1:]
+        assert strip(a) == strip(b)
+        rows = b[b.index(b"The Posterior distribution of Selfing Rates:"):b.index(b"The Posterior distribution of Generations:")]
+        assert rows.count(b"Indv ") == N and b"Indv 0\t\t" in rows
+    else:
+        assert a == b
+    assert b"Chain#1\x00:" in b                            # the NUL the reference writes (App. B #6)
+
+
+def test_gelman_rubin_c_matches_python(host):
+    from instruct_b200.converge import gelman_rubin
+    rng = np.random.default_rng(1)
+    tr = np.ascontiguousarray(rng.normal(size=(5, 9)) + np.arange(5)[:, None] * 0.3)
+    got = host.wr_gelman_rubin(tr.ctypes.data_as(C.POINTER(C.c_double)), 5, 9)
+    assert abs(got - gelman_rubin(tr)) < 1e-12
