@@ -117,6 +117,8 @@ struct ig_ctx {
 	DevScalars *sc = nullptr;
 	uint16_t *pcnt = nullptr;
 	double *plog = nullptr;
+	uint16_t *pnsh = nullptr;
+	int32_t *nhet = nullptr, *nsh = nullptr;
 	int32_t *cnt = nullptr;
 	double *llparts = nullptr;
 	float *initd_dev = nullptr;
@@ -204,7 +206,7 @@ static void free_all(ig_ctx *c)
 {
 	cudaFree(c->Xt); cudaFree(c->Zt); cudaFree(c->P); cudaFree(c->P64); cudaFree(c->n); cudaFree(c->allelenum);
 	cudaFree(c->ind); cudaFree(c->Qf); cudaFree(c->gprop); cudaFree(c->gpair); cudaFree(c->S); cudaFree(c->state);
-	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
+	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->pnsh); cudaFree(c->nhet); cudaFree(c->nsh); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
 	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2);
 	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
 	cudaFree(c->mom.self2); cudaFree(c->mom.gen); cudaFree(c->mom.gen2); cudaFree(c->mom.freq); cudaFree(c->mom.freq2);
@@ -247,7 +249,10 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	CK(dalloc(&c->state, (size_t)MAX_K));
 	CK(dalloc(&c->sc, 1));
 	CK(dalloc(&c->pcnt, (size_t)g.nchunks * g.Nloc * g.KP));
-	CK(dalloc(&c->plog, (size_t)g.nchunks * 4 * g.Nloc));
+	CK(dalloc(&c->plog, (size_t)g.nchunks * 3 * g.Nloc));
+	CK(dalloc(&c->pnsh, (size_t)g.nchunks * g.Nloc));
+	CK(dalloc(&c->nhet, (size_t)g.Nloc));
+	CK(dalloc(&c->nsh, (size_t)g.Nloc));
 	CK(dalloc(&c->cnt, (size_t)g.Nloc * g.K));
 	CK(dalloc(&c->llparts, (size_t)g.Nloc * 4));
 	CK(dalloc(&c->initd_dev, (size_t)MAX_K));
@@ -268,7 +273,9 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 		CK(dalloc(&c->mom.freq2, (size_t)g.K * g.L * g.A));
 	}
 	CK(launch_tile_x(x_dev_canon, c->Xt, c->allelenum, g, c->stream));
-	c->launches++;
+	CK(launch_het_counts(c->Xt, nullptr, c->nhet, nullptr, g, c->stream));
+	CK(cudaMemsetAsync(c->nsh, 0, (size_t)g.Nloc * sizeof(int32_t), c->stream));
+	c->launches += 2;
 	CK(cudaStreamSynchronize(c->stream));
 	c->loaded = true;
 	return IG_OK;
@@ -459,9 +466,9 @@ static ZQArgs zq_args(ig_ctx *c)
 {
 	ZQArgs a;
 	a.Xt = c->Xt; a.Zt = c->Zt; a.P = c->P; a.n = c->n; a.Qf = c->Qf; a.gpair = c->gpair;
-	a.pcnt = c->pcnt; a.plog = c->plog; a.geo = c->geo; a.iter = c->iter; a.key0 = c->key0; a.key1 = c->key1;
+	a.pcnt = c->pcnt; a.plog = c->plog; a.pnsh = c->pnsh; a.geo = c->geo; a.iter = c->iter; a.key0 = c->key0; a.key1 = c->key1;
 	a.type_freq = c->cfg.type_freq;
-	a.k512 = 512u; a.k_mant = 0x007fffffu; a.k_one = 0x3f800000u;
+	a.k_mant = 0x007fffffu; a.k_one = 0x3f800000u;
 	return a;
 }
 
@@ -502,7 +509,8 @@ static ig_status phase_zq(ig_ctx *c, int init)
 	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
 	CK(launch_zq_sweep(a, c->rounds, c->stream));
 	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
-	EpiArgs e{c->pcnt, c->plog, c->ind, c->Qf, c->cnt, c->llparts, c->gpair, c->sc, c->geo, c->iter, c->key0, c->key1, init};
+	EpiArgs e{c->pcnt, c->plog, c->pnsh, c->nhet, c->nsh, c->ind, c->Qf, c->cnt, c->llparts, c->gpair, c->sc, c->geo,
+	          c->iter, c->key0, c->key1, init, a.type_freq};
 	CK(launch_epilogue(e, c->stream));
 	c->launches += 2;
 	return exchange_individuals(c);
@@ -550,10 +558,10 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	CK(launch_init_chain(c->ind, c->S, c->state, c->sc, c->initd_dev, c->gprop, c->gpair, g, c->cfg.mode, c->cfg.prior_flag,
 	                     c->cfg.back_refl, c->key0, c->key1, c->stream));
 	// initial assignment (update_ZQ with init_flag = 1, mcmc.c:206,1143-1144): uniform Z is the
-	// categorical draw with all weights equal, so the sweep kernel runs once with P = Q = 1
+	// categorical draw with all weights equal, so the sweep kernel runs once with P = 1, Q = 1/K
 	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
 	CK(launch_fill_f32(c->P, 1.0f, pn, c->stream));
-	CK(launch_fill_f32(c->Qf, 1.0f, (size_t)g.Nloc * g.KP, c->stream));
+	CK(launch_fill_q_uniform(c->Qf, g, c->stream));
 	CK(cudaMemsetAsync(c->n, 0, pn * sizeof(int32_t), c->stream));
 	CK(cudaMemsetAsync(c->Zt, 0, (size_t)g.LT * g.Nloc * TILE * 2, c->stream));
 	c->launches += 3;
@@ -860,6 +868,7 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 		cudaError_t e = cudaMemcpyAsync(tmp, host, want, cudaMemcpyHostToDevice, c->stream);
 		if (e == cudaSuccess) e = launch_tile_z((const int8_t *)tmp, c->Zt, g, c->stream);
 		if (e == cudaSuccess) e = launch_tally(c->Xt, c->Zt, c->n, g, c->stream);    // n always mirrors Z
+		if (e == cudaSuccess) e = launch_het_counts(c->Xt, c->Zt, nullptr, c->nsh, g, c->stream);   // and so does nsh
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		cudaFree(tmp);
 		CK(e);

@@ -60,12 +60,13 @@ struct ZQArgs {
 	const float *Qf;         // [Nloc][KP]
 	const int2 *gpair;       // [Nloc] (g, g')
 	uint16_t *pcnt;          // [nchunks][Nloc][KP]
-	double *plog;            // [nchunks][4][Nloc]
+	double *plog;            // [nchunks][3][Nloc]  old-Z ratio piece, new-Z likelihood under g and under g'
+	uint16_t *pnsh;          // [nchunks][Nloc]     same-z heterozygotes on the new Z
 	Geometry geo;
 	uint32_t iter;
 	uint32_t key0, key1;
 	int type_freq;
-	uint32_t k512, k_mant, k_one;   // 512, 0x007fffff, 0x3f800000 kept in registers on purpose (see LogProd::mul)
+	uint32_t k_mant, k_one;  // 0x007fffff, 0x3f800000 kept in registers on purpose (see uniform_big)
 };
 
 // ---- launchers (ig_kernels.cu) -------------------------------------------------------
@@ -73,7 +74,9 @@ cudaError_t launch_zq_sweep(const ZQArgs &a, int rounds, cudaStream_t s);
 cudaError_t zq_configure(Geometry &g, int device);
 
 struct EpiArgs {
-	const uint16_t *pcnt; const double *plog;
+	const uint16_t *pcnt; const double *plog; const uint16_t *pnsh;
+	const int32_t *nhet;     // [Nloc] usable heterozygous genotypes (data only; computed at load)
+	int32_t *nsh;            // [Nloc] same-z heterozygotes on the current Z: read as the old-Z count, rewritten with the new one
 	double *ind;             // [Npad][REC]
 	float *Qf;               // [Nloc][KP]
 	int32_t *cnt;            // [Nloc][K]
@@ -83,6 +86,7 @@ struct EpiArgs {
 	Geometry geo;
 	uint32_t iter, key0, key1;
 	int init;                // 1: initial assignment pass (no G accept, no likelihood)
+	int type_freq;
 };
 cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s);
 
@@ -116,10 +120,12 @@ cudaError_t launch_tile_x(const int16_t *x_canon, int16_t *Xt, const int32_t *al
 cudaError_t launch_untile_x(const int16_t *Xt, int16_t *x_canon, Geometry g, cudaStream_t s);
 cudaError_t launch_tile_z(const int8_t *z_canon, int8_t *Zt, Geometry g, cudaStream_t s);
 cudaError_t launch_untile_z(const int8_t *Zt, int8_t *z_canon, Geometry g, cudaStream_t s);
+cudaError_t launch_het_counts(const int16_t *Xt, const int8_t *Zt, int32_t *nhet, int32_t *nsh, Geometry g, cudaStream_t s);
 cudaError_t launch_tally(const int16_t *Xt, const int8_t *Zt, int32_t *n, Geometry g, cudaStream_t s);
 cudaError_t launch_loglik(const int16_t *Xt, const int8_t *Zt, const float *P, const float *Qf, const int32_t *gen,
                           double *out, Geometry g, int type_freq, cudaStream_t s);
 cudaError_t launch_fill_f32(float *p, float v, size_t n, cudaStream_t s);
+cudaError_t launch_fill_q_uniform(float *Qf, Geometry g, cudaStream_t s);
 cudaError_t launch_init_chain(double *ind, double *S, int32_t *state, DevScalars *sc, const float *initd_dev,
                               int32_t *gprop, int2 *gpair, Geometry g, int mode, int prior_flag, int back_refl,
                               uint32_t key0, uint32_t key1, cudaStream_t s);

@@ -6,9 +6,9 @@
 // plus the O(N*L*A*K) tally at the top of update_P.  Here it is
 //     p_dirichlet   (L*K threads)       P | n            mcmc.c:846-857
 //     pre_sweep     (1 CTA)             S | G,Q  and the G proposals   mcmc.c:913-983,864-886,1062-1084
-//     zq_sweep      (the one big pass)  Z | P,Q ; per-individual K-counts ; n[l][a][k] for the
-//                                       NEXT update_P ; the four log-likelihood pieces that the
-//                                       G accept and cal_lkh need           mcmc.c:1122-1194,1726-1773,810-845
+//     zq_sweep      (the one big pass, zq_sweep.cu)  Z | P,Q ; per-individual K-counts ;
+//                                       n[l][a][k] for the NEXT update_P ; the log-likelihood pieces
+//                                       that the G accept and cal_lkh need   mcmc.c:1122-1194,1726-1773,810-845
 //     indiv_epilogue(N threads)         G accept, Q | Z,alpha, indvlkh     mcmc.c:1085-1089,1196-1198,1931
 //     post_sweep    (1 CTA)             alpha | Q, totallkh, column sums   mcmc.c:1244-1263,1940,1954-1961
 //     moments       (N*K threads)       store_chn                         mcmc.c:1320-1456
@@ -28,381 +28,6 @@ namespace cg = cooperative_groups;
 namespace ig {
 
 #define LN2_D 0.69314718055994530942
-
-// --------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP), cache-hinted
-// 128-bit global accesses.
-// --------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-	asm volatile(
-	    "{\n\t.reg .pred p;\n\t"
-	    "WAIT_LOOP:\n\t"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-	    "@p bra DONE;\n\t"
-	    "bra WAIT_LOOP;\n\t"
-	    "DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-	                 smem_addr(dst_smem)),
-	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-	             : "memory");
-}
-__device__ __forceinline__ int4 ldg_stream(const int4 *p)   // read-once data: bypass L1 allocation
-{
-	int4 r;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-	return r;
-}
-__device__ __forceinline__ int4 ldg_rw(const int4 *p)       // data this kernel also writes: no .nc
-{
-	int4 r;
-	asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-	return r;
-}
-__device__ __forceinline__ void stg_stream(int4 *p, const int4 &v)
-{
-	asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// --------------------------------------------------------------------------------------
-// Instruction-mix note (profiles/r1_zq_sweep_v1.md): the first version of this kernel was
-// bound by the ALU pipe (LOP3 / IADD / ISETP / FSETP / SHF, 16 lanes per SM sub-partition)
-// at 68 % while the FMA pipe (FFMA / FMUL / FADD / IMAD, twice as wide) idled at 35 %.  The
-// helpers below therefore phrase comparisons, shifts and index arithmetic as FMA-pipe work
-// wherever that is exact: saturating FFMA instead of FSETP+IADD for the categorical search,
-// IMAD.HI instead of SHF for exponent extraction, IMAD for index math, shared-memory RED
-// instead of register bit-field counters.
-// --------------------------------------------------------------------------------------
-
-// Product accumulator: a log-likelihood is a sum of logs of per-locus probabilities; the
-// kernel keeps the PRODUCT instead, as an fp32 mantissa in [1,2^64) and the integer sum of
-// the factors' biased exponents, and takes one logarithm per (individual, chunk).  Relative
-// error of an n-term product is <= n * 2^-24, i.e. an ABSOLUTE error <= 6e-8 * n on a
-// log-likelihood of magnitude ~n: relative ~1e-7, inside the 1e-6 gate of BASELINE.json.
-// constants that must live in registers: ptxas turns a literal 512 into LEA.HI (ALU pipe) and
-// splits an and-or with two literals into two LOP3; kernel-argument values stay IMAD.HI / one LOP3
-struct LogProdConst { uint32_t k512, mant, one; };
-
-struct LogProd {
-	float m;
-	int e;        // sum of biased exponents; value() removes 127 per multiplication
-	__device__ __forceinline__ void init() { m = 1.0f; e = 0; }
-	// k512 is the constant 512 passed as a kernel argument: ptxas strength-reduces a literal
-	// power-of-two multiplier to LEA.HI (ALU pipe), a register operand stays an IMAD.HI
-	__device__ __forceinline__ void mul(float t, const LogProdConst &k)
-	{
-		const uint32_t b = __float_as_uint(t);
-		uint32_t mb;
-		asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(e) : "r"(b), "r"(k.k512));     // e += b >> 23 on the FMA pipe
-		asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mb) : "r"(b), "r"(k.mant), "r"(k.one));   // (b & mant) | one, one LOP3
-		m *= __uint_as_float(mb);
-	}
-	__device__ __forceinline__ void renorm()
-	{
-		const uint32_t b = __float_as_uint(m);
-		e += (int)(b >> 23) - 127;
-		m = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
-	}
-	__device__ __forceinline__ double value(int nmul)
-	{
-		renorm();
-		return log((double)m) + (double)(e - 127 * nmul) * LN2_D;
-	}
-};
-
-constexpr float BIG126 = 8.507059173023462e37f;          // 2^126
-constexpr float U_SCALE = 8.507059173023462e37f;         // (f - 1 + 2^-24) * 2^126, f in [1,2)
-constexpr float U_OFFS = -8.5070586659632355e37f;        // (-1 + 2^-24) * 2^126
-
-// uniform in (0,1) scaled by 2^126, from 23 random bits: ((r >> 9) + 0.5) * 2^-23 * 2^126.
-// One funnel shift builds the float 1.mantissa, one FFMA rescales it.
-__device__ __forceinline__ float uniform_big(uint32_t r)
-{
-	const float f = __uint_as_float(__funnelshift_r(r, 0x7Fu, 9));        // [1, 2)
-	return fmaf(f, U_SCALE, U_OFFS);
-}
-
-// index of the first cumulative weight that exceeds t:  #{k < KP-1 : t > c_k}, evaluated as a
-// sum of saturated differences (t - c_k) * 2^126 -- FFMA.SAT + FADD on the FMA pipe.  t and
-// c_k are fp32 values whose difference is either 0 or at least one ulp(t) >= 2^-126 in
-// magnitude (t >= 2^-24 * total, total >= P_FLOOR / K), so every term is exactly 0 or 1.
-// Padded populations have c_k = total > t and never count; no clamp is needed.
-template <int KP>
-__device__ __forceinline__ int pick_category(const float (&c)[KP], float ub)
-{
-	const float tb = ub * c[KP - 1];                                      // t * 2^126, t = u * total
-	float zf = 0.0f;
-#pragma unroll
-	for (int k = 0; k < KP - 1; k++) zf += __saturatef(fmaf(c[k], -BIG126, tb));
-	return __float2int_rn(zf);
-}
-
-// --------------------------------------------------------------------------------------
-// zq_sweep: grid (locus chunks, individual blocks), 256 threads, one thread = one
-// individual, marching over the chunk's micro-tiles of 8 loci.
-//   global  : X  int16 [LT][Nloc][8][2]  two 128-bit loads per thread per micro-tile
-//             Z  int8  [LT][Nloc][8][2]  one 128-bit load + one 128-bit store
-//   shared  : P chunk [TL][A][KP] fp32, landed by ONE TMA bulk copy on an mbarrier;
-//             n chunk [TL][A][KP][R] int32 histogram, R lane-replicas to thin out conflicts,
-//             reduced and pushed to global n with RED at the end of the CTA;
-//             per-thread ancestry counters [KP][256] int32 (column tid: conflict-free RED)
-//   output  : per (chunk, individual) partials: K counts (u16) + 4 log-likelihood pieces
-// --------------------------------------------------------------------------------------
-template <int KP, int ROUNDS, bool TF0>
-__global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const ZQArgs a)
-{
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	__shared__ __align__(8) unsigned long long bar;
-	const Geometry &g = a.geo;
-	const int tid = threadIdx.x;
-	const int chunk = blockIdx.x;
-	const int l0 = chunk * g.TL;
-	const int nl = min(g.TL, g.Lpad - l0);
-	const int nmt = nl / TILE;
-	const int A = g.A;
-	const int rowsz = A * KP;                       // floats per locus
-	float *Psm = reinterpret_cast<float *>(smem_raw);
-	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);
-	int *cntsm = hist + (size_t)g.TL * rowsz * g.R;                 // [KP][ZQ_THREADS]
-	const int nbins = nl * rowsz;
-	const int R = g.R;
-
-	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-	__syncthreads();
-	if (tid == 0) {
-		mbar_expect_tx(&bar, (uint32_t)nbins * 4u);
-		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
-	}
-	for (int j = tid; j < nbins * R; j += ZQ_THREADS) hist[j] = 0;
-#pragma unroll
-	for (int k = 0; k < KP; k++) cntsm[k * ZQ_THREADS + tid] = 0;
-	__syncthreads();
-	mbar_wait(&bar, 0);
-
-	const int Nloc = g.Nloc;
-	const int mt0 = l0 / TILE;
-	const int sub0 = blockIdx.y * g.subs_per_blk;
-	const int nsub_total = (Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
-	const int sub1 = min(sub0 + g.subs_per_blk, nsub_total);
-	int *hist_t = hist + (tid & (R - 1));           // this lane's replica column
-	int *cnt_t = cntsm + tid;                       // this thread's counter column
-	const LogProdConst k512{a.k512, a.k_mant, a.k_one};
-
-	for (int sub = sub0; sub < sub1; ++sub) {
-		const int il = sub * ZQ_THREADS + tid;
-		if (il < Nloc) {
-			float q[KP];
-			{
-				const float4 *qp = reinterpret_cast<const float4 *>(a.Qf + (size_t)il * KP);
-#pragma unroll
-				for (int v = 0; v < KP / 4; v++) {
-					float4 t = __ldg(qp + v);
-					q[4 * v] = t.x; q[4 * v + 1] = t.y; q[4 * v + 2] = t.z; q[4 * v + 3] = t.w;
-				}
-			}
-			const int2 gg = __ldg(a.gpair + il);
-			// 1 - h(g) = 2^-(g-1); exact in fp32 down to 2^-126, 0 beyond (g can start huge in mode 3)
-			const float omh_g = (gg.x <= 127) ? __int_as_float((128 - gg.x) << 23) : 0.0f;
-			const float omh_p = (gg.y <= 127) ? __int_as_float((128 - gg.y) << 23) : 0.0f;
-			const float h_g = 1.0f - omh_g, h_p = 1.0f - omh_p;
-
-			// new Z: D_g = prod T_g, T_g = f (h_g + f (1-h_g)) for same-z homozygotes, f0 f1 otherwise
-			// old Z: only the ratio B/A over same-z homozygotes enters update_G's accept
-			LogProd An, Bn, Ao, Bo;
-			An.init(); Bn.init(); Ao.init(); Bo.init();
-			int nhet = 0, nsh_new = 0, nsh_old = 0;
-
-			const int4 *xp = reinterpret_cast<const int4 *>(a.Xt) + ((size_t)mt0 * Nloc + il) * 2;
-			int4 *zp = reinterpret_cast<int4 *>(a.Zt) + ((size_t)mt0 * Nloc + il);
-			const size_t xstride = (size_t)Nloc * 2, zstride = (size_t)Nloc;
-			const uint32_t ig_global = (uint32_t)(g.i0 + il);
-
-			// No software prefetch: a micro-tile is ~1300 instructions per warp, so with four
-			// resident warps per scheduler the ~1 us load latency of one warp hides behind the
-			// other three; rotating prefetch registers cost 7 instructions per genotype.
-			for (int mt = 0; mt < nmt; ++mt) {
-				const int4 xa = ldg_stream(xp + (size_t)mt * xstride), xb = ldg_stream(xp + (size_t)mt * xstride + 1);
-				const int4 zz = ldg_rw(zp + (size_t)mt * zstride);
-				const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-				const uint32_t zwo[4] = {(uint32_t)zz.x, (uint32_t)zz.y, (uint32_t)zz.z, (uint32_t)zz.w};
-				uint32_t zwn[4];
-#pragma unroll
-				for (int pr = 0; pr < 4; ++pr) {
-					const u32x4 rnd = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
-					const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-					uint32_t pair[2];
-#pragma unroll
-					for (int h2 = 0; h2 < 2; ++h2) {
-						const int j = 2 * pr + h2;
-						const uint32_t pold = h2 ? (zwo[pr] >> 16) : (zwo[pr] & 0xFFFFu);
-						pair[h2] = pold;
-						// the tiler stores a genotype with ANY missing copy as (-9,-9): one sign test
-						if (xw[j] >= 0) {
-							const int x0 = xw[j] & 0xFFFF, x1 = xw[j] >> 16;
-							const int lj = mt * TILE + j;
-							const int row0 = (lj * A + x0) * KP, row1 = (lj * A + x1) * KP;
-							const bool het = (x0 != x1);
-							// ---- cumulative weights w_k = sum_{m<=k} Q_im P_m,l,x (mcmc.c:1141-1149)
-							float p0[KP], p1[KP], c0[KP], c1[KP];
-#pragma unroll
-							for (int v = 0; v < KP / 4; v++) {
-								const float4 t0 = *reinterpret_cast<const float4 *>(Psm + row0 + 4 * v);
-								const float4 t1 = *reinterpret_cast<const float4 *>(Psm + row1 + 4 * v);
-								p0[4 * v] = t0.x; p0[4 * v + 1] = t0.y; p0[4 * v + 2] = t0.z; p0[4 * v + 3] = t0.w;
-								p1[4 * v] = t1.x; p1[4 * v + 1] = t1.y; p1[4 * v + 2] = t1.z; p1[4 * v + 3] = t1.w;
-							}
-							c0[0] = q[0] * p0[0];
-							c1[0] = q[0] * p1[0];
-#pragma unroll
-							for (int k = 1; k < KP; k++) { c0[k] = fmaf(q[k], p0[k], c0[k - 1]); c1[k] = fmaf(q[k], p1[k], c1[k - 1]); }
-							// ---- old-Z pieces of update_G's ratio (log_ld_indv, mcmc.c:1752-1759)
-							if (!TF0) {
-								const int zo0 = pold & 0xFF, zo1 = pold >> 8;
-								const bool same_o = (zo0 == zo1);
-								const float fo = Psm[row0 + zo0];
-								const bool sh_o = same_o && !het;
-								Ao.mul(sh_o ? fmaf(fo, omh_g, h_g) : 1.0f, k512);
-								Bo.mul(sh_o ? fmaf(fo, omh_p, h_p) : 1.0f, k512);
-								nsh_old += (same_o && het) ? 1 : 0;
-							}
-							// ---- categorical draws (disc_unif, random.c:403-430)
-							const int z0 = pick_category<KP>(c0, uniform_big(rr[2 * h2]));
-							const int z1 = pick_category<KP>(c1, uniform_big(rr[2 * h2 + 1]));
-							// ---- n[l][a][k] tally for the next update_P (mcmc.c:815-845), and the
-							//      individual's ancestry counts (mcmc.c:1176-1194): shared-memory RED
-							atomicAdd(hist_t + (row0 + z0) * R, 1);
-							atomicAdd(hist_t + (row1 + z1) * R, 1);
-							atomicAdd(cnt_t + z0 * ZQ_THREADS, 1);
-							atomicAdd(cnt_t + z1 * ZQ_THREADS, 1);
-							// ---- new-Z likelihood pieces (cal_lkh and the accepted-G selection)
-							float f0, f1;
-							bool same_n;
-							if (TF0) { f0 = c0[KP - 1]; f1 = c1[KP - 1]; same_n = true; }   // mcmc.c:1739-1749
-							else { f0 = Psm[row0 + z0]; f1 = Psm[row1 + z1]; same_n = (z0 == z1); }
-							const bool sh_n = same_n && !het;
-							An.mul(f0 * (sh_n ? fmaf(f0, omh_g, h_g) : f1), k512);
-							Bn.mul(f0 * (sh_n ? fmaf(f0, omh_p, h_p) : f1), k512);
-							nhet += het ? 1 : 0;
-							nsh_new += (same_n && het) ? 1 : 0;
-							pair[h2] = (uint32_t)(z1 * 256 + z0);
-						}
-					}
-					zwn[pr] = pair[1] * 65536u + pair[0];
-				}
-				stg_stream(zp + (size_t)mt * zstride, make_int4((int)zwn[0], (int)zwn[1], (int)zwn[2], (int)zwn[3]));
-				if ((mt & 7) == 7) { An.renorm(); Bn.renorm(); Ao.renorm(); Bo.renorm(); }
-			}
-			// ---- partials of this (chunk, individual)
-			{
-				int csum = 0;
-				uint32_t *pc = reinterpret_cast<uint32_t *>(a.pcnt + ((size_t)chunk * Nloc + il) * KP);
-#pragma unroll
-				for (int j = 0; j < KP / 2; j++) {
-					const int ca = cnt_t[(2 * j) * ZQ_THREADS], cb = cnt_t[(2 * j + 1) * ZQ_THREADS];
-					cnt_t[(2 * j) * ZQ_THREADS] = 0;
-					cnt_t[(2 * j + 1) * ZQ_THREADS] = 0;
-					csum += ca + cb;
-					pc[j] = (uint32_t)ca | ((uint32_t)cb << 16);
-				}
-				const int nmul = csum >> 1;               // usable genotypes = multiplications per accumulator
-				double *pl = a.plog + (size_t)chunk * 4 * Nloc + il;
-				const double la = An.value(nmul), lb = Bn.value(nmul);
-				double d_old;
-				if (TF0) d_old = (lb - la) - (double)nsh_new * (double)(gg.y - gg.x) * LN2_D;
-				else d_old = (Bo.value(nmul) - Ao.value(nmul)) - (double)nsh_old * (double)(gg.y - gg.x) * LN2_D;
-				pl[0] = d_old;
-				pl[(size_t)Nloc] = (double)nhet * LN2_D;
-				pl[(size_t)2 * Nloc] = la - (double)nsh_new * (double)(gg.x - 1) * LN2_D;
-				pl[(size_t)3 * Nloc] = lb - (double)nsh_new * (double)(gg.y - 1) * LN2_D;
-			}
-		}
-	}
-	__syncthreads();
-	// ---- reduce the replicas and push this CTA's tally into global n (RED, no return value)
-	int32_t *ng = a.n + (size_t)l0 * rowsz;
-	for (int b = tid; b < nbins; b += ZQ_THREADS) {
-		int s = 0;
-		for (int r = 0; r < R; r++) s += hist[b * R + r];
-		if (s) atomicAdd(ng + b, s);
-	}
-}
-
-template <int KP>
-static cudaError_t launch_zq_kp(const ZQArgs &a, int rounds, cudaStream_t s)
-{
-	dim3 grid(a.geo.nchunks, a.geo.nblk), block(ZQ_THREADS);
-	const size_t sm = a.geo.zq_smem;
-#define IG_LAUNCH(RND, TF)                                                                                   \
-	do {                                                                                                 \
-		cudaError_t e = cudaFuncSetAttribute(zq_sweep_kernel<KP, RND, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-		if (e != cudaSuccess) return e;                                                                  \
-		zq_sweep_kernel<KP, RND, TF><<<grid, block, sm, s>>>(a);                                          \
-	} while (0)
-	if (a.type_freq == 0) { if (rounds == 7) IG_LAUNCH(7, true); else IG_LAUNCH(10, true); }
-	else { if (rounds == 7) IG_LAUNCH(7, false); else IG_LAUNCH(10, false); }
-#undef IG_LAUNCH
-	return cudaGetLastError();
-}
-
-cudaError_t launch_zq_sweep(const ZQArgs &a, int rounds, cudaStream_t s)
-{
-	switch (a.geo.KP) {
-	case 4: return launch_zq_kp<4>(a, rounds, s);
-	case 8: return launch_zq_kp<8>(a, rounds, s);
-	case 16: return launch_zq_kp<16>(a, rounds, s);
-	default: return cudaErrorInvalidValue;
-	}
-}
-
-// Choose the decomposition: chunks of TL loci x blocks of individuals.  The tally of a chunk
-// is complete inside one CTA when nblk == 1 (no contention on global n); per-individual
-// pieces are always combined by indiv_epilogue in chunk order (deterministic).
-cudaError_t zq_configure(Geometry &g, int device)
-{
-	int sms = 148, smem_optin = 227 * 1024;
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-	const int target_ctas = 2 * ZQ_MIN_CTAS * sms;         // ZQ_MIN_CTAS resident CTAs per SM, two waves
-	const size_t cnt_bytes = (size_t)g.KP * ZQ_THREADS * sizeof(int);
-	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / ZQ_MIN_CTAS - 2048 - cnt_bytes;
-	const size_t per_locus = (size_t)g.A * g.KP * 4;
-	const int nsub_total = (g.Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
-	int R = 8;
-	while (R > 1 && per_locus * (1 + R) * TILE > budget) R >>= 1;
-	if (per_locus * (1 + R) * TILE > (size_t)smem_optin - 2048 - cnt_bytes) return cudaErrorInvalidConfiguration;
-	int tl_max = (int)(budget / (per_locus * (1 + R)));
-	if (tl_max < TILE) tl_max = (int)(((size_t)smem_optin - 2048 - cnt_bytes) / (per_locus * (1 + R)));
-	tl_max = (tl_max / TILE) * TILE;
-	if (tl_max < TILE) return cudaErrorInvalidConfiguration;
-	if (tl_max > 1024) tl_max = 1024;
-	int tl = ((g.Lpad + target_ctas - 1) / target_ctas + TILE - 1) / TILE * TILE;
-	if (tl < TILE) tl = TILE;
-	if (tl > tl_max) tl = tl_max;
-	g.TL = tl;
-	g.nchunks = (g.Lpad + tl - 1) / tl;
-	int nblk = 1;
-	if (g.nchunks < target_ctas) nblk = min(nsub_total, (target_ctas + g.nchunks - 1) / g.nchunks);
-	if (nblk < 1) nblk = 1;
-	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
-	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
-	g.R = R;
-	g.zq_smem = (size_t)tl * per_locus * (1 + R) + (size_t)g.KP * ZQ_THREADS * sizeof(int);
-	return cudaSuccess;
-}
 
 // --------------------------------------------------------------------------------------
 // p_dirichlet: P[k][l][.] ~ Dirichlet(n[k][l][.] + 1)  (update_P, mcmc.c:846-857, lambda = 1).
@@ -691,7 +316,8 @@ constexpr int EPI_GROUPS = 8;
 __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const EpiArgs a)
 {
 	__shared__ int cnt_sh[EPI_GROUPS][MAX_K][32];
-	__shared__ double ll_sh[EPI_GROUPS][4][32];
+	__shared__ double ll_sh[EPI_GROUPS][3][32];
+	__shared__ int nsh_sh[EPI_GROUPS][32];
 	const Geometry &g = a.geo;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int il = blockIdx.x * 32 + lane;
@@ -700,38 +326,47 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 	int cnt[MAX_K];
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
-	double d_old = 0.0, c_new = 0.0, a_new = 0.0, b_new = 0.0;
+	double d_old = 0.0, a_new = 0.0, b_new = 0.0;
+	int nsh_new = 0;
 	if (live) {
 		for (int c = w; c < g.nchunks; c += EPI_GROUPS) {
 			const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.pcnt + ((size_t)c * g.Nloc + il) * KP);
 #pragma unroll
 			for (int j = 0; j < MAX_K / 2; j++)
 				if (2 * j < KP) { const uint32_t v = pc[j]; cnt[2 * j] += v & 0xFFFFu; cnt[2 * j + 1] += v >> 16; }
-			const double *pl = a.plog + (size_t)c * 4 * g.Nloc + il;
+			const double *pl = a.plog + (size_t)c * 3 * g.Nloc + il;
 			d_old += pl[0];
-			c_new += pl[(size_t)g.Nloc];
-			a_new += pl[(size_t)2 * g.Nloc];
-			b_new += pl[(size_t)3 * g.Nloc];
+			a_new += pl[(size_t)g.Nloc];
+			b_new += pl[(size_t)2 * g.Nloc];
+			nsh_new += a.pnsh[(size_t)c * g.Nloc + il];
 		}
 	}
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++) cnt_sh[w][k][lane] = cnt[k];
-	ll_sh[w][0][lane] = d_old; ll_sh[w][1][lane] = c_new; ll_sh[w][2][lane] = a_new; ll_sh[w][3][lane] = b_new;
+	ll_sh[w][0][lane] = d_old; ll_sh[w][1][lane] = a_new; ll_sh[w][2][lane] = b_new;
+	nsh_sh[w][lane] = nsh_new;
 	__syncthreads();
 	if (w != 0 || !live) return;
-	d_old = c_new = a_new = b_new = 0.0;
+	d_old = a_new = b_new = 0.0;
+	nsh_new = 0;
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
 	for (int ww = 0; ww < EPI_GROUPS; ww++) {
 #pragma unroll
 		for (int k = 0; k < MAX_K; k++) cnt[k] += cnt_sh[ww][k][lane];
-		d_old += ll_sh[ww][0][lane]; c_new += ll_sh[ww][1][lane]; a_new += ll_sh[ww][2][lane]; b_new += ll_sh[ww][3][lane];
+		d_old += ll_sh[ww][0][lane]; a_new += ll_sh[ww][1][lane]; b_new += ll_sh[ww][2][lane];
+		nsh_new += nsh_sh[ww][lane];
 	}
+	// heterozygotes contribute ln 2 each (genofreq, mcmc.c:1700); the count is data only
+	const double c_new = (double)a.nhet[il] * LN2_D;
 	const int ig_global = g.i0 + il;
 	double *rec = a.ind + (size_t)ig_global * g.REC;
-	if (a.llparts) { double *lp = a.llparts + (size_t)il * 4; lp[0] = d_old; lp[1] = c_new; lp[2] = a_new; lp[3] = b_new; }
 	if (!a.init) {
 		const int2 gg = a.gpair[il];
+		// same-z heterozygotes carry 2^-(g-1) (genofreq, mcmc.c:1692-1699): on the OLD Z their
+		// count is what the previous pass left in nsh (type_freq 0: already inside d_old)
+		if (a.type_freq != 0) d_old -= (double)a.nsh[il] * (double)(gg.y - gg.x) * LN2_D;
+		if (a.llparts) { double *lp = a.llparts + (size_t)il * 4; lp[0] = d_old; lp[1] = c_new; lp[2] = a_new; lp[3] = b_new; }
 		Stream sa((uint32_t)ig_global, 0u, a.iter, TAG_GACC, a.key0, a.key1);
 		const double u = sa.uniform();
 		const double ratio = exp(d_old);
@@ -757,6 +392,7 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 		}
 	for (int k = K; k < KP; k++) a.Qf[(size_t)il * KP + k] = 0.0f;
 	rec[K + 1] = slq;
+	a.nsh[il] = nsh_new;
 }
 cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s)
 {
@@ -931,6 +567,32 @@ __global__ void untile_z_kernel(const int8_t *Zt, int8_t *zc, Geometry g)
 	zc[t * 2 + 1] = Zt[src + 1];
 }
 static inline unsigned nblocks(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// per individual: usable heterozygous genotypes (nhet, data only) and those of them whose two
+// copies share an ancestry (nsh, a function of Z).  Run at load and whenever Z is injected;
+// during a chain zq_sweep / indiv_epilogue keep nsh current.
+__global__ void het_counts_kernel(const int16_t *Xt, const int8_t *Zt, int32_t *nhet, int32_t *nsh, Geometry g)
+{
+	const int il = blockIdx.x * blockDim.x + threadIdx.x;
+	if (il >= g.Nloc) return;
+	int h = 0, s = 0;
+	for (int mt = 0; mt < g.LT; mt++) {
+		const size_t base = ((size_t)mt * g.Nloc + il) * TILE * 2;
+		for (int j = 0; j < TILE; j++) {
+			const int x0 = Xt[base + 2 * j], x1 = Xt[base + 2 * j + 1];
+			if (x0 < 0 || x0 == x1) continue;
+			h++;
+			if (Zt && Zt[base + 2 * j] == Zt[base + 2 * j + 1]) s++;
+		}
+	}
+	if (nhet) nhet[il] = h;
+	if (nsh) nsh[il] = s;
+}
+cudaError_t launch_het_counts(const int16_t *Xt, const int8_t *Zt, int32_t *nhet, int32_t *nsh, Geometry g, cudaStream_t s)
+{
+	het_counts_kernel<<<nblocks((size_t)g.Nloc, 128), 128, 0, s>>>(Xt, Zt, nhet, nsh, g);
+	return cudaGetLastError();
+}
 cudaError_t launch_tile_x(const int16_t *xc, int16_t *Xt, const int32_t *an, Geometry g, cudaStream_t s)
 {
 	tile_x_kernel<<<nblocks((size_t)g.LT * g.Nloc * TILE, 256), 256, 0, s>>>(xc, Xt, an, g);
@@ -1026,6 +688,17 @@ __global__ void fill_f32_kernel(float *p, float v, size_t n)
 {
 	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t < n) p[t] = v;
+}
+// Q rows that make the categorical draw uniform over the K real populations (padded ones get 0)
+__global__ void fill_q_uniform_kernel(float *Qf, Geometry g)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < (size_t)g.Nloc * g.KP) Qf[t] = ((int)(t % g.KP) < g.K) ? 1.0f / (float)g.K : 0.0f;
+}
+cudaError_t launch_fill_q_uniform(float *Qf, Geometry g, cudaStream_t s)
+{
+	fill_q_uniform_kernel<<<nblocks((size_t)g.Nloc * g.KP, 256), 256, 0, s>>>(Qf, g);
+	return cudaGetLastError();
 }
 cudaError_t launch_fill_f32(float *p, float v, size_t n, cudaStream_t s)
 {

@@ -1,0 +1,459 @@
+// zq_sweep.cu -- the one big pass of the diploid sweep (sm_100a).
+//
+//   new Z | P, Q            update_ZQ, mcmc.c:1133-1174 (disc_unif, random.c:403-430)
+//   n[l][a][k] += ...       the tally half of the NEXT update_P, mcmc.c:810-845
+//   cnt[i][k]               ancestry counts for the Q draw, mcmc.c:1176-1194
+//   log-likelihood pieces   log_ld_indv (mcmc.c:1726-1773) on the OLD Z for update_G's accept
+//                           (mcmc.c:1062-1089) and on the NEW Z for cal_lkh (mcmc.c:1916-1942)
+//
+// update_G reads the OLD Z and update_ZQ never reads G, so both ride one pass over the
+// genotype store: the pass reads x (int16) and old z (int8) and writes new z (int8) -- the
+// 4 bytes per allele copy of SURVEY.md section 8d.
+//
+// The kernel is bound by instruction issue, not by HBM, so every choice
+// below is about warp instructions per genotype.  Measured pipe rates on B200
+// (tools/ubench/pipes.cu): FFMA/FADD/FMUL/FFMA.SAT issue at 1 per clock per sub-partition,
+// ALU-pipe ops (LOP3, SHF, IADD3, LEA, ISETP, FSEL) and IMAD at 1 per 2 clocks, IMAD.WIDE and
+// IMAD.HI at 1 per 4, F2I at 1 per 8+.  Hence:
+//   * the categorical search is a sum of saturating FFMAs (FMA pipe), its result becomes an
+//     integer by a multiplication with a denormal (2^-147 * z has the bit pattern 4z), not F2I;
+//   * the log-likelihood pieces are sums of MUFU.LG2 (the otherwise idle XU pipe) instead of
+//     mantissa/exponent product accumulators (IMAD.HI + LOP3 + FMUL per factor);
+//   * the new z pair is packed by denormal FFMAs, shared-memory addresses come from one LEA /
+//     IADD each, per-genotype missing-data branches exist only in micro-tiles that contain
+//     a missing genotype somewhere in the warp.
+#include <math.h>
+#include <stdio.h>
+#include "ig_internal.h"
+#include "philox.cuh"
+
+namespace ig {
+
+#define LN2_D 0.69314718055994530942
+
+// --------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP), cache-hinted
+// 128-bit global accesses, shared-space loads / reductions on 32-bit addresses.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "WAIT_LOOP:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@p bra DONE;\n\t"
+	    "bra WAIT_LOOP;\n\t"
+	    "DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	                 smem_addr(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+	             : "memory");
+}
+__device__ __forceinline__ int4 ldg_stream(const int4 *p)   // read-once data: bypass L1 allocation
+{
+	int4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ int4 ldg_rw(const int4 *p)       // data this kernel also writes: no .nc
+{
+	int4 r;
+	asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void stg_stream(int4 *p, const int4 &v)
+{
+	asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// the P chunk is read-only between the mbarrier wait and the end of the kernel: plain asm,
+// so that ptxas may schedule these loads freely
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+	float4 v;
+	asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr)
+{
+	float v;
+	asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void red_inc(uint32_t addr)
+{
+	asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ float lg2_fast(float x)           // MUFU.LG2; |abs err| <= 2^-22 on [0.5,2], 2 ulp elsewhere
+{
+	float r;
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+constexpr float BIG126 = 8.507059173023462e37f;          // 2^126
+constexpr float U_SCALE = 8.507059173023462e37f;         // (f - 1 + 2^-24) * 2^126, f in [1,2)
+constexpr float U_OFFS = -8.5070586659632355e37f;        // (-1 + 2^-24) * 2^126
+
+struct RegConst { uint32_t mant, one; };                 // 0x007fffff, 0x3f800000 held in registers
+
+// uniform in (0,1) scaled by 2^126, from the low 23 bits of r: ((r & m) + 0.5) * 2^-23 * 2^126.
+// One LOP3 builds the float 1.mantissa (the and-or needs its two constants in registers to
+// stay ONE instruction), one FFMA rescales it.
+__device__ __forceinline__ float uniform_big(uint32_t r, const RegConst &k)
+{
+	uint32_t b;
+	asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(b) : "r"(r), "r"(k.mant), "r"(k.one));     // (r & mant) | one
+	return fmaf(__uint_as_float(b), U_SCALE, U_OFFS);
+}
+
+// index of the first cumulative weight that exceeds t, as a FLOAT in {0..KP-1}:
+//     #{k < KP-1 : t > c_k} = sum_k sat((t - c_k) * 2^126)          (FFMA.SAT + FADD)
+// t and c_k are fp32 values whose difference is 0 or at least one ulp(t) >= 2^-126 in
+// magnitude (t >= 2^-24 * total, total >= P_FLOOR / K), so every term is exactly 0 or 1.
+// Padded populations have q = 0, hence c_k = total > t: they never count.
+template <int KP>
+__device__ __forceinline__ float pick_category(const float (&c)[KP], float ub)
+{
+	const float tb = ub * c[KP - 1];                                      // t * 2^126, t = u * total
+	float s[KP - 1];
+#pragma unroll
+	for (int k = 0; k < KP - 1; k++) s[k] = __saturatef(fmaf(c[k], -BIG126, tb));
+	// balanced tree: shorter dependency chain than a running sum
+#pragma unroll
+	for (int w = 1; w < KP - 1; w <<= 1)
+#pragma unroll
+		for (int k = 0; k + w < KP - 1; k += 2 * w) s[k] += s[k + w];
+	return s[0];
+}
+
+// Small non-negative integers (shared-memory addresses < 2^23, allele and population indices)
+// are the bit patterns of denormal floats, and FFMA on denormals is exact integer arithmetic
+// at full FMA-pipe rate (tools/ubench/denorm.cu).  All address arithmetic of the inner loop
+// is phrased that way: it costs one FFMA where the integer form costs LEA / IADD3 on the
+// half-rate ALU pipe, which is this kernel's second-busiest resource.
+__device__ __forceinline__ float as_dn(uint32_t v) { return __uint_as_float(v); }
+__device__ __forceinline__ float as_dn_signed(int v) { return __uint_as_float(v >= 0 ? (uint32_t)v : (0x80000000u | (uint32_t)(-v))); }
+
+// per-thread running state of one (chunk, individual)
+struct Acc {
+	float lgA, lgB, lgD;       // chunk totals of log2: new Z under g, new Z under g', old Z (g' - g)
+	float mA, mB, mD;          // the same within the current micro-tile (two-level fp32 summation)
+	int nsh_new;               // same-z heterozygotes on the new Z (the 2^-(g-1) factor of genofreq, mcmc.c:1692-1699)
+};
+
+struct Thr {
+	float hist_bias;           // shared address of this lane's tally replica column minus R * psm, as a signed denormal
+	float cnt_t;               // shared address of this thread's ancestry-counter column, as a denormal
+	float omh_g, h_g, omh_p, h_p;
+};
+
+// One genotype.  xw = packed allele pair (x0 | x1 << 16), zw = word holding the old pair
+// (z0 | z1 << 8) in its half H, r0/r1 = 32 random bits per copy, rowbf = shared address of
+// P[l][0][0] as a denormal.  Returns the new packed pair (z0 | z1 << 8).
+template <int KP, bool TF0, int LR, int H>
+__device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, uint32_t r1, float rowbf, const float (&q)[KP],
+                                             const Thr &t, Acc &acc, const RegConst &kc)
+{
+	const uint32_t x0 = __byte_perm((uint32_t)xw, 0u, 0x4410), x1 = __byte_perm((uint32_t)xw, 0u, 0x4432);
+	const float row0f = fmaf(as_dn(x0), (float)(KP * 4), rowbf), row1f = fmaf(as_dn(x1), (float)(KP * 4), rowbf);
+	const uint32_t row0 = __float_as_uint(row0f), row1 = __float_as_uint(row1f);
+	const bool het = (x0 != x1);
+	// ---- cumulative weights w_k = sum_{m<=k} Q_im P_m,l,x (mcmc.c:1141-1149)
+	float p0[KP], p1[KP], c0[KP], c1[KP];
+#pragma unroll
+	for (int v = 0; v < KP / 4; v++) {
+		const float4 t0 = lds_f4(row0 + 16 * v), t1 = lds_f4(row1 + 16 * v);
+		p0[4 * v] = t0.x; p0[4 * v + 1] = t0.y; p0[4 * v + 2] = t0.z; p0[4 * v + 3] = t0.w;
+		p1[4 * v] = t1.x; p1[4 * v + 1] = t1.y; p1[4 * v + 2] = t1.z; p1[4 * v + 3] = t1.w;
+	}
+	c0[0] = q[0] * p0[0];
+	c1[0] = q[0] * p1[0];
+#pragma unroll
+	for (int k = 1; k < KP; k++) { c0[k] = fmaf(q[k], p0[k], c0[k - 1]); c1[k] = fmaf(q[k], p1[k], c1[k - 1]); }
+	// ---- old-Z piece of update_G's ratio (log_ld_indv, mcmc.c:1752-1759): only same-z
+	//      homozygotes depend on g.  (The 2^-(g-1) count of same-z heterozygotes on the old
+	//      Z is the previous pass's nsh_new; indiv_epilogue carries it over.)
+	if (!TF0) {
+		const uint32_t zo0 = __byte_perm(zw, 0u, H ? 0x4442 : 0x4440), zo1 = __byte_perm(zw, 0u, H ? 0x4443 : 0x4441);
+		const float fo = lds_f(__float_as_uint(fmaf(as_dn(zo0), 4.0f, row0f)));
+		const float fe = (zo0 == zo1 && !het) ? fo : 1.0f;                // h + 1 * (1 - h) == 1 exactly
+		acc.mD += lg2_fast(fmaf(fe, t.omh_p, t.h_p)) - lg2_fast(fmaf(fe, t.omh_g, t.h_g));
+	}
+	// ---- categorical draws (disc_unif, random.c:403-430)
+	const float zf0 = pick_category<KP>(c0, uniform_big(r0, kc));
+	const float zf1 = pick_category<KP>(c1, uniform_big(r1, kc));
+	const float pa0f = fmaf(zf0, as_dn(4u), row0f), pa1f = fmaf(zf1, as_dn(4u), row1f);           // &P[l][x][z]
+	// ---- n[l][a][k] tally for the next update_P (mcmc.c:815-845) and the individual's
+	//      ancestry counts (mcmc.c:1176-1194): shared-memory RED
+	red_inc(__float_as_uint(fmaf(pa0f, (float)(1 << LR), t.hist_bias)));
+	red_inc(__float_as_uint(fmaf(pa1f, (float)(1 << LR), t.hist_bias)));
+	red_inc(__float_as_uint(fmaf(zf0, as_dn(4u * ZQ_THREADS), t.cnt_t)));
+	red_inc(__float_as_uint(fmaf(zf1, as_dn(4u * ZQ_THREADS), t.cnt_t)));
+	// ---- new-Z likelihood pieces (cal_lkh and the accepted-G selection)
+	float f0, f1;
+	bool same_n;
+	if (TF0) { f0 = c0[KP - 1]; f1 = c1[KP - 1]; same_n = true; }                                 // mcmc.c:1739-1749
+	else { f0 = lds_f(__float_as_uint(pa0f)); f1 = lds_f(__float_as_uint(pa1f)); same_n = (zf0 == zf1); }
+	const bool sh_n = same_n && !het;
+	acc.mA += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_g, t.h_g) : f1));
+	acc.mB += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_p, t.h_p) : f1));
+	acc.nsh_new += (same_n && het) ? 1 : 0;
+	return __float_as_uint(fmaf(zf1, as_dn(256u), zf0 * as_dn(1u)));                              // z0 | z1 << 8
+}
+
+// One micro-tile of 8 loci.  CHECK = false: no thread of the warp holds a missing genotype
+// here, so the per-genotype sign test and its divergence bookkeeping are compiled out.
+template <int KP, int ROUNDS, bool TF0, int LR, bool CHECK>
+__device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&zwo)[4], uint32_t (&zwn)[4], float rowb0f, float rowstridef,
+                                           uint32_t mt_global, uint32_t ig_global, const ZQArgs &a, const float (&q)[KP], const Thr &t,
+                                           Acc &acc, const RegConst &kc)
+{
+#pragma unroll
+	for (int pr = 0; pr < 4; ++pr) {
+		const u32x4 rnd = philox4x32<ROUNDS>(u32x4{mt_global, ig_global, a.iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
+		const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+		uint32_t pair[2];
+#pragma unroll
+		for (int h2 = 0; h2 < 2; ++h2) {
+			const int j = 2 * pr + h2;
+			const float rowbf = fmaf((float)j, rowstridef, rowb0f);
+			if (CHECK) {
+				pair[h2] = h2 ? (zwo[pr] >> 16) : (zwo[pr] & 0xFFFFu);
+				// the tiler stores a genotype with ANY missing copy as (-9,-9): one sign test
+				if (xw[j] >= 0) {
+					if (h2) pair[h2] = genotype<KP, TF0, LR, 1>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
+					else pair[h2] = genotype<KP, TF0, LR, 0>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
+				}
+			} else {
+				if (h2) pair[h2] = genotype<KP, TF0, LR, 1>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
+				else pair[h2] = genotype<KP, TF0, LR, 0>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
+			}
+		}
+		zwn[pr] = __byte_perm(pair[0], pair[1], 0x5410);
+	}
+}
+
+// --------------------------------------------------------------------------------------
+// zq_sweep: grid (locus chunks, individual blocks), 256 threads, one thread = one
+// individual, marching over the chunk's micro-tiles of 8 loci.
+//   global  : X  int16 [LT][Nloc][8][2]  two 128-bit loads per thread per micro-tile
+//             Z  int8  [LT][Nloc][8][2]  one 128-bit load + one 128-bit store
+//   shared  : P chunk [TL][A][KP] fp32, landed by ONE TMA bulk copy on an mbarrier;
+//             n chunk [TL][A][KP][R] int32 histogram, R lane-replicas to thin out conflicts,
+//             reduced and pushed to global n with RED at the end of the CTA;
+//             per-thread ancestry counters [KP][256] int32 (column tid: conflict-free RED)
+//   output  : per (chunk, individual) partials: K counts (u16) + 3 log-likelihood pieces
+// --------------------------------------------------------------------------------------
+template <int KP, int ROUNDS, bool TF0, int LR>
+__global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const ZQArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bar;
+	constexpr int R = 1 << LR;
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x;
+	const int chunk = blockIdx.x;
+	const int l0 = chunk * g.TL;
+	const int nl = min(g.TL, g.Lpad - l0);
+	const int nmt = nl / TILE;
+	const int rowsz = g.A * KP;                     // floats per locus
+	float *Psm = reinterpret_cast<float *>(smem_raw);
+	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);
+	int *cntsm = hist + (size_t)g.TL * rowsz * R;                   // [KP][ZQ_THREADS]
+	const int nbins = nl * rowsz;
+
+	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+	__syncthreads();
+	if (tid == 0) {
+		mbar_expect_tx(&bar, (uint32_t)nbins * 4u);
+		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
+	}
+	for (int j = tid; j < nbins * R; j += ZQ_THREADS) hist[j] = 0;
+#pragma unroll
+	for (int k = 0; k < KP; k++) cntsm[k * ZQ_THREADS + tid] = 0;
+	__syncthreads();
+	mbar_wait(&bar, 0);
+
+	const int Nloc = g.Nloc;
+	const int mt0 = l0 / TILE;
+	const int sub0 = blockIdx.y * g.subs_per_blk;
+	const int nsub_total = (Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
+	const int sub1 = min(sub0 + g.subs_per_blk, nsub_total);
+	const uint32_t psm = smem_addr(Psm);
+	const float rowstridef = as_dn((uint32_t)rowsz * 4u);           // bytes per locus in the P chunk
+	const float tilestridef = as_dn((uint32_t)rowsz * 4u * TILE);
+	const RegConst kc{a.k_mant, a.k_one};
+	Thr t;
+	t.hist_bias = as_dn_signed((int)smem_addr(hist) + (tid & (R - 1)) * 4 - (int)(psm << LR));
+	t.cnt_t = as_dn(smem_addr(cntsm) + (uint32_t)tid * 4u);
+
+	for (int sub = sub0; sub < sub1; ++sub) {
+		// Warps vote inside the loop (__any_sync), so a warp stays together: a warp with no
+		// individual at all leaves as a whole, and in the last, partly filled warp the surplus
+		// lanes shadow individual Nloc-1 with every genotype marked missing and nothing stored.
+		if (sub * ZQ_THREADS + (tid & ~31) >= Nloc) continue;
+		const bool live = sub * ZQ_THREADS + tid < Nloc;
+		const int il = live ? sub * ZQ_THREADS + tid : Nloc - 1;
+		{
+			float q[KP];
+			{
+				const float4 *qp = reinterpret_cast<const float4 *>(a.Qf + (size_t)il * KP);
+#pragma unroll
+				for (int v = 0; v < KP / 4; v++) {
+					float4 w = __ldg(qp + v);
+					q[4 * v] = w.x; q[4 * v + 1] = w.y; q[4 * v + 2] = w.z; q[4 * v + 3] = w.w;
+				}
+			}
+			const int2 gg = __ldg(a.gpair + il);
+			// 1 - h(g) = 2^-(g-1); exact in fp32 down to 2^-126, 0 beyond (g can start huge in mode 3)
+			t.omh_g = (gg.x <= 127) ? __int_as_float((128 - gg.x) << 23) : 0.0f;
+			t.omh_p = (gg.y <= 127) ? __int_as_float((128 - gg.y) << 23) : 0.0f;
+			t.h_g = 1.0f - t.omh_g;
+			t.h_p = 1.0f - t.omh_p;
+			Acc acc;
+			acc.lgA = acc.lgB = acc.lgD = 0.0f;
+			acc.nsh_new = 0;
+
+			const int4 *xp = reinterpret_cast<const int4 *>(a.Xt) + ((size_t)mt0 * Nloc + il) * 2;
+			int4 *zp = reinterpret_cast<int4 *>(a.Zt) + ((size_t)mt0 * Nloc + il);
+			const size_t xstride = (size_t)Nloc * 2, zstride = (size_t)Nloc;
+			const uint32_t ig_global = (uint32_t)(g.i0 + il);
+			float rowb0f = as_dn(psm);
+
+			// No software prefetch: with four resident warps per scheduler the ~1 us load latency
+			// of one warp hides behind the other three.
+			for (int mt = 0; mt < nmt; ++mt, rowb0f += tilestridef) {
+				const int4 xa = ldg_stream(xp + (size_t)mt * xstride), xb = ldg_stream(xp + (size_t)mt * xstride + 1);
+				const int4 zz = ldg_rw(zp + (size_t)mt * zstride);
+				const int dead = live ? 0 : -1;
+				const int xw[8] = {xa.x | dead, xa.y | dead, xa.z | dead, xa.w | dead, xb.x | dead, xb.y | dead, xb.z | dead, xb.w | dead};
+				const uint32_t zwo[4] = {(uint32_t)zz.x, (uint32_t)zz.y, (uint32_t)zz.z, (uint32_t)zz.w};
+				uint32_t zwn[4];
+				acc.mA = acc.mB = acc.mD = 0.0f;
+				// sign of the AND of all eight words: set iff every genotype is usable
+				const int any_missing = (xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6] | xw[7]) < 0;
+				if (__any_sync(0xffffffffu, any_missing))
+					micro_tile<KP, ROUNDS, TF0, LR, true>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, a, q, t, acc, kc);
+				else
+					micro_tile<KP, ROUNDS, TF0, LR, false>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, a, q, t, acc, kc);
+				if (live) stg_stream(zp + (size_t)mt * zstride, make_int4((int)zwn[0], (int)zwn[1], (int)zwn[2], (int)zwn[3]));
+				acc.lgA += acc.mA; acc.lgB += acc.mB; acc.lgD += acc.mD;
+			}
+			// ---- partials of this (chunk, individual)
+			if (live) {
+				uint32_t *pc = reinterpret_cast<uint32_t *>(a.pcnt + ((size_t)chunk * Nloc + il) * KP);
+				int *cnt_col = cntsm + tid;
+#pragma unroll
+				for (int j = 0; j < KP / 2; j++) {
+					const int ca = cnt_col[(2 * j) * ZQ_THREADS], cb = cnt_col[(2 * j + 1) * ZQ_THREADS];
+					cnt_col[(2 * j) * ZQ_THREADS] = 0;
+					cnt_col[(2 * j + 1) * ZQ_THREADS] = 0;
+					pc[j] = (uint32_t)ca | ((uint32_t)cb << 16);
+				}
+				double *pl = a.plog + (size_t)chunk * 3 * Nloc + il;
+				const double la = (double)acc.lgA * LN2_D, lb = (double)acc.lgB * LN2_D;
+				// TF0: the likelihood does not depend on Z, so the old-Z ratio is the new-Z one
+				pl[0] = TF0 ? (lb - la) - (double)acc.nsh_new * (double)(gg.y - gg.x) * LN2_D : (double)acc.lgD * LN2_D;
+				pl[(size_t)Nloc] = la - (double)acc.nsh_new * (double)(gg.x - 1) * LN2_D;
+				pl[(size_t)2 * Nloc] = lb - (double)acc.nsh_new * (double)(gg.y - 1) * LN2_D;
+				a.pnsh[(size_t)chunk * Nloc + il] = (uint16_t)acc.nsh_new;
+			}
+		}
+	}
+	__syncthreads();
+	// ---- reduce the replicas and push this CTA's tally into global n (RED, no return value)
+	int32_t *ng = a.n + (size_t)l0 * rowsz;
+	for (int b = tid; b < nbins; b += ZQ_THREADS) {
+		int s = 0;
+#pragma unroll
+		for (int r = 0; r < R; r++) s += hist[b * R + r];
+		if (s) atomicAdd(ng + b, s);
+	}
+}
+
+template <int KP, int LR>
+static cudaError_t launch_zq_kp(const ZQArgs &a, int rounds, cudaStream_t s)
+{
+	dim3 grid(a.geo.nchunks, a.geo.nblk), block(ZQ_THREADS);
+	const size_t sm = a.geo.zq_smem;
+#define IG_LAUNCH(RND, TF)                                                                                   \
+	do {                                                                                                 \
+		cudaError_t e = cudaFuncSetAttribute(zq_sweep_kernel<KP, RND, TF, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+		if (e != cudaSuccess) return e;                                                                  \
+		zq_sweep_kernel<KP, RND, TF, LR><<<grid, block, sm, s>>>(a);                                      \
+	} while (0)
+	if (a.type_freq == 0) { if (rounds == 7) IG_LAUNCH(7, true); else IG_LAUNCH(10, true); }
+	else { if (rounds == 7) IG_LAUNCH(7, false); else IG_LAUNCH(10, false); }
+#undef IG_LAUNCH
+	return cudaGetLastError();
+}
+
+cudaError_t launch_zq_sweep(const ZQArgs &a, int rounds, cudaStream_t s)
+{
+	const int key = a.geo.KP * 16 + a.geo.R;
+	switch (key) {
+#ifndef IG_FAST_BUILD
+	case 4 * 16 + 8: return launch_zq_kp<4, 3>(a, rounds, s);
+	case 4 * 16 + 1: return launch_zq_kp<4, 0>(a, rounds, s);
+	case 8 * 16 + 1: return launch_zq_kp<8, 0>(a, rounds, s);
+	case 16 * 16 + 8: return launch_zq_kp<16, 3>(a, rounds, s);
+	case 16 * 16 + 1: return launch_zq_kp<16, 0>(a, rounds, s);
+#endif
+	case 8 * 16 + 8: return launch_zq_kp<8, 3>(a, rounds, s);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+// Choose the decomposition: chunks of TL loci x blocks of individuals.  The tally of a chunk
+// is complete inside one CTA when nblk == 1 (no contention on global n); per-individual
+// pieces are always combined by indiv_epilogue in chunk order (deterministic).
+cudaError_t zq_configure(Geometry &g, int device)
+{
+	int sms = 148, smem_optin = 227 * 1024;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+	const int target_ctas = 2 * ZQ_MIN_CTAS * sms;         // ZQ_MIN_CTAS resident CTAs per SM, two waves
+	const size_t cnt_bytes = (size_t)g.KP * ZQ_THREADS * sizeof(int);
+	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / ZQ_MIN_CTAS - 2048 - cnt_bytes;
+	const size_t per_locus = (size_t)g.A * g.KP * 4;
+	const int nsub_total = (g.Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
+	// 8 lane-replicas of the tally histogram, or none when allelenum_max is so large that
+	// eight do not fit (many alleles spread the lanes over many bins anyway)
+	int R = 8;
+	if (per_locus * (1 + R) * TILE > budget) R = 1;
+	if (per_locus * (1 + R) * TILE > (size_t)smem_optin - 2048 - cnt_bytes) return cudaErrorInvalidConfiguration;
+	int tl_max = (int)(budget / (per_locus * (1 + R)));
+	if (tl_max < TILE) tl_max = (int)(((size_t)smem_optin - 2048 - cnt_bytes) / (per_locus * (1 + R)));
+	tl_max = (tl_max / TILE) * TILE;
+	if (tl_max < TILE) return cudaErrorInvalidConfiguration;
+	if (tl_max > 1024) tl_max = 1024;
+	int tl = ((g.Lpad + target_ctas - 1) / target_ctas + TILE - 1) / TILE * TILE;
+	if (tl < TILE) tl = TILE;
+	if (tl > tl_max) tl = tl_max;
+	g.TL = tl;
+	g.nchunks = (g.Lpad + tl - 1) / tl;
+	int nblk = 1;
+	if (g.nchunks < target_ctas) nblk = min(nsub_total, (target_ctas + g.nchunks - 1) / g.nchunks);
+	if (nblk < 1) nblk = 1;
+	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
+	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
+	g.R = R;
+	g.zq_smem = (size_t)tl * per_locus * (1 + R) + (size_t)g.KP * ZQ_THREADS * sizeof(int);
+	return cudaSuccess;
+}
+
+}  // namespace ig
