@@ -273,7 +273,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} diploid mode {mode} miss={miss}",
                        "parallelism": ("individual-sharded x%d" % world) if shard_ind else ("chains x%d" % world),
                        "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel()) / 1e9),
-                       "geometry": geo, "rng": f"philox4x32-{args.rng_rounds or 10}"},
+                       "geometry": geo, "rng": f"philox4x32-{args.rng_rounds or 7} (Z draw), philox4x32-10 (all other draws)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
                          "algorithmic_bytes_per_launch": algo_bytes_launch, "peak_source": peak_src,

@@ -68,7 +68,7 @@ typedef struct ig_config {
 	int32_t shard_size;
 	int32_t shard_rank;
 	int32_t shard_count;
-	int32_t rng_rounds;                 /* Philox rounds for the Z draw: 10 (default when 0) or 7 */
+	int32_t rng_rounds;                 /* Philox4x32 rounds of the bulk Z draw: 7 (default when 0; the Crush-resistant minimum of Salmon et al. SC11) or 10; every other draw uses 10 */
 	int32_t reserved[7];
 } ig_config;
 

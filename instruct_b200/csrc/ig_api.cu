@@ -100,7 +100,7 @@ struct ig_ctx {
 	cudaStream_t stream = nullptr;
 	bool loaded = false, chain_ready = false;
 	uint32_t iter = 0, key0 = 0, key1 = 0;
-	int rounds = 10;
+	int rounds = 7;
 	// device buffers
 	int16_t *Xt = nullptr;
 	int8_t *Zt = nullptr;
@@ -194,7 +194,7 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	g.A = 2;                   // fixed when the genotypes are loaded
 	g.REC = g.K + 3;
 	c->ns = (cfg->mode == 3) ? N : g.K;
-	c->rounds = (cfg->rng_rounds == 7) ? 7 : 10;
+	c->rounds = (cfg->rng_rounds == 10) ? 10 : 7;
 	c->key0 = (uint32_t)cfg->seed;
 	c->key1 = (uint32_t)(cfg->seed >> 32);
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(IG_ERR_CUDA, "stream creation failed"); }
