@@ -178,3 +178,73 @@ def write_reference_text(path, x: np.ndarray, labels=True, popdata=True, pop=Non
                 col = x[:, i, c]
                 tok.extend(missing if v < 0 else str(allele_base + 2 * int(v)) for v in col)
                 fh.write(" ".join(tok) + "\n")
+
+
+# ---------------------------------------------------------------------------------------
+# autotetraploid data (config 5): the reader keeps, per individual and locus, the SET of
+# distinct alleles observed (ascending dense codes) and how many there are ("alleleid"); the
+# dosage is hidden (transform_data2, data_interface.c:571-669).
+# ---------------------------------------------------------------------------------------
+@dataclass
+class TetraData:
+    x: np.ndarray            # int16 [L][N][4] distinct alleles, ascending, -1 padding (all -1 when missing)
+    nd: np.ndarray           # uint8 [L][N] number of distinct alleles, 0 = missing
+    allelenum: np.ndarray    # int32 [L]
+    K: int
+    S_true: np.ndarray
+    Q_true: np.ndarray
+    pop: np.ndarray
+    dosage: np.ndarray       # int16 [L][N][4] the four hidden copies (for write_reference_text_tetra)
+
+    @property
+    def L(self):
+        return self.x.shape[0]
+
+    @property
+    def N(self):
+        return self.x.shape[1]
+
+
+def observed_sets(copies: np.ndarray):
+    """[L][N][4] allele copies (negative = missing genotype) -> (x, nd) as the reader stores them."""
+    L, N, _ = copies.shape
+    srt = np.sort(copies, axis=2)
+    first = np.ones_like(srt, dtype=bool)
+    first[:, :, 1:] = srt[:, :, 1:] != srt[:, :, :-1]
+    missing = (copies < 0).any(axis=2)
+    nd = first.sum(axis=2).astype(np.uint8)
+    # stable partition: distinct values first, in ascending order
+    key = np.where(first, srt, np.int16(32767))
+    x = np.sort(key, axis=2).astype(np.int16)
+    x[x == 32767] = -1
+    x[missing] = -1
+    nd[missing] = 0
+    return np.ascontiguousarray(x), np.ascontiguousarray(nd)
+
+
+def make_tetra_dataset(N, L, K, A=4, miss=0.0, seed=0, own=0.9) -> TetraData:
+    """Autotetraploid synthetic data: four copies per locus from the individual's admixed
+    frequencies; with probability s (the home cluster's selfing rate) a genotype is replaced
+    by two copies of each of two of its own alleles, a crude stand-in for the excess
+    homozygosity selfing causes (the sampler is tested on conditionals, not on recovering s)."""
+    rng = np.random.default_rng(seed)
+    P = rng.dirichlet(np.ones(A), size=(K, L))
+    pop = np.arange(N) % K
+    Q = np.full((N, K), (1.0 - own) / max(K - 1, 1))
+    Q[np.arange(N), pop] = own if K > 1 else 1.0
+    S_k = np.linspace(0.1, 0.9, K) if K > 1 else np.array([0.5])
+    cumP = np.cumsum(P, axis=2)
+    cumQ = np.cumsum(Q, axis=1)
+    copies = np.empty((L, N, 4), dtype=np.int16)
+    for l in range(L):
+        anc = np.minimum((rng.random((N, 4))[:, :, None] > cumQ[:, None, :]).sum(axis=2), K - 1)
+        a = np.minimum((rng.random((N, 4))[:, :, None] > cumP[anc, l, :]).sum(axis=2), A - 1)
+        selfed = rng.random(N) < S_k[pop]
+        a[selfed, 2] = a[selfed, 0]
+        a[selfed, 3] = a[selfed, 1]
+        copies[l] = a
+    if miss > 0:
+        copies[rng.random((L, N)) < miss] = MISSING
+    copies, allelenum = recode_dense(copies)
+    x, nd = observed_sets(copies)
+    return TetraData(x=x, nd=nd, allelenum=allelenum, K=K, S_true=S_k, Q_true=Q, pop=pop, dosage=copies)

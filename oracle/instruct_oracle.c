@@ -213,6 +213,11 @@ static int draw_bracket(orc_rng *r, double *vec, int len)
 	return pick;
 }
 
+/* the same samplers on a bare stream, for oracle/tetra_oracle.c */
+double orc_rng_u01(orc_rng *r) { return u01(r); }
+void orc_rng_dirichlet(orc_rng *r, const double *alpha, int len, double *out, double add) { draw_dirichlet(r, alpha, len, out, add); }
+int orc_rng_bracket(orc_rng *r, double *vec, int len) { return draw_bracket(r, vec, len); }
+
 double orc_ran1(orc_model *m) { return u01(&m->rng); }
 double orc_rgamma(orc_model *m, double a, double b) { return draw_gamma(&m->rng, a, b); }
 double orc_rbeta(orc_model *m, double a, double b) { return draw_beta(&m->rng, a, b); }
@@ -411,6 +416,9 @@ static double trans_prob(int a, int b)
 	if (a == 1) return (b == 1) ? 0.90 : 0.05;
 	return 0.0;
 }
+
+double orc_rng_three_state(orc_rng *r, int *new_state, int cur) { return propose_three_state(r, new_state, cur); }
+double orc_trans_prob(int a, int b) { return trans_prob(a, b); }
 
 /* update_S_POP, mcmc.c:913-983 */
 void orc_update_S_POP(orc_model *m)

@@ -1,0 +1,61 @@
+"""Pins oracle/tetra_oracle.c (the autotetraploid CPU restatement) to the UNMODIFIED reference
+compiled in oracle/_ref/ (poly_geno.c through oracle/ref_harness_poly.c): genotype catalogues,
+the float log genotype-frequency tables and whole-chain running moments, bit for bit on
+identical Wichmann-Hill seeds.  CPU only."""
+import numpy as np
+import pytest
+
+from instruct_b200.synth import make_tetra_dataset
+from oracle.pyoracle import have_ref
+from oracle.pytetra import RefTetra, TetraOracle
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference once)")
+
+
+def _random_freq(rng, K, L, allelenum, Amax):
+    f = rng.dirichlet(np.ones(Amax), size=(K, L))
+    for l in range(L):
+        a = allelenum[l]
+        f[:, l, a:] = 0
+        f[:, l, :a] /= f[:, l, :a].sum(axis=1, keepdims=True)
+    return f
+
+
+@pytest.mark.parametrize("A,K", [(2, 2), (3, 3), (4, 3), (6, 2)])
+def test_catalogue_and_tables_bit_exact(A, K):
+    d = make_tetra_dataset(N=30, L=9, K=K, A=A, miss=0.05, seed=A)
+    o = TetraOracle(d.x, d.nd, d.allelenum, K)
+    r = RefTetra(d.x, d.nd, d.allelenum, K)
+    assert o.Gmax == r.Gmax
+    for l in range(d.L):
+        assert np.array_equal(o.genolist(l), r.genolist(l))
+    rng = np.random.default_rng(A)
+    f = _random_freq(rng, K, d.L, d.allelenum, o.Amax)
+    S = rng.uniform(0.02, 0.98, size=K)
+    o.freq[...] = f
+    o.self_rates[...] = S
+    o.tables()
+    ex, gf = r.tables(f, S)
+    assert np.array_equal(o.exfreq, ex)
+    assert np.array_equal(o.genofreq, gf)
+    # log frequencies are <= 0 (the reference aborts otherwise, poly_geno.c:2015-2019).  They do
+    # NOT sum to one: the monoallelic class re-uses a stale index (poly_geno.c:1984-1989), which
+    # the oracle reproduces as written.
+    for l in range(d.L):
+        n = len(o.genolist(l))
+        assert (gf[:, l, :n] <= 0).all()
+
+
+@pytest.mark.parametrize("A,K,miss,back_refl", [(4, 3, 0.05, 1), (3, 2, 0.0, 1), (2, 2, 0.1, 1), (5, 2, 0.02, 0)])
+def test_whole_chain_bit_exact(A, K, miss, back_refl):
+    d = make_tetra_dataset(N=36, L=10, K=K, A=A, miss=miss, seed=10 + A)
+    o = TetraOracle(d.x, d.nd, d.allelenum, K, back_refl=back_refl)
+    r = RefTetra(d.x, d.nd, d.allelenum, K, back_refl=back_refl)
+    o.setseeds(13, 4, 1972)
+    r.setseeds(13, 4, 1972)
+    initd = np.linspace(0.3, 0.7, K)
+    a = o.run_chain(50, 20, 3, ckrep=4, initd=initd)
+    b = r.run_chain(50, 20, 3, ckrep=4, initd=initd)
+    assert a["flag"] == b["flag"] == 0
+    for key in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
+        assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
