@@ -108,7 +108,15 @@ typedef enum ig_state_id {
 	IG_STATE_STATE = 12,   /* int32  [K]               UPMCMC.state (-e 0)                           */
 	IG_STATE_MASK = 13,    /* uint8  [L][Nloc]         missindx (derived from X; get only)           */
 	IG_STATE_GENO = 14,    /* int8   [L][Nloc][4]      UPMCMC.geno, tetraploid latent dosage          */
-	IG_STATE_ITER = 15     /* int64  [1]               sweep counter that keys the RNG               */
+	IG_STATE_ITER = 15,    /* int64  [1]               sweep counter that keys the RNG               */
+	/* autotetraploid tables (poly_geno.h:18-19), float [K][L][Gmax] natural logs, get only; setting
+	 * IG_STATE_TABLES (any 4-byte payload) recomputes all three from the current P, S and S' */
+	IG_STATE_TABLES = 16,      /* POLY.genofreq at the current selfing rates                        */
+	IG_STATE_TABLES_PROP = 17, /* genofreq_tmp of update_S_POP at the proposed rates                */
+	IG_STATE_EXFREQ = 18,      /* POLY.exfreq                                                       */
+	IG_STATE_SPROP = 19,   /* double [K]               proposed selfing rates of the current sweep    */
+	IG_STATE_DSTAT = 20,   /* double [K]               cal_lkd_props(k) - cal_lkd() (get only)        */
+	IG_STATE_GMAX = 21     /* int32  [1]               genotypes in the largest catalogue (get only)  */
 } ig_state_id;
 
 /* sweep phases for ig_run_phase (test hook; ig_sweep runs them in the reference's order) */
@@ -116,7 +124,8 @@ typedef enum ig_phase {
 	IG_PHASE_UPDATE_P = 1,     /* Dirichlet draw from the held tally (update_P, mcmc.c:846-857)     */
 	IG_PHASE_UPDATE_S = 2,     /* update_S_POP / update_S_IND / update_DP, then propose G           */
 	IG_PHASE_ZQ = 4,           /* fused update_G likelihoods + update_ZQ + tally + cal_lkh          */
-	IG_PHASE_ALPHA = 8         /* update_alpha + totallkh + empty-cluster sums                      */
+	IG_PHASE_ALPHA = 8,        /* update_alpha + totallkh + empty-cluster sums                      */
+	IG_PHASE_GENO = 16         /* ploid 4: update_geno + cal_lkd + tally (poly_geno.c:520,715)      */
 } ig_phase;
 
 const char *ig_version(void);

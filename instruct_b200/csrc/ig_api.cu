@@ -15,17 +15,16 @@
 #include <utility>
 #include <vector>
 
-#include "ig_internal.h"
+#include "ig_ctx.h"
 #include "philox.cuh"
 #include "samplers.cuh"
 
-using namespace ig;
 
 // --------------------------------------------------------------------------------------
 // errors
 // --------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static ig_status fail(ig_status st, const char *fmt, ...)
+ig_status ig_fail(ig_status st, const char *fmt, ...)
 {
 	va_list ap;
 	va_start(ap, fmt);
@@ -33,14 +32,9 @@ static ig_status fail(ig_status st, const char *fmt, ...)
 	va_end(ap);
 	return st;
 }
-#define CK(call)                                                                                           \
-	do {                                                                                               \
-		cudaError_t e_ = (call);                                                                       \
-		if (e_ != cudaSuccess) return fail(IG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-	} while (0)
 
 extern "C" const char *ig_last_error(void) { return g_err; }
-extern "C" const char *ig_version(void) { return "instruct_b200 0.1 (sm_100a)"; }
+extern "C" const char *ig_version(void) { return "instruct_b200 0.2 (sm_100a)"; }
 extern "C" int ig_device_count(void)
 {
 	int n = 0;
@@ -86,78 +80,12 @@ static ig_status nccl_load()
 		if (r_ != ncclSuccess) return fail(IG_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r_)); \
 	} while (0)
 
-// --------------------------------------------------------------------------------------
-// context
-// --------------------------------------------------------------------------------------
-struct DpCluster { double value; int num; int next; };
-
-struct ig_ctx {
-	ig_config cfg;
-	Geometry geo;
-	int ns;                    // length of S: K (mode 2) or N (mode 3)
-	int Npad;                  // records in ind: shard_count * shard_cap
-	int shard_cap;
-	cudaStream_t stream = nullptr;
-	bool loaded = false, chain_ready = false;
-	uint32_t iter = 0, key0 = 0, key1 = 0;
-	int rounds = 7;
-	// device buffers
-	int16_t *Xt = nullptr;
-	int8_t *Zt = nullptr;
-	float *P = nullptr;
-	double *P64 = nullptr;
-	int32_t *n = nullptr;
-	int32_t *allelenum = nullptr;
-	double *ind = nullptr;
-	float *Qf = nullptr;
-	int32_t *gprop = nullptr;
-	int2 *gpair = nullptr;
-	double *S = nullptr;
-	int32_t *state = nullptr;
-	DevScalars *sc = nullptr;
-	uint16_t *pcnt = nullptr;
-	double *plog = nullptr;
-	uint16_t *pnsh = nullptr;
-	int32_t *nhet = nullptr, *nsh = nullptr;
-	int32_t *cnt = nullptr;
-	double *llparts = nullptr;
-	float *initd_dev = nullptr;
-	double *scratch = nullptr;      // small device scratch (parity hooks)
-	double *gpart = nullptr;        // partials of the cooperative grid sums
-	int32_t *state2 = nullptr;      // double buffer of UPMCMC.state (-e 0)
-	Moments mom{};
-	// host mirrors
-	std::vector<int32_t> allelenum_h;
-	std::vector<double> ind_h, S_h;
-	// DP prior (host)
-	std::vector<DpCluster> dp;
-	std::vector<int> dp_of;
-	int dp_head = -1, dp_free = -1, dp_cnt = 0;
-	// NCCL
-	ncclComm_t comm = nullptr;
-	// profiling
-	bool profile = false;
-	std::vector<cudaEvent_t> ev;
-	int ev_used = 0;
-	int64_t launches = 0;
-};
-
-static uint32_t pad_k(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
-
-template <typename T>
-static cudaError_t dalloc(T **p, size_t n)
-{
-	cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
-	if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
-	return e;
-}
-
 extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 {
 	if (!cfg || !out) return fail(IG_ERR_ARG, "null argument");
 	*out = nullptr;
-	if (cfg->ploid != 2) return fail(IG_ERR_UNSUPPORTED, "ploid %d: only the diploid sampler is built in this library version", cfg->ploid);
-	if (cfg->mode != 2 && cfg->mode != 3) return fail(IG_ERR_UNSUPPORTED, "mode %d: only modes 2 and 3 are on the hot path", cfg->mode);
+	if (cfg->ploid != 2 && cfg->ploid != 4) return fail(IG_ERR_UNSUPPORTED, "ploid %d: 2 (diploid) or 4 (autotetraploid)", cfg->ploid);
+	if (cfg->ploid == 2 && cfg->mode != 2 && cfg->mode != 3) return fail(IG_ERR_UNSUPPORTED, "mode %d: only modes 2 and 3 are on the hot path", cfg->mode);
 	if (cfg->popnum < 1 || cfg->popnum > MAX_K) return fail(IG_ERR_UNSUPPORTED, "popnum %d outside 1..%d", cfg->popnum, MAX_K);
 	if (cfg->locinum < 1 || cfg->totalsize < 1) return fail(IG_ERR_ARG, "empty data set (N=%d, L=%d)", cfg->totalsize, cfg->locinum);
 	if (cfg->mode == 3 && cfg->prior_flag != 0 && cfg->prior_flag != 1) return fail(IG_ERR_ARG, "prior_flag must be 0 or 1");
@@ -198,6 +126,10 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	c->key0 = (uint32_t)cfg->seed;
 	c->key1 = (uint32_t)(cfg->seed >> 32);
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(IG_ERR_CUDA, "stream creation failed"); }
+	if (cfg->ploid == 4) {
+		ig_status st = tetra_create(c);
+		if (st != IG_OK) { cudaStreamDestroy(c->stream); delete c; return st; }
+	}
 	*out = c;
 	return IG_OK;
 }
@@ -220,6 +152,7 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
 	for (auto e : c->ev) cudaEventDestroy(e);
+	tetra_destroy(c);
 	free_all(c);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -291,11 +224,11 @@ extern "C" ig_status ig_load_genotypes(ig_ctx *c, const int16_t *x_host, const i
 	CK(dalloc(&c->allelenum, (size_t)g.Lpad));
 	CK(cudaMemcpyAsync(c->allelenum, allelenum_host, (size_t)g.L * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
 	int16_t *tmp = nullptr;
-	const size_t bytes = (size_t)g.L * g.Nloc * 2 * sizeof(int16_t);
+	const size_t bytes = (size_t)g.L * g.Nloc * c->cfg.ploid * sizeof(int16_t);
 	CK(cudaMalloc((void **)&tmp, bytes));
 	cudaError_t e = cudaMemcpyAsync(tmp, x_host, bytes, cudaMemcpyHostToDevice, c->stream);
 	if (e != cudaSuccess) { cudaFree(tmp); CK(e); }
-	ig_status st = finish_load(c, tmp);
+	ig_status st = c->tetra ? tetra_load(c, tmp) : finish_load(c, tmp);
 	cudaFree(tmp);
 	return st;
 }
@@ -310,7 +243,7 @@ extern "C" ig_status ig_load_genotypes_device(ig_ctx *c, const int16_t *x_dev, c
 	CK(cudaMemcpy(c->allelenum_h.data(), allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToHost));
 	CK(dalloc(&c->allelenum, (size_t)g.Lpad));
 	CK(cudaMemcpy(c->allelenum, allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToDevice));
-	return finish_load(c, x_dev);
+	return c->tetra ? tetra_load(c, x_dev) : finish_load(c, x_dev);
 }
 
 // --------------------------------------------------------------------------------------
@@ -476,7 +409,7 @@ static ig_status phase_update_P(ig_ctx *c)
 {
 	ig_status st = exchange_tally(c);
 	if (st != IG_OK) return st;
-	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1};
+	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, 0};
 	CK(launch_p_dirichlet(a, c->stream));
 	c->launches++;
 	return IG_OK;
@@ -527,6 +460,7 @@ static ig_status phase_alpha(ig_ctx *c)
 static ig_status one_sweep(ig_ctx *c)
 {
 	ig_status st;
+	if (c->tetra) return tetra_one_sweep(c);
 	c->iter++;
 	if ((st = phase_update_P(c)) != IG_OK) return st;      // update_P            mcmc.c:210
 	if ((st = phase_update_S(c)) != IG_OK) return st;      // update_S_* + G proposal  :211-212
@@ -539,6 +473,7 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	if (!c) return fail(IG_ERR_ARG, "null context");
 	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
 	CK(cudaSetDevice(c->cfg.device));
+	if (c->tetra) return tetra_chain_init(c, chain_id, initd);
 	const Geometry &g = c->geo;
 	c->key0 = (uint32_t)c->cfg.seed ^ (0x9E3779B9u * (uint32_t)(chain_id + 1));
 	c->key1 = (uint32_t)(c->cfg.seed >> 32) ^ (0x85EBCA6Bu * (uint32_t)(chain_id + 1));
@@ -621,6 +556,7 @@ extern "C" ig_status ig_run_phase(ig_ctx *c, int32_t mask)
 	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
 	CK(cudaSetDevice(c->cfg.device));
 	ig_status st;
+	if (c->tetra) return tetra_run_phase(c, mask);
 	if (mask & IG_PHASE_UPDATE_P) if ((st = phase_update_P(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_UPDATE_S) if ((st = phase_update_S(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_ZQ) if ((st = phase_zq(c, 0)) != IG_OK) return st;
@@ -746,6 +682,11 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 	const Geometry &g = c->geo;
 	ig_status st;
 	CK(cudaStreamSynchronize(c->stream));
+	if (c->tetra) {
+		bool handled = false;
+		st = tetra_get_state(c, id, host, bytes, &handled);
+		if (handled || st != IG_OK) return st;
+	}
 	switch (id) {
 	case IG_STATE_X:
 	case IG_STATE_Z: {
@@ -859,6 +800,11 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 	const Geometry &g = c->geo;
 	ig_status st;
 	CK(cudaStreamSynchronize(c->stream));
+	if (c->tetra) {
+		bool handled = false;
+		st = tetra_set_state(c, id, host, bytes, &handled);
+		if (handled || st != IG_OK) return st;
+	}
 	switch (id) {
 	case IG_STATE_Z: {
 		const size_t want = (size_t)g.L * g.Nloc * 2;

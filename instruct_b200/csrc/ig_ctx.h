@@ -1,0 +1,101 @@
+// ig_ctx.h -- the context object behind the C-ABI and the error helpers, shared by ig_api.cu
+// (diploid driver, hooks) and tetra.cu (autotetraploid driver).  Not part of the C-ABI.
+#pragma once
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ig_internal.h"
+
+ig_status ig_fail(ig_status st, const char *fmt, ...);
+#define fail ig_fail
+#define CK(call)                                                                                           \
+	do {                                                                                               \
+		cudaError_t e_ = (call);                                                                       \
+		if (e_ != cudaSuccess) return ig_fail(IG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+namespace ig { struct TetraState; }
+using namespace ig;
+
+struct DpCluster { double value; int num; int next; };
+
+struct ig_ctx {
+	ig_config cfg;
+	Geometry geo;
+	int ns;                    // length of S: K (mode 2) or N (mode 3)
+	int Npad;                  // records in ind: shard_count * shard_cap
+	int shard_cap;
+	cudaStream_t stream = nullptr;
+	bool loaded = false, chain_ready = false;
+	uint32_t iter = 0, key0 = 0, key1 = 0;
+	int rounds = 7;
+	// device buffers
+	int16_t *Xt = nullptr;
+	int8_t *Zt = nullptr;
+	float *P = nullptr;
+	double *P64 = nullptr;
+	int32_t *n = nullptr;
+	int32_t *allelenum = nullptr;
+	double *ind = nullptr;
+	float *Qf = nullptr;
+	int32_t *gprop = nullptr;
+	int2 *gpair = nullptr;
+	double *S = nullptr;
+	int32_t *state = nullptr;
+	DevScalars *sc = nullptr;
+	uint16_t *pcnt = nullptr;
+	double *plog = nullptr;
+	uint16_t *pnsh = nullptr;
+	int32_t *nhet = nullptr, *nsh = nullptr;
+	int32_t *cnt = nullptr;
+	double *llparts = nullptr;
+	float *initd_dev = nullptr;
+	double *scratch = nullptr;      // small device scratch (parity hooks)
+	double *gpart = nullptr;        // partials of the cooperative grid sums
+	int32_t *state2 = nullptr;      // double buffer of UPMCMC.state (-e 0)
+	Moments mom{};
+	// host mirrors
+	std::vector<int32_t> allelenum_h;
+	std::vector<double> ind_h, S_h;
+	// DP prior (host)
+	std::vector<DpCluster> dp;
+	std::vector<int> dp_of;
+	int dp_head = -1, dp_free = -1, dp_cnt = 0;
+	// NCCL
+	ncclComm_t comm = nullptr;
+	// profiling
+	bool profile = false;
+	std::vector<cudaEvent_t> ev;
+	int ev_used = 0;
+	int64_t launches = 0;
+	// autotetraploid driver (tetra.cu); null for ploid 2
+	ig::TetraState *tetra = nullptr;
+};
+
+static inline uint32_t pad_k(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n)
+{
+	cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+	if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+	return e;
+}
+
+
+// autotetraploid driver (tetra.cu)
+ig_status tetra_create(ig_ctx *c);
+void tetra_destroy(ig_ctx *c);
+ig_status tetra_load(ig_ctx *c, const int16_t *x_dev);
+ig_status tetra_chain_init(ig_ctx *c, int32_t chain_id, const float *initd);
+ig_status tetra_one_sweep(ig_ctx *c);
+ig_status tetra_run_phase(ig_ctx *c, int32_t mask);
+ig_status tetra_get_state(ig_ctx *c, int32_t id, void *host, size_t bytes, bool *handled);
+ig_status tetra_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes, bool *handled);

@@ -93,6 +93,7 @@ cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s);
 struct PArgs {
 	int32_t *n; float *P; double *P64; const int32_t *allelenum;
 	Geometry geo; uint32_t iter, key0, key1;
+	int mono_ok;             // 1: a locus with one allele gets P = 1 (update_P_auto has no allelenum > 1 guard, poly_geno.c:425)
 };
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s);
 

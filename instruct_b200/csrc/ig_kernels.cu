@@ -42,7 +42,7 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 	const size_t base = (size_t)l * g.A * g.KP + k;
 	const int Al = (l < g.L) ? a.allelenum[l] : 0;
 	if (k >= g.K || Al <= 1) {
-		for (int al = 0; al < g.A; al++) { a.P[base + (size_t)al * g.KP] = 0.0f; a.n[base + (size_t)al * g.KP] = 0; }
+		for (int al = 0; al < g.A; al++) { a.P[base + (size_t)al * g.KP] = (a.mono_ok && k < g.K && Al == 1 && al == 0) ? 1.0f : 0.0f; a.n[base + (size_t)al * g.KP] = 0; }
 		return;
 	}
 	Stream st((uint32_t)l, (uint32_t)k, a.iter, TAG_P, a.key0, a.key1);

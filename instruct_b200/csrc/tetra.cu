@@ -1,0 +1,1140 @@
+// tetra.cu -- the autotetraploid sweep (`-p 4 -ap 1`) on sm_100a.
+//
+// Reference order (mcmc_POP_tetra_selfing, poly_geno.c:97-112):
+//     update_P_auto -> calc_exfreq_auto -> update_S_POP -> update_ZQ -> update_geno -> cal_lkd
+// where update_S_POP alone makes 2K+1 full passes over the data (cal_lkd_props - cal_lkd per
+// population, poly_geno.c:625) and cal_lkd a further one.  Here a sweep is TWO passes:
+//
+//   p_dirichlet     P | n                              update_P_auto draw half      :425-434
+//   tetra_propose   S'_k = reflect(S_k + U(-.05,.05))  update_S_POP proposals       :604-612
+//   tetra_tables    log HWE table R, then the selfing tables of S and of S'          calc_exfreq_auto :1515,
+//                   for every (locus, population)                                    auto_genfreq :1803
+//   tetra_zs        PASS A over (geno, old z): the S statistics D_k = sum over genotypes whose four
+//                   copies all sit in k of (table_S'[g] - table_S[g])  -- everything else cancels in
+//                   cal_lkd_props(k) - cal_lkd(), and the K steps do not interact, so one pass
+//                   serves all K Metropolis steps;  then the new z | P, Q and the counts  :750-836
+//   tetra_accept    the K accept decisions, S and the tables of the accepted proposals   :628-634
+//   tetra_q         Q_i ~ Dirichlet(cnt_i + alpha)                                       :831-833
+//   tetra_geno      PASS B over (x, new z): dosage resolution | z, Q, tables (update_geno :520,
+//                   choose_two_auto :854, choose_tri_auto :907), the likelihood of the result
+//                   (cal_lkd :715, calc_genofq :1235) and the tally n[l][a][k] of the next update_P_auto
+//   tetra_lkh       indvlkh, totallkh, column sums of Q
+//
+// update_geno needs the Q drawn from the finished Z of the same sweep, which is why there are two
+// passes and not one.  Bytes per allele copy: pass A 3 (geno, old z, new z), pass B 4 (int16 x,
+// z, new geno) against the 6 of SURVEY.md section 8d.
+//
+// Restrictions of this version: single GPU per chain (chains still spread over GPUs), -e 1 only
+// (with -e 0 the reference's own tables are log(0), tests/test_tetra_oracle_vs_reference.py),
+// allelenum_max <= 6, alpha is never updated (the reference's tetraploid driver never calls
+// update_alpha).
+#include "ig_ctx.h"
+#include "philox.cuh"
+#include "samplers.cuh"
+#include "sweep_common.cuh"
+
+namespace ig {
+
+constexpr int TT = 4;                 // loci per micro-tile: one 128-bit z / geno vector, two 128-bit x vectors
+constexpr int TETRA_MAX_A = 6;
+constexpr int TETRA_THREADS = 256;
+#define LN2_D 0.69314718055994530942
+
+// genotype catalogue of one allele count n (auto_geno_num / auto_geno_list, poly_geno.c:1698-1800):
+// codes are the four alleles read as a base-n number, grouped by dosage class
+struct TetraCat {
+	int n;
+	int cls[5];      // iiii, iiij, iijj, iijk, ijkl
+	int total;
+	int code_off;    // into codes[]
+	int c2i_off;     // into c2i[] (n^4 entries: code -> index, 255 = not a catalogue genotype)
+};
+
+struct TetraState {
+	int ncat = 0, Gmax = 0, Lq = 0, LTq = 0;
+	TetraCat cat_h[TETRA_MAX_A + 1];
+	int16_t *Xq = nullptr;            // [LTq][Nloc][TT][4] distinct alleles ascending, -1 padding
+	int8_t *Zq = nullptr, *Gq = nullptr;   // [LTq][Nloc][TT][4]; geno = -1 on missing genotypes
+	TetraCat *cats = nullptr;
+	int32_t *codes = nullptr;
+	uint8_t *c2i = nullptr;
+	int32_t *loc_cat = nullptr;       // [Lq] catalogue of each locus (-1 beyond L)
+	float *exf = nullptr, *tabC = nullptr, *tabP = nullptr;    // [Lq][K][Gmax] natural logs
+	double *Sprop = nullptr, *dstat = nullptr;                  // [K]
+	int32_t *accepted = nullptr;      // [K]
+	float *dpart = nullptr;           // [nchunks][K][Nloc]
+	double *lpart = nullptr;          // [nchunks][Nloc]
+	double *part = nullptr;           // reduction scratch
+};
+
+// --------------------------------------------------------------------------------------
+// catalogue (host)
+// --------------------------------------------------------------------------------------
+static void build_catalogue(int n, std::vector<int> &code, int cls[5])
+{
+	cls[0] = n; cls[1] = n * (n - 1); cls[2] = n * (n - 1) / 2;
+	cls[3] = n * (n - 1) * (n - 2) / 2; cls[4] = n * (n - 1) * (n - 2) * (n - 3) / 24;
+	const int n2 = n * n, n3 = n2 * n;
+	for (int j = 0; j < n; j++) code.push_back(j * (n3 + n2 + n + 1));
+	for (int j = 0; j < n - 1; j++) for (int k = j + 1; k < n; k++) { code.push_back(j * (n3 + n2 + n) + k); code.push_back(k * (n3 + n2 + n) + j); }
+	for (int j = 0; j < n - 1; j++) for (int k = j + 1; k < n; k++) code.push_back(j * (n3 + n2) + k * (n + 1));
+	for (int j = 0; j < n - 2; j++) for (int k = j + 1; k < n - 1; k++) for (int a = k + 1; a < n; a++) {
+		code.push_back(j * (n3 + n2) + k * n + a);
+		code.push_back(k * (n3 + n2) + j * n + a);
+		code.push_back(a * (n3 + n2) + j * n + k);
+	}
+	for (int j = 0; j < n - 3; j++) for (int k = j + 1; k < n - 2; k++) for (int a = k + 1; a < n - 1; a++) for (int b = a + 1; b < n; b++)
+		code.push_back(j * n3 + k * n2 + a * n + b);
+}
+
+// --------------------------------------------------------------------------------------
+// layout transforms: canonical [L][Nloc][4] <-> tiled [LTq][Nloc][TT][4]
+// --------------------------------------------------------------------------------------
+template <typename T>
+__global__ void tile4_kernel(const T *canon, T *tiled, int L, int Nloc, int LTq, T fill)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (size_t)LTq * Nloc * TT) return;
+	const int j = (int)(t % TT), i = (int)((t / TT) % Nloc), mt = (int)(t / ((size_t)TT * Nloc));
+	const int l = mt * TT + j;
+	for (int c = 0; c < 4; c++) tiled[t * 4 + c] = (l < L) ? canon[((size_t)l * Nloc + i) * 4 + c] : fill;
+}
+template <typename T>
+__global__ void untile4_kernel(const T *tiled, T *canon, int L, int Nloc)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (size_t)L * Nloc) return;
+	const int i = (int)(t % Nloc), l = (int)(t / Nloc);
+	const size_t src = (((size_t)(l / TT) * Nloc + i) * TT + (l % TT)) * 4;
+	for (int c = 0; c < 4; c++) canon[t * 4 + c] = tiled[src + c];
+}
+static inline unsigned nb(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// --------------------------------------------------------------------------------------
+// tables: one thread per (locus, population)
+// --------------------------------------------------------------------------------------
+struct TabArgs {
+	const float *P; const int32_t *allelenum; const int32_t *loc_cat; const TetraCat *cats; const int32_t *codes; const uint8_t *c2i;
+	const double *S, *Sprop; float *exf, *tabC, *tabP;
+	int L, K, KP, A, Gmax, do_cur, do_prop;
+};
+
+// gaussj (poly_geno.c:2384) for the 3x3 float system of the triallelic class: Gauss-Jordan with
+// full pivoting, same pivot choice and elimination order
+__device__ void solve3(float a[3][3], float b[3])
+{
+	int piv[3] = {0, 0, 0}, row = 0, col = 0;
+	for (int i = 0; i < 3; i++) {
+		float big = 0.0f;
+		for (int j = 0; j < 3; j++)
+			if (piv[j] != 1)
+				for (int k = 0; k < 3; k++)
+					if (piv[k] == 0 && fabsf(a[j][k]) >= big) { big = fabsf(a[j][k]); row = j; col = k; }
+		++piv[col];
+		if (row != col) {
+			float t;
+			for (int k = 0; k < 3; k++) { t = a[row][k]; a[row][k] = a[col][k]; a[col][k] = t; }
+			t = b[row]; b[row] = b[col]; b[col] = t;
+		}
+		const float pivinv = (float)(1.0 / (double)a[col][col]);
+		a[col][col] = 1.0f;
+		for (int k = 0; k < 3; k++) a[col][k] *= pivinv;
+		b[col] *= pivinv;
+		for (int j = 0; j < 3; j++)
+			if (j != col) {
+				const float dum = a[j][col];
+				a[j][col] = 0.0f;
+				for (int k = 0; k < 3; k++) a[j][k] -= a[col][k] * dum;
+				b[j] -= b[col] * dum;
+			}
+	}
+}
+__device__ __forceinline__ bool in3(int v, const int *d, int len) { for (int i = 0; i < len; i++) if (d[i] == v) return true; return false; }
+// calc_val / calc_val2 (poly_geno.c:2307,2333): the ijkl code holding the given alleles
+__device__ int quad_with(const int *d, int v, int n)
+{
+	const int n2 = n * n, n3 = n2 * n;
+	if (v < d[0]) return v * n3 + d[0] * n2 + d[1] * n + d[2];
+	if (v > d[0] && v < d[1]) return d[0] * n3 + v * n2 + d[1] * n + d[2];
+	if (v > d[1] && v < d[2]) return d[0] * n3 + d[1] * n2 + v * n + d[2];
+	if (v > d[2]) return d[0] * n3 + d[1] * n2 + d[2] * n + v;
+	return 0;
+}
+__device__ int quad_with2(const int *d, int v1, int v2, int n)
+{
+	const int n2 = n * n, n3 = n2 * n;
+	if (v2 < d[1]) return v1 * n3 + v2 * n2 + d[1] * n + d[0];
+	if (v2 > d[1] && v2 < d[0] && v1 < d[1]) return v1 * n3 + d[1] * n2 + v2 * n + d[0];
+	if (v1 > d[1] && v2 < d[0]) return d[1] * n3 + v1 * n2 + v2 * n + d[0];
+	if (v1 > d[1] && v1 < d[0] && v2 > d[0]) return d[1] * n3 + v1 * n2 + d[0] * n + v2;
+	if (v1 > d[0]) return d[1] * n3 + d[0] * n2 + v1 * n + v2;
+	if (v1 < d[1] && v2 > d[0]) return v1 * n3 + d[1] * n2 + n * d[0] + v2;
+	return 0;
+}
+
+// auto_genfreq (poly_geno.c:1803-2028): log genotype frequencies under partial selfing, solved
+// class by class from the most to the least heterozygous, (I - sA) P = (1 - s) R.  Same float /
+// double mix and operation order as the reference; its re-use of a stale index in the
+// monoallelic class (:1984-1989) is reproduced as written.
+__device__ void genfreq_locus(float self, const TetraCat &c, const int32_t *code, const uint8_t *c2i, const float *R, float *P)
+{
+	const int n = c.n, n2 = n * n;
+	int hi = c.total, num = 0, d[3];
+	float temp;
+#define IDX(cd) ((int)c2i[(cd)])
+	if (n >= 4)
+		for (int i = hi - c.cls[4]; i < hi; i++) P[i] = (float)(log((double)(1 - self)) + (double)R[i] - log((double)(1 - self / 6)));
+	hi -= c.cls[4];
+	if (n >= 3)
+		for (int i = 0; i < c.cls[3] / 3; i++) {
+			const int base = hi - c.cls[3] + i * 3;
+			float A[3][3], v[3];
+			num = code[base];
+			for (int j = 2; j >= 0; j--) { d[j] = num % n; num /= n; }
+			temp = 0;
+			if (n >= 4)
+				for (int q = 0; q < n; q++)
+					if (!in3(q, d, 3)) { num = IDX(quad_with(d, q, n)); temp = (float)((double)temp + exp((double)P[num])); }
+			for (int j = 0; j < 3; j++) {
+				for (int q = 0; q < 3; q++) A[j][q] = (j == q) ? (float)(1 - (double)self * 10.0 / 36.0) : (float)(-(double)self / 9.0);
+				v[j] = (float)((double)self / 18.0 * (double)temp + (1.0 - (double)self) * exp((double)R[base + j]));
+			}
+			temp = v[0];
+			for (int j = 0; j < 3; j++) v[j] /= temp;
+			solve3(A, v);
+			for (int j = 0; j < 3; j++) P[base + j] = (float)(log((double)v[j]) + log((double)temp));
+		}
+	hi -= c.cls[3];
+	for (int i = hi - c.cls[2]; i < hi; i++) {                                  // iijj
+		num = code[i];
+		d[0] = num % n; num /= n2; d[1] = num % n;
+		temp = 0;
+		if (n >= 3)
+			for (int j = 0; j < n; j++) {
+				if (in3(j, d, 2)) continue;
+				if (d[0] < j) num = IDX(d[1] * n2 * (n + 1) + d[0] * n + j);
+				else if (d[0] > j) num = IDX(d[1] * n2 * (n + 1) + j * n + d[0]);
+				temp = (float)((double)temp + exp((double)P[num]) / 9.0 * (double)self);
+				if (d[1] < j) num = IDX(d[0] * n2 * (n + 1) + d[1] * n + j);
+				else if (d[1] > j) num = IDX(d[0] * n2 * (n + 1) + j * n + d[1]);
+				temp = (float)((double)temp + exp((double)P[num]) / 9.0 * (double)self);
+				num = IDX(j * n2 * (n + 1) + d[1] * n + d[0]);
+				temp = (float)((double)temp + exp((double)P[num]) / 36.0 * (double)self);
+				if (n >= 4)
+					for (int q = j + 1; q < n; q++)
+						if (!in3(q, d, 2)) { num = IDX(quad_with2(d, j, q, n)); temp = (float)((double)temp + exp((double)P[num]) / 36.0 * (double)self); }
+			}
+		P[i] = (float)(log((double)(1 - self) * exp((double)R[i]) + (double)temp) - log(1 - (double)self / 2.0));
+	}
+	hi -= c.cls[2];
+	for (int i = hi - c.cls[1]; i < hi; i++) {                                  // iiij
+		num = code[i];
+		d[0] = num % n; num /= n; d[1] = num % n;
+		if (d[0] < d[1]) num = IDX((d[0] * n2 + d[1]) * (n + 1));
+		else if (d[0] > d[1]) num = IDX((d[1] * n2 + d[0]) * (n + 1));
+		temp = (float)(8.0 / 36.0 * exp((double)P[num]) * (double)self);
+		if (n >= 3)
+			for (int j = 0; j < n; j++) {
+				if (in3(j, d, 2)) continue;
+				if (d[0] < j) num = IDX(d[1] * n2 * (n + 1) + d[0] * n + j);
+				else if (d[0] > j) num = IDX(d[1] * n2 * (n + 1) + j * n + d[0]);
+				temp = (float)((double)temp + exp((double)P[num]) / 9.0 * (double)self);
+			}
+		P[i] = (float)(log((double)(1 - self) * exp((double)R[i]) + (double)temp) - log(1 - (double)self / 2.0));
+	}
+	hi -= c.cls[1];
+	for (int i = hi - c.cls[0]; i < hi; i++) {                                  // iiii
+		num = code[i];
+		d[0] = num % n;
+		temp = 0;
+		for (int j = 0; j < n; j++) {
+			if (j == d[0]) continue;
+			num = IDX(d[0] * n * (n2 + n + 1) + j);
+			temp = (float)((double)temp + exp((double)P[num]) / 4.0 * (double)self);
+			if (d[0] < j) num = IDX(d[0] * n2 * (n + 1) + j * (n + 1));       // as written: otherwise the iiij index is re-used
+			temp = (float)((double)temp + exp((double)P[num]) / 36.0 * (double)self);
+			if (n >= 3)
+				for (int q = j + 1; q < n; q++)
+					if (q != d[0]) { num = IDX(d[0] * n2 * (n + 1) + j * n + q); temp = (float)((double)temp + exp((double)P[num]) / 36.0 * (double)self); }
+		}
+		P[i] = (float)(log((double)(1 - self) * exp((double)R[i]) + (double)temp) - log((double)(1 - self)));
+	}
+#undef IDX
+}
+
+__global__ void tetra_tables_kernel(const TabArgs a)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.L * a.K) return;
+	const int l = t / a.K, k = t % a.K;
+	const TetraCat c = a.cats[a.loc_cat[l]];
+	const int32_t *code = a.codes + c.code_off;
+	const uint8_t *c2i = a.c2i + c.c2i_off;
+	const int n = c.n;
+	float *R = a.exf + (size_t)t * a.Gmax;
+	double lf[TETRA_MAX_A];
+	for (int al = 0; al < n; al++) lf[al] = log((double)a.P[((size_t)l * a.A + al) * a.KP + k]);
+	// calc_exfreq_auto, poly_geno.c:1515-1577
+	int lo = 0, d[4], w;
+	for (int g = lo; g < lo + c.cls[0]; g++) R[g] = (float)lf[code[g] % n] * 4.0f;
+	lo += c.cls[0];
+	for (int g = lo; g < lo + c.cls[1]; g++) { w = code[g]; d[0] = w % n; w /= n; d[1] = w % n; R[g] = (float)(log(4.0) + lf[d[1]] * (double)3.0f + lf[d[0]]); }
+	lo += c.cls[1];
+	for (int g = lo; g < lo + c.cls[2]; g++) { w = code[g]; d[0] = w % n; w /= (n * n); d[1] = w % n; R[g] = (float)(log(6.0) + (lf[d[1]] + lf[d[0]]) * 2); }
+	lo += c.cls[2];
+	for (int g = lo; g < lo + c.cls[3]; g++) {
+		w = code[g];
+		for (int q = 0; q < 3; q++) { d[q] = w % n; w /= n; }
+		R[g] = (float)(log(12.0) + lf[d[2]] * 2 + lf[d[0]] + lf[d[1]]);
+	}
+	lo += c.cls[3];
+	for (int g = lo; g < lo + c.cls[4]; g++) {
+		w = code[g];
+		for (int q = 0; q < 4; q++) { d[q] = w % n; w /= n; }
+		float r = (float)log(24.0);
+		for (int q = 0; q < 4; q++) r += (float)lf[d[q]];
+		R[g] = r;
+	}
+	// calc_self_genofreq, poly_geno.c:1219: the rate arrives as double and is passed on as float
+	if (a.do_cur) genfreq_locus((float)a.S[k], c, code, c2i, R, a.tabC + (size_t)t * a.Gmax);
+	if (a.do_prop) genfreq_locus((float)a.Sprop[k], c, code, c2i, R, a.tabP + (size_t)t * a.Gmax);
+}
+
+// --------------------------------------------------------------------------------------
+// proposals and accepts of update_S_POP (poly_geno.c:604-634), -e 1
+// --------------------------------------------------------------------------------------
+__global__ void tetra_propose_kernel(const double *S, double *Sprop, int K, uint32_t iter, uint32_t key0, uint32_t key1)
+{
+	const int k = threadIdx.x;
+	if (k >= K) return;
+	Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
+	double p = st.uniform() * 2 * 0.05 - 0.05;
+	p += S[k];
+	if (p <= 0.0) p = 0.0 - p;
+	else if (p >= 1.0) p = 1.0 - (p - 1.0);
+	Sprop[k] = p;
+}
+
+constexpr int RED1 = 1024;
+__device__ double block_sum1(double v, double *sh)
+{
+	const int tid = threadIdx.x;
+	__syncthreads();
+	sh[tid] = v;
+	__syncthreads();
+	for (int s = RED1 / 2; s > 0; s >>= 1) { if (tid < s) sh[tid] += sh[tid + s]; __syncthreads(); }
+	const double r = sh[0];
+	__syncthreads();
+	return r;
+}
+
+// D_k = cal_lkd_props(k) - cal_lkd(): fixed launch shape => fixed summation tree
+__global__ void __launch_bounds__(RED1) tetra_accept_kernel(const float *dpart, int nchunks, int Nloc, int K, double *S, const double *Sprop,
+                                                           double *dstat, int32_t *accepted, DevScalars *sc, uint32_t iter, uint32_t key0, uint32_t key1, int decide)
+{
+	__shared__ double sh[RED1];
+	for (int k = 0; k < K; k++) {
+		double v = 0.0;
+		for (int c = 0; c < nchunks; c++) {
+			const float *row = dpart + ((size_t)c * K + k) * Nloc;
+			for (int i = threadIdx.x; i < Nloc; i += RED1) v += (double)row[i];
+		}
+		const double D = block_sum1(v, sh);
+		if (threadIdx.x == 0) {
+			dstat[k] = D;
+			if (decide) {
+				Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
+				(void)st.uniform();                                       // the proposal's draw
+				const double u = st.uniform();
+				// ran1() < exp(MIN2(0, mhratio)) (poly_geno.c:628); MIN2(0, NaN) == 0 accepts
+				const bool acc = (D != D) || (u < exp(fmin(0.0, D)));
+				accepted[k] = acc ? 1 : 0;
+				if (acc) { S[k] = Sprop[k]; sc->s_accepts++; }
+			}
+		}
+	}
+}
+// move_genofreq, poly_geno.c:738-748
+__global__ void tetra_select_kernel(float *tabC, const float *tabP, const int32_t *accepted, int L, int K, int Gmax)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (size_t)L * K * Gmax) return;
+	const int k = (int)((t / Gmax) % K);
+	if (accepted[k]) tabC[t] = tabP[t];
+}
+
+// --------------------------------------------------------------------------------------
+// PASS A: S statistics on the old z, then the new z and the ancestry counts
+// --------------------------------------------------------------------------------------
+struct ZsArgs {
+	int8_t *Zq; const int8_t *Gq; const float *P; const float *Qf;
+	const float *tabC, *tabP; const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
+	uint16_t *pcnt; float *dpart;
+	Geometry geo; int Gmax; int init;
+	uint32_t iter, key0, key1, k_mant, k_one;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bar;
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x, chunk = blockIdx.x;
+	const int l0 = chunk * g.TL, nl = min(g.TL, g.Lpad - l0), nmt = nl / TT, rowsz = g.A * KP;
+	float *Psm = reinterpret_cast<float *>(smem_raw);
+	int *cntsm = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);           // [KP][threads]
+	float *dsm = reinterpret_cast<float *>(cntsm + KP * TETRA_THREADS);         // [KP][threads]
+	int2 *locsm = reinterpret_cast<int2 *>(dsm + KP * TETRA_THREADS);           // [TL] (n, c2i offset)
+	const int nbins = nl * rowsz;
+	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+	__syncthreads();
+	if (tid == 0) { mbar_expect_tx(&bar, (uint32_t)nbins * 4u); tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar); }
+	for (int k = 0; k < KP; k++) { cntsm[k * TETRA_THREADS + tid] = 0; dsm[k * TETRA_THREADS + tid] = 0.0f; }
+	for (int j = tid; j < nl; j += TETRA_THREADS) {
+		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
+		locsm[j] = ci >= 0 ? make_int2(a.cats[ci].n, a.cats[ci].c2i_off) : make_int2(1, 0);
+	}
+	__syncthreads();
+	mbar_wait(&bar, 0);
+
+	const int Nloc = g.Nloc, mt0 = l0 / TT;
+	const int nsub_total = (Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
+	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
+	const uint32_t psm = smem_addr(Psm);
+	const RegConst kc{a.k_mant, a.k_one};
+	const float cnt_t = as_dn(smem_addr(cntsm) + (uint32_t)tid * 4u);
+
+	for (int sub = sub0; sub < sub1; ++sub) {
+		const int il = sub * TETRA_THREADS + tid;
+		if (il >= Nloc) continue;
+		float q[KP];
+#pragma unroll
+		for (int v = 0; v < KP / 4; v++) {
+			const float4 w = __ldg(reinterpret_cast<const float4 *>(a.Qf + (size_t)il * KP) + v);
+			q[4 * v] = w.x; q[4 * v + 1] = w.y; q[4 * v + 2] = w.z; q[4 * v + 3] = w.w;
+		}
+		const uint32_t ig_global = (uint32_t)(g.i0 + il);
+		int4 *zp = reinterpret_cast<int4 *>(a.Zq) + ((size_t)mt0 * Nloc + il);
+		const int4 *gp = reinterpret_cast<const int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
+		for (int mt = 0; mt < nmt; ++mt) {
+			const int4 gv = ldg_stream(gp + (size_t)mt * Nloc);
+			const int4 zv = ldg_rw(zp + (size_t)mt * Nloc);
+			const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
+			const uint32_t zo[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
+			uint32_t zn[4];
+#pragma unroll
+			for (int j = 0; j < TT; ++j) {
+				zn[j] = zo[j];
+				if ((gw[j] & 0x80u) != 0u) continue;                      // missing genotype: geno = -1
+				const int lj = mt * TT + j;
+				const uint32_t ga[4] = {gw[j] & 0xFFu, (gw[j] >> 8) & 0xFFu, (gw[j] >> 16) & 0xFFu, gw[j] >> 24};
+				// ---- S statistics on the OLD z (cal_lkd_props - cal_lkd, poly_geno.c:625): only genotypes
+				//      whose four copies sit in one population see that population's table
+				if (!a.init) {
+					const uint32_t z0 = zo[j] & 0xFFu;
+					if (zo[j] == z0 * 0x01010101u) {
+						const int2 li = locsm[lj];
+						const int code = ((ga[0] * li.x + ga[1]) * li.x + ga[2]) * li.x + ga[3];
+						const int gid = a.c2i[li.y + code];
+						const size_t o = ((size_t)(l0 + lj) * g.K + z0) * a.Gmax + gid;
+						dsm[z0 * TETRA_THREADS + tid] += __ldg(a.tabP + o) - __ldg(a.tabC + o);
+					}
+				}
+				// ---- new z: one categorical draw per copy, weights Q_ik P_k,l,geno_c (poly_geno.c:766-779)
+				const u32x4 rnd = philox4x32<10>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z | (uint32_t)j}, a.key0, a.key1);
+				const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+				const float rowbf = as_dn(psm + (uint32_t)(lj * rowsz) * 4u);
+				uint32_t packed = 0;
+#pragma unroll
+				for (int cidx = 0; cidx < 4; ++cidx) {
+					const uint32_t row = __float_as_uint(fmaf(as_dn(ga[cidx]), (float)(KP * 4), rowbf));
+					float p[KP], cw[KP];
+#pragma unroll
+					for (int v = 0; v < KP / 4; v++) {
+						const float4 w = lds_f4(row + 16 * v);
+						p[4 * v] = w.x; p[4 * v + 1] = w.y; p[4 * v + 2] = w.z; p[4 * v + 3] = w.w;
+					}
+					cw[0] = q[0] * p[0];
+#pragma unroll
+					for (int k = 1; k < KP; k++) cw[k] = fmaf(q[k], p[k], cw[k - 1]);
+					const float zf = pick_category<KP>(cw, uniform_big(rr[cidx], kc));
+					red_inc(__float_as_uint(fmaf(zf, as_dn(4u * TETRA_THREADS), cnt_t)));
+					packed |= __float_as_uint(zf * as_dn(1u)) << (8 * cidx);
+				}
+				zn[j] = packed;
+			}
+			stg_stream(zp + (size_t)mt * Nloc, make_int4((int)zn[0], (int)zn[1], (int)zn[2], (int)zn[3]));
+		}
+		// ---- partials of this (chunk, individual)
+		uint32_t *pc = reinterpret_cast<uint32_t *>(a.pcnt + ((size_t)chunk * Nloc + il) * KP);
+#pragma unroll
+		for (int j = 0; j < KP / 2; j++) {
+			const int ca = cntsm[(2 * j) * TETRA_THREADS + tid], cb = cntsm[(2 * j + 1) * TETRA_THREADS + tid];
+			cntsm[(2 * j) * TETRA_THREADS + tid] = 0;
+			cntsm[(2 * j + 1) * TETRA_THREADS + tid] = 0;
+			pc[j] = (uint32_t)ca | ((uint32_t)cb << 16);
+		}
+		for (int k = 0; k < g.K; k++) {
+			a.dpart[((size_t)chunk * g.K + k) * Nloc + il] = dsm[k * TETRA_THREADS + tid];
+			dsm[k * TETRA_THREADS + tid] = 0.0f;
+		}
+	}
+}
+
+// --------------------------------------------------------------------------------------
+// Q_i ~ Dirichlet(cnt_i + alpha), poly_geno.c:812-833
+// --------------------------------------------------------------------------------------
+__global__ void tetra_q_kernel(const uint16_t *pcnt, double *ind, float *Qf, int32_t *cnt_out, const DevScalars *sc, Geometry g,
+                               uint32_t iter, uint32_t key0, uint32_t key1)
+{
+	const int il = blockIdx.x * blockDim.x + threadIdx.x;
+	if (il >= g.Nloc) return;
+	int cnt[MAX_K];
+	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
+	for (int c = 0; c < g.nchunks; c++) {
+		const uint16_t *pc = pcnt + ((size_t)c * g.Nloc + il) * g.KP;
+		for (int k = 0; k < g.K; k++) cnt[k] += pc[k];
+	}
+	const int ig_global = g.i0 + il;
+	double *rec = ind + (size_t)ig_global * g.REC;
+	const double alpha = sc->alpha;
+	Stream sq((uint32_t)ig_global, 0u, iter, TAG_Q, key0, key1);
+	double qv[MAX_K], sum = 0.0;
+	for (int k = 0; k < g.K; k++) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
+	double slq = 0.0;
+	for (int k = 0; k < g.K; k++) {
+		const double qk = qv[k] / sum;
+		rec[k] = qk;
+		slq += log(qk);
+		Qf[(size_t)il * g.KP + k] = (float)qk;
+		cnt_out[(size_t)il * g.K + k] = cnt[k];
+	}
+	for (int k = g.K; k < g.KP; k++) Qf[(size_t)il * g.KP + k] = 0.0f;
+	rec[g.K + 1] = slq;
+	rec[g.K + 2] = 0.0;
+}
+
+// --------------------------------------------------------------------------------------
+// PASS B: dosage resolution | new z, Q, tables; likelihood; tally for the next update_P_auto
+// --------------------------------------------------------------------------------------
+struct GenoArgs {
+	const int16_t *Xq; const int8_t *Zq; int8_t *Gq; const float *P; const float *Qf; const float *tab;
+	const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
+	int32_t *n; double *lpart;
+	Geometry geo; int Gmax; int init;       // init: uniform resolution (initial_geno), no likelihood, no tally
+	uint32_t iter, key0, key1;
+};
+
+__device__ __forceinline__ int dosage_class(const int *gq)   // get_cat_auto, poly_geno.c:1313
+{
+	int seen[4], ns = 1, c0 = 0;
+	seen[0] = gq[0];
+	for (int i = 1; i < 4; i++) { bool f = false; for (int s = 0; s < ns; s++) f |= (seen[s] == gq[i]); if (!f) seen[ns++] = gq[i]; }
+	if (ns == 1) return 0;
+	if (ns == 2) { for (int i = 0; i < 4; i++) c0 += (gq[i] == seen[0]); return c0 == 2 ? 2 : 1; }
+	return ns == 3 ? 3 : 4;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const GenoArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bar;
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x, chunk = blockIdx.x, R = g.R;
+	const int l0 = chunk * g.TL, nl = min(g.TL, g.Lpad - l0), nmt = nl / TT, rowsz = g.A * KP;
+	float *Psm = reinterpret_cast<float *>(smem_raw);
+	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);            // [TL][A][KP][R]
+	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)g.TL * rowsz * R);
+	const int nbins = nl * rowsz;
+	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+	__syncthreads();
+	if (tid == 0) { mbar_expect_tx(&bar, (uint32_t)nbins * 4u); tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar); }
+	for (int j = tid; j < nbins * R; j += TETRA_THREADS) hist[j] = 0;
+	for (int j = tid; j < nl; j += TETRA_THREADS) {
+		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
+		locsm[j] = ci >= 0 ? make_int2(a.cats[ci].n, a.cats[ci].c2i_off) : make_int2(1, 0);
+	}
+	__syncthreads();
+	mbar_wait(&bar, 0);
+
+	const int Nloc = g.Nloc, mt0 = l0 / TT;
+	const int nsub_total = (Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
+	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
+	int *hist_t = hist + (tid & (R - 1));
+	const double LOGMULT[5] = {0.0, log(4.0), log(6.0), log(12.0), log(24.0)};
+
+	for (int sub = sub0; sub < sub1; ++sub) {
+		const int il = sub * TETRA_THREADS + tid;
+		if (il >= Nloc) continue;
+		float q[KP];
+#pragma unroll
+		for (int v = 0; v < KP / 4; v++) {
+			const float4 w = __ldg(reinterpret_cast<const float4 *>(a.Qf + (size_t)il * KP) + v);
+			q[4 * v] = w.x; q[4 * v + 1] = w.y; q[4 * v + 2] = w.z; q[4 * v + 3] = w.w;
+		}
+		const uint32_t ig_global = (uint32_t)(g.i0 + il);
+		const int4 *xp = reinterpret_cast<const int4 *>(a.Xq) + ((size_t)mt0 * Nloc + il) * 2;
+		const int4 *zp = reinterpret_cast<const int4 *>(a.Zq) + ((size_t)mt0 * Nloc + il);
+		int4 *gp = reinterpret_cast<int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
+		double ll = 0.0;
+		for (int mt = 0; mt < nmt; ++mt) {
+			const int4 xa = ldg_stream(xp + (size_t)mt * Nloc * 2), xb = ldg_stream(xp + (size_t)mt * Nloc * 2 + 1);
+			const int4 zv = ldg_stream(zp + (size_t)mt * Nloc);
+			const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+			const uint32_t zw[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
+			uint32_t gn[4];
+#pragma unroll
+			for (int j = 0; j < TT; ++j) {
+				gn[j] = 0xFFFFFFFFu;
+				// distinct alleles ascending, -1 padding; all -1 = missing (data_interface.c:636-650)
+				int al[4] = {(int)(short)(xw[2 * j] & 0xFFFF), xw[2 * j] >> 16, (int)(short)(xw[2 * j + 1] & 0xFFFF), xw[2 * j + 1] >> 16};
+				const int nd = (al[0] >= 0) + (al[1] >= 0) + (al[2] >= 0) + (al[3] >= 0);
+				if (nd == 0) continue;
+				const int lj = mt * TT + j;
+				const int2 li = locsm[lj];
+				const int n = li.x;
+				const int zc[4] = {(int)(zw[j] & 0xFFu), (int)((zw[j] >> 8) & 0xFFu), (int)((zw[j] >> 16) & 0xFFu), (int)(zw[j] >> 24)};
+				const bool same = (zw[j] == (uint32_t)zc[0] * 0x01010101u);
+				const float *tab = a.tab + ((size_t)(l0 + lj) * g.K + zc[0]) * a.Gmax;
+				int gq[4];
+				if (nd == 1) { gq[0] = gq[1] = gq[2] = gq[3] = al[0]; }
+				else if (nd == 4) { gq[0] = al[0]; gq[1] = al[1]; gq[2] = al[2]; gq[3] = al[3]; }
+				else {
+					// ---- three dosage resolutions (choose_two_auto :854, choose_tri_auto :907)
+					double w[3];
+					int pick;
+					if (a.init) { w[0] = 1.0 / 3.0; w[1] = 2.0 / 3.0; w[2] = 1.0; }     // choose_unif, poly_geno.c:842
+					else {
+						if (same) {
+							int code[3];
+							if (nd == 2) {
+								code[0] = al[0] * n * (n * n + n + 1) + al[1];
+								code[1] = al[1] * n * (n * n + n + 1) + al[0];
+								code[2] = (al[0] * n * n + al[1]) * (n + 1);
+							} else {
+								code[0] = al[0] * n * n * (n + 1) + al[1] * n + al[2];
+								code[1] = al[1] * n * n * (n + 1) + al[0] * n + al[2];
+								code[2] = al[2] * n * n * (n + 1) + al[0] * n + al[1];
+							}
+							for (int t = 0; t < 3; t++) w[t] = (double)__ldg(tab + a.c2i[li.y + code[t]]);
+						} else {
+							double lf[3];
+							for (int t = 0; t < nd; t++) {
+								const float *row = Psm + (lj * g.A + al[t]) * KP;
+								double f = 0.0;
+#pragma unroll
+								for (int k = 0; k < KP; k++) f += (double)q[k] * (double)row[k];
+								lf[t] = log(f);
+							}
+							if (nd == 2) {
+								w[0] = log(4.0) + 3 * lf[0] + lf[1];
+								w[1] = log(4.0) + 3 * lf[1] + lf[0];
+								w[2] = log(6.0) + 2 * lf[0] + 2 * lf[1];
+							} else {
+								w[0] = 2 * lf[0] + lf[1] + lf[2];
+								w[1] = 2 * lf[1] + lf[0] + lf[2];
+								w[2] = 2 * lf[2] + lf[1] + lf[0];
+							}
+						}
+						const double tm = w[0];
+						for (int t = 0; t < 3; t++) w[t] = exp(w[t] - tm);
+						w[1] += w[0];
+						w[2] += w[1];
+					}
+					const u32x4 rnd = philox4x32<10>(u32x4{(uint32_t)(l0 + lj), ig_global, a.iter, TAG_GENO}, a.key0, a.key1);
+					const double u = u01d(rnd.x, rnd.y) * w[2];
+					pick = (u <= w[0]) ? 0 : (u <= w[1] ? 1 : 2);
+					// two_allele_auto :2440 / tri_allele_auto :2509
+					if (nd == 2) {
+						if (pick == 0) { gq[0] = al[0]; gq[1] = al[0]; gq[2] = al[0]; gq[3] = al[1]; }
+						else if (pick == 1) { gq[0] = al[1]; gq[1] = al[1]; gq[2] = al[1]; gq[3] = al[0]; }
+						else { gq[0] = al[0]; gq[1] = al[0]; gq[2] = al[1]; gq[3] = al[1]; }
+					} else {
+						if (pick == 0) { gq[0] = al[0]; gq[1] = al[0]; gq[2] = al[1]; gq[3] = al[2]; }
+						else if (pick == 1) { gq[0] = al[1]; gq[1] = al[1]; gq[2] = al[0]; gq[3] = al[2]; }
+						else { gq[0] = al[2]; gq[1] = al[2]; gq[2] = al[0]; gq[3] = al[1]; }
+					}
+				}
+				gn[j] = (uint32_t)gq[0] | ((uint32_t)gq[1] << 8) | ((uint32_t)gq[2] << 16) | ((uint32_t)gq[3] << 24);
+				if (a.init) continue;
+				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286)
+				if (same) {
+					const int code = ((gq[0] * n + gq[1]) * n + gq[2]) * n + gq[3];
+					ll += (double)__ldg(tab + a.c2i[li.y + code]);
+				} else {
+					double s = LOGMULT[dosage_class(gq)];
+#pragma unroll
+					for (int cidx = 0; cidx < 4; cidx++) s += log((double)Psm[(lj * g.A + gq[cidx]) * KP + zc[cidx]]);
+					ll += s;
+				}
+				// ---- tally of the next update_P_auto over the latent genotype (poly_geno.c:403-424)
+#pragma unroll
+				for (int cidx = 0; cidx < 4; cidx++) atomicAdd(hist_t + ((lj * g.A + gq[cidx]) * KP + zc[cidx]) * R, 1);
+			}
+			*(gp + (size_t)mt * Nloc) = make_int4((int)gn[0], (int)gn[1], (int)gn[2], (int)gn[3]);
+		}
+		if (!a.init) a.lpart[(size_t)chunk * Nloc + il] = ll;
+	}
+	__syncthreads();
+	if (a.init) return;
+	int32_t *ng = a.n + (size_t)l0 * rowsz;
+	for (int b = tid; b < nbins; b += TETRA_THREADS) {
+		int s = 0;
+		for (int r = 0; r < R; r++) s += hist[b * R + r];
+		if (s) atomicAdd(ng + b, s);
+	}
+}
+
+// indvlkh, totallkh and the column sums of Q (cal_lkd :715, check_empty_cluster mcmc.c:1944)
+__global__ void __launch_bounds__(RED1) tetra_lkh_kernel(const double *lpart, double *ind, DevScalars *sc, Geometry g)
+{
+	__shared__ double sh[RED1];
+	double tot = 0.0, qc[MAX_K];
+	for (int k = 0; k < MAX_K; k++) qc[k] = 0.0;
+	for (int il = threadIdx.x; il < g.Nloc; il += RED1) {
+		double s = 0.0;
+		for (int c = 0; c < g.nchunks; c++) s += lpart[(size_t)c * g.Nloc + il];
+		double *rec = ind + (size_t)(g.i0 + il) * g.REC;
+		rec[g.K] = s;
+		tot += s;
+		for (int k = 0; k < g.K; k++) qc[k] += rec[k];
+	}
+	const double T = block_sum1(tot, sh);
+	if (threadIdx.x == 0) sc->totallkh = T;
+	for (int k = 0; k < g.K; k++) {
+		const double v = block_sum1(qc[k], sh);
+		if (threadIdx.x == 0) sc->qcol[k] = v;
+	}
+}
+
+// stand-alone tally over (z, geno), for state injection and the start of a chain
+__global__ void tetra_tally_kernel(const int8_t *Zq, const int8_t *Gq, int32_t *n, Geometry g, int LTq)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (size_t)LTq * g.Nloc * TT) return;
+	const int j = (int)(t % TT), mt = (int)(t / ((size_t)TT * g.Nloc)), l = mt * TT + j;
+	if (Gq[t * 4] < 0) return;
+	for (int c = 0; c < 4; c++) atomicAdd(&n[((size_t)l * g.A + Gq[t * 4 + c]) * g.KP + Zq[t * 4 + c]], 1);
+}
+
+// geno = -1 wherever the genotype is missing (the sweep kernels read the mask from there)
+__global__ void tetra_mask_geno_kernel(const int16_t *Xq, int8_t *Gq, size_t ngeno)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= ngeno) return;
+	if (Xq[t * 4] < 0) for (int c = 0; c < 4; c++) Gq[t * 4 + c] = -1;
+}
+
+__global__ void tetra_init_scalars_kernel(DevScalars *sc, double *S, const float *initd, int K, uint32_t key0, uint32_t key1)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	Stream st(0u, 1u, 0u, TAG_INIT, key0, key1);
+	sc->alpha = st.uniform() * 10;                       // initial_chn, poly_geno.c:386
+	sc->totallkh = 0.0; sc->sumlogq = 0.0; sc->cur_prop_ll = 0.0;
+	sc->alpha_accepts = 0; sc->s_accepts = 0; sc->flags = 0;
+	for (int k = 0; k < K; k++) S[k] = (double)initd[k];
+}
+
+// --------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------
+static cudaError_t tetra_configure(Geometry &g, int device)
+{
+	int sms = 148, smem_optin = 227 * 1024;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+	const int target = 4 * sms;
+	const size_t per_locus = (size_t)g.A * g.KP * 4;
+	const int R = 4;
+	const size_t fixedA = (size_t)2 * g.KP * TETRA_THREADS * 4 + 2048;
+	const size_t budget = (size_t)smem_optin / 2 - 1024;
+	int tl = (int)((budget - fixedA) / (per_locus * (1 + R) + 8));
+	tl = tl / TT * TT;
+	if (tl < TT) return cudaErrorInvalidConfiguration;
+	if (tl > 256) tl = 256;
+	int want = ((g.Lpad + target - 1) / target + TT - 1) / TT * TT;
+	if (want < TT) want = TT;
+	if (want < tl) tl = want;
+	g.TL = tl;
+	g.nchunks = (g.Lpad + tl - 1) / tl;
+	const int nsub_total = (g.Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
+	int nblk = 1;
+	if (g.nchunks < target) nblk = std::min(nsub_total, (target + g.nchunks - 1) / g.nchunks);
+	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
+	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
+	g.R = R;
+	g.zq_smem = 0;
+	return cudaSuccess;
+}
+static size_t smem_zs(const Geometry &g) { return (size_t)g.TL * g.A * g.KP * 4 + (size_t)2 * g.KP * TETRA_THREADS * 4 + (size_t)g.TL * 8; }
+static size_t smem_geno(const Geometry &g) { return (size_t)g.TL * g.A * g.KP * 4 * (1 + g.R) + (size_t)g.TL * 8; }
+
+}  // namespace ig
+
+using namespace ig;
+
+ig_status tetra_create(ig_ctx *c)
+{
+	if (c->cfg.autopoly != 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4: only the autotetraploid model (-ap 1) is built");
+	if (c->cfg.back_refl != 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4 needs -e 1: with -e 0 the reference's genotype tables are log(0)");
+	if (c->cfg.shard_count > 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4: individuals of one chain are not sharded in this version (spread chains over GPUs)");
+	c->tetra = new TetraState();
+	Geometry &g = c->geo;
+	TetraState *t = c->tetra;
+	t->Lq = (g.L + TT - 1) / TT * TT;
+	t->LTq = t->Lq / TT;
+	g.Lpad = t->Lq;
+	g.LT = t->LTq;
+	c->ns = g.K;
+	return IG_OK;
+}
+
+void tetra_destroy(ig_ctx *c)
+{
+	TetraState *t = c->tetra;
+	if (!t) return;
+	cudaFree(t->Xq); cudaFree(t->Zq); cudaFree(t->Gq); cudaFree(t->cats); cudaFree(t->codes); cudaFree(t->c2i); cudaFree(t->loc_cat);
+	cudaFree(t->exf); cudaFree(t->tabC); cudaFree(t->tabP); cudaFree(t->Sprop); cudaFree(t->dstat); cudaFree(t->accepted);
+	cudaFree(t->dpart); cudaFree(t->lpart);
+	delete t;
+	c->tetra = nullptr;
+}
+
+template <typename T>
+static cudaError_t dalloc0(T **p, size_t n)
+{
+	cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+	if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+	return e;
+}
+
+// x_dev: int16 [L][Nloc][4] distinct alleles ascending, -1 padding (include/instruct_b200.h)
+ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
+{
+	Geometry &g = c->geo;
+	TetraState *t = c->tetra;
+	int amax = 1;
+	for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] > amax) amax = c->allelenum_h[l];
+	if (amax > TETRA_MAX_A) return fail(IG_ERR_UNSUPPORTED, "ploid 4: allelenum_max %d > %d", amax, TETRA_MAX_A);
+	g.A = amax < 2 ? 2 : amax;
+	// catalogues, one per distinct allele count
+	std::vector<int> codes;
+	std::vector<uint8_t> c2i;
+	std::vector<int32_t> loc_cat(t->Lq, -1);
+	t->ncat = 0; t->Gmax = 1;
+	for (int n = 1; n <= amax; n++) {
+		bool used = false;
+		for (int l = 0; l < g.L; l++) used |= (c->allelenum_h[l] == n);
+		if (!used) continue;
+		TetraCat &cat = t->cat_h[t->ncat];
+		cat.n = n; cat.code_off = (int)codes.size(); cat.c2i_off = (int)c2i.size();
+		std::vector<int> cd;
+		build_catalogue(n, cd, cat.cls);
+		cat.total = (int)cd.size();
+		if (cat.total > t->Gmax) t->Gmax = cat.total;
+		c2i.resize(c2i.size() + (size_t)n * n * n * n, 255);
+		for (int gi = 0; gi < cat.total; gi++) { codes.push_back(cd[gi]); c2i[cat.c2i_off + cd[gi]] = (uint8_t)gi; }
+		for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] == n) loc_cat[l] = t->ncat;
+		t->ncat++;
+	}
+	CK(tetra_configure(g, c->cfg.device));
+	const size_t tiles = (size_t)t->LTq * g.Nloc * TT * 4;
+	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
+	const size_t tn = (size_t)t->Lq * g.K * t->Gmax;
+	CK(dalloc0(&t->Xq, tiles)); CK(dalloc0(&t->Zq, tiles)); CK(dalloc0(&t->Gq, tiles));
+	CK(dalloc0(&t->cats, (size_t)t->ncat)); CK(dalloc0(&t->codes, codes.size())); CK(dalloc0(&t->c2i, c2i.size())); CK(dalloc0(&t->loc_cat, (size_t)t->Lq));
+	CK(cudaMemcpy(t->cats, t->cat_h, sizeof(TetraCat) * t->ncat, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(t->codes, codes.data(), codes.size() * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(t->c2i, c2i.data(), c2i.size(), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(t->loc_cat, loc_cat.data(), loc_cat.size() * 4, cudaMemcpyHostToDevice));
+	CK(dalloc0(&t->exf, tn)); CK(dalloc0(&t->tabC, tn)); CK(dalloc0(&t->tabP, tn));
+	CK(dalloc0(&t->Sprop, (size_t)MAX_K)); CK(dalloc0(&t->dstat, (size_t)MAX_K)); CK(dalloc0(&t->accepted, (size_t)MAX_K));
+	CK(dalloc0(&t->dpart, (size_t)g.nchunks * g.K * g.Nloc)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * g.Nloc));
+	CK(dalloc0(&c->P, pn)); CK(dalloc0(&c->n, pn));
+	if (c->cfg.print_freq) CK(dalloc0(&c->P64, (size_t)g.K * g.L * g.A));
+	CK(dalloc0(&c->ind, (size_t)c->Npad * g.REC)); CK(dalloc0(&c->Qf, (size_t)g.Nloc * g.KP));
+	CK(dalloc0(&c->S, (size_t)MAX_K)); CK(dalloc0(&c->state, (size_t)MAX_K)); CK(dalloc0(&c->state2, (size_t)MAX_K)); CK(dalloc0(&c->sc, 1));
+	CK(dalloc0(&c->pcnt, (size_t)g.nchunks * g.Nloc * g.KP)); CK(dalloc0(&c->cnt, (size_t)g.Nloc * g.K));
+	CK(dalloc0(&c->initd_dev, (size_t)MAX_K)); CK(dalloc0(&c->scratch, (size_t)64));
+	CK(dalloc0(&c->mom.tot, 2)); CK(dalloc0(&c->mom.indvlkh, (size_t)g.N)); CK(dalloc0(&c->mom.qq, (size_t)g.N * g.K)); CK(dalloc0(&c->mom.qq2, (size_t)g.N * g.K));
+	CK(dalloc0(&c->mom.self, (size_t)g.K)); CK(dalloc0(&c->mom.self2, (size_t)g.K)); CK(dalloc0(&c->mom.gen, (size_t)g.N)); CK(dalloc0(&c->mom.gen2, (size_t)g.N));
+	CK(dalloc0(&c->mom.convg, (size_t)(c->cfg.ckrep > 0 ? c->cfg.ckrep : 1)));
+	if (c->cfg.print_freq) { CK(dalloc0(&c->mom.freq, (size_t)g.K * g.L * g.A)); CK(dalloc0(&c->mom.freq2, (size_t)g.K * g.L * g.A)); }
+	tile4_kernel<int16_t><<<nb((size_t)t->LTq * g.Nloc * TT, 256), 256, 0, c->stream>>>(x_dev, t->Xq, g.L, g.Nloc, t->LTq, (int16_t)-1);
+	CK(cudaGetLastError());
+	CK(cudaMemsetAsync(t->Gq, 0xFF, tiles, c->stream));
+	c->launches++;
+	CK(cudaStreamSynchronize(c->stream));
+	c->loaded = true;
+	return IG_OK;
+}
+
+// ---- phases ---------------------------------------------------------------------------
+template <typename K>
+static cudaError_t opt_smem(K kernel, size_t bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+
+static ig_status tetra_pass_a(ig_ctx *c, int init)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	ZsArgs a{t->Zq, t->Gq, c->P, c->Qf, t->tabC, t->tabP, t->loc_cat, t->cats, t->c2i, c->pcnt, t->dpart, g, t->Gmax, init,
+	         c->iter, c->key0, c->key1, 0x007fffffu, 0x3f800000u};
+	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
+	const size_t sm = smem_zs(g);
+	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
+	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
+	switch (g.KP) {
+	case 4: CK(opt_smem(tetra_zs_kernel<4>, sm)); tetra_zs_kernel<4><<<grid, block, sm, c->stream>>>(a); break;
+	case 8: CK(opt_smem(tetra_zs_kernel<8>, sm)); tetra_zs_kernel<8><<<grid, block, sm, c->stream>>>(a); break;
+	default: CK(opt_smem(tetra_zs_kernel<16>, sm)); tetra_zs_kernel<16><<<grid, block, sm, c->stream>>>(a); break;
+	}
+	CK(cudaGetLastError());
+	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status tetra_pass_b(ig_ctx *c, int init)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	GenoArgs a{t->Xq, t->Zq, t->Gq, c->P, c->Qf, t->tabC, t->loc_cat, t->cats, t->c2i, c->n, t->lpart, g, t->Gmax, init, c->iter, c->key0, c->key1};
+	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
+	const size_t sm = smem_geno(g);
+	switch (g.KP) {
+	case 4: CK(opt_smem(tetra_geno_kernel<4>, sm)); tetra_geno_kernel<4><<<grid, block, sm, c->stream>>>(a); break;
+	case 8: CK(opt_smem(tetra_geno_kernel<8>, sm)); tetra_geno_kernel<8><<<grid, block, sm, c->stream>>>(a); break;
+	default: CK(opt_smem(tetra_geno_kernel<16>, sm)); tetra_geno_kernel<16><<<grid, block, sm, c->stream>>>(a); break;
+	}
+	CK(cudaGetLastError());
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status tetra_tables(ig_ctx *c, int do_cur, int do_prop)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	TabArgs a{c->P, c->allelenum, t->loc_cat, t->cats, t->codes, t->c2i, c->S, t->Sprop, t->exf, t->tabC, t->tabP, g.L, g.K, g.KP, g.A, t->Gmax, do_cur, do_prop};
+	tetra_tables_kernel<<<nb((size_t)g.L * g.K, 64), 64, 0, c->stream>>>(a);
+	CK(cudaGetLastError());
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status tetra_q(ig_ctx *c)
+{
+	const Geometry &g = c->geo;
+	tetra_q_kernel<<<nb((size_t)g.Nloc, 128), 128, 0, c->stream>>>(c->pcnt, c->ind, c->Qf, c->cnt, c->sc, g, c->iter, c->key0, c->key1);
+	CK(cudaGetLastError());
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status tetra_lkh(ig_ctx *c)
+{
+	tetra_lkh_kernel<<<1, RED1, 0, c->stream>>>(c->tetra->lpart, c->ind, c->sc, c->geo);
+	CK(cudaGetLastError());
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status tetra_update_p(ig_ctx *c)
+{
+	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, 1};
+	CK(launch_p_dirichlet(a, c->stream));
+	c->launches++;
+	return IG_OK;
+}
+
+static ig_status tetra_s_begin(ig_ctx *c)
+{
+	TetraState *t = c->tetra;
+	tetra_propose_kernel<<<1, 32, 0, c->stream>>>(c->S, t->Sprop, c->geo.K, c->iter, c->key0, c->key1);
+	CK(cudaGetLastError());
+	c->launches++;
+	return tetra_tables(c, 1, 1);
+}
+
+static ig_status tetra_s_end(ig_ctx *c, int decide)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	tetra_accept_kernel<<<1, RED1, 0, c->stream>>>(t->dpart, g.nchunks, g.Nloc, g.K, c->S, t->Sprop, t->dstat, t->accepted, c->sc, c->iter, c->key0, c->key1, decide);
+	CK(cudaGetLastError());
+	if (decide) {
+		tetra_select_kernel<<<nb((size_t)g.L * g.K * t->Gmax, 256), 256, 0, c->stream>>>(t->tabC, t->tabP, t->accepted, g.L, g.K, t->Gmax);
+		CK(cudaGetLastError());
+		c->launches++;
+	}
+	c->launches++;
+	return IG_OK;
+}
+
+ig_status tetra_one_sweep(ig_ctx *c)
+{
+	ig_status st;
+	c->iter++;
+	if ((st = tetra_update_p(c)) != IG_OK) return st;           // update_P_auto          poly_geno.c:101
+	if ((st = tetra_s_begin(c)) != IG_OK) return st;            // calc_exfreq_auto, proposals and both tables  :102,:106
+	if ((st = tetra_pass_a(c, 0)) != IG_OK) return st;          // S statistics + update_ZQ (Z half)            :106,:108
+	if ((st = tetra_s_end(c, 1)) != IG_OK) return st;           // update_S_POP accepts
+	if ((st = tetra_q(c)) != IG_OK) return st;                  // update_ZQ (Q half)
+	if ((st = tetra_pass_b(c, 0)) != IG_OK) return st;          // update_geno + cal_lkd + tally                :110,:112
+	return tetra_lkh(c);
+}
+
+ig_status tetra_chain_init(ig_ctx *c, int32_t chain_id, const float *initd)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	c->key0 = (uint32_t)c->cfg.seed ^ (0x9E3779B9u * (uint32_t)(chain_id + 1));
+	c->key1 = (uint32_t)(c->cfg.seed >> 32) ^ (0x85EBCA6Bu * (uint32_t)(chain_id + 1));
+	c->iter = 0;
+	float init_h[MAX_K];
+	for (int k = 0; k < MAX_K; k++) init_h[k] = (initd && k < g.K) ? initd[k] : 0.5f;
+	if (!initd) {            // read_init without an -i file draws the starting rates from U(0,1) (initial.c:52-58)
+		Stream st(0u, 2u, 0u, TAG_INIT, c->key0, c->key1);
+		for (int k = 0; k < g.K; k++) init_h[k] = (float)st.uniform();
+	}
+	CK(cudaMemcpyAsync(c->initd_dev, init_h, sizeof(init_h), cudaMemcpyHostToDevice, c->stream));
+	tetra_init_scalars_kernel<<<1, 32, 0, c->stream>>>(c->sc, c->S, c->initd_dev, g.K, c->key0, c->key1);
+	CK(cudaGetLastError());
+	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
+	CK(launch_fill_f32(c->P, 1.0f, pn, c->stream));
+	CK(launch_fill_q_uniform(c->Qf, g, c->stream));
+	CK(cudaMemsetAsync(c->n, 0, pn * sizeof(int32_t), c->stream));
+	CK(cudaMemsetAsync(t->Zq, 0, (size_t)t->LTq * g.Nloc * TT * 4, c->stream));
+	c->launches += 3;
+	ig_status st;
+	if ((st = tetra_pass_b(c, 1)) != IG_OK) return st;          // initial_geno, poly_geno.c:316 (uniform resolution)
+	if ((st = tetra_pass_a(c, 1)) != IG_OK) return st;          // update_ZQ(init_flag = 1): uniform z, :87
+	if ((st = tetra_q(c)) != IG_OK) return st;
+	tetra_tally_kernel<<<nb((size_t)t->LTq * g.Nloc * TT, 256), 256, 0, c->stream>>>(t->Zq, t->Gq, c->n, g, t->LTq);
+	CK(cudaGetLastError());
+	c->launches++;
+	c->chain_ready = true;
+	return IG_OK;
+}
+
+ig_status tetra_run_phase(ig_ctx *c, int32_t mask)
+{
+	ig_status st;
+	if (mask & IG_PHASE_UPDATE_P) if ((st = tetra_update_p(c)) != IG_OK) return st;
+	if (mask & IG_PHASE_UPDATE_S) if ((st = tetra_s_begin(c)) != IG_OK) return st;
+	if (mask & IG_PHASE_ZQ) {
+		if ((st = tetra_pass_a(c, 0)) != IG_OK) return st;
+		if ((st = tetra_s_end(c, (mask & IG_PHASE_UPDATE_S) ? 1 : 0)) != IG_OK) return st;
+		if ((st = tetra_q(c)) != IG_OK) return st;
+	}
+	if (mask & IG_PHASE_GENO) {
+		if ((st = tetra_pass_b(c, 0)) != IG_OK) return st;
+		if ((st = tetra_lkh(c)) != IG_OK) return st;
+	}
+	CK(cudaStreamSynchronize(c->stream));
+	return IG_OK;
+}
+
+// state hooks: returns IG_ERR_UNSUPPORTED for ids that the common code handles
+ig_status tetra_get_state(ig_ctx *c, int32_t id, void *host, size_t bytes, bool *handled)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	*handled = true;
+	const size_t el = (size_t)g.L * g.Nloc * 4;
+	switch (id) {
+	case IG_STATE_X: case IG_STATE_Z: case IG_STATE_GENO: {
+		const size_t want = el * (id == IG_STATE_X ? 2 : 1);
+		if (bytes != want) return fail(IG_ERR_ARG, "X/Z/GENO: expected %zu bytes, got %zu", want, bytes);
+		void *tmp = nullptr;
+		CK(cudaMalloc(&tmp, want));
+		if (id == IG_STATE_X) untile4_kernel<int16_t><<<nb((size_t)g.L * g.Nloc, 256), 256, 0, c->stream>>>(t->Xq, (int16_t *)tmp, g.L, g.Nloc);
+		else untile4_kernel<int8_t><<<nb((size_t)g.L * g.Nloc, 256), 256, 0, c->stream>>>(id == IG_STATE_Z ? t->Zq : t->Gq, (int8_t *)tmp, g.L, g.Nloc);
+		cudaError_t e = cudaGetLastError();
+		if (e == cudaSuccess) e = cudaMemcpyAsync(host, tmp, want, cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		cudaFree(tmp);
+		CK(e);
+		return IG_OK;
+	}
+	case IG_STATE_MASK: {      // get_missing_tetra, data_interface.c:722-741: missing <=> no allele observed
+		if (bytes != (size_t)g.L * g.Nloc) return fail(IG_ERR_ARG, "MASK: expected %zu bytes, got %zu", (size_t)g.L * g.Nloc, bytes);
+		std::vector<int16_t> x(el);
+		bool h2 = false;
+		ig_status st = tetra_get_state(c, IG_STATE_X, x.data(), el * 2, &h2);
+		if (st != IG_OK) return st;
+		for (size_t q = 0; q < (size_t)g.L * g.Nloc; q++) ((uint8_t *)host)[q] = x[4 * q] < 0 ? 1 : 0;
+		return IG_OK;
+	}
+	case IG_STATE_TABLES: case IG_STATE_TABLES_PROP: case IG_STATE_EXFREQ: {
+		// float [K][L][Gmax], the reference's exfreq / genofreq layout
+		const size_t n = (size_t)g.K * g.L * t->Gmax;
+		if (bytes != n * 4) return fail(IG_ERR_ARG, "TABLES: expected %zu bytes, got %zu", n * 4, bytes);
+		std::vector<float> h((size_t)t->Lq * g.K * t->Gmax);
+		const float *src = id == IG_STATE_TABLES ? t->tabC : (id == IG_STATE_TABLES_PROP ? t->tabP : t->exf);
+		CK(cudaMemcpy(h.data(), src, h.size() * 4, cudaMemcpyDeviceToHost));
+		for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int q = 0; q < t->Gmax; q++)
+			((float *)host)[((size_t)k * g.L + l) * t->Gmax + q] = h[((size_t)l * g.K + k) * t->Gmax + q];
+		return IG_OK;
+	}
+	case IG_STATE_SPROP: case IG_STATE_DSTAT:
+		if (bytes != (size_t)g.K * 8) return fail(IG_ERR_ARG, "SPROP/DSTAT: expected %zu bytes", (size_t)g.K * 8);
+		CK(cudaMemcpy(host, id == IG_STATE_SPROP ? t->Sprop : t->dstat, bytes, cudaMemcpyDeviceToHost));
+		return IG_OK;
+	case IG_STATE_GMAX:
+		if (bytes != 4) return fail(IG_ERR_ARG, "GMAX: expected 4 bytes");
+		*(int32_t *)host = t->Gmax;
+		return IG_OK;
+	default:
+		*handled = false;
+		return IG_OK;
+	}
+}
+
+ig_status tetra_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes, bool *handled)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	*handled = true;
+	switch (id) {
+	case IG_STATE_Z: case IG_STATE_GENO: {
+		const size_t want = (size_t)g.L * g.Nloc * 4;
+		if (bytes != want) return fail(IG_ERR_ARG, "Z/GENO: expected %zu bytes, got %zu", want, bytes);
+		void *tmp = nullptr;
+		CK(cudaMalloc(&tmp, want));
+		cudaError_t e = cudaMemcpyAsync(tmp, host, want, cudaMemcpyHostToDevice, c->stream);
+		if (e == cudaSuccess) {
+			tile4_kernel<int8_t><<<nb((size_t)t->LTq * g.Nloc * TT, 256), 256, 0, c->stream>>>((const int8_t *)tmp, id == IG_STATE_Z ? t->Zq : t->Gq, g.L, g.Nloc, t->LTq,
+			                                                                               (int8_t)(id == IG_STATE_Z ? 0 : -1));
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess && id == IG_STATE_GENO) {
+			tetra_mask_geno_kernel<<<nb((size_t)t->LTq * g.Nloc * TT, 256), 256, 0, c->stream>>>(t->Xq, t->Gq, (size_t)t->LTq * g.Nloc * TT);
+			e = cudaGetLastError();
+		}
+		// n always mirrors (z, geno)
+		if (e == cudaSuccess) e = cudaMemsetAsync(c->n, 0, (size_t)g.Lpad * g.A * g.KP * 4, c->stream);
+		if (e == cudaSuccess) { tetra_tally_kernel<<<nb((size_t)t->LTq * g.Nloc * TT, 256), 256, 0, c->stream>>>(t->Zq, t->Gq, c->n, g, t->LTq); e = cudaGetLastError(); }
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		cudaFree(tmp);
+		CK(e);
+		return IG_OK;
+	}
+	case IG_STATE_SPROP:
+		if (bytes != (size_t)g.K * 8) return fail(IG_ERR_ARG, "SPROP: expected %zu bytes", (size_t)g.K * 8);
+		CK(cudaMemcpy(t->Sprop, host, bytes, cudaMemcpyHostToDevice));
+		return IG_OK;
+	case IG_STATE_TABLES: {
+		// recompute exfreq and BOTH tables from the current P, S and S' (no proposal draw)
+		ig_status st = tetra_tables(c, 1, 1);
+		if (st != IG_OK) return st;
+		CK(cudaStreamSynchronize(c->stream));
+		return IG_OK;
+	}
+	default:
+		*handled = false;
+		return IG_OK;
+	}
+}

@@ -50,7 +50,10 @@ class SeqData:
 
     @property
     def missindx(self):
-        """[L][N] uint8: 1 if any copy is missing (get_missing, data_interface.c:812-835)."""
+        """[L][N] uint8: 1 if any copy is missing (get_missing, data_interface.c:812-835); for
+        ploid 4, 1 if no allele was observed (get_missing_tetra, data_interface.c:722-741)."""
+        if self.ploid == 4:
+            return (self.seqdata < 0).all(axis=2).astype(np.uint8)
         return (self.seqdata < 0).any(axis=2).astype(np.uint8)
 
 
@@ -151,7 +154,7 @@ def mcmc_updating(data: SeqData, initial: Init, chn: int, cvg: Convg | None, see
     cfg = _config(data, initial.update, initial.burnin, initial.thinning, ckrep, seed, device)
     x = np.ascontiguousarray(data.seqdata, dtype=np.int16)
     an = np.ascontiguousarray(data.allelenum, dtype=np.int32)
-    ns = data.totalsize if data.mode == 3 else data.popnum
+    ns = data.totalsize if (data.mode == 3 and data.ploid == 2) else data.popnum
     res = _Result(data.totalsize, data.popnum, ns, data.locinum, data.allelenum_max, data.print_freq)
     initd = None
     if initial.initd is not None:
@@ -182,7 +185,8 @@ class Sampler:
         cap = -(-self.N // shard_count)
         self.i0 = shard_rank * cap
         self.Nloc = min(cap, self.N - self.i0)
-        self.ns = self.N if data.mode == 3 else self.K
+        self.ns = self.N if (data.mode == 3 and data.ploid == 2) else self.K
+        self.ploid = data.ploid
         if x_device_ptr is not None:
             check(self.lib.ig_load_genotypes_device(self.h, x_device_ptr, allelenum_device_ptr))
             self.A = None
@@ -255,8 +259,13 @@ class Sampler:
     # -- state hooks -------------------------------------------------------------------
     def _shape(self, sid):
         L, N, K, Nl, A = self.L, self.N, self.K, self.Nloc, self.A
+        pl = self.ploid
+        if sid in (_lib.STATE_TABLES, _lib.STATE_TABLES_PROP, _lib.STATE_EXFREQ):
+            return (K, L, self.gmax()), np.float32
         return {
-            _lib.STATE_X: ((L, Nl, 2), np.int16), _lib.STATE_Z: ((L, Nl, 2), np.int8),
+            _lib.STATE_X: ((L, Nl, pl), np.int16), _lib.STATE_Z: ((L, Nl, pl), np.int8),
+            _lib.STATE_GENO: ((L, Nl, 4), np.int8), _lib.STATE_SPROP: ((K,), np.float64),
+            _lib.STATE_DSTAT: ((K,), np.float64), _lib.STATE_GMAX: ((1,), np.int32),
             _lib.STATE_Q: ((N, K), np.float64), _lib.STATE_P: ((K, L, A), np.float64),
             _lib.STATE_ALPHA: ((1,), np.float64), _lib.STATE_S: ((self.ns,), np.float64),
             _lib.STATE_G: ((N,), np.int32), _lib.STATE_INDVLKH: ((N,), np.float64),
@@ -277,6 +286,16 @@ class Sampler:
         shape, dt = self._shape(sid)
         a = np.ascontiguousarray(np.asarray(value, dtype=dt).reshape(shape))
         check(self.lib.ig_set_state(self.h, sid, a.ctypes.data, a.nbytes))
+
+    def gmax(self):
+        a = np.zeros(1, dtype=np.int32)
+        check(self.lib.ig_get_state(self.h, _lib.STATE_GMAX, a.ctypes.data, a.nbytes))
+        return int(a[0])
+
+    def refresh_tables(self):
+        """ploid 4: recompute exfreq and both selfing tables from the current P, S and S'."""
+        a = np.zeros(1, dtype=np.int32)
+        check(self.lib.ig_set_state(self.h, _lib.STATE_TABLES, a.ctypes.data, a.nbytes))
 
     def geometry(self):
         a = np.zeros(8, dtype=np.int32)
