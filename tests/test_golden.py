@@ -57,3 +57,26 @@ def test_gelman_rubin_variants():
     # what the reference computes (check_converg.c:67): segments of chain 0 only
     assert abs(gelman_rubin_ref_compat(flat, 4, 12) - pyoracle.gelman_rubin_ref(flat, 4, 12)) < 1e-12
     assert gelman_rubin(tr) > 1.2      # four chains with shifted means do not look converged
+
+
+def test_tetra_fixture():
+    """Autotetraploid: catalogues, float tables and one whole chain against the golden outputs of
+    the reference's poly_geno.c (tools/make_golden.py tetra)."""
+    from oracle.pytetra import TetraOracle
+    g = np.load(os.path.join(GOLD, "tetra_chain.npz"))
+    K = int(g["K"])
+    o = TetraOracle(g["x"], g["nd"], g["allelenum"], K)
+    for l in range(o.L):
+        assert np.array_equal(o.genolist(l), g["codes"][l][: len(o.genolist(l))])
+    o.freq[...] = g["freq"]
+    o.self_rates[...] = g["S"]
+    o.tables()
+    # float tables: same binary libm here, but allow one float ulp across hosts
+    np.testing.assert_allclose(o.exfreq, g["exfreq"], rtol=2e-7, atol=0)
+    np.testing.assert_allclose(o.genofreq, g["genofreq"], rtol=2e-7, atol=0)
+    o.setseeds(*[int(v) for v in g["seeds"]])
+    c = o.run_chain(update=int(g["kw_update"]), burnin=int(g["kw_burnin"]), thinning=int(g["kw_thinning"]),
+                    ckrep=int(g["kw_ckrep"]), initd=g["kw_initd"])
+    assert c["flag"] == int(g["flag"]) == 0
+    for k in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
+        np.testing.assert_allclose(np.asarray(c[k]), g[k], rtol=1e-12, atol=0, err_msg=k)

@@ -15,6 +15,9 @@ Fixtures
                       the reference's own mcmc_updating()            (whole-chain pin)
   posterior_c1.npz    config-1 shaped data (K=2 N=200 L=10), posterior means of S, Q, log-lik
                       from R independent reference chains            (parity level 3)
+  tetra_chain.npz     autotetraploid: genotype catalogues, float tables on an injected state and
+                      the CHAIN moments of one short chain through mcmc_POP_tetra_selfing
+  posterior_tetra.npz autotetraploid posterior means from R independent reference chains
 """
 import os
 import sys
@@ -24,8 +27,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from instruct_b200.synth import make_dataset  # noqa: E402
+from instruct_b200.synth import make_dataset, make_tetra_dataset  # noqa: E402
 from oracle.pyoracle import Reference  # noqa: E402
+from oracle.pytetra import RefTetra  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -83,7 +87,45 @@ def posterior_fixture(R=12):
                         S_true=d.S_true, pop=d.pop, update=6000, burnin=2000, thinning=10)
 
 
+def tetra_fixtures(R=12):
+    """poly_geno.c through the harness: tables + one whole chain, and the posterior target."""
+    K = 3
+    d = make_tetra_dataset(N=36, L=10, K=K, A=4, miss=0.05, seed=21)
+    r = RefTetra(d.x, d.nd, d.allelenum, K)
+    rng = np.random.default_rng(22)
+    f = rng.dirichlet(np.ones(r.Amax), size=(K, d.L))
+    S = rng.uniform(0.05, 0.95, size=K)
+    ex, gf = r.tables(f, S)
+    r.setseeds(13, 4, 1972)
+    kw = dict(update=50, burnin=20, thinning=3, ckrep=4, initd=[0.3, 0.5, 0.7])
+    c = r.run_chain(**kw)
+    np.savez_compressed(os.path.join(OUT, "tetra_chain.npz"), x=d.x, nd=d.nd, allelenum=d.allelenum, K=K, freq=f, S=S,
+                        exfreq=ex, genofreq=gf, codes=np.stack([r.genolist(l) for l in range(d.L)]), seeds=[13, 4, 1972],
+                        **{f"kw_{k}": v for k, v in kw.items()}, **{k: np.asarray(v) for k, v in c.items()})
+    K = 2
+    d = make_tetra_dataset(N=120, L=30, K=K, A=4, miss=0.02, seed=23)
+    Ss, Qm, LL, alphas = [], [], [], []
+    for rep in range(R):
+        r = RefTetra(d.x, d.nd, d.allelenum, K)
+        r.setseeds(13 + 7 * rep, 4 + 3 * rep, 1972 + 11 * rep)
+        # the tetraploid driver draws alpha = ran1() * 10 once (poly_geno.c:386) and never updates it,
+        # so every chain samples a DIFFERENT posterior: record it (first Wichmann-Hill draw, random.c:34-47)
+        s1, s2, s3 = (171 * (13 + 7 * rep)) % 30269, (172 * (4 + 3 * rep)) % 30307, (170 * (1972 + 11 * rep)) % 30323
+        alphas.append(10 * ((s1 / 30269.0 + s2 / 30307.0 + s3 / 30323.0) % 1.0))
+        c = r.run_chain(update=1500, burnin=500, thinning=5, ckrep=5, initd=[0.3 + 0.02 * rep, 0.6 - 0.02 * rep])
+        o = np.argsort(c["qq"][d.pop == 0].mean(axis=0))[::-1]        # label switching: cluster 0 = home of pop 0
+        Ss.append(c["self_rates"][o]); Qm.append(c["qq"][:, o]); LL.append(c["totallkh"])
+        print("tetra posterior rep", rep, c["self_rates"][o], c["totallkh"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "posterior_tetra.npz"), x=d.x, nd=d.nd, allelenum=d.allelenum, K=K, S=np.array(Ss),
+                        Q=np.array(Qm).astype(np.float32), LL=np.array(LL), pop=d.pop, update=1500, burnin=500, thinning=5,
+                        alpha=np.array(alphas))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tetra":
+        os.makedirs(OUT, exist_ok=True)
+        tetra_fixtures()
+        sys.exit(0)
     os.makedirs(OUT, exist_ok=True)
     state_fixture(2, 3, 0.0, 1)
     state_fixture(5, 6, 0.06, 2)
@@ -92,3 +134,4 @@ if __name__ == "__main__":
     chain_fixture(3, 0)
     chain_fixture(3, 1)
     posterior_fixture()
+    tetra_fixtures()
