@@ -37,7 +37,10 @@ WORKLOADS = {
     "c1": (200, 10, 2, 8, 0.0, 2),              # configs[0]
     "c3": (5_000, 1_000, 4, 4, 0.0, 3),         # configs[2] (DP prior)
     "tiny": (600, 256, 8, 2, 0.0, 2),
+    "c5": (20_000, 20_000, 6, 4, 0.0, 2),       # configs[4]: autotetraploid (-p 4 -ap 1), per chain
+    "tiny5": (500, 128, 6, 4, 0.0, 2),
 }
+TETRA = {"c5", "tiny5"}
 
 
 def peaks():
@@ -107,6 +110,8 @@ def cpu_reference_sample(workload, steps, warmup, budget_s=20.0):
     from oracle import pyoracle
 
     N, L, K, A, miss, mode = WORKLOADS[workload]
+    if workload in TETRA:
+        return cpu_reference_sample_tetra(workload, steps, warmup, budget_s)
     # ~2.5 M allele copies per sweep at ~2.5 M copy-updates/s ~= 1 s per step
     target = 1_250_000
     n = min(N, 500)
@@ -139,6 +144,50 @@ def cpu_reference_sample(workload, steps, warmup, budget_s=20.0):
             "sweeps_per_sec_sample": done / dt, "ms_per_step": 1e3 * dt / done, "steps": done}
 
 
+def cpu_reference_sample_tetra(workload, steps, warmup, budget_s):
+    """Autotetraploid: whole short chains through the reference's own mcmc_POP_tetra_selfing (poly_geno.c:75)
+    at two lengths, differenced so that setup cancels -- the reference's sweep makes 2K+2 passes over the data."""
+    import numpy as np
+    from instruct_b200.synth import make_tetra_dataset
+    from oracle import pyoracle, pytetra
+
+    N, L, K, A, miss, mode = WORKLOADS[workload]
+    n, l = min(N, 300), min(L, 100)
+    d = make_tetra_dataset(N=n, L=l, K=K, A=A, miss=miss, seed=4)
+    copies = float((d.nd > 0).sum() * 4)
+    kind = "reference" if pyoracle.have_ref() else "port"
+    initd = np.linspace(0.2, 0.8, K)
+
+    def run(u):
+        if kind == "reference":
+            e = pytetra.RefTetra(d.x, d.nd, d.allelenum, K)
+            e.setseeds(13, 4, 1972)
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            saved = os.dup(1)
+            sys.stdout.flush()
+            os.dup2(devnull, 1)                     # the reference prints a banner per chain
+            try:
+                t0 = time.perf_counter()
+                e.run_chain(u, 1, 1, ckrep=1, initd=initd)
+                return time.perf_counter() - t0
+            finally:
+                os.dup2(saved, 1); os.close(devnull); os.close(saved)
+        e = pytetra.TetraOracle(d.x, d.nd, d.allelenum, K)
+        t0 = time.perf_counter()
+        e.run_chain(u, 1, 1, ckrep=1, initd=initd)
+        return time.perf_counter() - t0
+    u1 = 2
+    t1 = run(u1)
+    per = max(t1 / u1, 1e-3)
+    u2 = u1 + max(2, min(steps, int(budget_s / per)))
+    t2 = run(u2)
+    done, dt = u2 - u1, max(t2 - t1, 1e-9)
+    return {"value": copies * done / dt, "unit": "copy-updates/s", "cores": 1, "kind": kind,
+            "sample": f"autotetraploid N={d.N} L={d.L} K={K} A={A}: {done} sweeps in {dt:.2f} s (chains of {u1} and {u2} sweeps "
+                      f"differenced; one chain of the reference is single-threaded)",
+            "sweeps_per_sec_sample": done / dt, "ms_per_step": 1e3 * dt / done, "steps": done}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -150,7 +199,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "strong" if args.shard == "individuals" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} diploid mode {mode} (bounded sample, see cpu_baseline.sample)"},
+        "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + ("autotetraploid" if args.workload in TETRA else f"diploid mode {mode}") + " (bounded sample, see cpu_baseline.sample)"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "copy-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -167,7 +216,7 @@ def run_ours(args):
 
     from instruct_b200 import Sampler, SeqData, _lib
     from instruct_b200.shard import shard_bounds, broadcast_unique_id
-    from instruct_b200.synth import make_dataset_torch
+    from instruct_b200.synth import make_dataset_torch, make_tetra_dataset_torch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,20 +235,27 @@ def run_ours(args):
         N = args.N
     if args.L:
         L = args.L
-    shard_ind = world > 1 and args.shard == "individuals"
+    tetra = args.workload in TETRA
+    ploid = 4 if tetra else 2
+    shard_ind = world > 1 and args.shard == "individuals" and not tetra     # ploid 4: chains only
     if shard_ind:
         b, e = shard_bounds(N, world, rank)
         nloc, i0, count, srank, seed_data = e - b, b, world, rank, 4
     else:
         nloc, i0, count, srank, seed_data = N, 0, 1, 0, 4 + rank
-    x, an = make_dataset_torch(N, L, K, A=A, miss=miss, seed=seed_data, device=dev, i0=i0, n_local=nloc)
-    torch.cuda.synchronize()
-    usable = float((~(x < 0).any(dim=2)).sum().item())
-    copies_local = 2.0 * usable
+    if tetra:
+        x, an = make_tetra_dataset_torch(N, L, K, A=A, miss=miss, seed=seed_data, device=dev)
+        torch.cuda.synchronize()
+        usable = float((x[:, :, 0] >= 0).sum().item())
+    else:
+        x, an = make_dataset_torch(N, L, K, A=A, miss=miss, seed=seed_data, device=dev, i0=i0, n_local=nloc)
+        torch.cuda.synchronize()
+        usable = float((~(x < 0).any(dim=2)).sum().item())
+    copies_local = float(ploid) * usable
     # the genotype store is passed by device pointer (inputs resident in HBM); this SeqData only
     # carries the flags and the (L, Nloc, ploid) shape, through a zero-strided placeholder
-    shape_only = np.lib.stride_tricks.as_strided(np.zeros(1, dtype=np.int16), shape=(L, nloc, 2), strides=(0, 0, 0))
-    sd = SeqData(shape_only, np.zeros(L, dtype=np.int32), K, mode=mode, prior_flag=1 if args.workload == "c3" else 0,
+    shape_only = np.lib.stride_tricks.as_strided(np.zeros(1, dtype=np.int16), shape=(L, nloc, ploid), strides=(0, 0, 0))
+    sd = SeqData(shape_only, np.zeros(L, dtype=np.int32), K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0,
                  alpha_dpm=2.0)
     s = Sampler(sd, seed=args.seed, device=local, shard_rank=srank, shard_count=count, totalsize=N,
                 rng_rounds=args.rng_rounds, x_device_ptr=x.data_ptr(), allelenum_device_ptr=an.data_ptr())
@@ -233,7 +289,8 @@ def run_ours(args):
         copies_total = copies_local
     clk = clocks.stop() if rank == 0 else None
     geo = s.geometry()
-    algo_bytes_launch = 4.0 * copies_local           # 4 B per allele copy x copies one launch processes
+    # 4 B per allele copy (6 B for ploid 4: + latent genotype read and write) x copies one launch processes
+    algo_bytes_launch = (6.0 if tetra else 4.0) * copies_local
     zq_avg_ms = zq_ms / max(nz, 1)
     peak, peak_src = peaks()
     achieved = algo_bytes_launch / (zq_avg_ms * 1e-3) / 1e9 if zq_avg_ms > 0 else 0.0
@@ -247,7 +304,7 @@ def run_ours(args):
         xh = torch.empty(x.shape, dtype=torch.int16, pin_memory=True)
         xh.copy_(x)
         torch.cuda.synchronize()
-        sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, mode=mode, nstep_check_empty_cluster=10 ** 9)
+        sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, ploid=ploid, mode=mode, nstep_check_empty_cluster=10 ** 9)
         upd = args.steps + args.warmup
         t0 = time.perf_counter()
         ch = mcmc_updating(sd_h, Init(update=upd, burnin=args.warmup if args.warmup > 0 else 1, thinning=1), 0, None,
@@ -270,12 +327,12 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if (shard_ind or world == 1) else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "sweeps_per_sec": sweeps_per_s,
-            "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} diploid mode {mode} miss={miss}",
+            "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + ("autotetraploid" if tetra else f"diploid mode {mode}") + f" miss={miss}",
                        "parallelism": ("individual-sharded x%d" % world) if shard_ind else ("chains x%d" % world),
-                       "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel()) / 1e9),
+                       "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel() * (2 if tetra else 1)) / 1e9),
                        "geometry": geo, "rng": f"philox4x32-{args.rng_rounds or 7} (Z draw), philox4x32-10 (all other draws)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
+                         "traffic": None, "kernel": "tetra_zs + tetra_geno (the two passes of one sweep)" if tetra else "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
                          "algorithmic_bytes_per_launch": algo_bytes_launch, "peak_source": peak_src,
                          "share_of_step": zq_ms / ms if ms > 0 else None},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None,

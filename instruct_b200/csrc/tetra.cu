@@ -64,7 +64,7 @@ struct TetraState {
 	int32_t *accepted = nullptr;      // [K]
 	float *dpart = nullptr;           // [nchunks][K][Nloc]
 	double *lpart = nullptr;          // [nchunks][Nloc]
-	double *part = nullptr;           // reduction scratch
+	bool timing = false;              // a profiled sweep is between its PASS A start and PASS B end events
 };
 
 // --------------------------------------------------------------------------------------
@@ -891,7 +891,7 @@ static ig_status tetra_pass_a(ig_ctx *c, int init)
 	default: CK(opt_smem(tetra_zs_kernel<16>, sm)); tetra_zs_kernel<16><<<grid, block, sm, c->stream>>>(a); break;
 	}
 	CK(cudaGetLastError());
-	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
+	t->timing = timed;           // the closing event is recorded after PASS B: the two passes are one unit of work
 	c->launches++;
 	return IG_OK;
 }
@@ -909,6 +909,7 @@ static ig_status tetra_pass_b(ig_ctx *c, int init)
 	default: CK(opt_smem(tetra_geno_kernel<16>, sm)); tetra_geno_kernel<16><<<grid, block, sm, c->stream>>>(a); break;
 	}
 	CK(cudaGetLastError());
+	if (t->timing && !init) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; t->timing = false; }
 	c->launches++;
 	return IG_OK;
 }

@@ -248,3 +248,42 @@ def make_tetra_dataset(N, L, K, A=4, miss=0.0, seed=0, own=0.9) -> TetraData:
     copies, allelenum = recode_dense(copies)
     x, nd = observed_sets(copies)
     return TetraData(x=x, nd=nd, allelenum=allelenum, K=K, S_true=S_k, Q_true=Q, pop=pop, dosage=copies)
+
+
+def make_tetra_dataset_torch(N, L, K, A=4, miss=0.0, seed=0, device="cuda", own=0.9, chunk=1024):
+    """Config-5 scale generator: the model of :func:`make_tetra_dataset` in torch ops on ``device``,
+    written straight into an int16 [L][N][4] tensor of distinct-allele sets (ascending, -1 padding).
+    Loci are assumed to show all A alleles (true with overwhelming probability for N >= 1000)."""
+    import torch
+
+    gP = torch.Generator(device=device)
+    gP.manual_seed(seed)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 1000003 + 29)
+    pop = torch.arange(N, device=device) % K
+    Q = torch.full((N, K), (1.0 - own) / max(K - 1, 1), device=device)
+    Q[torch.arange(N, device=device), pop] = own if K > 1 else 1.0
+    cumQ = torch.cumsum(Q, 1)
+    S_k = torch.linspace(0.1, 0.9, K, device=device) if K > 1 else torch.tensor([0.5], device=device)
+    s_i = S_k[pop]
+    x = torch.empty((L, N, 4), dtype=torch.int16, device=device)
+    for l0 in range(0, L, chunk):
+        n = min(L, l0 + chunk) - l0
+        e = -torch.log(torch.rand((K, n, A), generator=gP, device=device).clamp_min(1e-12))
+        cumP = torch.cumsum(e / e.sum(2, keepdim=True), 2)
+        anc = (torch.rand((n, N, 4, 1), generator=g, device=device) > cumQ[None, :, None, :]).sum(3).clamp_(max=K - 1)
+        li = torch.arange(n, device=device)[:, None, None].expand(n, N, 4)
+        a = (torch.rand((n, N, 4, 1), generator=g, device=device) > cumP[anc, li]).sum(3).clamp_(max=A - 1)
+        selfed = torch.rand((n, N), generator=g, device=device) < s_i[None, :]
+        a[:, :, 2] = torch.where(selfed, a[:, :, 0], a[:, :, 2])
+        a[:, :, 3] = torch.where(selfed, a[:, :, 1], a[:, :, 3])
+        srt, _ = torch.sort(a, dim=2)
+        first = torch.ones_like(srt, dtype=torch.bool)
+        first[:, :, 1:] = srt[:, :, 1:] != srt[:, :, :-1]
+        key, _ = torch.sort(torch.where(first, srt, torch.full_like(srt, 32767)), dim=2)
+        key[key == 32767] = -1
+        if miss > 0:
+            key[torch.rand((n, N), generator=g, device=device) < miss] = -1
+        x[l0:l0 + n] = key.to(torch.int16)
+    allelenum = torch.full((L,), A, dtype=torch.int32, device=device)
+    return x, allelenum
