@@ -62,8 +62,8 @@ struct TetraState {
 	float *exf = nullptr, *tabC = nullptr, *tabP = nullptr;    // [Lq][K][Gmax] natural logs
 	double *Sprop = nullptr, *dstat = nullptr;                  // [K]
 	int32_t *accepted = nullptr;      // [K]
-	float *dpart = nullptr;           // [nchunks][K][Nloc]
-	double *lpart = nullptr;          // [nchunks][Nloc]
+	double *dpart = nullptr;          // [nchunks * nblk][K] per-CTA sums of the S statistics
+	float *lpart = nullptr;           // [nchunks][2][Nloc] likelihood partials: natural-log part, log2 part
 	bool timing = false;              // a profiled sweep is between its PASS A start and PASS B end events
 };
 
@@ -328,31 +328,24 @@ __device__ double block_sum1(double v, double *sh)
 	return r;
 }
 
-// D_k = cal_lkd_props(k) - cal_lkd(): fixed launch shape => fixed summation tree
-__global__ void __launch_bounds__(RED1) tetra_accept_kernel(const float *dpart, int nchunks, int Nloc, int K, double *S, const double *Sprop,
-                                                           double *dstat, int32_t *accepted, DevScalars *sc, uint32_t iter, uint32_t key0, uint32_t key1, int decide)
+// D_k = cal_lkd_props(k) - cal_lkd(), summed over the CTAs of PASS A in CTA order (fixed launch
+// shape => fixed summation order), then the K accept decisions
+__global__ void tetra_accept_kernel(const double *dpart, int nctas, int K, double *S, const double *Sprop,
+                                    double *dstat, int32_t *accepted, DevScalars *sc, uint32_t iter, uint32_t key0, uint32_t key1, int decide)
 {
-	__shared__ double sh[RED1];
-	for (int k = 0; k < K; k++) {
-		double v = 0.0;
-		for (int c = 0; c < nchunks; c++) {
-			const float *row = dpart + ((size_t)c * K + k) * Nloc;
-			for (int i = threadIdx.x; i < Nloc; i += RED1) v += (double)row[i];
-		}
-		const double D = block_sum1(v, sh);
-		if (threadIdx.x == 0) {
-			dstat[k] = D;
-			if (decide) {
-				Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
-				(void)st.uniform();                                       // the proposal's draw
-				const double u = st.uniform();
-				// ran1() < exp(MIN2(0, mhratio)) (poly_geno.c:628); MIN2(0, NaN) == 0 accepts
-				const bool acc = (D != D) || (u < exp(fmin(0.0, D)));
-				accepted[k] = acc ? 1 : 0;
-				if (acc) { S[k] = Sprop[k]; sc->s_accepts++; }
-			}
-		}
-	}
+	const int k = threadIdx.x;
+	if (k >= K) return;
+	double D = 0.0;
+	for (int c = 0; c < nctas; c++) D += dpart[(size_t)c * K + k];
+	dstat[k] = D;
+	if (!decide) return;
+	Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
+	(void)st.uniform();                                       // the proposal's draw
+	const double u = st.uniform();
+	// ran1() < exp(MIN2(0, mhratio)) (poly_geno.c:628); MIN2(0, NaN) == 0 accepts
+	const bool acc = (D != D) || (u < exp(fmin(0.0, D)));
+	accepted[k] = acc ? 1 : 0;
+	if (acc) { S[k] = Sprop[k]; atomicAdd(&sc->s_accepts, 1); }
 }
 // move_genofreq, poly_geno.c:738-748
 __global__ void tetra_select_kernel(float *tabC, const float *tabP, const int32_t *accepted, int L, int K, int Gmax)
@@ -369,7 +362,7 @@ __global__ void tetra_select_kernel(float *tabC, const float *tabP, const int32_
 struct ZsArgs {
 	int8_t *Zq; const int8_t *Gq; const float *P; const float *Qf;
 	const float *tabC, *tabP; const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
-	uint16_t *pcnt; float *dpart;
+	uint16_t *pcnt; double *dpart;
 	Geometry geo; int Gmax; int init;
 	uint32_t iter, key0, key1, k_mant, k_one;
 };
@@ -475,9 +468,23 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 			cntsm[(2 * j + 1) * TETRA_THREADS + tid] = 0;
 			pc[j] = (uint32_t)ca | ((uint32_t)cb << 16);
 		}
+	}
+	// ---- this CTA's share of D_k: fixed-shape tree over the thread columns (deterministic)
+	__syncthreads();
+	if (!a.init) {
+		double *red = reinterpret_cast<double *>(cntsm);                 // the counters are done: reuse their space
 		for (int k = 0; k < g.K; k++) {
-			a.dpart[((size_t)chunk * g.K + k) * Nloc + il] = dsm[k * TETRA_THREADS + tid];
-			dsm[k * TETRA_THREADS + tid] = 0.0f;
+			double v = (double)dsm[k * TETRA_THREADS + tid];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+			if ((tid & 31) == 0) red[tid >> 5] = v;
+			__syncthreads();
+			if (tid == 0) {
+				double t = 0.0;
+				for (int w = 0; w < TETRA_THREADS / 32; w++) t += red[w];
+				a.dpart[((size_t)blockIdx.y * gridDim.x + chunk) * g.K + k] = t;
+			}
+			__syncthreads();
 		}
 	}
 }
@@ -521,21 +528,21 @@ __global__ void tetra_q_kernel(const uint16_t *pcnt, double *ind, float *Qf, int
 struct GenoArgs {
 	const int16_t *Xq; const int8_t *Zq; int8_t *Gq; const float *P; const float *Qf; const float *tab;
 	const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
-	int32_t *n; double *lpart;
+	int32_t *n; float *lpart;
 	Geometry geo; int Gmax; int init;       // init: uniform resolution (initial_geno), no likelihood, no tally
 	uint32_t iter, key0, key1;
 };
 
-__device__ __forceinline__ int dosage_class(const int *gq)   // get_cat_auto, poly_geno.c:1313
+__device__ __forceinline__ float ex2_fast(float x)            // MUFU.EX2
 {
-	int seen[4], ns = 1, c0 = 0;
-	seen[0] = gq[0];
-	for (int i = 1; i < 4; i++) { bool f = false; for (int s = 0; s < ns; s++) f |= (seen[s] == gq[i]); if (!f) seen[ns++] = gq[i]; }
-	if (ns == 1) return 0;
-	if (ns == 2) { for (int i = 0; i < 4; i++) c0 += (gq[i] == seen[0]); return c0 == 2 ? 2 : 1; }
-	return ns == 3 ? 3 : 4;
+	float r;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
 }
 
+// The reference evaluates the resolution weights and the likelihood in double (libm log / exp); here
+// they are fp32 with MUFU.LG2 / MUFU.EX2: the weights carry ~1e-6 relative error (the z draw's fp32
+// weights carry as much), the likelihood sums stay inside the 1e-6 gate (tests/test_gpu_tetra.py).
 template <int KP>
 __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const GenoArgs a)
 {
@@ -563,7 +570,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 	const int nsub_total = (Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
 	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
 	int *hist_t = hist + (tid & (R - 1));
-	const double LOGMULT[5] = {0.0, log(4.0), log(6.0), log(12.0), log(24.0)};
+	const float LOG2E = 1.4426950408889634f;
+	const float LG2_6 = 2.584962500721156f;
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		const int il = sub * TETRA_THREADS + tid;
@@ -578,104 +586,89 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 		const int4 *xp = reinterpret_cast<const int4 *>(a.Xq) + ((size_t)mt0 * Nloc + il) * 2;
 		const int4 *zp = reinterpret_cast<const int4 *>(a.Zq) + ((size_t)mt0 * Nloc + il);
 		int4 *gp = reinterpret_cast<int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
-		double ll = 0.0;
+		float ll_nat = 0.0f, ll_lg2 = 0.0f;      // natural-log part (tables, multiplicities) and log2 part (allele frequencies)
 		for (int mt = 0; mt < nmt; ++mt) {
 			const int4 xa = ldg_stream(xp + (size_t)mt * Nloc * 2), xb = ldg_stream(xp + (size_t)mt * Nloc * 2 + 1);
 			const int4 zv = ldg_stream(zp + (size_t)mt * Nloc);
 			const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 			const uint32_t zw[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
 			uint32_t gn[4];
+			float m_nat = 0.0f, m_lg2 = 0.0f;
 #pragma unroll
 			for (int j = 0; j < TT; ++j) {
 				gn[j] = 0xFFFFFFFFu;
 				// distinct alleles ascending, -1 padding; all -1 = missing (data_interface.c:636-650)
-				int al[4] = {(int)(short)(xw[2 * j] & 0xFFFF), xw[2 * j] >> 16, (int)(short)(xw[2 * j + 1] & 0xFFFF), xw[2 * j + 1] >> 16};
-				const int nd = (al[0] >= 0) + (al[1] >= 0) + (al[2] >= 0) + (al[3] >= 0);
-				if (nd == 0) continue;
+				const int a0 = (int)(short)(xw[2 * j] & 0xFFFF), a1 = xw[2 * j] >> 16, a2 = (int)(short)(xw[2 * j + 1] & 0xFFFF), a3 = xw[2 * j + 1] >> 16;
+				if (a0 < 0) continue;
+				const int nd = 1 + (a1 >= 0) + (a2 >= 0) + (a3 >= 0);
 				const int lj = mt * TT + j;
 				const int2 li = locsm[lj];
-				const int n = li.x;
-				const int zc[4] = {(int)(zw[j] & 0xFFu), (int)((zw[j] >> 8) & 0xFFu), (int)((zw[j] >> 16) & 0xFFu), (int)(zw[j] >> 24)};
-				const bool same = (zw[j] == (uint32_t)zc[0] * 0x01010101u);
-				const float *tab = a.tab + ((size_t)(l0 + lj) * g.K + zc[0]) * a.Gmax;
-				int gq[4];
-				if (nd == 1) { gq[0] = gq[1] = gq[2] = gq[3] = al[0]; }
-				else if (nd == 4) { gq[0] = al[0]; gq[1] = al[1]; gq[2] = al[2]; gq[3] = al[3]; }
+				const int n = li.x, n2 = n * n;
+				const uint32_t z0 = zw[j] & 0xFFu;
+				const bool same = (zw[j] == z0 * 0x01010101u);
+				const float *tab = a.tab + ((size_t)(l0 + lj) * g.K + z0) * a.Gmax;
+				const uint8_t *c2i = a.c2i + li.y;
+				const float *Pl = Psm + lj * rowsz;
+				int g0, g1, g2, g3, cls;
+				if (nd == 1) { g0 = g1 = g2 = g3 = a0; cls = 0; }
+				else if (nd == 4) { g0 = a0; g1 = a1; g2 = a2; g3 = a3; cls = 4; }
 				else {
-					// ---- three dosage resolutions (choose_two_auto :854, choose_tri_auto :907)
-					double w[3];
-					int pick;
-					if (a.init) { w[0] = 1.0 / 3.0; w[1] = 2.0 / 3.0; w[2] = 1.0; }     // choose_unif, poly_geno.c:842
-					else {
-						if (same) {
-							int code[3];
-							if (nd == 2) {
-								code[0] = al[0] * n * (n * n + n + 1) + al[1];
-								code[1] = al[1] * n * (n * n + n + 1) + al[0];
-								code[2] = (al[0] * n * n + al[1]) * (n + 1);
-							} else {
-								code[0] = al[0] * n * n * (n + 1) + al[1] * n + al[2];
-								code[1] = al[1] * n * n * (n + 1) + al[0] * n + al[2];
-								code[2] = al[2] * n * n * (n + 1) + al[0] * n + al[1];
-							}
-							for (int t = 0; t < 3; t++) w[t] = (double)__ldg(tab + a.c2i[li.y + code[t]]);
-						} else {
-							double lf[3];
-							for (int t = 0; t < nd; t++) {
-								const float *row = Psm + (lj * g.A + al[t]) * KP;
-								double f = 0.0;
+					// ---- three dosage resolutions (choose_two_auto :854, choose_tri_auto :907), weights in log2
+					float w0, w1, w2;
+					if (a.init) { w0 = w1 = w2 = 0.0f; }                                // choose_unif, poly_geno.c:842
+					else if (same) {
+						int c0, c1, c2;
+						if (nd == 2) { c0 = a0 * n * (n2 + n + 1) + a1; c1 = a1 * n * (n2 + n + 1) + a0; c2 = (a0 * n2 + a1) * (n + 1); }
+						else { c0 = a0 * n2 * (n + 1) + a1 * n + a2; c1 = a1 * n2 * (n + 1) + a0 * n + a2; c2 = a2 * n2 * (n + 1) + a0 * n + a1; }
+						w0 = __ldg(tab + c2i[c0]) * LOG2E; w1 = __ldg(tab + c2i[c1]) * LOG2E; w2 = __ldg(tab + c2i[c2]) * LOG2E;
+					} else {
+						const float *r0 = Pl + a0 * KP, *r1 = Pl + a1 * KP, *r2 = Pl + (nd == 3 ? a2 : a0) * KP;
+						float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
 #pragma unroll
-								for (int k = 0; k < KP; k++) f += (double)q[k] * (double)row[k];
-								lf[t] = log(f);
-							}
-							if (nd == 2) {
-								w[0] = log(4.0) + 3 * lf[0] + lf[1];
-								w[1] = log(4.0) + 3 * lf[1] + lf[0];
-								w[2] = log(6.0) + 2 * lf[0] + 2 * lf[1];
-							} else {
-								w[0] = 2 * lf[0] + lf[1] + lf[2];
-								w[1] = 2 * lf[1] + lf[0] + lf[2];
-								w[2] = 2 * lf[2] + lf[1] + lf[0];
-							}
-						}
-						const double tm = w[0];
-						for (int t = 0; t < 3; t++) w[t] = exp(w[t] - tm);
-						w[1] += w[0];
-						w[2] += w[1];
+						for (int k = 0; k < KP; k++) { f0 = fmaf(q[k], r0[k], f0); f1 = fmaf(q[k], r1[k], f1); f2 = fmaf(q[k], r2[k], f2); }
+						const float l0f = lg2_fast(f0), l1f = lg2_fast(f1), l2f = lg2_fast(f2);
+						if (nd == 2) { w0 = 2.0f + 3.0f * l0f + l1f; w1 = 2.0f + 3.0f * l1f + l0f; w2 = LG2_6 + 2.0f * l0f + 2.0f * l1f; }
+						else { w0 = 2.0f * l0f + l1f + l2f; w1 = 2.0f * l1f + l0f + l2f; w2 = 2.0f * l2f + l1f + l0f; }
 					}
+					const float e1 = ex2_fast(w1 - w0), e2 = ex2_fast(w2 - w0);          // e0 = 1
+					const float c1w = 1.0f + e1, c2w = c1w + e2;
 					const u32x4 rnd = philox4x32<10>(u32x4{(uint32_t)(l0 + lj), ig_global, a.iter, TAG_GENO}, a.key0, a.key1);
-					const double u = u01d(rnd.x, rnd.y) * w[2];
-					pick = (u <= w[0]) ? 0 : (u <= w[1] ? 1 : 2);
+					const float u = u01f(rnd.x) * c2w;
+					const int pick = (u < 1.0f) ? 0 : (u < c1w ? 1 : 2);
 					// two_allele_auto :2440 / tri_allele_auto :2509
 					if (nd == 2) {
-						if (pick == 0) { gq[0] = al[0]; gq[1] = al[0]; gq[2] = al[0]; gq[3] = al[1]; }
-						else if (pick == 1) { gq[0] = al[1]; gq[1] = al[1]; gq[2] = al[1]; gq[3] = al[0]; }
-						else { gq[0] = al[0]; gq[1] = al[0]; gq[2] = al[1]; gq[3] = al[1]; }
+						const int major = (pick == 1) ? a1 : a0, minor = (pick == 1) ? a0 : a1;
+						g0 = major; g1 = major; g2 = (pick == 2) ? minor : major; g3 = minor;
+						cls = (pick == 2) ? 2 : 1;
 					} else {
-						if (pick == 0) { gq[0] = al[0]; gq[1] = al[0]; gq[2] = al[1]; gq[3] = al[2]; }
-						else if (pick == 1) { gq[0] = al[1]; gq[1] = al[1]; gq[2] = al[0]; gq[3] = al[2]; }
-						else { gq[0] = al[2]; gq[1] = al[2]; gq[2] = al[0]; gq[3] = al[1]; }
+						const int dbl = (pick == 0) ? a0 : (pick == 1 ? a1 : a2);
+						g0 = dbl; g1 = dbl; g2 = (pick == 0) ? a1 : a0; g3 = (pick == 2) ? a1 : a2;
+						cls = 3;
 					}
 				}
-				gn[j] = (uint32_t)gq[0] | ((uint32_t)gq[1] << 8) | ((uint32_t)gq[2] << 16) | ((uint32_t)gq[3] << 24);
+				gn[j] = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
 				if (a.init) continue;
+				const uint32_t z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286)
-				if (same) {
-					const int code = ((gq[0] * n + gq[1]) * n + gq[2]) * n + gq[3];
-					ll += (double)__ldg(tab + a.c2i[li.y + code]);
-				} else {
-					double s = LOGMULT[dosage_class(gq)];
-#pragma unroll
-					for (int cidx = 0; cidx < 4; cidx++) s += log((double)Psm[(lj * g.A + gq[cidx]) * KP + zc[cidx]]);
-					ll += s;
+				if (same) m_nat += __ldg(tab + c2i[((g0 * n + g1) * n + g2) * n + g3]);
+				else {
+					// heterozygote multiplicities log 4, 6, 12, 24 (poly_geno.c:1262-1268)
+					m_nat += (cls == 0) ? 0.0f : (cls == 1 ? 1.3862943611198906f : (cls == 2 ? 1.791759469228055f : (cls == 3 ? 2.4849066497880004f : 3.1780538303479458f)));
+					m_lg2 += lg2_fast(Pl[g0 * KP + z0] * Pl[g1 * KP + z1]) + lg2_fast(Pl[g2 * KP + z2] * Pl[g3 * KP + z3]);
 				}
 				// ---- tally of the next update_P_auto over the latent genotype (poly_geno.c:403-424)
-#pragma unroll
-				for (int cidx = 0; cidx < 4; cidx++) atomicAdd(hist_t + ((lj * g.A + gq[cidx]) * KP + zc[cidx]) * R, 1);
+				atomicAdd(hist_t + ((lj * g.A + g0) * KP + z0) * R, 1);
+				atomicAdd(hist_t + ((lj * g.A + g1) * KP + z1) * R, 1);
+				atomicAdd(hist_t + ((lj * g.A + g2) * KP + z2) * R, 1);
+				atomicAdd(hist_t + ((lj * g.A + g3) * KP + z3) * R, 1);
 			}
 			*(gp + (size_t)mt * Nloc) = make_int4((int)gn[0], (int)gn[1], (int)gn[2], (int)gn[3]);
+			ll_nat += m_nat; ll_lg2 += m_lg2;
 		}
-		if (!a.init) a.lpart[(size_t)chunk * Nloc + il] = ll;
+		if (!a.init) {
+			a.lpart[((size_t)chunk * 2) * Nloc + il] = ll_nat;
+			a.lpart[((size_t)chunk * 2 + 1) * Nloc + il] = ll_lg2;
+		}
 	}
 	__syncthreads();
 	if (a.init) return;
@@ -687,18 +680,25 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 	}
 }
 
-// indvlkh, totallkh and the column sums of Q (cal_lkd :715, check_empty_cluster mcmc.c:1944)
-__global__ void __launch_bounds__(RED1) tetra_lkh_kernel(const double *lpart, double *ind, DevScalars *sc, Geometry g)
+// indvlkh (cal_lkd :715): chunk partials in chunk order, one thread per individual
+__global__ void tetra_indv_lkh_kernel(const float *lpart, double *ind, Geometry g)
+{
+	const int il = blockIdx.x * blockDim.x + threadIdx.x;
+	if (il >= g.Nloc) return;
+	double s = 0.0;
+	for (int c = 0; c < g.nchunks; c++)
+		s += (double)lpart[((size_t)c * 2) * g.Nloc + il] + (double)lpart[((size_t)c * 2 + 1) * g.Nloc + il] * LN2_D;
+	ind[(size_t)(g.i0 + il) * g.REC + g.K] = s;
+}
+// totallkh and the column sums of Q (check_empty_cluster mcmc.c:1944): one CTA, fixed tree
+__global__ void __launch_bounds__(RED1) tetra_lkh_kernel(const double *ind, DevScalars *sc, Geometry g)
 {
 	__shared__ double sh[RED1];
 	double tot = 0.0, qc[MAX_K];
 	for (int k = 0; k < MAX_K; k++) qc[k] = 0.0;
 	for (int il = threadIdx.x; il < g.Nloc; il += RED1) {
-		double s = 0.0;
-		for (int c = 0; c < g.nchunks; c++) s += lpart[(size_t)c * g.Nloc + il];
-		double *rec = ind + (size_t)(g.i0 + il) * g.REC;
-		rec[g.K] = s;
-		tot += s;
+		const double *rec = ind + (size_t)(g.i0 + il) * g.REC;
+		tot += rec[g.K];
 		for (int k = 0; k < g.K; k++) qc[k] += rec[k];
 	}
 	const double T = block_sum1(tot, sh);
@@ -851,7 +851,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	CK(cudaMemcpy(t->loc_cat, loc_cat.data(), loc_cat.size() * 4, cudaMemcpyHostToDevice));
 	CK(dalloc0(&t->exf, tn)); CK(dalloc0(&t->tabC, tn)); CK(dalloc0(&t->tabP, tn));
 	CK(dalloc0(&t->Sprop, (size_t)MAX_K)); CK(dalloc0(&t->dstat, (size_t)MAX_K)); CK(dalloc0(&t->accepted, (size_t)MAX_K));
-	CK(dalloc0(&t->dpart, (size_t)g.nchunks * g.K * g.Nloc)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * g.Nloc));
+	CK(dalloc0(&t->dpart, (size_t)g.nchunks * g.nblk * g.K)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * 2 * g.Nloc));
 	CK(dalloc0(&c->P, pn)); CK(dalloc0(&c->n, pn));
 	if (c->cfg.print_freq) CK(dalloc0(&c->P64, (size_t)g.K * g.L * g.A));
 	CK(dalloc0(&c->ind, (size_t)c->Npad * g.REC)); CK(dalloc0(&c->Qf, (size_t)g.Nloc * g.KP));
@@ -936,9 +936,11 @@ static ig_status tetra_q(ig_ctx *c)
 
 static ig_status tetra_lkh(ig_ctx *c)
 {
-	tetra_lkh_kernel<<<1, RED1, 0, c->stream>>>(c->tetra->lpart, c->ind, c->sc, c->geo);
+	tetra_indv_lkh_kernel<<<nb((size_t)c->geo.Nloc, 128), 128, 0, c->stream>>>(c->tetra->lpart, c->ind, c->geo);
 	CK(cudaGetLastError());
-	c->launches++;
+	tetra_lkh_kernel<<<1, RED1, 0, c->stream>>>(c->ind, c->sc, c->geo);
+	CK(cudaGetLastError());
+	c->launches += 2;
 	return IG_OK;
 }
 
@@ -963,7 +965,7 @@ static ig_status tetra_s_end(ig_ctx *c, int decide)
 {
 	TetraState *t = c->tetra;
 	const Geometry &g = c->geo;
-	tetra_accept_kernel<<<1, RED1, 0, c->stream>>>(t->dpart, g.nchunks, g.Nloc, g.K, c->S, t->Sprop, t->dstat, t->accepted, c->sc, c->iter, c->key0, c->key1, decide);
+	tetra_accept_kernel<<<1, 32, 0, c->stream>>>(t->dpart, g.nchunks * g.nblk, g.K, c->S, t->Sprop, t->dstat, t->accepted, c->sc, c->iter, c->key0, c->key1, decide);
 	CK(cudaGetLastError());
 	if (decide) {
 		tetra_select_kernel<<<nb((size_t)g.L * g.K * t->Gmax, 256), 256, 0, c->stream>>>(t->tabC, t->tabP, t->accepted, g.L, g.K, t->Gmax);
