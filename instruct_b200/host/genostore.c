@@ -85,7 +85,9 @@ int gs_read(const char *path, const gs_options *opt, gs_store *out, char *err, i
 	long row = 0;
 
 	memset(out, 0, sizeof(*out));
-	if (ploid != 2) return fail(err, errlen, "genostore: only the diploid formats are handled here");
+	int datafmt = opt->datafmt;
+	if (ploid != 2 && ploid != 4) return fail(err, errlen, "genostore: ploid must be 2 or 4");
+	if (ploid == 4) datafmt = 1;                        /* read_data: ploid 4 is always the one-line format (data_interface.c:78-82) */
 	if ((fp = fopen(path, "r")) == NULL) return fail(err, errlen, "Cannot open input file!");
 	meta = opt->label + opt->popdata + opt->n_extra_col;
 
@@ -103,19 +105,19 @@ int gs_read(const char *path, const gs_options *opt, gs_store *out, char *err, i
 				fprintf(stdout, "The number of loci is %d now!\n", Lf);
 				continue;
 			}
-			Lf = (opt->datafmt == 0) ? ntok - meta : (ntok - meta) / ploid;
+			Lf = (datafmt == 0) ? ntok - meta : (ntok - meta) / ploid;
 			if (Lf != opt->locinum)
 				fprintf(stdout, "The Input Number of Loci is wrong!\nThe number of loci is %d now!\n", Lf);
 		}
 		lines++;
 	}
 	if (Lf < 1) { fclose(fp); free(line); free(tok); return fail(err, errlen, "no loci found in the input file"); }
-	if (opt->datafmt == 0) {
+	if (datafmt == 0) {
 		if (lines % ploid != 0) { fclose(fp); free(line); free(tok); return fail(err, errlen, "Some individuals do not have two copies of haplotype!"); }
 		N = lines / ploid;
 	} else N = lines;
 	if (N != opt->totalsize) fprintf(stdout, "The input population size is incorrect!\nThe population size is %d\n", N);
-	cnt_token = (opt->datafmt == 0) ? meta + Lf : meta + Lf * ploid;
+	cnt_token = (datafmt == 0) ? meta + Lf : meta + Lf * ploid;
 
 	out->ploid = ploid; out->totalsize = N; out->locinum_file = Lf; out->n_extra_col = opt->n_extra_col;
 	raw = (int16_t *)malloc((size_t)Lf * N * ploid * sizeof(int16_t));
@@ -139,8 +141,8 @@ int gs_read(const char *path, const gs_options *opt, gs_store *out, char *err, i
 			snprintf(msg, sizeof msg, "The number of tokens in one line does not match the parameters input from the commandline (line %ld has %d, expected %d)", row + 1, ntok, cnt_token);
 			return fail(err, errlen, msg);
 		}
-		i = (opt->datafmt == 0) ? (int)(row / ploid) : (int)row;
-		c = (opt->datafmt == 0) ? (int)(row % ploid) : 0;
+		i = (datafmt == 0) ? (int)(row / ploid) : (int)row;
+		c = (datafmt == 0) ? (int)(row % ploid) : 0;
 		if (c == 0) {
 			if (opt->label) out->indvname[i] = dup_str(tok[opt->label - 1]);
 			if (opt->popdata) out->popindx[i] = pop_id(out, &popcap, tok[opt->label + opt->popdata - 1]);
@@ -152,7 +154,7 @@ int gs_read(const char *path, const gs_options *opt, gs_store *out, char *err, i
 			fclose(fp);
 			return fail(err, errlen, "Some individuals have different number of haplotypes!");
 		}
-		if (opt->datafmt == 0) {
+		if (datafmt == 0) {
 			for (l = 0; l < Lf; l++) {
 				const char *t = tok[meta + l];
 				raw[((size_t)l * N + i) * ploid + c] = strcmp(t, opt->missing) == 0 ? GS_MISSING : (int16_t)dict_id(&dict[l], t);
@@ -169,6 +171,58 @@ int gs_read(const char *path, const gs_options *opt, gs_store *out, char *err, i
 	fclose(fp);
 	free(line);
 	free(tok);
+
+	if (ploid == 4) {
+		/* transform_data2 (data_interface.c:571-669): every locus is kept; a genotype becomes the
+		 * ascending set of its distinct alleles padded with -1; "alleleid" is the set's size and
+		 * 0 of them means missing (get_missing_tetra :722-741) */
+		out->locinum = Lf;
+		out->x = raw;
+		out->allelenum = (int32_t *)malloc((size_t)Lf * sizeof(int32_t));
+		out->alleletype = (char ***)calloc((size_t)Lf, sizeof(char **));
+		out->locus_of = (int *)malloc((size_t)Lf * sizeof(int));
+		out->missvec = (int *)calloc((size_t)N, sizeof(int));
+		for (l = 0; l < Lf; l++) {
+			if (dict[l].n < 1) { snprintf(msg, sizeof msg, "locus %d has no observed allele", l + 1); return fail(err, errlen, msg); }
+			out->allelenum[l] = dict[l].n;
+			out->alleletype[l] = dict[l].name;
+			out->locus_of[l] = l;
+			if (dict[l].n > out->allelenum_max) out->allelenum_max = dict[l].n;
+			for (i = 0; i < N; i++) {
+				int16_t *g4 = raw + ((size_t)l * N + i) * 4, set[4];
+				int ns = 0, a, b;
+				for (c = 0; c < 4; c++) {
+					int seen = 0;
+					if (g4[c] < 0) continue;
+					for (a = 0; a < ns; a++) if (set[a] == g4[c]) seen = 1;
+					if (!seen) set[ns++] = g4[c];
+				}
+				for (a = 0; a < ns; a++) for (b = a + 1; b < ns; b++) if (set[a] > set[b]) { int16_t t = set[a]; set[a] = set[b]; set[b] = t; }
+				for (c = 0; c < 4; c++) g4[c] = c < ns ? set[c] : (int16_t)-1;
+				if (ns == 0) out->missvec[i]++;
+			}
+		}
+		free(dict);
+		if (!opt->quiet) {                             /* the reference's echo, :652-676 */
+			fprintf(stdout, "Print the number of alleles per individual per locus:\n");
+			for (i = 0; i < N; i++) {
+				for (l = 0; l < Lf; l++) { int ns = 0; for (c = 0; c < 4; c++) ns += out->x[((size_t)l * N + i) * 4 + c] >= 0; fprintf(stdout, "%d ", ns); }
+				fprintf(stdout, "\n");
+			}
+			fprintf(stdout, "Print the transformed allele data:\n");
+			for (i = 0; i < N; i++)
+				for (c = 0; c < 4; c++) {
+					for (l = 0; l < Lf; l++) {
+						int v = out->x[((size_t)l * N + i) * 4 + c];
+						if (c == 0 && v < 0) v = GS_MISSING;   /* seqdata[0] = -9 on a missing genotype (:648-649) */
+						fprintf(stdout, "%d ", v);
+					}
+					fprintf(stdout, "\n");
+				}
+			fprintf(stdout, "End the printing of the transformed allele data.\n");
+		}
+		return 0;
+	}
 
 	/* ---- keep the polymorphic loci (:524-548) and compact */
 	for (l = 0; l < Lf; l++) {

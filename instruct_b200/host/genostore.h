@@ -22,7 +22,7 @@
 #define GS_ELMLEN 100        /* longest token, as in the reference (data_interface.c:18) */
 
 typedef struct gs_options {
-	int ploid;               /* 2 */
+	int ploid;               /* 2, or 4 (autotetraploid: the store then holds distinct-allele sets) */
 	int totalsize;           /* -N (corrected from the file like the reference does) */
 	int locinum;             /* -L (corrected from the file) */
 	const char *missing;     /* -m, default "-9" */
@@ -36,7 +36,7 @@ typedef struct gs_options {
 
 typedef struct gs_store {
 	int ploid, totalsize, locinum, locinum_file, allelenum_max;
-	int16_t *x;              /* [locinum][totalsize][ploid], -9 = missing              */
+	int16_t *x;              /* [locinum][totalsize][ploid], -9 = missing; ploid 4: ascending distinct alleles, -1 padding */
 	int32_t *allelenum;      /* [locinum]                                              */
 	char ***alleletype;      /* [locinum][allelenum[l]] original allele strings        */
 	int *locus_of;           /* [locinum] index of the locus in the file (0-based)     */

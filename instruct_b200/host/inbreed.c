@@ -254,10 +254,12 @@ int main(int argc, char **argv)
 	go.ploid = ploid; go.totalsize = totalsize; go.locinum = nloci; go.missing = missingdata; go.label = label;
 	go.popdata = popdata; go.n_extra_col = n_extra_col; go.markername_flag = markername_flag; go.datafmt = data_fmt;
 	go.quiet = quiet_data;
-	if (ploid != 2) die("this build runs the diploid sampler (-p 2); the tetraploid driver is not built yet");
+	if (ploid != 2 && ploid != 4) die("ploid must be 2 or 4");
+	if (ploid == 4 && autopoly != 1) die("-p 4 runs the autotetraploid model (-ap 1); the allotetraploid model is not built");
+	if (ploid == 4 && shard_individuals) die("-p 4: individuals of one chain are not sharded over GPUs in this build; spread chains instead");
 	if (inf_K == 1) die("-ik 1 (inference of K) is not built yet");
 	if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
-	N = gs.totalsize; K = popnum; ns = (mode == 3) ? N : K;
+	N = gs.totalsize; K = popnum; ns = (mode == 3 && ploid == 2) ? N : K;
 	init = read_init(initialfilename, chainnum, K);
 
 	/* mem_cal, InStruct.c:204-225 (the estimate is the reference's; kept for its two log lines) */

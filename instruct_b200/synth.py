@@ -287,3 +287,19 @@ def make_tetra_dataset_torch(N, L, K, A=4, miss=0.0, seed=0, device="cuda", own=
         x[l0:l0 + n] = key.to(torch.int16)
     allelenum = torch.full((L,), A, dtype=torch.int32, device=device)
     return x, allelenum
+
+
+def write_reference_text_tetra(path, copies: np.ndarray, labels=True, popdata=True, pop=None, allele_base=100, missing="-9"):
+    """Write a tetraploid data set in the one-line-per-individual format the reference reads for
+    ``-p 4`` (read_data_fmt2, data_interface.c:715): ``[label] [pop]`` then four tokens per locus."""
+    L, N, _ = copies.shape
+    with open(path, "w") as fh:
+        for i in range(N):
+            tok = []
+            if labels:
+                tok.append(f"ind{i}")
+            if popdata:
+                tok.append(str(int(pop[i]) if pop is not None else 0))
+            for l in range(L):
+                tok.extend(missing if v < 0 else str(allele_base + 2 * int(v)) for v in copies[l, i])
+            fh.write(" ".join(tok) + "\n")

@@ -57,3 +57,46 @@ def test_cli_matches_reference_program(tmp_path):
         return np.array([_floats(ln)[0] for ln in t.decode(errors="ignore").split("\n") if "Posterior Mean" in ln])
     assert np.abs(selfing(outs["ref"]).mean(0) - selfing(outs["gpu"]).mean(0)).max() < 0.08
     assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 15.0
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built")
+def test_cli_tetraploid_matches_reference_program(tmp_path):
+    """`-p 4 -ap 1`: the one-line-per-individual tetraploid format, the autotetraploid driver and
+    the ploid-4 result tables, against the compiled reference on the same file."""
+    from instruct_b200.synth import make_tetra_dataset, write_reference_text_tetra
+    d = make_tetra_dataset(N=80, L=16, K=2, A=4, miss=0.03, seed=31)
+    data = str(tmp_path / "geno4.txt")
+    write_reference_text_tetra(data, d.dosage, pop=d.pop)
+    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "4", "-ap", "1", "-u", "1200", "-b", "400", "-t", "5", "-c", "2",
+             "-v", "2", "-g", "1", "-r", "10", "-pi", "0", "-s", "13", "4", "1972"]
+    outs = {}
+    for name, exe, extra in (("ref", REFBIN, []), ("gpu", INBREED, ["--quiet-data"])):
+        out = str(tmp_path / f"{name}.out")
+        p = subprocess.run([exe, "-d", data, "-o", out] + flags + extra, capture_output=True, text=True, timeout=900,
+                           cwd=str(tmp_path))
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        assert "THE JOB IS SUCCESSFULLY FINISHED" in p.stdout
+        outs[name] = open(out, "rb").read()
+
+    def banner(t):
+        t = t[: t.index(b"Chain#1")]
+        t = re.sub(rb"Command line arguments:\n.*\n", b"", t)
+        return re.sub(rb"Output File:   .*\n", b"Output File:   X\n", t)
+    assert banner(outs["ref"]) == banner(outs["gpu"])
+
+    def skeleton(t):
+        return [re.sub(rb"-?\d+\.\d+", b"#", ln) for ln in t[t.index(b"Chain#1"):].split(b"\n")
+                if not ln.startswith(b"The Gelman-Rubin")]
+    sr, sg = skeleton(outs["ref"]), skeleton(outs["gpu"])
+    assert len(sr) == len(sg)
+    assert sum(a == b for a, b in zip(sr, sg)) > 0.97 * len(sr)
+
+    def selfing(t):
+        rows = [ln for ln in t.decode(errors="ignore").split("\n") if ln.startswith("Cluster ")]
+        return np.array([_floats(r)[0] for r in rows]).reshape(2, 2)
+
+    def loglik(t):
+        return np.array([_floats(ln)[0] for ln in t.decode(errors="ignore").split("\n") if "Posterior Mean" in ln])
+    # each chain draws its own alpha once (poly_geno.c:386), so chains differ more than MCMC noise alone
+    assert np.abs(np.sort(selfing(outs["ref"]).mean(0)) - np.sort(selfing(outs["gpu"]).mean(0))).max() < 0.15
+    assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 0.03 * abs(loglik(outs["ref"]).mean())

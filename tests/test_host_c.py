@@ -171,3 +171,32 @@ def test_gelman_rubin_c_matches_python(host):
     tr = np.ascontiguousarray(rng.normal(size=(5, 9)) + np.arange(5)[:, None] * 0.3)
     got = host.wr_gelman_rubin(tr.ctypes.data_as(C.POINTER(C.c_double)), 5, 9)
     assert abs(got - gelman_rubin(tr)) < 1e-12
+
+
+def test_packer_matches_reference_reader_tetraploid(host, tmp_path):
+    """-p 4: the store holds the ascending distinct-allele set per genotype (transform_data2,
+    data_interface.c:571-669), every locus is kept, missing = no allele observed."""
+    from instruct_b200.synth import make_tetra_dataset, write_reference_text_tetra
+    d = make_tetra_dataset(N=19, L=11, K=2, A=5, miss=0.1, seed=9)
+    copies = d.dosage.copy()
+    copies[4, :, :] = np.where(copies[4] >= 0, 1, copies[4])   # a monomorphic locus: kept for ploid 4
+    copies[2, 5, 1] = -9                                         # a partly missing genotype: the observed alleles still count
+    p = str(tmp_path / "geno4.txt")
+    write_reference_text_tetra(p, copies, pop=d.pop)
+    opt = GsOptions(4, 19, 11, b"-9", 1, 1, 0, 0, 1, 1)
+    st = GsStore()
+    err = C.create_string_buffer(512)
+    assert host.gs_read(p.encode(), C.byref(opt), C.byref(st), err, 512) == 0, err.value
+    N, L = st.totalsize, st.locinum
+    mine = np.ctypeslib.as_array(st.x, (L, N, 4)).copy()
+    an = np.ctypeslib.as_array(st.allelenum, (L,)).copy()
+    rx, ran, rmiss, rid = pyoracle.ref_read_data(p, 4, 19, 2, 11, label=1, popdata=1, datafmt=1)
+    assert (L, N) == (rx.shape[0], rx.shape[1]) == (11, 19)
+    assert np.array_equal(an, ran)
+    want = rx.copy()
+    want[(rid == 0)] = -1                                  # the reference writes -9 into slot 0 of a missing genotype
+    assert np.array_equal(mine, want)
+    assert np.array_equal((mine >= 0).sum(axis=2), rid)    # alleleid
+    mv = np.ctypeslib.as_array(st.missvec, (N,))
+    assert np.array_equal(mv, rmiss.sum(axis=0))
+    host.gs_free(C.byref(st))
