@@ -85,7 +85,7 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	if (!cfg || !out) return fail(IG_ERR_ARG, "null argument");
 	*out = nullptr;
 	if (cfg->ploid != 2 && cfg->ploid != 4) return fail(IG_ERR_UNSUPPORTED, "ploid %d: 2 (diploid) or 4 (autotetraploid)", cfg->ploid);
-	if (cfg->ploid == 2 && cfg->mode != 2 && cfg->mode != 3) return fail(IG_ERR_UNSUPPORTED, "mode %d: only modes 2 and 3 are on the hot path", cfg->mode);
+	if (cfg->ploid == 2 && (cfg->mode < 1 || cfg->mode > 3)) return fail(IG_ERR_UNSUPPORTED, "mode %d: modes 1, 2 and 3 are built", cfg->mode);
 	if (cfg->popnum < 1 || cfg->popnum > MAX_K) return fail(IG_ERR_UNSUPPORTED, "popnum %d outside 1..%d", cfg->popnum, MAX_K);
 	if (cfg->locinum < 1 || cfg->totalsize < 1) return fail(IG_ERR_ARG, "empty data set (N=%d, L=%d)", cfg->totalsize, cfg->locinum);
 	if (cfg->mode == 3 && cfg->prior_flag != 0 && cfg->prior_flag != 1) return fail(IG_ERR_ARG, "prior_flag must be 0 or 1");
@@ -121,7 +121,7 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	g.KP = (int)pad_k(g.K);
 	g.A = 2;                   // fixed when the genotypes are loaded
 	g.REC = g.K + 3;
-	c->ns = (cfg->mode == 3) ? N : g.K;
+	c->ns = (cfg->mode == 3) ? N : (cfg->mode == 1 ? 0 : g.K);       // mode 1 has no selfing rates
 	c->rounds = (cfg->rng_rounds == 10) ? 10 : 7;
 	c->key0 = (uint32_t)cfg->seed;
 	c->key1 = (uint32_t)(cfg->seed >> 32);
@@ -418,6 +418,10 @@ static ig_status phase_update_P(ig_ctx *c)
 static ig_status phase_update_S(ig_ctx *c)
 {
 	const Geometry &g = c->geo;
+	// mode 1 (mcmc_POP_admixture, mcmc.c:135-180) has neither update_S nor update_G: the (1, 1)
+	// generation pairs written by init_chain stay, and with G == 1 the sweep's likelihood is
+	// log_ld_noselfing_indv (mcmc.c:1869)
+	if (c->cfg.mode == 1) return IG_OK;
 	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1) {
 		c->ind_h.resize((size_t)c->Npad * g.REC);
 		CK(cudaMemcpyAsync(c->ind_h.data(), c->ind, c->ind_h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

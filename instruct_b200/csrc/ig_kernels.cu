@@ -739,7 +739,8 @@ __global__ void init_chain_kernel(double *ind, double *S, int32_t *state, DevSca
 	Stream st((uint32_t)i, 0u, 0u, TAG_INIT, key0, key1);
 	double *rec = ind + (size_t)i * g.REC;
 	int gen;
-	if (mode == 2) {
+	if (mode == 1) gen = 1;                         // admixture without selfing: G == 1 makes log_ld_indv the mode-1 likelihood (mcmc.c:1869)
+	else if (mode == 2) {
 		const double p = st.uniform(), u = st.uniform();
 		const double v = floor(log(u) / log(1.0 - p)) + 1.0;
 		gen = (v > 50.0) ? 50 : (v < 1.0 ? 1 : (int)v);

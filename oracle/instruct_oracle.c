@@ -525,12 +525,26 @@ void orc_update_alpha(orc_model *m)
 }
 
 /* cal_lkh, mcmc.c:1916-1942 (modes 2 and 3) */
+/* log_ld_noselfing_indv, mcmc.c:1869-1891 (mode 1: no selfing term) */
+double orc_log_ld_noselfing(const orc_model *m, int i)
+{
+	double ll = 0;
+	int l, c;
+	for (l = 0; l < m->L; l++) {
+		if (!usable(m, i, l)) continue;
+		for (c = 0; c < m->ploid; c++) ll += log(m->freq[FO(m, m->z[XO(m, l, i, c)], l, m->x[XO(m, l, i, c)])]);
+		if (m->x[XO(m, l, i, 0)] != m->x[XO(m, l, i, 1)]) ll += log(2);
+	}
+	return ll;
+}
+
+/* cal_lkh, mcmc.c:1916-1942 (modes 1, 2, 3) */
 void orc_cal_lkh(orc_model *m)
 {
 	int i;
 	m->totallkh = 0;
 	for (i = 0; i < m->N; i++) {
-		m->indvlkh[i] = orc_log_ld_indv(m, m->gen[i], i);
+		m->indvlkh[i] = (m->mode == 1) ? orc_log_ld_noselfing(m, i) : orc_log_ld_indv(m, m->gen[i], i);
 		m->totallkh += m->indvlkh[i];
 	}
 }
@@ -648,10 +662,16 @@ int orc_dp_nclusters(const orc_model *m) { return m->dp_cnt; }
 
 /* ------------------------------------------------------------------ sweeps / chains --- */
 
-/* one sweep in the reference's order: mcmc.c:210-215 (mode 2), :336-348 (mode 3) */
+/* one sweep in the reference's order: mcmc.c:152-155 (mode 1), :210-215 (mode 2), :336-348 (mode 3) */
 static void one_sweep(orc_model *m)
 {
 	orc_update_P(m);
+	if (m->mode == 1) {
+		orc_update_ZQ(m, 0);
+		orc_update_alpha(m);
+		orc_cal_lkh(m);
+		return;
+	}
 	if (m->mode == 2) orc_update_S_POP(m);
 	if (m->mode == 3) {
 		if (m->prior_flag == 1) orc_update_DP(m);
@@ -716,6 +736,7 @@ void orc_store_chn(const orc_model *m, orc_chain *c)
 		c->qq[j] = run_mean(c->qq[j], m->qq[j], c->step);
 		c->qq2[j] = run_mean(c->qq2[j], m->qq[j] * m->qq[j], c->step);
 	}
+	if (m->mode == 1) { c->step++; return; }          /* mode 1 stores neither selfing rates nor generations */
 	for (j = 0; j < ns; j++) {
 		c->self_rates[j] = run_mean(c->self_rates[j], m->self_rates[j], c->step);
 		c->self_rates2[j] = run_mean(c->self_rates2[j], m->self_rates[j] * m->self_rates[j], c->step);
@@ -740,7 +761,9 @@ int orc_run_chain(orc_model *m, long update, long burnin, int thinning, int ckre
 	out->flag_empty_cluster = 0;
 	out->steps = (int)((update - burnin) / thinning);            /* mcmc.c:485 */
 	m->alpha = u01(&m->rng) * 10;                                /* mcmc.c:479 */
-	if (m->mode == 2) {
+	if (m->mode == 1) {
+		/* mcmc_POP_admixture, mcmc.c:135-180: nothing else to initialise */
+	} else if (m->mode == 2) {
 		for (i = 0; i < m->N; i++) {                             /* mcmc.c:196-199 */
 			double p = u01(&m->rng);
 			m->gen[i] = draw_geom(&m->rng, p);

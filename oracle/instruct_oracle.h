@@ -60,6 +60,7 @@ void orc_tally_range(const orc_model *m, int i0, int i1, int32_t *n);
 void orc_count_z(const orc_model *m, double *cnt /*[N][K]*/);
 double orc_genofreq(int a0, int a1, double f0, double f1, int gen);
 double orc_log_ld_indv(const orc_model *m, int gen, int i);
+double orc_log_ld_noselfing(const orc_model *m, int i);
 double orc_proposal(const orc_model *m, const double *S);
 double orc_dgeom(double s, int g);
 int orc_dt_stat(double s);

@@ -330,3 +330,24 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(instruct_b200.InstructError):
         s.sweep(1)                             # chain not initialised
     s.close()
+
+
+def test_mode1_sweep_is_the_no_selfing_model():
+    """Mode 1 (mcmc_POP_admixture, mcmc.c:135-180): update_P, update_ZQ, update_alpha, cal_lkh with
+    log_ld_noselfing_indv (mcmc.c:1869).  After a few sweeps the stored likelihood is that of the
+    state, the tally and counts are in step with Z, and G stays 1."""
+    d, sd = _mk(257, 33, 5, 6, 0.05, seed=21, mode=1)
+    s = Sampler(sd, seed=3)
+    s.chain_init(0)
+    s.sweep(4)
+    o = Oracle(d.x, d.allelenum, 5, mode=1)
+    o.z[...] = s.get(_lib.STATE_Z)
+    o.freq[...] = s.get(_lib.STATE_P)
+    assert np.array_equal(s.get(_lib.STATE_TALLY), o.tally())
+    assert np.array_equal(s.get(_lib.STATE_CNT).astype(np.float64), o.count_z())
+    assert (s.get(_lib.STATE_G) == 1).all()
+    o.cal_lkh()
+    lk = s.get(_lib.STATE_INDVLKH)
+    assert np.max(np.abs(lk - o.indvlkh) / np.maximum(np.abs(o.indvlkh), 1.0)) <= RTOL
+    assert abs(float(s.get(_lib.STATE_TOTALLKH)[0]) - o.totallkh) <= RTOL * abs(o.totallkh)
+    s.close()

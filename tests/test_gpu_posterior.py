@@ -97,3 +97,31 @@ def test_tetra_posterior_matches_reference_within_mcse():
     assert abs(z(dQ)) < 3.5, msg
     assert np.all(np.abs(dS.mean(0)) < 0.03), msg
     assert abs(dLL.mean()) < 0.005 * abs(g["LL"].mean()), msg
+
+
+def test_mode1_posterior_matches_reference_within_mcse():
+    """Mode 1 (admixture without selfing, the CLI default): posterior Q and log-likelihood of the GPU
+    chains against R independent chains of the compiled reference (tests/golden/posterior_mode1.npz)."""
+    g = np.load(os.path.join(os.path.dirname(GOLD), "posterior_mode1.npz"))
+    K = int(g["K"])
+    R = g["LL"].shape[0]
+    sd = SeqData(g["x"], g["allelenum"], K, mode=1)
+    pop = g["pop"]
+    LL, M = [], []
+    for rep in range(R):
+        s = Sampler(sd, update=int(g["update"]), burnin=int(g["burnin"]), thinning=int(g["thinning"]), ckrep=5, seed=3000 + rep)
+        ch, _ = s.run_chain(rep)
+        s.close()
+        assert ch.flag_empty_cluster == 0 and ch.step == ch.steps
+        o = np.argsort(ch.qq[pop == 0].mean(axis=0))[::-1]
+        LL.append(ch.totallkh)
+        M.append([ch.qq[pop == p][:, o[0]].mean() for p in range(K)])
+    LL, M = np.array(LL), np.array(M)
+    refM = np.stack([g["Q"][:, pop == p, 0].mean(axis=1) for p in range(K)], axis=1).astype(np.float64)
+    zLL = _z(LL[:, None], g["LL"][:, None])
+    zQ = _z(M, refM)
+    msg = f"zLL={zLL} zQ={zQ} LL_gpu={LL.mean()} LL_ref={g['LL'].mean()} M_gpu={M.mean(0)} M_ref={refM.mean(0)}"
+    assert np.all(np.abs(zLL) < 3.5), msg
+    assert np.all(np.abs(zQ) < 3.5), msg
+    assert abs(LL.mean() - g["LL"].mean()) < 10.0, msg
+    assert np.all(np.abs(M.mean(0) - refM.mean(0)) < 0.02), msg

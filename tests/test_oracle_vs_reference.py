@@ -85,6 +85,21 @@ def test_whole_chain_bit_exact(mode, prior, back_refl):
         assert np.array_equal(np.asarray(co[k]), np.asarray(cr[k])), k
 
 
+def test_whole_chain_bit_exact_mode1():
+    """Mode 1, the CLI default (mcmc_POP_admixture, mcmc.c:135-180): admixture without selfing."""
+    K = 3
+    d = make_dataset(N=45, L=21, K=K, A=4, miss=0.04, seed=12)
+    o = Oracle(d.x, d.allelenum, K, mode=1)
+    r = Reference(d.x, d.allelenum, K, mode=1)
+    o.setseeds(13, 4, 1972); r.setseeds(13, 4, 1972)
+    kw = dict(update=160, burnin=60, thinning=5, ckrep=8, nstep_check_empty=10)
+    co = o.run_chain(**kw)
+    cr = r.mcmc_updating(**kw)
+    assert co["flag_empty_cluster"] == cr["flag_empty_cluster"] == 0
+    for k in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "convg"]:
+        assert np.array_equal(np.asarray(co[k]), np.asarray(cr[k])), k
+
+
 def test_single_updates_follow_reference_stream():
     """Each conditional update consumes the RNG like the reference (state compared after each)."""
     K = 3

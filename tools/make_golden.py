@@ -87,6 +87,22 @@ def posterior_fixture(R=12):
                         S_true=d.S_true, pop=d.pop, update=6000, burnin=2000, thinning=10)
 
 
+def posterior_mode1_fixture(R=10):
+    """Mode 1 (the CLI default, mcmc_POP_admixture mcmc.c:135): admixture without selfing."""
+    K = 2
+    d = make_dataset(N=200, L=10, K=K, A=8, miss=0.0, seed=1001, pure=False, own=0.85)
+    Qm, LL = [], []
+    for rep in range(R):
+        r = Reference(d.x, d.allelenum, K, mode=1)
+        r.setseeds(13 + 7 * rep, 4 + 3 * rep, 1972 + 11 * rep)
+        c = r.mcmc_updating(update=4000, burnin=1500, thinning=10, ckrep=5, nstep_check_empty=20)
+        o = np.argsort(c["qq"][d.pop == 0].mean(axis=0))[::-1]
+        Qm.append(c["qq"][:, o]); LL.append(c["totallkh"])
+        print("mode-1 posterior rep", rep, c["totallkh"], c["qq"][d.pop == 0].mean(axis=0)[o], flush=True)
+    np.savez_compressed(os.path.join(OUT, "posterior_mode1.npz"), x=d.x, allelenum=d.allelenum, K=K, Q=np.array(Qm).astype(np.float32),
+                        LL=np.array(LL), pop=d.pop, update=4000, burnin=1500, thinning=10)
+
+
 def tetra_fixtures(R=12):
     """poly_geno.c through the harness: tables + one whole chain, and the posterior target."""
     K = 3
@@ -122,6 +138,9 @@ def tetra_fixtures(R=12):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mode1":
+        posterior_mode1_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tetra":
         os.makedirs(OUT, exist_ok=True)
         tetra_fixtures()
@@ -134,4 +153,5 @@ if __name__ == "__main__":
     chain_fixture(3, 0)
     chain_fixture(3, 1)
     posterior_fixture()
+    posterior_mode1_fixture()
     tetra_fixtures()
