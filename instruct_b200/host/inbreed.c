@@ -234,55 +234,25 @@ static void *worker(void *arg)
 	return NULL;
 }
 
-int main(int argc, char **argv)
+/* all chains of one K: run (chains over GPUs, or one chain's individuals over GPUs), write the
+ * chain tables in chain order, the Gelman-Rubin line; returns the smallest DIC over the chains */
+static double run_for_K(const gs_store *gsp, int K, wr_run *runp, const wr_data *wdp)
 {
-	gs_options go;
-	gs_store gs;
-	char err[512];
+	const gs_store gs = *gsp;
+	wr_run run = *runp;
+	const wr_data wd = *wdp;
 	init_t init;
-	wr_run run;
-	wr_data wd;
 	chain_out *outs;
-	double *convg = NULL, memreq;
+	double *convg = NULL, dic_min = 0;
 	worker_t *ws;
 	pthread_t *th;
-	int g, chn, N, K, ns, ndev;
+	int g, chn, N = gs.totalsize, ns;
 	size_t nfreq;
 
-	parse_args(argc, argv);
-	memset(&go, 0, sizeof go);
-	go.ploid = ploid; go.totalsize = totalsize; go.locinum = nloci; go.missing = missingdata; go.label = label;
-	go.popdata = popdata; go.n_extra_col = n_extra_col; go.markername_flag = markername_flag; go.datafmt = data_fmt;
-	go.quiet = quiet_data;
-	if (ploid != 2 && ploid != 4) die("ploid must be 2 or 4");
-	if (ploid == 4 && autopoly != 1) die("-p 4 runs the autotetraploid model (-ap 1); the allotetraploid model is not built");
-	if (ploid == 4 && shard_individuals) die("-p 4: individuals of one chain are not sharded over GPUs in this build; spread chains instead");
-	if (inf_K == 1) die("-ik 1 (inference of K) is not built yet");
-	if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
-	N = gs.totalsize; K = popnum; ns = (mode == 3 && ploid == 2) ? N : K;
+	popnum = K;
+	run.popnum = K;
+	ns = (mode == 3 && ploid == 2) ? N : K;
 	init = read_init(initialfilename, chainnum, K);
-
-	/* mem_cal, InStruct.c:204-225 (the estimate is the reference's; kept for its two log lines) */
-	memreq = (print_freq ? 8.0 * K * gs.locinum * gs.allelenum_max : 0.0) + 8.0 + 8.0 * N + 8.0 * ns + 4.0 * N + 8.0 * N * K;
-	memreq *= (double)((updatenum - burnin) / thinning);
-	fprintf(stdout, "The memory required for this run is %f \n", memreq);
-	fprintf(stdout, "The maximum memory allowed is %f \n", max_mem);
-
-	memset(&run, 0, sizeof run);
-	run.datafilename = datafilename; run.initialfilename = initialfilename; run.missingdata = missingdata;
-	run.chainnum = chainnum; run.thinning = thinning; run.ploid = ploid; run.autopoly = autopoly; run.totalsize = N;
-	run.locinum = gs.locinum; run.popnum = K; run.mode = mode; run.inf_K = inf_K; run.prior_flag = prior_flag;
-	run.back_refl = back_refl; run.print_freq = print_freq; run.GR_flag = GR_flag; run.ckrep = ckrep; run.distr_fmt = distr_fmt;
-	run.label = label; run.popdata = popdata; run.markername_flag = markername_flag; run.update = updatenum; run.burnin = burnin;
-	run.siglevel = siglevel; run.alpha_dpm = alpha_dpm;
-	if (wr_banner(outfilename, argc, argv, &run)) die("Cannot open output file!");
-
-	ndev = ig_device_count();
-	if (ndev < 1) die("no CUDA device: inbreed has no CPU path");
-	if (n_gpus < 1) n_gpus = 1;
-	if (n_gpus > ndev) { fprintf(stdout, "Only %d GPU(s) visible; using %d.\n", ndev, ndev); n_gpus = ndev; }
-	if (!shard_individuals && n_gpus > chainnum) n_gpus = chainnum;
-
 	nfreq = print_freq ? (size_t)K * gs.locinum * gs.allelenum_max : 0;
 	outs = (chain_out *)calloc((size_t)chainnum, sizeof(chain_out));
 	for (chn = 0; chn < chainnum; chn++) alloc_out(&outs[chn], N, K, ns, nfreq);
@@ -307,10 +277,6 @@ int main(int argc, char **argv)
 	for (g = 0; g < n_gpus; g++) pthread_join(th[g], NULL);
 	for (g = 0; g < n_gpus; g++) if (ws[g].status < 0) die(ws[g].err);
 
-	memset(&wd, 0, sizeof wd);
-	wd.indvname = gs.indvname; wd.poptype = gs.poptype; wd.marker_names = gs.marker_names; wd.alleletype = gs.alleletype;
-	wd.popindx = gs.popindx; wd.missvec = gs.missvec; wd.allelenum = gs.allelenum; wd.pop_count = gs.pop_count;
-	wd.allelenum_max = gs.allelenum_max;
 	for (chn = 0; chn < chainnum; chn++) {               /* chain_stat in chain order, InStruct.c:191 */
 		wr_chain_t c;
 		chain_out *o = &outs[chn];
@@ -318,10 +284,88 @@ int main(int argc, char **argv)
 		c.chn_name = init.name[chn]; c.name_len = (int)strlen(init.name[chn]) + 1;
 		c.totallkh = o->totallkh; c.totallkh2 = o->totallkh2; c.indvlkh = o->indvlkh; c.qq = o->qq; c.qq2 = o->qq2;
 		c.self_rates = o->self; c.self_rates2 = o->self2; c.gen = o->gen; c.gen2 = o->gen2; c.freq = o->freq; c.freq2 = o->freq2;
-		if (wr_chain(outfilename, &run, &wd, &c, NULL)) die("Cannot open output file!");
+		{
+			double dic = 0;
+			if (wr_chain(outfilename, &run, &wd, &c, &dic)) die("Cannot open output file!");
+			if (chn == 0 || dic < dic_min) dic_min = dic;
+		}
 	}
 	if (GR_flag == 1 && wr_convergence(outfilename, convg, chainnum, ckrep, convgfilename, ref_compat_gr) < 0)
 		die("ERROR: Cannot open output file!\n");
+	free(ws); free(th); free(outs); free(convg);
+	return dic_min;
+}
+
+int main(int argc, char **argv)
+{
+	gs_options go;
+	gs_store gs;
+	char err[512];
+	wr_run run;
+	wr_data wd;
+	double memreq;
+	int N, K, ns, ndev;
+
+	parse_args(argc, argv);
+	memset(&go, 0, sizeof go);
+	go.ploid = ploid; go.totalsize = totalsize; go.locinum = nloci; go.missing = missingdata; go.label = label;
+	go.popdata = popdata; go.n_extra_col = n_extra_col; go.markername_flag = markername_flag; go.datafmt = data_fmt;
+	go.quiet = quiet_data;
+	if (ploid != 2 && ploid != 4) die("ploid must be 2 or 4");
+	if (ploid == 4 && autopoly != 1) die("-p 4 runs the autotetraploid model (-ap 1); the allotetraploid model is not built");
+	if (ploid == 4 && shard_individuals) die("-p 4: individuals of one chain are not sharded over GPUs in this build; spread chains instead");
+	if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
+	N = gs.totalsize; K = popnum; ns = (mode == 3 && ploid == 2) ? N : K;
+	/* mem_cal, InStruct.c:204-225 (the estimate is the reference's; kept for its two log lines) */
+	memreq = (print_freq ? 8.0 * K * gs.locinum * gs.allelenum_max : 0.0) + 8.0 + 8.0 * N + 8.0 * ns + 4.0 * N + 8.0 * N * K;
+	memreq *= (double)((updatenum - burnin) / thinning);
+	fprintf(stdout, "The memory required for this run is %f \n", memreq);
+	fprintf(stdout, "The maximum memory allowed is %f \n", max_mem);
+
+	memset(&run, 0, sizeof run);
+	run.datafilename = datafilename; run.initialfilename = initialfilename; run.missingdata = missingdata;
+	run.chainnum = chainnum; run.thinning = thinning; run.ploid = ploid; run.autopoly = autopoly; run.totalsize = N;
+	run.locinum = gs.locinum; run.popnum = K; run.mode = mode; run.inf_K = inf_K; run.prior_flag = prior_flag;
+	run.back_refl = back_refl; run.print_freq = print_freq; run.GR_flag = GR_flag; run.ckrep = ckrep; run.distr_fmt = distr_fmt;
+	run.label = label; run.popdata = popdata; run.markername_flag = markername_flag; run.update = updatenum; run.burnin = burnin;
+	run.siglevel = siglevel; run.alpha_dpm = alpha_dpm;
+	if (wr_banner(outfilename, argc, argv, &run)) die("Cannot open output file!");
+
+	ndev = ig_device_count();
+	if (ndev < 1) die("no CUDA device: inbreed has no CPU path");
+	if (n_gpus < 1) n_gpus = 1;
+	if (n_gpus > ndev) { fprintf(stdout, "Only %d GPU(s) visible; using %d.\n", ndev, ndev); n_gpus = ndev; }
+	if (!shard_individuals && n_gpus > chainnum) n_gpus = chainnum;
+
+	memset(&wd, 0, sizeof wd);
+	wd.indvname = gs.indvname; wd.poptype = gs.poptype; wd.marker_names = gs.marker_names; wd.alleletype = gs.alleletype;
+	wd.popindx = gs.popindx; wd.missvec = gs.missvec; wd.allelenum = gs.allelenum; wd.pop_count = gs.pop_count;
+	wd.allelenum_max = gs.allelenum_max;
+	if (inf_K == 1) {
+		/* inf_K_val, InStruct.c:536-601: every K of the range, all chains each, the K whose best
+		 * chain has the smallest DIC wins.  (K, chain) pairs are independent: chains spread over GPUs. */
+		int Kb, K_best = 0;
+		double best = 0;
+		FILE *f;
+		if (n_large < 1 || n_small < 1 || n_small > n_large) {
+			n_small = 1;
+			n_large = (int)pow((double)N, 0.3) + 1;
+			fprintf(stdout, "The range of value for K is not correct! Change to default value (%d - %d)!\n", n_small, n_large);
+		}
+		if (n_large > 16) die("K inference: the library supports K <= 16");
+		for (Kb = n_small; Kb <= n_large; Kb++) {
+			double d;
+			if ((f = fopen(outfilename, "a+")) == NULL) die("Cannot open output file!");
+			fprintf(f, "\n\nThe current K is %d\n", Kb);
+			fclose(f);
+			d = run_for_K(&gs, Kb, &run, &wd);
+			if (Kb == n_small || d < best) { best = d; K_best = Kb; }
+		}
+		if ((f = fopen(outfilename, "a+")) == NULL) die("Cannot open output file!");
+		fprintf(f, "\n\nThe range of value for K is (%d - %d)!\n", n_small, n_large);
+		fprintf(f, "The optimal K is %d\n", K_best);
+		fclose(f);
+	} else run_for_K(&gs, popnum, &run, &wd);
 	fprintf(stdout, "THE JOB IS SUCCESSFULLY FINISHED\n");
 	gs_free(&gs);
 	return 0;

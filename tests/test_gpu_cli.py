@@ -100,3 +100,31 @@ def test_cli_tetraploid_matches_reference_program(tmp_path):
     # each chain draws its own alpha once (poly_geno.c:386), so chains differ more than MCMC noise alone
     assert np.abs(np.sort(selfing(outs["ref"]).mean(0)) - np.sort(selfing(outs["gpu"]).mean(0))).max() < 0.15
     assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 0.03 * abs(loglik(outs["ref"]).mean())
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built")
+def test_cli_k_inference(tmp_path):
+    """`-ik 1 -kv 1 3` (inf_K_val, InStruct.c:536-601): every K of the range is run and tabulated, the
+    K with the smallest DIC is reported.  Same file, same flags, both programs."""
+    d = make_dataset(N=150, L=20, K=2, A=6, miss=0.02, seed=77, pure=True)
+    data = str(tmp_path / "geno.txt")
+    write_reference_text(data, d.x, pop=d.pop)
+    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "2", "-u", "1500", "-b", "500", "-t", "5", "-c", "2",
+             "-v", "1", "-g", "1", "-r", "10", "-pi", "0", "-ik", "1", "-kv", "1", "3", "-s", "13", "4", "1972"]
+    best, dics = {}, {}
+    for name, exe, extra in (("ref", REFBIN, []), ("gpu", INBREED, ["--quiet-data"])):
+        out = str(tmp_path / f"{name}.out")
+        p = subprocess.run([exe, "-d", data, "-o", out] + flags + extra, capture_output=True, text=True, timeout=900,
+                           cwd=str(tmp_path))
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        t = open(out, "rb").read().decode(errors="ignore")
+        for k in (1, 2, 3):
+            assert f"The current K is {k}" in t
+        assert "The range of value for K is (1 - 3)!" in t
+        best[name] = int(re.search(r"The optimal K is (\d+)", t).group(1))
+        dics[name] = [float(v) for v in re.findall(r"Deviance information criterion of this model is (-?\d+\.\d+)", t)]
+        assert len(dics[name]) == 6                       # 3 values of K x 2 chains
+    # K = 1 has no admixture freedom: its DIC is the same model on both sides up to MCMC noise
+    assert abs(np.mean(dics["ref"][:2]) - np.mean(dics["gpu"][:2])) < 0.01 * abs(np.mean(dics["ref"][:2]))
+    # two well-separated pure clusters: K = 1 must lose on both sides
+    assert best["ref"] >= 2 and best["gpu"] >= 2, (best, dics)
