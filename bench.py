@@ -237,7 +237,7 @@ def run_ours(args):
         L = args.L
     tetra = args.workload in TETRA
     ploid = 4 if tetra else 2
-    shard_ind = world > 1 and args.shard == "individuals" and not tetra     # ploid 4: chains only
+    shard_ind = world > 1 and args.shard == "individuals"
     if shard_ind:
         b, e = shard_bounds(N, world, rank)
         nloc, i0, count, srank, seed_data = e - b, b, world, rank, 4
@@ -245,6 +245,8 @@ def run_ours(args):
         nloc, i0, count, srank, seed_data = N, 0, 1, 0, 4 + rank
     if tetra:
         x, an = make_tetra_dataset_torch(N, L, K, A=A, miss=miss, seed=seed_data, device=dev)
+        if shard_ind:
+            x = x[:, i0:i0 + nloc, :].contiguous()     # every rank generates the same data set and keeps its block
         torch.cuda.synchronize()
         usable = float((x[:, :, 0] >= 0).sum().item())
     else:

@@ -274,6 +274,18 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 	return IG_OK;
 }
 
+static ig_status exchange_tally(ig_ctx *c);
+static ig_status exchange_individuals(ig_ctx *c);
+ig_status ig_exchange_tally(ig_ctx *c) { return exchange_tally(c); }
+ig_status ig_exchange_individuals(ig_ctx *c) { return exchange_individuals(c); }
+// all-gather of `per_rank` doubles per shard, in place (rank r's block at buf + r * per_rank)
+ig_status ig_allgather_double(ig_ctx *c, double *buf, size_t per_rank)
+{
+	if (!c->comm) return IG_OK;
+	NCK(g_nccl.AllGather(buf + (size_t)c->cfg.shard_rank * per_rank, buf, per_rank, ncclDouble, c->comm, c->stream));
+	return IG_OK;
+}
+
 static ig_status exchange_tally(ig_ctx *c)
 {
 	// the one per-sweep reduction of the sharded mode: int32 n[L][A][K] summed over the shards

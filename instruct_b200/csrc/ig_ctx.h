@@ -75,7 +75,12 @@ struct ig_ctx {
 	std::vector<cudaEvent_t> ev;
 	int ev_used = 0;
 	int64_t launches = 0;
-	// autotetraploid driver (tetra.cu); null for ploid 2
+	// per-sweep exchanges of the individual-sharded mode (ig_api.cu); no-ops on one GPU
+ig_status ig_exchange_tally(ig_ctx *c);
+ig_status ig_exchange_individuals(ig_ctx *c);
+ig_status ig_allgather_double(ig_ctx *c, double *buf, size_t per_rank);
+
+// autotetraploid driver (tetra.cu); null for ploid 2
 	ig::TetraState *tetra = nullptr;
 };
 
@@ -89,6 +94,11 @@ static cudaError_t dalloc(T **p, size_t n)
 	return e;
 }
 
+
+// per-sweep exchanges of the individual-sharded mode (ig_api.cu); no-ops on one GPU
+ig_status ig_exchange_tally(ig_ctx *c);
+ig_status ig_exchange_individuals(ig_ctx *c);
+ig_status ig_allgather_double(ig_ctx *c, double *buf, size_t per_rank);
 
 // autotetraploid driver (tetra.cu)
 ig_status tetra_create(ig_ctx *c);

@@ -24,7 +24,9 @@
 // passes and not one.  Bytes per allele copy: pass A 3 (geno, old z, new z), pass B 4 (int16 x,
 // z, new geno) against the 6 of SURVEY.md section 8d.
 //
-// Restrictions of this version: single GPU per chain (chains still spread over GPUs), -e 1 only
+// Multi-GPU: chains over GPUs, or the individuals of one chain sharded (int32 all-reduce of n, all-gather of
+// the per-individual S statistics and records; fixed-order reductions => bit-identical to one GPU).
+// Restrictions of this version: -e 1 only
 // (with -e 0 the reference's own tables are log(0), tests/test_tetra_oracle_vs_reference.py),
 // allelenum_max <= 6, alpha is never updated (the reference's tetraploid driver never calls
 // update_alpha).
@@ -62,7 +64,8 @@ struct TetraState {
 	float *exf = nullptr, *tabC = nullptr, *tabP = nullptr;    // [Lq][K][Gmax] natural logs
 	double *Sprop = nullptr, *dstat = nullptr;                  // [K]
 	int32_t *accepted = nullptr;      // [K]
-	double *dpart = nullptr;          // [nchunks * nblk][K] per-CTA sums of the S statistics
+	float *dpart = nullptr;           // [nchunks][K][Nloc] S statistics per (chunk, population, individual)
+	double *dind = nullptr;           // [Npad][K] the same summed over chunks, all shards (all-gathered)
 	float *lpart = nullptr;           // [nchunks][2][Nloc] likelihood partials: natural-log part, log2 part
 	bool timing = false;              // a profiled sweep is between its PASS A start and PASS B end events
 };
@@ -328,24 +331,29 @@ __device__ double block_sum1(double v, double *sh)
 	return r;
 }
 
-// D_k = cal_lkd_props(k) - cal_lkd(), summed over the CTAs of PASS A in CTA order (fixed launch
-// shape => fixed summation order), then the K accept decisions
-__global__ void tetra_accept_kernel(const double *dpart, int nctas, int K, double *S, const double *Sprop,
-                                    double *dstat, int32_t *accepted, DevScalars *sc, uint32_t iter, uint32_t key0, uint32_t key1, int decide)
+// D_k = cal_lkd_props(k) - cal_lkd(): fixed-shape tree over ALL individuals (identical on every
+// rank and for every shard count), then the K accept decisions
+__global__ void __launch_bounds__(RED1) tetra_accept_kernel(const double *dind, int N, int K, double *S, const double *Sprop,
+                                                           double *dstat, int32_t *accepted, DevScalars *sc, uint32_t iter, uint32_t key0, uint32_t key1, int decide)
 {
-	const int k = threadIdx.x;
-	if (k >= K) return;
-	double D = 0.0;
-	for (int c = 0; c < nctas; c++) D += dpart[(size_t)c * K + k];
-	dstat[k] = D;
-	if (!decide) return;
-	Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
-	(void)st.uniform();                                       // the proposal's draw
-	const double u = st.uniform();
-	// ran1() < exp(MIN2(0, mhratio)) (poly_geno.c:628); MIN2(0, NaN) == 0 accepts
-	const bool acc = (D != D) || (u < exp(fmin(0.0, D)));
-	accepted[k] = acc ? 1 : 0;
-	if (acc) { S[k] = Sprop[k]; atomicAdd(&sc->s_accepts, 1); }
+	__shared__ double sh[RED1];
+	for (int k = 0; k < K; k++) {
+		double v = 0.0;
+		for (int i = threadIdx.x; i < N; i += RED1) v += dind[(size_t)i * K + k];
+		const double D = block_sum1(v, sh);
+		if (threadIdx.x == 0) {
+			dstat[k] = D;
+			if (decide) {
+				Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
+				(void)st.uniform();                                       // the proposal's draw
+				const double u = st.uniform();
+				// ran1() < exp(MIN2(0, mhratio)) (poly_geno.c:628); MIN2(0, NaN) == 0 accepts
+				const bool acc = (D != D) || (u < exp(fmin(0.0, D)));
+				accepted[k] = acc ? 1 : 0;
+				if (acc) { S[k] = Sprop[k]; sc->s_accepts++; }
+			}
+		}
+	}
 }
 // move_genofreq, poly_geno.c:738-748
 __global__ void tetra_select_kernel(float *tabC, const float *tabP, const int32_t *accepted, int L, int K, int Gmax)
@@ -362,7 +370,7 @@ __global__ void tetra_select_kernel(float *tabC, const float *tabP, const int32_
 struct ZsArgs {
 	int8_t *Zq; const int8_t *Gq; const float *P; const float *Qf;
 	const float *tabC, *tabP; const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
-	uint16_t *pcnt; double *dpart;
+	uint16_t *pcnt; float *dpart;
 	Geometry geo; int Gmax; int init;
 	uint32_t iter, key0, key1, k_mant, k_one;
 };
@@ -468,24 +476,24 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 			cntsm[(2 * j + 1) * TETRA_THREADS + tid] = 0;
 			pc[j] = (uint32_t)ca | ((uint32_t)cb << 16);
 		}
-	}
-	// ---- this CTA's share of D_k: fixed-shape tree over the thread columns (deterministic)
-	__syncthreads();
-	if (!a.init) {
-		double *red = reinterpret_cast<double *>(cntsm);                 // the counters are done: reuse their space
-		for (int k = 0; k < g.K; k++) {
-			double v = (double)dsm[k * TETRA_THREADS + tid];
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-			if ((tid & 31) == 0) red[tid >> 5] = v;
-			__syncthreads();
-			if (tid == 0) {
-				double t = 0.0;
-				for (int w = 0; w < TETRA_THREADS / 32; w++) t += red[w];
-				a.dpart[((size_t)blockIdx.y * gridDim.x + chunk) * g.K + k] = t;
+		if (!a.init)
+			for (int k = 0; k < g.K; k++) {
+				a.dpart[((size_t)chunk * g.K + k) * Nloc + il] = dsm[k * TETRA_THREADS + tid];
+				dsm[k * TETRA_THREADS + tid] = 0.0f;
 			}
-			__syncthreads();
-		}
+	}
+}
+
+// per individual: the S statistics summed over chunks in chunk order (shard-invariant), written
+// at the individual's GLOBAL slot so that one all-gather completes the array on every rank
+__global__ void tetra_dind_kernel(const float *dpart, double *dind, Geometry g)
+{
+	const int il = blockIdx.x * blockDim.x + threadIdx.x;
+	if (il >= g.Nloc) return;
+	for (int k = 0; k < g.K; k++) {
+		double s = 0.0;
+		for (int c = 0; c < g.nchunks; c++) s += (double)dpart[((size_t)c * g.K + k) * g.Nloc + il];
+		dind[(size_t)(g.i0 + il) * g.K + k] = s;
 	}
 }
 
@@ -696,8 +704,8 @@ __global__ void __launch_bounds__(RED1) tetra_lkh_kernel(const double *ind, DevS
 	__shared__ double sh[RED1];
 	double tot = 0.0, qc[MAX_K];
 	for (int k = 0; k < MAX_K; k++) qc[k] = 0.0;
-	for (int il = threadIdx.x; il < g.Nloc; il += RED1) {
-		const double *rec = ind + (size_t)(g.i0 + il) * g.REC;
+	for (int i = threadIdx.x; i < g.N; i += RED1) {
+		const double *rec = ind + (size_t)i * g.REC;
 		tot += rec[g.K];
 		for (int k = 0; k < g.K; k++) qc[k] += rec[k];
 	}
@@ -779,7 +787,6 @@ ig_status tetra_create(ig_ctx *c)
 {
 	if (c->cfg.autopoly != 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4: only the autotetraploid model (-ap 1) is built");
 	if (c->cfg.back_refl != 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4 needs -e 1: with -e 0 the reference's genotype tables are log(0)");
-	if (c->cfg.shard_count > 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4: individuals of one chain are not sharded in this version (spread chains over GPUs)");
 	c->tetra = new TetraState();
 	Geometry &g = c->geo;
 	TetraState *t = c->tetra;
@@ -797,7 +804,7 @@ void tetra_destroy(ig_ctx *c)
 	if (!t) return;
 	cudaFree(t->Xq); cudaFree(t->Zq); cudaFree(t->Gq); cudaFree(t->cats); cudaFree(t->codes); cudaFree(t->c2i); cudaFree(t->loc_cat);
 	cudaFree(t->exf); cudaFree(t->tabC); cudaFree(t->tabP); cudaFree(t->Sprop); cudaFree(t->dstat); cudaFree(t->accepted);
-	cudaFree(t->dpart); cudaFree(t->lpart);
+	cudaFree(t->dpart); cudaFree(t->dind); cudaFree(t->lpart);
 	delete t;
 	c->tetra = nullptr;
 }
@@ -851,7 +858,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	CK(cudaMemcpy(t->loc_cat, loc_cat.data(), loc_cat.size() * 4, cudaMemcpyHostToDevice));
 	CK(dalloc0(&t->exf, tn)); CK(dalloc0(&t->tabC, tn)); CK(dalloc0(&t->tabP, tn));
 	CK(dalloc0(&t->Sprop, (size_t)MAX_K)); CK(dalloc0(&t->dstat, (size_t)MAX_K)); CK(dalloc0(&t->accepted, (size_t)MAX_K));
-	CK(dalloc0(&t->dpart, (size_t)g.nchunks * g.nblk * g.K)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * 2 * g.Nloc));
+	CK(dalloc0(&t->dpart, (size_t)g.nchunks * g.K * g.Nloc)); CK(dalloc0(&t->dind, (size_t)c->Npad * g.K)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * 2 * g.Nloc));
 	CK(dalloc0(&c->P, pn)); CK(dalloc0(&c->n, pn));
 	if (c->cfg.print_freq) CK(dalloc0(&c->P64, (size_t)g.K * g.L * g.A));
 	CK(dalloc0(&c->ind, (size_t)c->Npad * g.REC)); CK(dalloc0(&c->Qf, (size_t)g.Nloc * g.KP));
@@ -938,6 +945,9 @@ static ig_status tetra_lkh(ig_ctx *c)
 {
 	tetra_indv_lkh_kernel<<<nb((size_t)c->geo.Nloc, 128), 128, 0, c->stream>>>(c->tetra->lpart, c->ind, c->geo);
 	CK(cudaGetLastError());
+	// (Q, indvlkh) of every shard: totallkh, the empty-cluster sums and the moments run redundantly everywhere
+	ig_status st = ig_exchange_individuals(c);
+	if (st != IG_OK) return st;
 	tetra_lkh_kernel<<<1, RED1, 0, c->stream>>>(c->ind, c->sc, c->geo);
 	CK(cudaGetLastError());
 	c->launches += 2;
@@ -946,6 +956,8 @@ static ig_status tetra_lkh(ig_ctx *c)
 
 static ig_status tetra_update_p(ig_ctx *c)
 {
+	ig_status st = ig_exchange_tally(c);        // int32 n[L][A][K] summed over the shards
+	if (st != IG_OK) return st;
 	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, 1};
 	CK(launch_p_dirichlet(a, c->stream));
 	c->launches++;
@@ -965,7 +977,12 @@ static ig_status tetra_s_end(ig_ctx *c, int decide)
 {
 	TetraState *t = c->tetra;
 	const Geometry &g = c->geo;
-	tetra_accept_kernel<<<1, 32, 0, c->stream>>>(t->dpart, g.nchunks * g.nblk, g.K, c->S, t->Sprop, t->dstat, t->accepted, c->sc, c->iter, c->key0, c->key1, decide);
+	tetra_dind_kernel<<<nb((size_t)g.Nloc, 128), 128, 0, c->stream>>>(t->dpart, t->dind, g);
+	CK(cudaGetLastError());
+	ig_status st = ig_allgather_double(c, t->dind, (size_t)c->shard_cap * g.K);
+	if (st != IG_OK) return st;
+	tetra_accept_kernel<<<1, RED1, 0, c->stream>>>(t->dind, g.N, g.K, c->S, t->Sprop, t->dstat, t->accepted, c->sc, c->iter, c->key0, c->key1, decide);
+	c->launches++;
 	CK(cudaGetLastError());
 	if (decide) {
 		tetra_select_kernel<<<nb((size_t)g.L * g.K * t->Gmax, 256), 256, 0, c->stream>>>(t->tabC, t->tabP, t->accepted, g.L, g.K, t->Gmax);

@@ -199,8 +199,8 @@ static void *worker(void *arg)
 		const int cap = (N + w->nrank - 1) / w->nrank, b = w->rank * cap, n = (N - b < cap) ? N - b : cap;
 		int l;
 		cfg.shard_rank = w->rank; cfg.shard_count = w->nrank; cfg.shard_begin = b; cfg.shard_size = n;
-		xs = (int16_t *)malloc((size_t)L * n * 2 * sizeof(int16_t));
-		for (l = 0; l < L; l++) memcpy(xs + (size_t)l * n * 2, gs->x + ((size_t)l * N + b) * 2, (size_t)n * 2 * sizeof(int16_t));
+		xs = (int16_t *)malloc((size_t)L * n * ploid * sizeof(int16_t));
+		for (l = 0; l < L; l++) memcpy(xs + (size_t)l * n * ploid, gs->x + ((size_t)l * N + b) * ploid, (size_t)n * ploid * sizeof(int16_t));
 		x = xs;
 		if (w->rank != 0) cfg.print_iter = 0;
 	}
@@ -313,7 +313,6 @@ int main(int argc, char **argv)
 	go.quiet = quiet_data;
 	if (ploid != 2 && ploid != 4) die("ploid must be 2 or 4");
 	if (ploid == 4 && autopoly != 1) die("-p 4 runs the autotetraploid model (-ap 1); the allotetraploid model is not built");
-	if (ploid == 4 && shard_individuals) die("-p 4: individuals of one chain are not sharded over GPUs in this build; spread chains instead");
 	if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
 	N = gs.totalsize; K = popnum; ns = (mode == 3 && ploid == 2) ? N : K;
 	/* mem_cal, InStruct.c:204-225 (the estimate is the reference's; kept for its two log lines) */

@@ -75,11 +75,42 @@ def gpu_mode():
             ok &= bool(np.array_equal(getattr(ch, name), getattr(c1, name)))
         ok &= ch.totallkh == c1.totallkh and ch.totallkh2 == c1.totallkh2 and bool(np.array_equal(cv, cv1))
         ok &= bool(np.array_equal(zloc, z1[:, b:e, :]))
+    ok &= _tetra_sharded(rank, world, local)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("GPU_SHARD_OK" if int(flag.item()) == 1 else "GPU_SHARD_MISMATCH")
     dist.destroy_process_group()
+
+
+def _tetra_sharded(rank, world, local):
+    """Autotetraploid: the sharded chain (int32 tally all-reduce, per-individual S statistics and
+    records all-gathered, fixed-order reductions) is bit-identical to the one-GPU chain."""
+    from instruct_b200 import Sampler, SeqData, _lib
+    from instruct_b200.synth import make_tetra_dataset
+    K = 3
+    d = make_tetra_dataset(N=301, L=45, K=K, A=4, miss=0.04, seed=9)
+    kw = dict(update=20, burnin=8, thinning=3, ckrep=4, seed=77)
+    xs = shard_genotypes(d.x, world, rank)
+    s = Sampler(SeqData(xs, d.allelenum, K, ploid=4, autopoly=1), device=local, shard_rank=rank, shard_count=world, totalsize=d.N, **kw)
+    s.comm_init(broadcast_unique_id(Sampler.unique_id, rank))
+    ch, cv = s.run_chain(0, initd=[0.3, 0.5, 0.7])
+    zloc, gloc = s.get(_lib.STATE_Z), s.get(_lib.STATE_GENO)
+    s.close()
+    ok = True
+    if rank == 0:
+        s1 = Sampler(SeqData(d.x, d.allelenum, K, ploid=4, autopoly=1), device=local, **kw)
+        c1, cv1 = s1.run_chain(0, initd=[0.3, 0.5, 0.7])
+        z1, g1 = s1.get(_lib.STATE_Z), s1.get(_lib.STATE_GENO)
+        s1.close()
+        b, e = shard_bounds(d.N, world, 0)
+        for name in ("qq", "qq2", "self_rates", "self_rates2", "indvlkh"):
+            ok &= bool(np.array_equal(getattr(ch, name), getattr(c1, name)))
+        ok &= ch.totallkh == c1.totallkh and ch.totallkh2 == c1.totallkh2 and bool(np.array_equal(cv, cv1))
+        ok &= bool(np.array_equal(zloc, z1[:, b:e, :])) and bool(np.array_equal(gloc, g1[:, b:e, :]))
+        if not ok:
+            print("TETRA_SHARD_MISMATCH", ch.totallkh, c1.totallkh, ch.self_rates, c1.self_rates)
+    return ok
 
 
 if __name__ == "__main__":
