@@ -267,7 +267,12 @@ def run_ours(args):
     s.chain_init(0 if shard_ind else rank, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
     s.sweep(args.warmup)
     s.sync()
-    s.profile(True)
+    # per-launch events around the dominant kernel ride inside the timed region for the HBM-sized
+    # workloads; the small ones are launch-bound and replayed as a CUDA graph (no events inside a
+    # graph), so their kernel share is measured on a second, directly launched run of the same length
+    inline_profile = L * N >= 50_000_000 or world > 1
+    if inline_profile:
+        s.profile(True)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -278,6 +283,12 @@ def run_ours(args):
     ms = s.time_sweeps(args.steps)               # CUDA events on the library's stream, sync both sides
     torch.cuda.synchronize()
     nz, zq_ms, k1 = s.profile_read()
+    ms_direct = ms
+    if not inline_profile:
+        s.profile(True)
+        ms_direct = s.time_sweeps(args.steps)
+        torch.cuda.synchronize()
+        nz, zq_ms, _ = s.profile_read()
     if dist is not None:
         t = torch.tensor([ms, copies_local if not shard_ind else 0.0], device=dev, dtype=torch.float64)
         mx = t.clone()
@@ -336,7 +347,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "tetra_zs + tetra_geno (the two passes of one sweep)" if tetra else "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
                          "algorithmic_bytes_per_launch": algo_bytes_launch, "peak_source": peak_src,
-                         "share_of_step": zq_ms / ms if ms > 0 else None},
+                         "share_of_step": zq_ms / ms_direct if ms_direct > 0 else None,
+                         "graph_replay": not inline_profile, "ms_per_step_direct_launch": ms_direct / args.steps},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None,
             "e2e": e2e, "gpu_launches": int(k1 - k0), "clocks": clk,
         }

@@ -69,7 +69,9 @@ typedef struct ig_config {
 	int32_t shard_rank;
 	int32_t shard_count;
 	int32_t rng_rounds;                 /* Philox4x32 rounds of the bulk Z draw: 7 (default when 0; the Crush-resistant minimum of Salmon et al. SC11) or 10; every other draw uses 10 */
-	int32_t reserved[7];
+	int32_t use_graph;                  /* 0 (default): replay each sweep as a CUDA graph where every kernel argument is
+	                                       sweep-invariant (no host DP step, -e 1, one GPU); 2: always launch directly */
+	int32_t reserved[6];
 } ig_config;
 
 /* The running moments of CHAIN (mcmc.h:29-53), host-resident, caller-allocated. Sizes:

@@ -42,7 +42,7 @@ class IgConfig(C.Structure):
         ("update", C.c_int64), ("burnin", C.c_int64), ("thinning", C.c_int32), ("ckrep", C.c_int32),
         ("seed", C.c_uint64),
         ("device", C.c_int32), ("shard_begin", C.c_int32), ("shard_size", C.c_int32), ("shard_rank", C.c_int32),
-        ("shard_count", C.c_int32), ("rng_rounds", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("shard_count", C.c_int32), ("rng_rounds", C.c_int32), ("use_graph", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -152,6 +152,7 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
 	for (auto e : c->ev) cudaEventDestroy(e);
+	if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
 	tetra_destroy(c);
 	free_all(c);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -413,6 +414,7 @@ static ZQArgs zq_args(ig_ctx *c)
 	a.Xt = c->Xt; a.Zt = c->Zt; a.P = c->P; a.n = c->n; a.Qf = c->Qf; a.gpair = c->gpair;
 	a.pcnt = c->pcnt; a.plog = c->plog; a.pnsh = c->pnsh; a.geo = c->geo; a.iter = c->iter; a.key0 = c->key0; a.key1 = c->key1;
 	a.type_freq = c->cfg.type_freq;
+	a.iter_dev = c->iter_dev;
 	a.k_mant = 0x007fffffu; a.k_one = 0x3f800000u;
 	return a;
 }
@@ -421,7 +423,7 @@ static ig_status phase_update_P(ig_ctx *c)
 {
 	ig_status st = exchange_tally(c);
 	if (st != IG_OK) return st;
-	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, 0};
+	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, c->iter_dev, 0};
 	CK(launch_p_dirichlet(a, c->stream));
 	c->launches++;
 	return IG_OK;
@@ -443,7 +445,7 @@ static ig_status phase_update_S(ig_ctx *c)
 	}
 	// UPMCMC.state is read by every CTA and written by one: double-buffered
 	PreArgs a{c->ind, c->S, c->state, c->state2, c->gprop, c->gpair, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1,
-	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl};
+	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl, c->iter_dev};
 	CK(launch_pre_sweep(a, c->stream));
 	if (c->cfg.mode == 2 && c->cfg.back_refl == 0) std::swap(c->state, c->state2);
 	c->launches++;
@@ -459,7 +461,7 @@ static ig_status phase_zq(ig_ctx *c, int init)
 	CK(launch_zq_sweep(a, c->rounds, c->stream));
 	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
 	EpiArgs e{c->pcnt, c->plog, c->pnsh, c->nhet, c->nsh, c->ind, c->Qf, c->cnt, c->llparts, c->gpair, c->sc, c->geo,
-	          c->iter, c->key0, c->key1, init, a.type_freq};
+	          c->iter, c->key0, c->key1, init, a.type_freq, init ? nullptr : c->iter_dev};
 	CK(launch_epilogue(e, c->stream));
 	c->launches += 2;
 	return exchange_individuals(c);
@@ -467,13 +469,13 @@ static ig_status phase_zq(ig_ctx *c, int init)
 
 static ig_status phase_alpha(ig_ctx *c)
 {
-	PostArgs a{c->ind, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1};
+	PostArgs a{c->ind, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1, c->iter_dev};
 	CK(launch_post_sweep(a, c->stream));
 	c->launches++;
 	return IG_OK;
 }
 
-static ig_status one_sweep(ig_ctx *c)
+static ig_status one_sweep_direct(ig_ctx *c)
 {
 	ig_status st;
 	if (c->tetra) return tetra_one_sweep(c);
@@ -482,6 +484,64 @@ static ig_status one_sweep(ig_ctx *c)
 	if ((st = phase_update_S(c)) != IG_OK) return st;      // update_S_* + G proposal  :211-212
 	if ((st = phase_zq(c, 0)) != IG_OK) return st;         // update_G accept, update_ZQ, cal_lkh :212-215
 	return phase_alpha(c);                                 // update_alpha, totallkh    :214-215
+}
+
+// A sweep of the small configurations is five launches of a few microseconds each: launch latency,
+// not the GPU, sets the rate.  Where every kernel argument is constant from sweep to sweep (no host
+// step, no buffer ping-pong, no communicator) the sweep is captured ONCE into a CUDA graph; the
+// sweep counter that keys the RNG is then read from device memory (DevScalars.iter, advanced by
+// post_sweep), and a replay is bit-identical to the direct launches.
+static bool graph_eligible(const ig_ctx *c)
+{
+	if (c->tetra || c->comm || c->profile || c->cfg.use_graph == 2) return false;
+	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1) return false;        // host Dirichlet-process step every sweep
+	if (c->cfg.mode == 2 && c->cfg.back_refl == 0) return false;         // UPMCMC.state is double-buffered
+	return true;
+}
+
+static ig_status one_sweep(ig_ctx *c)
+{
+	if (c->graph_failed || !graph_eligible(c)) return one_sweep_direct(c);
+	if (!c->graph_exec) {
+		cudaGraph_t graph = nullptr;
+		const uint32_t it0 = c->iter;
+		const int64_t l0 = c->launches;
+		// the device copy of the counter is kept current by post_sweep and ig_set_state; make sure
+		const uint32_t next = c->iter + 1;
+		CK(cudaMemcpyAsync(&c->sc->iter, &next, sizeof(next), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		c->iter_dev = &c->sc->iter;
+		c->dev_iter_valid = true;
+		cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+		ig_status st = IG_OK;
+		if (e == cudaSuccess) {
+			st = one_sweep_direct(c);
+			e = cudaStreamEndCapture(c->stream, &graph);
+		}
+		c->launches_per_sweep = c->launches - l0;
+		c->iter = it0;
+		c->launches = l0;
+		if (e == cudaSuccess && st == IG_OK) e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+		if (graph) cudaGraphDestroy(graph);
+		if (e != cudaSuccess || st != IG_OK || !c->graph_exec) {             // not capturable here: keep launching directly
+			cudaGetLastError();
+			c->graph_failed = true;
+			c->graph_exec = nullptr;
+			c->iter_dev = nullptr;
+			return one_sweep_direct(c);
+		}
+		c->iter_dev = nullptr;
+	}
+	if (!c->dev_iter_valid) {                                               // a phase hook or set_state ran in between
+		const uint32_t next = c->iter + 1;
+		CK(cudaMemcpyAsync(&c->sc->iter, &next, sizeof(next), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		c->dev_iter_valid = true;
+	}
+	CK(cudaGraphLaunch(c->graph_exec, c->stream));
+	c->iter++;
+	c->launches += c->launches_per_sweep;
+	return IG_OK;
 }
 
 extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *initd)
@@ -518,6 +578,7 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	c->launches += 3;
 	ig_status st = phase_zq(c, 1);
 	if (st != IG_OK) return st;
+	c->dev_iter_valid = false;
 	c->chain_ready = true;
 	return IG_OK;
 }
@@ -573,6 +634,7 @@ extern "C" ig_status ig_run_phase(ig_ctx *c, int32_t mask)
 	CK(cudaSetDevice(c->cfg.device));
 	ig_status st;
 	if (c->tetra) return tetra_run_phase(c, mask);
+	c->dev_iter_valid = false;
 	if (mask & IG_PHASE_UPDATE_P) if ((st = phase_update_P(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_UPDATE_S) if ((st = phase_update_S(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_ZQ) if ((st = phase_zq(c, 0)) != IG_OK) return st;
@@ -901,6 +963,7 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 		if ((st = need(bytes, 8, "ITER")) != IG_OK) return st;
 		c->iter = (uint32_t) * (const int64_t *)host;
 		c->chain_ready = true;
+		c->dev_iter_valid = false;
 		return IG_OK;
 	default:
 		return fail(IG_ERR_ARG, "state id %d cannot be set", id);

@@ -75,12 +75,13 @@ struct ig_ctx {
 	std::vector<cudaEvent_t> ev;
 	int ev_used = 0;
 	int64_t launches = 0;
-	// per-sweep exchanges of the individual-sharded mode (ig_api.cu); no-ops on one GPU
-ig_status ig_exchange_tally(ig_ctx *c);
-ig_status ig_exchange_individuals(ig_ctx *c);
-ig_status ig_allgather_double(ig_ctx *c, double *buf, size_t per_rank);
-
-// autotetraploid driver (tetra.cu); null for ploid 2
+	// CUDA-graph replay of one sweep (ig_api.cu one_sweep)
+	cudaGraphExec_t graph_exec = nullptr;
+	bool graph_failed = false;
+	int64_t launches_per_sweep = 0;
+	const uint32_t *iter_dev = nullptr;   // non-null only while a sweep is being captured
+	bool dev_iter_valid = false;          // DevScalars.iter is known to equal iter + 1
+	// autotetraploid driver (tetra.cu); null for ploid 2
 	ig::TetraState *tetra = nullptr;
 };
 

@@ -25,7 +25,7 @@ struct DevScalars {
 	int32_t alpha_accepts;
 	int32_t s_accepts;
 	int32_t flags;
-	int32_t pad;
+	uint32_t iter;           // the NEXT sweep's counter (RNG key); read by the kernels of a graph-replayed sweep, advanced by post_sweep
 };
 
 // running moments (store_chn, mcmc.c:1320) on the device
@@ -65,6 +65,7 @@ struct ZQArgs {
 	Geometry geo;
 	uint32_t iter;
 	uint32_t key0, key1;
+	const uint32_t *iter_dev;   // non-null: read the sweep counter from device memory (CUDA-graph replay)
 	int type_freq;
 	uint32_t k_mant, k_one;  // 0x007fffff, 0x3f800000 kept in registers on purpose (see uniform_big)
 };
@@ -87,12 +88,14 @@ struct EpiArgs {
 	uint32_t iter, key0, key1;
 	int init;                // 1: initial assignment pass (no G accept, no likelihood)
 	int type_freq;
+	const uint32_t *iter_dev;
 };
 cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s);
 
 struct PArgs {
 	int32_t *n; float *P; double *P64; const int32_t *allelenum;
 	Geometry geo; uint32_t iter, key0, key1;
+	const uint32_t *iter_dev;
 	int mono_ok;             // 1: a locus with one allele gets P = 1 (update_P_auto has no allelenum > 1 guard, poly_geno.c:425)
 };
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s);
@@ -101,11 +104,13 @@ struct PreArgs {
 	double *ind; double *S; const int32_t *state_in; int32_t *state_out; int32_t *gprop; int2 *gpair; DevScalars *sc;
 	double *gpart;           // [2][SC_MAX_CTAS][20] partials of the grid-wide sums
 	Geometry geo; uint32_t iter, key0, key1; int mode, prior_flag, back_refl;
+	const uint32_t *iter_dev;
 };
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s);
 
 struct PostArgs {
 	const double *ind; DevScalars *sc; double *gpart; Geometry geo; uint32_t iter, key0, key1;
+	const uint32_t *iter_dev;
 };
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
 

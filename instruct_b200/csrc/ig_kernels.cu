@@ -37,6 +37,7 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 {
 	const Geometry &g = a.geo;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	if (t >= g.Lpad * g.KP) return;
 	const int l = t / g.KP, k = t % g.KP;
 	const size_t base = (size_t)l * g.A * g.KP + k;
@@ -45,7 +46,7 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 		for (int al = 0; al < g.A; al++) { a.P[base + (size_t)al * g.KP] = (a.mono_ok && k < g.K && Al == 1 && al == 0) ? 1.0f : 0.0f; a.n[base + (size_t)al * g.KP] = 0; }
 		return;
 	}
-	Stream st((uint32_t)l, (uint32_t)k, a.iter, TAG_P, a.key0, a.key1);
+	Stream st((uint32_t)l, (uint32_t)k, iter, TAG_P, a.key0, a.key1);
 	double sum = 0.0;
 	double gam[64];
 	// allelenum_max is small (2 for SNPs, tens for microsatellites); larger loci spill to a second pass
@@ -59,7 +60,7 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 		}
 	} else {
 		for (int al = 0; al < Al; al++) sum += draw_gamma(st, (double)a.n[base + (size_t)al * g.KP] + 1.0);
-		Stream st2((uint32_t)l, (uint32_t)k, a.iter, TAG_P, a.key0, a.key1);     // replay the same stream
+		Stream st2((uint32_t)l, (uint32_t)k, iter, TAG_P, a.key0, a.key1);     // replay the same stream
 		for (int al = 0; al < g.A; al++) {
 			const double p = (al < Al) ? draw_gamma(st2, (double)a.n[base + (size_t)al * g.KP] + 1.0) / sum : 0.0;
 			a.P[base + (size_t)al * g.KP] = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 	const int K = g.K, REC = g.REC;
 	const int gstride = gridDim.x * SC_THREADS;
 	const int i_first = blockIdx.x * SC_THREADS + tid;
+	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	int phase = 0;
 
 	if (a.mode == 2) {
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 		grid_sum(grid, &part, 1, &cur, a.gpart, phase, sh);
 		int accepts = 0;
 		for (int j = 0; j < K; j++) {
-			Stream st((uint32_t)j, 0u, a.iter, TAG_SPOP, a.key0, a.key1);
+			Stream st((uint32_t)j, 0u, iter, TAG_SPOP, a.key0, a.key1);
 			double prop;
 			int new_state = 1;
 			const int cs = (a.back_refl == 0) ? a.state_in[j] : 1;
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 			const int stt = sel_state(s);
 			int gp;
 			if (stt == 1) {
-				Stream st((uint32_t)i, 0u, a.iter, TAG_GPROP, a.key0, a.key1);
+				Stream st((uint32_t)i, 0u, iter, TAG_GPROP, a.key0, a.key1);
 				const double v = floor(log(st.uniform()) / log(s)) + 1.0;    // rgeom(1 - s), random.c:311-321
 				gp = (v < 1.0) ? 1 : (v > 50.0 ? 50 : (int)v);
 			} else gp = (stt == 0) ? 1 : 50;
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 		double s = a.S[i];
 		const int gen = (int)a.ind[(size_t)i * REC + K + 2];
 		if (a.prior_flag == 0) {                             // update_S_IND, mcmc.c:864-886
-			Stream st((uint32_t)i, 0u, a.iter, TAG_SIND, a.key0, a.key1);
+			Stream st((uint32_t)i, 0u, iter, TAG_SIND, a.key0, a.key1);
 			double prop = s + (st.uniform() * 2.0 * 0.05 - 0.05);
 			if (prop <= 0.0) prop = -prop;
 			if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 		const int stt = sel_state(s);
 		int gp;
 		if (stt == 1) {
-			Stream st((uint32_t)i, 0u, a.iter, TAG_GPROP, a.key0, a.key1);
+			Stream st((uint32_t)i, 0u, iter, TAG_GPROP, a.key0, a.key1);
 			const double v = floor(log(st.uniform()) / log(s)) + 1.0;
 			gp = (v < 1.0) ? 1 : (v > 50.0 ? 50 : (int)v);
 		} else gp = (stt == 0) ? 1 : 50;
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 	const Geometry &g = a.geo;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int il = blockIdx.x * 32 + lane;
+	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	const int K = g.K, KP = g.KP;
 	const bool live = il < g.Nloc;
 	int cnt[MAX_K];
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 		// count is what the previous pass left in nsh (type_freq 0: already inside d_old)
 		if (a.type_freq != 0) d_old -= (double)a.nsh[il] * (double)(gg.y - gg.x) * LN2_D;
 		if (a.llparts) { double *lp = a.llparts + (size_t)il * 4; lp[0] = d_old; lp[1] = c_new; lp[2] = a_new; lp[3] = b_new; }
-		Stream sa((uint32_t)ig_global, 0u, a.iter, TAG_GACC, a.key0, a.key1);
+		Stream sa((uint32_t)ig_global, 0u, iter, TAG_GACC, a.key0, a.key1);
 		const double u = sa.uniform();
 		const double ratio = exp(d_old);
 		const bool acc = (ratio != ratio) || (u < fmin(1.0, ratio));
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 		rec[K] = c_new + (acc ? b_new : a_new);
 	}
 	const double alpha = a.sc->alpha;
-	Stream sq((uint32_t)ig_global, 0u, a.iter, TAG_Q, a.key0, a.key1);
+	Stream sq((uint32_t)ig_global, 0u, iter, TAG_Q, a.key0, a.key1);
 	double qv[MAX_K], sum = 0.0;
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++)
@@ -413,6 +416,7 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x, K = g.K, REC = g.REC;
 	const int gstride = gridDim.x * SC_THREADS;
+	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	double v[SC_MAXV], tot[SC_MAXV];
 #pragma unroll
 	for (int j = 0; j < SC_MAXV; j++) v[j] = 0.0;
@@ -430,8 +434,9 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 	a.sc->totallkh = tot[0];
 	a.sc->sumlogq = slq;
 	for (int k = 0; k < K; k++) a.sc->qcol[k] = tot[2 + k];
-	if (a.iter == 0xFFFFFFFFu) return;                      // statistics only (parity hook)
-	Stream st(0u, 0u, a.iter, TAG_ALPHA, a.key0, a.key1);
+	if (iter == 0xFFFFFFFFu) return;                        // statistics only (parity hook)
+	a.sc->iter = iter + 1;                                  // the next sweep's counter, for graph replay
+	Stream st(0u, 0u, iter, TAG_ALPHA, a.key0, a.key1);
 	const double alpha = a.sc->alpha;
 	const double ralpha = alpha + draw_normal(st);
 	if (ralpha > 0.0) {

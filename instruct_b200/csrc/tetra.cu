@@ -958,7 +958,7 @@ static ig_status tetra_update_p(ig_ctx *c)
 {
 	ig_status st = ig_exchange_tally(c);        // int32 n[L][A][K] summed over the shards
 	if (st != IG_OK) return st;
-	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, 1};
+	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, nullptr, 1};
 	CK(launch_p_dirichlet(a, c->stream));
 	c->launches++;
 	return IG_OK;

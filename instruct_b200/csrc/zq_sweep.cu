@@ -103,12 +103,12 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 // here, so the per-genotype sign test and its divergence bookkeeping are compiled out.
 template <int KP, int ROUNDS, bool TF0, int LR, bool CHECK>
 __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&zwo)[4], uint32_t (&zwn)[4], float rowb0f, float rowstridef,
-                                           uint32_t mt_global, uint32_t ig_global, const ZQArgs &a, const float (&q)[KP], const Thr &t,
+                                           uint32_t mt_global, uint32_t ig_global, uint32_t iter, const ZQArgs &a, const float (&q)[KP], const Thr &t,
                                            Acc &acc, const RegConst &kc)
 {
 #pragma unroll
 	for (int pr = 0; pr < 4; ++pr) {
-		const u32x4 rnd = philox4x32<ROUNDS>(u32x4{mt_global, ig_global, a.iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
+		const u32x4 rnd = philox4x32<ROUNDS>(u32x4{mt_global, ig_global, iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
 		const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 		uint32_t pair[2];
 #pragma unroll
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 	const float rowstridef = as_dn((uint32_t)rowsz * 4u);           // bytes per locus in the P chunk
 	const float tilestridef = as_dn((uint32_t)rowsz * 4u * TILE);
 	const RegConst kc{a.k_mant, a.k_one};
+	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	Thr t;
 	t.hist_bias = as_dn_signed((int)smem_addr(hist) + (tid & (R - 1)) * 4 - (int)(psm << LR));
 	t.cnt_t = as_dn(smem_addr(cntsm) + (uint32_t)tid * 4u);
@@ -238,9 +239,9 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 				// sign of the AND of all eight words: set iff every genotype is usable
 				const int any_missing = (xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6] | xw[7]) < 0;
 				if (__any_sync(0xffffffffu, any_missing))
-					micro_tile<KP, ROUNDS, TF0, LR, true>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, a, q, t, acc, kc);
+					micro_tile<KP, ROUNDS, TF0, LR, true>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, iter, a, q, t, acc, kc);
 				else
-					micro_tile<KP, ROUNDS, TF0, LR, false>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, a, q, t, acc, kc);
+					micro_tile<KP, ROUNDS, TF0, LR, false>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, iter, a, q, t, acc, kc);
 				if (live) stg_stream(zp + (size_t)mt * zstride, make_int4((int)zwn[0], (int)zwn[1], (int)zwn[2], (int)zwn[3]));
 				acc.lgA += acc.mA; acc.lgB += acc.mB; acc.lgD += acc.mD;
 			}

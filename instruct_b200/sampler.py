@@ -104,7 +104,7 @@ class Chain:
 
 
 def _config(data: SeqData, update=1, burnin=1, thinning=1, ckrep=0, seed=1, device=0, shard_rank=0, shard_count=1,
-            rng_rounds=0, totalsize=None) -> IgConfig:
+            rng_rounds=0, totalsize=None, use_graph=0) -> IgConfig:
     cfg = IgConfig()
     cfg.ploid, cfg.popnum, cfg.locinum = data.ploid, data.popnum, data.locinum
     cfg.totalsize = data.totalsize if totalsize is None else totalsize
@@ -118,6 +118,7 @@ def _config(data: SeqData, update=1, burnin=1, thinning=1, ckrep=0, seed=1, devi
     cfg.shard_rank, cfg.shard_count = shard_rank, shard_count
     cfg.shard_begin, cfg.shard_size = 0, 0
     cfg.rng_rounds = rng_rounds
+    cfg.use_graph = use_graph
     return cfg
 
 
@@ -173,11 +174,11 @@ class Sampler:
 
     def __init__(self, data: SeqData, update=1, burnin=1, thinning=1, ckrep=0, seed=1, device=0,
                  shard_rank=0, shard_count=1, rng_rounds=0, totalsize=None, x_device_ptr=None,
-                 allelenum_device_ptr=None):
+                 allelenum_device_ptr=None, use_graph=0):
         self.lib = _lib.load()
         self.data = data
         self.cfg = _config(data, update, burnin, thinning, ckrep, seed, device, shard_rank, shard_count, rng_rounds,
-                           totalsize)
+                           totalsize, use_graph)
         self.N = self.cfg.totalsize
         self.K, self.L = data.popnum, data.locinum
         self.h = C.c_void_p()

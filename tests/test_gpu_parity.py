@@ -256,6 +256,31 @@ def test_same_seed_same_chain_and_launch_shape_independence():
     assert a[0].step == a[0].steps == 10
 
 
+@pytest.mark.parametrize("mode,prior", [(2, 0), (3, 0), (1, 0)])
+def test_graph_replay_is_bit_identical_to_direct_launches(mode, prior):
+    """A sweep replayed as a CUDA graph (the default where it is eligible) reads its RNG counter
+    from device memory; the chain must equal the directly launched one bit for bit, also when
+    state hooks and single phases run between sweeps."""
+    d, sd = _mk(210, 37, 3, 4, 0.05, seed=19, mode=mode, prior_flag=prior)
+    res = []
+    for ug in (0, 2):
+        s = Sampler(sd, update=40, burnin=12, thinning=3, ckrep=4, seed=31, use_graph=ug)
+        ch, cv = s.run_chain(0, initd=[0.2, 0.5, 0.8])
+        s.chain_init(1, initd=[0.3, 0.4, 0.6])
+        s.sweep(3)
+        s.run_phase(_lib.PHASE_UPDATE_P)            # a hook between replays must not desynchronise the counter
+        s.sweep(2)
+        s.set(_lib.STATE_ITER, [11])
+        s.sweep(2)
+        res.append((ch, cv, s.get(_lib.STATE_Z), s.get(_lib.STATE_Q), s.get(_lib.STATE_INDVLKH), s.get(_lib.STATE_ITER)))
+        s.close()
+    a, b = res
+    assert a[0].totallkh == b[0].totallkh and np.array_equal(a[0].qq, b[0].qq) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0].gen, b[0].gen) and np.array_equal(a[0].indvlkh, b[0].indvlkh)
+    for u, v in zip(a[2:], b[2:]):
+        assert np.array_equal(u, v)
+
+
 def test_running_moments_match_direct_average():
     """store_chn (mcmc.c:1320): the device running means equal the plain average of the
     retained states read back sweep by sweep."""
