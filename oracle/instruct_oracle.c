@@ -72,7 +72,7 @@ orc_model *orc_new(int N, int L, int K, int ploid, int mode, int prior_flag, int
 	m->qq = (double *)calloc((size_t)N * K, sizeof(double));
 	m->qqnum = (double *)calloc((size_t)N * K, sizeof(double));
 	m->freq = (double *)calloc((size_t)K * L * m->Amax, sizeof(double));
-	ns = (mode == 3) ? N : K;
+	ns = (mode == 3 || mode == 5) ? N : K;   /* modes 4/5: self_rates holds UPMCMC.inbreed (mcmc.c:521-522) */
 	m->self_rates = (double *)calloc(ns, sizeof(double));
 	m->state = (int *)calloc(K, sizeof(int));
 	m->gen = (int *)calloc(N, sizeof(int));
@@ -321,6 +321,46 @@ double orc_proposal(const orc_model *m, const double *S)
 	return ld;
 }
 
+/* genofreq_inbreedcoff, mcmc.c:1707-1723 (diploid) */
+double orc_genofreq_F(int a0, int a1, double f0, double f1, double F)
+{
+	if (a0 == a1) return pow(f0, 2.0) * (1 - F) + f0 * F;
+	return 2 * f0 * f1 * (1 - F);
+}
+
+/* log_ld_F_pop (mcmc.c:1776-1809, by_pop = 1: F = inbreed[z0]) and log_ld_F_indv
+ * (mcmc.c:1812-1845, by_pop = 0: F = inbreed[0]) */
+double orc_log_ld_F(const orc_model *m, const double *inbreed, int by_pop, int i)
+{
+	double ll = 0;
+	int l;
+	for (l = 0; l < m->L; l++) {
+		int a0, a1, z0, z1;
+		double f0, f1;
+		if (!usable(m, i, l)) continue;
+		a0 = m->x[XO(m, l, i, 0)]; a1 = m->x[XO(m, l, i, 1)];
+		z0 = m->z[XO(m, l, i, 0)]; z1 = m->z[XO(m, l, i, 1)];
+		f0 = m->freq[FO(m, z0, l, a0)]; f1 = m->freq[FO(m, z1, l, a1)];
+		if (z0 == z1) ll += log(orc_genofreq_F(a0, a1, f0, f1, by_pop ? inbreed[z0] : inbreed[0]));
+		else {
+			ll += log(f0);
+			ll += log(f1);
+			if (a0 != a1) ll += log(2);
+		}
+	}
+	return ll;
+}
+
+/* log_ld_F_total, mcmc.c:1849-1866 */
+double orc_log_ld_F_total(const orc_model *m, const double *inbreed)
+{
+	double ld = 0;
+	int i;
+	if (m->mode == 4) for (i = 0; i < m->N; i++) ld += orc_log_ld_F(m, inbreed, 1, i);
+	if (m->mode == 5) for (i = 0; i < m->N; i++) ld += orc_log_ld_F(m, inbreed + i, 0, i);
+	return ld;
+}
+
 /* dgeom, mcmc.c:1596-1604 */
 double orc_dgeom(double s, int g) { return pow(s, (double)(g - 1)) * (1 - s); }
 
@@ -447,6 +487,49 @@ void orc_update_S_POP(orc_model *m)
 	}
 }
 
+/* update_inbreedcoff_POP, mcmc.c:986-1050.  The difference of log-likelihoods is used as it
+ * stands there: multiplied (not added to) by the Hastings ratio under -e 0 and accepted when
+ * u < exp(min(1, .)), which for u < 1 is the usual min(1, ratio) rule. */
+void orc_update_F_POP(orc_model *m)
+{
+	const double delta0 = 0.05;
+	double *tmp = m->scratch;
+	int j, i, st = 0;
+	for (j = 0; j < m->K; j++) {
+		double mh;
+		for (i = 0; i < m->K; i++) tmp[i] = m->self_rates[i];
+		if (m->back_refl == 1) {
+			tmp[j] = u01(&m->rng) * 2 * delta0 - delta0;
+			tmp[j] += m->self_rates[j];
+			if (tmp[j] <= 0.000) tmp[j] = 0.000 - tmp[j];
+			else if (tmp[j] >= 1.000) tmp[j] = 1.000 - (tmp[j] - 1.000);
+		} else {
+			tmp[j] = propose_three_state(&m->rng, &st, m->state[j]);
+		}
+		mh = orc_log_ld_F_total(m, tmp) - orc_log_ld_F_total(m, m->self_rates);
+		if (m->back_refl == 0) mh *= trans_prob(m->state[j], st) / trans_prob(st, m->state[j]);
+		if (u01(&m->rng) < exp(MIN2(1, mh))) {
+			m->self_rates[j] = tmp[j];
+			if (m->back_refl == 0) m->state[j] = st;
+		}
+	}
+}
+
+/* update_F_IND, mcmc.c:888-910 (two independent reflections, unlike update_inbreedcoff_POP) */
+void orc_update_F_IND(orc_model *m)
+{
+	const double delta0 = 0.05;
+	int j;
+	for (j = 0; j < m->N; j++) {
+		double t = u01(&m->rng) * 2 * delta0 - delta0, mh;
+		t += m->self_rates[j];
+		if (t <= 0.0) t = 0.0 - t;
+		if (t >= 1.0) t = 1.0 - (t - 1);
+		mh = exp(orc_log_ld_F(m, &t, 0, j) - orc_log_ld_F(m, m->self_rates + j, 0, j));
+		m->self_rates[j] = (u01(&m->rng) < MIN2(1, mh)) ? t : m->self_rates[j];
+	}
+}
+
 /* update_S_IND, mcmc.c:864-886 */
 void orc_update_S_IND(orc_model *m)
 {
@@ -544,7 +627,9 @@ void orc_cal_lkh(orc_model *m)
 	int i;
 	m->totallkh = 0;
 	for (i = 0; i < m->N; i++) {
-		m->indvlkh[i] = (m->mode == 1) ? orc_log_ld_noselfing(m, i) : orc_log_ld_indv(m, m->gen[i], i);
+		if (m->mode == 4) m->indvlkh[i] = orc_log_ld_F(m, m->self_rates, 1, i);
+		else if (m->mode == 5) m->indvlkh[i] = orc_log_ld_F(m, m->self_rates + i, 0, i);
+		else m->indvlkh[i] = (m->mode == 1) ? orc_log_ld_noselfing(m, i) : orc_log_ld_indv(m, m->gen[i], i);
 		m->totallkh += m->indvlkh[i];
 	}
 }
@@ -672,6 +757,13 @@ static void one_sweep(orc_model *m)
 		orc_cal_lkh(m);
 		return;
 	}
+	if (m->mode == 4 || m->mode == 5) {               /* mcmc.c:266-270, :424-437 (uniform prior) */
+		if (m->mode == 4) orc_update_F_POP(m); else orc_update_F_IND(m);
+		orc_update_ZQ(m, 0);
+		orc_update_alpha(m);
+		orc_cal_lkh(m);
+		return;
+	}
 	if (m->mode == 2) orc_update_S_POP(m);
 	if (m->mode == 3) {
 		if (m->prior_flag == 1) orc_update_DP(m);
@@ -687,7 +779,7 @@ void orc_sweeps(orc_model *m, int n) { while (n-- > 0) one_sweep(m); }
 orc_chain *orc_chain_new(const orc_model *m, int ckrep)
 {
 	orc_chain *c = (orc_chain *)calloc(1, sizeof(orc_chain));
-	int ns = (m->mode == 3) ? m->N : m->K;
+	int ns = (m->mode == 3 || m->mode == 5) ? m->N : m->K;
 	c->indvlkh = (double *)calloc(m->N, sizeof(double));
 	c->qq = (double *)calloc((size_t)m->N * m->K, sizeof(double));
 	c->qq2 = (double *)calloc((size_t)m->N * m->K, sizeof(double));
@@ -708,7 +800,7 @@ void orc_chain_free(orc_chain *c)
 /* initialize_chn, mcmc.c:644-738: every running moment starts at 1 with step = 0 */
 static void chain_reset(const orc_model *m, orc_chain *c)
 {
-	int ns = (m->mode == 3) ? m->N : m->K;
+	int ns = (m->mode == 3 || m->mode == 5) ? m->N : m->K;
 	long j;
 	c->step = 0; c->totallkh = 1; c->totallkh2 = 1;
 	for (j = 0; j < m->N; j++) { c->indvlkh[j] = 1; c->gen[j] = 1; c->gen2[j] = 1; }
@@ -727,7 +819,7 @@ static inline double run_mean(double mean, double xv, long step)
 /* store_chn, mcmc.c:1320-1456 (modes 2/3 members) */
 void orc_store_chn(const orc_model *m, orc_chain *c)
 {
-	int ns = (m->mode == 3) ? m->N : m->K;
+	int ns = (m->mode == 3 || m->mode == 5) ? m->N : m->K;
 	long j;
 	c->totallkh = run_mean(c->totallkh, m->totallkh, c->step);
 	c->totallkh2 = run_mean(c->totallkh2, m->totallkh * m->totallkh, c->step);
@@ -741,6 +833,7 @@ void orc_store_chn(const orc_model *m, orc_chain *c)
 		c->self_rates[j] = run_mean(c->self_rates[j], m->self_rates[j], c->step);
 		c->self_rates2[j] = run_mean(c->self_rates2[j], m->self_rates[j] * m->self_rates[j], c->step);
 	}
+	if (m->mode == 4 || m->mode == 5) { c->step++; return; }   /* :1388-1409 store inbreed in the same way; no generations */
 	for (j = 0; j < m->N; j++) {
 		/* :1428-1433 -- the fallbacks there use integer division; gen >= 1 keeps the mean non-zero */
 		if (c->gen[j] != 0) c->gen[j] = c->gen[j] * ((c->step + m->gen[j] / c->gen[j]) / (1 + c->step));
@@ -773,6 +866,13 @@ int orc_run_chain(orc_model *m, long update, long burnin, int thinning, int ckre
 			m->self_rates[i] = initd[i];
 			if (m->back_refl == 0) m->state[i] = orc_dt_stat(m->self_rates[i]);
 		}
+	} else if (m->mode == 4) {
+		for (i = 0; i < m->K; i++) {                             /* mcmc.c:256-260 */
+			m->self_rates[i] = initd[i];
+			if (m->back_refl == 0) m->state[i] = orc_dt_stat(m->self_rates[i]);
+		}
+	} else if (m->mode == 5) {
+		for (i = 0; i < m->N; i++) m->self_rates[i] = u01(&m->rng);          /* mcmc.c:416-419, uniform prior only */
 	} else {
 		if (m->prior_flag == 1) orc_init_DP(m);                  /* mcmc.c:318-324 */
 		else for (i = 0; i < m->N; i++) m->self_rates[i] = u01(&m->rng);   /* :326-327 */

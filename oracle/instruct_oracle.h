@@ -63,6 +63,9 @@ double orc_log_ld_indv(const orc_model *m, int gen, int i);
 double orc_log_ld_noselfing(const orc_model *m, int i);
 double orc_proposal(const orc_model *m, const double *S);
 double orc_dgeom(double s, int g);
+double orc_genofreq_F(int a0, int a1, double f0, double f1, double F);      /* genofreq_inbreedcoff, mcmc.c:1707 */
+double orc_log_ld_F(const orc_model *m, const double *inbreed, int by_pop, int i); /* log_ld_F_pop / _indv, mcmc.c:1776,1812 */
+double orc_log_ld_F_total(const orc_model *m, const double *inbreed);       /* mcmc.c:1849 */
 int orc_dt_stat(double s);
 double orc_alpha_logratio(const orc_model *m, double ralpha);      /* log form of mcmc.c:1254-1260 */
 double orc_alpha_ratio_product(const orc_model *m, double ralpha); /* the reference's product form */
@@ -73,6 +76,8 @@ void orc_z_conditional(const orc_model *m, int i, int l, int c, double *prob /*[
 void orc_update_P(orc_model *m);
 void orc_update_S_POP(orc_model *m);
 void orc_update_S_IND(orc_model *m);
+void orc_update_F_POP(orc_model *m);   /* update_inbreedcoff_POP, mcmc.c:986 (mode 4; self_rates holds inbreed) */
+void orc_update_F_IND(orc_model *m);   /* update_F_IND, mcmc.c:888 (mode 5, uniform prior) */
 void orc_update_G(orc_model *m);
 void orc_update_ZQ(orc_model *m, int init_flag);
 void orc_update_alpha(orc_model *m);

@@ -88,7 +88,11 @@ def oracle_lib():
         L.orc_alpha_ratio_product.argtypes = [C.c_void_p, C.c_double]
         L.orc_check_empty_cluster.argtypes = [C.c_void_p]
         L.orc_z_conditional.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]
-        for name in ["orc_update_P", "orc_update_S_POP", "orc_update_S_IND", "orc_update_G", "orc_update_alpha",
+        L.orc_log_ld_F.restype = C.c_double
+        L.orc_log_ld_F.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int]
+        L.orc_log_ld_F_total.restype = C.c_double
+        L.orc_log_ld_F_total.argtypes = [C.c_void_p, c_dp]
+        for name in ["orc_update_P", "orc_update_S_POP", "orc_update_S_IND", "orc_update_F_POP", "orc_update_F_IND", "orc_update_G", "orc_update_alpha",
                      "orc_cal_lkh", "orc_init_DP", "orc_update_DP"]:
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_update_ZQ.argtypes = [C.c_void_p, C.c_int]
@@ -125,7 +129,7 @@ class Oracle:
         self.h = self.lib.orc_new(self.N, self.L, K, self.ploid, mode, prior_flag, back_refl, type_freq,
                                   float(alpha_dpm), self.x.ctypes.data, self.allelenum.ctypes.data)
         self.Amax = self.lib.orc_amax(self.h)
-        ns = self.N if mode == 3 else K
+        ns = self.N if mode in (3, 5) else K
         as_arr = np.ctypeslib.as_array
         self.z = as_arr(C.cast(self.lib.orc_z(self.h), C.POINTER(C.c_int8)), (self.L, self.N, self.ploid))
         self.qq = as_arr(self.lib.orc_qq(self.h), (self.N, K))
@@ -210,6 +214,21 @@ class Oracle:
     def update_S_IND(self):
         self.lib.orc_update_S_IND(self.h)
 
+    def update_F_POP(self):
+        self.lib.orc_update_F_POP(self.h)
+
+    def update_F_IND(self):
+        self.lib.orc_update_F_IND(self.h)
+
+    def log_ld_F(self, inbreed, by_pop, i):
+        """log_ld_F_pop (by_pop=1, inbreed[K]) / log_ld_F_indv (by_pop=0, inbreed[0]), mcmc.c:1776,1812"""
+        v = np.ascontiguousarray(np.atleast_1d(inbreed), dtype=np.float64)
+        return self.lib.orc_log_ld_F(self.h, _dp(v), int(by_pop), int(i))
+
+    def log_ld_F_total(self, inbreed):
+        v = np.ascontiguousarray(inbreed, dtype=np.float64)
+        return self.lib.orc_log_ld_F_total(self.h, _dp(v))
+
     def update_G(self):
         self.lib.orc_update_G(self.h)
 
@@ -235,7 +254,7 @@ class Oracle:
         self.lib.orc_sweeps(self.h, n)
 
     def run_chain(self, update, burnin, thinning, ckrep=0, nstep_check_empty=20, initd=None):
-        ns = self.N if self.mode == 3 else self.K
+        ns = self.N if self.mode in (3, 5) else self.K
         ch = self.lib.orc_chain_new(self.h, ckrep)
         initd = np.ascontiguousarray(initd if initd is not None else np.full(self.K, 0.5), dtype=np.float32)
         flag = self.lib.orc_run_chain(self.h, update, burnin, thinning, ckrep, nstep_check_empty,
@@ -290,7 +309,11 @@ def ref_lib():
         L.refh_ran1.restype = C.c_double
         L.refh_update_P.argtypes = [C.c_void_p, c_ip]
         L.refh_update_ZQ.argtypes = [C.c_void_p, C.c_int]
-        for n_ in ["refh_update_G", "refh_update_S_POP", "refh_update_S_IND", "refh_update_alpha", "refh_cal_lkh",
+        L.refh_log_ld_F.restype = C.c_double
+        L.refh_log_ld_F.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int]
+        L.refh_log_ld_F_total.restype = C.c_double
+        L.refh_log_ld_F_total.argtypes = [C.c_void_p, c_dp]
+        for n_ in ["refh_update_G", "refh_update_S_POP", "refh_update_S_IND", "refh_update_F_POP", "refh_update_F_IND", "refh_update_alpha", "refh_cal_lkh",
                    "refh_init_DP", "refh_update_DP", "refh_check_empty_cluster", "refh_dp_nclusters"]:
             getattr(L, n_).argtypes = [C.c_void_p]
         L.refh_log_ld_indv.restype = C.c_double
@@ -359,10 +382,10 @@ class Reference:
     def get_freq(self): return self._xd(self.lib.refh_freq, (self.K, self.L, self.Amax))
 
     def set_self(self, s):
-        self._xd(self.lib.refh_self, (self.N if self.mode == 3 else self.K,), s)
+        self._xd(self.lib.refh_self, (self.N if self.mode in (3, 5) else self.K,), s)
 
     def get_self(self):
-        return self._xd(self.lib.refh_self, (self.N if self.mode == 3 else self.K,))
+        return self._xd(self.lib.refh_self, (self.N if self.mode in (3, 5) else self.K,))
 
     def set_gen(self, g):
         a = np.ascontiguousarray(g, dtype=np.int32)
@@ -407,6 +430,16 @@ class Reference:
     def update_G(self): self.lib.refh_update_G(self.h)
     def update_S_POP(self): self.lib.refh_update_S_POP(self.h)
     def update_S_IND(self): self.lib.refh_update_S_IND(self.h)
+    def update_F_POP(self): self.lib.refh_update_F_POP(self.h)
+    def update_F_IND(self): self.lib.refh_update_F_IND(self.h)
+
+    def log_ld_F(self, inbreed, by_pop, i):
+        v = np.ascontiguousarray(np.atleast_1d(inbreed), dtype=np.float64)
+        return self.lib.refh_log_ld_F(self.h, _dp(v), int(by_pop), int(i))
+
+    def log_ld_F_total(self, inbreed):
+        v = np.ascontiguousarray(inbreed, dtype=np.float64)
+        return self.lib.refh_log_ld_F_total(self.h, _dp(v))
     def update_alpha(self): self.lib.refh_update_alpha(self.h)
     def cal_lkh(self): self.lib.refh_cal_lkh(self.h)
     def init_DP(self): self.lib.refh_init_DP(self.h)
@@ -424,7 +457,7 @@ class Reference:
     def mcmc_updating(self, update, burnin, thinning, ckrep=1, nstep_check_empty=20, initd=None):
         """One chain through the reference's own driver (mcmc.c:63)."""
         N, K = self.N, self.K
-        ns = N if self.mode == 3 else K
+        ns = N if self.mode in (3, 5) else K
         self.lib.refh_set_flags(self.h, nstep_check_empty, 0, 0)
         tot, ind = np.zeros(2), np.zeros(N)
         qq, qq2 = np.zeros((N, K)), np.zeros((N, K))

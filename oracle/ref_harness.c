@@ -149,10 +149,13 @@ void refh_gen(REFH *h, int *g, int dir)
 {
 	int i; for (i = 0; i < h->data.totalsize; i++) { if (dir) h->ptr->generation[i] = g[i]; else g[i] = h->ptr->generation[i]; }
 }
-static int n_self(REFH *h) { return h->data.mode == 3 ? h->data.totalsize : h->data.popnum; }
+static int n_self(REFH *h) { return (h->data.mode == 3 || h->data.mode == 5) ? h->data.totalsize : h->data.popnum; }
+/* modes 4/5 keep their inbreeding coefficients in UPMCMC.inbreed (mcmc.c:521-522) */
+static double *self_vec(REFH *h) { return (h->data.mode == 4 || h->data.mode == 5) ? h->ptr->inbreed : h->ptr->self_rates; }
 void refh_self(REFH *h, double *s, int dir)
 {
-	int i; for (i = 0; i < n_self(h); i++) { if (dir) h->ptr->self_rates[i] = s[i]; else s[i] = h->ptr->self_rates[i]; }
+	int i; double *v = self_vec(h);
+	for (i = 0; i < n_self(h); i++) { if (dir) v[i] = s[i]; else s[i] = v[i]; }
 }
 void refh_state(REFH *h, int *s, int dir)
 {
@@ -192,6 +195,13 @@ void refh_update_ZQ(REFH *h, int init_flag) { update_ZQ(&h->ptr, h->data, init_f
 void refh_update_G(REFH *h) { update_G(h->data, &h->ptr); }
 void refh_update_S_POP(REFH *h) { update_S_POP(h->data, &h->ptr); }
 void refh_update_S_IND(REFH *h) { update_S_IND(h->data.totalsize, &h->ptr); }
+void refh_update_F_POP(REFH *h) { update_inbreedcoff_POP(h->data, &h->ptr); }
+void refh_update_F_IND(REFH *h) { update_F_IND(h->data.totalsize, &h->ptr, h->data); }
+double refh_log_ld_F(REFH *h, double *inbreed, int by_pop, int i)
+{
+	return by_pop ? log_ld_F_pop(inbreed, h->ptr, i, h->data) : log_ld_F_indv(inbreed[0], h->ptr, i, h->data);
+}
+double refh_log_ld_F_total(REFH *h, double *inbreed) { return log_ld_F_total(inbreed, h->ptr, h->data); }
 void refh_update_alpha(REFH *h) { update_alpha(&h->ptr, h->data, h->qqnum); }
 void refh_cal_lkh(REFH *h) { cal_lkh(&h->ptr, h->data); }
 double refh_log_ld_indv(REFH *h, int gen, int i) { return log_ld_indv(gen, h->ptr, i, h->data); }
@@ -242,6 +252,8 @@ void refh_sweeps(REFH *h, int n)
 			if (h->data.prior_flag == 1) refh_update_DP(h);
 			if (h->data.prior_flag == 0) update_S_IND(h->data.totalsize, &h->ptr);
 		}
+		if (h->data.mode == 4) update_inbreedcoff_POP(h->data, &h->ptr);
+		if (h->data.mode == 5) update_F_IND(h->data.totalsize, &h->ptr, h->data);
 		if (h->data.mode == 2 || h->data.mode == 3) update_G(h->data, &h->ptr);
 		update_ZQ(&h->ptr, h->data, 0, &h->qqnum);
 		update_alpha(&h->ptr, h->data, h->qqnum);
@@ -269,7 +281,7 @@ int refh_mcmc_updating(REFH *h, long update, long burnin, int thinning, int ckre
 	c = mcmc_updating(*d, init, 0, &cvg);
 	flag = c.flag_empty_cluster;
 	if (flag == 1) return 1;
-	ns = (d->mode == 3) ? d->totalsize : d->popnum;
+	ns = (d->mode == 3 || d->mode == 5) ? d->totalsize : d->popnum;
 	if (out_tot) { out_tot[0] = c.totallkh; out_tot[1] = c.totallkh2; }
 	for (i = 0; i < d->totalsize; i++) {
 		if (out_indvlkh) out_indvlkh[i] = c.indvlkh[i];
@@ -286,6 +298,11 @@ int refh_mcmc_updating(REFH *h, long update, long burnin, int thinning, int ckre
 		for (i = 0; i < ns; i++) {
 			if (out_self) out_self[i] = c.self_rates[i];
 			if (out_self2) out_self2[i] = c.self_rates2[i];
+		}
+	if (d->mode == 4 || d->mode == 5)
+		for (i = 0; i < ns; i++) {
+			if (out_self) out_self[i] = c.inbreed[i];
+			if (out_self2) out_self2[i] = c.inbreed2[i];
 		}
 	if (out_convg) for (i = 0; i < ckrep; i++) out_convg[i] = cvg.convg_ld[i];
 	free_chain(&c, *d);

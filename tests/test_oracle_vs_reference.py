@@ -100,6 +100,45 @@ def test_whole_chain_bit_exact_mode1():
         assert np.array_equal(np.asarray(co[k]), np.asarray(cr[k])), k
 
 
+@pytest.mark.parametrize("mode,back_refl", [(4, 1), (4, 0), (5, 1)])
+def test_whole_chain_bit_exact_inbreeding_modes(mode, back_refl):
+    """Modes 4/5 (mcmc_POP_inbreedcoff mcmc.c:242, mcmc_INDV_inbreedcoff :386 with the uniform
+    prior): inbreeding coefficients per population / per individual instead of selfing rates."""
+    K = 3
+    d = make_dataset(N=40, L=19, K=K, A=4, miss=0.04, seed=13)
+    o = Oracle(d.x, d.allelenum, K, mode=mode, back_refl=back_refl)
+    r = Reference(d.x, d.allelenum, K, mode=mode, back_refl=back_refl)
+    o.setseeds(13, 4, 1972); r.setseeds(13, 4, 1972)
+    kw = dict(update=120, burnin=40, thinning=5, ckrep=8, nstep_check_empty=10, initd=[0.3, 0.5, 0.7])
+    co = o.run_chain(**kw)
+    cr = r.mcmc_updating(**kw)
+    assert co["flag_empty_cluster"] == cr["flag_empty_cluster"] == 0
+    for k in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
+        assert np.array_equal(np.asarray(co[k]), np.asarray(cr[k])), k
+
+
+@pytest.mark.parametrize("mode", [4, 5])
+def test_inbreeding_loglik(mode):
+    K = 4
+    d = make_dataset(N=30, L=40, K=K, A=5, miss=0.05, seed=10)
+    o, r = Oracle(d.x, d.allelenum, K, mode=mode), Reference(d.x, d.allelenum, K, mode=mode)
+    rng = np.random.default_rng(3)
+    _state(o, rng, K)
+    o.self_rates[...] = rng.uniform(0.05, 0.95, o.self_rates.shape)
+    r.set_z(o.z); r.set_qq(o.qq); r.set_freq(o.freq); r.set_alpha(o.alpha); r.set_self(o.self_rates)
+    F = rng.uniform(0.0, 1.0, K)
+    for i in range(0, 30, 4):
+        if mode == 4:
+            assert o.log_ld_F(F, 1, i) == r.log_ld_F(F, 1, i)
+        else:
+            assert o.log_ld_F(F[:1], 0, i) == r.log_ld_F(F[:1], 0, i)
+    Ft = rng.uniform(0, 1, o.self_rates.shape)
+    assert o.log_ld_F_total(Ft) == r.log_ld_F_total(Ft)
+    r.cal_lkh(); o.cal_lkh()
+    ind, tot = r.get_lkh()
+    assert np.array_equal(ind, o.indvlkh) and tot == o.totallkh
+
+
 def test_single_updates_follow_reference_stream():
     """Each conditional update consumes the RNG like the reference (state compared after each)."""
     K = 3
