@@ -85,7 +85,9 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	if (!cfg || !out) return fail(IG_ERR_ARG, "null argument");
 	*out = nullptr;
 	if (cfg->ploid != 2 && cfg->ploid != 4) return fail(IG_ERR_UNSUPPORTED, "ploid %d: 2 (diploid) or 4 (autotetraploid)", cfg->ploid);
-	if (cfg->ploid == 2 && (cfg->mode < 1 || cfg->mode > 3)) return fail(IG_ERR_UNSUPPORTED, "mode %d: modes 1, 2 and 3 are built", cfg->mode);
+	if (cfg->ploid == 2 && (cfg->mode < 1 || cfg->mode > 5)) return fail(IG_ERR_UNSUPPORTED, "mode %d: modes 1 to 5 are built", cfg->mode);
+	if (cfg->ploid == 2 && cfg->mode == 5 && cfg->prior_flag != 0)
+		return fail(IG_ERR_UNSUPPORTED, "mode 5 with the Dirichlet-process prior (-f 1) is not built; use the uniform prior (-f 0)");
 	if (cfg->popnum < 1 || cfg->popnum > MAX_K) return fail(IG_ERR_UNSUPPORTED, "popnum %d outside 1..%d", cfg->popnum, MAX_K);
 	if (cfg->locinum < 1 || cfg->totalsize < 1) return fail(IG_ERR_ARG, "empty data set (N=%d, L=%d)", cfg->totalsize, cfg->locinum);
 	if (cfg->mode == 3 && cfg->prior_flag != 0 && cfg->prior_flag != 1) return fail(IG_ERR_ARG, "prior_flag must be 0 or 1");
@@ -120,8 +122,10 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	g.K = cfg->popnum;
 	g.KP = (int)pad_k(g.K);
 	g.A = 2;                   // fixed when the genotypes are loaded
-	g.REC = g.K + 3;
-	c->ns = (cfg->mode == 3) ? N : (cfg->mode == 1 ? 0 : g.K);       // mode 1 has no selfing rates
+	g.fmode = (cfg->ploid == 2 && cfg->mode == 5) ? 1 : ((cfg->ploid == 2 && cfg->mode == 4) ? 2 : 0);
+	g.REC = g.K + 3 + (g.fmode == 2 ? 2 * g.K : 0);
+	if (g.fmode) c->cfg.type_freq = 1;                                // log_ld_F_* have no -y 0 branch (mcmc.c:1776-1847)
+	c->ns = (cfg->mode == 3 || cfg->mode == 5) ? N : (cfg->mode == 1 ? 0 : g.K);       // mode 1 has no selfing rates
 	c->rounds = (cfg->rng_rounds == 10) ? 10 : 7;
 	c->key0 = (uint32_t)cfg->seed;
 	c->key1 = (uint32_t)(cfg->seed >> 32);
@@ -140,6 +144,7 @@ static void free_all(ig_ctx *c)
 	cudaFree(c->ind); cudaFree(c->Qf); cudaFree(c->gprop); cudaFree(c->gpair); cudaFree(c->S); cudaFree(c->state);
 	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->pnsh); cudaFree(c->nhet); cudaFree(c->nsh); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
 	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2);
+	cudaFree(c->fprop); cudaFree(c->hpair); cudaFree(c->ftab); cudaFree(c->pfk);
 	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
 	cudaFree(c->mom.self2); cudaFree(c->mom.gen); cudaFree(c->mom.gen2); cudaFree(c->mom.freq); cudaFree(c->mom.freq2);
 	cudaFree(c->mom.convg);
@@ -193,6 +198,12 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	CK(dalloc(&c->scratch, (size_t)64));
 	CK(dalloc(&c->gpart, (size_t)2 * SC_MAX_CTAS * 20));
 	CK(dalloc(&c->state2, (size_t)MAX_K));
+	if (g.fmode) {
+		CK(dalloc(&c->fprop, (size_t)(c->ns > g.K ? c->ns : g.K)));
+		CK(dalloc(&c->hpair, (size_t)g.Nloc));
+		CK(dalloc(&c->ftab, (size_t)MAX_K * 5));
+		if (g.fmode == 2) CK(dalloc(&c->pfk, (size_t)g.nchunks * g.Nloc * 2 * g.KP));
+	}
 	CK(dalloc(&c->mom.tot, 2));
 	CK(dalloc(&c->mom.indvlkh, (size_t)g.N));
 	CK(dalloc(&c->mom.qq, (size_t)g.N * g.K));
@@ -415,6 +426,9 @@ static ZQArgs zq_args(ig_ctx *c)
 	a.pcnt = c->pcnt; a.plog = c->plog; a.pnsh = c->pnsh; a.geo = c->geo; a.iter = c->iter; a.key0 = c->key0; a.key1 = c->key1;
 	a.type_freq = c->cfg.type_freq;
 	a.iter_dev = c->iter_dev;
+	a.fmode = c->geo.fmode;
+	a.hpair = (c->geo.fmode == 1) ? c->hpair : nullptr;
+	a.ftab = c->ftab; a.pfk = c->pfk;
 	a.k_mant = 0x007fffffu; a.k_one = 0x3f800000u;
 	return a;
 }
@@ -445,7 +459,7 @@ static ig_status phase_update_S(ig_ctx *c)
 	}
 	// UPMCMC.state is read by every CTA and written by one: double-buffered
 	PreArgs a{c->ind, c->S, c->state, c->state2, c->gprop, c->gpair, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1,
-	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl, c->iter_dev};
+	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl, c->iter_dev, c->fprop, c->hpair, c->ftab};
 	CK(launch_pre_sweep(a, c->stream));
 	if (c->cfg.mode == 2 && c->cfg.back_refl == 0) std::swap(c->state, c->state2);
 	c->launches++;
@@ -455,21 +469,24 @@ static ig_status phase_update_S(ig_ctx *c)
 static ig_status phase_zq(ig_ctx *c, int init)
 {
 	ZQArgs a = zq_args(c);
-	if (init) a.type_freq = 1;
+	if (init) { a.type_freq = 1; a.fmode = 0; a.hpair = nullptr; }     // uniform initial assignment: no likelihood is kept
 	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
 	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
 	CK(launch_zq_sweep(a, c->rounds, c->stream));
 	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
 	EpiArgs e{c->pcnt, c->plog, c->pnsh, c->nhet, c->nsh, c->ind, c->Qf, c->cnt, c->llparts, c->gpair, c->sc, c->geo,
-	          c->iter, c->key0, c->key1, init, a.type_freq, init ? nullptr : c->iter_dev};
+	          c->iter, c->key0, c->key1, init, a.type_freq, init ? nullptr : c->iter_dev, c->geo.fmode, c->S, c->fprop, c->pfk};
 	CK(launch_epilogue(e, c->stream));
 	c->launches += 2;
+	if (c->geo.fmode == 2 && !init) { CK(launch_fk_epilogue(e, c->stream)); c->launches++; }
 	return exchange_individuals(c);
 }
 
 static ig_status phase_alpha(ig_ctx *c)
 {
-	PostArgs a{c->ind, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1, c->iter_dev};
+	// mode 4: pre_sweep left the proposed adaptive-independence states in state2 (-e 0)
+	PostArgs a{c->ind, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1, c->iter_dev, c->cfg.mode, c->cfg.back_refl,
+	           c->S, c->fprop, c->state, c->state2};
 	CK(launch_post_sweep(a, c->stream));
 	c->launches++;
 	return IG_OK;
@@ -557,7 +574,7 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // the chain's RNG key is baked into the captured arguments
 	float init_h[MAX_K];
 	for (int k = 0; k < MAX_K; k++) init_h[k] = (initd && k < g.K) ? initd[k] : 0.5f;
-	if (c->cfg.mode == 2 && !initd) {
+	if ((c->cfg.mode == 2 || c->cfg.mode == 4) && !initd) {
 		// read_init without an -i file draws the starting rates from U(0,1) (initial.c:52-58)
 		Stream st(0u, 2u, 0u, TAG_INIT, c->key0, c->key1);
 		for (int k = 0; k < g.K; k++) init_h[k] = (float)st.uniform();
@@ -698,10 +715,10 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 			CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
 			CK(cudaStreamSynchronize(c->stream));
 			fprintf(stdout, "\nStep=%ld\tlog_likelihood=%f\n", step + 1, h.totallkh);
-			if (cf.mode == 2) {
+			if (cf.mode == 2 || cf.mode == 4) {                          // print_info, mcmc.c:1276-1297
 				double sh[MAX_K];
 				CK(cudaMemcpy(sh, c->S, g.K * sizeof(double), cudaMemcpyDeviceToHost));
-				for (int k = 0; k < g.K; k++) fprintf(stdout, "s_%d=%f%s", k, sh[k], k < g.K - 1 ? " " : "");
+				for (int k = 0; k < g.K; k++) fprintf(stdout, "%c_%d=%f%s", cf.mode == 2 ? 's' : 'f', k, sh[k], k < g.K - 1 ? " " : "");
 				fprintf(stdout, "\n");
 			}
 		}
@@ -860,6 +877,19 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 		if ((st = need(bytes, (size_t)g.Nloc * 32, "LLPARTS")) != IG_OK) return st;
 		CK(cudaMemcpy(host, c->llparts, bytes, cudaMemcpyDeviceToHost));
 		return IG_OK;
+	case 102:     /* debug: proposed inbreeding coefficients of the last sweep, double [K] (mode 4) or [N] (mode 5) */
+		if (!c->fprop) return fail(IG_ERR_ARG, "FPROP exists in modes 4 and 5 only");
+		if ((st = need(bytes, (size_t)c->ns * 8, "FPROP")) != IG_OK) return st;
+		CK(cudaMemcpy(host, c->fprop, bytes, cudaMemcpyDeviceToHost));
+		return IG_OK;
+	case 103: {   /* debug, mode 4: per-individual old-Z and new-Z differences per population, double [N][2][K] (nats) */
+		if (g.fmode != 2) return fail(IG_ERR_ARG, "FK exists in mode 4 only");
+		if ((st = need(bytes, (size_t)g.N * 2 * g.K * 8, "FK")) != IG_OK) return st;
+		std::vector<double> r((size_t)c->Npad * g.REC);
+		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		for (int i = 0; i < g.N; i++) for (int j = 0; j < 2 * g.K; j++) ((double *)host)[(size_t)i * 2 * g.K + j] = r[(size_t)i * g.REC + g.K + 3 + j];
+		return IG_OK;
+	}
 	case 101: {   /* debug: launch geometry int32[8] = TL, nchunks, nblk, subs_per_blk, R, smem, KP, A */
 		if ((st = need(bytes, 32, "GEOMETRY")) != IG_OK) return st;
 		int32_t *o = (int32_t *)host;
@@ -1014,7 +1044,8 @@ extern "C" ig_status ig_alpha_logratio(ig_ctx *c, double ralpha, double *out)
 	DevScalars keep;
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpy(&keep, c->sc, sizeof(keep), cudaMemcpyDeviceToHost));
-	PostArgs a{c->ind, c->sc, c->gpart, c->geo, 0xFFFFFFFFu, c->key0, c->key1};
+	PostArgs a{c->ind, c->sc, c->gpart, c->geo, 0xFFFFFFFFu, c->key0, c->key1, nullptr, c->cfg.mode, c->cfg.back_refl,
+	           c->S, c->fprop, c->state, c->state2};
 	CK(launch_post_sweep(a, c->stream));
 	DevScalars h;
 	CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

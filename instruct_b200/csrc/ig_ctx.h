@@ -60,6 +60,11 @@ struct ig_ctx {
 	double *scratch = nullptr;      // small device scratch (parity hooks)
 	double *gpart = nullptr;        // partials of the cooperative grid sums
 	int32_t *state2 = nullptr;      // double buffer of UPMCMC.state (-e 0)
+	// modes 4/5 (inbreeding coefficients; S holds UPMCMC.inbreed)
+	double *fprop = nullptr;        // proposed coefficients [K] / [N]
+	float2 *hpair = nullptr;        // mode 5: (1 - F, 1 - F') per local individual
+	float *ftab = nullptr;          // mode 4: the sweep kernel's per-population table
+	float *pfk = nullptr;           // mode 4: per-population partials of the sweep kernel
 	Moments mom{};
 	// host mirrors
 	std::vector<int32_t> allelenum_h;

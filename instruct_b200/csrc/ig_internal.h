@@ -43,12 +43,13 @@ struct Geometry {
 	int N, Nloc, i0;         // global individuals, local shard size and first global index
 	int L, Lpad, LT;         // loci, padded to TILE, micro-tiles
 	int K, KP, A;            // populations, padded populations, allelenum_max
-	int REC;                 // doubles per individual record: Q[K], lkh, slq, G
+	int REC;                 // doubles per individual record: Q[K], lkh, slq, G (mode 5: F); mode 4 appends D[K], E[K]
 	int TL;                  // loci per chunk (multiple of TILE)
 	int nchunks;             // ceil(Lpad / TL)
 	int nblk;                // individual blocks (grid.y)
 	int subs_per_blk;        // 256-individual passes per CTA
 	int R;                   // smem histogram replicas
+	int fmode;               // 0: selfing generations (modes 1-3), 1: inbreeding coefficient per individual (mode 5), 2: per population (mode 4)
 	size_t zq_smem;          // dynamic shared memory bytes of zq_sweep
 };
 
@@ -58,7 +59,7 @@ struct ZQArgs {
 	const float *P;          // [Lpad][A][KP]
 	int32_t *n;              // [Lpad][A][KP]
 	const float *Qf;         // [Nloc][KP]
-	const int2 *gpair;       // [Nloc] (g, g')
+ 	const int2 *gpair;       // [Nloc] (g, g')
 	uint16_t *pcnt;          // [nchunks][Nloc][KP]
 	double *plog;            // [nchunks][3][Nloc]  old-Z ratio piece, new-Z likelihood under g and under g'
 	uint16_t *pnsh;          // [nchunks][Nloc]     same-z heterozygotes on the new Z
@@ -66,6 +67,10 @@ struct ZQArgs {
 	uint32_t iter;
 	uint32_t key0, key1;
 	const uint32_t *iter_dev;   // non-null: read the sweep counter from device memory (CUDA-graph replay)
+	const float2 *hpair;        // mode 5: [Nloc] (1 - F, 1 - F') in place of the generation pair
+	const float *ftab;          // mode 4: {F, 1-F, F', 1-F'}[KP] then lg2(1-F') - lg2(1-F) [KP]
+	float *pfk;                 // mode 4: [nchunks][Nloc][2][KP] per-population old-Z / new-Z differences (log2 units)
+	int fmode;
 	int type_freq;
 	uint32_t k_mant, k_one;  // 0x007fffff, 0x3f800000 kept in registers on purpose (see uniform_big)
 };
@@ -89,8 +94,13 @@ struct EpiArgs {
 	int init;                // 1: initial assignment pass (no G accept, no likelihood)
 	int type_freq;
 	const uint32_t *iter_dev;
+	int fmode;               // Geometry.fmode
+	const double *S;         // mode 5: current F [N]
+	const double *fprop;     // mode 5: proposed F [N]
+	const float *pfk;        // mode 4: the sweep kernel's per-population partials
 };
 cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s);
+cudaError_t launch_fk_epilogue(const EpiArgs &a, cudaStream_t s);   // mode 4: per-population differences into the records
 
 struct PArgs {
 	int32_t *n; float *P; double *P64; const int32_t *allelenum;
@@ -105,12 +115,17 @@ struct PreArgs {
 	double *gpart;           // [2][SC_MAX_CTAS][20] partials of the grid-wide sums
 	Geometry geo; uint32_t iter, key0, key1; int mode, prior_flag, back_refl;
 	const uint32_t *iter_dev;
+	double *fprop;           // modes 4/5: proposed inbreeding coefficients [K] / [N]
+	float2 *hpair;           // mode 5: [Nloc] (1 - F, 1 - F')
+	float *ftab;             // mode 4: table for the sweep kernel (ZQArgs.ftab)
 };
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s);
 
 struct PostArgs {
-	const double *ind; DevScalars *sc; double *gpart; Geometry geo; uint32_t iter, key0, key1;
+	double *ind; DevScalars *sc; double *gpart; Geometry geo; uint32_t iter, key0, key1;
 	const uint32_t *iter_dev;
+	int mode, back_refl;
+	double *S; const double *fprop; int32_t *state; const int32_t *state_prop;   // modes 4/5
 };
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
 

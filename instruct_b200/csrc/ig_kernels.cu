@@ -187,6 +187,51 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	int phase = 0;
 
+	if (a.mode == 4) {
+		// update_inbreedcoff_POP (mcmc.c:986-1050), proposal half: the K Metropolis steps do not
+		// interact (a genotype's term depends on the F of one population only), so all K proposals
+		// are made here, evaluated by the one sweep pass and accepted in post_sweep.
+		if (blockIdx.x == 0 && tid < g.KP) {
+			const int j = tid;
+			double cur = 0.0, prop = 0.0;
+			int new_state = 1;
+			if (j < K) {
+				cur = a.S[j];
+				Stream st((uint32_t)j, 0u, iter, TAG_SPOP, a.key0, a.key1);
+				if (a.back_refl == 1) {                         // mcmc.c:1012-1018
+					prop = cur + (st.uniform() * 2.0 * 0.05 - 0.05);
+					if (prop <= 0.0) prop = -prop;
+					else if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
+				} else {                                        // adpt_indp, mcmc.c:1461-1520
+					const int cs = a.state_in[j];
+					const double u = st.uniform();
+					if (cs == 0) { if (u < 0.5) { prop = 0.0; new_state = 0; } else { prop = st.uniform(); new_state = 1; } }
+					else if (cs == 2) { if (u < 0.5) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
+					else { if (u <= 0.05) { prop = 0.0; new_state = 0; } else if (u >= 0.95) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
+					a.state_out[j] = new_state;
+				}
+				a.fprop[j] = prop;
+			}
+			const float omh = (float)(1.0 - cur), omhp = (float)(1.0 - prop);
+			a.ftab[4 * j] = 1.0f - omh; a.ftab[4 * j + 1] = omh; a.ftab[4 * j + 2] = 1.0f - omhp; a.ftab[4 * j + 3] = omhp;
+			a.ftab[4 * g.KP + j] = (float)(log2((double)omhp) - log2((double)omh));
+		}
+		return;
+	}
+	if (a.mode == 5) {
+		// update_F_IND (mcmc.c:888-910), proposal half; the accept is taken by indiv_epilogue
+		for (int i = i_first; i < g.N; i += gstride) {
+			const double f = a.S[i];
+			Stream st((uint32_t)i, 0u, iter, TAG_SIND, a.key0, a.key1);
+			double prop = f + (st.uniform() * 2.0 * 0.05 - 0.05);
+			if (prop <= 0.0) prop = -prop;
+			if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
+			a.fprop[i] = prop;
+			const int il = i - g.i0;
+			if (il >= 0 && il < g.Nloc) a.hpair[il] = make_float2((float)(1.0 - f), (float)(1.0 - prop));
+		}
+		return;
+	}
 	if (a.mode == 2) {
 		if (tid < K) Ssh[tid] = a.S[tid];
 		__syncthreads();
@@ -364,7 +409,23 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 	const double c_new = (double)a.nhet[il] * LN2_D;
 	const int ig_global = g.i0 + il;
 	double *rec = a.ind + (size_t)ig_global * g.REC;
-	if (!a.init) {
+	if (!a.init && a.fmode == 2) {
+		rec[K] = c_new + a_new;                                // at the current F; post_sweep adds the accepted differences
+		rec[K + 2] = 0.0;
+	} else if (!a.init && a.fmode == 1) {
+		// update_F_IND accept (mcmc.c:905-907) and cal_lkh at the accepted F (log_ld_F_indv, mcmc.c:1812)
+		const double f = a.S[ig_global], fp = a.fprop[ig_global];
+		const double lo = log((double)(float)(1.0 - f)), lp = log((double)(float)(1.0 - fp));   // the sweep kernel's fp32 1 - F
+		const int no = a.nsh[il];
+		if (no) d_old += (double)no * (lp - lo);
+		if (a.llparts) { double *lq = a.llparts + (size_t)il * 4; lq[0] = d_old; lq[1] = c_new; lq[2] = a_new; lq[3] = b_new; }
+		Stream sa((uint32_t)ig_global, 0u, iter, TAG_GACC, a.key0, a.key1);
+		const double u = sa.uniform();
+		const double ratio = exp(d_old);
+		const bool acc = (ratio != ratio) || (u < fmin(1.0, ratio));
+		rec[K + 2] = acc ? fp : f;
+		rec[K] = c_new + (acc ? b_new : a_new);
+	} else if (!a.init) {
 		const int2 gg = a.gpair[il];
 		// same-z heterozygotes carry 2^-(g-1) (genofreq, mcmc.c:1692-1699): on the OLD Z their
 		// count is what the previous pass left in nsh (type_freq 0: already inside d_old)
@@ -403,6 +464,29 @@ cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s)
 	return cudaGetLastError();
 }
 
+// mode 4: thread = (individual, j), j < 2 KP: sums the sweep kernel's per-population partials
+// over the chunks in chunk order (shard-invariant) into the record, D_k at [K+3+k] (old Z,
+// for the K accepts) and E_k at [2K+3+k] (new Z, for cal_lkh at the accepted F), in nats.
+__global__ void fk_epilogue_kernel(const EpiArgs a)
+{
+	const Geometry &g = a.geo;
+	const int KP2 = 2 * g.KP;
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long)g.Nloc * KP2) return;
+	const int il = (int)(t / KP2), j = (int)(t % KP2);
+	const int k = j % g.KP, which = j / g.KP;
+	if (k >= g.K) return;
+	double s = 0.0;
+	for (int c = 0; c < g.nchunks; c++) s += (double)a.pfk[((size_t)c * g.Nloc + il) * KP2 + j];
+	a.ind[(size_t)(g.i0 + il) * g.REC + g.K + 3 + which * g.K + k] = s * LN2_D;
+}
+cudaError_t launch_fk_epilogue(const EpiArgs &a, cudaStream_t s)
+{
+	const long n = (long)a.geo.Nloc * 2 * a.geo.KP;
+	fk_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
 // --------------------------------------------------------------------------------------
 // post_sweep (cooperative grid): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
 // (update_alpha, mcmc.c:1244-1263, in log form: (alpha'-alpha) * sum log q), and the
@@ -429,6 +513,54 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 	}
 	int phase = 0;
 	grid_sum(grid, v, K + 2, tot, a.gpart, phase, sh);
+	if (a.mode == 5)                                        // the accepted F of every individual, from the (all-gathered) records
+		for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) a.S[i] = a.ind[(size_t)i * REC + K + 2];
+	if (a.mode == 4 && iter != 0xFFFFFFFFu) {
+		// update_inbreedcoff_POP accepts (mcmc.c:1038-1047): D_k = sum over individuals of the old-Z
+		// differences; the reference multiplies that LOG ratio by the Hastings ratio under -e 0 and
+		// accepts when u < exp(min(1, .)) -- reproduced as written (NaN accepts: MIN2(1, NaN) == 1).
+		double Fc[MAX_K], Fp[MAX_K];
+		int cs[MAX_K], ns_[MAX_K];
+		for (int k = 0; k < K; k++) {
+			Fc[k] = a.S[k]; Fp[k] = a.fprop[k];
+			cs[k] = (a.back_refl == 0) ? a.state[k] : 1;
+			ns_[k] = (a.back_refl == 0) ? a.state_prop[k] : 1;
+		}
+		double dv[SC_MAXV], dt[SC_MAXV];
+#pragma unroll
+		for (int j = 0; j < SC_MAXV; j++) dv[j] = 0.0;
+		for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) {
+			const double *rec = a.ind + (size_t)i * REC + K + 3;
+#pragma unroll
+			for (int k = 0; k < MAX_K; k++) if (k < K) dv[k] += rec[k];
+		}
+		grid_sum(grid, dv, K, dt, a.gpart, phase, sh);
+		bool acc[MAX_K];
+		int naccept = 0;
+		for (int k = 0; k < K; k++) {
+			double mh = dt[k];
+			if (a.back_refl == 0) mh *= trans_prob(cs[k], ns_[k]) / trans_prob(ns_[k], cs[k]);
+			Stream st((uint32_t)k, 1u, iter, TAG_SPOP, a.key0, a.key1);
+			const double u = st.uniform();
+			acc[k] = (mh != mh) || (u < exp(fmin(1.0, mh)));
+			naccept += acc[k] ? 1 : 0;
+		}
+		// cal_lkh at the accepted coefficients (log_ld_F_pop, mcmc.c:1776): add the new-Z differences
+		double lv = 0.0, lt;
+		for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) {
+			double *rec = a.ind + (size_t)i * REC;
+			double l = rec[K];
+			for (int k = 0; k < K; k++) if (acc[k]) l += rec[2 * K + 3 + k];
+			rec[K] = l;
+			lv += l;
+		}
+		grid_sum(grid, &lv, 1, &lt, a.gpart, phase, sh);
+		tot[0] = lt;
+		if (blockIdx.x == 0 && tid == 0) {
+			for (int k = 0; k < K; k++) if (acc[k]) { a.S[k] = Fp[k]; if (a.back_refl == 0) a.state[k] = ns_[k]; }
+			a.sc->s_accepts += naccept;
+		}
+	}
 	if (blockIdx.x != 0 || tid != 0) return;
 	const double slq = tot[1];
 	a.sc->totallkh = tot[0];
@@ -737,14 +869,16 @@ __global__ void init_chain_kernel(double *ind, double *S, int32_t *state, DevSca
 		Stream st(0u, 1u, 0u, TAG_INIT, key0, key1);
 		sc->alpha = st.uniform() * 10.0;
 		sc->totallkh = 0.0; sc->sumlogq = 0.0; sc->alpha_accepts = 0; sc->s_accepts = 0; sc->flags = 0;
-		if (mode == 2)
+		if (mode == 2 || mode == 4)                          // mcmc.c:200-205, :256-260
 			for (int k = 0; k < g.K; k++) { S[k] = (double)initd[k]; if (back_refl == 0) state[k] = sel_state(S[k]); }
 	}
 	if (i >= g.N) return;
 	Stream st((uint32_t)i, 0u, 0u, TAG_INIT, key0, key1);
 	double *rec = ind + (size_t)i * g.REC;
 	int gen;
-	if (mode == 1) gen = 1;                         // admixture without selfing: G == 1 makes log_ld_indv the mode-1 likelihood (mcmc.c:1869)
+	double fi = 0.0;
+	if (mode == 1 || mode == 4) gen = 1;            // admixture without selfing: G == 1 makes log_ld_indv the mode-1 likelihood (mcmc.c:1869)
+	else if (mode == 5) { gen = 1; fi = st.uniform(); S[i] = fi; }    // mcmc.c:416-419
 	else if (mode == 2) {
 		const double p = st.uniform(), u = st.uniform();
 		const double v = floor(log(u) / log(1.0 - p)) + 1.0;
@@ -756,7 +890,8 @@ __global__ void init_chain_kernel(double *ind, double *S, int32_t *state, DevSca
 		gen = (v > 50.0) ? 50 : (v < 1.0 ? 1 : (int)v);
 	}
 	for (int k = 0; k < g.K; k++) rec[k] = 1.0 / g.K;
-	rec[g.K] = 0.0; rec[g.K + 1] = 0.0; rec[g.K + 2] = (double)gen;
+	rec[g.K] = 0.0; rec[g.K + 1] = 0.0; rec[g.K + 2] = (mode == 5) ? fi : (double)gen;
+	for (int j = g.K + 3; j < g.REC; j++) rec[j] = 0.0;
 	gprop[i] = gen;
 	const int il = i - g.i0;
 	if (il >= 0 && il < g.Nloc) gpair[il] = make_int2(gen, gen);

@@ -43,12 +43,30 @@ struct Thr {
 	float hist_bias;           // shared address of this lane's tally replica column minus R * psm, as a signed denormal
 	float cnt_t;               // shared address of this thread's ancestry-counter column, as a denormal
 	float omh_g, h_g, omh_p, h_p;
+	float ftabf;               // FM == 2: shared address of the per-population table {h, 1-h, h', 1-h'}[KP], as a denormal
+	float dltabf;              // FM == 2: shared address of lg2(1-h'_k) - lg2(1-h_k), as a denormal
+	float dcolf, ecolf;        // FM == 2: shared addresses of this thread's per-population accumulator columns
 };
+
+__device__ __forceinline__ void sm_fadd(uint32_t addr, float v)      // this thread's private column: plain read-modify-write
+{
+	float o;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(addr) : "memory");
+	o += v;
+	asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(o) : "memory");
+}
 
 // One genotype.  xw = packed allele pair (x0 | x1 << 16), zw = word holding the old pair
 // (z0 | z1 << 8) in its half H, r0/r1 = 32 random bits per copy, rowbf = shared address of
 // P[l][0][0] as a denormal.  Returns the new packed pair (z0 | z1 << 8).
-template <int KP, bool TF0, int LR, int H>
+//
+// FM = 2 (mode 4, mcmc_POP_inbreedcoff): the homozygosity excess h is the inbreeding coefficient
+// of the population a same-z genotype sits in (log_ld_F_pop, mcmc.c:1776; genofreq_inbreedcoff
+// :1707 is genofreq with h := F), so h comes from a table indexed by z, and the old-Z / new-Z
+// differences between the proposed and the current coefficients are kept per population
+// (all K Metropolis steps of update_inbreedcoff_POP, mcmc.c:986, ride this one pass: a
+// genotype's term depends on one F_k only).
+template <int KP, bool TF0, int LR, int H, int FM>
 __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, uint32_t r1, float rowbf, const float (&q)[KP],
                                              const Thr &t, Acc &acc, const RegConst &kc)
 {
@@ -71,11 +89,21 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 	// ---- old-Z piece of update_G's ratio (log_ld_indv, mcmc.c:1752-1759): only same-z
 	//      homozygotes depend on g.  (The 2^-(g-1) count of same-z heterozygotes on the old
 	//      Z is the previous pass's nsh_new; indiv_epilogue carries it over.)
-	if (!TF0) {
+	if (!TF0 && FM != 2) {
 		const uint32_t zo0 = __byte_perm(zw, 0u, H ? 0x4442 : 0x4440), zo1 = __byte_perm(zw, 0u, H ? 0x4443 : 0x4441);
 		const float fo = lds_f(__float_as_uint(fmaf(as_dn(zo0), 4.0f, row0f)));
 		const float fe = (zo0 == zo1 && !het) ? fo : 1.0f;                // h + 1 * (1 - h) == 1 exactly
 		acc.mD += lg2_fast(fmaf(fe, t.omh_p, t.h_p)) - lg2_fast(fmaf(fe, t.omh_g, t.h_g));
+	}
+	if (FM == 2) {
+		const uint32_t zo0 = __byte_perm(zw, 0u, H ? 0x4442 : 0x4440), zo1 = __byte_perm(zw, 0u, H ? 0x4443 : 0x4441);
+		if (zo0 == zo1) {
+			const float fo = lds_f(__float_as_uint(fmaf(as_dn(zo0), 4.0f, row0f)));
+			const float4 ft = lds_f4(__float_as_uint(fmaf(as_dn(zo0), 16.0f, t.ftabf)));
+			const float dl = lds_f(__float_as_uint(fmaf(as_dn(zo0), 4.0f, t.dltabf)));
+			const float term = het ? dl : lg2_fast(fmaf(fo, ft.w, ft.z)) - lg2_fast(fmaf(fo, ft.y, ft.x));
+			sm_fadd(__float_as_uint(fmaf(as_dn(zo0), (float)(4 * ZQ_THREADS), t.dcolf)), term);
+		}
 	}
 	// ---- categorical draws (disc_unif, random.c:403-430)
 	const float zf0 = pick_category<KP>(c0, uniform_big(r0, kc));
@@ -93,15 +121,28 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 	if (TF0) { f0 = c0[KP - 1]; f1 = c1[KP - 1]; same_n = true; }                                 // mcmc.c:1739-1749
 	else { f0 = lds_f(__float_as_uint(pa0f)); f1 = lds_f(__float_as_uint(pa1f)); same_n = (zf0 == zf1); }
 	const bool sh_n = same_n && !het;
-	acc.mA += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_g, t.h_g) : f1));
-	acc.mB += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_p, t.h_p) : f1));
-	acc.nsh_new += (same_n && het) ? 1 : 0;
+	if (FM == 2) {
+		float fac = f1;
+		if (same_n) {
+			const float4 fn = lds_f4(__float_as_uint(fmaf(zf0, as_dn(16u), t.ftabf)));
+			const float dl = lds_f(__float_as_uint(fmaf(zf0, as_dn(4u), t.dltabf)));
+			const float cur = fmaf(f0, fn.y, fn.x);
+			fac = het ? f1 * fn.y : cur;                                                      // 2 f0 f1 (1 - F) : f0 (F + f0 (1 - F))
+			const float term = het ? dl : lg2_fast(fmaf(f0, fn.w, fn.z)) - lg2_fast(cur);
+			sm_fadd(__float_as_uint(fmaf(zf0, as_dn(4u * ZQ_THREADS), t.ecolf)), term);
+		}
+		acc.mA += lg2_fast(f0 * fac);
+	} else {
+		acc.mA += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_g, t.h_g) : f1));
+		acc.mB += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_p, t.h_p) : f1));
+		acc.nsh_new += (same_n && het) ? 1 : 0;
+	}
 	return __float_as_uint(fmaf(zf1, as_dn(256u), zf0 * as_dn(1u)));                              // z0 | z1 << 8
 }
 
 // One micro-tile of 8 loci.  CHECK = false: no thread of the warp holds a missing genotype
 // here, so the per-genotype sign test and its divergence bookkeeping are compiled out.
-template <int KP, int ROUNDS, bool TF0, int LR, bool CHECK>
+template <int KP, int ROUNDS, bool TF0, int LR, bool CHECK, int FM>
 __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&zwo)[4], uint32_t (&zwn)[4], float rowb0f, float rowstridef,
                                            uint32_t mt_global, uint32_t ig_global, uint32_t iter, const ZQArgs &a, const float (&q)[KP], const Thr &t,
                                            Acc &acc, const RegConst &kc)
@@ -119,12 +160,12 @@ __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&
 				pair[h2] = h2 ? (zwo[pr] >> 16) : (zwo[pr] & 0xFFFFu);
 				// the tiler stores a genotype with ANY missing copy as (-9,-9): one sign test
 				if (xw[j] >= 0) {
-					if (h2) pair[h2] = genotype<KP, TF0, LR, 1>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
-					else pair[h2] = genotype<KP, TF0, LR, 0>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
+					if (h2) pair[h2] = genotype<KP, TF0, LR, 1, FM>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
+					else pair[h2] = genotype<KP, TF0, LR, 0, FM>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
 				}
 			} else {
-				if (h2) pair[h2] = genotype<KP, TF0, LR, 1>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
-				else pair[h2] = genotype<KP, TF0, LR, 0>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
+				if (h2) pair[h2] = genotype<KP, TF0, LR, 1, FM>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
+				else pair[h2] = genotype<KP, TF0, LR, 0, FM>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
 			}
 		}
 		zwn[pr] = __byte_perm(pair[0], pair[1], 0x5410);
@@ -142,7 +183,7 @@ __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&
 //             per-thread ancestry counters [KP][256] int32 (column tid: conflict-free RED)
 //   output  : per (chunk, individual) partials: K counts (u16) + 3 log-likelihood pieces
 // --------------------------------------------------------------------------------------
-template <int KP, int ROUNDS, bool TF0, int LR>
+template <int KP, int ROUNDS, bool TF0, int LR, int FM>
 __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const ZQArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -158,6 +199,9 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 	float *Psm = reinterpret_cast<float *>(smem_raw);
 	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);
 	int *cntsm = hist + (size_t)g.TL * rowsz * R;                   // [KP][ZQ_THREADS]
+	float *dsm = reinterpret_cast<float *>(cntsm + KP * ZQ_THREADS); // FM == 2: [KP][ZQ_THREADS] old-Z differences per population
+	float *esm = dsm + KP * ZQ_THREADS;                             //          [KP][ZQ_THREADS] new-Z differences
+	float *ftab = esm + KP * ZQ_THREADS;                            //          [KP][4] + [KP]
 	const int nbins = nl * rowsz;
 
 	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
@@ -169,6 +213,11 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 	for (int j = tid; j < nbins * R; j += ZQ_THREADS) hist[j] = 0;
 #pragma unroll
 	for (int k = 0; k < KP; k++) cntsm[k * ZQ_THREADS + tid] = 0;
+	if (FM == 2) {
+#pragma unroll
+		for (int k = 0; k < KP; k++) { dsm[k * ZQ_THREADS + tid] = 0.0f; esm[k * ZQ_THREADS + tid] = 0.0f; }
+		if (tid < KP * 5) ftab[tid] = a.ftab[tid];
+	}
 	__syncthreads();
 	mbar_wait(&bar, 0);
 
@@ -185,6 +234,13 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 	Thr t;
 	t.hist_bias = as_dn_signed((int)smem_addr(hist) + (tid & (R - 1)) * 4 - (int)(psm << LR));
 	t.cnt_t = as_dn(smem_addr(cntsm) + (uint32_t)tid * 4u);
+	t.ftabf = t.dltabf = t.dcolf = t.ecolf = 0.0f;
+	if (FM == 2) {
+		t.ftabf = as_dn(smem_addr(ftab));
+		t.dltabf = as_dn(smem_addr(ftab + KP * 4));
+		t.dcolf = as_dn(smem_addr(dsm) + (uint32_t)tid * 4u);
+		t.ecolf = as_dn(smem_addr(esm) + (uint32_t)tid * 4u);
+	}
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		// Warps vote inside the loop (__any_sync), so a warp stays together: a warp with no
@@ -207,7 +263,10 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 			// 1 - h(g) = 2^-(g-1); exact in fp32 down to 2^-126, 0 beyond (g can start huge in mode 3)
 			t.omh_g = (gg.x <= 127) ? __int_as_float((128 - gg.x) << 23) : 0.0f;
 			t.omh_p = (gg.y <= 127) ? __int_as_float((128 - gg.y) << 23) : 0.0f;
-			t.h_g = 1.0f - t.omh_g;
+			// mode 5 (mcmc_INDV_inbreedcoff): h is the individual's inbreeding coefficient, current and
+			// proposed (genofreq_inbreedcoff, mcmc.c:1707, is genofreq with h := F); hpair holds 1 - F
+			if (FM == 0 && a.hpair) { const float2 hp = __ldg(a.hpair + il); t.omh_g = hp.x; t.omh_p = hp.y; }
+			t.h_g = 1.0f - t.omh_g;                                         // omh + (1 - omh) == 1 exactly in fp32
 			t.h_p = 1.0f - t.omh_p;
 			Acc acc;
 			acc.lgA = acc.lgB = acc.lgD = 0.0f;
@@ -239,9 +298,9 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 				// sign of the AND of all eight words: set iff every genotype is usable
 				const int any_missing = (xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6] | xw[7]) < 0;
 				if (__any_sync(0xffffffffu, any_missing))
-					micro_tile<KP, ROUNDS, TF0, LR, true>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, iter, a, q, t, acc, kc);
+					micro_tile<KP, ROUNDS, TF0, LR, true, FM>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, iter, a, q, t, acc, kc);
 				else
-					micro_tile<KP, ROUNDS, TF0, LR, false>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, iter, a, q, t, acc, kc);
+					micro_tile<KP, ROUNDS, TF0, LR, false, FM>(xw, zwo, zwn, rowb0f, rowstridef, (uint32_t)(mt0 + mt), ig_global, iter, a, q, t, acc, kc);
 				if (live) stg_stream(zp + (size_t)mt * zstride, make_int4((int)zwn[0], (int)zwn[1], (int)zwn[2], (int)zwn[3]));
 				acc.lgA += acc.mA; acc.lgB += acc.mB; acc.lgD += acc.mD;
 			}
@@ -258,10 +317,25 @@ __global__ void __launch_bounds__(ZQ_THREADS, ZQ_MIN_CTAS) zq_sweep_kernel(const
 				}
 				double *pl = a.plog + (size_t)chunk * 3 * Nloc + il;
 				const double la = (double)acc.lgA * LN2_D, lb = (double)acc.lgB * LN2_D;
-				// TF0: the likelihood does not depend on Z, so the old-Z ratio is the new-Z one
-				pl[0] = TF0 ? (lb - la) - (double)acc.nsh_new * (double)(gg.y - gg.x) * LN2_D : (double)acc.lgD * LN2_D;
-				pl[(size_t)Nloc] = la - (double)acc.nsh_new * (double)(gg.x - 1) * LN2_D;
-				pl[(size_t)2 * Nloc] = lb - (double)acc.nsh_new * (double)(gg.y - 1) * LN2_D;
+				if (FM == 2) {
+					pl[0] = 0.0; pl[(size_t)Nloc] = la; pl[(size_t)2 * Nloc] = la;
+					float *pd = a.pfk + ((size_t)chunk * Nloc + il) * 2 * KP;
+#pragma unroll
+					for (int k = 0; k < KP; k++) {
+						pd[k] = dsm[k * ZQ_THREADS + tid]; pd[KP + k] = esm[k * ZQ_THREADS + tid];
+						dsm[k * ZQ_THREADS + tid] = 0.0f; esm[k * ZQ_THREADS + tid] = 0.0f;
+					}
+				} else if (a.hpair) {
+					// same-z heterozygotes carry (1 - F) (genofreq_inbreedcoff, mcmc.c:1719); 0 * log 0 is kept at 0
+					const double wg = acc.nsh_new ? (double)acc.nsh_new * log((double)t.omh_g) : 0.0;
+					const double wp = acc.nsh_new ? (double)acc.nsh_new * log((double)t.omh_p) : 0.0;
+					pl[0] = (double)acc.lgD * LN2_D; pl[(size_t)Nloc] = la + wg; pl[(size_t)2 * Nloc] = lb + wp;
+				} else {
+					// TF0: the likelihood does not depend on Z, so the old-Z ratio is the new-Z one
+					pl[0] = TF0 ? (lb - la) - (double)acc.nsh_new * (double)(gg.y - gg.x) * LN2_D : (double)acc.lgD * LN2_D;
+					pl[(size_t)Nloc] = la - (double)acc.nsh_new * (double)(gg.x - 1) * LN2_D;
+					pl[(size_t)2 * Nloc] = lb - (double)acc.nsh_new * (double)(gg.y - 1) * LN2_D;
+				}
 				a.pnsh[(size_t)chunk * Nloc + il] = (uint16_t)acc.nsh_new;
 			}
 		}
@@ -282,14 +356,15 @@ static cudaError_t launch_zq_kp(const ZQArgs &a, int rounds, cudaStream_t s)
 {
 	dim3 grid(a.geo.nchunks, a.geo.nblk), block(ZQ_THREADS);
 	const size_t sm = a.geo.zq_smem;
-#define IG_LAUNCH(RND, TF)                                                                                   \
+#define IG_LAUNCH(RND, TF, FM)                                                                               \
 	do {                                                                                                 \
-		cudaError_t e = cudaFuncSetAttribute(zq_sweep_kernel<KP, RND, TF, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+		cudaError_t e = cudaFuncSetAttribute(zq_sweep_kernel<KP, RND, TF, LR, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
 		if (e != cudaSuccess) return e;                                                                  \
-		zq_sweep_kernel<KP, RND, TF, LR><<<grid, block, sm, s>>>(a);                                      \
+		zq_sweep_kernel<KP, RND, TF, LR, FM><<<grid, block, sm, s>>>(a);                                  \
 	} while (0)
-	if (a.type_freq == 0) { if (rounds == 7) IG_LAUNCH(7, true); else IG_LAUNCH(10, true); }
-	else { if (rounds == 7) IG_LAUNCH(7, false); else IG_LAUNCH(10, false); }
+	if (a.fmode == 2) { if (rounds == 7) IG_LAUNCH(7, false, 2); else IG_LAUNCH(10, false, 2); }
+	else if (a.type_freq == 0) { if (rounds == 7) IG_LAUNCH(7, true, 0); else IG_LAUNCH(10, true, 0); }
+	else { if (rounds == 7) IG_LAUNCH(7, false, 0); else IG_LAUNCH(10, false, 0); }
 #undef IG_LAUNCH
 	return cudaGetLastError();
 }
@@ -319,7 +394,8 @@ cudaError_t zq_configure(Geometry &g, int device)
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
 	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 	const int target_ctas = 2 * ZQ_MIN_CTAS * sms;         // ZQ_MIN_CTAS resident CTAs per SM, two waves
-	const size_t cnt_bytes = (size_t)g.KP * ZQ_THREADS * sizeof(int);
+	// per-thread counter columns; mode 4 adds two float columns per population and the F table
+	const size_t cnt_bytes = (size_t)g.KP * ZQ_THREADS * sizeof(int) * (g.fmode == 2 ? 3 : 1) + (g.fmode == 2 ? (size_t)g.KP * 5 * 4 + 16 : 0);
 	const size_t budget = (size_t)min(smem_optin, 227 * 1024) / ZQ_MIN_CTAS - 2048 - cnt_bytes;
 	const size_t per_locus = (size_t)g.A * g.KP * 4;
 	const int nsub_total = (g.Nloc + ZQ_THREADS - 1) / ZQ_THREADS;
@@ -344,7 +420,7 @@ cudaError_t zq_configure(Geometry &g, int device)
 	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
 	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
 	g.R = R;
-	g.zq_smem = (size_t)tl * per_locus * (1 + R) + (size_t)g.KP * ZQ_THREADS * sizeof(int);
+	g.zq_smem = (size_t)tl * per_locus * (1 + R) + cnt_bytes;
 	return cudaSuccess;
 }
 

@@ -137,7 +137,32 @@ def tetra_fixtures(R=12):
                         alpha=np.array(alphas))
 
 
+def posterior_inbreeding_fixture(mode, R=10):
+    """Modes 4/5 (mcmc_POP_inbreedcoff mcmc.c:242, mcmc_INDV_inbreedcoff :386, uniform prior):
+    inbreeding coefficients per population / per individual on the config-1 shaped data set."""
+    K = 2
+    d = make_dataset(N=200, L=10, K=K, A=8, miss=0.0, seed=1001, pure=True)
+    F, Qm, LL = [], [], []
+    for rep in range(R):
+        r = Reference(d.x, d.allelenum, K, mode=mode)
+        r.setseeds(13 + 7 * rep, 4 + 3 * rep, 1972 + 11 * rep)
+        c = r.mcmc_updating(update=5000, burnin=2000, thinning=10, ckrep=5, nstep_check_empty=20,
+                            initd=[0.3 + 0.02 * rep, 0.6 - 0.02 * rep])
+        o = np.argsort(c["qq"][d.pop == 0].mean(axis=0))[::-1]          # cluster that holds population 0 first
+        F.append(c["self_rates"][o] if mode == 4 else c["self_rates"])
+        Qm.append(c["qq"][:, o]); LL.append(c["totallkh"])
+        print(f"mode-{mode} posterior rep", rep, c["totallkh"], F[-1][:4], flush=True)
+    np.savez_compressed(os.path.join(OUT, f"posterior_mode{mode}.npz"), x=d.x, allelenum=d.allelenum, K=K, F=np.array(F),
+                        Q=np.array(Qm).astype(np.float32), LL=np.array(LL), pop=d.pop, update=5000, burnin=2000, thinning=10)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "inbreeding":
+        chain_fixture(4, 0)
+        chain_fixture(5, 0)
+        posterior_inbreeding_fixture(4)
+        posterior_inbreeding_fixture(5)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mode1":
         posterior_mode1_fixture()
         sys.exit(0)
@@ -152,6 +177,10 @@ if __name__ == "__main__":
     chain_fixture(2, 0)
     chain_fixture(3, 0)
     chain_fixture(3, 1)
+    chain_fixture(4, 0)
+    chain_fixture(5, 0)
+    posterior_inbreeding_fixture(4)
+    posterior_inbreeding_fixture(5)
     posterior_fixture()
     posterior_mode1_fixture()
     tetra_fixtures()
