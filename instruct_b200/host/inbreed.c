@@ -251,7 +251,7 @@ static double run_for_K(const gs_store *gsp, int K, wr_run *runp, const wr_data 
 
 	popnum = K;
 	run.popnum = K;
-	ns = (mode == 3 && ploid == 2) ? N : K;
+	ns = ((mode == 3 || mode == 5) && ploid == 2) ? N : K;
 	init = read_init(initialfilename, chainnum, K);
 	nfreq = print_freq ? (size_t)K * gs.locinum * gs.allelenum_max : 0;
 	outs = (chain_out *)calloc((size_t)chainnum, sizeof(chain_out));
@@ -314,7 +314,7 @@ int main(int argc, char **argv)
 	if (ploid != 2 && ploid != 4) die("ploid must be 2 or 4");
 	if (ploid == 4 && autopoly != 1) die("-p 4 runs the autotetraploid model (-ap 1); the allotetraploid model is not built");
 	if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
-	N = gs.totalsize; K = popnum; ns = (mode == 3 && ploid == 2) ? N : K;
+	N = gs.totalsize; K = popnum; ns = ((mode == 3 || mode == 5) && ploid == 2) ? N : K;
 	/* mem_cal, InStruct.c:204-225 (the estimate is the reference's; kept for its two log lines) */
 	memreq = (print_freq ? 8.0 * K * gs.locinum * gs.allelenum_max : 0.0) + 8.0 + 8.0 * N + 8.0 * ns + 4.0 * N + 8.0 * N * K;
 	memreq *= (double)((updatenum - burnin) / thinning);

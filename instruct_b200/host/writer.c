@@ -121,6 +121,24 @@ int wr_chain(const char *path, const wr_run *r, const wr_data *d, const wr_chain
 			fprintf(f, "Cluster %d\t%.3f\t%.3f\n", j + 1, m, c->self_rates2[ord[j]] - m * m);
 		}
 	}
+	if (r->ploid == 2 && r->mode == 4) {                            /* print_F_POP_to_file :114-133 */
+		order_ascending(K, c->self_rates, ord);
+		fprintf(f, "\nThe Posterior distribution of Inbreeding Coefficients:\n");
+		fprintf(f, "\t\tMean\tVar\n");
+		for (j = 0; j < K; j++) {
+			double m = c->self_rates[ord[j]];
+			fprintf(f, "Cluster %d\t%.3f\t%.3f\n", j + 1, m, c->self_rates2[ord[j]] - m * m);
+		}
+	}
+	if (r->ploid == 2 && r->mode == 5) {                            /* print_F_INDV_to_file :135-148 */
+		fprintf(f, "\nThe Posterior distribution of Inbreeding Coefficients:\n");
+		fprintf(f, "\t\tMean\tVar\n");
+		for (j = 0; j < N; j++) {
+			fprintf(f, "Indv %d\t\t", j);
+			if (r->label == 1) fprintf(f, "%s\t", d->indvname[j]);
+			fprintf(f, "%.3f\t%.3f\n", c->self_rates[j], c->self_rates2[j] - c->self_rates[j] * c->self_rates[j]);
+		}
+	}
 	if (r->ploid == 2 && r->mode == 3) {                            /* print_S_INDV_to_file :97-111 */
 		fprintf(f, "\nThe Posterior distribution of Selfing Rates:\n");
 		if (r->label == 1) fprintf(f, "\t");
@@ -181,7 +199,7 @@ int wr_chain(const char *path, const wr_run *r, const wr_data *d, const wr_chain
 			fprintf(f, "%d:\t", i);
 			/* population-selfing modes list the clusters in the order of the selfing-rate table (:299) */
 			for (j = 0; j < K; j++) {
-				int col = ((r->ploid == 2 && r->mode == 2) || r->ploid == 4) ? ord[j] : j;
+				int col = ((r->ploid == 2 && (r->mode == 2 || r->mode == 4)) || r->ploid == 4) ? ord[j] : j;
 				fprintf(f, "%.3f ", acc[(size_t)i * K + col] / cnt[i]);
 			}
 			fprintf(f, "\t%d\n", cnt[i]);
@@ -211,7 +229,7 @@ int wr_chain(const char *path, const wr_run *r, const wr_data *d, const wr_chain
 				}
 				fprintf(f, "%s\t", d->alleletype[j][i]);
 				for (k = 0; k < K; k++) {
-					int kk = (r->mode == 2) ? ord[k] : k;
+					int kk = (r->mode == 2 || r->mode == 4) ? ord[k] : k;
 					double m = c->freq[((size_t)kk * L + j) * A + i];
 					fprintf(f, "\t%.3f\t%.3f\t", m, c->freq2[((size_t)kk * L + j) * A + i] - m * m);
 				}

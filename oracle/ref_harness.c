@@ -319,7 +319,7 @@ double refh_chain_stat(REFH *h, const char *outfile, int label, int popdata, int
 {
 	SEQDATA d = h->data;
 	CHAIN c;
-	int i, k, ns = (d.mode == 3) ? d.totalsize : d.popnum;
+	int i, k, ns = (d.mode == 3 || d.mode == 5) ? d.totalsize : d.popnum;
 	double dic;
 	d.label = label; d.popdata = popdata; d.distr_fmt = distr_fmt; d.print_freq = 0; d.pop_count = pop_count;
 	d.indvname = cmatrix(0, d.totalsize, 0, 99);      /* one spare row: print_S_INDV reads indvname[N] (App. B #2) */
@@ -344,6 +344,7 @@ double refh_chain_stat(REFH *h, const char *outfile, int label, int popdata, int
 	}
 	for (i = 0; i < ns; i++) { c.self_rates[i] = self[i]; c.self_rates2[i] = self2[i]; }
 	c.self_rates[ns] = 0; c.self_rates2[ns] = 0;
+	c.inbreed = c.self_rates; c.inbreed2 = c.self_rates2;      /* modes 4/5 print CHAIN.inbreed (result_analysis.c:114-148) */
 	dic = chain_stat((char *)outfile, c, d, 0);
 	return dic;
 }

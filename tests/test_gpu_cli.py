@@ -128,3 +128,53 @@ def test_cli_k_inference(tmp_path):
     assert abs(np.mean(dics["ref"][:2]) - np.mean(dics["gpu"][:2])) < 0.01 * abs(np.mean(dics["ref"][:2]))
     # two well-separated pure clusters: K = 1 must lose on both sides
     assert best["ref"] >= 2 and best["gpu"] >= 2, (best, dics)
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built")
+@pytest.mark.parametrize("mode", [4, 5])
+def test_cli_inbreeding_modes_match_reference_program(tmp_path, mode):
+    """`-v 4` / `-v 5`: inbreeding coefficients per population / per individual (uniform prior)."""
+    d = make_dataset(N=120, L=12, K=2, A=6, miss=0.03, seed=2025, pure=True)
+    data = str(tmp_path / "geno.txt")
+    write_reference_text(data, d.x, pop=d.pop)
+    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "2", "-u", "3000", "-b", "1000", "-t", "5", "-c", "2",
+             "-v", str(mode), "-f", "0", "-g", "1", "-r", "10", "-pi", "0", "-s", "13", "4", "1972"]
+    outs = {}
+    for name, exe, extra in (("ref", REFBIN, []), ("gpu", INBREED, ["--quiet-data"])):
+        out = str(tmp_path / f"{name}.out")
+        p = subprocess.run([exe, "-d", data, "-o", out] + flags + extra, capture_output=True, text=True, timeout=600,
+                           cwd=str(tmp_path))
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        assert "THE JOB IS SUCCESSFULLY FINISHED" in p.stdout
+        outs[name] = open(out, "rb").read()
+
+    def banner(t):
+        t = t[: t.index(b"Chain#1")]
+        t = re.sub(rb"Command line arguments:\n.*\n", b"", t)
+        return re.sub(rb"Output File:   .*\n", b"Output File:   X\n", t)
+    assert banner(outs["ref"]) == banner(outs["gpu"])
+
+    def skeleton(t):
+        return [re.sub(rb"-?\d+\.\d+", b"#", ln) for ln in t[t.index(b"Chain#1"):].split(b"\n")
+                if not ln.startswith(b"The Gelman-Rubin")]
+    sr, sg = skeleton(outs["ref"]), skeleton(outs["gpu"])
+    assert len(sr) == len(sg)
+    assert sum(a == b for a, b in zip(sr, sg)) > 0.97 * len(sr)
+    assert b"The Posterior distribution of Inbreeding Coefficients:" in outs["gpu"]
+
+    def coeff(t):
+        key = "Cluster " if mode == 4 else "Indv "
+        sec = t.decode(errors="ignore")
+        sec = sec[sec.index("Inbreeding Coefficients"):]
+        rows = [ln for ln in sec.split("\n") if ln.startswith(key)]
+        n = 2 if mode == 4 else d.N
+        return np.array([_floats(r)[0] for r in rows[:n]])
+
+    def loglik(t):
+        return np.array([_floats(ln)[0] for ln in t.decode(errors="ignore").split("\n") if "Posterior Mean" in ln])
+    a, b = coeff(outs["ref"]), coeff(outs["gpu"])
+    if mode == 4:
+        assert np.abs(a - b).max() < 0.08
+    else:
+        assert abs(a.mean() - b.mean()) < 0.05 and np.corrcoef(a, b)[0, 1] > 0.6
+    assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 15.0

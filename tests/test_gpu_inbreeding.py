@@ -169,18 +169,23 @@ def test_inbreeding_posterior_matches_reference_within_mcse(mode):
         M.append([ch.qq[pop == p][:, o[0]].mean() for p in range(K)])
         F.append(ch.self_rates[o] if mode == 4 else [ch.self_rates[pop == p].mean() for p in range(K)])
     LL, M, F = np.array(LL), np.array(M), np.array(F)
-    refQ, refF = g["Q"].astype(np.float64), g["F"]
+    refQ, refF, refLL = g["Q"].astype(np.float64), g["F"], g["LL"]
+    # store_chn's running mean m*((step + x/m)/(1+step)) (mcmc.c:1327) turns into inf once a mean of q
+    # underflows; such a reference chain (one of the ten mode-4 chains) is left out of the comparison
+    good = np.isfinite(refQ).all(axis=(1, 2))
+    assert good.sum() >= R - 2
+    refQ, refF, refLL = refQ[good], refF[good], refLL[good]
     if mode == 4:
         ro = np.argsort(refF, axis=1)
-        refQ = np.stack([refQ[r][:, ro[r]] for r in range(R)])
+        refQ = np.stack([refQ[r][:, ro[r]] for r in range(len(refQ))])
         refF = np.take_along_axis(refF, ro, axis=1)
     else:
         refF = np.stack([refF[:, pop == p].mean(axis=1) for p in range(K)], axis=1)
     refM = np.stack([refQ[:, pop == p, 0].mean(axis=1) for p in range(K)], axis=1)
-    zLL, zQ, zF = _z(LL[:, None], g["LL"][:, None]), _z(M, refM), _z(F, refF)
-    msg = f"zLL={zLL} zQ={zQ} zF={zF} LL={LL.mean()} ref={g['LL'].mean()} F={F.mean(0)} refF={refF.mean(0)} M={M.mean(0)} refM={refM.mean(0)}"
+    zLL, zQ, zF = _z(LL[:, None], refLL[:, None]), _z(M, refM), _z(F, refF)
+    msg = f"zLL={zLL} zQ={zQ} zF={zF} LL={LL.mean()} ref={refLL.mean()} F={F.mean(0)} refF={refF.mean(0)} M={M.mean(0)} refM={refM.mean(0)}"
     assert np.all(np.abs(zLL) < 3.5), msg
     assert np.all(np.abs(zQ) < 3.5), msg
     assert np.all(np.abs(zF) < 3.5), msg
     assert np.all(np.abs(F.mean(0) - refF.mean(0)) < 0.03), msg
-    assert abs(LL.mean() - g["LL"].mean()) < 10.0, msg
+    assert abs(LL.mean() - refLL.mean()) < 10.0, msg

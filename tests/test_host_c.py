@@ -112,12 +112,12 @@ def test_packer_matches_reference_reader(host, tmp_path, label, popdata, extra, 
     host.gs_free(C.byref(st))
 
 
-@pytest.mark.parametrize("mode,label,popdata,distr", [(2, 1, 1, 1), (2, 0, 0, 0), (3, 0, 1, 1)])
+@pytest.mark.parametrize("mode,label,popdata,distr", [(2, 1, 1, 1), (2, 0, 0, 0), (3, 0, 1, 1), (4, 1, 1, 1), (4, 0, 1, 0), (5, 1, 1, 1), (5, 0, 0, 1)])
 def test_result_file_bytes_match_reference_writer(host, tmp_path, mode, label, popdata, distr):
     K, N = 3, 17
     d = make_dataset(N=N, L=9, K=K, A=4, miss=0.1, seed=5)
     rng = np.random.default_rng(3)
-    ns = N if mode == 3 else K
+    ns = N if mode in (3, 5) else K
     tot, tot2 = -1234.5678, 1234.5678 ** 2 + 33.3
     indv = rng.normal(-70, 5, N)
     qq = rng.dirichlet(np.ones(K), N); qq2 = qq ** 2 + rng.uniform(0, 0.01, (N, K))
