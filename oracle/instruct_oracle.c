@@ -27,6 +27,7 @@ struct orc_model {
 	const int16_t *x;
 	const int32_t *allelenum;
 	int8_t *z;
+	int *zz;              /* mode 0: UPMCMC.zz, the cluster of each individual (mcmc.c:539) */
 	double *qq, *qqnum, *freq;
 	double alpha;
 	double *self_rates;
@@ -69,6 +70,7 @@ orc_model *orc_new(int N, int L, int K, int ploid, int mode, int prior_flag, int
 	m->Amax = 1;
 	for (l = 0; l < L; l++) if (allelenum[l] > m->Amax) m->Amax = allelenum[l];
 	m->z = (int8_t *)calloc((size_t)L * N * ploid, 1);
+	m->zz = (int *)calloc(N, sizeof(int));
 	m->qq = (double *)calloc((size_t)N * K, sizeof(double));
 	m->qqnum = (double *)calloc((size_t)N * K, sizeof(double));
 	m->freq = (double *)calloc((size_t)K * L * m->Amax, sizeof(double));
@@ -93,12 +95,13 @@ orc_model *orc_new(int N, int L, int K, int ploid, int mode, int prior_flag, int
 void orc_free(orc_model *m)
 {
 	if (!m) return;
-	free(m->z); free(m->qq); free(m->qqnum); free(m->freq); free(m->self_rates); free(m->state);
+	free(m->z); free(m->zz); free(m->qq); free(m->qqnum); free(m->freq); free(m->self_rates); free(m->state);
 	free(m->gen); free(m->indvlkh); free(m->dp_value); free(m->dp_num); free(m->dp_next);
 	free(m->dp_of); free(m->dp_sval); free(m->scratch); free(m);
 }
 
 int8_t *orc_z(orc_model *m) { return m->z; }
+int *orc_zz(orc_model *m) { return m->zz; }
 double *orc_qq(orc_model *m) { return m->qq; }
 double *orc_qqnum(orc_model *m) { return m->qqnum; }
 double *orc_freq(orc_model *m) { return m->freq; }
@@ -247,7 +250,7 @@ void orc_tally_range(const orc_model *m, int i0, int i1, int32_t *n)
 		for (i = i0; i < i1; i++)
 			if (usable(m, i, l))
 				for (c = 0; c < m->ploid; c++)
-					n[FO(m, m->z[XO(m, l, i, c)], l, m->x[XO(m, l, i, c)])]++;
+					n[FO(m, m->mode == 0 ? m->zz[i] : m->z[XO(m, l, i, c)], l, m->x[XO(m, l, i, c)])]++;   /* mcmc.c:825-831: mode 0 counts by zz */
 }
 void orc_tally(const orc_model *m, int32_t *n) { orc_tally_range(m, 0, m->N, n); }
 
@@ -621,13 +624,46 @@ double orc_log_ld_noselfing(const orc_model *m, int i)
 	return ll;
 }
 
-/* cal_lkh, mcmc.c:1916-1942 (modes 1, 2, 3) */
+/* log_ld_indv_K, mcmc.c:1893-1913: individual i wholly in cluster k */
+double orc_log_ld_indv_K(const orc_model *m, int i, int k)
+{
+	double ll = 0;
+	int l, c;
+	for (l = 0; l < m->L; l++) {
+		if (!usable(m, i, l)) continue;
+		for (c = 0; c < m->ploid; c++) ll += log(m->freq[FO(m, k, l, m->x[XO(m, l, i, c)])]);
+		if (m->x[XO(m, l, i, 0)] != m->x[XO(m, l, i, 1)]) ll += log(2);
+	}
+	return ll;
+}
+
+/* update_Z, mcmc.c:1094-1119 (mode 0): whole-individual assignment, weights relative to cluster 0 */
+void orc_update_Z(orc_model *m, int init_flag)
+{
+	double *tmp = m->scratch, temp = 0;
+	int i, k;
+	for (i = 0; i < m->N; i++) {
+		for (k = 0; k < m->K; k++) {
+			if (init_flag == 1) tmp[k] = (double)(k + 1) / m->K;
+			else {
+				tmp[k] = orc_log_ld_indv_K(m, i, k);
+				if (k == 0) temp = tmp[k];
+				tmp[k] = exp(tmp[k] - temp);
+				if (k >= 1) tmp[k] += tmp[k - 1];
+			}
+		}
+		m->zz[i] = draw_bracket(&m->rng, tmp, m->K);
+	}
+}
+
+/* cal_lkh, mcmc.c:1916-1942 */
 void orc_cal_lkh(orc_model *m)
 {
 	int i;
 	m->totallkh = 0;
 	for (i = 0; i < m->N; i++) {
-		if (m->mode == 4) m->indvlkh[i] = orc_log_ld_F(m, m->self_rates, 1, i);
+		if (m->mode == 0) m->indvlkh[i] = orc_log_ld_indv_K(m, i, m->zz[i]);
+		else if (m->mode == 4) m->indvlkh[i] = orc_log_ld_F(m, m->self_rates, 1, i);
 		else if (m->mode == 5) m->indvlkh[i] = orc_log_ld_F(m, m->self_rates + i, 0, i);
 		else m->indvlkh[i] = (m->mode == 1) ? orc_log_ld_noselfing(m, i) : orc_log_ld_indv(m, m->gen[i], i);
 		m->totallkh += m->indvlkh[i];
@@ -751,6 +787,11 @@ int orc_dp_nclusters(const orc_model *m) { return m->dp_cnt; }
 static void one_sweep(orc_model *m)
 {
 	orc_update_P(m);
+	if (m->mode == 0) {                               /* mcmc_POP_no_admixture, mcmc.c:111-113 */
+		orc_update_Z(m, 0);
+		orc_cal_lkh(m);
+		return;
+	}
 	if (m->mode == 1) {
 		orc_update_ZQ(m, 0);
 		orc_update_alpha(m);
@@ -804,7 +845,7 @@ static void chain_reset(const orc_model *m, orc_chain *c)
 	long j;
 	c->step = 0; c->totallkh = 1; c->totallkh2 = 1;
 	for (j = 0; j < m->N; j++) { c->indvlkh[j] = 1; c->gen[j] = 1; c->gen2[j] = 1; }
-	for (j = 0; j < (long)m->N * m->K; j++) { c->qq[j] = 1; c->qq2[j] = 1; }
+	for (j = 0; j < (long)m->N * m->K; j++) { c->qq[j] = (m->mode == 0) ? 0 : 1; c->qq2[j] = 1; }   /* CHAIN.z starts at 0, mcmc.c:671 */
 	for (j = 0; j < ns; j++) { c->self_rates[j] = 1; c->self_rates2[j] = 1; }
 }
 
@@ -824,6 +865,11 @@ void orc_store_chn(const orc_model *m, orc_chain *c)
 	c->totallkh = run_mean(c->totallkh, m->totallkh, c->step);
 	c->totallkh2 = run_mean(c->totallkh2, m->totallkh * m->totallkh, c->step);
 	for (j = 0; j < m->N; j++) c->indvlkh[j] = run_mean(c->indvlkh[j], m->indvlkh[j], c->step);
+	if (m->mode == 0) {                               /* :1356-1362: CHAIN.z[i][zz[i]] += 1, kept here in qq */
+		for (j = 0; j < m->N; j++) c->qq[j * m->K + m->zz[j]] += 1;
+		c->step++;
+		return;
+	}
 	for (j = 0; j < (long)m->N * m->K; j++) {
 		c->qq[j] = run_mean(c->qq[j], m->qq[j], c->step);
 		c->qq2[j] = run_mean(c->qq2[j], m->qq[j] * m->qq[j], c->step);
@@ -853,6 +899,20 @@ int orc_run_chain(orc_model *m, long update, long burnin, int thinning, int ckre
 	int i;
 	out->flag_empty_cluster = 0;
 	out->steps = (int)((update - burnin) / thinning);            /* mcmc.c:485 */
+	if (m->mode == 0) {
+		/* mcmc_POP_no_admixture, mcmc.c:90-131: no alpha, no empty-cluster check */
+		orc_update_Z(m, 1);
+		for (step = 0; step < update; step++) {
+			one_sweep(m);
+			if (step == burnin - 1) chain_reset(m, out);
+			if (step >= burnin && (step + 1 - burnin) % thinning == 0) {
+				orc_store_chn(m, out);
+				if (cnt_step < ckrep) out->convg[cnt_step] = m->totallkh;
+				cnt_step++;
+			}
+		}
+		return 0;
+	}
 	m->alpha = u01(&m->rng) * 10;                                /* mcmc.c:479 */
 	if (m->mode == 1) {
 		/* mcmc_POP_admixture, mcmc.c:135-180: nothing else to initialise */

@@ -32,6 +32,7 @@ void orc_free(orc_model *m);
 
 /* raw pointers into the model state, for ctypes/numpy views */
 int8_t *orc_z(orc_model *m);
+int *orc_zz(orc_model *m);                 /* mode 0: cluster of each individual */
 double *orc_qq(orc_model *m);
 double *orc_qqnum(orc_model *m);
 double *orc_freq(orc_model *m);
@@ -80,6 +81,8 @@ void orc_update_F_POP(orc_model *m);   /* update_inbreedcoff_POP, mcmc.c:986 (mo
 void orc_update_F_IND(orc_model *m);   /* update_F_IND, mcmc.c:888 (mode 5, uniform prior) */
 void orc_update_G(orc_model *m);
 void orc_update_ZQ(orc_model *m, int init_flag);
+void orc_update_Z(orc_model *m, int init_flag);      /* mode 0, mcmc.c:1094 */
+double orc_log_ld_indv_K(const orc_model *m, int i, int k);   /* mcmc.c:1893 */
 void orc_update_alpha(orc_model *m);
 void orc_cal_lkh(orc_model *m);
 void orc_init_DP(orc_model *m);

@@ -88,6 +88,11 @@ def oracle_lib():
         L.orc_alpha_ratio_product.argtypes = [C.c_void_p, C.c_double]
         L.orc_check_empty_cluster.argtypes = [C.c_void_p]
         L.orc_z_conditional.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]
+        L.orc_zz.restype = c_ip
+        L.orc_zz.argtypes = [C.c_void_p]
+        L.orc_update_Z.argtypes = [C.c_void_p, C.c_int]
+        L.orc_log_ld_indv_K.restype = C.c_double
+        L.orc_log_ld_indv_K.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_log_ld_F.restype = C.c_double
         L.orc_log_ld_F.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int]
         L.orc_log_ld_F_total.restype = C.c_double
@@ -132,6 +137,7 @@ class Oracle:
         ns = self.N if mode in (3, 5) else K
         as_arr = np.ctypeslib.as_array
         self.z = as_arr(C.cast(self.lib.orc_z(self.h), C.POINTER(C.c_int8)), (self.L, self.N, self.ploid))
+        self.zz = as_arr(self.lib.orc_zz(self.h), (self.N,))
         self.qq = as_arr(self.lib.orc_qq(self.h), (self.N, K))
         self.qqnum = as_arr(self.lib.orc_qqnum(self.h), (self.N, K))
         self.freq = as_arr(self.lib.orc_freq(self.h), (K, self.L, self.Amax))
@@ -213,6 +219,12 @@ class Oracle:
 
     def update_S_IND(self):
         self.lib.orc_update_S_IND(self.h)
+
+    def update_Z(self, init_flag=0):
+        self.lib.orc_update_Z(self.h, init_flag)
+
+    def log_ld_indv_K(self, i, k):
+        return self.lib.orc_log_ld_indv_K(self.h, int(i), int(k))
 
     def update_F_POP(self):
         self.lib.orc_update_F_POP(self.h)
@@ -309,6 +321,10 @@ def ref_lib():
         L.refh_ran1.restype = C.c_double
         L.refh_update_P.argtypes = [C.c_void_p, c_ip]
         L.refh_update_ZQ.argtypes = [C.c_void_p, C.c_int]
+        L.refh_zz.argtypes = [C.c_void_p, c_ip, C.c_int]
+        L.refh_update_Z.argtypes = [C.c_void_p, C.c_int]
+        L.refh_log_ld_indv_K.restype = C.c_double
+        L.refh_log_ld_indv_K.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.refh_log_ld_F.restype = C.c_double
         L.refh_log_ld_F.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int]
         L.refh_log_ld_F_total.restype = C.c_double
@@ -430,6 +446,18 @@ class Reference:
     def update_G(self): self.lib.refh_update_G(self.h)
     def update_S_POP(self): self.lib.refh_update_S_POP(self.h)
     def update_S_IND(self): self.lib.refh_update_S_IND(self.h)
+    def update_Z(self, init_flag=0): self.lib.refh_update_Z(self.h, init_flag)
+    def log_ld_indv_K(self, i, k): return self.lib.refh_log_ld_indv_K(self.h, int(i), int(k))
+
+    def set_zz(self, zz):
+        a = np.ascontiguousarray(zz, dtype=np.int32)
+        self.lib.refh_zz(self.h, _ip(a), 1)
+
+    def get_zz(self):
+        a = np.zeros(self.N, dtype=np.int32)
+        self.lib.refh_zz(self.h, _ip(a), 0)
+        return a
+
     def update_F_POP(self): self.lib.refh_update_F_POP(self.h)
     def update_F_IND(self): self.lib.refh_update_F_IND(self.h)
 

@@ -92,7 +92,8 @@ REFH *refh_new(int N, int L, int K, int ploid, int mode, int prior_flag, int bac
 	allocate_node(&h->ptr, *d);
 	h->qqnum = dmatrix(0, N - 1, 0, K - 1);
 	h->ptr->alpha = 1.0;
-	for (i = 0; i < N; i++) for (k = 0; k < K; k++) { h->qqnum[i][k] = 0; h->ptr->qq[i][k] = 1.0 / K; }
+	for (i = 0; i < N; i++) for (k = 0; k < K; k++) { h->qqnum[i][k] = 0; if (mode != 0) h->ptr->qq[i][k] = 1.0 / K; }
+	if (mode == 0) for (i = 0; i < N; i++) h->ptr->zz[i] = 0;
 	for (k = 0; k < K; k++) for (j = 0; j < L; j++) for (i = 0; i < amax; i++) h->ptr->freq[k][j][i] = 0.0;
 	return h;
 }
@@ -123,6 +124,12 @@ void refh_z(REFH *h, int *z /*[N][L][ploid]*/, int dir)
 		if (dir) h->ptr->z[i][j][k] = z[o]; else z[o] = h->ptr->z[i][j][k];
 	}
 }
+void refh_zz(REFH *h, int *zz /*[N]*/, int dir)
+{
+	int i; for (i = 0; i < h->data.totalsize; i++) { if (dir) h->ptr->zz[i] = zz[i]; else zz[i] = h->ptr->zz[i]; }
+}
+void refh_update_Z(REFH *h, int init_flag) { update_Z(&h->ptr, h->data, init_flag); }
+double refh_log_ld_indv_K(REFH *h, int i, int k) { return log_ld_indv_K(h->ptr, h->data, i, k); }
 void refh_qq(REFH *h, double *qq /*[N][K]*/, int dir)
 {
 	int i, k; SEQDATA *d = &h->data;
@@ -252,6 +259,7 @@ void refh_sweeps(REFH *h, int n)
 			if (h->data.prior_flag == 1) refh_update_DP(h);
 			if (h->data.prior_flag == 0) update_S_IND(h->data.totalsize, &h->ptr);
 		}
+		if (h->data.mode == 0) { update_Z(&h->ptr, h->data, 0); cal_lkh(&h->ptr, h->data); continue; }
 		if (h->data.mode == 4) update_inbreedcoff_POP(h->data, &h->ptr);
 		if (h->data.mode == 5) update_F_IND(h->data.totalsize, &h->ptr, h->data);
 		if (h->data.mode == 2 || h->data.mode == 3) update_G(h->data, &h->ptr);
@@ -279,13 +287,18 @@ int refh_mcmc_updating(REFH *h, long update, long burnin, int thinning, int ckre
 	cvg.n_chain = 1; cvg.ckrep = ckrep; cvg.convgfilename = NULL;
 	cvg.convg_ld = dvector(0, ckrep > 0 ? ckrep - 1 : 0);
 	c = mcmc_updating(*d, init, 0, &cvg);
-	flag = c.flag_empty_cluster;
+	flag = (d->mode == 0) ? 0 : c.flag_empty_cluster;     /* mcmc_POP_no_admixture never sets the flag */
 	if (flag == 1) return 1;
 	ns = (d->mode == 3 || d->mode == 5) ? d->totalsize : d->popnum;
 	if (out_tot) { out_tot[0] = c.totallkh; out_tot[1] = c.totallkh2; }
 	for (i = 0; i < d->totalsize; i++) {
 		if (out_indvlkh) out_indvlkh[i] = c.indvlkh[i];
 		for (k = 0; k < d->popnum; k++) {
+			if (d->mode == 0) {              /* CHAIN.z: retained samples of individual i in cluster k (mcmc.c:1356-1362) */
+				if (out_qq) out_qq[(long)i * d->popnum + k] = (double)c.z[i][k];
+				if (out_qq2) out_qq2[(long)i * d->popnum + k] = 1.0;
+				continue;
+			}
 			if (out_qq) out_qq[(long)i * d->popnum + k] = c.qq[i][k];
 			if (out_qq2) out_qq2[(long)i * d->popnum + k] = c.qq2[i][k];
 		}

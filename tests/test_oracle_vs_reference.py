@@ -139,6 +139,43 @@ def test_inbreeding_loglik(mode):
     assert np.array_equal(ind, o.indvlkh) and tot == o.totallkh
 
 
+def test_whole_chain_bit_exact_mode0():
+    """Mode 0 (mcmc_POP_no_admixture, mcmc.c:90-131): every individual wholly in one cluster;
+    CHAIN.z counts the retained samples per (individual, cluster)."""
+    K = 3
+    d = make_dataset(N=45, L=21, K=K, A=4, miss=0.04, seed=14, pure=True)
+    o = Oracle(d.x, d.allelenum, K, mode=0)
+    r = Reference(d.x, d.allelenum, K, mode=0)
+    o.setseeds(13, 4, 1972); r.setseeds(13, 4, 1972)
+    kw = dict(update=160, burnin=60, thinning=5, ckrep=8, nstep_check_empty=10)
+    co = o.run_chain(**kw)
+    cr = r.mcmc_updating(**kw)
+    for k in ["totallkh", "totallkh2", "indvlkh", "qq", "convg"]:
+        assert np.array_equal(np.asarray(co[k]), np.asarray(cr[k])), k
+    assert np.array_equal(co["qq"].sum(axis=1), np.full(45, 20.0))      # 20 retained samples per individual
+
+
+def test_mode0_updates_follow_reference_stream():
+    K = 4
+    d = make_dataset(N=30, L=17, K=K, A=3, miss=0.05, seed=22)
+    o, r = Oracle(d.x, d.allelenum, K, mode=0), Reference(d.x, d.allelenum, K, mode=0)
+    rng = np.random.default_rng(4)
+    o.zz[...] = rng.integers(0, K, size=o.N)
+    o.freq[...] = rng.dirichlet(np.ones(o.Amax), size=(K, o.L))
+    r.set_zz(o.zz); r.set_freq(o.freq)
+    assert np.array_equal(o.tally(), r.update_P(want_tally=True))     # mcmc.c:825-831: counts by zz
+    r.set_freq(o.freq)
+    for i in range(0, 30, 5):
+        for k in range(K):
+            assert o.log_ld_indv_K(i, k) == r.log_ld_indv_K(i, k)
+    o.setseeds(7, 8, 9); r.setseeds(7, 8, 9)
+    o.update_Z(0); r.update_Z(0)
+    assert np.array_equal(o.zz, r.get_zz())
+    o.cal_lkh(); r.cal_lkh()
+    ind, tot = r.get_lkh()
+    assert np.array_equal(ind, o.indvlkh) and tot == o.totallkh
+
+
 def test_single_updates_follow_reference_stream():
     """Each conditional update consumes the RNG like the reference (state compared after each)."""
     K = 3
