@@ -85,7 +85,7 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	if (!cfg || !out) return fail(IG_ERR_ARG, "null argument");
 	*out = nullptr;
 	if (cfg->ploid != 2 && cfg->ploid != 4) return fail(IG_ERR_UNSUPPORTED, "ploid %d: 2 (diploid) or 4 (autotetraploid)", cfg->ploid);
-	if (cfg->ploid == 2 && (cfg->mode < 1 || cfg->mode > 5)) return fail(IG_ERR_UNSUPPORTED, "mode %d: modes 1 to 5 are built", cfg->mode);
+	if (cfg->ploid == 2 && (cfg->mode < 0 || cfg->mode > 5)) return fail(IG_ERR_UNSUPPORTED, "mode %d: modes 0 to 5 exist", cfg->mode);
 	if (cfg->ploid == 2 && cfg->mode == 5 && cfg->prior_flag != 0)
 		return fail(IG_ERR_UNSUPPORTED, "mode 5 with the Dirichlet-process prior (-f 1) is not built; use the uniform prior (-f 0)");
 	if (cfg->popnum < 1 || cfg->popnum > MAX_K) return fail(IG_ERR_UNSUPPORTED, "popnum %d outside 1..%d", cfg->popnum, MAX_K);
@@ -125,7 +125,7 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	g.fmode = (cfg->ploid == 2 && cfg->mode == 5) ? 1 : ((cfg->ploid == 2 && cfg->mode == 4) ? 2 : 0);
 	g.REC = g.K + 3 + (g.fmode == 2 ? 2 * g.K : 0);
 	if (g.fmode) c->cfg.type_freq = 1;                                // log_ld_F_* have no -y 0 branch (mcmc.c:1776-1847)
-	c->ns = (cfg->mode == 3 || cfg->mode == 5) ? N : (cfg->mode == 1 ? 0 : g.K);       // mode 1 has no selfing rates
+	c->ns = (cfg->mode == 3 || cfg->mode == 5) ? N : (cfg->mode <= 1 ? 0 : g.K);       // modes 0 and 1 have no selfing rates
 	c->rounds = (cfg->rng_rounds == 10) ? 10 : 7;
 	c->key0 = (uint32_t)cfg->seed;
 	c->key1 = (uint32_t)(cfg->seed >> 32);
@@ -145,6 +145,7 @@ static void free_all(ig_ctx *c)
 	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->pnsh); cudaFree(c->nhet); cudaFree(c->nsh); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
 	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2);
 	cudaFree(c->fprop); cudaFree(c->hpair); cudaFree(c->ftab); cudaFree(c->pfk);
+	cudaFree(c->logP); cudaFree(c->na_pll);
 	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
 	cudaFree(c->mom.self2); cudaFree(c->mom.gen); cudaFree(c->mom.gen2); cudaFree(c->mom.freq); cudaFree(c->mom.freq2);
 	cudaFree(c->mom.convg);
@@ -198,6 +199,7 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	CK(dalloc(&c->scratch, (size_t)64));
 	CK(dalloc(&c->gpart, (size_t)2 * SC_MAX_CTAS * 20));
 	CK(dalloc(&c->state2, (size_t)MAX_K));
+	if (c->cfg.mode == 0) { ig_status st0 = na_alloc(c); if (st0 != IG_OK) return st0; }
 	if (g.fmode) {
 		CK(dalloc(&c->fprop, (size_t)(c->ns > g.K ? c->ns : g.K)));
 		CK(dalloc(&c->hpair, (size_t)g.Nloc));
@@ -449,7 +451,7 @@ static ig_status phase_update_S(ig_ctx *c)
 	// mode 1 (mcmc_POP_admixture, mcmc.c:135-180) has neither update_S nor update_G: the (1, 1)
 	// generation pairs written by init_chain stay, and with G == 1 the sweep's likelihood is
 	// log_ld_noselfing_indv (mcmc.c:1869)
-	if (c->cfg.mode == 1) return IG_OK;
+	if (c->cfg.mode <= 1) return IG_OK;
 	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1) {
 		c->ind_h.resize((size_t)c->Npad * g.REC);
 		CK(cudaMemcpyAsync(c->ind_h.data(), c->ind, c->ind_h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -468,6 +470,7 @@ static ig_status phase_update_S(ig_ctx *c)
 
 static ig_status phase_zq(ig_ctx *c, int init)
 {
+	if (c->cfg.mode == 0) return init ? na_chain_init(c) : na_phase_z(c);     // no admixture: whole-individual labels (noadmix.cu)
 	ZQArgs a = zq_args(c);
 	if (init) { a.type_freq = 1; a.fmode = 0; a.hpair = nullptr; }     // uniform initial assignment: no likelihood is kept
 	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
@@ -589,11 +592,13 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	// initial assignment (update_ZQ with init_flag = 1, mcmc.c:206,1143-1144): uniform Z is the
 	// categorical draw with all weights equal, so the sweep kernel runs once with P = 1, Q = 1/K
 	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
-	CK(launch_fill_f32(c->P, 1.0f, pn, c->stream));
-	CK(launch_fill_q_uniform(c->Qf, g, c->stream));
-	CK(cudaMemsetAsync(c->n, 0, pn * sizeof(int32_t), c->stream));
-	CK(cudaMemsetAsync(c->Zt, 0, (size_t)g.LT * g.Nloc * TILE * 2, c->stream));
-	c->launches += 3;
+	if (c->cfg.mode != 0) {
+		CK(launch_fill_f32(c->P, 1.0f, pn, c->stream));
+		CK(launch_fill_q_uniform(c->Qf, g, c->stream));
+		CK(cudaMemsetAsync(c->n, 0, pn * sizeof(int32_t), c->stream));
+		CK(cudaMemsetAsync(c->Zt, 0, (size_t)g.LT * g.Nloc * TILE * 2, c->stream));
+		c->launches += 3;
+	}
 	ig_status st = phase_zq(c, 1);
 	if (st != IG_OK) return st;
 	c->dev_iter_valid = false;
@@ -956,6 +961,13 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 			for (int i = 0; i < g.N; i++) r[(size_t)i * g.REC + g.K] = ((const double *)host)[i];
 		}
 		CK(cudaMemcpy(c->ind, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+		if (id == IG_STATE_G && c->cfg.mode == 0 && c->cfg.ploid == 2) {       // mode 0: G carries the cluster labels zz; n mirrors them
+			std::vector<double> r2(r);
+			for (int i = 0; i < g.N; i++) for (int k = 0; k < g.K; k++) r2[(size_t)i * g.REC + k] = (k == ((const int32_t *)host)[i]) ? 1.0 : 0.0;
+			CK(cudaMemcpy(c->ind, r2.data(), r2.size() * 8, cudaMemcpyHostToDevice));
+			if ((st = na_retally(c)) != IG_OK) return st;
+			CK(cudaStreamSynchronize(c->stream));
+		}
 		return IG_OK;
 	}
 	case IG_STATE_P: {

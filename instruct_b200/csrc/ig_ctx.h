@@ -65,6 +65,9 @@ struct ig_ctx {
 	float2 *hpair = nullptr;        // mode 5: (1 - F, 1 - F') per local individual
 	float *ftab = nullptr;          // mode 4: the sweep kernel's per-population table
 	float *pfk = nullptr;           // mode 4: per-population partials of the sweep kernel
+	// mode 0 (no admixture, noadmix.cu)
+	float *logP = nullptr;          // log2 P, [Lpad][A][KP]
+	double *na_pll = nullptr;       // [nchunks][KP][Nloc] per-chunk log-likelihoods of each individual in each cluster
 	Moments mom{};
 	// host mirrors
 	std::vector<int32_t> allelenum_h;
@@ -105,6 +108,12 @@ static cudaError_t dalloc(T **p, size_t n)
 ig_status ig_exchange_tally(ig_ctx *c);
 ig_status ig_exchange_individuals(ig_ctx *c);
 ig_status ig_allgather_double(ig_ctx *c, double *buf, size_t per_rank);
+
+// no-admixture driver (noadmix.cu)
+ig_status na_alloc(ig_ctx *c);
+ig_status na_chain_init(ig_ctx *c);
+ig_status na_phase_z(ig_ctx *c);
+ig_status na_retally(ig_ctx *c);
 
 // autotetraploid driver (tetra.cu)
 ig_status tetra_create(ig_ctx *c);

@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 	for (int k = 0; k < K; k++) a.sc->qcol[k] = tot[2 + k];
 	if (iter == 0xFFFFFFFFu) return;                        // statistics only (parity hook)
 	a.sc->iter = iter + 1;                                  // the next sweep's counter, for graph replay
+	if (a.mode == 0) return;                                // no admixture: there is no alpha (mcmc.c:90-131)
 	Stream st(0u, 0u, iter, TAG_ALPHA, a.key0, a.key1);
 	const double alpha = a.sc->alpha;
 	const double ralpha = alpha + draw_normal(st);
@@ -877,7 +878,7 @@ __global__ void init_chain_kernel(double *ind, double *S, int32_t *state, DevSca
 	double *rec = ind + (size_t)i * g.REC;
 	int gen;
 	double fi = 0.0;
-	if (mode == 1 || mode == 4) gen = 1;            // admixture without selfing: G == 1 makes log_ld_indv the mode-1 likelihood (mcmc.c:1869)
+	if (mode == 0 || mode == 1 || mode == 4) gen = 1;            // admixture without selfing: G == 1 makes log_ld_indv the mode-1 likelihood (mcmc.c:1869)
 	else if (mode == 5) { gen = 1; fi = st.uniform(); S[i] = fi; }    // mcmc.c:416-419
 	else if (mode == 2) {
 		const double p = st.uniform(), u = st.uniform();

@@ -155,7 +155,7 @@ def mcmc_updating(data: SeqData, initial: Init, chn: int, cvg: Convg | None, see
     cfg = _config(data, initial.update, initial.burnin, initial.thinning, ckrep, seed, device)
     x = np.ascontiguousarray(data.seqdata, dtype=np.int16)
     an = np.ascontiguousarray(data.allelenum, dtype=np.int32)
-    ns = data.totalsize if (data.mode in (3, 5) and data.ploid == 2) else (0 if (data.mode == 1 and data.ploid == 2) else data.popnum)
+    ns = data.totalsize if (data.mode in (3, 5) and data.ploid == 2) else (0 if (data.mode <= 1 and data.ploid == 2) else data.popnum)
     res = _Result(data.totalsize, data.popnum, ns, data.locinum, data.allelenum_max, data.print_freq)
     initd = None
     if initial.initd is not None:
@@ -186,7 +186,7 @@ class Sampler:
         cap = -(-self.N // shard_count)
         self.i0 = shard_rank * cap
         self.Nloc = min(cap, self.N - self.i0)
-        self.ns = self.N if (data.mode in (3, 5) and data.ploid == 2) else (0 if (data.mode == 1 and data.ploid == 2) else self.K)
+        self.ns = self.N if (data.mode in (3, 5) and data.ploid == 2) else (0 if (data.mode <= 1 and data.ploid == 2) else self.K)
         self.ploid = data.ploid
         if x_device_ptr is not None:
             check(self.lib.ig_load_genotypes_device(self.h, x_device_ptr, allelenum_device_ptr))

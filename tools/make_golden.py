@@ -137,6 +137,23 @@ def tetra_fixtures(R=12):
                         alpha=np.array(alphas))
 
 
+def posterior_mode0_fixture(R=10):
+    """Mode 0 (mcmc_POP_no_admixture, mcmc.c:90): whole-individual assignment; CHAIN.z / steps."""
+    K = 2
+    d = make_dataset(N=200, L=10, K=K, A=8, miss=0.0, seed=1001, pure=True)
+    Zm, LL = [], []
+    for rep in range(R):
+        r = Reference(d.x, d.allelenum, K, mode=0)
+        r.setseeds(13 + 7 * rep, 4 + 3 * rep, 1972 + 11 * rep)
+        c = r.mcmc_updating(update=3000, burnin=1000, thinning=10, ckrep=5, nstep_check_empty=20)
+        z = c["qq"] / c["qq"].sum(axis=1, keepdims=True)
+        o = np.argsort(z[d.pop == 0].mean(axis=0))[::-1]
+        Zm.append(z[:, o]); LL.append(c["totallkh"])
+        print("mode-0 posterior rep", rep, c["totallkh"], z[d.pop == 0].mean(axis=0)[o], flush=True)
+    np.savez_compressed(os.path.join(OUT, "posterior_mode0.npz"), x=d.x, allelenum=d.allelenum, K=K, Z=np.array(Zm).astype(np.float32),
+                        LL=np.array(LL), pop=d.pop, update=3000, burnin=1000, thinning=10)
+
+
 def posterior_inbreeding_fixture(mode, R=10):
     """Modes 4/5 (mcmc_POP_inbreedcoff mcmc.c:242, mcmc_INDV_inbreedcoff :386, uniform prior):
     inbreeding coefficients per population / per individual on the config-1 shaped data set."""
@@ -157,6 +174,10 @@ def posterior_inbreeding_fixture(mode, R=10):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mode0":
+        chain_fixture(0, 0)
+        posterior_mode0_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "inbreeding":
         chain_fixture(4, 0)
         chain_fixture(5, 0)
@@ -177,6 +198,8 @@ if __name__ == "__main__":
     chain_fixture(2, 0)
     chain_fixture(3, 0)
     chain_fixture(3, 1)
+    chain_fixture(0, 0)
+    posterior_mode0_fixture()
     chain_fixture(4, 0)
     chain_fixture(5, 0)
     posterior_inbreeding_fixture(4)
