@@ -159,6 +159,25 @@ int wr_chain(const char *path, const wr_run *r, const wr_data *d, const wr_chain
 		}
 	}
 
+	/* ---- print_Z_to_file :153-192 (mode 0): c->qq holds CHAIN.z / steps, the share of the retained
+	 *      samples in which the individual sat in each cluster */
+	if (r->ploid == 2 && r->mode == 0) {
+		fprintf(f, "\nInferred Classification of individuals:\n");
+		fprintf(f, "\nIndv\t");
+		if (r->label == 1) fprintf(f, "Label\t");
+		fprintf(f, "(Miss)\t");
+		if (r->popdata == 1) fprintf(f, "Pop : ");
+		for (j = 0; j < K; j++) fprintf(f, "Prob in Cluster %d\t", j + 1);
+		fprintf(f, "\n");
+		for (j = 0; j < N; j++) {
+			fprintf(f, "%d\t", j + 1);
+			if (r->label == 1) fprintf(f, "%s\t", d->indvname[j]);
+			fprintf(f, "(%d)\t", d->missvec[j]);
+			if (r->popdata == 1) fprintf(f, "%d : ", d->popindx[j]);
+			for (i = 0; i < K; i++) fprintf(f, "\t%f", c->qq[(size_t)j * K + i]);
+			fprintf(f, "\n");
+		}
+	} else
 	/* ---- print_Q_to_file :194-311 */
 	{
 		int pc = (r->popdata == 0) ? 1 : d->pop_count;

@@ -357,6 +357,10 @@ double refh_chain_stat(REFH *h, const char *outfile, int label, int popdata, int
 	}
 	for (i = 0; i < ns; i++) { c.self_rates[i] = self[i]; c.self_rates2[i] = self2[i]; }
 	c.self_rates[ns] = 0; c.self_rates2[ns] = 0;
+	if (d.mode == 0) {                                          /* mode 0 prints CHAIN.z / steps (result_analysis.c:153-192) */
+		c.z = lmatrix(0, d.totalsize - 1, 0, d.popnum - 1);
+		for (i = 0; i < d.totalsize; i++) for (k = 0; k < d.popnum; k++) c.z[i][k] = (long)(qq[(long)i * d.popnum + k] * c.steps + 0.5);
+	}
 	c.inbreed = c.self_rates; c.inbreed2 = c.self_rates2;      /* modes 4/5 print CHAIN.inbreed (result_analysis.c:114-148) */
 	dic = chain_stat((char *)outfile, c, d, 0);
 	return dic;

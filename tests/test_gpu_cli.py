@@ -178,3 +178,50 @@ def test_cli_inbreeding_modes_match_reference_program(tmp_path, mode):
     else:
         assert abs(a.mean() - b.mean()) < 0.05 and np.corrcoef(a, b)[0, 1] > 0.6
     assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 15.0
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built")
+def test_cli_no_admixture_matches_reference_program(tmp_path):
+    """`-v 0`: the no-admixture model; the result file lists the classification probabilities."""
+    d = make_dataset(N=120, L=12, K=2, A=6, miss=0.03, seed=2026, pure=True)
+    data = str(tmp_path / "geno.txt")
+    write_reference_text(data, d.x, pop=d.pop)
+    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "2", "-u", "1500", "-b", "500", "-t", "5", "-c", "2",
+             "-v", "0", "-g", "1", "-r", "10", "-pi", "0", "-s", "13", "4", "1972"]
+    outs = {}
+    for name, exe, extra in (("ref", REFBIN, []), ("gpu", INBREED, ["--quiet-data"])):
+        out = str(tmp_path / f"{name}.out")
+        p = subprocess.run([exe, "-d", data, "-o", out] + flags + extra, capture_output=True, text=True, timeout=600,
+                           cwd=str(tmp_path))
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        assert "THE JOB IS SUCCESSFULLY FINISHED" in p.stdout
+        outs[name] = open(out, "rb").read()
+
+    def banner(t):
+        t = t[: t.index(b"Chain#1")]
+        t = re.sub(rb"Command line arguments:\n.*\n", b"", t)
+        return re.sub(rb"Output File:   .*\n", b"Output File:   X\n", t)
+    assert banner(outs["ref"]) == banner(outs["gpu"])
+
+    def skeleton(t):
+        return [re.sub(rb"-?\d+\.\d+", b"#", ln) for ln in t[t.index(b"Chain#1"):].split(b"\n")
+                if not ln.startswith(b"The Gelman-Rubin")]
+    sr, sg = skeleton(outs["ref"]), skeleton(outs["gpu"])
+    assert len(sr) == len(sg)
+    assert sum(a == b for a, b in zip(sr, sg)) > 0.97 * len(sr)
+    assert b"Inferred Classification of individuals:" in outs["gpu"]
+
+    def probs(t):
+        sec = t.decode(errors="ignore")
+        sec = sec[sec.index("Inferred Classification"):]
+        rows = [ln for ln in sec.split("\n") if re.match(r"^\d+\t", ln)][: d.N]
+        return np.array([_floats(r)[-2:] for r in rows])
+
+    def loglik(t):
+        return np.array([_floats(ln)[0] for ln in t.decode(errors="ignore").split("\n") if "Posterior Mean" in ln])
+    a, b = probs(outs["ref"]), probs(outs["gpu"])
+    assert a.shape == b.shape == (d.N, 2)
+    # cluster labels may be swapped between the programs: compare the partition
+    agree = max(np.mean((a[:, 0] > 0.5) == (b[:, 0] > 0.5)), np.mean((a[:, 0] > 0.5) == (b[:, 1] > 0.5)))
+    assert agree > 0.95
+    assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 15.0

@@ -112,7 +112,8 @@ def test_packer_matches_reference_reader(host, tmp_path, label, popdata, extra, 
     host.gs_free(C.byref(st))
 
 
-@pytest.mark.parametrize("mode,label,popdata,distr", [(2, 1, 1, 1), (2, 0, 0, 0), (3, 0, 1, 1), (4, 1, 1, 1), (4, 0, 1, 0), (5, 1, 1, 1), (5, 0, 0, 1)])
+@pytest.mark.parametrize("mode,label,popdata,distr", [(2, 1, 1, 1), (2, 0, 0, 0), (3, 0, 1, 1), (4, 1, 1, 1), (4, 0, 1, 0), (5, 1, 1, 1), (5, 0, 0, 1),
+                                                       (0, 1, 1, 1), (0, 0, 0, 1)])
 def test_result_file_bytes_match_reference_writer(host, tmp_path, mode, label, popdata, distr):
     K, N = 3, 17
     d = make_dataset(N=N, L=9, K=K, A=4, miss=0.1, seed=5)
@@ -121,6 +122,8 @@ def test_result_file_bytes_match_reference_writer(host, tmp_path, mode, label, p
     tot, tot2 = -1234.5678, 1234.5678 ** 2 + 33.3
     indv = rng.normal(-70, 5, N)
     qq = rng.dirichlet(np.ones(K), N); qq2 = qq ** 2 + rng.uniform(0, 0.01, (N, K))
+    if mode == 0:                                   # CHAIN.z / steps: shares of 10 retained samples
+        qq = rng.multinomial(10, np.ones(K) / K, N) / 10.0
     s = rng.uniform(0.05, 0.95, ns); s2 = s ** 2 + rng.uniform(0, 0.01, ns)
     g = rng.uniform(1, 6, N); g2 = g ** 2 + rng.uniform(0, 1, N)
     pops = (np.arange(N) % 2).astype(np.int32)
