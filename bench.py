@@ -273,12 +273,12 @@ def run_ours(args):
     inline_profile = L * N >= 50_000_000 or world > 1
     if inline_profile:
         s.profile(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                            # before the barrier: starting the sampler must not delay rank 0 into the timed region
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     n0, _, k0 = s.profile_read()
     ms = s.time_sweeps(args.steps)               # CUDA events on the library's stream, sync both sides
     torch.cuda.synchronize()

@@ -159,6 +159,10 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
 	for (auto e : c->ev) cudaEventDestroy(e);
 	if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+	if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+	if (c->ev_zq) cudaEventDestroy(c->ev_zq);
+	if (c->ev_p) cudaEventDestroy(c->ev_p);
+	cudaFree(c->Pnext);
 	tetra_destroy(c);
 	free_all(c);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -285,6 +289,12 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 	ncclUniqueId id;
 	memcpy(&id, id128, 128);
 	NCK(g_nccl.CommInitRank(&c->comm, c->cfg.shard_count, id, c->cfg.shard_rank));
+	if (!c->tetra && c->cfg.mode != 0 && !c->cfg.print_freq && c->loaded && !c->stream2) {
+		CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&c->ev_zq, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&c->ev_p, cudaEventDisableTiming));
+		CK(dalloc(&c->Pnext, (size_t)c->geo.Lpad * c->geo.A * c->geo.KP));
+	}
 	return IG_OK;
 }
 
@@ -437,6 +447,12 @@ static ZQArgs zq_args(ig_ctx *c)
 
 static ig_status phase_update_P(ig_ctx *c)
 {
+	if (c->early_p) {                       // drawn behind the previous sweep's kernel on the side stream
+		CK(cudaStreamWaitEvent(c->stream, c->ev_p, 0));
+		std::swap(c->P, c->Pnext);
+		c->early_p = false;
+		return IG_OK;
+	}
 	ig_status st = exchange_tally(c);
 	if (st != IG_OK) return st;
 	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, c->iter_dev, 0};
@@ -477,6 +493,20 @@ static ig_status phase_zq(ig_ctx *c, int init)
 	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
 	CK(launch_zq_sweep(a, c->rounds, c->stream));
 	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
+	if (!init && c->comm && c->stream2 && c->more_follow) {
+		// Sharded chain: n is complete once this kernel ends, and nothing else of this sweep reads it.
+		// Its all-reduce and the P draw of the NEXT sweep (same Philox keys, iter + 1: identical on every
+		// rank) go to the side stream, overlapping the epilogue, the all-gather and the scalar updates.
+		const Geometry &g = c->geo;
+		CK(cudaEventRecord(c->ev_zq, c->stream));
+		CK(cudaStreamWaitEvent(c->stream2, c->ev_zq, 0));
+		NCK(g_nccl.AllReduce(c->n, c->n, (size_t)g.Lpad * g.A * g.KP, ncclInt32, ncclSum, c->comm, c->stream2));
+		PArgs pa{c->n, c->Pnext, c->P64, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0};
+		CK(launch_p_dirichlet(pa, c->stream2));
+		CK(cudaEventRecord(c->ev_p, c->stream2));
+		c->launches++;
+		c->early_p = true;
+	}
 	EpiArgs e{c->pcnt, c->plog, c->pnsh, c->nhet, c->nsh, c->ind, c->Qf, c->cnt, c->llparts, c->gpair, c->sc, c->geo,
 	          c->iter, c->key0, c->key1, init, a.type_freq, init ? nullptr : c->iter_dev, c->geo.fmode, c->S, c->fprop, c->pfk};
 	CK(launch_epilogue(e, c->stream));
@@ -574,6 +604,8 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	c->key0 = (uint32_t)c->cfg.seed ^ (0x9E3779B9u * (uint32_t)(chain_id + 1));
 	c->key1 = (uint32_t)(c->cfg.seed >> 32) ^ (0x85EBCA6Bu * (uint32_t)(chain_id + 1));
 	c->iter = 0;
+	if (c->stream2) CK(cudaStreamSynchronize(c->stream2));
+	c->early_p = false;
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // the chain's RNG key is baked into the captured arguments
 	float init_h[MAX_K];
 	for (int k = 0; k < MAX_K; k++) init_h[k] = (initd && k < g.K) ? initd[k] : 0.5f;
@@ -612,7 +644,9 @@ extern "C" ig_status ig_sweep(ig_ctx *c, int32_t nsweeps)
 	if (!c->chain_ready) return fail(IG_ERR_STATE, "call ig_chain_init first");
 	CK(cudaSetDevice(c->cfg.device));
 	for (int s = 0; s < nsweeps; s++) {
+		c->more_follow = s + 1 < nsweeps;
 		ig_status st = one_sweep(c);
+		c->more_follow = false;
 		if (st != IG_OK) return st;
 	}
 	return IG_OK;
@@ -629,7 +663,8 @@ extern "C" ig_status ig_time_sweeps(ig_ctx *c, int32_t nsweeps, double *elapsed_
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaEventRecord(e0, c->stream));
 	ig_status st = IG_OK;
-	for (int s = 0; s < nsweeps && st == IG_OK; s++) st = one_sweep(c);
+	for (int s = 0; s < nsweeps && st == IG_OK; s++) { c->more_follow = s + 1 < nsweeps; st = one_sweep(c); }
+	c->more_follow = false;
 	cudaEventRecord(e1, c->stream);
 	cudaError_t e = cudaEventSynchronize(e1);
 	float ms = 0.f;
@@ -714,7 +749,10 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 	MomArgs m{c->ind, c->S, c->sc, c->P, c->mom, g, c->ns, 0, -1, cf.print_freq};
 	const long print_every = cf.update >= 100 ? cf.update / 100 : 1;   // print_info, mcmc.c:1273 (guards the /0 of App. B #7)
 	for (long step = 0; step < cf.update; step++) {
-		if ((st = one_sweep(c)) != IG_OK) return st;
+		c->more_follow = step + 1 < cf.update;
+		st = one_sweep(c);
+		c->more_follow = false;
+		if (st != IG_OK) return st;
 		if (cf.print_iter == 1 && step % print_every == 0) {
 			DevScalars h;
 			CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -733,6 +771,7 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 		}
 		if (step >= cf.burnin && (step + 1 - cf.burnin) % cf.thinning == 0) {    // mcmc.c:220-226
 			m.step = cnt_step;
+			m.P = c->P;
 			m.convg_slot = (cnt_step < cf.ckrep) ? (int)cnt_step : -1;
 			CK(launch_moments(m, c->stream));
 			c->launches++;

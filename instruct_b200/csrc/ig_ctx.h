@@ -78,6 +78,13 @@ struct ig_ctx {
 	int dp_head = -1, dp_free = -1, dp_cnt = 0;
 	// NCCL
 	ncclComm_t comm = nullptr;
+	// sharded chains: the tally all-reduce and the NEXT sweep's P draw run on a side stream behind
+	// the sweep kernel, off the critical path (ig_api.cu early_update_P)
+	cudaStream_t stream2 = nullptr;
+	cudaEvent_t ev_zq = nullptr, ev_p = nullptr;
+	float *Pnext = nullptr;
+	bool early_p = false;            // Pnext holds the P of sweep iter + 1 and n has been consumed
+	bool more_follow = false;        // another sweep follows inside the current API call
 	// profiling
 	bool profile = false;
 	std::vector<cudaEvent_t> ev;
