@@ -348,7 +348,7 @@ def run_ours(args):
                          "traffic": None, "kernel": "tetra_zs + tetra_geno (the two passes of one sweep)" if tetra else "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
                          "algorithmic_bytes_per_launch": algo_bytes_launch, "peak_source": peak_src,
                          "share_of_step": zq_ms / ms_direct if ms_direct > 0 else None,
-                         "graph_replay": not inline_profile, "ms_per_step_direct_launch": ms_direct / args.steps},
+                         "graph_replay": (not inline_profile) and world == 1 and not tetra and args.workload != "c3", "ms_per_step_direct_launch": ms_direct / args.steps},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None,
             "e2e": e2e, "gpu_launches": int(k1 - k0), "clocks": clk,
         }

@@ -15,7 +15,15 @@
 #include <utility>
 #include <vector>
 
+#include <time.h>
 #include "ig_ctx.h"
+
+static double wall_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 #include "philox.cuh"
 #include "samplers.cuh"
 
@@ -243,11 +251,19 @@ extern "C" ig_status ig_load_genotypes(ig_ctx *c, const int16_t *x_host, const i
 	CK(cudaMemcpyAsync(c->allelenum, allelenum_host, (size_t)g.L * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
 	int16_t *tmp = nullptr;
 	const size_t bytes = (size_t)g.L * g.Nloc * c->cfg.ploid * sizeof(int16_t);
+	const bool trace = getenv("IG_TRACE") != nullptr;
+	const double t0 = wall_ms();
 	CK(cudaMalloc((void **)&tmp, bytes));
+	const double t1 = wall_ms();
 	cudaError_t e = cudaMemcpyAsync(tmp, x_host, bytes, cudaMemcpyHostToDevice, c->stream);
 	if (e != cudaSuccess) { cudaFree(tmp); CK(e); }
+	if (trace) cudaStreamSynchronize(c->stream);
+	const double t2 = wall_ms();
 	ig_status st = c->tetra ? tetra_load(c, tmp) : finish_load(c, tmp);
+	const double t3 = wall_ms();
 	cudaFree(tmp);
+	if (trace) fprintf(stderr, "[ig_trace] load: malloc %.1f ms, H2D %.1f (%.1f GB/s), allocate+tile %.1f, free %.1f\n", t1 - t0, t2 - t1,
+	                   bytes / (t2 - t1) * 1e-6, t3 - t2, wall_ms() - t3);
 	return st;
 }
 
@@ -350,6 +366,14 @@ static int dp_create(ig_ctx *c, double v)
 	const int s = c->dp_free;
 	c->dp_free = c->dp[s].next;
 	c->dp[s].value = v; c->dp[s].num = 1;
+	{	// dgeom(v, g) = v^(g-1) (1-v) for g = 1..50 (mcmc.c:1602), once per cluster instead of a pow() per
+		// (individual, cluster) in the Gibbs scan
+		if (c->dp_w.size() < c->dp.size() * 51) c->dp_w.resize(c->dp.size() * 51);
+		double *w = &c->dp_w[(size_t)s * 51];
+		double pw = 1.0 - v;
+		w[0] = 0.0;
+		for (int gg = 1; gg <= 50; gg++) { w[gg] = pw; pw *= v; }
+	}
 	if (c->dp_head < 0 || v <= c->dp[c->dp_head].value) { c->dp[s].next = c->dp_head; c->dp_head = s; return s; }
 	int q = c->dp_head, p = c->dp[q].next;
 	while (p >= 0 && c->dp[p].value <= v) { q = p; p = c->dp[p].next; }
@@ -411,10 +435,9 @@ static void dp_update(ig_ctx *c, const std::vector<double> &ind_h)   // update_D
 		dp_leave(c, j);
 		cum[0] = c->cfg.alpha_dpm / (gen + 1) / gen;                  // gen_post_prob, DPMM.c:369
 		int n = 1;
-		for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++) {
-			const double v = c->dp[p].value;
-			cum[n] = cum[n - 1] + c->dp[p].num * (pow(v, (double)(gen - 1)) * (1.0 - v));   // dgeom, mcmc.c:1602
-		}
+		const int gi = gen < 1 ? 1 : (gen > 50 ? 50 : gen);
+		for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++)
+			cum[n] = cum[n - 1] + c->dp[p].num * c->dp_w[(size_t)p * 51 + gi];             // num * dgeom(value, G_j), DPMM.c:373
 		const int pick = pick_weighted(cum, n, st.uniform());
 		if (pick == 0) {                                              // sample_poster, DPMM.c:395: Beta(G, 2)
 			c->S_h[j] = draw_beta(st, (double)gen, 2.0);
@@ -797,11 +820,17 @@ extern "C" ig_status ig_mcmc_updating(const ig_config *cfg, const int16_t *x_hos
                                       int32_t chain_id, const float *initd, ig_chain_result *out, double *convg_ld)
 {
 	ig_ctx *c = nullptr;
+	const bool trace = getenv("IG_TRACE") != nullptr;       // wall-clock stages of the drop-in call on stderr
+	const double t0 = wall_ms();
 	ig_status st = ig_create(cfg, &c);
 	if (st != IG_OK) return st;
+	const double t1 = wall_ms();
 	st = ig_load_genotypes(c, x_host, allelenum_host);
+	const double t2 = wall_ms();
 	if (st == IG_OK) st = ig_run_chain(c, chain_id, initd, out, convg_ld);
+	const double t3 = wall_ms();
 	ig_destroy(c);
+	if (trace) fprintf(stderr, "[ig_trace] create %.1f ms, load %.1f, run_chain %.1f, destroy %.1f\n", t1 - t0, t2 - t1, t3 - t2, wall_ms() - t3);
 	return st;
 }
 

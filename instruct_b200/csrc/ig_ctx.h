@@ -74,6 +74,7 @@ struct ig_ctx {
 	std::vector<double> ind_h, S_h;
 	// DP prior (host)
 	std::vector<DpCluster> dp;
+	std::vector<double> dp_w;     // [slot][51] dgeom(value, g), g = 1..50
 	std::vector<int> dp_of;
 	int dp_head = -1, dp_free = -1, dp_cnt = 0;
 	// NCCL

@@ -718,13 +718,48 @@ __global__ void __launch_bounds__(RED1) tetra_lkh_kernel(const double *ind, DevS
 }
 
 // stand-alone tally over (z, geno), for state injection and the start of a chain
-__global__ void tetra_tally_kernel(const int8_t *Zq, const int8_t *Gq, int32_t *n, Geometry g, int LTq)
+// One CTA per micro-tile of TT loci: a shared histogram [TT][A][KP] with one replica per lane
+// (the threads of a warp share their loci, so un-replicated atomics would all collide), flushed
+// to n with one atomicAdd per non-empty bin.
+constexpr int TALLY_REP = 16;
+__global__ void __launch_bounds__(256) tetra_tally_kernel(const int8_t *Zq, const int8_t *Gq, int32_t *n, Geometry g, int LTq)
 {
-	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= (size_t)LTq * g.Nloc * TT) return;
-	const int j = (int)(t % TT), mt = (int)(t / ((size_t)TT * g.Nloc)), l = mt * TT + j;
-	if (Gq[t * 4] < 0) return;
-	for (int c = 0; c < 4; c++) atomicAdd(&n[((size_t)l * g.A + Gq[t * 4 + c]) * g.KP + Zq[t * 4 + c]], 1);
+	extern __shared__ int th[];                                    // [TT * A * KP][TALLY_REP]
+	const int mt = blockIdx.x, tid = threadIdx.x;
+	const int nb = TT * g.A * g.KP;
+	for (int b = tid; b < nb * TALLY_REP; b += blockDim.x) th[b] = 0;
+	__syncthreads();
+	const int rep = tid & (TALLY_REP - 1);
+	const int4 *zp = reinterpret_cast<const int4 *>(Zq) + (size_t)mt * g.Nloc;
+	const int4 *gp = reinterpret_cast<const int4 *>(Gq) + (size_t)mt * g.Nloc;
+	for (int il = tid; il < g.Nloc; il += blockDim.x) {
+		const int4 zv = zp[il], gv = gp[il];
+		const uint32_t zw[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
+		const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
+#pragma unroll
+		for (int j = 0; j < TT; j++) {
+			if ((int8_t)(gw[j] & 0xFF) < 0) continue;              // missing genotype
+#pragma unroll
+			for (int cpy = 0; cpy < 4; cpy++) {
+				const int a = (gw[j] >> (8 * cpy)) & 0xFF, z = (zw[j] >> (8 * cpy)) & 0xFF;
+				atomicAdd(&th[((j * g.A + a) * g.KP + z) * TALLY_REP + rep], 1);
+			}
+		}
+	}
+	__syncthreads();
+	for (int b = tid; b < nb; b += blockDim.x) {
+		int sacc = 0;
+		for (int r = 0; r < TALLY_REP; r++) sacc += th[b * TALLY_REP + r];
+		if (sacc) atomicAdd(&n[(size_t)mt * TT * g.A * g.KP + b], sacc);
+	}
+}
+static cudaError_t launch_tetra_tally(const int8_t *Zq, const int8_t *Gq, int32_t *n, const Geometry &g, int LTq, cudaStream_t s)
+{
+	const size_t sm = (size_t)TT * g.A * g.KP * TALLY_REP * sizeof(int);
+	cudaError_t e = cudaFuncSetAttribute(tetra_tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+	if (e != cudaSuccess) return e;
+	tetra_tally_kernel<<<LTq, 256, sm, s>>>(Zq, Gq, n, g, LTq);
+	return cudaGetLastError();
 }
 
 // geno = -1 wherever the genotype is missing (the sweep kernels read the mask from there)
@@ -1032,7 +1067,7 @@ ig_status tetra_chain_init(ig_ctx *c, int32_t chain_id, const float *initd)
 	if ((st = tetra_pass_b(c, 1)) != IG_OK) return st;          // initial_geno, poly_geno.c:316 (uniform resolution)
 	if ((st = tetra_pass_a(c, 1)) != IG_OK) return st;          // update_ZQ(init_flag = 1): uniform z, :87
 	if ((st = tetra_q(c)) != IG_OK) return st;
-	tetra_tally_kernel<<<nb((size_t)t->LTq * g.Nloc * TT, 256), 256, 0, c->stream>>>(t->Zq, t->Gq, c->n, g, t->LTq);
+	CK(launch_tetra_tally(t->Zq, t->Gq, c->n, g, t->LTq, c->stream));
 	CK(cudaGetLastError());
 	c->launches++;
 	c->chain_ready = true;
@@ -1136,7 +1171,7 @@ ig_status tetra_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes,
 		}
 		// n always mirrors (z, geno)
 		if (e == cudaSuccess) e = cudaMemsetAsync(c->n, 0, (size_t)g.Lpad * g.A * g.KP * 4, c->stream);
-		if (e == cudaSuccess) { tetra_tally_kernel<<<nb((size_t)t->LTq * g.Nloc * TT, 256), 256, 0, c->stream>>>(t->Zq, t->Gq, c->n, g, t->LTq); e = cudaGetLastError(); }
+		if (e == cudaSuccess) e = launch_tetra_tally(t->Zq, t->Gq, c->n, g, t->LTq, c->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		cudaFree(tmp);
 		CK(e);
