@@ -375,7 +375,7 @@ struct ZsArgs {
 	uint32_t iter, key0, key1, k_mant, k_one;
 };
 
-template <int KP>
+template <int KP, int ROUNDS>
 __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -418,9 +418,11 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 		const uint32_t ig_global = (uint32_t)(g.i0 + il);
 		int4 *zp = reinterpret_cast<int4 *>(a.Zq) + ((size_t)mt0 * Nloc + il);
 		const int4 *gp = reinterpret_cast<const int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
+		// software prefetch, one micro-tile ahead (as in zq_sweep): four warps per scheduler do not cover HBM latency
+		int4 gv_n = ldg_stream(gp), zv_n = ldg_rw(zp);
 		for (int mt = 0; mt < nmt; ++mt) {
-			const int4 gv = ldg_stream(gp + (size_t)mt * Nloc);
-			const int4 zv = ldg_rw(zp + (size_t)mt * Nloc);
+			const int4 gv = gv_n, zv = zv_n;
+			if (mt + 1 < nmt) { gv_n = ldg_stream(gp + (size_t)(mt + 1) * Nloc); zv_n = ldg_rw(zp + (size_t)(mt + 1) * Nloc); }
 			const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
 			const uint32_t zo[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
 			uint32_t zn[4];
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 					}
 				}
 				// ---- new z: one categorical draw per copy, weights Q_ik P_k,l,geno_c (poly_geno.c:766-779)
-				const u32x4 rnd = philox4x32<10>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z | (uint32_t)j}, a.key0, a.key1);
+				const u32x4 rnd = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z | (uint32_t)j}, a.key0, a.key1);
 				const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 				const float rowbf = as_dn(psm + (uint32_t)(lj * rowsz) * 4u);
 				uint32_t packed = 0;
@@ -551,7 +553,7 @@ __device__ __forceinline__ float ex2_fast(float x)            // MUFU.EX2
 // The reference evaluates the resolution weights and the likelihood in double (libm log / exp); here
 // they are fp32 with MUFU.LG2 / MUFU.EX2: the weights carry ~1e-6 relative error (the z draw's fp32
 // weights carry as much), the likelihood sums stay inside the 1e-6 gate (tests/test_gpu_tetra.py).
-template <int KP>
+template <int KP, int ROUNDS>
 __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const GenoArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -595,9 +597,16 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 		const int4 *zp = reinterpret_cast<const int4 *>(a.Zq) + ((size_t)mt0 * Nloc + il);
 		int4 *gp = reinterpret_cast<int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
 		float ll_nat = 0.0f, ll_lg2 = 0.0f;      // natural-log part (tables, multiplicities) and log2 part (allele frequencies)
+		int4 xa_n = ldg_stream(xp), xb_n = ldg_stream(xp + 1), zv_n = ldg_stream(zp);      // prefetch one micro-tile ahead
 		for (int mt = 0; mt < nmt; ++mt) {
-			const int4 xa = ldg_stream(xp + (size_t)mt * Nloc * 2), xb = ldg_stream(xp + (size_t)mt * Nloc * 2 + 1);
-			const int4 zv = ldg_stream(zp + (size_t)mt * Nloc);
+			const int4 xa = xa_n, xb = xb_n, zv = zv_n;
+			if (mt + 1 < nmt) {
+				xa_n = ldg_stream(xp + (size_t)(mt + 1) * Nloc * 2); xb_n = ldg_stream(xp + (size_t)(mt + 1) * Nloc * 2 + 1);
+				zv_n = ldg_stream(zp + (size_t)(mt + 1) * Nloc);
+			}
+			// one Philox block per (micro-tile, individual): word j resolves the dosage of locus j
+			const u32x4 rnd4 = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_GENO}, a.key0, a.key1);
+			const uint32_t rj[4] = {rnd4.x, rnd4.y, rnd4.z, rnd4.w};
 			const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 			const uint32_t zw[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
 			uint32_t gn[4];
@@ -640,8 +649,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 					}
 					const float e1 = ex2_fast(w1 - w0), e2 = ex2_fast(w2 - w0);          // e0 = 1
 					const float c1w = 1.0f + e1, c2w = c1w + e2;
-					const u32x4 rnd = philox4x32<10>(u32x4{(uint32_t)(l0 + lj), ig_global, a.iter, TAG_GENO}, a.key0, a.key1);
-					const float u = u01f(rnd.x) * c2w;
+					const float u = u01f(rj[j]) * c2w;
 					const int pick = (u < 1.0f) ? 0 : (u < c1w ? 1 : 2);
 					// two_allele_auto :2440 / tri_allele_auto :2509
 					if (nd == 2) {
@@ -928,9 +936,12 @@ static ig_status tetra_pass_a(ig_ctx *c, int init)
 	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
 	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
 	switch (g.KP) {
-	case 4: CK(opt_smem(tetra_zs_kernel<4>, sm)); tetra_zs_kernel<4><<<grid, block, sm, c->stream>>>(a); break;
-	case 8: CK(opt_smem(tetra_zs_kernel<8>, sm)); tetra_zs_kernel<8><<<grid, block, sm, c->stream>>>(a); break;
-	default: CK(opt_smem(tetra_zs_kernel<16>, sm)); tetra_zs_kernel<16><<<grid, block, sm, c->stream>>>(a); break;
+	case 4: if (c->rounds == 10) { CK(opt_smem(tetra_zs_kernel<4, 10>, sm)); tetra_zs_kernel<4, 10><<<grid, block, sm, c->stream>>>(a); }
+	         else { CK(opt_smem(tetra_zs_kernel<4, 7>, sm)); tetra_zs_kernel<4, 7><<<grid, block, sm, c->stream>>>(a); } break;
+	case 8: if (c->rounds == 10) { CK(opt_smem(tetra_zs_kernel<8, 10>, sm)); tetra_zs_kernel<8, 10><<<grid, block, sm, c->stream>>>(a); }
+	         else { CK(opt_smem(tetra_zs_kernel<8, 7>, sm)); tetra_zs_kernel<8, 7><<<grid, block, sm, c->stream>>>(a); } break;
+	default: if (c->rounds == 10) { CK(opt_smem(tetra_zs_kernel<16, 10>, sm)); tetra_zs_kernel<16, 10><<<grid, block, sm, c->stream>>>(a); }
+	         else { CK(opt_smem(tetra_zs_kernel<16, 7>, sm)); tetra_zs_kernel<16, 7><<<grid, block, sm, c->stream>>>(a); } break;
 	}
 	CK(cudaGetLastError());
 	t->timing = timed;           // the closing event is recorded after PASS B: the two passes are one unit of work
@@ -946,9 +957,12 @@ static ig_status tetra_pass_b(ig_ctx *c, int init)
 	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
 	const size_t sm = smem_geno(g);
 	switch (g.KP) {
-	case 4: CK(opt_smem(tetra_geno_kernel<4>, sm)); tetra_geno_kernel<4><<<grid, block, sm, c->stream>>>(a); break;
-	case 8: CK(opt_smem(tetra_geno_kernel<8>, sm)); tetra_geno_kernel<8><<<grid, block, sm, c->stream>>>(a); break;
-	default: CK(opt_smem(tetra_geno_kernel<16>, sm)); tetra_geno_kernel<16><<<grid, block, sm, c->stream>>>(a); break;
+	case 4: if (c->rounds == 10) { CK(opt_smem(tetra_geno_kernel<4, 10>, sm)); tetra_geno_kernel<4, 10><<<grid, block, sm, c->stream>>>(a); }
+	         else { CK(opt_smem(tetra_geno_kernel<4, 7>, sm)); tetra_geno_kernel<4, 7><<<grid, block, sm, c->stream>>>(a); } break;
+	case 8: if (c->rounds == 10) { CK(opt_smem(tetra_geno_kernel<8, 10>, sm)); tetra_geno_kernel<8, 10><<<grid, block, sm, c->stream>>>(a); }
+	         else { CK(opt_smem(tetra_geno_kernel<8, 7>, sm)); tetra_geno_kernel<8, 7><<<grid, block, sm, c->stream>>>(a); } break;
+	default: if (c->rounds == 10) { CK(opt_smem(tetra_geno_kernel<16, 10>, sm)); tetra_geno_kernel<16, 10><<<grid, block, sm, c->stream>>>(a); }
+	         else { CK(opt_smem(tetra_geno_kernel<16, 7>, sm)); tetra_geno_kernel<16, 7><<<grid, block, sm, c->stream>>>(a); } break;
 	}
 	CK(cudaGetLastError());
 	if (t->timing && !init) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; t->timing = false; }
