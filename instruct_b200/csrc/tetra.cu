@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 	const int Nloc = g.Nloc, mt0 = l0 / TT;
 	const int nsub_total = (Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
 	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
-	int *hist_t = hist + (tid & (R - 1));
+	const uint32_t hist_sa = smem_addr(hist) + (uint32_t)(tid & (R - 1)) * 4u, R4 = (uint32_t)R * 4u;
 	const float LOG2E = 1.4426950408889634f;
 	const float LG2_6 = 2.584962500721156f;
 
@@ -673,10 +673,12 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 					m_lg2 += lg2_fast(Pl[g0 * KP + z0] * Pl[g1 * KP + z1]) + lg2_fast(Pl[g2 * KP + z2] * Pl[g3 * KP + z3]);
 				}
 				// ---- tally of the next update_P_auto over the latent genotype (poly_geno.c:403-424)
-				atomicAdd(hist_t + ((lj * g.A + g0) * KP + z0) * R, 1);
-				atomicAdd(hist_t + ((lj * g.A + g1) * KP + z1) * R, 1);
-				atomicAdd(hist_t + ((lj * g.A + g2) * KP + z2) * R, 1);
-				atomicAdd(hist_t + ((lj * g.A + g3) * KP + z3) * R, 1);
+				// shared-space RED on explicit 32-bit addresses (a generic atomicAdd costs an address-space check per call)
+				const uint32_t hrow = hist_sa + (uint32_t)(lj * g.A * KP) * R4;
+				red_inc(hrow + (uint32_t)(g0 * KP + (int)z0) * R4);
+				red_inc(hrow + (uint32_t)(g1 * KP + (int)z1) * R4);
+				red_inc(hrow + (uint32_t)(g2 * KP + (int)z2) * R4);
+				red_inc(hrow + (uint32_t)(g3 * KP + (int)z3) * R4);
 			}
 			*(gp + (size_t)mt * Nloc) = make_int4((int)gn[0], (int)gn[1], (int)gn[2], (int)gn[3]);
 			ll_nat += m_nat; ll_lg2 += m_lg2;
