@@ -43,6 +43,18 @@ WORKLOADS = {
 TETRA = {"c5", "tiny5"}
 
 
+def measured_traffic(workload, N, L):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json),
+    valid for the workload's default shape only."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if workload in t and (N, L) == WORKLOADS[workload][:2]:
+            return float(t[workload]["bytes"])
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -345,7 +357,7 @@ def run_ours(args):
                        "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel() * (2 if tetra else 1)) / 1e9),
                        "geometry": geo, "rng": f"philox4x32-{args.rng_rounds or 7} (Z draw), philox4x32-10 (all other draws)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "tetra_zs + tetra_geno (the two passes of one sweep)" if tetra else "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
+                         "traffic": measured_traffic(args.workload, N, L) if world == 1 else None, "kernel": "tetra_zs + tetra_geno (the two passes of one sweep)" if tetra else "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,
                          "algorithmic_bytes_per_launch": algo_bytes_launch, "peak_source": peak_src,
                          "share_of_step": zq_ms / ms_direct if ms_direct > 0 else None,
                          "graph_replay": (not inline_profile) and world == 1 and not tetra and args.workload != "c3", "ms_per_step_direct_launch": ms_direct / args.steps},

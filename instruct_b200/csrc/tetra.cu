@@ -488,45 +488,83 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 
 // per individual: the S statistics summed over chunks in chunk order (shard-invariant), written
 // at the individual's GLOBAL slot so that one all-gather completes the array on every rank
-__global__ void tetra_dind_kernel(const float *dpart, double *dind, Geometry g)
+// CTA = 32 individuals (lanes) x CG chunk groups (warps): warp w adds the partials of chunks w,
+// w + CG, ... (coalesced over the 32 individuals), warp 0 then adds the CG group sums in group
+// order.  The order depends only on the chunk decomposition, i.e. on (L, K, A): shard-invariant.
+constexpr int CG = 8;
+__global__ void __launch_bounds__(32 * CG) tetra_dind_kernel(const float *dpart, double *dind, Geometry g)
 {
-	const int il = blockIdx.x * blockDim.x + threadIdx.x;
-	if (il >= g.Nloc) return;
+	__shared__ double sh[CG][MAX_K][32];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int il = blockIdx.x * 32 + lane;
+	const bool live = il < g.Nloc;
+	double s[MAX_K];
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) s[k] = 0.0;
+	if (live)
+		for (int c = w; c < g.nchunks; c += CG)
+#pragma unroll
+			for (int k = 0; k < MAX_K; k++)
+				if (k < g.K) s[k] += (double)dpart[((size_t)c * g.K + k) * g.Nloc + il];
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) sh[w][k][lane] = s[k];
+	__syncthreads();
+	if (w != 0 || !live) return;
 	for (int k = 0; k < g.K; k++) {
-		double s = 0.0;
-		for (int c = 0; c < g.nchunks; c++) s += (double)dpart[((size_t)c * g.K + k) * g.Nloc + il];
-		dind[(size_t)(g.i0 + il) * g.K + k] = s;
+		double t = 0.0;
+		for (int ww = 0; ww < CG; ww++) t += sh[ww][k][lane];
+		dind[(size_t)(g.i0 + il) * g.K + k] = t;
 	}
 }
 
 // --------------------------------------------------------------------------------------
 // Q_i ~ Dirichlet(cnt_i + alpha), poly_geno.c:812-833
 // --------------------------------------------------------------------------------------
-__global__ void tetra_q_kernel(const uint16_t *pcnt, double *ind, float *Qf, int32_t *cnt_out, const DevScalars *sc, Geometry g,
-                               uint32_t iter, uint32_t key0, uint32_t key1)
+__global__ void __launch_bounds__(32 * CG) tetra_q_kernel(const uint16_t *pcnt, double *ind, float *Qf, int32_t *cnt_out, const DevScalars *sc, Geometry g,
+                                                          uint32_t iter, uint32_t key0, uint32_t key1)
 {
-	const int il = blockIdx.x * blockDim.x + threadIdx.x;
-	if (il >= g.Nloc) return;
+	__shared__ int shc[CG][MAX_K][32];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int il = blockIdx.x * 32 + lane;
+	const bool live = il < g.Nloc;
 	int cnt[MAX_K];
+#pragma unroll
 	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
-	for (int c = 0; c < g.nchunks; c++) {
-		const uint16_t *pc = pcnt + ((size_t)c * g.Nloc + il) * g.KP;
-		for (int k = 0; k < g.K; k++) cnt[k] += pc[k];
+	if (live)
+		for (int c = w; c < g.nchunks; c += CG) {
+			const uint16_t *pc = pcnt + ((size_t)c * g.Nloc + il) * g.KP;
+#pragma unroll
+			for (int k = 0; k < MAX_K; k++)
+				if (k < g.K) cnt[k] += pc[k];
+		}
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) shc[w][k][lane] = cnt[k];
+	__syncthreads();
+	if (w != 0 || !live) return;
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) {
+		int t = 0;
+		for (int ww = 0; ww < CG; ww++) t += shc[ww][k][lane];
+		cnt[k] = t;
 	}
 	const int ig_global = g.i0 + il;
 	double *rec = ind + (size_t)ig_global * g.REC;
 	const double alpha = sc->alpha;
 	Stream sq((uint32_t)ig_global, 0u, iter, TAG_Q, key0, key1);
 	double qv[MAX_K], sum = 0.0;
-	for (int k = 0; k < g.K; k++) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++)
+		if (k < g.K) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
 	double slq = 0.0;
-	for (int k = 0; k < g.K; k++) {
-		const double qk = qv[k] / sum;
-		rec[k] = qk;
-		slq += log(qk);
-		Qf[(size_t)il * g.KP + k] = (float)qk;
-		cnt_out[(size_t)il * g.K + k] = cnt[k];
-	}
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++)
+		if (k < g.K) {
+			const double qk = qv[k] / sum;
+			rec[k] = qk;
+			slq += log(qk);
+			Qf[(size_t)il * g.KP + k] = (float)qk;
+			cnt_out[(size_t)il * g.K + k] = cnt[k];
+		}
 	for (int k = g.K; k < g.KP; k++) Qf[(size_t)il * g.KP + k] = 0.0f;
 	rec[g.K + 1] = slq;
 	rec[g.K + 2] = 0.0;
@@ -699,14 +737,22 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 }
 
 // indvlkh (cal_lkd :715): chunk partials in chunk order, one thread per individual
-__global__ void tetra_indv_lkh_kernel(const float *lpart, double *ind, Geometry g)
+__global__ void __launch_bounds__(32 * CG) tetra_indv_lkh_kernel(const float *lpart, double *ind, Geometry g)
 {
-	const int il = blockIdx.x * blockDim.x + threadIdx.x;
-	if (il >= g.Nloc) return;
+	__shared__ double sh[CG][32];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int il = blockIdx.x * 32 + lane;
+	const bool live = il < g.Nloc;
 	double s = 0.0;
-	for (int c = 0; c < g.nchunks; c++)
-		s += (double)lpart[((size_t)c * 2) * g.Nloc + il] + (double)lpart[((size_t)c * 2 + 1) * g.Nloc + il] * LN2_D;
-	ind[(size_t)(g.i0 + il) * g.REC + g.K] = s;
+	if (live)
+		for (int c = w; c < g.nchunks; c += CG)
+			s += (double)lpart[((size_t)c * 2) * g.Nloc + il] + (double)lpart[((size_t)c * 2 + 1) * g.Nloc + il] * LN2_D;
+	sh[w][lane] = s;
+	__syncthreads();
+	if (w != 0 || !live) return;
+	double t = 0.0;
+	for (int ww = 0; ww < CG; ww++) t += sh[ww][lane];
+	ind[(size_t)(g.i0 + il) * g.REC + g.K] = t;
 }
 // totallkh and the column sums of Q (check_empty_cluster mcmc.c:1944): one CTA, fixed tree
 __global__ void __launch_bounds__(RED1) tetra_lkh_kernel(const double *ind, DevScalars *sc, Geometry g)
@@ -986,7 +1032,7 @@ static ig_status tetra_tables(ig_ctx *c, int do_cur, int do_prop)
 static ig_status tetra_q(ig_ctx *c)
 {
 	const Geometry &g = c->geo;
-	tetra_q_kernel<<<nb((size_t)g.Nloc, 128), 128, 0, c->stream>>>(c->pcnt, c->ind, c->Qf, c->cnt, c->sc, g, c->iter, c->key0, c->key1);
+	tetra_q_kernel<<<nb((size_t)g.Nloc, 32), 32 * CG, 0, c->stream>>>(c->pcnt, c->ind, c->Qf, c->cnt, c->sc, g, c->iter, c->key0, c->key1);
 	CK(cudaGetLastError());
 	c->launches++;
 	return IG_OK;
@@ -994,7 +1040,7 @@ static ig_status tetra_q(ig_ctx *c)
 
 static ig_status tetra_lkh(ig_ctx *c)
 {
-	tetra_indv_lkh_kernel<<<nb((size_t)c->geo.Nloc, 128), 128, 0, c->stream>>>(c->tetra->lpart, c->ind, c->geo);
+	tetra_indv_lkh_kernel<<<nb((size_t)c->geo.Nloc, 32), 32 * CG, 0, c->stream>>>(c->tetra->lpart, c->ind, c->geo);
 	CK(cudaGetLastError());
 	// (Q, indvlkh) of every shard: totallkh, the empty-cluster sums and the moments run redundantly everywhere
 	ig_status st = ig_exchange_individuals(c);
@@ -1028,7 +1074,7 @@ static ig_status tetra_s_end(ig_ctx *c, int decide)
 {
 	TetraState *t = c->tetra;
 	const Geometry &g = c->geo;
-	tetra_dind_kernel<<<nb((size_t)g.Nloc, 128), 128, 0, c->stream>>>(t->dpart, t->dind, g);
+	tetra_dind_kernel<<<nb((size_t)g.Nloc, 32), 32 * CG, 0, c->stream>>>(t->dpart, t->dind, g);
 	CK(cudaGetLastError());
 	ig_status st = ig_allgather_double(c, t->dind, (size_t)c->shard_cap * g.K);
 	if (st != IG_OK) return st;
