@@ -329,6 +329,9 @@ def run_ours(args):
         xh = torch.empty(x.shape, dtype=torch.int16, pin_memory=True)
         xh.copy_(x)
         torch.cuda.synchronize()
+        if os.environ.get("IG_BENCH_DEBUG"):
+            print("debug: xh==x", bool((xh.to(dev) == x).all().item()), "neg frac", float((xh < 0).float().mean()), "an", an[:4].tolist(),
+                  "shape", tuple(xh.shape), "contig", xh.is_contiguous(), file=sys.stderr)
         sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, ploid=ploid, mode=mode, nstep_check_empty_cluster=10 ** 9)
         upd = args.steps + args.warmup
         t0 = time.perf_counter()
@@ -339,6 +342,7 @@ def run_ours(args):
         d2h = 8 * (nloc * (2 * K + 3) + 2 * K + 2)
         e2e = {"value": copies_local * upd / dt, "unit": "copy-updates/s", "h2d_bytes_per_step": h2d / upd,
                "d2h_bytes_per_step": d2h / upd, "sweeps": upd, "seconds": dt,
+               "retained_samples": int(ch.step), "posterior_mean_loglik": float(ch.totallkh),
                "note": "one ig_mcmc_updating() call: create + H2D of the pinned genotype store + all sweeps + D2H of CHAIN"}
         del xh
     s.close()

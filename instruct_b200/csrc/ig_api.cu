@@ -32,6 +32,7 @@ static double wall_ms()
 // errors
 // --------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+thread_local cudaStream_t ig_alloc_stream = nullptr;
 ig_status ig_fail(ig_status st, const char *fmt, ...)
 {
 	va_list ap;
@@ -138,6 +139,7 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	c->key0 = (uint32_t)cfg->seed;
 	c->key1 = (uint32_t)(cfg->seed >> 32);
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(IG_ERR_CUDA, "stream creation failed"); }
+	ig_alloc_stream = c->stream;
 	if (cfg->ploid == 4) {
 		ig_status st = tetra_create(c);
 		if (st != IG_OK) { cudaStreamDestroy(c->stream); delete c; return st; }
@@ -245,6 +247,7 @@ extern "C" ig_status ig_load_genotypes(ig_ctx *c, const int16_t *x_host, const i
 	if (!c || !x_host || !allelenum_host) return fail(IG_ERR_ARG, "null argument");
 	if (c->loaded) return fail(IG_ERR_STATE, "genotypes already loaded");
 	CK(cudaSetDevice(c->cfg.device));
+	ig_alloc_stream = c->stream;
 	Geometry &g = c->geo;
 	c->allelenum_h.assign(allelenum_host, allelenum_host + g.L);
 	CK(dalloc(&c->allelenum, (size_t)g.Lpad));
@@ -272,11 +275,15 @@ extern "C" ig_status ig_load_genotypes_device(ig_ctx *c, const int16_t *x_dev, c
 	if (!c || !x_dev || !allelenum_dev) return fail(IG_ERR_ARG, "null argument");
 	if (c->loaded) return fail(IG_ERR_STATE, "genotypes already loaded");
 	CK(cudaSetDevice(c->cfg.device));
+	ig_alloc_stream = c->stream;
 	Geometry &g = c->geo;
 	c->allelenum_h.resize(g.L);
-	CK(cudaMemcpy(c->allelenum_h.data(), allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+	// the caller produced x_dev / allelenum_dev on its own stream(s): wait for the whole device once
+	CK(cudaDeviceSynchronize());
+	CK(cudaMemcpyAsync(c->allelenum_h.data(), allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
 	CK(dalloc(&c->allelenum, (size_t)g.Lpad));
-	CK(cudaMemcpy(c->allelenum, allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+	CK(cudaMemcpyAsync(c->allelenum, allelenum_dev, (size_t)g.L * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
 	return c->tetra ? tetra_load(c, x_dev) : finish_load(c, x_dev);
 }
 
@@ -302,6 +309,7 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 	ig_status st = nccl_load();
 	if (st != IG_OK) return st;
 	CK(cudaSetDevice(c->cfg.device));
+	ig_alloc_stream = c->stream;
 	ncclUniqueId id;
 	memcpy(&id, id128, 128);
 	NCK(g_nccl.CommInitRank(&c->comm, c->cfg.shard_count, id, c->cfg.shard_rank));

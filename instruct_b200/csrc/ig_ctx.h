@@ -103,11 +103,18 @@ struct ig_ctx {
 
 static inline uint32_t pad_k(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
 
+// Zero-filled device allocation, complete on return.  A plain cudaMemset runs on the legacy default
+// stream, which is NOT ordered with the context's non-blocking stream: the fill could land after the
+// first asynchronous write into the buffer (seen: the allele-count vector zeroed after its upload when
+// the caller had work queued on stream 0).  Filling on the context's stream alone would leave the
+// opposite race with the synchronous cudaMemcpy uploads, so the fill is waited for.
+extern thread_local cudaStream_t ig_alloc_stream;      // set by the API entry points that allocate
 template <typename T>
 static cudaError_t dalloc(T **p, size_t n)
 {
 	cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
-	if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+	if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, (n ? n : 1) * sizeof(T), ig_alloc_stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ig_alloc_stream);
 	return e;
 }
 

@@ -904,7 +904,8 @@ template <typename T>
 static cudaError_t dalloc0(T **p, size_t n)
 {
 	cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
-	if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+	if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, (n ? n : 1) * sizeof(T), ig_alloc_stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ig_alloc_stream);       // see dalloc (ig_ctx.h)
 	return e;
 }
 
