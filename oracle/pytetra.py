@@ -21,6 +21,12 @@ def _tet_lib():
         return lib
     lib.tet_new.restype = C.c_void_p
     lib.tet_new.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3
+    lib.tet_new2.restype = C.c_void_p
+    lib.tet_new2.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
+    lib.tet_freq2.restype = c_dp
+    lib.tet_freq2.argtypes = [C.c_void_p]
+    lib.tet_tally_allo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tet_geno_conditional_allo.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     for f, rt in [("tet_z", C.c_void_p), ("tet_geno", C.c_void_p), ("tet_qq", c_dp), ("tet_qqnum", c_dp), ("tet_freq", c_dp),
                   ("tet_self", c_dp), ("tet_state", C.POINTER(C.c_int)), ("tet_alpha", c_dp), ("tet_indvlkh", c_dp),
                   ("tet_totallkh", c_dp), ("tet_exfreq", C.POINTER(C.c_float)), ("tet_genofreq", C.POINTER(C.c_float))]:
@@ -55,14 +61,16 @@ def _tet_lib():
 
 
 class TetraOracle:
-    def __init__(self, x, nd, allelenum, K, back_refl=1):
+    def __init__(self, x, nd, allelenum, K, back_refl=1, autopoly=1):
         self.lib = _tet_lib()
+        self.autopoly = autopoly
         self.x = np.ascontiguousarray(x, dtype=np.int16)
         self.nd = np.ascontiguousarray(nd, dtype=np.uint8)
         self.allelenum = np.ascontiguousarray(allelenum, dtype=np.int32)
         self.L, self.N, _ = self.x.shape
         self.K = K
-        self.h = self.lib.tet_new(self.N, self.L, K, back_refl, self.x.ctypes.data, self.nd.ctypes.data, self.allelenum.ctypes.data)
+        self.h = self.lib.tet_new2(self.N, self.L, K, back_refl, autopoly, self.x.ctypes.data, self.nd.ctypes.data,
+                                   self.allelenum.ctypes.data)
         self.Amax = self.lib.tet_amax(self.h)
         self.Gmax = self.lib.tet_gmax(self.h)
         as_arr = np.ctypeslib.as_array
@@ -71,6 +79,7 @@ class TetraOracle:
         self.qq = as_arr(self.lib.tet_qq(self.h), (self.N, K))
         self.qqnum = as_arr(self.lib.tet_qqnum(self.h), (self.N, K))
         self.freq = as_arr(self.lib.tet_freq(self.h), (K, self.L, self.Amax))
+        self.freq2 = as_arr(self.lib.tet_freq2(self.h), (K, self.L, self.Amax))     # allotetraploid: second subgenome
         self.self_rates = as_arr(self.lib.tet_self(self.h), (K,))
         self.state = as_arr(self.lib.tet_state(self.h), (K,))
         self.indvlkh = as_arr(self.lib.tet_indvlkh(self.h), (self.N,))
@@ -104,6 +113,17 @@ class TetraOracle:
         n = np.zeros((self.K, self.L, self.Amax), dtype=np.int32)
         self.lib.tet_tally(self.h, n.ctypes.data)
         return n
+
+    def tally_allo(self):
+        n1 = np.zeros((self.K, self.L, self.Amax), dtype=np.int32)
+        n2 = np.zeros((self.K, self.L, self.Amax), dtype=np.int32)
+        self.lib.tet_tally_allo(self.h, n1.ctypes.data, n2.ctypes.data)
+        return n1, n2
+
+    def geno_conditional_allo(self, i, l):
+        p = np.zeros(12)
+        n = self.lib.tet_geno_conditional_allo(self.h, i, l, p.ctypes.data)
+        return p[:n]
 
     def count_z(self):
         c = np.zeros((self.N, self.K))
@@ -175,10 +195,10 @@ class TetraOracle:
 class RefTetra:
     """The reference's own poly_geno.c on the same data (individual-major, as the reference holds it)."""
 
-    def __init__(self, x, nd, allelenum, K, back_refl=1):
+    def __init__(self, x, nd, allelenum, K, back_refl=1, autopoly=1):
         self.lib = ref_lib()
-        self.lib.refp_new.restype = C.c_void_p
-        self.lib.refp_new.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3
+        self.lib.refp_new2.restype = C.c_void_p
+        self.lib.refp_new2.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
         self.lib.refp_gmax.argtypes = [C.c_void_p]
         self.lib.refp_genolist.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         self.lib.refp_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -191,7 +211,7 @@ class RefTetra:
         self._x = xi
         self._nd = np.ascontiguousarray(np.transpose(nd, (1, 0)).astype(np.int32))
         self._an = np.ascontiguousarray(allelenum, dtype=np.int32)
-        self.h = self.lib.refp_new(N, L, K, back_refl, self._x.ctypes.data, self._nd.ctypes.data, self._an.ctypes.data)
+        self.h = self.lib.refp_new2(N, L, K, back_refl, autopoly, self._x.ctypes.data, self._nd.ctypes.data, self._an.ctypes.data)
         self.Gmax = self.lib.refp_gmax(self.h)
         self.Amax = int(self._an.max())
 
@@ -203,8 +223,9 @@ class RefTetra:
         n = self.lib.refp_genolist(self.h, l, buf.ctypes.data)
         return buf[:n].copy()
 
-    def tables(self, freq, S):
-        f = np.ascontiguousarray(freq, dtype=np.float64)
+    def tables(self, freq, S, freq2=None):
+        """freq2: the second subgenome's frequencies (allotetraploid harness)"""
+        f = np.ascontiguousarray(freq if freq2 is None else np.stack([freq, freq2]), dtype=np.float64)
         s = np.ascontiguousarray(S, dtype=np.float64)
         ex = np.zeros((self.K, self.L, self.Gmax), dtype=np.float32)
         gf = np.zeros((self.K, self.L, self.Gmax), dtype=np.float32)

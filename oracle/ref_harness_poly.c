@@ -25,14 +25,22 @@ typedef struct {
 	POLY *poly;
 } REFP;
 
+REFP *refp_new2(int N, int L, int K, int back_refl, int autopoly, const int *x, const int *alleleid, const int *allelenum);
 REFP *refp_new(int N, int L, int K, int back_refl, const int *x /*[N][L][4]*/, const int *alleleid /*[N][L]*/,
                const int *allelenum /*[L]*/)
+{
+	return refp_new2(N, L, K, back_refl, 1, x, alleleid, allelenum);
+}
+
+/* autopoly = 0: the allotetraploid model (-ap 0) */
+REFP *refp_new2(int N, int L, int K, int back_refl, int autopoly, const int *x /*[N][L][4]*/, const int *alleleid /*[N][L]*/,
+                const int *allelenum /*[L]*/)
 {
 	int i, j, k, amax = 0;
 	REFP *h = (REFP *)calloc(1, sizeof(REFP));
 	SEQDATA *d = &h->data;
 	d->ploid = 4; d->popnum = K; d->locinum = L; d->totalsize = N;
-	d->mode = 2; d->prior_flag = 0; d->back_refl = back_refl; d->type_freq = 1; d->autopoly = 1;
+	d->mode = 2; d->prior_flag = 0; d->back_refl = back_refl; d->type_freq = 1; d->autopoly = autopoly;
 	d->nstep_check_empty_cluster = 1 << 30; d->print_iter = 0; d->print_freq = 0;
 	d->missingnum = -9; d->missingdata = "-9";
 	d->seqdata = i3tensor(0, N - 1, 0, L - 1, 0, 3);
@@ -82,7 +90,15 @@ void refp_tables(REFP *h, const double *freq /*[K][L][Amax]*/, const double *S /
 	up.freq = d3tensor(0, d->popnum - 1, 0, d->locinum - 1, 0, A - 1);
 	for (k = 0; k < d->popnum; k++) for (l = 0; l < d->locinum; l++) for (a = 0; a < A; a++)
 		up.freq[k][l][a] = freq[((long)k * d->locinum + l) * A + a];
-	calc_exfreq_auto(&up, *d, h->poly);
+	if (d->autopoly == 1) calc_exfreq_auto(&up, *d, h->poly);
+	else {
+		/* allotetraploid: the second subgenome's frequencies follow the first in the same array, [2][K][L][Amax] */
+		up.freq2 = d3tensor(0, d->popnum - 1, 0, d->locinum - 1, 0, A - 1);
+		for (k = 0; k < d->popnum; k++) for (l = 0; l < d->locinum; l++) for (a = 0; a < A; a++)
+			up.freq2[k][l][a] = freq[(((long)d->popnum + k) * d->locinum + l) * A + a];
+		calc_exfreq_allo(&up, *d, h->poly);
+		free_d3tensor(up.freq2, 0, d->popnum - 1, 0, d->locinum - 1, 0, A - 1);
+	}
 	for (k = 0; k < d->popnum; k++) calc_self_genofreq(S[k], h->poly->genofreq[k], *d, h->poly, k);
 	for (k = 0; k < d->popnum; k++) for (l = 0; l < d->locinum; l++) {
 		int id = find_id(d->allelenum[l], h->poly->allele_poly, h->poly->num_allele);

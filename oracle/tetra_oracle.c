@@ -34,11 +34,13 @@ typedef struct {
 
 struct tet_model {
 	int N, L, K, Amax, Gmax, back_refl;
+	int autopoly;      /* 1: autotetraploid (-ap 1); 0: allotetraploid (-ap 0): copies 0,1 and copies 2,3 are two subgenomes */
 	const int16_t *x;
 	const uint8_t *nd;
 	const int32_t *allelenum;
 	int8_t *geno, *z;
 	double *qq, *qqnum, *freq;
+	double *freq2;     /* allotetraploid: allele frequencies of the second subgenome (UPMCMC.freq2, mcmc.h:16) */
 	double alpha, totallkh;
 	double *self_rates, *indvlkh;
 	int *state;
@@ -77,6 +79,23 @@ static void build_catalogue(tet_cat *c, int n)
 		c->code[p++] = j * n * n * n + k * n * n + n * a + b;
 }
 
+/* allo_geno_num / allo_geno_list, poly_geno.c:2031-2120: classes iikk | iikl (k<l) | ijkk (i<j) | ijkl
+ * (i<j, k<l); cls[0..3] hold the four class sizes, cls[4] = 0 */
+static void build_catalogue_allo(tet_cat *c, int n)
+{
+	int j, k, a, b, p = 0;
+	c->n = n;
+	c->cls[0] = n * n; c->cls[1] = n * (n - 1) / 2 * n; c->cls[2] = n * (n - 1) / 2 * n;
+	c->cls[3] = n * (n - 1) * n * (n - 1) / 4; c->cls[4] = 0;
+	c->total = n * n + n * (n - 1) * n + n * (n - 1) * n * (n - 1) / 4;
+	c->code = (int *)malloc(sizeof(int) * (c->total > 0 ? c->total : 1));
+	for (j = 0; j < n; j++) for (k = 0; k < n; k++) c->code[p++] = j * n * n * (n + 1) + k * (n + 1);
+	for (j = 0; j < n; j++) for (k = 0; k < n - 1; k++) for (a = k + 1; a < n; a++) c->code[p++] = j * n * n * (n + 1) + n * k + a;
+	for (j = 0; j < n - 1; j++) for (k = j + 1; k < n; k++) for (a = 0; a < n; a++) c->code[p++] = (j * n + k) * n * n + a * (n + 1);
+	for (j = 0; j < n - 1; j++) for (k = j + 1; k < n; k++) for (a = 0; a < n - 1; a++) for (b = a + 1; b < n; b++)
+		c->code[p++] = j * n * n * n + k * n * n + a * n + b;
+}
+
 /* find_id, poly_geno.c:2367 */
 static int lookup(const tet_cat *c, int code)
 {
@@ -90,9 +109,15 @@ static int member(int v, const int *set, int len) { int i; for (i = 0; i < len; 
 
 tet_model *tet_new(int N, int L, int K, int back_refl, const int16_t *x, const uint8_t *nd, const int32_t *allelenum)
 {
+	return tet_new2(N, L, K, back_refl, 1, x, nd, allelenum);
+}
+
+tet_model *tet_new2(int N, int L, int K, int back_refl, int autopoly, const int16_t *x, const uint8_t *nd, const int32_t *allelenum)
+{
 	int l, j, i, k;
 	tet_model *m = (tet_model *)calloc(1, sizeof(tet_model));
 	m->N = N; m->L = L; m->K = K; m->back_refl = back_refl; m->x = x; m->nd = nd; m->allelenum = allelenum;
+	m->autopoly = autopoly;
 	m->Amax = 1;
 	for (l = 0; l < L; l++) if (allelenum[l] > m->Amax) m->Amax = allelenum[l];
 	/* one catalogue per distinct allele count, ascending (gen_allele_poly, poly_geno.c:1673) */
@@ -102,7 +127,7 @@ tet_model *tet_new(int N, int L, int K, int back_refl, const int16_t *x, const u
 		int used = 0;
 		for (l = 0; l < L; l++) if (allelenum[l] == j) used = 1;
 		if (!used) continue;
-		build_catalogue(&m->cat[m->ncat], j);
+		if (autopoly) build_catalogue(&m->cat[m->ncat], j); else build_catalogue_allo(&m->cat[m->ncat], j);
 		if (m->cat[m->ncat].total > m->Gmax) m->Gmax = m->cat[m->ncat].total;
 		for (l = 0; l < L; l++) if (allelenum[l] == j) m->cat_of[l] = m->ncat;
 		m->ncat++;
@@ -112,6 +137,7 @@ tet_model *tet_new(int N, int L, int K, int back_refl, const int16_t *x, const u
 	m->qq = (double *)calloc((size_t)N * K, sizeof(double));
 	m->qqnum = (double *)calloc((size_t)N * K, sizeof(double));
 	m->freq = (double *)calloc((size_t)K * L * m->Amax, sizeof(double));
+	m->freq2 = (double *)calloc((size_t)K * L * m->Amax, sizeof(double));
 	m->self_rates = (double *)calloc(K, sizeof(double));
 	m->state = (int *)calloc(K, sizeof(int));
 	m->indvlkh = (double *)calloc(N, sizeof(double));
@@ -128,7 +154,7 @@ void tet_free(tet_model *m)
 	int j;
 	if (!m) return;
 	for (j = 0; j < m->ncat; j++) free(m->cat[j].code);
-	free(m->cat); free(m->cat_of); free(m->geno); free(m->z); free(m->qq); free(m->qqnum); free(m->freq);
+	free(m->cat); free(m->cat_of); free(m->geno); free(m->z); free(m->qq); free(m->qqnum); free(m->freq); free(m->freq2);
 	free(m->self_rates); free(m->state); free(m->indvlkh); free(m->exfreq); free(m->genofreq); free(m);
 }
 
@@ -138,6 +164,7 @@ int8_t *tet_geno(tet_model *m) { return m->geno; }
 double *tet_qq(tet_model *m) { return m->qq; }
 double *tet_qqnum(tet_model *m) { return m->qqnum; }
 double *tet_freq(tet_model *m) { return m->freq; }
+double *tet_freq2(tet_model *m) { return m->freq2; }
 double *tet_self(tet_model *m) { return m->self_rates; }
 int *tet_state(tet_model *m) { return m->state; }
 double *tet_alpha(tet_model *m) { return &m->alpha; }
@@ -166,6 +193,15 @@ static int dosage_class(const int8_t *g)
 	return ns == 3 ? 3 : 4;
 }
 
+/* get_cat_allo, poly_geno.c:1341-1372: 0 iikk, 1 iikl, 2 ijkk, 3 ijkl */
+static int allo_class(const int8_t *g)
+{
+	const int c1 = (g[0] == g[1]) ? 1 : 2, c2 = (g[2] == g[3]) ? 1 : 2;
+	if (c1 + c2 == 2) return 0;
+	if (c1 + c2 == 3) return (c1 == 1 && c2 == 2) ? 1 : 2;
+	return 3;
+}
+
 /* get_index_auto, poly_geno.c:1289 (genotypes here always follow the writing rules of
  * check_rule_auto :1346: two_/tri_allele_auto only emit canonical forms) */
 int tet_geno_index(const tet_model *m, int l, const int8_t *g)
@@ -180,9 +216,11 @@ static inline int all_same4(const int8_t *z) { return z[0] == z[1] && z[1] == z[
 
 /* ---------------------------------------------------------------- tables -------------- */
 /* calc_exfreq_auto, poly_geno.c:1515-1577: log Hardy-Weinberg genotype frequencies, float */
+static void calc_exfreq_allo(tet_model *m);
 void tet_calc_exfreq(tet_model *m)
 {
 	int k, l, g, d[4], t, q;
+	if (!m->autopoly) { calc_exfreq_allo(m); return; }
 	for (k = 0; k < m->K; k++)
 		for (l = 0; l < m->L; l++) {
 			const int n = m->allelenum[l];
@@ -369,10 +407,119 @@ static void genfreq_locus(const tet_model *m, float self, int k, int l, float *P
 }
 
 /* calc_self_genofreq, poly_geno.c:1219-1233 (self_rate arrives as double, is passed as float) */
+/* calc_exfreq_allo, poly_geno.c:1592-1671: log Hardy-Weinberg frequencies of the two-subgenome
+ * genotypes; the float / double mix of the reference is kept */
+static void calc_exfreq_allo(tet_model *m)
+{
+	int k, l, g, d[4], t, q;
+	for (k = 0; k < m->K; k++)
+		for (l = 0; l < m->L; l++) {
+			const int n = m->allelenum[l];
+			const tet_cat *c = &m->cat[m->cat_of[l]];
+			const double *f = m->freq + FO(m, k, l, 0), *f2 = m->freq2 + FO(m, k, l, 0);
+			float *R = m->exfreq + TO(m, k, l);
+			int lo = 0;
+			for (g = lo; g < lo + c->cls[0]; g++) {                     /* iikk */
+				t = c->code[g]; d[0] = t % n; t /= (n * n); d[1] = t % n;
+				R[g] = (float)((log(f[d[1]]) + log(f2[d[0]])) * (4 / 2));
+			}
+			lo += c->cls[0];
+			for (g = lo; g < lo + c->cls[1]; g++) {                     /* iikl */
+				t = c->code[g];
+				for (q = 0; q < 3; q++) { d[q] = t % n; t /= n; }
+				R[g] = (float)(log(2.0) + log(f[d[2]]) * (4 / 2) + log(f2[d[0]]) + log(f2[d[1]]));
+			}
+			lo += c->cls[1];
+			for (g = lo; g < lo + c->cls[2]; g++) {                     /* ijkk */
+				t = c->code[g]; t /= n;
+				for (q = 0; q < 3; q++) { d[q] = t % n; t /= n; }
+				R[g] = (float)(log(2.0) + log(f2[d[0]]) * (4 / 2) + log(f[d[2]]) + log(f[d[1]]));
+			}
+			lo += c->cls[2];
+			for (g = lo; g < lo + c->cls[3]; g++) {                     /* ijkl */
+				t = c->code[g];
+				for (q = 0; q < 4; q++) { d[q] = t % n; t /= n; }
+				R[g] = (float)log(4.0);
+				for (q = 0; q < 2; q++) R[g] += (float)log(f2[d[q]]);
+				for (q = 2; q < 4; q++) R[g] += (float)log(f[d[q]]);
+			}
+		}
+}
+
+/* allo_genfreq, poly_geno.c:2122-2305: (I - sA) P = (1 - s) R solved class by class from the
+ * doubly heterozygous genotypes down; operation order and float / double mix as in the reference */
+static void genfreq_locus_allo(const tet_model *m, float self, int k, int l, float *P)
+{
+	const int n = m->allelenum[l];
+	const tet_cat *c = &m->cat[m->cat_of[l]];
+	const float *R = m->exfreq + TO(m, k, l);
+	int i, j, kk, tmp, num, d[3];
+	float temp;
+	tmp = c->total;
+	for (i = tmp - c->cls[3]; i < tmp; i++)                             /* ijkl */
+		P[i] = log(1 - self) + R[i] - log(1 - self / 4);
+	tmp -= c->cls[3];
+	for (i = tmp - c->cls[2]; i < tmp; i++) {                           /* ijkk */
+		num = c->code[i];
+		d[0] = num % n; num /= (n * n); d[1] = num % n; num /= n; d[2] = num % n;
+		temp = 0;
+		for (j = 0; j < n; j++)
+			if (j != d[0]) {
+				if (d[0] < j) num = lookup(c, d[2] * n * n * n + d[1] * n * n + d[0] * n + j);
+				else num = lookup(c, d[2] * n * n * n + d[1] * n * n + j * n + d[0]);
+				temp += exp(P[num]) * self / 8.0;
+			}
+		P[i] = log((1 - self) * exp(R[i]) + temp) - log(1 - self / 2.0);
+	}
+	tmp -= c->cls[2];
+	for (i = tmp - c->cls[1]; i < tmp; i++) {                           /* iikl */
+		num = c->code[i];
+		d[0] = num % n; num /= n; d[1] = num % n; num /= n; d[2] = num % n;
+		temp = 0;
+		for (j = 0; j < n; j++)
+			if (j != d[2]) {
+				if (d[2] < j) num = lookup(c, d[2] * n * n * n + j * n * n + d[1] * n + d[0]);
+				else num = lookup(c, j * n * n * n + d[2] * n * n + d[1] * n + d[0]);
+				temp += exp(P[num]) * self / 8.0;
+			}
+		P[i] = log((1 - self) * exp(R[i]) + temp) - log(1 - self / 2.0);
+	}
+	tmp -= c->cls[1];
+	for (i = tmp - c->cls[0]; i < tmp; i++) {                           /* iikk */
+		num = c->code[i];
+		d[0] = num % n; num /= (n * n); d[1] = num % n;
+		temp = 0;
+		for (j = 0; j < n; j++)                                         /* P_iikl */
+			if (j != d[0]) {
+				if (d[0] < j) num = lookup(c, d[1] * n * n * (n + 1) + d[0] * n + j);
+				else num = lookup(c, d[1] * n * n * (n + 1) + j * n + d[0]);
+				temp += exp(P[num]) * self / 4.0;
+			}
+		for (j = 0; j < n; j++)                                         /* P_ijkk */
+			if (j != d[1]) {
+				if (d[1] < j) num = lookup(c, d[1] * n * n * n + j * n * n + d[0] * (n + 1));
+				else num = lookup(c, j * n * n * n + d[1] * n * n + d[0] * (n + 1));
+				temp += exp(P[num]) * self / 4.0;
+			}
+		for (j = 0; j < n; j++)                                         /* P_ijkl */
+			for (kk = 0; kk < n; kk++)
+				if (j != d[1] && kk != d[0]) {
+					const int a0 = d[1] < j ? d[1] : j, a1 = d[1] < j ? j : d[1];
+					const int b0 = d[0] < kk ? d[0] : kk, b1 = d[0] < kk ? kk : d[0];
+					num = lookup(c, a0 * n * n * n + a1 * n * n + b0 * n + b1);
+					temp += exp(P[num]) * self / 16.0;
+				}
+		P[i] = log((1 - self) * exp(R[i]) + temp) - log(1 - self);
+	}
+}
+
 void tet_calc_genofreq(tet_model *m, int k, double self, float *out)
 {
 	int l;
-	for (l = 0; l < m->L; l++) genfreq_locus(m, (float)self, k, l, out + (long)l * m->Gmax);
+	for (l = 0; l < m->L; l++) {
+		if (m->autopoly) genfreq_locus(m, (float)self, k, l, out + (long)l * m->Gmax);
+		else genfreq_locus_allo(m, (float)self, k, l, out + (long)l * m->Gmax);
+	}
 }
 
 /* ---------------------------------------------------------------- likelihood ---------- */
@@ -384,6 +531,17 @@ static double site_loglik(const tet_model *m, int l, int i, const int8_t *z, con
 	int c, q;
 	if (m->nd[(long)l * m->N + i] == 0) return 0;
 	if (all_same4(z)) return (double)tab_of_z0[tet_geno_index(m, l, g)];
+	if (!m->autopoly) {                                    /* :1267-1283 */
+		c = allo_class(g);
+		for (q = 0; q < 2; q++) ld += log(m->freq[FO(m, z[q], l, g[q])]);
+		for (q = 2; q < 4; q++) ld += log(m->freq2[FO(m, z[q], l, g[q])]);
+		switch (c) {
+		case 1: ld += log(2); break;
+		case 2: ld += log(2); break;
+		case 3: ld += log(4); break;
+		}
+		return ld;
+	}
 	c = dosage_class(g);
 	for (q = 0; q < 4; q++) ld += log(m->freq[FO(m, z[q], l, g[q])]);
 	switch (c) {
@@ -440,6 +598,20 @@ void tet_tally(const tet_model *m, int32_t *n)
 		for (i = 0; i < m->N; i++) {
 			if (m->nd[(long)l * m->N + i] == 0) continue;
 			for (q = 0; q < 4; q++) n[FO(m, m->z[XO(m, l, i) + q], l, m->geno[XO(m, l, i) + q])]++;
+		}
+}
+
+/* the count half of update_P_allo, poly_geno.c:441-489: copies 0,1 and copies 2,3 are tallied apart */
+void tet_tally_allo(const tet_model *m, int32_t *n1, int32_t *n2)
+{
+	int i, l, q;
+	memset(n1, 0, sizeof(int32_t) * (size_t)m->K * m->L * m->Amax);
+	memset(n2, 0, sizeof(int32_t) * (size_t)m->K * m->L * m->Amax);
+	for (l = 0; l < m->L; l++)
+		for (i = 0; i < m->N; i++) {
+			if (m->nd[(long)l * m->N + i] == 0) continue;
+			for (q = 0; q < 2; q++) n1[FO(m, m->z[XO(m, l, i) + q], l, m->geno[XO(m, l, i) + q])]++;
+			for (q = 2; q < 4; q++) n2[FO(m, m->z[XO(m, l, i) + q], l, m->geno[XO(m, l, i) + q])]++;
 		}
 }
 
@@ -507,6 +679,108 @@ static void resolution_logw(const tet_model *m, int i, int l, double *w)
 	}
 }
 
+/* ---- allotetraploid resolutions: two_allele_allo :2465 (7 ways), tri_allele_allo :2533 (12),
+ *      tetra_allele_allo :2602 (6).  ALLO_RES[nd-2][pick-1][copy] = index into the observed allele set */
+static const int8_t ALLO_RES2[7][4] = {{0,0,0,1},{0,1,0,0},{0,0,1,1},{1,1,0,0},{0,1,1,1},{1,1,0,1},{0,1,0,1}};
+static const int8_t ALLO_RES3[12][4] = {{0,0,1,2},{1,2,0,0},{1,1,0,2},{0,2,1,1},{2,2,0,1},{0,1,2,2},
+                                        {0,1,1,2},{1,2,0,1},{1,2,0,2},{0,2,1,2},{0,2,0,1},{0,1,0,2}};
+static const int8_t ALLO_RES4[6][4] = {{0,1,2,3},{2,3,0,1},{0,2,1,3},{1,3,0,2},{0,3,1,2},{1,2,0,3}};
+static int allo_nres(int nd) { return nd == 2 ? 7 : (nd == 3 ? 12 : 6); }
+static const int8_t *allo_res(int nd, int pick) { return nd == 2 ? ALLO_RES2[pick - 1] : (nd == 3 ? ALLO_RES3[pick - 1] : ALLO_RES4[pick - 1]); }
+
+static void write_resolution_allo(const int16_t *a, int nd, int pick, int8_t *g)
+{
+	const int8_t *r = allo_res(nd, pick);
+	int q;
+	for (q = 0; q < 4; q++) g[q] = (int8_t)a[r[q]];
+}
+
+/* log weights of the resolutions: choose_two_allo :962, choose_tri_allo :1043, choose_tetra_allo :1144.
+ * Same-z genotypes read population z's table at the resolution's genotype code (the codes the reference
+ * writes out case by case are exactly the base-n numbers of the resolved genotypes); otherwise the product
+ * of the admixture-averaged frequencies, subgenome 1 with freq and subgenome 2 with freq2, times 2 per
+ * heterozygous pair -- except that the reference leaves the factor out when only ONE pair is heterozygous
+ * (cases 1,2,5,6 of the two-allele list, 1-6 of the three-allele list) and in all six four-allele cases. */
+static void resolution_logw_allo(const tet_model *m, int i, int l, double *w)
+{
+	const int16_t *a = m->x + XO(m, l, i);
+	const int8_t *z = m->z + XO(m, l, i);
+	const int nd = m->nd[(long)l * m->N + i], n = m->allelenum[l], nr = allo_nres(nd);
+	const tet_cat *c = &m->cat[m->cat_of[l]];
+	int t, j;
+	if (all_same4(z)) {
+		const float *tab = m->genofreq + TO(m, z[0], l);
+		for (t = 0; t < nr; t++) {
+			const int8_t *r = allo_res(nd, t + 1);
+			const int code = ((a[r[0]] * n + a[r[1]]) * n + a[r[2]]) * n + a[r[3]];
+			w[t] = (double)tab[lookup(c, code)];
+		}
+	} else {
+		double f[4], f2[4];
+		for (t = 0; t < nd; t++) {
+			f[t] = 0; f2[t] = 0;
+			for (j = 0; j < m->K; j++) {
+				f[t] += m->qq[(long)i * m->K + j] * m->freq[FO(m, j, l, a[t])];
+				f2[t] += m->qq[(long)i * m->K + j] * m->freq2[FO(m, j, l, a[t])];
+			}
+		}
+		if (nd == 2) {
+			w[0] = 2 * log(f[0]) + log(f2[0]) + log(f2[1]);
+			w[1] = log(f[0]) + log(f[1]) + 2 * log(f2[0]);
+			w[2] = 2 * log(f[0]) + 2 * log(f2[1]);
+			w[3] = 2 * log(f[1]) + 2 * log(f2[0]);
+			w[4] = log(f[0]) + log(f[1]) + 2 * log(f2[1]);
+			w[5] = 2 * log(f[1]) + log(f2[0]) + log(f2[1]);
+			w[6] = log(2) + log(f[0]) + log(f[1]) + log(f2[0]) + log(f2[1]);
+		} else if (nd == 3) {
+			w[0] = 2 * log(f[0]) + log(f2[1]) + log(f2[2]);
+			w[1] = log(f[1]) + log(f[2]) + 2 * log(f2[0]);
+			w[2] = 2 * log(f[1]) + log(f2[0]) + log(f2[2]);
+			w[3] = log(f[0]) + log(f[2]) + 2 * log(f2[1]);
+			w[4] = 2 * log(f[2]) + log(f2[0]) + log(f2[1]);
+			w[5] = log(f[0]) + log(f[1]) + 2 * log(f2[2]);
+			w[6] = log(2) + log(f[0]) + log(f[1]) + log(f2[1]) + log(f2[2]);
+			w[7] = log(2) + log(f[1]) + log(f[2]) + log(f2[0]) + log(f2[1]);
+			w[8] = log(2) + log(f[1]) + log(f[2]) + log(f2[0]) + log(f2[2]);
+			w[9] = log(2) + log(f[0]) + log(f[2]) + log(f2[1]) + log(f2[2]);
+			w[10] = log(2) + log(f[0]) + log(f[2]) + log(f2[0]) + log(f2[1]);
+			w[11] = log(2) + log(f[0]) + log(f[1]) + log(f2[0]) + log(f2[2]);
+		} else {
+			w[0] = log(f[0]) + log(f[1]) + log(f2[2]) + log(f2[3]);
+			w[1] = log(f[2]) + log(f[3]) + log(f2[0]) + log(f2[1]);
+			w[2] = log(f[0]) + log(f[2]) + log(f2[1]) + log(f2[3]);
+			w[3] = log(f[1]) + log(f[3]) + log(f2[0]) + log(f2[2]);
+			w[4] = log(f[0]) + log(f[3]) + log(f2[1]) + log(f2[2]);
+			w[5] = log(f[1]) + log(f[2]) + log(f2[0]) + log(f2[3]);
+		}
+	}
+}
+
+static int draw_resolution_allo(tet_model *m, int i, int l)
+{
+	double w[12], tm;
+	const int nr = allo_nres(m->nd[(long)l * m->N + i]);
+	int t;
+	resolution_logw_allo(m, i, l, w);
+	tm = w[0];
+	for (t = 0; t < nr; t++) w[t] = exp(w[t] - tm);
+	for (t = 1; t < nr; t++) w[t] += w[t - 1];
+	return orc_rng_bracket(&m->rng, w, nr) + 1;
+}
+
+/* exact conditional of the allotetraploid resolution (tests); returns the number of resolutions */
+int tet_geno_conditional_allo(const tet_model *m, int i, int l, double *prob)
+{
+	double w[12], s = 0, w0;
+	const int nr = allo_nres(m->nd[(long)l * m->N + i]);
+	int t;
+	resolution_logw_allo(m, i, l, w);
+	w0 = w[0];
+	for (t = 0; t < nr; t++) { w[t] = exp(w[t] - w0); s += w[t]; }
+	for (t = 0; t < nr; t++) prob[t] = w[t] / s;
+	return nr;
+}
+
 void tet_geno_conditional(const tet_model *m, int i, int l, double *prob)
 {
 	double w[3], s = 0;
@@ -531,7 +805,7 @@ static int draw_resolution(tet_model *m, int i, int l)
 /* choose_unif, poly_geno.c:842-852 */
 static int draw_uniform_pick(tet_model *m, int n)
 {
-	double w[8];
+	double w[12];
 	int j;
 	for (j = 0; j < n; j++) w[j] = (double)(j + 1) / (double)n;
 	return orc_rng_bracket(&m->rng, w, n) + 1;
@@ -547,6 +821,15 @@ static void resolve_all(tet_model *m, int initial)
 			const int16_t *a = m->x + XO(m, l, i);
 			int8_t *g = m->geno + XO(m, l, i);
 			if (nd == 0) continue;
+			if (!m->autopoly) {                                 /* initial_geno :320-340, update_geno :524-548 */
+				if (nd == 1) for (q = 0; q < 4; q++) g[q] = (int8_t)a[0];
+				else write_resolution_allo(a, nd, initial ? draw_uniform_pick(m, allo_nres(nd)) : draw_resolution_allo(m, i, l), g);
+				if (!initial) {                                 /* change_geno_allo :1475: each pair ascending */
+					if (g[0] > g[1]) { int8_t t = g[0]; g[0] = g[1]; g[1] = t; }
+					if (g[2] > g[3]) { int8_t t = g[2]; g[2] = g[3]; g[3] = t; }
+				}
+				continue;
+			}
 			if (nd == 1) for (q = 0; q < 4; q++) g[q] = (int8_t)a[0];
 			else if (nd == 4) for (q = 0; q < 4; q++) g[q] = (int8_t)a[q];
 			else write_resolution(a, nd, initial ? draw_uniform_pick(m, 3) : draw_resolution(m, i, l), g);
@@ -562,6 +845,19 @@ void tet_update_P(tet_model *m)
 	int32_t *n = (int32_t *)malloc(sizeof(int32_t) * (size_t)m->K * m->L * m->Amax);
 	double *cnt = (double *)malloc(sizeof(double) * m->Amax);
 	int k, l, a;
+	if (!m->autopoly) {                                        /* update_P_allo, poly_geno.c:441-518 */
+		int32_t *n2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)m->K * m->L * m->Amax);
+		tet_tally_allo(m, n, n2);
+		for (k = 0; k < m->K; k++)
+			for (l = 0; l < m->L; l++) {
+				for (a = 0; a < m->allelenum[l]; a++) cnt[a] = (double)n[FO(m, k, l, a)];
+				orc_rng_dirichlet(&m->rng, cnt, m->allelenum[l], m->freq + FO(m, k, l, 0), 1.0);
+				for (a = 0; a < m->allelenum[l]; a++) cnt[a] = (double)n2[FO(m, k, l, a)];
+				orc_rng_dirichlet(&m->rng, cnt, m->allelenum[l], m->freq2 + FO(m, k, l, 0), 1.0);
+			}
+		free(n); free(n2); free(cnt);
+		return;
+	}
 	tet_tally(m, n);
 	for (k = 0; k < m->K; k++)
 		for (l = 0; l < m->L; l++) {

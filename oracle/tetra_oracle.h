@@ -24,6 +24,13 @@
 typedef struct tet_model tet_model;
 
 tet_model *tet_new(int N, int L, int K, int back_refl, const int16_t *x, const uint8_t *nd, const int32_t *allelenum);
+/* autopoly = 0: the ALLOTETRAPLOID model (-ap 0): two subgenomes (copies 0,1 / copies 2,3) with their own
+ * allele frequencies freq / freq2; update_P_allo :441, calc_exfreq_allo :1592, allo_genfreq :2122,
+ * choose_two/tri/tetra_allo :962-1215.  Pinned bit for bit like the autotetraploid path. */
+tet_model *tet_new2(int N, int L, int K, int back_refl, int autopoly, const int16_t *x, const uint8_t *nd, const int32_t *allelenum);
+double *tet_freq2(tet_model *m);
+void tet_tally_allo(const tet_model *m, int32_t *n1, int32_t *n2);
+int tet_geno_conditional_allo(const tet_model *m, int i, int l, double *prob /*[12]*/);
 void tet_free(tet_model *m);
 void tet_setseeds(tet_model *m, long a, long b, long c);
 
