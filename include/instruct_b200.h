@@ -118,7 +118,10 @@ typedef enum ig_state_id {
 	IG_STATE_EXFREQ = 18,      /* POLY.exfreq                                                       */
 	IG_STATE_SPROP = 19,   /* double [K]               proposed selfing rates of the current sweep    */
 	IG_STATE_DSTAT = 20,   /* double [K]               cal_lkd_props(k) - cal_lkd() (get only)        */
-	IG_STATE_GMAX = 21     /* int32  [1]               genotypes in the largest catalogue (get only)  */
+	IG_STATE_GMAX = 21,    /* int32  [1]               genotypes in the largest catalogue (get only)  */
+	/* allotetraploid (-p 4 -ap 0) only: the second subgenome (copies 2,3), mcmc.h:16, poly_geno.c:441-518 */
+	IG_STATE_P2 = 22,      /* double [K][L][Amax]      UPMCMC.freq2                                  */
+	IG_STATE_TALLY2 = 23   /* int32  [K][L][Amax]      tally of copies 2,3 (get only)                 */
 } ig_state_id;
 
 /* sweep phases for ig_run_phase (test hook; ig_sweep runs them in the reference's order) */

@@ -19,6 +19,7 @@ IG_EMPTY_CLUSTER = 1
 STATE_X, STATE_Z, STATE_Q, STATE_P, STATE_ALPHA, STATE_S, STATE_G, STATE_INDVLKH, STATE_TOTALLKH, \
     STATE_TALLY, STATE_CNT, STATE_GPROP, STATE_STATE, STATE_MASK, STATE_GENO, STATE_ITER = range(16)
 STATE_TABLES, STATE_TABLES_PROP, STATE_EXFREQ, STATE_SPROP, STATE_DSTAT, STATE_GMAX = 16, 17, 18, 19, 20, 21
+STATE_P2, STATE_TALLY2 = 22, 23      # allotetraploid: second subgenome
 STATE_LLPARTS, STATE_GEOMETRY, STATE_FPROP, STATE_FK = 100, 101, 102, 103
 # ig_phase
 PHASE_UPDATE_P, PHASE_UPDATE_S, PHASE_ZQ, PHASE_ALPHA, PHASE_GENO = 1, 2, 4, 8, 16

@@ -334,6 +334,13 @@ ig_status ig_allgather_double(ig_ctx *c, double *buf, size_t per_rank)
 	return IG_OK;
 }
 
+ig_status ig_allreduce_int32(ig_ctx *c, int32_t *buf, size_t count)
+{
+	if (!c->comm) return IG_OK;
+	NCK(g_nccl.AllReduce(buf, buf, count, ncclInt32, ncclSum, c->comm, c->stream));
+	return IG_OK;
+}
+
 static ig_status exchange_tally(ig_ctx *c)
 {
 	// the one per-sweep reduction of the sharded mode: int32 n[L][A][K] summed over the shards

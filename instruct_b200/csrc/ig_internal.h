@@ -107,6 +107,7 @@ struct PArgs {
 	Geometry geo; uint32_t iter, key0, key1;
 	const uint32_t *iter_dev;
 	int mono_ok;             // 1: a locus with one allele gets P = 1 (update_P_auto has no allelenum > 1 guard, poly_geno.c:425)
+	int sub;                 // 1: the second subgenome of the allotetraploid model (its own random stream)
 };
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s);
 

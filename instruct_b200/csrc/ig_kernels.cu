@@ -46,7 +46,7 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 		for (int al = 0; al < g.A; al++) { a.P[base + (size_t)al * g.KP] = (a.mono_ok && k < g.K && Al == 1 && al == 0) ? 1.0f : 0.0f; a.n[base + (size_t)al * g.KP] = 0; }
 		return;
 	}
-	Stream st((uint32_t)l, (uint32_t)k, iter, TAG_P, a.key0, a.key1);
+	Stream st((uint32_t)l, (uint32_t)k + 256u * (uint32_t)a.sub, iter, TAG_P, a.key0, a.key1);
 	double sum = 0.0;
 	double gam[64];
 	// allelenum_max is small (2 for SNPs, tens for microsatellites); larger loci spill to a second pass
@@ -60,7 +60,7 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 		}
 	} else {
 		for (int al = 0; al < Al; al++) sum += draw_gamma(st, (double)a.n[base + (size_t)al * g.KP] + 1.0);
-		Stream st2((uint32_t)l, (uint32_t)k, iter, TAG_P, a.key0, a.key1);     // replay the same stream
+		Stream st2((uint32_t)l, (uint32_t)k + 256u * (uint32_t)a.sub, iter, TAG_P, a.key0, a.key1);     // replay the same stream
 		for (int al = 0; al < g.A; al++) {
 			const double p = (al < Al) ? draw_gamma(st2, (double)a.n[base + (size_t)al * g.KP] + 1.0) / sum : 0.0;
 			a.P[base + (size_t)al * g.KP] = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;

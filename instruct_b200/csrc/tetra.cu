@@ -68,6 +68,10 @@ struct TetraState {
 	double *dind = nullptr;           // [Npad][K] the same summed over chunks, all shards (all-gathered)
 	float *lpart = nullptr;           // [nchunks][2][Nloc] likelihood partials: natural-log part, log2 part
 	bool timing = false;              // a profiled sweep is between its PASS A start and PASS B end events
+	// allotetraploid (-ap 0): copies 0,1 and copies 2,3 are two subgenomes with their own allele frequencies
+	bool allo = false;
+	float *P2 = nullptr;              // UPMCMC.freq2, [Lpad][A][KP]
+	int32_t *n2 = nullptr;            // tally of the second subgenome, same indexing
 };
 
 // --------------------------------------------------------------------------------------
@@ -87,6 +91,18 @@ static void build_catalogue(int n, std::vector<int> &code, int cls[5])
 		code.push_back(a * (n3 + n2) + j * n + k);
 	}
 	for (int j = 0; j < n - 3; j++) for (int k = j + 1; k < n - 2; k++) for (int a = k + 1; a < n - 1; a++) for (int b = a + 1; b < n; b++)
+		code.push_back(j * n3 + k * n2 + a * n + b);
+}
+
+// allo_geno_num / allo_geno_list, poly_geno.c:2031-2120: iikk | iikl (k<l) | ijkk (i<j) | ijkl (i<j, k<l)
+static void build_catalogue_allo(int n, std::vector<int> &code, int cls[5])
+{
+	cls[0] = n * n; cls[1] = n * (n - 1) / 2 * n; cls[2] = n * (n - 1) / 2 * n; cls[3] = n * (n - 1) * n * (n - 1) / 4; cls[4] = 0;
+	const int n2 = n * n, n3 = n2 * n;
+	for (int j = 0; j < n; j++) for (int k = 0; k < n; k++) code.push_back(j * n2 * (n + 1) + k * (n + 1));
+	for (int j = 0; j < n; j++) for (int k = 0; k < n - 1; k++) for (int a = k + 1; a < n; a++) code.push_back(j * n2 * (n + 1) + n * k + a);
+	for (int j = 0; j < n - 1; j++) for (int k = j + 1; k < n; k++) for (int a = 0; a < n; a++) code.push_back((j * n + k) * n2 + a * (n + 1));
+	for (int j = 0; j < n - 1; j++) for (int k = j + 1; k < n; k++) for (int a = 0; a < n - 1; a++) for (int b = a + 1; b < n; b++)
 		code.push_back(j * n3 + k * n2 + a * n + b);
 }
 
@@ -120,6 +136,7 @@ struct TabArgs {
 	const float *P; const int32_t *allelenum; const int32_t *loc_cat; const TetraCat *cats; const int32_t *codes; const uint8_t *c2i;
 	const double *S, *Sprop; float *exf, *tabC, *tabP;
 	int L, K, KP, A, Gmax, do_cur, do_prop;
+	const float *P2; int allo;
 };
 
 // gaussj (poly_geno.c:2384) for the 3x3 float system of the triallelic class: Gauss-Jordan with
@@ -265,6 +282,67 @@ __device__ void genfreq_locus(float self, const TetraCat &c, const int32_t *code
 #undef IDX
 }
 
+// allo_genfreq, poly_geno.c:2122-2305: (I - sA) P = (1 - s) R solved class by class, from the doubly
+// heterozygous genotypes down; operation order and float / double mix of the reference
+__device__ void genfreq_locus_allo(float self, const TetraCat &c, const int32_t *code, const uint8_t *c2i, const float *R, float *P)
+{
+	const int n = c.n, n2 = n * n, n3 = n2 * n;
+#define IDX(cd) ((int)c2i[(cd)])
+	int tmp = c.total, num, d[3];
+	float temp;
+	for (int i = tmp - c.cls[3]; i < tmp; i++)                            // ijkl
+		P[i] = (float)(log((double)(1 - self)) + (double)R[i] - log((double)(1 - self / 4)));
+	tmp -= c.cls[3];
+	for (int i = tmp - c.cls[2]; i < tmp; i++) {                          // ijkk
+		num = code[i];
+		d[0] = num % n; num /= n2; d[1] = num % n; num /= n; d[2] = num % n;
+		temp = 0;
+		for (int j = 0; j < n; j++)
+			if (j != d[0]) {
+				num = (d[0] < j) ? IDX(d[2] * n3 + d[1] * n2 + d[0] * n + j) : IDX(d[2] * n3 + d[1] * n2 + j * n + d[0]);
+				temp = (float)((double)temp + exp((double)P[num]) * (double)self / 8.0);
+			}
+		P[i] = (float)(log((double)(1 - self) * exp((double)R[i]) + (double)temp) - log(1 - (double)self / 2.0));
+	}
+	tmp -= c.cls[2];
+	for (int i = tmp - c.cls[1]; i < tmp; i++) {                          // iikl
+		num = code[i];
+		d[0] = num % n; num /= n; d[1] = num % n; num /= n; d[2] = num % n;
+		temp = 0;
+		for (int j = 0; j < n; j++)
+			if (j != d[2]) {
+				num = (d[2] < j) ? IDX(d[2] * n3 + j * n2 + d[1] * n + d[0]) : IDX(j * n3 + d[2] * n2 + d[1] * n + d[0]);
+				temp = (float)((double)temp + exp((double)P[num]) * (double)self / 8.0);
+			}
+		P[i] = (float)(log((double)(1 - self) * exp((double)R[i]) + (double)temp) - log(1 - (double)self / 2.0));
+	}
+	tmp -= c.cls[1];
+	for (int i = tmp - c.cls[0]; i < tmp; i++) {                          // iikk
+		num = code[i];
+		d[0] = num % n; num /= n2; d[1] = num % n;
+		temp = 0;
+		for (int j = 0; j < n; j++)
+			if (j != d[0]) {
+				num = (d[0] < j) ? IDX(d[1] * n2 * (n + 1) + d[0] * n + j) : IDX(d[1] * n2 * (n + 1) + j * n + d[0]);
+				temp = (float)((double)temp + exp((double)P[num]) * (double)self / 4.0);
+			}
+		for (int j = 0; j < n; j++)
+			if (j != d[1]) {
+				num = (d[1] < j) ? IDX(d[1] * n3 + j * n2 + d[0] * (n + 1)) : IDX(j * n3 + d[1] * n2 + d[0] * (n + 1));
+				temp = (float)((double)temp + exp((double)P[num]) * (double)self / 4.0);
+			}
+		for (int j = 0; j < n; j++)
+			for (int kk = 0; kk < n; kk++)
+				if (j != d[1] && kk != d[0]) {
+					const int a0 = d[1] < j ? d[1] : j, a1 = d[1] < j ? j : d[1], b0 = d[0] < kk ? d[0] : kk, b1 = d[0] < kk ? kk : d[0];
+					num = IDX(a0 * n3 + a1 * n2 + b0 * n + b1);
+					temp = (float)((double)temp + exp((double)P[num]) * (double)self / 16.0);
+				}
+		P[i] = (float)(log((double)(1 - self) * exp((double)R[i]) + (double)temp) - log((double)(1 - self)));
+	}
+#undef IDX
+}
+
 __global__ void tetra_tables_kernel(const TabArgs a)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,6 +355,37 @@ __global__ void tetra_tables_kernel(const TabArgs a)
 	float *R = a.exf + (size_t)t * a.Gmax;
 	double lf[TETRA_MAX_A];
 	for (int al = 0; al < n; al++) lf[al] = log((double)a.P[((size_t)l * a.A + al) * a.KP + k]);
+	if (a.allo) {
+		// calc_exfreq_allo, poly_geno.c:1592-1671: subgenome 1 (copies 0,1) with freq, subgenome 2 with freq2
+		double lf2[TETRA_MAX_A];
+		for (int al = 0; al < n; al++) lf2[al] = log((double)a.P2[((size_t)l * a.A + al) * a.KP + k]);
+		int lo = 0, d[4], w;
+		for (int g = lo; g < lo + c.cls[0]; g++) { w = code[g]; d[0] = w % n; w /= (n * n); d[1] = w % n; R[g] = (float)((lf[d[1]] + lf2[d[0]]) * 2); }
+		lo += c.cls[0];
+		for (int g = lo; g < lo + c.cls[1]; g++) {
+			w = code[g];
+			for (int q = 0; q < 3; q++) { d[q] = w % n; w /= n; }
+			R[g] = (float)(log(2.0) + lf[d[2]] * 2 + lf2[d[0]] + lf2[d[1]]);
+		}
+		lo += c.cls[1];
+		for (int g = lo; g < lo + c.cls[2]; g++) {
+			w = code[g]; w /= n;
+			for (int q = 0; q < 3; q++) { d[q] = w % n; w /= n; }
+			R[g] = (float)(log(2.0) + lf2[d[0]] * 2 + lf[d[2]] + lf[d[1]]);
+		}
+		lo += c.cls[2];
+		for (int g = lo; g < lo + c.cls[3]; g++) {
+			w = code[g];
+			for (int q = 0; q < 4; q++) { d[q] = w % n; w /= n; }
+			float r = (float)log(4.0);
+			for (int q = 0; q < 2; q++) r += (float)lf2[d[q]];
+			for (int q = 2; q < 4; q++) r += (float)lf[d[q]];
+			R[g] = r;
+		}
+		if (a.do_cur) genfreq_locus_allo((float)a.S[k], c, code, c2i, R, a.tabC + (size_t)t * a.Gmax);
+		if (a.do_prop) genfreq_locus_allo((float)a.Sprop[k], c, code, c2i, R, a.tabP + (size_t)t * a.Gmax);
+		return;
+	}
 	// calc_exfreq_auto, poly_geno.c:1515-1577
 	int lo = 0, d[4], w;
 	for (int g = lo; g < lo + c.cls[0]; g++) R[g] = (float)lf[code[g] % n] * 4.0f;
@@ -736,6 +845,169 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 	}
 }
 
+// --------------------------------------------------------------------------------------
+// PASS B, allotetraploid (-ap 0): update_geno :524-548 with choose_two_allo :962 (7 resolutions),
+// choose_tri_allo :1043 (12), choose_tetra_allo :1144 (6); calc_genofq :1267-1283; tally of
+// update_P_allo :441-489 (copies 0,1 -> n, copies 2,3 -> n2).  A first, untuned version: same
+// thread mapping and shared-memory staging as the autotetraploid kernel, resolutions from a table.
+// --------------------------------------------------------------------------------------
+__constant__ int8_t ALLO_RES2[7][4] = {{0,0,0,1},{0,1,0,0},{0,0,1,1},{1,1,0,0},{0,1,1,1},{1,1,0,1},{0,1,0,1}};
+__constant__ int8_t ALLO_RES3[12][4] = {{0,0,1,2},{1,2,0,0},{1,1,0,2},{0,2,1,1},{2,2,0,1},{0,1,2,2},
+                                        {0,1,1,2},{1,2,0,1},{1,2,0,2},{0,2,1,2},{0,2,0,1},{0,1,0,2}};
+__constant__ int8_t ALLO_RES4[6][4] = {{0,1,2,3},{2,3,0,1},{0,2,1,3},{1,3,0,2},{0,3,1,2},{1,2,0,3}};
+
+struct GenoAlloArgs {
+	const int16_t *Xq; const int8_t *Zq; int8_t *Gq; const float *P, *P2; const float *Qf; const float *tab;
+	const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
+	int32_t *n, *n2; float *lpart;
+	Geometry geo; int Gmax; int init;
+	uint32_t iter, key0, key1;
+};
+
+template <int KP, int ROUNDS>
+__global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const GenoAlloArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bar;
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x, chunk = blockIdx.x, R = g.R;
+	const int l0 = chunk * g.TL, nl = min(g.TL, g.Lpad - l0), nmt = nl / TT, rowsz = g.A * KP;
+	float *Psm = reinterpret_cast<float *>(smem_raw);
+	float *P2sm = Psm + (size_t)g.TL * rowsz;
+	int *hist = reinterpret_cast<int *>(P2sm + (size_t)g.TL * rowsz);          // [2][TL][A][KP][R]
+	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)2 * g.TL * rowsz * R);
+	const int nbins = nl * rowsz;
+	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+	__syncthreads();
+	if (tid == 0) {
+		mbar_expect_tx(&bar, (uint32_t)nbins * 8u);
+		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
+		tma_bulk_g2s(P2sm, a.P2 + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
+	}
+	for (int j = tid; j < 2 * g.TL * rowsz * R; j += TETRA_THREADS) hist[j] = 0;
+	for (int j = tid; j < nl; j += TETRA_THREADS) {
+		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
+		locsm[j] = ci >= 0 ? make_int2(a.cats[ci].n, a.cats[ci].c2i_off) : make_int2(1, 0);
+	}
+	__syncthreads();
+	mbar_wait(&bar, 0);
+
+	const int Nloc = g.Nloc, mt0 = l0 / TT;
+	const int nsub_total = (Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
+	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
+	const uint32_t R4 = (uint32_t)R * 4u;
+	const uint32_t hist1_sa = smem_addr(hist) + (uint32_t)(tid & (R - 1)) * 4u;
+	const uint32_t hist2_sa = hist1_sa + (uint32_t)(g.TL * rowsz) * R4;
+	const float LOG2E = 1.4426950408889634f;
+
+	for (int sub = sub0; sub < sub1; ++sub) {
+		const int il = sub * TETRA_THREADS + tid;
+		if (il >= Nloc) continue;
+		float q[KP];
+#pragma unroll
+		for (int v = 0; v < KP / 4; v++) {
+			const float4 w = __ldg(reinterpret_cast<const float4 *>(a.Qf + (size_t)il * KP) + v);
+			q[4 * v] = w.x; q[4 * v + 1] = w.y; q[4 * v + 2] = w.z; q[4 * v + 3] = w.w;
+		}
+		const uint32_t ig_global = (uint32_t)(g.i0 + il);
+		const int4 *xp = reinterpret_cast<const int4 *>(a.Xq) + ((size_t)mt0 * Nloc + il) * 2;
+		const int4 *zp = reinterpret_cast<const int4 *>(a.Zq) + ((size_t)mt0 * Nloc + il);
+		int4 *gp = reinterpret_cast<int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
+		float ll_nat = 0.0f, ll_lg2 = 0.0f;
+		for (int mt = 0; mt < nmt; ++mt) {
+			const int4 xa = ldg_stream(xp + (size_t)mt * Nloc * 2), xb = ldg_stream(xp + (size_t)mt * Nloc * 2 + 1);
+			const int4 zv = ldg_stream(zp + (size_t)mt * Nloc);
+			const u32x4 rnd4 = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_GENO}, a.key0, a.key1);
+			const uint32_t rj[4] = {rnd4.x, rnd4.y, rnd4.z, rnd4.w};
+			const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+			const uint32_t zw[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
+			uint32_t gn[4];
+			float m_nat = 0.0f, m_lg2 = 0.0f;
+#pragma unroll 1
+			for (int j = 0; j < TT; ++j) {
+				gn[j] = 0xFFFFFFFFu;
+				int av[4];
+				av[0] = (int)(short)(xw[2 * j] & 0xFFFF); av[1] = xw[2 * j] >> 16; av[2] = (int)(short)(xw[2 * j + 1] & 0xFFFF); av[3] = xw[2 * j + 1] >> 16;
+				if (av[0] < 0) continue;
+				const int nd = 1 + (av[1] >= 0) + (av[2] >= 0) + (av[3] >= 0);
+				const int lj = mt * TT + j;
+				const int2 li = locsm[lj];
+				const int n = li.x;
+				const uint32_t z0 = zw[j] & 0xFFu, z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
+				const bool same = (zw[j] == z0 * 0x01010101u);
+				const float *tab = a.tab + ((size_t)(l0 + lj) * g.K + z0) * a.Gmax;
+				const uint8_t *c2i = a.c2i + li.y;
+				const float *Pl = Psm + lj * rowsz, *P2l = P2sm + lj * rowsz;
+				int g0, g1, g2, g3;
+				if (nd == 1) { g0 = g1 = g2 = g3 = av[0]; }
+				else {
+					const int nres = (nd == 2) ? 7 : (nd == 3 ? 12 : 6);
+					const int8_t (*RES)[4] = (nd == 2) ? ALLO_RES2 : (nd == 3 ? ALLO_RES3 : ALLO_RES4);
+					float w[12];
+					if (a.init) { for (int r = 0; r < nres; r++) w[r] = 0.0f; }           // choose_unif, poly_geno.c:842
+					else if (same) {
+						for (int r = 0; r < nres; r++) {
+							const int code = ((av[RES[r][0]] * n + av[RES[r][1]]) * n + av[RES[r][2]]) * n + av[RES[r][3]];
+							w[r] = __ldg(tab + c2i[code]) * LOG2E;
+						}
+					} else {
+						float lf[4], lf2[4];
+						for (int t = 0; t < nd; t++) {
+							const float *r1 = Pl + av[t] * KP, *r2 = P2l + av[t] * KP;
+							float f = 0.0f, f2 = 0.0f;
+#pragma unroll
+							for (int k = 0; k < KP; k++) { f = fmaf(q[k], r1[k], f); f2 = fmaf(q[k], r2[k], f2); }
+							lf[t] = lg2_fast(f); lf2[t] = lg2_fast(f2);
+						}
+						for (int r = 0; r < nres; r++) {
+							// the reference adds log 2 only where BOTH pairs are heterozygous, and never with four alleles
+							const bool both_het = (nd != 4) && (RES[r][0] != RES[r][1]) && (RES[r][2] != RES[r][3]);
+							w[r] = lf[RES[r][0]] + lf[RES[r][1]] + lf2[RES[r][2]] + lf2[RES[r][3]] + (both_het ? 1.0f : 0.0f);
+						}
+					}
+					float cum[12], run = 0.0f;
+					for (int r = 0; r < nres; r++) { run += ex2_fast(w[r] - w[0]); cum[r] = run; }
+					const float u = u01f(rj[j]) * run;
+					int pick = 0;
+					for (int r = 0; r < nres - 1; r++) pick += (u >= cum[r]) ? 1 : 0;
+					g0 = av[RES[pick][0]]; g1 = av[RES[pick][1]]; g2 = av[RES[pick][2]]; g3 = av[RES[pick][3]];
+				}
+				gn[j] = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+				if (a.init) continue;
+				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286, allotetraploid branch)
+				if (same) m_nat += __ldg(tab + c2i[((g0 * n + g1) * n + g2) * n + g3]);
+				else {
+					const int nhet = (g0 != g1) + (g2 != g3);                         // classes 1,2: log 2; class 3: log 4
+					m_nat += (float)nhet * 0.6931471805599453f;
+					m_lg2 += lg2_fast(Pl[g0 * KP + z0] * Pl[g1 * KP + z1]) + lg2_fast(P2l[g2 * KP + z2] * P2l[g3 * KP + z3]);
+				}
+				const uint32_t hrow = (uint32_t)(lj * g.A * KP) * R4;
+				red_inc(hist1_sa + hrow + (uint32_t)(g0 * KP + (int)z0) * R4);
+				red_inc(hist1_sa + hrow + (uint32_t)(g1 * KP + (int)z1) * R4);
+				red_inc(hist2_sa + hrow + (uint32_t)(g2 * KP + (int)z2) * R4);
+				red_inc(hist2_sa + hrow + (uint32_t)(g3 * KP + (int)z3) * R4);
+			}
+			*(gp + (size_t)mt * Nloc) = make_int4((int)gn[0], (int)gn[1], (int)gn[2], (int)gn[3]);
+			ll_nat += m_nat; ll_lg2 += m_lg2;
+		}
+		if (!a.init) {
+			a.lpart[((size_t)chunk * 2) * Nloc + il] = ll_nat;
+			a.lpart[((size_t)chunk * 2 + 1) * Nloc + il] = ll_lg2;
+		}
+	}
+	__syncthreads();
+	if (a.init) return;
+	for (int h2 = 0; h2 < 2; h2++) {
+		int32_t *ng = (h2 ? a.n2 : a.n) + (size_t)l0 * rowsz;
+		const int *hh = hist + (size_t)h2 * g.TL * rowsz * R;
+		for (int b = tid; b < nbins; b += TETRA_THREADS) {
+			int sacc = 0;
+			for (int r = 0; r < R; r++) sacc += hh[b * R + r];
+			if (sacc) atomicAdd(ng + b, sacc);
+		}
+	}
+}
+
 // indvlkh (cal_lkd :715): chunk partials in chunk order, one thread per individual
 __global__ void __launch_bounds__(32 * CG) tetra_indv_lkh_kernel(const float *lpart, double *ind, Geometry g)
 {
@@ -778,12 +1050,13 @@ __global__ void __launch_bounds__(RED1) tetra_lkh_kernel(const double *ind, DevS
 // (the threads of a warp share their loci, so un-replicated atomics would all collide), flushed
 // to n with one atomicAdd per non-empty bin.
 constexpr int TALLY_REP = 16;
-__global__ void __launch_bounds__(256) tetra_tally_kernel(const int8_t *Zq, const int8_t *Gq, int32_t *n, Geometry g, int LTq)
+__global__ void __launch_bounds__(256) tetra_tally_kernel(const int8_t *Zq, const int8_t *Gq, int32_t *n, int32_t *n2, Geometry g, int LTq)
 {
-	extern __shared__ int th[];                                    // [TT * A * KP][TALLY_REP]
+	extern __shared__ int th[];                                    // [TT * A * KP][TALLY_REP] (twice for the allotetraploid model)
 	const int mt = blockIdx.x, tid = threadIdx.x;
 	const int nb = TT * g.A * g.KP;
-	for (int b = tid; b < nb * TALLY_REP; b += blockDim.x) th[b] = 0;
+	const int nsub = n2 ? 2 : 1;
+	for (int b = tid; b < nsub * nb * TALLY_REP; b += blockDim.x) th[b] = 0;
 	__syncthreads();
 	const int rep = tid & (TALLY_REP - 1);
 	const int4 *zp = reinterpret_cast<const int4 *>(Zq) + (size_t)mt * g.Nloc;
@@ -798,7 +1071,7 @@ __global__ void __launch_bounds__(256) tetra_tally_kernel(const int8_t *Zq, cons
 #pragma unroll
 			for (int cpy = 0; cpy < 4; cpy++) {
 				const int a = (gw[j] >> (8 * cpy)) & 0xFF, z = (zw[j] >> (8 * cpy)) & 0xFF;
-				atomicAdd(&th[((j * g.A + a) * g.KP + z) * TALLY_REP + rep], 1);
+				atomicAdd(&th[(((n2 && cpy >= 2) ? nb : 0) + (j * g.A + a) * g.KP + z) * TALLY_REP + rep], 1);   // update_P_allo: copies 2,3 apart
 			}
 		}
 	}
@@ -808,13 +1081,19 @@ __global__ void __launch_bounds__(256) tetra_tally_kernel(const int8_t *Zq, cons
 		for (int r = 0; r < TALLY_REP; r++) sacc += th[b * TALLY_REP + r];
 		if (sacc) atomicAdd(&n[(size_t)mt * TT * g.A * g.KP + b], sacc);
 	}
+	if (n2)
+		for (int b = tid; b < nb; b += blockDim.x) {
+			int sacc = 0;
+			for (int r = 0; r < TALLY_REP; r++) sacc += th[(nb + b) * TALLY_REP + r];
+			if (sacc) atomicAdd(&n2[(size_t)mt * TT * g.A * g.KP + b], sacc);
+		}
 }
-static cudaError_t launch_tetra_tally(const int8_t *Zq, const int8_t *Gq, int32_t *n, const Geometry &g, int LTq, cudaStream_t s)
+static cudaError_t launch_tetra_tally(const int8_t *Zq, const int8_t *Gq, int32_t *n, int32_t *n2, const Geometry &g, int LTq, cudaStream_t s)
 {
-	const size_t sm = (size_t)TT * g.A * g.KP * TALLY_REP * sizeof(int);
+	const size_t sm = (size_t)TT * g.A * g.KP * TALLY_REP * sizeof(int) * (n2 ? 2 : 1);
 	cudaError_t e = cudaFuncSetAttribute(tetra_tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
 	if (e != cudaSuccess) return e;
-	tetra_tally_kernel<<<LTq, 256, sm, s>>>(Zq, Gq, n, g, LTq);
+	tetra_tally_kernel<<<LTq, 256, sm, s>>>(Zq, Gq, n, n2, g, LTq);
 	return cudaGetLastError();
 }
 
@@ -839,7 +1118,7 @@ __global__ void tetra_init_scalars_kernel(DevScalars *sc, double *S, const float
 // --------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------
-static cudaError_t tetra_configure(Geometry &g, int device)
+static cudaError_t tetra_configure(Geometry &g, int device, bool allo)
 {
 	int sms = 148, smem_optin = 227 * 1024;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -849,7 +1128,7 @@ static cudaError_t tetra_configure(Geometry &g, int device)
 	const int R = 4;
 	const size_t fixedA = (size_t)2 * g.KP * TETRA_THREADS * 4 + 2048;
 	const size_t budget = (size_t)smem_optin / 2 - 1024;
-	int tl = (int)((budget - fixedA) / (per_locus * (1 + R) + 8));
+	int tl = (int)((budget - fixedA) / (per_locus * (1 + R) * (allo ? 2 : 1) + 8));     // allotetraploid: two P chunks, two histograms
 	tl = tl / TT * TT;
 	if (tl < TT) return cudaErrorInvalidConfiguration;
 	if (tl > 256) tl = 256;
@@ -869,6 +1148,7 @@ static cudaError_t tetra_configure(Geometry &g, int device)
 }
 static size_t smem_zs(const Geometry &g) { return (size_t)g.TL * g.A * g.KP * 4 + (size_t)2 * g.KP * TETRA_THREADS * 4 + (size_t)g.TL * 8; }
 static size_t smem_geno(const Geometry &g) { return (size_t)g.TL * g.A * g.KP * 4 * (1 + g.R) + (size_t)g.TL * 8; }
+static size_t smem_geno_allo(const Geometry &g) { return (size_t)2 * g.TL * g.A * g.KP * 4 * (1 + g.R) + (size_t)g.TL * 8; }
 
 }  // namespace ig
 
@@ -876,11 +1156,12 @@ using namespace ig;
 
 ig_status tetra_create(ig_ctx *c)
 {
-	if (c->cfg.autopoly != 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4: only the autotetraploid model (-ap 1) is built");
+	if (c->cfg.autopoly != 1 && c->cfg.autopoly != 0) return fail(IG_ERR_ARG, "ploid 4: autopoly must be 1 (autotetraploid) or 0 (allotetraploid)");
 	if (c->cfg.back_refl != 1) return fail(IG_ERR_UNSUPPORTED, "ploid 4 needs -e 1: with -e 0 the reference's genotype tables are log(0)");
 	c->tetra = new TetraState();
 	Geometry &g = c->geo;
 	TetraState *t = c->tetra;
+	t->allo = (c->cfg.autopoly == 0);
 	t->Lq = (g.L + TT - 1) / TT * TT;
 	t->LTq = t->Lq / TT;
 	g.Lpad = t->Lq;
@@ -895,7 +1176,7 @@ void tetra_destroy(ig_ctx *c)
 	if (!t) return;
 	cudaFree(t->Xq); cudaFree(t->Zq); cudaFree(t->Gq); cudaFree(t->cats); cudaFree(t->codes); cudaFree(t->c2i); cudaFree(t->loc_cat);
 	cudaFree(t->exf); cudaFree(t->tabC); cudaFree(t->tabP); cudaFree(t->Sprop); cudaFree(t->dstat); cudaFree(t->accepted);
-	cudaFree(t->dpart); cudaFree(t->dind); cudaFree(t->lpart);
+	cudaFree(t->dpart); cudaFree(t->dind); cudaFree(t->lpart); cudaFree(t->P2); cudaFree(t->n2);
 	delete t;
 	c->tetra = nullptr;
 }
@@ -917,6 +1198,8 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	int amax = 1;
 	for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] > amax) amax = c->allelenum_h[l];
 	if (amax > TETRA_MAX_A) return fail(IG_ERR_UNSUPPORTED, "ploid 4: allelenum_max %d > %d", amax, TETRA_MAX_A);
+	// the code -> index tables hold one byte per genotype: 441 allotetraploid genotypes at 6 alleles do not fit
+	if (t->allo && amax > 5) return fail(IG_ERR_UNSUPPORTED, "allotetraploid: allelenum_max %d > 5", amax);
 	g.A = amax < 2 ? 2 : amax;
 	// catalogues, one per distinct allele count
 	std::vector<int> codes;
@@ -930,7 +1213,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 		TetraCat &cat = t->cat_h[t->ncat];
 		cat.n = n; cat.code_off = (int)codes.size(); cat.c2i_off = (int)c2i.size();
 		std::vector<int> cd;
-		build_catalogue(n, cd, cat.cls);
+		if (t->allo) build_catalogue_allo(n, cd, cat.cls); else build_catalogue(n, cd, cat.cls);
 		cat.total = (int)cd.size();
 		if (cat.total > t->Gmax) t->Gmax = cat.total;
 		c2i.resize(c2i.size() + (size_t)n * n * n * n, 255);
@@ -938,7 +1221,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 		for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] == n) loc_cat[l] = t->ncat;
 		t->ncat++;
 	}
-	CK(tetra_configure(g, c->cfg.device));
+	CK(tetra_configure(g, c->cfg.device, t->allo));
 	const size_t tiles = (size_t)t->LTq * g.Nloc * TT * 4;
 	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
 	const size_t tn = (size_t)t->Lq * g.K * t->Gmax;
@@ -952,6 +1235,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	CK(dalloc0(&t->Sprop, (size_t)MAX_K)); CK(dalloc0(&t->dstat, (size_t)MAX_K)); CK(dalloc0(&t->accepted, (size_t)MAX_K));
 	CK(dalloc0(&t->dpart, (size_t)g.nchunks * g.K * g.Nloc)); CK(dalloc0(&t->dind, (size_t)c->Npad * g.K)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * 2 * g.Nloc));
 	CK(dalloc0(&c->P, pn)); CK(dalloc0(&c->n, pn));
+	if (t->allo) { CK(dalloc0(&t->P2, pn)); CK(dalloc0(&t->n2, pn)); }
 	if (c->cfg.print_freq) CK(dalloc0(&c->P64, (size_t)g.K * g.L * g.A));
 	CK(dalloc0(&c->ind, (size_t)c->Npad * g.REC)); CK(dalloc0(&c->Qf, (size_t)g.Nloc * g.KP));
 	CK(dalloc0(&c->S, (size_t)MAX_K)); CK(dalloc0(&c->state, (size_t)MAX_K)); CK(dalloc0(&c->state2, (size_t)MAX_K)); CK(dalloc0(&c->sc, 1));
@@ -998,10 +1282,36 @@ static ig_status tetra_pass_a(ig_ctx *c, int init)
 	return IG_OK;
 }
 
+static ig_status tetra_pass_b_allo(ig_ctx *c, int init)
+{
+	TetraState *t = c->tetra;
+	const Geometry &g = c->geo;
+	GenoAlloArgs a{t->Xq, t->Zq, t->Gq, c->P, t->P2, c->Qf, t->tabC, t->loc_cat, t->cats, t->c2i, c->n, t->n2, t->lpart, g, t->Gmax, init,
+	               c->iter, c->key0, c->key1};
+	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
+	const size_t sm = smem_geno_allo(g);
+#define ALLO_LAUNCH(KPV)                                                                                                   \
+	do {                                                                                                               \
+		if (c->rounds == 10) { CK(opt_smem(tetra_geno_allo_kernel<KPV, 10>, sm)); tetra_geno_allo_kernel<KPV, 10><<<grid, block, sm, c->stream>>>(a); } \
+		else { CK(opt_smem(tetra_geno_allo_kernel<KPV, 7>, sm)); tetra_geno_allo_kernel<KPV, 7><<<grid, block, sm, c->stream>>>(a); }               \
+	} while (0)
+	switch (g.KP) {
+	case 4: ALLO_LAUNCH(4); break;
+	case 8: ALLO_LAUNCH(8); break;
+	default: ALLO_LAUNCH(16); break;
+	}
+#undef ALLO_LAUNCH
+	CK(cudaGetLastError());
+	if (t->timing && !init) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; t->timing = false; }
+	c->launches++;
+	return IG_OK;
+}
+
 static ig_status tetra_pass_b(ig_ctx *c, int init)
 {
 	TetraState *t = c->tetra;
 	const Geometry &g = c->geo;
+	if (t->allo) return tetra_pass_b_allo(c, init);
 	GenoArgs a{t->Xq, t->Zq, t->Gq, c->P, c->Qf, t->tabC, t->loc_cat, t->cats, t->c2i, c->n, t->lpart, g, t->Gmax, init, c->iter, c->key0, c->key1};
 	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
 	const size_t sm = smem_geno(g);
@@ -1023,7 +1333,8 @@ static ig_status tetra_tables(ig_ctx *c, int do_cur, int do_prop)
 {
 	TetraState *t = c->tetra;
 	const Geometry &g = c->geo;
-	TabArgs a{c->P, c->allelenum, t->loc_cat, t->cats, t->codes, t->c2i, c->S, t->Sprop, t->exf, t->tabC, t->tabP, g.L, g.K, g.KP, g.A, t->Gmax, do_cur, do_prop};
+	TabArgs a{c->P, c->allelenum, t->loc_cat, t->cats, t->codes, t->c2i, c->S, t->Sprop, t->exf, t->tabC, t->tabP, g.L, g.K, g.KP, g.A, t->Gmax, do_cur, do_prop,
+	          t->P2, t->allo ? 1 : 0};
 	tetra_tables_kernel<<<nb((size_t)g.L * g.K, 64), 64, 0, c->stream>>>(a);
 	CK(cudaGetLastError());
 	c->launches++;
@@ -1059,6 +1370,13 @@ static ig_status tetra_update_p(ig_ctx *c)
 	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, nullptr, 1};
 	CK(launch_p_dirichlet(a, c->stream));
 	c->launches++;
+	if (c->tetra->allo) {                          // update_P_allo, poly_geno.c:441-518: freq2 from the second subgenome's tally
+		TetraState *t = c->tetra;
+		if ((st = ig_allreduce_int32(c, t->n2, (size_t)c->geo.Lpad * c->geo.A * c->geo.KP)) != IG_OK) return st;
+		PArgs b{t->n2, t->P2, nullptr, c->allelenum, c->geo, c->iter, c->key0, c->key1, nullptr, 1, 1};
+		CK(launch_p_dirichlet(b, c->stream));
+		c->launches++;
+	}
 	return IG_OK;
 }
 
@@ -1130,7 +1448,8 @@ ig_status tetra_chain_init(ig_ctx *c, int32_t chain_id, const float *initd)
 	if ((st = tetra_pass_b(c, 1)) != IG_OK) return st;          // initial_geno, poly_geno.c:316 (uniform resolution)
 	if ((st = tetra_pass_a(c, 1)) != IG_OK) return st;          // update_ZQ(init_flag = 1): uniform z, :87
 	if ((st = tetra_q(c)) != IG_OK) return st;
-	CK(launch_tetra_tally(t->Zq, t->Gq, c->n, g, t->LTq, c->stream));
+	if (t->allo) CK(cudaMemsetAsync(t->n2, 0, (size_t)g.Lpad * g.A * g.KP * sizeof(int32_t), c->stream));
+	CK(launch_tetra_tally(t->Zq, t->Gq, c->n, t->n2, g, t->LTq, c->stream));
 	CK(cudaGetLastError());
 	c->launches++;
 	c->chain_ready = true;
@@ -1205,6 +1524,19 @@ ig_status tetra_get_state(ig_ctx *c, int32_t id, void *host, size_t bytes, bool 
 		if (bytes != 4) return fail(IG_ERR_ARG, "GMAX: expected 4 bytes");
 		*(int32_t *)host = t->Gmax;
 		return IG_OK;
+	case IG_STATE_P2: case IG_STATE_TALLY2: {
+		if (!t->allo) return fail(IG_ERR_ARG, "P2/TALLY2: allotetraploid model only");
+		const size_t pn = (size_t)g.Lpad * g.A * g.KP, el = (size_t)g.K * g.L * g.A;
+		if (bytes != el * (id == IG_STATE_P2 ? 8 : 4)) return fail(IG_ERR_ARG, "P2/TALLY2: expected %zu bytes, got %zu", el * (id == IG_STATE_P2 ? 8 : 4), bytes);
+		std::vector<uint32_t> h(pn);
+		CK(cudaMemcpy(h.data(), id == IG_STATE_P2 ? (const void *)t->P2 : (const void *)t->n2, pn * 4, cudaMemcpyDeviceToHost));
+		for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int al = 0; al < g.A; al++) {
+			const size_t src = ((size_t)l * g.A + al) * g.KP + k, dst = ((size_t)k * g.L + l) * g.A + al;
+			if (id == IG_STATE_P2) { float f; memcpy(&f, &h[src], 4); ((double *)host)[dst] = (double)f; }
+			else ((int32_t *)host)[dst] = (int32_t)h[src];
+		}
+		return IG_OK;
+	}
 	default:
 		*handled = false;
 		return IG_OK;
@@ -1234,7 +1566,8 @@ ig_status tetra_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes,
 		}
 		// n always mirrors (z, geno)
 		if (e == cudaSuccess) e = cudaMemsetAsync(c->n, 0, (size_t)g.Lpad * g.A * g.KP * 4, c->stream);
-		if (e == cudaSuccess) e = launch_tetra_tally(t->Zq, t->Gq, c->n, g, t->LTq, c->stream);
+		if (e == cudaSuccess && t->allo) e = cudaMemsetAsync(t->n2, 0, (size_t)g.Lpad * g.A * g.KP * 4, c->stream);
+		if (e == cudaSuccess) e = launch_tetra_tally(t->Zq, t->Gq, c->n, t->n2, g, t->LTq, c->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		cudaFree(tmp);
 		CK(e);
@@ -1244,6 +1577,16 @@ ig_status tetra_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes,
 		if (bytes != (size_t)g.K * 8) return fail(IG_ERR_ARG, "SPROP: expected %zu bytes", (size_t)g.K * 8);
 		CK(cudaMemcpy(t->Sprop, host, bytes, cudaMemcpyHostToDevice));
 		return IG_OK;
+	case IG_STATE_P2: {
+		if (!t->allo) return fail(IG_ERR_ARG, "P2: allotetraploid model only");
+		const size_t pn = (size_t)g.Lpad * g.A * g.KP;
+		if (bytes != (size_t)g.K * g.L * g.A * 8) return fail(IG_ERR_ARG, "P2: expected %zu bytes, got %zu", (size_t)g.K * g.L * g.A * 8, bytes);
+		std::vector<float> p(pn, 0.0f);
+		for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int al = 0; al < g.A; al++)
+			p[((size_t)l * g.A + al) * g.KP + k] = (float)((const double *)host)[((size_t)k * g.L + l) * g.A + al];
+		CK(cudaMemcpy(t->P2, p.data(), pn * 4, cudaMemcpyHostToDevice));
+		return IG_OK;
+	}
 	case IG_STATE_TABLES: {
 		// recompute exfreq and BOTH tables from the current P, S and S' (no proposal draw)
 		ig_status st = tetra_tables(c, 1, 1);

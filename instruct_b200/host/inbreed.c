@@ -312,7 +312,7 @@ int main(int argc, char **argv)
 	go.popdata = popdata; go.n_extra_col = n_extra_col; go.markername_flag = markername_flag; go.datafmt = data_fmt;
 	go.quiet = quiet_data;
 	if (ploid != 2 && ploid != 4) die("ploid must be 2 or 4");
-	if (ploid == 4 && autopoly != 1) die("-p 4 runs the autotetraploid model (-ap 1); the allotetraploid model is not built");
+	if (ploid == 4 && autopoly != 1 && autopoly != 0) die("-ap must be 1 (autotetraploid) or 0 (allotetraploid)");
 	if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
 	N = gs.totalsize; K = popnum; ns = ((mode == 3 || mode == 5) && ploid == 2) ? N : K;
 	/* mem_cal, InStruct.c:204-225 (the estimate is the reference's; kept for its two log lines) */

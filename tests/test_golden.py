@@ -85,3 +85,26 @@ def test_tetra_fixture():
     assert c["flag"] == int(g["flag"]) == 0
     for k in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
         np.testing.assert_allclose(np.asarray(c[k]), g[k], rtol=1e-12, atol=0, err_msg=k)
+
+
+def test_allo_fixture():
+    """Allotetraploid (-ap 0): catalogue, two-subgenome float tables and one whole chain against the
+    golden outputs of the reference's poly_geno.c (tools/make_golden.py allo)."""
+    from oracle.pytetra import TetraOracle
+    g = np.load(os.path.join(GOLD, "allo_chain.npz"))
+    K = int(g["K"])
+    o = TetraOracle(g["x"], g["nd"], g["allelenum"], K, autopoly=0)
+    for l in range(o.L):
+        assert np.array_equal(o.genolist(l), g["codes"][l][: len(o.genolist(l))])
+    o.freq[...] = g["freq"]
+    o.freq2[...] = g["freq2"]
+    o.self_rates[...] = g["S"]
+    o.tables()
+    np.testing.assert_allclose(o.exfreq, g["exfreq"], rtol=2e-7, atol=0)
+    np.testing.assert_allclose(o.genofreq, g["genofreq"], rtol=2e-7, atol=0)
+    o.setseeds(*[int(v) for v in g["seeds"]])
+    c = o.run_chain(update=int(g["kw_update"]), burnin=int(g["kw_burnin"]), thinning=int(g["kw_thinning"]),
+                    ckrep=int(g["kw_ckrep"]), initd=g["kw_initd"])
+    assert c["flag"] == int(g["flag"]) == 0
+    for k in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
+        np.testing.assert_allclose(np.asarray(c[k]), g[k], rtol=1e-12, atol=0, err_msg=k)

@@ -60,14 +60,15 @@ def test_cli_matches_reference_program(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built")
-def test_cli_tetraploid_matches_reference_program(tmp_path):
-    """`-p 4 -ap 1`: the one-line-per-individual tetraploid format, the autotetraploid driver and
-    the ploid-4 result tables, against the compiled reference on the same file."""
+@pytest.mark.parametrize("ap", [1, 0])
+def test_cli_tetraploid_matches_reference_program(tmp_path, ap):
+    """`-p 4 -ap 1` / `-ap 0`: the one-line-per-individual tetraploid format, the autotetraploid and
+    allotetraploid drivers and the ploid-4 result tables, against the compiled reference on the same file."""
     from instruct_b200.synth import make_tetra_dataset, write_reference_text_tetra
     d = make_tetra_dataset(N=80, L=16, K=2, A=4, miss=0.03, seed=31)
     data = str(tmp_path / "geno4.txt")
     write_reference_text_tetra(data, d.dosage, pop=d.pop)
-    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "4", "-ap", "1", "-u", "1200", "-b", "400", "-t", "5", "-c", "2",
+    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "4", "-ap", str(ap), "-u", "1200", "-b", "400", "-t", "5", "-c", "2",
              "-v", "2", "-g", "1", "-r", "10", "-pi", "0", "-s", "13", "4", "1972"]
     outs = {}
     for name, exe, extra in (("ref", REFBIN, []), ("gpu", INBREED, ["--quiet-data"])):
@@ -99,7 +100,10 @@ def test_cli_tetraploid_matches_reference_program(tmp_path):
         return np.array([_floats(ln)[0] for ln in t.decode(errors="ignore").split("\n") if "Posterior Mean" in ln])
     # each chain draws its own alpha once (poly_geno.c:386), so chains differ more than MCMC noise alone
     assert np.abs(np.sort(selfing(outs["ref"]).mean(0)) - np.sort(selfing(outs["gpu"]).mean(0))).max() < 0.15
-    assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < 0.03 * abs(loglik(outs["ref"]).mean())
+    # (the allotetraploid posterior moves ~6 % in log-likelihood across the alphas of the 12 reference chains of
+    # tests/golden/posterior_allo.npz; the alpha-paired comparison is tests/test_gpu_posterior.py)
+    tol = 0.03 if ap == 1 else 0.10
+    assert np.abs(loglik(outs["ref"]).mean() - loglik(outs["gpu"]).mean()) < tol * abs(loglik(outs["ref"]).mean())
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="reference binary not built")

@@ -99,6 +99,45 @@ def test_tetra_posterior_matches_reference_within_mcse():
     assert abs(dLL.mean()) < 0.005 * abs(g["LL"].mean()), msg
 
 
+def test_allo_posterior_matches_reference_within_mcse():
+    """Allotetraploid (-p 4 -ap 0): as the autotetraploid test above, against R chains of the reference's
+    allotetraploid driver (tests/golden/posterior_allo.npz), paired by each chain's fixed alpha."""
+    from instruct_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(GOLD), "posterior_allo.npz"))
+    K = int(g["K"])
+    R = g["S"].shape[0]
+    update, burnin, thinning = int(g["update"]), int(g["burnin"]), int(g["thinning"])
+    sd = SeqData(g["x"], g["allelenum"], K, ploid=4, autopoly=0)
+    pop = g["pop"]
+    dS, dLL, dQ = [], [], []
+    for rep in range(R):
+        s = Sampler(sd, seed=3000 + rep)
+        s.chain_init(rep, initd=[0.3 + 0.02 * rep, 0.6 - 0.02 * rep])
+        s.set(_lib.STATE_ALPHA, [float(g["alpha"][rep])])
+        accS, accQ, accL, n = np.zeros(K), np.zeros((s.N, K)), 0.0, 0
+        for step in range(update):
+            s.sweep(1)
+            if step >= burnin and (step + 1 - burnin) % thinning == 0:
+                accS += s.get(_lib.STATE_S); accQ += s.get(_lib.STATE_Q); accL += float(s.get(_lib.STATE_TOTALLKH)[0]); n += 1
+        s.close()
+        S, Q, LL = accS / n, accQ / n, accL / n
+        o = np.argsort(Q[pop == 0].mean(axis=0))[::-1]
+        dS.append(S[o] - g["S"][rep])
+        dLL.append(LL - g["LL"][rep])
+        dQ.append(Q[pop == 0][:, o[0]].mean() - g["Q"][rep][pop == 0][:, 0].mean())
+    dS, dLL, dQ = np.array(dS), np.array(dLL), np.array(dQ)
+
+    def z(d):
+        d = np.asarray(d, float)
+        return d.mean(axis=0) / np.maximum(d.std(axis=0, ddof=1) / np.sqrt(len(d)), 1e-12)
+    msg = f"dS={dS.mean(0)} zS={z(dS)} dLL={dLL.mean()} zLL={z(dLL)} dQ={dQ.mean()} zQ={z(dQ)}"
+    assert np.all(np.abs(z(dS)) < 3.5), msg
+    assert abs(z(dLL)) < 3.5, msg
+    assert abs(z(dQ)) < 3.5, msg
+    assert np.all(np.abs(dS.mean(0)) < 0.03), msg
+    assert abs(dLL.mean()) < 0.005 * abs(g["LL"].mean()), msg
+
+
 def test_mode1_posterior_matches_reference_within_mcse():
     """Mode 1 (admixture without selfing, the CLI default): posterior Q and log-likelihood of the GPU
     chains against R independent chains of the compiled reference (tests/golden/posterior_mode1.npz)."""

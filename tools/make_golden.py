@@ -18,6 +18,7 @@ Fixtures
   tetra_chain.npz     autotetraploid: genotype catalogues, float tables on an injected state and
                       the CHAIN moments of one short chain through mcmc_POP_tetra_selfing
   posterior_tetra.npz autotetraploid posterior means from R independent reference chains
+  allo_chain.npz / posterior_allo.npz   the same two for the allotetraploid model (-ap 0)
 """
 import os
 import sys
@@ -137,6 +138,40 @@ def tetra_fixtures(R=12):
                         alpha=np.array(alphas))
 
 
+def allo_fixtures(R=12):
+    """Allotetraploid (-p 4 -ap 0) through the same harness: catalogue, tables with two subgenomes,
+    one whole chain, and the posterior target (poly_geno.c *_allo)."""
+    K = 3
+    d = make_tetra_dataset(N=36, L=10, K=K, A=4, miss=0.05, seed=41)
+    r = RefTetra(d.x, d.nd, d.allelenum, K, autopoly=0)
+    rng = np.random.default_rng(42)
+    f = rng.dirichlet(np.ones(r.Amax), size=(K, d.L))
+    f2 = rng.dirichlet(np.ones(r.Amax), size=(K, d.L))
+    S = rng.uniform(0.05, 0.95, size=K)
+    ex, gf = r.tables(f, S, freq2=f2)
+    r.setseeds(13, 4, 1972)
+    kw = dict(update=50, burnin=20, thinning=3, ckrep=4, initd=[0.3, 0.5, 0.7])
+    c = r.run_chain(**kw)
+    np.savez_compressed(os.path.join(OUT, "allo_chain.npz"), x=d.x, nd=d.nd, allelenum=d.allelenum, K=K, freq=f, freq2=f2, S=S,
+                        exfreq=ex, genofreq=gf, codes=np.stack([r.genolist(l) for l in range(d.L)]), seeds=[13, 4, 1972],
+                        **{f"kw_{k}": v for k, v in kw.items()}, **{k: np.asarray(v) for k, v in c.items()})
+    K = 2
+    d = make_tetra_dataset(N=120, L=30, K=K, A=4, miss=0.02, seed=43)
+    Ss, Qm, LL, alphas = [], [], [], []
+    for rep in range(R):
+        r = RefTetra(d.x, d.nd, d.allelenum, K, autopoly=0)
+        r.setseeds(13 + 7 * rep, 4 + 3 * rep, 1972 + 11 * rep)
+        s1, s2, s3 = (171 * (13 + 7 * rep)) % 30269, (172 * (4 + 3 * rep)) % 30307, (170 * (1972 + 11 * rep)) % 30323
+        alphas.append(10 * ((s1 / 30269.0 + s2 / 30307.0 + s3 / 30323.0) % 1.0))      # poly_geno.c:386, as above
+        c = r.run_chain(update=1500, burnin=500, thinning=5, ckrep=5, initd=[0.3 + 0.02 * rep, 0.6 - 0.02 * rep])
+        o = np.argsort(c["qq"][d.pop == 0].mean(axis=0))[::-1]
+        Ss.append(c["self_rates"][o]); Qm.append(c["qq"][:, o]); LL.append(c["totallkh"])
+        print("allo posterior rep", rep, c["self_rates"][o], c["totallkh"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "posterior_allo.npz"), x=d.x, nd=d.nd, allelenum=d.allelenum, K=K, S=np.array(Ss),
+                        Q=np.array(Qm).astype(np.float32), LL=np.array(LL), pop=d.pop, update=1500, burnin=500, thinning=5,
+                        alpha=np.array(alphas))
+
+
 def posterior_mode0_fixture(R=10):
     """Mode 0 (mcmc_POP_no_admixture, mcmc.c:90): whole-individual assignment; CHAIN.z / steps."""
     K = 2
@@ -191,6 +226,10 @@ if __name__ == "__main__":
         os.makedirs(OUT, exist_ok=True)
         tetra_fixtures()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "allo":
+        os.makedirs(OUT, exist_ok=True)
+        allo_fixtures()
+        sys.exit(0)
     os.makedirs(OUT, exist_ok=True)
     state_fixture(2, 3, 0.0, 1)
     state_fixture(5, 6, 0.06, 2)
@@ -207,3 +246,4 @@ if __name__ == "__main__":
     posterior_fixture()
     posterior_mode1_fixture()
     tetra_fixtures()
+    allo_fixtures()
