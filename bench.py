@@ -12,7 +12,9 @@ target is quoted on, and it fits one GPU (4 GB genotype store + 2 GB Z).
 N > 1 (torchrun, one rank per GPU): ``--shard individuals`` (default) shards the individuals
 of the ONE chain over the ranks -- strong scaling, one int32 NCCL all-reduce of n[L][A][K] and
 one all-gather of the per-individual records per sweep; ``--shard chains`` runs one
-independent chain per rank (weak scaling, no communication).
+independent chain per rank (weak scaling, no communication); ``--shard groups --group-size G`` runs
+N/G independent chains, each sharded over G GPUs with its own NCCL communicator (BASELINE.json
+configs[4]: ``--workload c5 --gpus 8 --shard groups --group-size 2`` = 4 chains x 2 GPUs each).
 
 Output: ONE JSON line on rank 0 (see README / DESIGN.md for the keys).
 """
@@ -234,7 +236,7 @@ def run_ours(args):
     import torch
 
     from instruct_b200 import Sampler, SeqData, _lib
-    from instruct_b200.shard import shard_bounds, broadcast_unique_id
+    from instruct_b200.shard import shard_bounds, broadcast_unique_id, group_layout, make_groups
     from instruct_b200.synth import make_dataset_torch, make_tetra_dataset_torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,10 +258,18 @@ def run_ours(args):
         L = args.L
     tetra = args.workload in TETRA
     ploid = 4 if tetra else 2
-    shard_ind = world > 1 and args.shard == "individuals"
+    shard_ind = world > 1 and args.shard in ("individuals", "groups")
+    # --shard groups: world / G independent chains, each with its individuals sharded over G GPUs and its own
+    # NCCL communicator (the composition SURVEY.md section 8e names for configs[4]: 4 chains x 2 GPUs)
+    gsz = world if args.shard == "individuals" else max(1, min(args.group_size, world))
+    if shard_ind and world % gsz:
+        raise SystemExit(f"--group-size {gsz} does not divide the {world} ranks")
+    chain_of_rank, grp = rank, None
     if shard_ind:
-        b, e = shard_bounds(N, world, rank)
-        nloc, i0, count, srank, seed_data = e - b, b, world, rank, 4
+        chain_of_rank, srank, _ = group_layout(world, rank, gsz)
+        b, e = shard_bounds(N, gsz, srank)
+        nloc, i0, count, seed_data = e - b, b, gsz, 4 + chain_of_rank
+        grp = make_groups(world, rank, gsz)
     else:
         nloc, i0, count, srank, seed_data = N, 0, 1, 0, 4 + rank
     if tetra:
@@ -281,9 +291,9 @@ def run_ours(args):
     s = Sampler(sd, seed=args.seed, device=local, shard_rank=srank, shard_count=count, totalsize=N,
                 rng_rounds=args.rng_rounds, x_device_ptr=x.data_ptr(), allelenum_device_ptr=an.data_ptr())
     if shard_ind:
-        uid = broadcast_unique_id(Sampler.unique_id, rank)
+        uid = broadcast_unique_id(Sampler.unique_id, rank, src=chain_of_rank * gsz, group=grp)
         s.comm_init(uid)
-    s.chain_init(0 if shard_ind else rank, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
+    s.chain_init(chain_of_rank, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
     s.sweep(args.warmup)
     s.sync()
     # per-launch events around the dominant kernel ride inside the timed region for the HBM-sized
@@ -309,7 +319,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         nz, zq_ms, _ = s.profile_read()
     if dist is not None:
-        t = torch.tensor([ms, copies_local if not shard_ind else 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, 0.0], device=dev, dtype=torch.float64)
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         tot = torch.tensor([copies_local], device=dev, dtype=torch.float64)
@@ -364,10 +374,11 @@ def run_ours(args):
         line = {
             "metric": "genotype_copy_updates_per_sec", "value": value, "unit": "copy-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if (shard_ind or world == 1) else "weak", "vs_baseline": None, "dtype": "f32",
+            "scaling": "strong" if (world == 1 or (shard_ind and gsz == world)) else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "sweeps_per_sec": sweeps_per_s,
             "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + ("autotetraploid" if tetra else f"diploid mode {mode}") + f" miss={miss}",
-                       "parallelism": ("individual-sharded x%d" % world) if shard_ind else ("chains x%d" % world),
+                       "parallelism": ("individual-sharded x%d" % world) if (shard_ind and gsz == world) else
+                                      (("%d chains x %d GPUs each (individual-sharded)" % (world // gsz, gsz)) if shard_ind else ("chains x%d" % world)),
                        "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel() * (2 if tetra else 1)) / 1e9),
                        "geometry": geo, "rng": f"philox4x32-{args.rng_rounds or 7} (Z draw), philox4x32-10 (all other draws)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -390,7 +401,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--shard", default="individuals", choices=["individuals", "chains"])
+    ap.add_argument("--shard", default="individuals", choices=["individuals", "chains", "groups"])
+    ap.add_argument("--group-size", type=int, default=2, help="--shard groups: GPUs per chain (BASELINE configs[4]: 4 chains x 2 GPUs)")
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--rng-rounds", type=int, default=0)
     ap.add_argument("--N", type=int, default=0)

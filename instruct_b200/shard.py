@@ -34,6 +34,31 @@ def chains_of_rank(chainnum: int, world: int, rank: int):
     return [c for c in range(chainnum) if c % world == rank]
 
 
+def group_layout(world: int, rank: int, group_size: int):
+    """Chains x shards composed (SURVEY.md section 8e, configs[4] "4 chains x 2 GPUs each"): ``world`` ranks
+    form world / group_size groups of consecutive ranks; each group runs ONE chain whose individuals are
+    sharded over the group's ranks.  Returns (chain index, shard rank inside the group, the group's ranks)."""
+    if group_size < 1 or world % group_size:
+        raise ValueError(f"group size {group_size} does not divide {world} ranks")
+    c = rank // group_size
+    return c, rank % group_size, list(range(c * group_size, (c + 1) * group_size))
+
+
+def make_groups(world: int, rank: int, group_size: int):
+    """torch.distributed sub-groups for group_layout(); every rank creates every group, in the same order
+    (a requirement of new_group).  Returns this rank's group (None when one group spans all ranks)."""
+    import torch.distributed as dist
+
+    if group_size == world:
+        return None
+    mine = None
+    for c in range(world // group_size):
+        g = dist.new_group(list(range(c * group_size, (c + 1) * group_size)))
+        if c == rank // group_size:
+            mine = g
+    return mine
+
+
 def broadcast_unique_id(make_id, rank: int, src: int = 0, group=None) -> bytes:
     """Rank ``src`` creates the 128-byte NCCL unique id, everybody receives it through
     torch.distributed (any backend)."""

@@ -3,6 +3,8 @@
 mode "cpu"  (gloo, no GPU): the host-side sharding logic -- shard bounds tile the individuals,
              the per-shard integer tallies all-reduce to the full tally (the exchange the
              library issues over NCCL per sweep), traces gather, the id broadcast works.
+mode "groups" (gloo, world 4): chains x shards composed -- two groups of two ranks, one communicator id
+             and one tally reduction per group.
 mode "gpu"  (nccl, >= 2 GPUs): a chain whose individuals are sharded over the ranks is
              BIT-IDENTICAL to the same chain on one GPU (counter-based RNG keyed on global
              indices + integer all-reduce + fixed-order reductions).
@@ -17,8 +19,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from instruct_b200.shard import (broadcast_unique_id, chains_of_rank, gather_traces, shard_bounds,  # noqa: E402
-                                 shard_genotypes)
+from instruct_b200.shard import (broadcast_unique_id, chains_of_rank, gather_traces, group_layout,  # noqa: E402
+                                 make_groups, shard_bounds, shard_genotypes)
 from instruct_b200.synth import make_dataset  # noqa: E402
 
 
@@ -50,6 +52,38 @@ def cpu_mode():
     dist.destroy_process_group()
 
 
+def groups_mode():
+    """world 4 = 2 chains x 2 ranks each (gloo): every group gets ITS OWN communicator id and reduces ITS OWN
+    chain's tallies; nothing crosses groups."""
+    from oracle.pyoracle import Oracle
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    G = 2
+    chain, srank, ranks = group_layout(world, rank, G)
+    assert ranks == [chain * G, chain * G + 1] and srank == rank - chain * G
+    grp = make_groups(world, rank, G)
+    uid = broadcast_unique_id(lambda: bytes([chain]) * 128, rank, src=ranks[0], group=grp)
+    assert uid == bytes([chain]) * 128
+    K = 3
+    d = make_dataset(N=61, L=11, K=K, A=3, miss=0.05, seed=10 + chain)       # one data set per chain
+    o = Oracle(d.x, d.allelenum, K)
+    o.z[...] = np.random.default_rng(chain).integers(0, K, size=o.z.shape)
+    b, e = shard_bounds(d.N, G, srank)
+    part = torch.from_numpy(o.tally(b, e).astype(np.int32))
+    dist.all_reduce(part, group=grp)
+    assert np.array_equal(part.numpy(), o.tally())
+    try:
+        group_layout(6, 0, 4)
+        raise AssertionError("group size must divide the world")
+    except ValueError:
+        pass
+    assert make_groups(2, 0, 2) is None if world == 2 else True
+    dist.barrier()
+    if rank == 0:
+        print("CPU_GROUPS_OK")
+    dist.destroy_process_group()
+
+
 def gpu_mode():
     from instruct_b200 import Sampler, SeqData, _lib
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
@@ -75,7 +109,8 @@ def gpu_mode():
             ok &= bool(np.array_equal(getattr(ch, name), getattr(c1, name)))
         ok &= ch.totallkh == c1.totallkh and ch.totallkh2 == c1.totallkh2 and bool(np.array_equal(cv, cv1))
         ok &= bool(np.array_equal(zloc, z1[:, b:e, :]))
-    ok &= _tetra_sharded(rank, world, local)
+    ok &= _tetra_sharded(rank, world, local, 1)
+    ok &= _tetra_sharded(rank, world, local, 0)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -83,23 +118,24 @@ def gpu_mode():
     dist.destroy_process_group()
 
 
-def _tetra_sharded(rank, world, local):
-    """Autotetraploid: the sharded chain (int32 tally all-reduce, per-individual S statistics and
-    records all-gathered, fixed-order reductions) is bit-identical to the one-GPU chain."""
+def _tetra_sharded(rank, world, local, autopoly):
+    """Auto- and allotetraploid: the sharded chain (int32 tally all-reduce -- two tallies for the
+    allotetraploid model --, per-individual S statistics and records all-gathered, fixed-order
+    reductions) is bit-identical to the one-GPU chain."""
     from instruct_b200 import Sampler, SeqData, _lib
     from instruct_b200.synth import make_tetra_dataset
     K = 3
     d = make_tetra_dataset(N=301, L=45, K=K, A=4, miss=0.04, seed=9)
     kw = dict(update=20, burnin=8, thinning=3, ckrep=4, seed=77)
     xs = shard_genotypes(d.x, world, rank)
-    s = Sampler(SeqData(xs, d.allelenum, K, ploid=4, autopoly=1), device=local, shard_rank=rank, shard_count=world, totalsize=d.N, **kw)
+    s = Sampler(SeqData(xs, d.allelenum, K, ploid=4, autopoly=autopoly), device=local, shard_rank=rank, shard_count=world, totalsize=d.N, **kw)
     s.comm_init(broadcast_unique_id(Sampler.unique_id, rank))
     ch, cv = s.run_chain(0, initd=[0.3, 0.5, 0.7])
     zloc, gloc = s.get(_lib.STATE_Z), s.get(_lib.STATE_GENO)
     s.close()
     ok = True
     if rank == 0:
-        s1 = Sampler(SeqData(d.x, d.allelenum, K, ploid=4, autopoly=1), device=local, **kw)
+        s1 = Sampler(SeqData(d.x, d.allelenum, K, ploid=4, autopoly=autopoly), device=local, **kw)
         c1, cv1 = s1.run_chain(0, initd=[0.3, 0.5, 0.7])
         z1, g1 = s1.get(_lib.STATE_Z), s1.get(_lib.STATE_GENO)
         s1.close()
@@ -114,4 +150,4 @@ def _tetra_sharded(rank, world, local):
 
 
 if __name__ == "__main__":
-    cpu_mode() if sys.argv[1] == "cpu" else gpu_mode()
+    {"cpu": cpu_mode, "groups": groups_mode, "gpu": gpu_mode}[sys.argv[1]]()

@@ -21,6 +21,11 @@ def test_gloo_world2_host_logic():
     assert "CPU_SHARD_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
+def test_gloo_world4_two_chains_of_two_shards():
+    out = _torchrun(4, "groups", 29513)
+    assert "CPU_GROUPS_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 @pytest.mark.gpu
 def test_nccl_sharded_chain_bit_identical():
     import instruct_b200
