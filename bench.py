@@ -41,8 +41,11 @@ WORKLOADS = {
     "tiny": (600, 256, 8, 2, 0.0, 2),
     "c5": (20_000, 20_000, 6, 4, 0.0, 2),       # configs[4]: autotetraploid (-p 4 -ap 1), per chain
     "tiny5": (500, 128, 6, 4, 0.0, 2),
+    "c5a": (20_000, 20_000, 6, 4, 0.0, 2),      # the configs[4] shape under the allotetraploid model (-p 4 -ap 0)
+    "tiny5a": (500, 128, 6, 4, 0.0, 2),
 }
-TETRA = {"c5", "tiny5"}
+TETRA = {"c5", "tiny5", "c5a", "tiny5a"}
+ALLO = {"c5a", "tiny5a"}
 
 
 def measured_traffic(workload, N, L):
@@ -181,7 +184,7 @@ def cpu_reference_sample_tetra(workload, steps, warmup, budget_s):
 
     def run(u):
         if kind == "reference":
-            e = pytetra.RefTetra(d.x, d.nd, d.allelenum, K)
+            e = pytetra.RefTetra(d.x, d.nd, d.allelenum, K, autopoly=0 if workload in ALLO else 1)
             e.setseeds(13, 4, 1972)
             devnull = os.open(os.devnull, os.O_WRONLY)
             saved = os.dup(1)
@@ -193,7 +196,7 @@ def cpu_reference_sample_tetra(workload, steps, warmup, budget_s):
                 return time.perf_counter() - t0
             finally:
                 os.dup2(saved, 1); os.close(devnull); os.close(saved)
-        e = pytetra.TetraOracle(d.x, d.nd, d.allelenum, K)
+        e = pytetra.TetraOracle(d.x, d.nd, d.allelenum, K, autopoly=0 if workload in ALLO else 1)
         t0 = time.perf_counter()
         e.run_chain(u, 1, 1, ckrep=1, initd=initd)
         return time.perf_counter() - t0
@@ -204,7 +207,7 @@ def cpu_reference_sample_tetra(workload, steps, warmup, budget_s):
     t2 = run(u2)
     done, dt = u2 - u1, max(t2 - t1, 1e-9)
     return {"value": copies * done / dt, "unit": "copy-updates/s", "cores": 1, "kind": kind,
-            "sample": f"autotetraploid N={d.N} L={d.L} K={K} A={A}: {done} sweeps in {dt:.2f} s (chains of {u1} and {u2} sweeps "
+            "sample": f"{'allo' if workload in ALLO else 'auto'}tetraploid N={d.N} L={d.L} K={K} A={A}: {done} sweeps in {dt:.2f} s (chains of {u1} and {u2} sweeps "
                       f"differenced; one chain of the reference is single-threaded)",
             "sweeps_per_sec_sample": done / dt, "ms_per_step": 1e3 * dt / done, "steps": done}
 
@@ -220,7 +223,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "strong" if args.shard == "individuals" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + ("autotetraploid" if args.workload in TETRA else f"diploid mode {mode}") + " (bounded sample, see cpu_baseline.sample)"},
+        "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + (("allotetraploid" if args.workload in ALLO else "autotetraploid") if args.workload in TETRA else f"diploid mode {mode}") + " (bounded sample, see cpu_baseline.sample)"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "copy-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -287,7 +290,7 @@ def run_ours(args):
     # carries the flags and the (L, Nloc, ploid) shape, through a zero-strided placeholder
     shape_only = np.lib.stride_tricks.as_strided(np.zeros(1, dtype=np.int16), shape=(L, nloc, ploid), strides=(0, 0, 0))
     sd = SeqData(shape_only, np.zeros(L, dtype=np.int32), K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0,
-                 alpha_dpm=2.0)
+                 alpha_dpm=2.0, autopoly=0 if args.workload in ALLO else 1)
     s = Sampler(sd, seed=args.seed, device=local, shard_rank=srank, shard_count=count, totalsize=N,
                 rng_rounds=args.rng_rounds, x_device_ptr=x.data_ptr(), allelenum_device_ptr=an.data_ptr())
     if shard_ind:
@@ -348,7 +351,7 @@ def run_ours(args):
         xh.copy_(x)
         torch.cuda.synchronize()
         sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0,
-                       alpha_dpm=2.0, nstep_check_empty_cluster=10 ** 9)
+                       alpha_dpm=2.0, nstep_check_empty_cluster=10 ** 9, autopoly=0 if args.workload in ALLO else 1)
         upd = args.steps + args.warmup
         # the call is made three times and the fastest one reported: cudaMalloc / cudaFree of the multi-GB buffers
         # stall for hundreds of ms now and then on these boxes (IG_TRACE=1 shows the stages), both times are kept
@@ -376,7 +379,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if (world == 1 or (shard_ind and gsz == world)) else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "sweeps_per_sec": sweeps_per_s,
-            "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + ("autotetraploid" if tetra else f"diploid mode {mode}") + f" miss={miss}",
+            "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + (("allotetraploid" if args.workload in ALLO else "autotetraploid") if tetra else f"diploid mode {mode}") + f" miss={miss}",
                        "parallelism": ("individual-sharded x%d" % world) if (shard_ind and gsz == world) else
                                       (("%d chains x %d GPUs each (individual-sharded)" % (world // gsz, gsz)) if shard_ind else ("chains x%d" % world)),
                        "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel() * (2 if tetra else 1)) / 1e9),

@@ -848,13 +848,72 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const Geno
 // --------------------------------------------------------------------------------------
 // PASS B, allotetraploid (-ap 0): update_geno :524-548 with choose_two_allo :962 (7 resolutions),
 // choose_tri_allo :1043 (12), choose_tetra_allo :1144 (6); calc_genofq :1267-1283; tally of
-// update_P_allo :441-489 (copies 0,1 -> n, copies 2,3 -> n2).  A first, untuned version: same
-// thread mapping and shared-memory staging as the autotetraploid kernel, resolutions from a table.
+// update_P_allo :441-489 (copies 0,1 -> n, copies 2,3 -> n2).  Same thread mapping and staging as
+// the autotetraploid kernel.  A resolution is a PRMT selector: nibble c = index into the observed
+// allele set of copy c, so that byte_perm(observed alleles, selector) IS the resolved genotype, and
+// dp4a(genotype, (n^3, n^2, n, 1)) its catalogue code.  The three lists are compile-time constants
+// and each observed-allele count runs its own fully unrolled path: no table in memory, no
+// dynamically indexed array.
 // --------------------------------------------------------------------------------------
-__constant__ int8_t ALLO_RES2[7][4] = {{0,0,0,1},{0,1,0,0},{0,0,1,1},{1,1,0,0},{0,1,1,1},{1,1,0,1},{0,1,0,1}};
-__constant__ int8_t ALLO_RES3[12][4] = {{0,0,1,2},{1,2,0,0},{1,1,0,2},{0,2,1,1},{2,2,0,1},{0,1,2,2},
-                                        {0,1,1,2},{1,2,0,1},{1,2,0,2},{0,2,1,2},{0,2,0,1},{0,1,0,2}};
-__constant__ int8_t ALLO_RES4[6][4] = {{0,1,2,3},{2,3,0,1},{0,2,1,3},{1,3,0,2},{0,3,1,2},{1,2,0,3}};
+#define ASEL(a, b, c, d) ((uint32_t)((a) | ((b) << 4) | ((c) << 8) | ((d) << 12)))
+template <int ND> struct AlloRes { static constexpr int N = (ND == 2) ? 7 : (ND == 3 ? 12 : 6); };
+template <int ND>
+__host__ __device__ constexpr uint32_t allo_sel(int r)
+{
+	// two_allele_allo, poly_geno.c:2465 | tri_allele_allo :2533 | tetra_allele_allo :2602
+	constexpr uint32_t S2[7] = {ASEL(0,0,0,1), ASEL(0,1,0,0), ASEL(0,0,1,1), ASEL(1,1,0,0), ASEL(0,1,1,1), ASEL(1,1,0,1), ASEL(0,1,0,1)};
+	constexpr uint32_t S3[12] = {ASEL(0,0,1,2), ASEL(1,2,0,0), ASEL(1,1,0,2), ASEL(0,2,1,1), ASEL(2,2,0,1), ASEL(0,1,2,2),
+	                             ASEL(0,1,1,2), ASEL(1,2,0,1), ASEL(1,2,0,2), ASEL(0,2,1,2), ASEL(0,2,0,1), ASEL(0,1,0,2)};
+	constexpr uint32_t S4[6] = {ASEL(0,1,2,3), ASEL(2,3,0,1), ASEL(0,2,1,3), ASEL(1,3,0,2), ASEL(0,3,1,2), ASEL(1,2,0,3)};
+	return ND == 2 ? S2[r < 7 ? r : 0] : (ND == 3 ? S3[r < 12 ? r : 0] : S4[r < 6 ? r : 0]);
+}
+#undef ASEL
+
+// One genotype with ND observed alleles (bytes of apack, ascending): draws the resolution, returns the
+// resolved genotype g0 | g1 << 8 | g2 << 16 | g3 << 24.
+template <int ND, int KP>
+__device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack, int init, bool same, const float *tab, const uint8_t *c2i,
+                                                 const float *Pl, const float *P2l, const float (&q)[KP], float u01)
+{
+	using RS = AlloRes<ND>;
+	constexpr int NR = RS::N;
+	const float LOG2E = 1.4426950408889634f;
+	float w[NR];
+	if (init) {                                                        // choose_unif, poly_geno.c:842
+#pragma unroll
+		for (int r = 0; r < NR; r++) w[r] = 0.0f;
+	} else if (same) {                                                 // population z's table at the resolution's genotype
+#pragma unroll
+		for (int r = 0; r < NR; r++) w[r] = __ldg(tab + c2i[__dp4a(__byte_perm(apack, 0u, allo_sel<ND>(r)), npack, 0u)]) * LOG2E;
+	} else {                                                           // admixture-averaged frequencies of the two subgenomes
+		float lf[ND], lf2[ND];
+#pragma unroll
+		for (int t = 0; t < ND; t++) {
+			const int al = (int)((apack >> (8 * t)) & 0xFFu);
+			const float *r1 = Pl + al * KP, *r2 = P2l + al * KP;
+			float f = 0.0f, f2 = 0.0f;
+#pragma unroll
+			for (int k = 0; k < KP; k++) { f = fmaf(q[k], r1[k], f); f2 = fmaf(q[k], r2[k], f2); }
+			lf[t] = lg2_fast(f); lf2[t] = lg2_fast(f2);
+		}
+#pragma unroll
+		for (int r = 0; r < NR; r++) {
+			const int i0 = allo_sel<ND>(r) & 3, i1 = (allo_sel<ND>(r) >> 4) & 3, i2 = (allo_sel<ND>(r) >> 8) & 3, i3 = (allo_sel<ND>(r) >> 12) & 3;
+			// the reference adds log 2 only where BOTH pairs are heterozygous, and never with four alleles
+			const bool both_het = (ND != 4) && (i0 != i1) && (i2 != i3);
+			w[r] = lf[i0] + lf[i1] + lf2[i2] + lf2[i3] + (both_het ? 1.0f : 0.0f);
+		}
+	}
+	float cum[NR];
+	cum[0] = 1.0f;
+#pragma unroll
+	for (int r = 1; r < NR; r++) cum[r] = cum[r - 1] + ex2_fast(w[r] - w[0]);
+	const float u = u01 * cum[NR - 1];
+	uint32_t sel = allo_sel<ND>(0);
+#pragma unroll
+	for (int r = 1; r < NR; r++) sel = (u >= cum[r - 1]) ? allo_sel<ND>(r) : sel;
+	return __byte_perm(apack, 0u, sel);
+}
 
 struct GenoAlloArgs {
 	const int16_t *Xq; const int8_t *Zq; int8_t *Gq; const float *P, *P2; const float *Qf; const float *tab;
@@ -875,7 +934,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 	float *Psm = reinterpret_cast<float *>(smem_raw);
 	float *P2sm = Psm + (size_t)g.TL * rowsz;
 	int *hist = reinterpret_cast<int *>(P2sm + (size_t)g.TL * rowsz);          // [2][TL][A][KP][R]
-	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)2 * g.TL * rowsz * R);
+	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)2 * g.TL * rowsz * R); // [TL] ((n^3, n^2, n, 1) bytes, c2i offset)
 	const int nbins = nl * rowsz;
 	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 	__syncthreads();
@@ -887,7 +946,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 	for (int j = tid; j < 2 * g.TL * rowsz * R; j += TETRA_THREADS) hist[j] = 0;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
-		locsm[j] = ci >= 0 ? make_int2(a.cats[ci].n, a.cats[ci].c2i_off) : make_int2(1, 0);
+		const int n = ci >= 0 ? a.cats[ci].n : 1;                              // n <= 5: n^3 fits a byte
+		locsm[j] = make_int2((n * n * n) | ((n * n) << 8) | (n << 16) | (1 << 24), ci >= 0 ? a.cats[ci].c2i_off : 0);
 	}
 	__syncthreads();
 	mbar_wait(&bar, 0);
@@ -898,7 +958,6 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 	const uint32_t R4 = (uint32_t)R * 4u;
 	const uint32_t hist1_sa = smem_addr(hist) + (uint32_t)(tid & (R - 1)) * 4u;
 	const uint32_t hist2_sa = hist1_sa + (uint32_t)(g.TL * rowsz) * R4;
-	const float LOG2E = 1.4426950408889634f;
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		const int il = sub * TETRA_THREADS + tid;
@@ -914,68 +973,46 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 		const int4 *zp = reinterpret_cast<const int4 *>(a.Zq) + ((size_t)mt0 * Nloc + il);
 		int4 *gp = reinterpret_cast<int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
 		float ll_nat = 0.0f, ll_lg2 = 0.0f;
+		int4 xa_n = ldg_stream(xp), xb_n = ldg_stream(xp + 1), zv_n = ldg_stream(zp);      // prefetch one micro-tile ahead
 		for (int mt = 0; mt < nmt; ++mt) {
-			const int4 xa = ldg_stream(xp + (size_t)mt * Nloc * 2), xb = ldg_stream(xp + (size_t)mt * Nloc * 2 + 1);
-			const int4 zv = ldg_stream(zp + (size_t)mt * Nloc);
+			const int4 xa = xa_n, xb = xb_n, zv = zv_n;
+			if (mt + 1 < nmt) {
+				xa_n = ldg_stream(xp + (size_t)(mt + 1) * Nloc * 2); xb_n = ldg_stream(xp + (size_t)(mt + 1) * Nloc * 2 + 1);
+				zv_n = ldg_stream(zp + (size_t)(mt + 1) * Nloc);
+			}
 			const u32x4 rnd4 = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_GENO}, a.key0, a.key1);
 			const uint32_t rj[4] = {rnd4.x, rnd4.y, rnd4.z, rnd4.w};
-			const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+			const uint32_t xw[8] = {(uint32_t)xa.x, (uint32_t)xa.y, (uint32_t)xa.z, (uint32_t)xa.w, (uint32_t)xb.x, (uint32_t)xb.y, (uint32_t)xb.z, (uint32_t)xb.w};
 			const uint32_t zw[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
 			uint32_t gn[4];
 			float m_nat = 0.0f, m_lg2 = 0.0f;
-#pragma unroll 1
+#pragma unroll
 			for (int j = 0; j < TT; ++j) {
 				gn[j] = 0xFFFFFFFFu;
-				int av[4];
-				av[0] = (int)(short)(xw[2 * j] & 0xFFFF); av[1] = xw[2 * j] >> 16; av[2] = (int)(short)(xw[2 * j + 1] & 0xFFFF); av[3] = xw[2 * j + 1] >> 16;
-				if (av[0] < 0) continue;
-				const int nd = 1 + (av[1] >= 0) + (av[2] >= 0) + (av[3] >= 0);
+				// distinct alleles ascending in int16, -1 padding; all -1 = missing (data_interface.c:636-650)
+				if (xw[2 * j] & 0x8000u) continue;
+				const int nd = 1 + ((xw[2 * j] & 0x80000000u) ? 0 : 1) + ((xw[2 * j + 1] & 0x8000u) ? 0 : 1) + ((xw[2 * j + 1] & 0x80000000u) ? 0 : 1);
+				const uint32_t apack = __byte_perm(xw[2 * j], xw[2 * j + 1], 0x6420);     // low bytes of the four int16
 				const int lj = mt * TT + j;
 				const int2 li = locsm[lj];
-				const int n = li.x;
-				const uint32_t z0 = zw[j] & 0xFFu, z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
+				const uint32_t npack = (uint32_t)li.x;
+				const uint32_t z0 = zw[j] & 0xFFu;
 				const bool same = (zw[j] == z0 * 0x01010101u);
 				const float *tab = a.tab + ((size_t)(l0 + lj) * g.K + z0) * a.Gmax;
 				const uint8_t *c2i = a.c2i + li.y;
 				const float *Pl = Psm + lj * rowsz, *P2l = P2sm + lj * rowsz;
-				int g0, g1, g2, g3;
-				if (nd == 1) { g0 = g1 = g2 = g3 = av[0]; }
-				else {
-					const int nres = (nd == 2) ? 7 : (nd == 3 ? 12 : 6);
-					const int8_t (*RES)[4] = (nd == 2) ? ALLO_RES2 : (nd == 3 ? ALLO_RES3 : ALLO_RES4);
-					float w[12];
-					if (a.init) { for (int r = 0; r < nres; r++) w[r] = 0.0f; }           // choose_unif, poly_geno.c:842
-					else if (same) {
-						for (int r = 0; r < nres; r++) {
-							const int code = ((av[RES[r][0]] * n + av[RES[r][1]]) * n + av[RES[r][2]]) * n + av[RES[r][3]];
-							w[r] = __ldg(tab + c2i[code]) * LOG2E;
-						}
-					} else {
-						float lf[4], lf2[4];
-						for (int t = 0; t < nd; t++) {
-							const float *r1 = Pl + av[t] * KP, *r2 = P2l + av[t] * KP;
-							float f = 0.0f, f2 = 0.0f;
-#pragma unroll
-							for (int k = 0; k < KP; k++) { f = fmaf(q[k], r1[k], f); f2 = fmaf(q[k], r2[k], f2); }
-							lf[t] = lg2_fast(f); lf2[t] = lg2_fast(f2);
-						}
-						for (int r = 0; r < nres; r++) {
-							// the reference adds log 2 only where BOTH pairs are heterozygous, and never with four alleles
-							const bool both_het = (nd != 4) && (RES[r][0] != RES[r][1]) && (RES[r][2] != RES[r][3]);
-							w[r] = lf[RES[r][0]] + lf[RES[r][1]] + lf2[RES[r][2]] + lf2[RES[r][3]] + (both_het ? 1.0f : 0.0f);
-						}
-					}
-					float cum[12], run = 0.0f;
-					for (int r = 0; r < nres; r++) { run += ex2_fast(w[r] - w[0]); cum[r] = run; }
-					const float u = u01f(rj[j]) * run;
-					int pick = 0;
-					for (int r = 0; r < nres - 1; r++) pick += (u >= cum[r]) ? 1 : 0;
-					g0 = av[RES[pick][0]]; g1 = av[RES[pick][1]]; g2 = av[RES[pick][2]]; g3 = av[RES[pick][3]];
-				}
-				gn[j] = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+				const float u01 = u01f(rj[j]);
+				uint32_t gpk;
+				if (nd == 1) gpk = (apack & 0xFFu) * 0x01010101u;
+				else if (nd == 2) gpk = allo_resolve<2, KP>(apack, npack, a.init, same, tab, c2i, Pl, P2l, q, u01);
+				else if (nd == 3) gpk = allo_resolve<3, KP>(apack, npack, a.init, same, tab, c2i, Pl, P2l, q, u01);
+				else gpk = allo_resolve<4, KP>(apack, npack, a.init, same, tab, c2i, Pl, P2l, q, u01);
+				gn[j] = gpk;
 				if (a.init) continue;
+				const int g0 = (int)(gpk & 0xFFu), g1 = (int)((gpk >> 8) & 0xFFu), g2 = (int)((gpk >> 16) & 0xFFu), g3 = (int)(gpk >> 24);
+				const uint32_t z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286, allotetraploid branch)
-				if (same) m_nat += __ldg(tab + c2i[((g0 * n + g1) * n + g2) * n + g3]);
+				if (same) m_nat += __ldg(tab + c2i[__dp4a(gpk, npack, 0u)]);
 				else {
 					const int nhet = (g0 != g1) + (g2 != g3);                         // classes 1,2: log 2; class 3: log 4
 					m_nat += (float)nhet * 0.6931471805599453f;
