@@ -701,7 +701,7 @@ __device__ __forceinline__ float ex2_fast(float x)            // MUFU.EX2
 // they are fp32 with MUFU.LG2 / MUFU.EX2: the weights carry ~1e-6 relative error (the z draw's fp32
 // weights carry as much), the likelihood sums stay inside the 1e-6 gate (tests/test_gpu_tetra.py).
 template <int KP, int ROUNDS>
-__global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_kernel(const GenoArgs a)
+__global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const GenoArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bar;
