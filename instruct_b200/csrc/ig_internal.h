@@ -51,6 +51,8 @@ struct Geometry {
 	int R;                   // smem histogram replicas
 	int fmode;               // 0: selfing generations (modes 1-3), 1: inbreeding coefficient per individual (mode 5), 2: per population (mode 4)
 	size_t zq_smem;          // dynamic shared memory bytes of zq_sweep
+	int tab_stage;           // ploid 4, PASS B: the chunk's genotype-frequency tables and the code -> index bytes are staged in shared memory
+	int c2i_bytes;           // ploid 4: size of the code -> index byte array (all catalogues)
 };
 
 struct ZQArgs {

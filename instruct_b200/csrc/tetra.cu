@@ -711,10 +711,22 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 	float *Psm = reinterpret_cast<float *>(smem_raw);
 	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);            // [TL][A][KP][R]
 	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)g.TL * rowsz * R);
+	// the chunk's slice of the genotype-frequency tables [TL][K][Gmax] (one more bulk copy) and the code -> index
+	// bytes: the same-population look-ups become shared-memory loads instead of dependent L1 / L2 round trips
+	float *tabsm = reinterpret_cast<float *>(locsm + g.TL);
+	uint8_t *c2ism = reinterpret_cast<uint8_t *>(tabsm + (size_t)g.TL * g.K * a.Gmax);
 	const int nbins = nl * rowsz;
+	const uint32_t tab_bytes = g.tab_stage ? (uint32_t)nl * (uint32_t)(g.K * a.Gmax) * 4u : 0u;
 	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 	__syncthreads();
-	if (tid == 0) { mbar_expect_tx(&bar, (uint32_t)nbins * 4u); tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar); }
+	if (tid == 0) {
+		mbar_expect_tx(&bar, (uint32_t)nbins * 4u + tab_bytes);
+		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
+		if (tab_bytes) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
+	}
+	if (g.tab_stage) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
+	const float *tabbase = g.tab_stage ? tabsm : a.tab + (size_t)l0 * g.K * a.Gmax;
+	const uint8_t *c2ibase = g.tab_stage ? c2ism : a.c2i;
 	for (int j = tid; j < nbins * R; j += TETRA_THREADS) hist[j] = 0;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
@@ -770,8 +782,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 				const int n = li.x, n2 = n * n;
 				const uint32_t z0 = zw[j] & 0xFFu;
 				const bool same = (zw[j] == z0 * 0x01010101u);
-				const float *tab = a.tab + ((size_t)(l0 + lj) * g.K + z0) * a.Gmax;
-				const uint8_t *c2i = a.c2i + li.y;
+				const float *tab = tabbase + (lj * g.K + (int)z0) * a.Gmax;
+				const uint8_t *c2i = c2ibase + li.y;
 				const float *Pl = Psm + lj * rowsz;
 				int g0, g1, g2, g3, cls;
 				if (nd == 1) { g0 = g1 = g2 = g3 = a0; cls = 0; }
@@ -784,7 +796,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 						int c0, c1, c2;
 						if (nd == 2) { c0 = a0 * n * (n2 + n + 1) + a1; c1 = a1 * n * (n2 + n + 1) + a0; c2 = (a0 * n2 + a1) * (n + 1); }
 						else { c0 = a0 * n2 * (n + 1) + a1 * n + a2; c1 = a1 * n2 * (n + 1) + a0 * n + a2; c2 = a2 * n2 * (n + 1) + a0 * n + a1; }
-						w0 = __ldg(tab + c2i[c0]) * LOG2E; w1 = __ldg(tab + c2i[c1]) * LOG2E; w2 = __ldg(tab + c2i[c2]) * LOG2E;
+						w0 = tab[c2i[c0]] * LOG2E; w1 = tab[c2i[c1]] * LOG2E; w2 = tab[c2i[c2]] * LOG2E;
 					} else {
 						const float *r0 = Pl + a0 * KP, *r1 = Pl + a1 * KP, *r2 = Pl + (nd == 3 ? a2 : a0) * KP;
 						float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
@@ -813,7 +825,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 				if (a.init) continue;
 				const uint32_t z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286)
-				if (same) m_nat += __ldg(tab + c2i[((g0 * n + g1) * n + g2) * n + g3]);
+				if (same) m_nat += tab[c2i[((g0 * n + g1) * n + g2) * n + g3]];
 				else {
 					// heterozygote multiplicities log 4, 6, 12, 24 (poly_geno.c:1262-1268)
 					m_nat += (cls == 0) ? 0.0f : (cls == 1 ? 1.3862943611198906f : (cls == 2 ? 1.791759469228055f : (cls == 3 ? 2.4849066497880004f : 3.1780538303479458f)));
@@ -884,7 +896,7 @@ __device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack,
 		for (int r = 0; r < NR; r++) w[r] = 0.0f;
 	} else if (same) {                                                 // population z's table at the resolution's genotype
 #pragma unroll
-		for (int r = 0; r < NR; r++) w[r] = __ldg(tab + c2i[__dp4a(__byte_perm(apack, 0u, allo_sel<ND>(r)), npack, 0u)]) * LOG2E;
+		for (int r = 0; r < NR; r++) w[r] = tab[c2i[__dp4a(__byte_perm(apack, 0u, allo_sel<ND>(r)), npack, 0u)]] * LOG2E;
 	} else {                                                           // admixture-averaged frequencies of the two subgenomes
 		float lf[ND], lf2[ND];
 #pragma unroll
@@ -935,14 +947,21 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 	float *P2sm = Psm + (size_t)g.TL * rowsz;
 	int *hist = reinterpret_cast<int *>(P2sm + (size_t)g.TL * rowsz);          // [2][TL][A][KP][R]
 	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)2 * g.TL * rowsz * R); // [TL] ((n^3, n^2, n, 1) bytes, c2i offset)
+	float *tabsm = reinterpret_cast<float *>(locsm + g.TL);                       // staged tables, as in tetra_geno_kernel
+	uint8_t *c2ism = reinterpret_cast<uint8_t *>(tabsm + (size_t)g.TL * g.K * a.Gmax);
 	const int nbins = nl * rowsz;
+	const uint32_t tab_bytes = g.tab_stage ? (uint32_t)nl * (uint32_t)(g.K * a.Gmax) * 4u : 0u;
 	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 	__syncthreads();
 	if (tid == 0) {
-		mbar_expect_tx(&bar, (uint32_t)nbins * 8u);
+		mbar_expect_tx(&bar, (uint32_t)nbins * 8u + tab_bytes);
 		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
 		tma_bulk_g2s(P2sm, a.P2 + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
+		if (tab_bytes) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
 	}
+	if (g.tab_stage) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
+	const float *tabbase = g.tab_stage ? tabsm : a.tab + (size_t)l0 * g.K * a.Gmax;
+	const uint8_t *c2ibase = g.tab_stage ? c2ism : a.c2i;
 	for (int j = tid; j < 2 * g.TL * rowsz * R; j += TETRA_THREADS) hist[j] = 0;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
@@ -998,8 +1017,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 				const uint32_t npack = (uint32_t)li.x;
 				const uint32_t z0 = zw[j] & 0xFFu;
 				const bool same = (zw[j] == z0 * 0x01010101u);
-				const float *tab = a.tab + ((size_t)(l0 + lj) * g.K + z0) * a.Gmax;
-				const uint8_t *c2i = a.c2i + li.y;
+				const float *tab = tabbase + (lj * g.K + (int)z0) * a.Gmax;
+				const uint8_t *c2i = c2ibase + li.y;
 				const float *Pl = Psm + lj * rowsz, *P2l = P2sm + lj * rowsz;
 				const float u01 = u01f(rj[j]);
 				uint32_t gpk;
@@ -1012,7 +1031,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 				const int g0 = (int)(gpk & 0xFFu), g1 = (int)((gpk >> 8) & 0xFFu), g2 = (int)((gpk >> 16) & 0xFFu), g3 = (int)(gpk >> 24);
 				const uint32_t z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286, allotetraploid branch)
-				if (same) m_nat += __ldg(tab + c2i[__dp4a(gpk, npack, 0u)]);
+				if (same) m_nat += tab[c2i[__dp4a(gpk, npack, 0u)]];
 				else {
 					const int nhet = (g0 != g1) + (g2 != g3);                         // classes 1,2: log 2; class 3: log 4
 					m_nat += (float)nhet * 0.6931471805599453f;
@@ -1155,7 +1174,7 @@ __global__ void tetra_init_scalars_kernel(DevScalars *sc, double *S, const float
 // --------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------
-static cudaError_t tetra_configure(Geometry &g, int device, bool allo)
+static cudaError_t tetra_configure(Geometry &g, int device, bool allo, int Gmax, int c2i_bytes)
 {
 	int sms = 148, smem_optin = 227 * 1024;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -1172,6 +1191,16 @@ static cudaError_t tetra_configure(Geometry &g, int device, bool allo)
 	int want = ((g.Lpad + target - 1) / target + TT - 1) / TT * TT;
 	if (want < TT) want = TT;
 	if (want < tl) tl = want;
+	// PASS B stages its chunk of the tables [TL][K][Gmax] and the code -> index bytes in shared memory when that
+	// leaves the chunk at (nearly) the length the grid wants; it runs 3 resident CTAs per SM (allotetraploid: 2)
+	g.tab_stage = 0;
+	g.c2i_bytes = c2i_bytes;
+	{
+		const size_t per_b = per_locus * (1 + R) * (allo ? 2 : 1) + 8 + (size_t)g.K * Gmax * 4;
+		const size_t bud_b = (size_t)smem_optin / (allo ? 2 : 3) - 1024 - (size_t)((c2i_bytes + 15) / 16 * 16);
+		int tl_s = (int)(bud_b / per_b) / TT * TT;
+		if (tl_s >= TT && 4 * tl_s >= 3 * tl) { g.tab_stage = 1; if (tl_s < tl) tl = tl_s; }
+	}
 	g.TL = tl;
 	g.nchunks = (g.Lpad + tl - 1) / tl;
 	const int nsub_total = (g.Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
@@ -1184,8 +1213,9 @@ static cudaError_t tetra_configure(Geometry &g, int device, bool allo)
 	return cudaSuccess;
 }
 static size_t smem_zs(const Geometry &g) { return (size_t)g.TL * g.A * g.KP * 4 + (size_t)2 * g.KP * TETRA_THREADS * 4 + (size_t)g.TL * 8; }
-static size_t smem_geno(const Geometry &g) { return (size_t)g.TL * g.A * g.KP * 4 * (1 + g.R) + (size_t)g.TL * 8; }
-static size_t smem_geno_allo(const Geometry &g) { return (size_t)2 * g.TL * g.A * g.KP * 4 * (1 + g.R) + (size_t)g.TL * 8; }
+static size_t smem_tab(const Geometry &g, int Gmax) { return g.tab_stage ? (size_t)g.TL * g.K * Gmax * 4 + (size_t)((g.c2i_bytes + 15) / 16 * 16) : 0; }
+static size_t smem_geno(const Geometry &g, int Gmax) { return (size_t)g.TL * g.A * g.KP * 4 * (1 + g.R) + (size_t)g.TL * 8 + smem_tab(g, Gmax); }
+static size_t smem_geno_allo(const Geometry &g, int Gmax) { return (size_t)2 * g.TL * g.A * g.KP * 4 * (1 + g.R) + (size_t)g.TL * 8 + smem_tab(g, Gmax); }
 
 }  // namespace ig
 
@@ -1258,7 +1288,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 		for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] == n) loc_cat[l] = t->ncat;
 		t->ncat++;
 	}
-	CK(tetra_configure(g, c->cfg.device, t->allo));
+	CK(tetra_configure(g, c->cfg.device, t->allo, t->Gmax, (int)c2i.size()));
 	const size_t tiles = (size_t)t->LTq * g.Nloc * TT * 4;
 	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
 	const size_t tn = (size_t)t->Lq * g.K * t->Gmax;
@@ -1326,7 +1356,7 @@ static ig_status tetra_pass_b_allo(ig_ctx *c, int init)
 	GenoAlloArgs a{t->Xq, t->Zq, t->Gq, c->P, t->P2, c->Qf, t->tabC, t->loc_cat, t->cats, t->c2i, c->n, t->n2, t->lpart, g, t->Gmax, init,
 	               c->iter, c->key0, c->key1};
 	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
-	const size_t sm = smem_geno_allo(g);
+	const size_t sm = smem_geno_allo(g, t->Gmax);
 #define ALLO_LAUNCH(KPV)                                                                                                   \
 	do {                                                                                                               \
 		if (c->rounds == 10) { CK(opt_smem(tetra_geno_allo_kernel<KPV, 10>, sm)); tetra_geno_allo_kernel<KPV, 10><<<grid, block, sm, c->stream>>>(a); } \
@@ -1351,7 +1381,7 @@ static ig_status tetra_pass_b(ig_ctx *c, int init)
 	if (t->allo) return tetra_pass_b_allo(c, init);
 	GenoArgs a{t->Xq, t->Zq, t->Gq, c->P, c->Qf, t->tabC, t->loc_cat, t->cats, t->c2i, c->n, t->lpart, g, t->Gmax, init, c->iter, c->key0, c->key1};
 	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
-	const size_t sm = smem_geno(g);
+	const size_t sm = smem_geno(g, t->Gmax);
 	switch (g.KP) {
 	case 4: if (c->rounds == 10) { CK(opt_smem(tetra_geno_kernel<4, 10>, sm)); tetra_geno_kernel<4, 10><<<grid, block, sm, c->stream>>>(a); }
 	         else { CK(opt_smem(tetra_geno_kernel<4, 7>, sm)); tetra_geno_kernel<4, 7><<<grid, block, sm, c->stream>>>(a); } break;
