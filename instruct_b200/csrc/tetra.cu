@@ -785,9 +785,10 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 				const float *tab = tabbase + (lj * g.K + (int)z0) * a.Gmax;
 				const uint8_t *c2i = c2ibase + li.y;
 				const float *Pl = Psm + lj * rowsz;
-				int g0, g1, g2, g3, cls;
-				if (nd == 1) { g0 = g1 = g2 = g3 = a0; cls = 0; }
-				else if (nd == 4) { g0 = a0; g1 = a1; g2 = a2; g3 = a3; cls = 4; }
+				int g0, g1, g2, g3;
+				float lmul;                                                        // heterozygote multiplicities log 4, 6, 12, 24 (poly_geno.c:1262-1268)
+				if (nd == 1) { g0 = g1 = g2 = g3 = a0; lmul = 0.0f; }
+				else if (nd == 4) { g0 = a0; g1 = a1; g2 = a2; g3 = a3; lmul = 3.1780538303479458f; }
 				else {
 					// ---- three dosage resolutions (choose_two_auto :854, choose_tri_auto :907), weights in log2
 					float w0, w1, w2;
@@ -814,11 +815,11 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 					if (nd == 2) {
 						const int major = (pick == 1) ? a1 : a0, minor = (pick == 1) ? a0 : a1;
 						g0 = major; g1 = major; g2 = (pick == 2) ? minor : major; g3 = minor;
-						cls = (pick == 2) ? 2 : 1;
+						lmul = (pick == 2) ? 1.791759469228055f : 1.3862943611198906f;
 					} else {
 						const int dbl = (pick == 0) ? a0 : (pick == 1 ? a1 : a2);
 						g0 = dbl; g1 = dbl; g2 = (pick == 0) ? a1 : a0; g3 = (pick == 2) ? a1 : a2;
-						cls = 3;
+						lmul = 2.4849066497880004f;
 					}
 				}
 				gn[j] = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
@@ -827,8 +828,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286)
 				if (same) m_nat += tab[c2i[((g0 * n + g1) * n + g2) * n + g3]];
 				else {
-					// heterozygote multiplicities log 4, 6, 12, 24 (poly_geno.c:1262-1268)
-					m_nat += (cls == 0) ? 0.0f : (cls == 1 ? 1.3862943611198906f : (cls == 2 ? 1.791759469228055f : (cls == 3 ? 2.4849066497880004f : 3.1780538303479458f)));
+					m_nat += lmul;
 					m_lg2 += lg2_fast(Pl[g0 * KP + z0] * Pl[g1 * KP + z1]) + lg2_fast(Pl[g2 * KP + z2] * Pl[g3 * KP + z3]);
 				}
 				// ---- tally of the next update_P_auto over the latent genotype (poly_geno.c:403-424)
