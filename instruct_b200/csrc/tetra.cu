@@ -700,37 +700,64 @@ __device__ __forceinline__ float ex2_fast(float x)            // MUFU.EX2
 // The reference evaluates the resolution weights and the likelihood in double (libm log / exp); here
 // they are fp32 with MUFU.LG2 / MUFU.EX2: the weights carry ~1e-6 relative error (the z draw's fp32
 // weights carry as much), the likelihood sums stay inside the 1e-6 gate (tests/test_gpu_tetra.py).
-template <int KP, int ROUNDS>
+//
+// The kernel is bound by instruction issue and a third of its instructions were integer address
+// arithmetic (ncu source page, profiles/r1_tetra_geno_v4_source.txt), so all shared-memory accesses use
+// explicit 32-bit shared addresses that advance by additions, the four (allele, population) bin
+// indices of a genotype come from ONE multiply on the packed bytes (geno * KP + z), a resolution
+// is a PRMT selector over the observed alleles and its catalogue code one dp4a.
+constexpr int TETRA_R = 4;            // lane replicas of the tally histogram (tetra_configure)
+__device__ __forceinline__ int2 lds_i2(uint32_t addr)
+{
+	int2 v;
+	asm("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+	uint32_t v;
+	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+// table entry of the genotype with catalogue code `code`: staged copy (shared addresses) or global
+template <bool STAGE>
+__device__ __forceinline__ float tab_at(uint32_t tab_sa, const float *tab_g, uint32_t c2i_sa, const uint8_t *c2i_g, uint32_t code)
+{
+	if (STAGE) return lds_f(tab_sa + lds_u8(c2i_sa + code) * 4u);
+	return __ldg(tab_g + c2i_g[code]);
+}
+
+template <int KP, int ROUNDS, bool STAGE>
 __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const GenoArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bar;
 	const Geometry &g = a.geo;
-	const int tid = threadIdx.x, chunk = blockIdx.x, R = g.R;
+	constexpr int R = TETRA_R;
+	const int tid = threadIdx.x, chunk = blockIdx.x;
 	const int l0 = chunk * g.TL, nl = min(g.TL, g.Lpad - l0), nmt = nl / TT, rowsz = g.A * KP;
 	float *Psm = reinterpret_cast<float *>(smem_raw);
 	int *hist = reinterpret_cast<int *>(Psm + (size_t)g.TL * rowsz);            // [TL][A][KP][R]
-	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)g.TL * rowsz * R);
+	int2 *locsm = reinterpret_cast<int2 *>(hist + (size_t)g.TL * rowsz * R);    // [TL] ((n^3, n^2, n, 1) bytes, c2i offset)
 	// the chunk's slice of the genotype-frequency tables [TL][K][Gmax] (one more bulk copy) and the code -> index
 	// bytes: the same-population look-ups become shared-memory loads instead of dependent L1 / L2 round trips
 	float *tabsm = reinterpret_cast<float *>(locsm + g.TL);
 	uint8_t *c2ism = reinterpret_cast<uint8_t *>(tabsm + (size_t)g.TL * g.K * a.Gmax);
 	const int nbins = nl * rowsz;
-	const uint32_t tab_bytes = g.tab_stage ? (uint32_t)nl * (uint32_t)(g.K * a.Gmax) * 4u : 0u;
+	const uint32_t tab_bytes = STAGE ? (uint32_t)nl * (uint32_t)(g.K * a.Gmax) * 4u : 0u;
 	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 	__syncthreads();
 	if (tid == 0) {
 		mbar_expect_tx(&bar, (uint32_t)nbins * 4u + tab_bytes);
 		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
-		if (tab_bytes) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
+		if (STAGE) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
 	}
-	if (g.tab_stage) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
-	const float *tabbase = g.tab_stage ? tabsm : a.tab + (size_t)l0 * g.K * a.Gmax;
-	const uint8_t *c2ibase = g.tab_stage ? c2ism : a.c2i;
+	if (STAGE) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
 	for (int j = tid; j < nbins * R; j += TETRA_THREADS) hist[j] = 0;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
-		locsm[j] = ci >= 0 ? make_int2(a.cats[ci].n, a.cats[ci].c2i_off) : make_int2(1, 0);
+		const int n = ci >= 0 ? a.cats[ci].n : 1;                                // n <= 6: n^3 fits a byte
+		locsm[j] = make_int2((n * n * n) | ((n * n) << 8) | (n << 16) | (1 << 24), ci >= 0 ? a.cats[ci].c2i_off : 0);
 	}
 	__syncthreads();
 	mbar_wait(&bar, 0);
@@ -738,7 +765,10 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 	const int Nloc = g.Nloc, mt0 = l0 / TT;
 	const int nsub_total = (Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
 	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
-	const uint32_t hist_sa = smem_addr(hist) + (uint32_t)(tid & (R - 1)) * 4u, R4 = (uint32_t)R * 4u;
+	const uint32_t psm_sa = smem_addr(Psm), loc_sa = smem_addr(locsm), tab_sa0 = smem_addr(tabsm), c2i_sa0 = smem_addr(c2ism);
+	const uint32_t hist_sa = smem_addr(hist) + (uint32_t)(tid & (R - 1)) * 4u;
+	const uint32_t row4 = (uint32_t)rowsz * 4u;                 // bytes of one locus of P; one locus of the histogram is R of them
+	const uint32_t G4 = (uint32_t)a.Gmax * 4u, KG4 = (uint32_t)g.K * G4;
 	const float LOG2E = 1.4426950408889634f;
 	const float LG2_6 = 2.584962500721156f;
 
@@ -757,6 +787,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 		int4 *gp = reinterpret_cast<int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
 		float ll_nat = 0.0f, ll_lg2 = 0.0f;      // natural-log part (tables, multiplicities) and log2 part (allele frequencies)
 		int4 xa_n = ldg_stream(xp), xb_n = ldg_stream(xp + 1), zv_n = ldg_stream(zp);      // prefetch one micro-tile ahead
+		uint32_t p_sa = psm_sa, l_sa = loc_sa, t_sa = tab_sa0;                // running shared addresses of the micro-tile's first locus
+		const float *t_g = a.tab + (size_t)l0 * g.K * a.Gmax;
 		for (int mt = 0; mt < nmt; ++mt) {
 			const int4 xa = xa_n, xb = xb_n, zv = zv_n;
 			if (mt + 1 < nmt) {
@@ -766,43 +798,52 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 			// one Philox block per (micro-tile, individual): word j resolves the dosage of locus j
 			const u32x4 rnd4 = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_GENO}, a.key0, a.key1);
 			const uint32_t rj[4] = {rnd4.x, rnd4.y, rnd4.z, rnd4.w};
-			const int xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+			const uint32_t xw[8] = {(uint32_t)xa.x, (uint32_t)xa.y, (uint32_t)xa.z, (uint32_t)xa.w, (uint32_t)xb.x, (uint32_t)xb.y, (uint32_t)xb.z, (uint32_t)xb.w};
 			const uint32_t zw[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
 			uint32_t gn[4];
 			float m_nat = 0.0f, m_lg2 = 0.0f;
 #pragma unroll
 			for (int j = 0; j < TT; ++j) {
 				gn[j] = 0xFFFFFFFFu;
-				// distinct alleles ascending, -1 padding; all -1 = missing (data_interface.c:636-650)
-				const int a0 = (int)(short)(xw[2 * j] & 0xFFFF), a1 = xw[2 * j] >> 16, a2 = (int)(short)(xw[2 * j + 1] & 0xFFFF), a3 = xw[2 * j + 1] >> 16;
-				if (a0 < 0) continue;
-				const int nd = 1 + (a1 >= 0) + (a2 >= 0) + (a3 >= 0);
-				const int lj = mt * TT + j;
-				const int2 li = locsm[lj];
-				const int n = li.x, n2 = n * n;
+				// distinct alleles ascending in int16, -1 padding; all -1 = missing (data_interface.c:636-650)
+				if (xw[2 * j] & 0x8000u) continue;
+				const int nd = 1 + ((xw[2 * j] >> 31) ^ 1) + (((xw[2 * j + 1] >> 15) & 1) ^ 1) + ((xw[2 * j + 1] >> 31) ^ 1);
+				const uint32_t apack = __byte_perm(xw[2 * j], xw[2 * j + 1], 0x6420);   // the observed alleles, one per byte
+				const int2 li = lds_i2(l_sa + 8u * j);
+				const uint32_t npack = (uint32_t)li.x;                            // dp4a(genotype, npack) = catalogue code
+				const uint32_t pj_sa = p_sa + (uint32_t)j * row4;                 // &P[l][0][0]
 				const uint32_t z0 = zw[j] & 0xFFu;
 				const bool same = (zw[j] == z0 * 0x01010101u);
-				const float *tab = tabbase + (lj * g.K + (int)z0) * a.Gmax;
-				const uint8_t *c2i = c2ibase + li.y;
-				const float *Pl = Psm + lj * rowsz;
-				int g0, g1, g2, g3;
+				const uint32_t tj_sa = t_sa + (uint32_t)j * KG4 + z0 * G4;        // population z0's table of this locus
+				const float *tj_g = t_g + ((size_t)j * g.K + z0) * a.Gmax;
+				const uint32_t cj_sa = c2i_sa0 + (uint32_t)li.y;
+				const uint8_t *cj_g = a.c2i + li.y;
+				uint32_t gpk;
 				float lmul;                                                        // heterozygote multiplicities log 4, 6, 12, 24 (poly_geno.c:1262-1268)
-				if (nd == 1) { g0 = g1 = g2 = g3 = a0; lmul = 0.0f; }
-				else if (nd == 4) { g0 = a0; g1 = a1; g2 = a2; g3 = a3; lmul = 3.1780538303479458f; }
+				if (nd == 1) { gpk = (apack & 0xFFu) * 0x01010101u; lmul = 0.0f; }
+				else if (nd == 4) { gpk = apack; lmul = 3.1780538303479458f; }
 				else {
-					// ---- three dosage resolutions (choose_two_auto :854, choose_tri_auto :907), weights in log2
+					// ---- three dosage resolutions (choose_two_auto :854, choose_tri_auto :907), weights in log2; as PRMT
+					//      selectors over the observed alleles (two_allele_auto :2440 / tri_allele_auto :2509):
+					//      nd 2: a0a0a0a1 | a1a1a1a0 | a0a0a1a1     nd 3: a0a0a1a2 | a1a1a0a2 | a2a2a0a1
+					const uint32_t s0 = (nd == 2) ? 0x1000u : 0x2100u, s1 = (nd == 2) ? 0x0111u : 0x2011u, s2 = (nd == 2) ? 0x1100u : 0x1022u;
 					float w0, w1, w2;
 					if (a.init) { w0 = w1 = w2 = 0.0f; }                                // choose_unif, poly_geno.c:842
 					else if (same) {
-						int c0, c1, c2;
-						if (nd == 2) { c0 = a0 * n * (n2 + n + 1) + a1; c1 = a1 * n * (n2 + n + 1) + a0; c2 = (a0 * n2 + a1) * (n + 1); }
-						else { c0 = a0 * n2 * (n + 1) + a1 * n + a2; c1 = a1 * n2 * (n + 1) + a0 * n + a2; c2 = a2 * n2 * (n + 1) + a0 * n + a1; }
-						w0 = tab[c2i[c0]] * LOG2E; w1 = tab[c2i[c1]] * LOG2E; w2 = tab[c2i[c2]] * LOG2E;
+						w0 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(__byte_perm(apack, 0u, s0), npack, 0u)) * LOG2E;
+						w1 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(__byte_perm(apack, 0u, s1), npack, 0u)) * LOG2E;
+						w2 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(__byte_perm(apack, 0u, s2), npack, 0u)) * LOG2E;
 					} else {
-						const float *r0 = Pl + a0 * KP, *r1 = Pl + a1 * KP, *r2 = Pl + (nd == 3 ? a2 : a0) * KP;
+						const uint32_t r0 = pj_sa + (apack & 0xFFu) * (KP * 4u), r1 = pj_sa + ((apack >> 8) & 0xFFu) * (KP * 4u);
+						const uint32_t r2 = (nd == 3) ? pj_sa + ((apack >> 16) & 0xFFu) * (KP * 4u) : r0;
 						float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
 #pragma unroll
-						for (int k = 0; k < KP; k++) { f0 = fmaf(q[k], r0[k], f0); f1 = fmaf(q[k], r1[k], f1); f2 = fmaf(q[k], r2[k], f2); }
+						for (int v = 0; v < KP / 4; v++) {
+							const float4 t0 = lds_f4(r0 + 16 * v), t1 = lds_f4(r1 + 16 * v), t2 = lds_f4(r2 + 16 * v);
+							f0 = fmaf(q[4 * v], t0.x, f0); f0 = fmaf(q[4 * v + 1], t0.y, f0); f0 = fmaf(q[4 * v + 2], t0.z, f0); f0 = fmaf(q[4 * v + 3], t0.w, f0);
+							f1 = fmaf(q[4 * v], t1.x, f1); f1 = fmaf(q[4 * v + 1], t1.y, f1); f1 = fmaf(q[4 * v + 2], t1.z, f1); f1 = fmaf(q[4 * v + 3], t1.w, f1);
+							f2 = fmaf(q[4 * v], t2.x, f2); f2 = fmaf(q[4 * v + 1], t2.y, f2); f2 = fmaf(q[4 * v + 2], t2.z, f2); f2 = fmaf(q[4 * v + 3], t2.w, f2);
+						}
 						const float l0f = lg2_fast(f0), l1f = lg2_fast(f1), l2f = lg2_fast(f2);
 						if (nd == 2) { w0 = 2.0f + 3.0f * l0f + l1f; w1 = 2.0f + 3.0f * l1f + l0f; w2 = LG2_6 + 2.0f * l0f + 2.0f * l1f; }
 						else { w0 = 2.0f * l0f + l1f + l2f; w1 = 2.0f * l1f + l0f + l2f; w2 = 2.0f * l2f + l1f + l0f; }
@@ -810,37 +851,31 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 					const float e1 = ex2_fast(w1 - w0), e2 = ex2_fast(w2 - w0);          // e0 = 1
 					const float c1w = 1.0f + e1, c2w = c1w + e2;
 					const float u = u01f(rj[j]) * c2w;
-					const int pick = (u < 1.0f) ? 0 : (u < c1w ? 1 : 2);
-					// two_allele_auto :2440 / tri_allele_auto :2509
-					if (nd == 2) {
-						const int major = (pick == 1) ? a1 : a0, minor = (pick == 1) ? a0 : a1;
-						g0 = major; g1 = major; g2 = (pick == 2) ? minor : major; g3 = minor;
-						lmul = (pick == 2) ? 1.791759469228055f : 1.3862943611198906f;
-					} else {
-						const int dbl = (pick == 0) ? a0 : (pick == 1 ? a1 : a2);
-						g0 = dbl; g1 = dbl; g2 = (pick == 0) ? a1 : a0; g3 = (pick == 2) ? a1 : a2;
-						lmul = 2.4849066497880004f;
-					}
+					const uint32_t sel = (u < 1.0f) ? s0 : (u < c1w ? s1 : s2);
+					gpk = __byte_perm(apack, 0u, sel);
+					lmul = (nd == 3) ? 2.4849066497880004f : ((u < c1w) ? 1.3862943611198906f : 1.791759469228055f);
 				}
-				gn[j] = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+				gn[j] = gpk;
 				if (a.init) continue;
-				const uint32_t z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
+				// the four (allele, population) bins of the genotype, one per byte: geno * KP + z (< 256, no carries)
+				const uint32_t ipk = gpk * (uint32_t)KP + zw[j];
+				const uint32_t i0 = ipk & 0xFFu, i1 = (ipk >> 8) & 0xFFu, i2 = (ipk >> 16) & 0xFFu, i3 = ipk >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286)
-				if (same) m_nat += tab[c2i[((g0 * n + g1) * n + g2) * n + g3]];
+				if (same) m_nat += tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(gpk, npack, 0u));
 				else {
 					m_nat += lmul;
-					m_lg2 += lg2_fast(Pl[g0 * KP + z0] * Pl[g1 * KP + z1]) + lg2_fast(Pl[g2 * KP + z2] * Pl[g3 * KP + z3]);
+					m_lg2 += lg2_fast(lds_f(pj_sa + i0 * 4u) * lds_f(pj_sa + i1 * 4u)) + lg2_fast(lds_f(pj_sa + i2 * 4u) * lds_f(pj_sa + i3 * 4u));
 				}
-				// ---- tally of the next update_P_auto over the latent genotype (poly_geno.c:403-424)
-				// shared-space RED on explicit 32-bit addresses (a generic atomicAdd costs an address-space check per call)
-				const uint32_t hrow = hist_sa + (uint32_t)(lj * g.A * KP) * R4;
-				red_inc(hrow + (uint32_t)(g0 * KP + (int)z0) * R4);
-				red_inc(hrow + (uint32_t)(g1 * KP + (int)z1) * R4);
-				red_inc(hrow + (uint32_t)(g2 * KP + (int)z2) * R4);
-				red_inc(hrow + (uint32_t)(g3 * KP + (int)z3) * R4);
+				// ---- tally of the next update_P_auto over the latent genotype (poly_geno.c:403-424): shared-space RED
+				const uint32_t hj_sa = hist_sa + (pj_sa - psm_sa) * (uint32_t)R;
+				red_inc(hj_sa + i0 * (4u * R));
+				red_inc(hj_sa + i1 * (4u * R));
+				red_inc(hj_sa + i2 * (4u * R));
+				red_inc(hj_sa + i3 * (4u * R));
 			}
 			*(gp + (size_t)mt * Nloc) = make_int4((int)gn[0], (int)gn[1], (int)gn[2], (int)gn[3]);
 			ll_nat += m_nat; ll_lg2 += m_lg2;
+			p_sa += TT * row4; l_sa += TT * 8u; t_sa += TT * KG4; t_g += (size_t)TT * g.K * a.Gmax;
 		}
 		if (!a.init) {
 			a.lpart[((size_t)chunk * 2) * Nloc + il] = ll_nat;
@@ -1181,7 +1216,7 @@ static cudaError_t tetra_configure(Geometry &g, int device, bool allo, int Gmax,
 	cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 	const int target = 4 * sms;
 	const size_t per_locus = (size_t)g.A * g.KP * 4;
-	const int R = 4;
+	const int R = TETRA_R;
 	const size_t fixedA = (size_t)2 * g.KP * TETRA_THREADS * 4 + 2048;
 	const size_t budget = (size_t)smem_optin / 2 - 1024;
 	int tl = (int)((budget - fixedA) / (per_locus * (1 + R) * (allo ? 2 : 1) + 8));     // allotetraploid: two P chunks, two histograms
@@ -1382,14 +1417,17 @@ static ig_status tetra_pass_b(ig_ctx *c, int init)
 	GenoArgs a{t->Xq, t->Zq, t->Gq, c->P, c->Qf, t->tabC, t->loc_cat, t->cats, t->c2i, c->n, t->lpart, g, t->Gmax, init, c->iter, c->key0, c->key1};
 	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
 	const size_t sm = smem_geno(g, t->Gmax);
+#define GENO_LAUNCH(KPV, RV)                                                                                          \
+	do {                                                                                                          \
+		if (g.tab_stage) { CK(opt_smem(tetra_geno_kernel<KPV, RV, true>, sm)); tetra_geno_kernel<KPV, RV, true><<<grid, block, sm, c->stream>>>(a); }   \
+		else { CK(opt_smem(tetra_geno_kernel<KPV, RV, false>, sm)); tetra_geno_kernel<KPV, RV, false><<<grid, block, sm, c->stream>>>(a); }             \
+	} while (0)
 	switch (g.KP) {
-	case 4: if (c->rounds == 10) { CK(opt_smem(tetra_geno_kernel<4, 10>, sm)); tetra_geno_kernel<4, 10><<<grid, block, sm, c->stream>>>(a); }
-	         else { CK(opt_smem(tetra_geno_kernel<4, 7>, sm)); tetra_geno_kernel<4, 7><<<grid, block, sm, c->stream>>>(a); } break;
-	case 8: if (c->rounds == 10) { CK(opt_smem(tetra_geno_kernel<8, 10>, sm)); tetra_geno_kernel<8, 10><<<grid, block, sm, c->stream>>>(a); }
-	         else { CK(opt_smem(tetra_geno_kernel<8, 7>, sm)); tetra_geno_kernel<8, 7><<<grid, block, sm, c->stream>>>(a); } break;
-	default: if (c->rounds == 10) { CK(opt_smem(tetra_geno_kernel<16, 10>, sm)); tetra_geno_kernel<16, 10><<<grid, block, sm, c->stream>>>(a); }
-	         else { CK(opt_smem(tetra_geno_kernel<16, 7>, sm)); tetra_geno_kernel<16, 7><<<grid, block, sm, c->stream>>>(a); } break;
+	case 4: if (c->rounds == 10) GENO_LAUNCH(4, 10); else GENO_LAUNCH(4, 7); break;
+	case 8: if (c->rounds == 10) GENO_LAUNCH(8, 10); else GENO_LAUNCH(8, 7); break;
+	default: if (c->rounds == 10) GENO_LAUNCH(16, 10); else GENO_LAUNCH(16, 7); break;
 	}
+#undef GENO_LAUNCH
 	CK(cudaGetLastError());
 	if (t->timing && !init) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; t->timing = false; }
 	c->launches++;
