@@ -322,6 +322,13 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 	return IG_OK;
 }
 
+ig_status ig_allreduce_int64(ig_ctx *c, int64_t *buf, size_t count)
+{
+	if (!c->comm) return IG_OK;
+	NCK(g_nccl.AllReduce(buf, buf, count, ncclInt64, ncclSum, c->comm, c->stream));
+	return IG_OK;
+}
+
 static ig_status exchange_tally(ig_ctx *c);
 static ig_status exchange_individuals(ig_ctx *c);
 ig_status ig_exchange_tally(ig_ctx *c) { return exchange_tally(c); }

@@ -124,6 +124,7 @@ ig_status ig_exchange_tally(ig_ctx *c);
 ig_status ig_exchange_individuals(ig_ctx *c);
 ig_status ig_allgather_double(ig_ctx *c, double *buf, size_t per_rank);
 ig_status ig_allreduce_int32(ig_ctx *c, int32_t *buf, size_t count);
+ig_status ig_allreduce_int64(ig_ctx *c, int64_t *buf, size_t count);
 
 // no-admixture driver (noadmix.cu)
 ig_status na_alloc(ig_ctx *c);

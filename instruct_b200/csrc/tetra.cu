@@ -64,8 +64,7 @@ struct TetraState {
 	float *exf = nullptr, *tabC = nullptr, *tabP = nullptr;    // [Lq][K][Gmax] natural logs
 	double *Sprop = nullptr, *dstat = nullptr;                  // [K]
 	int32_t *accepted = nullptr;      // [K]
-	float *dpart = nullptr;           // [nchunks][K][Nloc] S statistics per (chunk, population, individual)
-	double *dind = nullptr;           // [Npad][K] the same summed over chunks, all shards (all-gathered)
+	unsigned long long *dfix = nullptr;   // [MAX_K] S statistics cal_lkd_props(k) - cal_lkd() of the current sweep, 2^-24 fixed point
 	float *lpart = nullptr;           // [nchunks][2][Nloc] likelihood partials: natural-log part, log2 part
 	bool timing = false;              // a profiled sweep is between its PASS A start and PASS B end events
 	// allotetraploid (-ap 0): copies 0,1 and copies 2,3 are two subgenomes with their own allele frequencies
@@ -345,8 +344,14 @@ __device__ void genfreq_locus_allo(float self, const TetraCat &c, const int32_t 
 
 __global__ void tetra_tables_kernel(const TabArgs a)
 {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	// when both tables are wanted (every sweep), two threads share a (locus, population): one solves for the current
+	// rate, the other for the proposed one; both write the same exfreq values first (identical stores)
+	const int split = (a.do_cur && a.do_prop) ? 2 : 1;
+	const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+	const int t = t2 / split;
 	if (t >= a.L * a.K) return;
+	const bool second = (split == 2) && (t2 & 1);
+	const bool want_cur = (split == 2) ? !second : (a.do_cur != 0), want_prop = (split == 2) ? second : (a.do_prop != 0);
 	const int l = t / a.K, k = t % a.K;
 	const TetraCat c = a.cats[a.loc_cat[l]];
 	const int32_t *code = a.codes + c.code_off;
@@ -382,8 +387,11 @@ __global__ void tetra_tables_kernel(const TabArgs a)
 			for (int q = 2; q < 4; q++) r += (float)lf[d[q]];
 			R[g] = r;
 		}
-		if (a.do_cur) genfreq_locus_allo((float)a.S[k], c, code, c2i, R, a.tabC + (size_t)t * a.Gmax);
-		if (a.do_prop) genfreq_locus_allo((float)a.Sprop[k], c, code, c2i, R, a.tabP + (size_t)t * a.Gmax);
+		if (split == 2) genfreq_locus_allo((float)(second ? a.Sprop[k] : a.S[k]), c, code, c2i, R, (second ? a.tabP : a.tabC) + (size_t)t * a.Gmax);
+		else {
+			if (want_cur) genfreq_locus_allo((float)a.S[k], c, code, c2i, R, a.tabC + (size_t)t * a.Gmax);
+			if (want_prop) genfreq_locus_allo((float)a.Sprop[k], c, code, c2i, R, a.tabP + (size_t)t * a.Gmax);
+		}
 		return;
 	}
 	// calc_exfreq_auto, poly_geno.c:1515-1577
@@ -408,8 +416,11 @@ __global__ void tetra_tables_kernel(const TabArgs a)
 		R[g] = r;
 	}
 	// calc_self_genofreq, poly_geno.c:1219: the rate arrives as double and is passed on as float
-	if (a.do_cur) genfreq_locus((float)a.S[k], c, code, c2i, R, a.tabC + (size_t)t * a.Gmax);
-	if (a.do_prop) genfreq_locus((float)a.Sprop[k], c, code, c2i, R, a.tabP + (size_t)t * a.Gmax);
+	if (split == 2) genfreq_locus((float)(second ? a.Sprop[k] : a.S[k]), c, code, c2i, R, (second ? a.tabP : a.tabC) + (size_t)t * a.Gmax);
+	else {
+		if (want_cur) genfreq_locus((float)a.S[k], c, code, c2i, R, a.tabC + (size_t)t * a.Gmax);
+		if (want_prop) genfreq_locus((float)a.Sprop[k], c, code, c2i, R, a.tabP + (size_t)t * a.Gmax);
+	}
 }
 
 // --------------------------------------------------------------------------------------
@@ -440,28 +451,23 @@ __device__ double block_sum1(double v, double *sh)
 	return r;
 }
 
-// D_k = cal_lkd_props(k) - cal_lkd(): fixed-shape tree over ALL individuals (identical on every
-// rank and for every shard count), then the K accept decisions
-__global__ void __launch_bounds__(RED1) tetra_accept_kernel(const double *dind, int N, int K, double *S, const double *Sprop,
-                                                           double *dstat, int32_t *accepted, DevScalars *sc, uint32_t iter, uint32_t key0, uint32_t key1, int decide)
+// D_k = cal_lkd_props(k) - cal_lkd() from the fixed-point totals of PASS A (all shards, all-reduced as
+// integers: identical on every rank and for every shard count), then the K accept decisions
+__global__ void tetra_accept_kernel(const unsigned long long *dfix, int K, double *S, const double *Sprop,
+                                    double *dstat, int32_t *accepted, DevScalars *sc, uint32_t iter, uint32_t key0, uint32_t key1, int decide)
 {
-	__shared__ double sh[RED1];
-	for (int k = 0; k < K; k++) {
-		double v = 0.0;
-		for (int i = threadIdx.x; i < N; i += RED1) v += dind[(size_t)i * K + k];
-		const double D = block_sum1(v, sh);
-		if (threadIdx.x == 0) {
-			dstat[k] = D;
-			if (decide) {
-				Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
-				(void)st.uniform();                                       // the proposal's draw
-				const double u = st.uniform();
-				// ran1() < exp(MIN2(0, mhratio)) (poly_geno.c:628); MIN2(0, NaN) == 0 accepts
-				const bool acc = (D != D) || (u < exp(fmin(0.0, D)));
-				accepted[k] = acc ? 1 : 0;
-				if (acc) { S[k] = Sprop[k]; sc->s_accepts++; }
-			}
-		}
+	const int k = threadIdx.x;
+	if (k >= K) return;
+	const double D = (double)(long long)dfix[k] * (1.0 / 16777216.0);
+	dstat[k] = D;
+	if (decide) {
+		Stream st((uint32_t)k, 0u, iter, TAG_TETRA, key0, key1);
+		(void)st.uniform();                                       // the proposal's draw
+		const double u = st.uniform();
+		// ran1() < exp(MIN2(0, mhratio)) (poly_geno.c:628)
+		const bool acc = (u < exp(fmin(0.0, D)));
+		accepted[k] = acc ? 1 : 0;
+		if (acc) { S[k] = Sprop[k]; atomicAdd(&sc->s_accepts, 1); }
 	}
 }
 // move_genofreq, poly_geno.c:738-748
@@ -479,7 +485,7 @@ __global__ void tetra_select_kernel(float *tabC, const float *tabP, const int32_
 struct ZsArgs {
 	int8_t *Zq; const int8_t *Gq; const float *P; const float *Qf;
 	const float *tabC, *tabP; const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
-	uint16_t *pcnt; float *dpart;
+	uint16_t *pcnt; unsigned long long *dfix;   // dfix [K]: S statistics, 2^-24 fixed point, summed over the launch
 	Geometry geo; int Gmax; int init;
 	uint32_t iter, key0, key1, k_mant, k_one;
 };
@@ -489,6 +495,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bar;
+	__shared__ unsigned long long dacc[MAX_K];              // this CTA's S statistics, fixed point
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x, chunk = blockIdx.x;
 	const int l0 = chunk * g.TL, nl = min(g.TL, g.Lpad - l0), nmt = nl / TT, rowsz = g.A * KP;
@@ -501,6 +508,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 	__syncthreads();
 	if (tid == 0) { mbar_expect_tx(&bar, (uint32_t)nbins * 4u); tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar); }
 	for (int k = 0; k < KP; k++) { cntsm[k * TETRA_THREADS + tid] = 0; dsm[k * TETRA_THREADS + tid] = 0.0f; }
+	if (tid < MAX_K) dacc[tid] = 0ull;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
 		locsm[j] = ci >= 0 ? make_int2(a.cats[ci].n, a.cats[ci].c2i_off) : make_int2(1, 0);
@@ -517,7 +525,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		const int il = sub * TETRA_THREADS + tid;
-		if (il >= Nloc) continue;
+		if (il < Nloc) {
 		float q[KP];
 #pragma unroll
 		for (int v = 0; v < KP / 4; v++) {
@@ -587,44 +595,25 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs
 			cntsm[(2 * j + 1) * TETRA_THREADS + tid] = 0;
 			pc[j] = (uint32_t)ca | ((uint32_t)cb << 16);
 		}
+		}
+		// ---- S statistics of this (chunk, 256 individuals): each thread's fp32 sum over the chunk's loci becomes a
+		//      2^-24 fixed-point integer, and integers add exactly in any order -- so the K totals are identical for
+		//      every grid shape and every shard count without keeping per-individual partials
 		if (!a.init)
 			for (int k = 0; k < g.K; k++) {
-				a.dpart[((size_t)chunk * g.K + k) * Nloc + il] = dsm[k * TETRA_THREADS + tid];
+				long long fx = __float2ll_rn(dsm[k * TETRA_THREADS + tid] * 16777216.0f);
 				dsm[k * TETRA_THREADS + tid] = 0.0f;
+#pragma unroll
+				for (int off = 16; off > 0; off >>= 1) fx += __shfl_down_sync(0xFFFFFFFFu, fx, off);
+				if ((tid & 31) == 0 && fx != 0) atomicAdd(&dacc[k], (unsigned long long)fx);
 			}
 	}
+	__syncthreads();
+	if (!a.init && tid < g.K && dacc[tid] != 0ull) atomicAdd(a.dfix + tid, dacc[tid]);
 }
 
-// per individual: the S statistics summed over chunks in chunk order (shard-invariant), written
-// at the individual's GLOBAL slot so that one all-gather completes the array on every rank
-// CTA = 32 individuals (lanes) x CG chunk groups (warps): warp w adds the partials of chunks w,
-// w + CG, ... (coalesced over the 32 individuals), warp 0 then adds the CG group sums in group
-// order.  The order depends only on the chunk decomposition, i.e. on (L, K, A): shard-invariant.
+// chunk-group width of the per-individual reductions below (tetra_q, tetra_indv_lkh)
 constexpr int CG = 8;
-__global__ void __launch_bounds__(32 * CG) tetra_dind_kernel(const float *dpart, double *dind, Geometry g)
-{
-	__shared__ double sh[CG][MAX_K][32];
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int il = blockIdx.x * 32 + lane;
-	const bool live = il < g.Nloc;
-	double s[MAX_K];
-#pragma unroll
-	for (int k = 0; k < MAX_K; k++) s[k] = 0.0;
-	if (live)
-		for (int c = w; c < g.nchunks; c += CG)
-#pragma unroll
-			for (int k = 0; k < MAX_K; k++)
-				if (k < g.K) s[k] += (double)dpart[((size_t)c * g.K + k) * g.Nloc + il];
-#pragma unroll
-	for (int k = 0; k < MAX_K; k++) sh[w][k][lane] = s[k];
-	__syncthreads();
-	if (w != 0 || !live) return;
-	for (int k = 0; k < g.K; k++) {
-		double t = 0.0;
-		for (int ww = 0; ww < CG; ww++) t += sh[ww][k][lane];
-		dind[(size_t)(g.i0 + il) * g.K + k] = t;
-	}
-}
 
 // --------------------------------------------------------------------------------------
 // Q_i ~ Dirichlet(cnt_i + alpha), poly_geno.c:812-833
@@ -1278,7 +1267,7 @@ void tetra_destroy(ig_ctx *c)
 	if (!t) return;
 	cudaFree(t->Xq); cudaFree(t->Zq); cudaFree(t->Gq); cudaFree(t->cats); cudaFree(t->codes); cudaFree(t->c2i); cudaFree(t->loc_cat);
 	cudaFree(t->exf); cudaFree(t->tabC); cudaFree(t->tabP); cudaFree(t->Sprop); cudaFree(t->dstat); cudaFree(t->accepted);
-	cudaFree(t->dpart); cudaFree(t->dind); cudaFree(t->lpart); cudaFree(t->P2); cudaFree(t->n2);
+	cudaFree(t->dfix); cudaFree(t->lpart); cudaFree(t->P2); cudaFree(t->n2);
 	delete t;
 	c->tetra = nullptr;
 }
@@ -1335,7 +1324,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	CK(cudaMemcpy(t->loc_cat, loc_cat.data(), loc_cat.size() * 4, cudaMemcpyHostToDevice));
 	CK(dalloc0(&t->exf, tn)); CK(dalloc0(&t->tabC, tn)); CK(dalloc0(&t->tabP, tn));
 	CK(dalloc0(&t->Sprop, (size_t)MAX_K)); CK(dalloc0(&t->dstat, (size_t)MAX_K)); CK(dalloc0(&t->accepted, (size_t)MAX_K));
-	CK(dalloc0(&t->dpart, (size_t)g.nchunks * g.K * g.Nloc)); CK(dalloc0(&t->dind, (size_t)c->Npad * g.K)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * 2 * g.Nloc));
+	CK(dalloc0(&t->dfix, (size_t)MAX_K)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * 2 * g.Nloc));
 	CK(dalloc0(&c->P, pn)); CK(dalloc0(&c->n, pn));
 	if (t->allo) { CK(dalloc0(&t->P2, pn)); CK(dalloc0(&t->n2, pn)); }
 	if (c->cfg.print_freq) CK(dalloc0(&c->P64, (size_t)g.K * g.L * g.A));
@@ -1364,11 +1353,12 @@ static ig_status tetra_pass_a(ig_ctx *c, int init)
 {
 	TetraState *t = c->tetra;
 	const Geometry &g = c->geo;
-	ZsArgs a{t->Zq, t->Gq, c->P, c->Qf, t->tabC, t->tabP, t->loc_cat, t->cats, t->c2i, c->pcnt, t->dpart, g, t->Gmax, init,
+	ZsArgs a{t->Zq, t->Gq, c->P, c->Qf, t->tabC, t->tabP, t->loc_cat, t->cats, t->c2i, c->pcnt, t->dfix, g, t->Gmax, init,
 	         c->iter, c->key0, c->key1, 0x007fffffu, 0x3f800000u};
 	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
 	const size_t sm = smem_zs(g);
 	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
+	if (!init) CK(cudaMemsetAsync(t->dfix, 0, MAX_K * sizeof(unsigned long long), c->stream));
 	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
 	switch (g.KP) {
 	case 4: if (c->rounds == 10) { CK(opt_smem(tetra_zs_kernel<4, 10>, sm)); tetra_zs_kernel<4, 10><<<grid, block, sm, c->stream>>>(a); }
@@ -1440,7 +1430,7 @@ static ig_status tetra_tables(ig_ctx *c, int do_cur, int do_prop)
 	const Geometry &g = c->geo;
 	TabArgs a{c->P, c->allelenum, t->loc_cat, t->cats, t->codes, t->c2i, c->S, t->Sprop, t->exf, t->tabC, t->tabP, g.L, g.K, g.KP, g.A, t->Gmax, do_cur, do_prop,
 	          t->P2, t->allo ? 1 : 0};
-	tetra_tables_kernel<<<nb((size_t)g.L * g.K, 64), 64, 0, c->stream>>>(a);
+	tetra_tables_kernel<<<nb((size_t)g.L * g.K * ((do_cur && do_prop) ? 2 : 1), 64), 64, 0, c->stream>>>(a);
 	CK(cudaGetLastError());
 	c->launches++;
 	return IG_OK;
@@ -1498,11 +1488,9 @@ static ig_status tetra_s_end(ig_ctx *c, int decide)
 {
 	TetraState *t = c->tetra;
 	const Geometry &g = c->geo;
-	tetra_dind_kernel<<<nb((size_t)g.Nloc, 32), 32 * CG, 0, c->stream>>>(t->dpart, t->dind, g);
-	CK(cudaGetLastError());
-	ig_status st = ig_allgather_double(c, t->dind, (size_t)c->shard_cap * g.K);
+	ig_status st = ig_allreduce_int64(c, (int64_t *)t->dfix, (size_t)g.K);      // the shards' integer totals: an exact sum
 	if (st != IG_OK) return st;
-	tetra_accept_kernel<<<1, RED1, 0, c->stream>>>(t->dind, g.N, g.K, c->S, t->Sprop, t->dstat, t->accepted, c->sc, c->iter, c->key0, c->key1, decide);
+	tetra_accept_kernel<<<1, 32, 0, c->stream>>>(t->dfix, g.K, c->S, t->Sprop, t->dstat, t->accepted, c->sc, c->iter, c->key0, c->key1, decide);
 	c->launches++;
 	CK(cudaGetLastError());
 	if (decide) {
