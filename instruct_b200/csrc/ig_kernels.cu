@@ -359,12 +359,13 @@ cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
 // (Q, indvlkh, sum_k log q, G) into the all-gatherable array.  The summation order depends
 // only on the chunk decomposition, which depends only on (L, K, A): shard-invariant.
 // --------------------------------------------------------------------------------------
-constexpr int EPI_GROUPS = 8;
+constexpr int EPI_GROUPS = 8;       // chunk groups (warps) per CTA
 __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const EpiArgs a)
 {
 	__shared__ int cnt_sh[EPI_GROUPS][MAX_K][32];
 	__shared__ double ll_sh[EPI_GROUPS][3][32];
 	__shared__ int nsh_sh[EPI_GROUPS][32];
+	__shared__ double gq_sh[MAX_K][32];
 	const Geometry &g = a.geo;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int il = blockIdx.x * 32 + lane;
@@ -378,10 +379,16 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 	int nsh_new = 0;
 	if (live) {
 		for (int c = w; c < g.nchunks; c += EPI_GROUPS) {
-			const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.pcnt + ((size_t)c * g.Nloc + il) * KP);
-#pragma unroll
-			for (int j = 0; j < MAX_K / 2; j++)
-				if (2 * j < KP) { const uint32_t v = pc[j]; cnt[2 * j] += v & 0xFFFFu; cnt[2 * j + 1] += v >> 16; }
+			// KP u16 counters per (chunk, individual): 8, 16 or 32 bytes, read as 64 / 128-bit vectors
+			const uint16_t *pcb = a.pcnt + ((size_t)c * g.Nloc + il) * KP;
+#define EPI_ADD(J, V) do { cnt[2 * (J)] += (V) & 0xFFFFu; cnt[2 * (J) + 1] += (V) >> 16; } while (0)
+			if (KP == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(pcb); EPI_ADD(0, t.x); EPI_ADD(1, t.y); }
+			else {
+				const uint4 t = *reinterpret_cast<const uint4 *>(pcb);
+				EPI_ADD(0, t.x); EPI_ADD(1, t.y); EPI_ADD(2, t.z); EPI_ADD(3, t.w);
+				if (KP == 16) { const uint4 t2 = *(reinterpret_cast<const uint4 *>(pcb) + 1); EPI_ADD(4, t2.x); EPI_ADD(5, t2.y); EPI_ADD(6, t2.z); EPI_ADD(7, t2.w); }
+			}
+#undef EPI_ADD
 			const double *pl = a.plog + (size_t)c * 3 * g.Nloc + il;
 			d_old += pl[0];
 			a_new += pl[(size_t)g.Nloc];
@@ -394,20 +401,33 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 	ll_sh[w][0][lane] = d_old; ll_sh[w][1][lane] = a_new; ll_sh[w][2][lane] = b_new;
 	nsh_sh[w][lane] = nsh_new;
 	__syncthreads();
-	if (w != 0 || !live) return;
-	d_old = a_new = b_new = 0.0;
-	nsh_new = 0;
+	// ---- Q_i ~ Dirichlet(cnt_i + alpha) (mcmc.c:1195-1197): the K gamma draws of an individual are the long pole
+	//      of this kernel (double-precision Marsaglia-Tsang), so warp k draws population k's gamma for the CTA's 32
+	//      individuals, each (individual, population) on its own Philox stream; warp 0 then normalises
+	const int ig_global = g.i0 + il;
+	if (live)
+		for (int k = w; k < K; k += EPI_GROUPS) {
+			int ck = 0;
+			for (int ww = 0; ww < EPI_GROUPS; ww++) ck += cnt_sh[ww][k][lane];
+			Stream sq((uint32_t)ig_global, (uint32_t)k, iter, TAG_Q, a.key0, a.key1);
+			gq_sh[k][lane] = draw_gamma(sq, (double)ck + a.sc->alpha);
+		}
+	if (w == 0 && live) {
+		d_old = a_new = b_new = 0.0;
+		nsh_new = 0;
 #pragma unroll
-	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
-	for (int ww = 0; ww < EPI_GROUPS; ww++) {
+		for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
+		for (int ww = 0; ww < EPI_GROUPS; ww++) {
 #pragma unroll
-		for (int k = 0; k < MAX_K; k++) cnt[k] += cnt_sh[ww][k][lane];
-		d_old += ll_sh[ww][0][lane]; a_new += ll_sh[ww][1][lane]; b_new += ll_sh[ww][2][lane];
-		nsh_new += nsh_sh[ww][lane];
+			for (int k = 0; k < MAX_K; k++) cnt[k] += cnt_sh[ww][k][lane];
+			d_old += ll_sh[ww][0][lane]; a_new += ll_sh[ww][1][lane]; b_new += ll_sh[ww][2][lane];
+			nsh_new += nsh_sh[ww][lane];
+		}
 	}
+	__syncthreads();
+	if (w != 0 || !live) return;
 	// heterozygotes contribute ln 2 each (genofreq, mcmc.c:1700); the count is data only
 	const double c_new = (double)a.nhet[il] * LN2_D;
-	const int ig_global = g.i0 + il;
 	double *rec = a.ind + (size_t)ig_global * g.REC;
 	if (!a.init && a.fmode == 2) {
 		rec[K] = c_new + a_new;                                // at the current F; post_sweep adds the accepted differences
@@ -438,12 +458,10 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 		rec[K + 2] = (double)(acc ? gg.y : gg.x);
 		rec[K] = c_new + (acc ? b_new : a_new);
 	}
-	const double alpha = a.sc->alpha;
-	Stream sq((uint32_t)ig_global, 0u, iter, TAG_Q, a.key0, a.key1);
 	double qv[MAX_K], sum = 0.0;
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++)
-		if (k < K) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
+		if (k < K) { qv[k] = gq_sh[k][lane]; sum += qv[k]; }
 	double slq = 0.0;
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++)
