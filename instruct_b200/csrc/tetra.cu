@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(32 * CG) tetra_q_kernel(const uint16_t *pcnt, 
                                                           uint32_t iter, uint32_t key0, uint32_t key1)
 {
 	__shared__ int shc[CG][MAX_K][32];
+	__shared__ double gq[MAX_K][32];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int il = blockIdx.x * 32 + lane;
 	const bool live = il < g.Nloc;
@@ -638,6 +639,16 @@ __global__ void __launch_bounds__(32 * CG) tetra_q_kernel(const uint16_t *pcnt, 
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++) shc[w][k][lane] = cnt[k];
 	__syncthreads();
+	// warp k draws population k's gamma for the CTA's 32 individuals (as in indiv_epilogue_kernel), warp 0 normalises
+	const int ig_global = g.i0 + il;
+	if (live)
+		for (int k = w; k < g.K; k += CG) {
+			int ck = 0;
+			for (int ww = 0; ww < CG; ww++) ck += shc[ww][k][lane];
+			Stream sq((uint32_t)ig_global, (uint32_t)k, iter, TAG_Q, key0, key1);
+			gq[k][lane] = draw_gamma(sq, (double)ck + sc->alpha);
+		}
+	__syncthreads();
 	if (w != 0 || !live) return;
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++) {
@@ -645,14 +656,11 @@ __global__ void __launch_bounds__(32 * CG) tetra_q_kernel(const uint16_t *pcnt, 
 		for (int ww = 0; ww < CG; ww++) t += shc[ww][k][lane];
 		cnt[k] = t;
 	}
-	const int ig_global = g.i0 + il;
 	double *rec = ind + (size_t)ig_global * g.REC;
-	const double alpha = sc->alpha;
-	Stream sq((uint32_t)ig_global, 0u, iter, TAG_Q, key0, key1);
 	double qv[MAX_K], sum = 0.0;
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++)
-		if (k < g.K) { qv[k] = draw_gamma(sq, (double)cnt[k] + alpha); sum += qv[k]; }
+		if (k < g.K) { qv[k] = gq[k][lane]; sum += qv[k]; }
 	double slq = 0.0;
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++)
