@@ -30,6 +30,7 @@
 // (with -e 0 the reference's own tables are log(0), tests/test_tetra_oracle_vs_reference.py),
 // allelenum_max <= 6, alpha is never updated (the reference's tetraploid driver never calls
 // update_alpha).
+#include <stdlib.h>
 #include "ig_ctx.h"
 #include "philox.cuh"
 #include "samplers.cuh"
@@ -915,9 +916,9 @@ __host__ __device__ constexpr uint32_t allo_sel(int r)
 
 // One genotype with ND observed alleles (bytes of apack, ascending): draws the resolution, returns the
 // resolved genotype g0 | g1 << 8 | g2 << 16 | g3 << 24.
-template <int ND, int KP>
-__device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack, int init, bool same, const float *tab, const uint8_t *c2i,
-                                                 const float *Pl, const float *P2l, const float (&q)[KP], float u01)
+template <int ND, int KP, bool STAGE>
+__device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack, int init, bool same, uint32_t tab_sa, const float *tab_g,
+                                                 uint32_t c2i_sa, const uint8_t *c2i_g, uint32_t p1_sa, uint32_t p2_sa, const float (&q)[KP], float u01)
 {
 	using RS = AlloRes<ND>;
 	constexpr int NR = RS::N;
@@ -928,16 +929,20 @@ __device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack,
 		for (int r = 0; r < NR; r++) w[r] = 0.0f;
 	} else if (same) {                                                 // population z's table at the resolution's genotype
 #pragma unroll
-		for (int r = 0; r < NR; r++) w[r] = tab[c2i[__dp4a(__byte_perm(apack, 0u, allo_sel<ND>(r)), npack, 0u)]] * LOG2E;
+		for (int r = 0; r < NR; r++)
+			w[r] = tab_at<STAGE>(tab_sa, tab_g, c2i_sa, c2i_g, __dp4a(__byte_perm(apack, 0u, allo_sel<ND>(r)), npack, 0u)) * LOG2E;
 	} else {                                                           // admixture-averaged frequencies of the two subgenomes
 		float lf[ND], lf2[ND];
 #pragma unroll
 		for (int t = 0; t < ND; t++) {
-			const int al = (int)((apack >> (8 * t)) & 0xFFu);
-			const float *r1 = Pl + al * KP, *r2 = P2l + al * KP;
+			const uint32_t off = ((apack >> (8 * t)) & 0xFFu) * (KP * 4u);
 			float f = 0.0f, f2 = 0.0f;
 #pragma unroll
-			for (int k = 0; k < KP; k++) { f = fmaf(q[k], r1[k], f); f2 = fmaf(q[k], r2[k], f2); }
+			for (int v = 0; v < KP / 4; v++) {
+				const float4 t1 = lds_f4(p1_sa + off + 16 * v), t2 = lds_f4(p2_sa + off + 16 * v);
+				f = fmaf(q[4 * v], t1.x, f); f = fmaf(q[4 * v + 1], t1.y, f); f = fmaf(q[4 * v + 2], t1.z, f); f = fmaf(q[4 * v + 3], t1.w, f);
+				f2 = fmaf(q[4 * v], t2.x, f2); f2 = fmaf(q[4 * v + 1], t2.y, f2); f2 = fmaf(q[4 * v + 2], t2.z, f2); f2 = fmaf(q[4 * v + 3], t2.w, f2);
+			}
 			lf[t] = lg2_fast(f); lf2[t] = lg2_fast(f2);
 		}
 #pragma unroll
@@ -967,13 +972,14 @@ struct GenoAlloArgs {
 	uint32_t iter, key0, key1;
 };
 
-template <int KP, int ROUNDS>
+template <int KP, int ROUNDS, bool STAGE>
 __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const GenoAlloArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bar;
 	const Geometry &g = a.geo;
-	const int tid = threadIdx.x, chunk = blockIdx.x, R = g.R;
+	constexpr int R = TETRA_R;
+	const int tid = threadIdx.x, chunk = blockIdx.x;
 	const int l0 = chunk * g.TL, nl = min(g.TL, g.Lpad - l0), nmt = nl / TT, rowsz = g.A * KP;
 	float *Psm = reinterpret_cast<float *>(smem_raw);
 	float *P2sm = Psm + (size_t)g.TL * rowsz;
@@ -982,18 +988,16 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 	float *tabsm = reinterpret_cast<float *>(locsm + g.TL);                       // staged tables, as in tetra_geno_kernel
 	uint8_t *c2ism = reinterpret_cast<uint8_t *>(tabsm + (size_t)g.TL * g.K * a.Gmax);
 	const int nbins = nl * rowsz;
-	const uint32_t tab_bytes = g.tab_stage ? (uint32_t)nl * (uint32_t)(g.K * a.Gmax) * 4u : 0u;
+	const uint32_t tab_bytes = STAGE ? (uint32_t)nl * (uint32_t)(g.K * a.Gmax) * 4u : 0u;
 	if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 	__syncthreads();
 	if (tid == 0) {
 		mbar_expect_tx(&bar, (uint32_t)nbins * 8u + tab_bytes);
 		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
 		tma_bulk_g2s(P2sm, a.P2 + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
-		if (tab_bytes) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
+		if (STAGE) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
 	}
-	if (g.tab_stage) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
-	const float *tabbase = g.tab_stage ? tabsm : a.tab + (size_t)l0 * g.K * a.Gmax;
-	const uint8_t *c2ibase = g.tab_stage ? c2ism : a.c2i;
+	if (STAGE) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
 	for (int j = tid; j < 2 * g.TL * rowsz * R; j += TETRA_THREADS) hist[j] = 0;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
@@ -1006,9 +1010,12 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 	const int Nloc = g.Nloc, mt0 = l0 / TT;
 	const int nsub_total = (Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
 	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
-	const uint32_t R4 = (uint32_t)R * 4u;
+	const uint32_t psm_sa = smem_addr(Psm), loc_sa = smem_addr(locsm), tab_sa0 = smem_addr(tabsm), c2i_sa0 = smem_addr(c2ism);
+	const uint32_t p2off = (uint32_t)(g.TL * rowsz) * 4u;             // P2 chunk sits right behind the P chunk
 	const uint32_t hist1_sa = smem_addr(hist) + (uint32_t)(tid & (R - 1)) * 4u;
-	const uint32_t hist2_sa = hist1_sa + (uint32_t)(g.TL * rowsz) * R4;
+	const uint32_t hist2off = (uint32_t)(g.TL * rowsz) * (4u * R);
+	const uint32_t row4 = (uint32_t)rowsz * 4u;
+	const uint32_t G4 = (uint32_t)a.Gmax * 4u, KG4 = (uint32_t)g.K * G4;
 
 	for (int sub = sub0; sub < sub1; ++sub) {
 		const int il = sub * TETRA_THREADS + tid;
@@ -1025,6 +1032,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 		int4 *gp = reinterpret_cast<int4 *>(a.Gq) + ((size_t)mt0 * Nloc + il);
 		float ll_nat = 0.0f, ll_lg2 = 0.0f;
 		int4 xa_n = ldg_stream(xp), xb_n = ldg_stream(xp + 1), zv_n = ldg_stream(zp);      // prefetch one micro-tile ahead
+		uint32_t p_sa = psm_sa, l_sa = loc_sa, t_sa = tab_sa0;                // running shared addresses of the micro-tile's first locus
+		const float *t_g = a.tab + (size_t)l0 * g.K * a.Gmax;
 		for (int mt = 0; mt < nmt; ++mt) {
 			const int4 xa = xa_n, xb = xb_n, zv = zv_n;
 			if (mt + 1 < nmt) {
@@ -1042,41 +1051,45 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 				gn[j] = 0xFFFFFFFFu;
 				// distinct alleles ascending in int16, -1 padding; all -1 = missing (data_interface.c:636-650)
 				if (xw[2 * j] & 0x8000u) continue;
-				const int nd = 1 + ((xw[2 * j] & 0x80000000u) ? 0 : 1) + ((xw[2 * j + 1] & 0x8000u) ? 0 : 1) + ((xw[2 * j + 1] & 0x80000000u) ? 0 : 1);
+				const int nd = 1 + ((xw[2 * j] >> 31) ^ 1) + (((xw[2 * j + 1] >> 15) & 1) ^ 1) + ((xw[2 * j + 1] >> 31) ^ 1);
 				const uint32_t apack = __byte_perm(xw[2 * j], xw[2 * j + 1], 0x6420);     // low bytes of the four int16
-				const int lj = mt * TT + j;
-				const int2 li = locsm[lj];
+				const int2 li = lds_i2(l_sa + 8u * j);
 				const uint32_t npack = (uint32_t)li.x;
+				const uint32_t p1_sa = p_sa + (uint32_t)j * row4, p2_sa = p1_sa + p2off;    // &P[l][0][0], &P2[l][0][0]
 				const uint32_t z0 = zw[j] & 0xFFu;
 				const bool same = (zw[j] == z0 * 0x01010101u);
-				const float *tab = tabbase + (lj * g.K + (int)z0) * a.Gmax;
-				const uint8_t *c2i = c2ibase + li.y;
-				const float *Pl = Psm + lj * rowsz, *P2l = P2sm + lj * rowsz;
+				const uint32_t tj_sa = t_sa + (uint32_t)j * KG4 + z0 * G4;
+				const float *tj_g = t_g + ((size_t)j * g.K + z0) * a.Gmax;
+				const uint32_t cj_sa = c2i_sa0 + (uint32_t)li.y;
+				const uint8_t *cj_g = a.c2i + li.y;
 				const float u01 = u01f(rj[j]);
 				uint32_t gpk;
 				if (nd == 1) gpk = (apack & 0xFFu) * 0x01010101u;
-				else if (nd == 2) gpk = allo_resolve<2, KP>(apack, npack, a.init, same, tab, c2i, Pl, P2l, q, u01);
-				else if (nd == 3) gpk = allo_resolve<3, KP>(apack, npack, a.init, same, tab, c2i, Pl, P2l, q, u01);
-				else gpk = allo_resolve<4, KP>(apack, npack, a.init, same, tab, c2i, Pl, P2l, q, u01);
+				else if (nd == 2) gpk = allo_resolve<2, KP, STAGE>(apack, npack, a.init, same, tj_sa, tj_g, cj_sa, cj_g, p1_sa, p2_sa, q, u01);
+				else if (nd == 3) gpk = allo_resolve<3, KP, STAGE>(apack, npack, a.init, same, tj_sa, tj_g, cj_sa, cj_g, p1_sa, p2_sa, q, u01);
+				else gpk = allo_resolve<4, KP, STAGE>(apack, npack, a.init, same, tj_sa, tj_g, cj_sa, cj_g, p1_sa, p2_sa, q, u01);
 				gn[j] = gpk;
 				if (a.init) continue;
-				const int g0 = (int)(gpk & 0xFFu), g1 = (int)((gpk >> 8) & 0xFFu), g2 = (int)((gpk >> 16) & 0xFFu), g3 = (int)(gpk >> 24);
-				const uint32_t z1 = (zw[j] >> 8) & 0xFFu, z2 = (zw[j] >> 16) & 0xFFu, z3 = zw[j] >> 24;
+				// the four (allele, population) bins, one per byte: geno * KP + z (< 256, no carries)
+				const uint32_t ipk = gpk * (uint32_t)KP + zw[j];
+				const uint32_t i0 = ipk & 0xFFu, i1 = (ipk >> 8) & 0xFFu, i2 = (ipk >> 16) & 0xFFu, i3 = ipk >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286, allotetraploid branch)
-				if (same) m_nat += tab[c2i[__dp4a(gpk, npack, 0u)]];
+				if (same) m_nat += tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(gpk, npack, 0u));
 				else {
-					const int nhet = (g0 != g1) + (g2 != g3);                         // classes 1,2: log 2; class 3: log 4
-					m_nat += (float)nhet * 0.6931471805599453f;
-					m_lg2 += lg2_fast(Pl[g0 * KP + z0] * Pl[g1 * KP + z1]) + lg2_fast(P2l[g2 * KP + z2] * P2l[g3 * KP + z3]);
+					// classes 1,2: log 2; class 3: log 4 -- one log 2 per heterozygous pair
+					const uint32_t hx = gpk ^ (gpk >> 8);                             // byte 0: g0 ^ g1, byte 2: g2 ^ g3
+					m_nat += (float)(((hx & 0xFFu) ? 1 : 0) + ((hx & 0xFF0000u) ? 1 : 0)) * 0.6931471805599453f;
+					m_lg2 += lg2_fast(lds_f(p1_sa + i0 * 4u) * lds_f(p1_sa + i1 * 4u)) + lg2_fast(lds_f(p2_sa + i2 * 4u) * lds_f(p2_sa + i3 * 4u));
 				}
-				const uint32_t hrow = (uint32_t)(lj * g.A * KP) * R4;
-				red_inc(hist1_sa + hrow + (uint32_t)(g0 * KP + (int)z0) * R4);
-				red_inc(hist1_sa + hrow + (uint32_t)(g1 * KP + (int)z1) * R4);
-				red_inc(hist2_sa + hrow + (uint32_t)(g2 * KP + (int)z2) * R4);
-				red_inc(hist2_sa + hrow + (uint32_t)(g3 * KP + (int)z3) * R4);
+				const uint32_t h1_sa = hist1_sa + (p1_sa - psm_sa) * (uint32_t)R, h2_sa = h1_sa + hist2off;
+				red_inc(h1_sa + i0 * (4u * R));
+				red_inc(h1_sa + i1 * (4u * R));
+				red_inc(h2_sa + i2 * (4u * R));
+				red_inc(h2_sa + i3 * (4u * R));
 			}
 			*(gp + (size_t)mt * Nloc) = make_int4((int)gn[0], (int)gn[1], (int)gn[2], (int)gn[3]);
 			ll_nat += m_nat; ll_lg2 += m_lg2;
+			p_sa += TT * row4; l_sa += TT * 8u; t_sa += TT * KG4; t_g += (size_t)TT * g.K * a.Gmax;
 		}
 		if (!a.init) {
 			a.lpart[((size_t)chunk * 2) * Nloc + il] = ll_nat;
@@ -1236,8 +1249,12 @@ static cudaError_t tetra_configure(Geometry &g, int device, bool allo, int Gmax,
 	g.TL = tl;
 	g.nchunks = (g.Lpad + tl - 1) / tl;
 	const int nsub_total = (g.Nloc + TETRA_THREADS - 1) / TETRA_THREADS;
-	int nblk = 1;
-	if (g.nchunks < target) nblk = std::min(nsub_total, (target + g.nchunks - 1) / g.nchunks);
+	// about 15 waves of CTAs (3 resident per SM, allotetraploid 2): at config 5 (556 chunks, 79 passes) 2 / 4 / 6 / 12
+	// individual blocks give 6.85 / 6.57 / 6.35 / 6.29 ms per sweep
+	const int want_ctas = 15 * (allo ? 2 : 3) * sms;
+	int nblk = std::max(1, std::min(nsub_total, (want_ctas + g.nchunks - 1) / g.nchunks));
+	if (g.nchunks >= (allo ? 2 : 3) * sms && nsub_total >= 2) nblk = std::min(nblk, nsub_total / 2);     // as in zq_configure
+	if (const char *e = getenv("IG_TETRA_NBLK")) nblk = std::max(1, std::min(nsub_total, atoi(e)));       // tuning hook
 	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
 	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
 	g.R = R;
@@ -1390,16 +1407,18 @@ static ig_status tetra_pass_b_allo(ig_ctx *c, int init)
 	               c->iter, c->key0, c->key1};
 	dim3 grid(g.nchunks, g.nblk), block(TETRA_THREADS);
 	const size_t sm = smem_geno_allo(g, t->Gmax);
+#define ALLO_LAUNCH1(KPV, RV, ST) do { CK(opt_smem(tetra_geno_allo_kernel<KPV, RV, ST>, sm)); tetra_geno_allo_kernel<KPV, RV, ST><<<grid, block, sm, c->stream>>>(a); } while (0)
 #define ALLO_LAUNCH(KPV)                                                                                                   \
 	do {                                                                                                               \
-		if (c->rounds == 10) { CK(opt_smem(tetra_geno_allo_kernel<KPV, 10>, sm)); tetra_geno_allo_kernel<KPV, 10><<<grid, block, sm, c->stream>>>(a); } \
-		else { CK(opt_smem(tetra_geno_allo_kernel<KPV, 7>, sm)); tetra_geno_allo_kernel<KPV, 7><<<grid, block, sm, c->stream>>>(a); }               \
+		if (c->rounds == 10) { if (g.tab_stage) ALLO_LAUNCH1(KPV, 10, true); else ALLO_LAUNCH1(KPV, 10, false); }     \
+		else { if (g.tab_stage) ALLO_LAUNCH1(KPV, 7, true); else ALLO_LAUNCH1(KPV, 7, false); }                       \
 	} while (0)
 	switch (g.KP) {
 	case 4: ALLO_LAUNCH(4); break;
 	case 8: ALLO_LAUNCH(8); break;
 	default: ALLO_LAUNCH(16); break;
 	}
+#undef ALLO_LAUNCH1
 #undef ALLO_LAUNCH
 	CK(cudaGetLastError());
 	if (t->timing && !init) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; t->timing = false; }

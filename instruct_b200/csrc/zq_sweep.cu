@@ -24,6 +24,7 @@
 //     a missing genotype somewhere in the warp.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "ig_internal.h"
 #include "philox.cuh"
 #include "sweep_common.cuh"
@@ -414,9 +415,15 @@ cudaError_t zq_configure(Geometry &g, int device)
 	if (tl > tl_max) tl = tl_max;
 	g.TL = tl;
 	g.nchunks = (g.Lpad + tl - 1) / tl;
-	int nblk = 1;
-	if (g.nchunks < target_ctas) nblk = min(nsub_total, (target_ctas + g.nchunks - 1) / g.nchunks);
+	// about 15 waves of CTAs: measured at config 4 (569 chunks, 40 passes of 256 individuals), 2 / 4 / 8 / 10 / 20
+	// individual blocks give 4.42 / 4.38 / 4.26 / 4.30 / 4.31 ms per launch -- a coarse grid loses its last wave
+	const int want_ctas = 15 * ZQ_MIN_CTAS * sms;
+	int nblk = min(nsub_total, (want_ctas + g.nchunks - 1) / g.nchunks);
+	// a CTA's prologue (P chunk, zeroed histogram) wants at least two passes behind it once the chunks alone fill the
+	// GPU: a shard of 1250 individuals (5 passes) runs 0.591 ms per launch as 2 blocks, 0.603 ms as 5
+	if (g.nchunks >= ZQ_MIN_CTAS * sms && nsub_total >= 2) nblk = min(nblk, nsub_total / 2);
 	if (nblk < 1) nblk = 1;
+	if (const char *e = getenv("IG_ZQ_NBLK")) nblk = max(1, min(nsub_total, atoi(e)));       // tuning hook
 	g.subs_per_blk = (nsub_total + nblk - 1) / nblk;
 	g.nblk = (nsub_total + g.subs_per_blk - 1) / g.subs_per_blk;
 	g.R = R;
