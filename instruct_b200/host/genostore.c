@@ -272,6 +272,125 @@ int gs_read(const char *path, const gs_options *opt, gs_store *out, char *err, i
 	return 0;
 }
 
+/* ------------------------------------------------------------------ packed on-disk form */
+#define GS_MAGIC "IGSTORE1"
+
+static int wr_i32(FILE *f, int32_t v) { return fwrite(&v, 4, 1, f) == 1 ? 0 : 1; }
+static int wr_str(FILE *f, const char *s)
+{
+	const int32_t n = s ? (int32_t)strlen(s) : -1;
+	if (wr_i32(f, n)) return 1;
+	return (n > 0 && fwrite(s, 1, (size_t)n, f) != (size_t)n) ? 1 : 0;
+}
+static int rd_i32(FILE *f, int32_t *v) { return fread(v, 4, 1, f) == 1 ? 0 : 1; }
+static int rd_str(FILE *f, char **out)
+{
+	int32_t n;
+	*out = NULL;
+	if (rd_i32(f, &n)) return 1;
+	if (n < 0) return 0;
+	if (n > 1 << 20) return 1;
+	*out = (char *)malloc((size_t)n + 1);
+	if (!*out) return 1;
+	if (n > 0 && fread(*out, 1, (size_t)n, f) != (size_t)n) return 1;
+	(*out)[n] = '\0';
+	return 0;
+}
+
+int gs_save(const char *path, const gs_store *s, char *err, int errlen)
+{
+	FILE *f = fopen(path, "wb");
+	int bad = 0, i, l;
+	const size_t nx = (size_t)s->locinum * s->totalsize * s->ploid;
+	if (!f) return fail(err, errlen, "genostore: cannot create the packed store");
+	bad |= fwrite(GS_MAGIC, 1, 8, f) != 8;
+	bad |= wr_i32(f, s->ploid) | wr_i32(f, s->totalsize) | wr_i32(f, s->locinum) | wr_i32(f, s->locinum_file) | wr_i32(f, s->allelenum_max);
+	bad |= wr_i32(f, s->pop_count) | wr_i32(f, s->n_extra_col);
+	bad |= wr_i32(f, s->marker_names != NULL) | wr_i32(f, s->indvname != NULL) | wr_i32(f, s->popindx != NULL) | wr_i32(f, s->extra_col != NULL);
+	bad |= fwrite(s->allelenum, 4, (size_t)s->locinum, f) != (size_t)s->locinum;
+	bad |= fwrite(s->locus_of, 4, (size_t)s->locinum, f) != (size_t)s->locinum;
+	bad |= fwrite(s->missvec, 4, (size_t)s->totalsize, f) != (size_t)s->totalsize;
+	bad |= fwrite(s->x, 2, nx, f) != nx;
+	for (l = 0; l < s->locinum && !bad; l++)
+		for (i = 0; i < s->allelenum[l]; i++) bad |= wr_str(f, s->alleletype[l][i]);
+	if (s->marker_names) for (l = 0; l < s->locinum_file && !bad; l++) bad |= wr_str(f, s->marker_names[l]);
+	if (s->indvname) for (i = 0; i < s->totalsize && !bad; i++) bad |= wr_str(f, s->indvname[i]);
+	if (s->popindx) bad |= fwrite(s->popindx, 4, (size_t)s->totalsize, f) != (size_t)s->totalsize;
+	for (i = 0; i < s->pop_count && !bad; i++) bad |= wr_str(f, s->poptype[i]);
+	if (s->extra_col)
+		for (i = 0; i < s->totalsize && !bad; i++)
+			for (l = 0; l < s->n_extra_col; l++) bad |= wr_str(f, s->extra_col[i] ? s->extra_col[i][l] : NULL);
+	bad |= wr_i32(f, 0x45444e45);                         /* "ENDE": a truncated file is detected on load */
+	if (fclose(f) != 0) bad = 1;
+	return bad ? fail(err, errlen, "genostore: write error on the packed store") : 0;
+}
+
+int gs_load(const char *path, gs_store *out, char *err, int errlen)
+{
+	FILE *f = fopen(path, "rb");
+	char magic[8];
+	int32_t h[11], tail = 0;
+	int bad = 0, i, l;
+	size_t nx;
+	memset(out, 0, sizeof(*out));
+	if (!f) return fail(err, errlen, "genostore: cannot open the packed store");
+	if (fread(magic, 1, 8, f) != 8 || memcmp(magic, GS_MAGIC, 8) != 0) { fclose(f); return fail(err, errlen, "genostore: not a packed store (bad magic)"); }
+	for (i = 0; i < 11; i++) bad |= rd_i32(f, &h[i]);
+	if (bad || (h[0] != 2 && h[0] != 4) || h[1] < 1 || h[2] < 0 || h[3] < h[2] || h[4] < 0 || h[4] > 32767 || h[5] < 0 || h[6] < 0) {
+		fclose(f);
+		return fail(err, errlen, "genostore: corrupt header in the packed store");
+	}
+	out->ploid = h[0]; out->totalsize = h[1]; out->locinum = h[2]; out->locinum_file = h[3]; out->allelenum_max = h[4];
+	out->pop_count = h[5]; out->n_extra_col = h[6];
+	nx = (size_t)out->locinum * out->totalsize * out->ploid;
+	out->allelenum = (int32_t *)malloc(sizeof(int32_t) * (size_t)(out->locinum ? out->locinum : 1));
+	out->locus_of = (int *)malloc(sizeof(int) * (size_t)(out->locinum ? out->locinum : 1));
+	out->missvec = (int *)malloc(sizeof(int) * (size_t)out->totalsize);
+	out->x = (int16_t *)malloc(sizeof(int16_t) * (nx ? nx : 1));
+	if (!out->allelenum || !out->locus_of || !out->missvec || !out->x) bad = 1;
+	if (!bad) {
+		bad |= fread(out->allelenum, 4, (size_t)out->locinum, f) != (size_t)out->locinum;
+		bad |= fread(out->locus_of, 4, (size_t)out->locinum, f) != (size_t)out->locinum;
+		bad |= fread(out->missvec, 4, (size_t)out->totalsize, f) != (size_t)out->totalsize;
+		bad |= fread(out->x, 2, nx, f) != nx;
+	}
+	for (l = 0; l < out->locinum && !bad; l++) if (out->allelenum[l] < 0 || out->allelenum[l] > out->allelenum_max) bad = 1;
+	if (!bad) {
+		out->alleletype = (char ***)calloc((size_t)(out->locinum ? out->locinum : 1), sizeof(char **));
+		for (l = 0; l < out->locinum && !bad; l++) {
+			out->alleletype[l] = (char **)calloc((size_t)(out->allelenum[l] ? out->allelenum[l] : 1), sizeof(char *));
+			for (i = 0; i < out->allelenum[l] && !bad; i++) bad |= rd_str(f, &out->alleletype[l][i]);
+		}
+	}
+	if (!bad && h[7]) {
+		out->marker_names = (char **)calloc((size_t)out->locinum_file, sizeof(char *));
+		for (l = 0; l < out->locinum_file && !bad; l++) bad |= rd_str(f, &out->marker_names[l]);
+	}
+	if (!bad && h[8]) {
+		out->indvname = (char **)calloc((size_t)out->totalsize, sizeof(char *));
+		for (i = 0; i < out->totalsize && !bad; i++) bad |= rd_str(f, &out->indvname[i]);
+	}
+	if (!bad && h[9]) {
+		out->popindx = (int *)malloc(sizeof(int) * (size_t)out->totalsize);
+		bad |= fread(out->popindx, 4, (size_t)out->totalsize, f) != (size_t)out->totalsize;
+	}
+	if (!bad) {
+		out->poptype = (char **)calloc((size_t)(out->pop_count ? out->pop_count : 1), sizeof(char *));
+		for (i = 0; i < out->pop_count && !bad; i++) bad |= rd_str(f, &out->poptype[i]);
+	}
+	if (!bad && h[10]) {
+		out->extra_col = (char ***)calloc((size_t)out->totalsize, sizeof(char **));
+		for (i = 0; i < out->totalsize && !bad; i++) {
+			out->extra_col[i] = (char **)calloc((size_t)(out->n_extra_col ? out->n_extra_col : 1), sizeof(char *));
+			for (l = 0; l < out->n_extra_col && !bad; l++) bad |= rd_str(f, &out->extra_col[i][l]);
+		}
+	}
+	if (!bad) bad |= rd_i32(f, &tail) || tail != 0x45444e45;
+	fclose(f);
+	if (bad) { gs_free(out); return fail(err, errlen, "genostore: truncated or corrupt packed store"); }
+	return 0;
+}
+
 void gs_free(gs_store *s)
 {
 	int i, l;
@@ -279,17 +398,18 @@ void gs_free(gs_store *s)
 	free(s->x);
 	if (s->alleletype)
 		for (l = 0; l < s->locinum; l++) {
+			if (!s->alleletype[l]) continue;                 /* a load that stopped half way */
 			for (i = 0; i < s->allelenum[l]; i++) free(s->alleletype[l][i]);
 			free(s->alleletype[l]);
 		}
 	free(s->alleletype); free(s->allelenum); free(s->locus_of); free(s->missvec);
-	if (s->marker_names) { for (l = 0; l < s->locinum_file; l++) free(s->marker_names[l]); free(s->marker_names); }
+	if (s->marker_names) { for (l = 0; l < s->locinum_file; l++) free(s->marker_names[l]); free(s->marker_names); }   /* free(NULL) is fine */
 	if (s->indvname) { for (i = 0; i < s->totalsize; i++) free(s->indvname[i]); free(s->indvname); }
 	if (s->extra_col) {
 		for (i = 0; i < s->totalsize; i++) if (s->extra_col[i]) { for (l = 0; l < s->n_extra_col; l++) free(s->extra_col[i][l]); free(s->extra_col[i]); }
 		free(s->extra_col);
 	}
-	for (i = 0; i < s->pop_count; i++) free(s->poptype[i]);
+	if (s->poptype) for (i = 0; i < s->pop_count; i++) free(s->poptype[i]);
 	free(s->poptype); free(s->popindx);
 	memset(s, 0, sizeof(*s));
 }

@@ -54,4 +54,12 @@ typedef struct gs_store {
 int gs_read(const char *path, const gs_options *opt, gs_store *out, char *err, int errlen);
 void gs_free(gs_store *s);
 
+/* Packed on-disk form of a store: the int16 matrix exactly as
+ * ig_load_genotypes() takes it, plus every table the result writer needs (allele strings, marker and
+ * individual names, population labels, extra columns), so that a second run on the same data skips the
+ * text reader altogether -- at config-4 size the text file is ~6 GB of tokens, the packed store 4 GB read
+ * with one fread.  Little-endian, versioned by the magic; gs_load() validates every length it reads. */
+int gs_save(const char *path, const gs_store *s, char *err, int errlen);
+int gs_load(const char *path, gs_store *out, char *err, int errlen);
+
 #endif

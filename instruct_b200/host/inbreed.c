@@ -16,6 +16,9 @@
  *                            one NCCL int32 all-reduce + one all-gather per sweep
  *   --ref-compat-gr          print the Gelman-Rubin value exactly as the reference computes it
  *   --quiet-data             do not echo the recoded genotype matrix to stdout
+ *   --save-store FILE        also write the packed genotype store (int16 matrix + name tables) to FILE
+ *   --load-store FILE        read the packed store instead of parsing the text file (-d is then only echoed)
+ *   --pack-only              stop after --save-store (text -> packed conversion; needs no GPU)
  */
 #define _GNU_SOURCE
 #include <pthread.h>
@@ -36,7 +39,8 @@ static int label = 1, popdata = 1, prior_flag = 0, back_refl = 1, type_freq = 1,
 static int n_extra_col = 0, markername_flag = 0, print_iter = 1, print_freq = 0, n_small = 1, n_large = 0, inf_K = 0;
 static int distr_fmt = 1, autopoly = 1, data_fmt = 0, mode = 1;
 static long seeds[3] = {13, 4, 1972};               /* random.c:10-12 */
-static int n_gpus = 1, shard_individuals = 0, ref_compat_gr = 0, quiet_data = 0;
+static int n_gpus = 1, shard_individuals = 0, ref_compat_gr = 0, quiet_data = 0, pack_only = 0;
+static const char *save_store = NULL, *load_store = NULL;
 
 static void die(const char *msg)                    /* nrerror's output convention, nrutil.c:9-16 */
 {
@@ -53,7 +57,8 @@ static void parse_args(int argc, char **argv)
 	    "[-f prior_flag] [-v mode] [-h alpha_dpm] [-e back_refl] [-y type_freq] [-j nstep_check_empty_cluster] "
 	    "[-x extra_columns] [-w markername] [-cf convgfilename] [-pi print_iter] [-pf print_freq]  [-ik inf_K] "
 	    "[-kv n_small n_large] [-df distr_fmt] [-ap autopoly] [-af data_fmt] [-mm max_mem] "
-	    "[--gpus N] [--shard chains|individuals] [--ref-compat-gr] [--quiet-data]\n";
+	    "[--gpus N] [--shard chains|individuals] [--ref-compat-gr] [--quiet-data] "
+	    "[--save-store file] [--load-store file] [--pack-only]\n";
 	int i;
 	if (argc == 2 && strcmp(argv[1], "-h") == 0) { fprintf(stdout, "%s", synopsis); exit(1); }
 	if (argc < 5) die("Too few arguments in the command line!");
@@ -98,6 +103,9 @@ static void parse_args(int argc, char **argv)
 		else if (ARG("--shard")) shard_individuals = (strcmp(argv[i + 1], "individuals") == 0);
 		else if (strcmp(argv[i], "--ref-compat-gr") == 0) ref_compat_gr = 1;
 		else if (strcmp(argv[i], "--quiet-data") == 0) quiet_data = 1;
+		else if (ARG("--save-store")) save_store = argv[i + 1];
+		else if (ARG("--load-store")) load_store = argv[i + 1];
+		else if (strcmp(argv[i], "--pack-only") == 0) pack_only = 1;
 	}
 #undef ARG
 	if (!datafilename || !outfilename) die("Both -d data_file and -o output_file are required!");
@@ -313,7 +321,19 @@ int main(int argc, char **argv)
 	go.quiet = quiet_data;
 	if (ploid != 2 && ploid != 4) die("ploid must be 2 or 4");
 	if (ploid == 4 && autopoly != 1 && autopoly != 0) die("-ap must be 1 (autotetraploid) or 0 (allotetraploid)");
-	if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
+	/* --load-store: the packed store a previous run wrote with --save-store replaces the text reader */
+	if (load_store) {
+		if (gs_load(load_store, &gs, err, sizeof err)) die(err);
+		if (gs.ploid != ploid) die("--load-store: the packed store was written for another ploidy (-p)");
+		fprintf(stdout, "Packed genotype store %s: %d individuals, %d polymorphic loci of %d.\n", load_store, gs.totalsize, gs.locinum, gs.locinum_file);
+	} else if (gs_read(datafilename, &go, &gs, err, sizeof err)) die(err);
+	if (save_store && gs_save(save_store, &gs, err, sizeof err)) die(err);
+	if (pack_only) {                                     /* text -> packed store, no chain (needs no GPU) */
+		if (!save_store) die("--pack-only needs --save-store file");
+		fprintf(stdout, "Packed genotype store written to %s\n", save_store);
+		gs_free(&gs);
+		return 0;
+	}
 	N = gs.totalsize; K = popnum; ns = ((mode == 3 || mode == 5) && ploid == 2) ? N : K;
 	/* mem_cal, InStruct.c:204-225 (the estimate is the reference's; kept for its two log lines) */
 	memreq = (print_freq ? 8.0 * K * gs.locinum * gs.allelenum_max : 0.0) + 8.0 + 8.0 * N + 8.0 * ns + 4.0 * N + 8.0 * N * K;

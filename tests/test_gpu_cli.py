@@ -255,3 +255,24 @@ def test_cli_multi_gpu_result_files_are_identical(tmp_path):
         outs[name] = re.sub(rb"Output File:   .*\n", b"Output File:   X\n", t)
     assert outs["one"] == outs["chains"]
     assert outs["one"] == outs["individuals"]
+
+
+def test_cli_packed_store_gives_the_same_result_file(tmp_path):
+    """--save-store / --load-store: a run that reads the packed store instead of the
+    text file writes the same result file, byte for byte apart from the echoed command line."""
+    d = make_dataset(N=90, L=15, K=2, A=5, miss=0.04, seed=77)
+    data = str(tmp_path / "geno.txt")
+    write_reference_text(data, d.x, pop=d.pop)
+    store = str(tmp_path / "geno.igs")
+    flags = ["-K", "2", "-L", str(d.L), "-N", str(d.N), "-p", "2", "-u", "400", "-b", "100", "-t", "5", "-c", "2",
+             "-v", "2", "-g", "1", "-r", "10", "-pi", "0", "-s", "13", "4", "1972", "--quiet-data"]
+    outs = []
+    for extra in (["--save-store", store], ["--load-store", store]):
+        out = str(tmp_path / f"o{len(outs)}.txt")
+        p = subprocess.run([INBREED, "-d", data, "-o", out] + flags + extra, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        t = open(out, "rb").read()
+        t = re.sub(rb"Command line arguments:\n.*\n", b"", t)
+        outs.append(re.sub(rb"Output File:   .*\n", b"Output File:   X\n", t))
+    assert os.path.getsize(store) > 2 * d.N * d.L
+    assert outs[0] == outs[1]

@@ -59,6 +59,8 @@ def host():
     lib = C.CDLL(HOST_SO)
     lib.gs_read.argtypes = [C.c_char_p, C.POINTER(GsOptions), C.POINTER(GsStore), C.c_char_p, C.c_int]
     lib.gs_free.argtypes = [C.POINTER(GsStore)]
+    lib.gs_save.argtypes = [C.c_char_p, C.POINTER(GsStore), C.c_char_p, C.c_int]
+    lib.gs_load.argtypes = [C.c_char_p, C.POINTER(GsStore), C.c_char_p, C.c_int]
     lib.wr_chain.argtypes = [C.c_char_p, C.POINTER(WrRun), C.POINTER(WrData), C.POINTER(WrChain), C.POINTER(C.c_double)]
     lib.wr_gelman_rubin.restype = C.c_double
     lib.wr_gelman_rubin.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
@@ -203,3 +205,77 @@ def test_packer_matches_reference_reader_tetraploid(host, tmp_path):
     mv = np.ctypeslib.as_array(st.missvec, (N,))
     assert np.array_equal(mv, rmiss.sum(axis=0))
     host.gs_free(C.byref(st))
+
+
+def _strings(pp, n):
+    a = C.cast(pp, C.POINTER(C.c_char_p))
+    return [a[i] for i in range(n)]
+
+
+@pytest.mark.parametrize("label,popdata,extra,fmt,markers", [(1, 1, 2, 0, 1), (0, 0, 0, 1, 0)])
+def test_packed_store_round_trip(host, tmp_path, label, popdata, extra, fmt, markers):
+    """gs_save / gs_load: the packed store carries the int16 matrix exactly as
+    ig_load_genotypes() takes it and every table the result writer reads; a damaged file is refused."""
+    rng = np.random.default_rng(5)
+    d = make_dataset(N=23, L=14, K=3, A=5, miss=0.08, seed=78)
+    x = d.x.copy()
+    x[3] = np.where(x[3] >= 0, 0, x[3])
+    alleles = [[str(int(v)) for v in rng.permutation(np.arange(100, 140))[:8]] for _ in range(x.shape[0])]
+    p = str(tmp_path / "geno.txt")
+    _write_text(p, x, d.pop, label, popdata, extra, fmt, markers, alleles)
+    opt = GsOptions(2, 23, 14, b"-9", label, popdata, extra, markers, fmt, 1)
+    a, b = GsStore(), GsStore()
+    err = C.create_string_buffer(512)
+    assert host.gs_read(p.encode(), C.byref(opt), C.byref(a), err, 512) == 0, err.value
+    q = str(tmp_path / "geno.igs")
+    assert host.gs_save(q.encode(), C.byref(a), err, 512) == 0, err.value
+    assert host.gs_load(q.encode(), C.byref(b), err, 512) == 0, err.value
+    for f in ("ploid", "totalsize", "locinum", "locinum_file", "allelenum_max", "pop_count", "n_extra_col"):
+        assert getattr(a, f) == getattr(b, f), f
+    N, L = a.totalsize, a.locinum
+    assert np.array_equal(np.ctypeslib.as_array(a.x, (L, N, 2)), np.ctypeslib.as_array(b.x, (L, N, 2)))
+    for f, n in (("allelenum", L), ("locus_of", L), ("missvec", N)):
+        assert np.array_equal(np.ctypeslib.as_array(getattr(a, f), (n,)), np.ctypeslib.as_array(getattr(b, f), (n,))), f
+    an = np.ctypeslib.as_array(a.allelenum, (L,))
+    ta, tb = C.cast(a.alleletype, C.POINTER(C.c_void_p)), C.cast(b.alleletype, C.POINTER(C.c_void_p))
+    for l in range(L):
+        assert _strings(ta[l], int(an[l])) == _strings(tb[l], int(an[l]))
+    assert bool(a.marker_names) == bool(b.marker_names) == bool(markers)
+    if markers:
+        assert _strings(a.marker_names, a.locinum_file) == _strings(b.marker_names, a.locinum_file)
+    assert bool(a.indvname) == bool(b.indvname)
+    if label:
+        assert [a.indvname[i] for i in range(N)] == [b.indvname[i] for i in range(N)]
+    if popdata:
+        assert np.array_equal(np.ctypeslib.as_array(a.popindx, (N,)), np.ctypeslib.as_array(b.popindx, (N,)))
+        assert [a.poptype[i] for i in range(a.pop_count)] == [b.poptype[i] for i in range(a.pop_count)]
+    if extra:
+        ea, eb = C.cast(a.extra_col, C.POINTER(C.c_void_p)), C.cast(b.extra_col, C.POINTER(C.c_void_p))
+        for i in range(N):
+            assert _strings(ea[i], extra) == _strings(eb[i], extra)
+    host.gs_free(C.byref(b))
+    # a truncated file and a foreign file are refused with a message, not read
+    raw = open(q, "rb").read()
+    open(q, "wb").write(raw[: len(raw) // 2])
+    assert host.gs_load(q.encode(), C.byref(b), err, 512) != 0 and b"packed store" in err.value
+    open(q, "wb").write(b"NOTASTORE" + raw[9:])
+    assert host.gs_load(q.encode(), C.byref(b), err, 512) != 0 and b"magic" in err.value
+    host.gs_free(C.byref(a))
+
+
+def test_cli_pack_only_needs_no_gpu(tmp_path):
+    """`inbreed --pack-only --save-store f`: text -> packed conversion stops before any CUDA call."""
+    out = subprocess.run(["make", "-C", HOST], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = make_dataset(N=30, L=12, K=2, A=4, miss=0.05, seed=79)
+    alleles = [[str(100 + a) for a in range(8)] for _ in range(d.x.shape[0])]
+    p = str(tmp_path / "g.txt")
+    _write_text(p, d.x, d.pop, 1, 1, 0, 0, 0, alleles)
+    q = str(tmp_path / "g.igs")
+    r = subprocess.run([os.path.join(HOST, "inbreed"), "-d", p, "-o", str(tmp_path / "o.txt"), "-K", "2", "-L", "12", "-N", "30",
+                        "-lb", "1", "-a", "1", "--quiet-data", "--pack-only", "--save-store", q], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(q, "rb").read()
+    assert raw[:8] == b"IGSTORE1" and raw[-4:] == b"ENDE"
+    hdr = np.frombuffer(raw[8:8 + 20], dtype=np.int32)
+    assert tuple(hdr[:3]) == (2, 30, 12)
