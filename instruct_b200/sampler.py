@@ -257,6 +257,17 @@ class Sampler:
         ch = res.chain(name or f"Chain#{chain_id + 1}")
         return ch, cv[: self.cfg.ckrep]
 
+    def trace(self, update, burnin, thinning=1):
+        """Sweeps an initialised chain and keeps the retained draws (same schedule as mcmc_updating: sweep `step` is kept
+        when step >= burnin and (step + 1 - burnin) % thinning == 0) of the log-likelihood, the rates S and Q -- the
+        input of converge.chain_diagnostics.  One device -> host read per retained sweep: a diagnostic, not the hot path."""
+        ll, S, Q = [], [], []
+        for step in range(update):
+            self.sweep(1)
+            if step >= burnin and (step + 1 - burnin) % thinning == 0:
+                ll.append(float(self.get(_lib.STATE_TOTALLKH)[0])); S.append(self.get(_lib.STATE_S)); Q.append(self.get(_lib.STATE_Q))
+        return np.array(ll), np.array(S), np.array(Q)
+
     # -- state hooks -------------------------------------------------------------------
     def _shape(self, sid):
         L, N, K, Nl, A = self.L, self.N, self.K, self.Nloc, self.A

@@ -108,3 +108,38 @@ def test_allo_fixture():
     assert c["flag"] == int(g["flag"]) == 0
     for k in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
         np.testing.assert_allclose(np.asarray(c[k]), g[k], rtol=1e-12, atol=0, err_msg=k)
+
+
+def test_gelman_rubin_params_and_label_alignment():
+    """R per parameter and the label-switching alignment it needs."""
+    from instruct_b200.converge import align_labels, chain_diagnostics, gelman_rubin, gelman_rubin_params
+    rng = np.random.default_rng(1)
+    m, n, N, K = 4, 60, 30, 3
+    home = rng.integers(0, K, size=N)
+    Qtrue = np.full((N, K), 0.05); Qtrue[np.arange(N), home] = 0.9
+    Strue = np.array([0.2, 0.5, 0.8])
+    perms = [np.arange(K), np.array([2, 0, 1]), np.array([1, 2, 0]), np.array([0, 2, 1])]
+    ll = rng.normal(-1000, 3, size=(m, n))
+    S = np.empty((m, n, K)); Q = np.empty((m, n, N, K))
+    for c in range(m):
+        inv = np.argsort(perms[c])
+        S[c] = (Strue + rng.normal(0, 0.02, size=(n, K)))[:, inv]          # chain c calls true cluster a "inv[a]"...
+        Q[c] = (Qtrue[None] + rng.normal(0, 0.01, size=(n, N, K)))[:, :, inv]
+    # per-parameter R agrees with the scalar statistic
+    assert abs(gelman_rubin_params(ll[:, :, None])[0] - gelman_rubin(ll)) < 1e-12
+    # without alignment the switched labels look unconverged, with it they do not
+    assert np.nanmax(gelman_rubin_params(S)) > 2.0
+    for c in range(m):
+        p = align_labels(Q[0].mean(axis=0), Q[c].mean(axis=0))
+        assert np.array_equal(Q[c].mean(axis=0)[:, p].argmax(axis=1), home)
+    d = chain_diagnostics(ll, S, Q)
+    assert d["R_loglik"] < 1.1 and np.all(d["R_S"] < 1.1) and np.all(d["R_cluster_size"] < 1.1)
+    # a chain stuck elsewhere is flagged on S only
+    S2 = S.copy(); S2[3, :, np.argsort(perms[3])[1]] += 0.3
+    assert chain_diagnostics(ll, S2, Q)["R_S"].max() > 1.5
+    # the greedy branch (K > 7) finds a planted permutation too
+    K2 = 9
+    q0 = np.eye(K2)[rng.integers(0, K2, size=200)] * 0.9 + 0.01
+    pp = rng.permutation(K2)
+    got = align_labels(q0, q0[:, pp])
+    assert np.allclose(q0[:, pp][:, got], q0)
