@@ -104,6 +104,24 @@ __device__ __forceinline__ float uniform_big(uint32_t r, const RegConst &k)
 template <int KP>
 __device__ __forceinline__ float pick_category(const float (&c)[KP], float ub)
 {
+#ifdef IG_PICK_BSEARCH
+	// EXPERIMENT (not built by default): the cumulative weights are non-decreasing, so the
+	// count #{k : t > c_k} is a three-level compare / select search for KP = 8 -- identical decisions, fewer issue slots
+	// (static SASS count in profiles/r1_zq_sweep_bsearch_sass.txt), but on the half-rate ALU pipe.  To be measured.
+	if (KP == 8) {
+		const float t = (ub * 1.1754943508222875e-38f) * c[KP - 1];          // 2^-126: a power of two, so t > c_k decides exactly as above
+		const bool p2 = t > c[3];
+		const float m1 = p2 ? c[5] : c[1];
+		const bool p1 = t > m1;
+		const float lo = p1 ? c[2] : c[0], hi = p1 ? c[6] : c[4];
+		const float m0 = p2 ? hi : lo;
+		const bool p0 = t > m0;
+		float z = p2 ? 4.0f : 0.0f;
+		z = p1 ? z + 2.0f : z;
+		z = p0 ? z + 1.0f : z;
+		return z;
+	}
+#endif
 	const float tb = ub * c[KP - 1];                                      // t * 2^126, t = u * total
 	float s[KP - 1];
 #pragma unroll
