@@ -42,7 +42,7 @@ typedef enum ig_status {
 /* Flat replacement for the fields of SEQDATA (data_interface.h:10-56) and INIT
  * (initial.h:9-21) that mcmc_updating() reads. */
 typedef struct ig_config {
-	int32_t ploid;                      /* SEQDATA.ploid: 2 (4: autotetraploid driver)          */
+	int32_t ploid;                      /* SEQDATA.ploid: 2, or 4 (mcmc_POP_tetra_selfing)      */
 	int32_t popnum;                     /* SEQDATA.popnum, K                                    */
 	int32_t locinum;                    /* SEQDATA.locinum, L (polymorphic loci)                */
 	int32_t totalsize;                  /* SEQDATA.totalsize, N over ALL shards                 */
@@ -54,7 +54,7 @@ typedef struct ig_config {
 	int32_t nstep_check_empty_cluster;  /* SEQDATA.nstep_check_empty_cluster                    */
 	int32_t print_iter;                 /* SEQDATA.print_iter                                   */
 	int32_t print_freq;                 /* SEQDATA.print_freq: also accumulate P moments        */
-	int32_t autopoly;                   /* SEQDATA.autopoly                                     */
+	int32_t autopoly;                   /* SEQDATA.autopoly: 1 auto-, 0 allotetraploid (-ap)    */
 	int64_t update;                     /* INIT.update: total sweeps                            */
 	int64_t burnin;                     /* INIT.burnin                                          */
 	int32_t thinning;                   /* INIT.thinning                                        */
