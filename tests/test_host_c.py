@@ -279,3 +279,50 @@ def test_cli_pack_only_needs_no_gpu(tmp_path):
     assert raw[:8] == b"IGSTORE1" and raw[-4:] == b"ENDE"
     hdr = np.frombuffer(raw[8:8 + 20], dtype=np.int32)
     assert tuple(hdr[:3]) == (2, 30, 12)
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_packer_fuzz_against_reference_reader(host, tmp_path, case):
+    """Random small files (shape, allele count, missingness up to whole individuals and whole loci, monomorphic loci,
+    both line formats, every combination of label / population / extra / marker columns): the packer and the reference's
+    own reader must agree on every cell, allele count and missing count."""
+    rng = np.random.default_rng(1000 + case)
+    N, L, A = int(rng.integers(2, 30)), int(rng.integers(1, 25)), int(rng.integers(2, 9))
+    label, popdata, extra, fmt, markers = (int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 3)),
+                                           int(rng.integers(0, 2)), int(rng.integers(0, 2)))
+    x = rng.integers(0, A, size=(L, N, 2)).astype(np.int16)
+    miss = rng.random((L, N, 2)) < rng.choice([0.0, 0.05, 0.4])
+    x[miss] = -9
+    for l in range(L):
+        r = rng.random()
+        if r < 0.15:
+            x[l] = np.where(x[l] >= 0, x[l].max(), x[l])          # monomorphic (possibly with missing cells)
+        elif r < 0.22:
+            x[l] = -9                                             # nothing observed at this locus
+    if N > 3 and rng.random() < 0.3:
+        x[:, int(rng.integers(0, N)), :] = -9                     # an individual with no data at all
+    pops = rng.integers(0, 3, size=N)
+    alleles = [[str(int(v)) for v in rng.permutation(np.arange(100, 160))[:A]] for _ in range(L)]
+    p = str(tmp_path / "geno.txt")
+    _write_text(p, x, pops, label, popdata, extra, fmt, markers, alleles)
+    opt = GsOptions(2, N, L, b"-9", label, popdata, extra, markers, fmt, 1)
+    st = GsStore()
+    err = C.create_string_buffer(512)
+    rc = host.gs_read(p.encode(), C.byref(opt), C.byref(st), err, 512)
+    try:
+        rx, ran, rmiss, _ = pyoracle.ref_read_data(p, 2, N, 3, L, label=label, popdata=popdata, n_extra_col=extra,
+                                                   markername_flag=markers, datafmt=fmt)
+    except Exception:
+        rx = None
+    if rc != 0:
+        # the only files the packer may refuse are those the reference cannot use either (no polymorphic locus left)
+        assert rx is None or rx.shape[0] == 0, err.value
+        return
+    assert rx is not None
+    Ls, Ns = st.locinum, st.totalsize
+    assert (Ls, Ns) == (rx.shape[0], rx.shape[1])
+    if Ls:
+        assert np.array_equal(np.ctypeslib.as_array(st.allelenum, (Ls,)), ran)
+        assert np.array_equal(np.ctypeslib.as_array(st.x, (Ls, Ns, 2)), rx)
+        assert np.array_equal(np.ctypeslib.as_array(st.missvec, (Ns,)), rmiss.sum(axis=0))
+    host.gs_free(C.byref(st))
