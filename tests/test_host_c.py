@@ -326,3 +326,34 @@ def test_packer_fuzz_against_reference_reader(host, tmp_path, case):
         assert np.array_equal(np.ctypeslib.as_array(st.x, (Ls, Ns, 2)), rx)
         assert np.array_equal(np.ctypeslib.as_array(st.missvec, (Ns,)), rmiss.sum(axis=0))
     host.gs_free(C.byref(st))
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_packer_fuzz_tetraploid(host, tmp_path, case):
+    """-p 4, random files: copies in any order, partly and wholly missing genotypes, monomorphic loci."""
+    from instruct_b200.synth import write_reference_text_tetra
+    rng = np.random.default_rng(2000 + case)
+    N, L, A = int(rng.integers(2, 25)), int(rng.integers(1, 16)), int(rng.integers(2, 7))
+    copies = rng.integers(0, A, size=(L, N, 4)).astype(np.int16)
+    copies[rng.random((L, N, 4)) < rng.choice([0.0, 0.1, 0.5])] = -9
+    for l in range(L):
+        if rng.random() < 0.2:
+            copies[l] = np.where(copies[l] >= 0, 0, copies[l])
+    pops = rng.integers(0, 2, size=N)
+    p = str(tmp_path / "geno4.txt")
+    write_reference_text_tetra(p, copies, pop=pops)
+    opt = GsOptions(4, N, L, b"-9", 1, 1, 0, 0, 1, 1)
+    st = GsStore()
+    err = C.create_string_buffer(512)
+    assert host.gs_read(p.encode(), C.byref(opt), C.byref(st), err, 512) == 0, err.value
+    Ls, Ns = st.locinum, st.totalsize
+    rx, ran, rmiss, rid = pyoracle.ref_read_data(p, 4, N, 2, L, label=1, popdata=1, datafmt=1)
+    assert (Ls, Ns) == (rx.shape[0], rx.shape[1])
+    mine = np.ctypeslib.as_array(st.x, (Ls, Ns, 4)).copy()
+    assert np.array_equal(np.ctypeslib.as_array(st.allelenum, (Ls,)), ran)
+    want = rx.copy()
+    want[(rid == 0)] = -1
+    assert np.array_equal(mine, want)
+    assert np.array_equal((mine >= 0).sum(axis=2), rid)
+    assert np.array_equal(np.ctypeslib.as_array(st.missvec, (Ns,)), rmiss.sum(axis=0))
+    host.gs_free(C.byref(st))
