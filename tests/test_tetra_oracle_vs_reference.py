@@ -104,3 +104,27 @@ def test_allo_whole_chain_bit_exact(A, K, miss, back_refl):
     assert a["flag"] == b["flag"] == 0
     for key in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
         assert np.array_equal(np.asarray(a[key]), np.asarray(b[key]), equal_nan=True), key
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_tetra_whole_chain_bit_exact_fuzz(case):
+    """Random shapes, allele counts, missingness, seeds and schedules, both tetraploid models: bit for bit."""
+    rng = np.random.default_rng(5000 + case)
+    autopoly = int(rng.integers(0, 2))
+    A = int(rng.integers(2, 6 if autopoly == 0 else 7))
+    K = int(rng.integers(2, 4))
+    N, L = int(rng.integers(10, 40)), int(rng.integers(2, 14))
+    d = make_tetra_dataset(N=N, L=L, K=K, A=A, miss=float(rng.choice([0.0, 0.05, 0.25])), seed=6000 + case)
+    o = TetraOracle(d.x, d.nd, d.allelenum, K, back_refl=1, autopoly=autopoly)
+    r = RefTetra(d.x, d.nd, d.allelenum, K, back_refl=1, autopoly=autopoly)
+    seeds = [int(v) for v in rng.integers(1, 30000, size=3)]
+    o.setseeds(*seeds)
+    r.setseeds(*seeds)
+    initd = rng.uniform(0.1, 0.9, size=K)
+    burnin = int(rng.integers(3, 15))
+    upd, thin = burnin + int(rng.integers(10, 40)), int(rng.integers(1, 5))
+    a = o.run_chain(upd, burnin, thin, ckrep=4, initd=initd)
+    b = r.run_chain(upd, burnin, thin, ckrep=4, initd=initd)
+    assert a["flag"] == b["flag"]
+    for key in ["totallkh", "totallkh2", "indvlkh", "qq", "qq2", "self_rates", "self_rates2", "convg"]:
+        assert np.array_equal(np.asarray(a[key]), np.asarray(b[key]), equal_nan=True), (key, autopoly, A, K)
