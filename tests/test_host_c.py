@@ -117,16 +117,28 @@ def test_packer_matches_reference_reader(host, tmp_path, label, popdata, extra, 
 @pytest.mark.parametrize("mode,label,popdata,distr", [(2, 1, 1, 1), (2, 0, 0, 0), (3, 0, 1, 1), (4, 1, 1, 1), (4, 0, 1, 0), (5, 1, 1, 1), (5, 0, 0, 1),
                                                        (0, 1, 1, 1), (0, 0, 0, 1)])
 def test_result_file_bytes_match_reference_writer(host, tmp_path, mode, label, popdata, distr):
-    K, N = 3, 17
+    _writer_case(host, tmp_path, mode, label, popdata, distr)
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_result_file_bytes_fuzz(host, tmp_path, case):
+    """Random sizes, models, column switches and value magnitudes (tiny variances, rates at the ends of (0,1), large
+    likelihoods): the result file stays byte-identical to the reference writer's."""
+    rng = np.random.default_rng(7000 + case)
+    _writer_case(host, tmp_path, int(rng.choice([0, 2, 4, 5])), int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 2)),
+                 seed=7100 + case, N=int(rng.integers(3, 40)), K=int(rng.integers(2, 7)), scale=float(rng.choice([1.0, 1e-3, 40.0])))
+
+
+def _writer_case(host, tmp_path, mode, label, popdata, distr, seed=3, N=17, K=3, scale=1.0):
     d = make_dataset(N=N, L=9, K=K, A=4, miss=0.1, seed=5)
-    rng = np.random.default_rng(3)
+    rng = np.random.default_rng(seed)
     ns = N if mode in (3, 5) else K
-    tot, tot2 = -1234.5678, 1234.5678 ** 2 + 33.3
-    indv = rng.normal(-70, 5, N)
+    tot, tot2 = -1234.5678 * scale, (1234.5678 * scale) ** 2 + 33.3 * scale
+    indv = rng.normal(-70, 5, N) * scale
     qq = rng.dirichlet(np.ones(K), N); qq2 = qq ** 2 + rng.uniform(0, 0.01, (N, K))
     if mode == 0:                                   # CHAIN.z / steps: shares of 10 retained samples
         qq = rng.multinomial(10, np.ones(K) / K, N) / 10.0
-    s = rng.uniform(0.05, 0.95, ns); s2 = s ** 2 + rng.uniform(0, 0.01, ns)
+    s = rng.uniform(0.05, 0.95, ns) if scale == 1.0 else rng.choice([1e-4, 0.5, 1 - 1e-4], ns); s2 = s ** 2 + rng.uniform(0, 0.01, ns) * min(scale, 1.0)
     g = rng.uniform(1, 6, N); g2 = g ** 2 + rng.uniform(0, 1, N)
     pops = (np.arange(N) % 2).astype(np.int32)
     missvec = (d.x < 0).any(axis=2).sum(axis=0).astype(np.int32)
