@@ -369,3 +369,27 @@ def test_packer_fuzz_tetraploid(host, tmp_path, case):
     assert np.array_equal((mine >= 0).sum(axis=2), rid)
     assert np.array_equal(np.ctypeslib.as_array(st.missvec, (Ns,)), rmiss.sum(axis=0))
     host.gs_free(C.byref(st))
+
+
+def test_reference_program_bound_to_the_library_fails_loudly_without_a_gpu(tmp_path):
+    """oracle/_ref/InStruct_b200 is the reference PROGRAM (its own flag parser, text reader and writers, compiled from
+    the sources in place) with mcmc_updating() bound to libinstruct_b200.so by instruct_b200/host/reference_binding/
+    mcmc_gpu.c.  Here, without a GPU: it links, reads the file with the reference's reader,
+    reaches the library, and the library's refusal ("no CPU path") comes back through the reference's own nrerror()."""
+    import torch
+    exe = os.path.join(ROOT, "oracle", "_ref", "InStruct_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/InStruct_b200 not built (needs /root/reference)")
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: see tests/test_gpu_cli.py")
+    d = make_dataset(N=30, L=8, K=2, A=4, miss=0.03, seed=3)
+    from instruct_b200.synth import write_reference_text
+    p = str(tmp_path / "g.txt")
+    write_reference_text(p, d.x, pop=d.pop)
+    r = subprocess.run([exe, "-d", p, "-o", str(tmp_path / "o.txt"), "-K", "2", "-L", "8", "-N", "30", "-u", "50", "-b", "10", "-t", "2", "-c", "1",
+                        "-v", "2", "-g", "1", "-r", "5", "-pi", "0", "-s", "13", "4", "1972"], capture_output=True, text=True, timeout=120,
+                       cwd=str(tmp_path))
+    assert r.returncode != 0
+    assert "Chain#1 Starts:" in r.stdout and "no CUDA device: instruct_b200 has no CPU path" in (r.stdout + r.stderr)
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libinstruct_b200.so" in ldd and "not found" not in ldd
