@@ -294,7 +294,7 @@ def test_reference_program_bound_to_the_library_matches_the_reference(tmp_path):
     outs = {}
     for name, exe in (("ref", REFBIN), ("gpu", REFBIN_B200)):
         out = str(tmp_path / f"{name}.out")
-        p = subprocess.run([exe, "-d", data, "-o", out] + flags, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+        p = subprocess.run([exe, "-d", data, "-o", out] + flags, capture_output=True, text=True, timeout=120, cwd=str(tmp_path))
         assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
         assert "THE JOB IS SUCCESSFULLY FINISHED" in p.stdout
         outs[name] = open(out, "rb").read()
