@@ -121,7 +121,11 @@ typedef enum ig_state_id {
 	IG_STATE_GMAX = 21,    /* int32  [1]               genotypes in the largest catalogue (get only)  */
 	/* allotetraploid (-p 4 -ap 0) only: the second subgenome (copies 2,3), mcmc.h:16, poly_geno.c:441-518 */
 	IG_STATE_P2 = 22,      /* double [K][L][Amax]      UPMCMC.freq2                                  */
-	IG_STATE_TALLY2 = 23   /* int32  [K][L][Amax]      tally of copies 2,3 (get only)                 */
+	IG_STATE_TALLY2 = 23,  /* int32  [K][L][Amax]      tally of copies 2,3 (get only)                 */
+	/* mode 3 with the Dirichlet-process prior (update_DP, DPMM.c:165-199): what gen_post_prob (DPMM.c:361-377) hands to
+	 * disc_unif for individual j, with j taken out of its cluster and everybody else where they are */
+	IG_STATE_DPWEIGHTS = 104,  /* double [N][N+1]  [j][0] = alpha/((G_j+1) G_j), [j][1..] = num_c dgeom(S_c, G_j) in value order (get only) */
+	IG_STATE_DPCLUSTERS = 105  /* int64  [1]       number of clusters (get only); setting IG_STATE_S regroups equal values into clusters */
 } ig_state_id;
 
 /* sweep phases for ig_run_phase (test hook; ig_sweep runs them in the reference's order) */

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libinstruct_b200.so")
+LIB_PATH = os.environ.get("IG_LIB") or os.path.join(HERE, "libinstruct_b200.so")     # IG_LIB: kernel-lab builds (tools/kernel_lab.sh)
 
 IG_OK = 0
 IG_EMPTY_CLUSTER = 1
@@ -21,6 +21,7 @@ STATE_X, STATE_Z, STATE_Q, STATE_P, STATE_ALPHA, STATE_S, STATE_G, STATE_INDVLKH
 STATE_TABLES, STATE_TABLES_PROP, STATE_EXFREQ, STATE_SPROP, STATE_DSTAT, STATE_GMAX = 16, 17, 18, 19, 20, 21
 STATE_P2, STATE_TALLY2 = 22, 23      # allotetraploid: second subgenome
 STATE_LLPARTS, STATE_GEOMETRY, STATE_FPROP, STATE_FK = 100, 101, 102, 103
+STATE_DPWEIGHTS, STATE_DPCLUSTERS = 104, 105     # mode 3, DP prior: gen_post_prob weights per individual; number of clusters
 # ig_phase
 PHASE_UPDATE_P, PHASE_UPDATE_S, PHASE_ZQ, PHASE_ALPHA, PHASE_GENO = 1, 2, 4, 8, 16
 

@@ -403,6 +403,25 @@ static int dp_create(ig_ctx *c, double v)
 	c->dp[q].next = s;
 	return s;
 }
+static inline double dp_dgeom(const ig_ctx *c, int p, int gen)     // dgeom(value_p, gen), mcmc.c:1596-1604
+{
+	if (gen >= 1 && gen <= 50) return c->dp_w[(size_t)p * 51 + gen];
+	return pow(c->dp[p].value, (double)(gen - 1)) * (1.0 - c->dp[p].value);
+}
+// clusters = groups of equal values (state injection: ig_set_state(IG_STATE_S) in mode 3 with the DP prior)
+static int dp_create(ig_ctx *c, double v);
+static void dp_from_values(ig_ctx *c, const double *S)
+{
+	const int N = c->geo.N;
+	dp_reset(c);
+	c->S_h.assign(S, S + N);
+	for (int j = 0; j < N; j++) {
+		int p = c->dp_head;
+		while (p >= 0 && c->dp[p].value != S[j]) p = c->dp[p].next;
+		if (p >= 0) { c->dp[p].num++; c->dp_of[j] = p; }
+		else { c->dp_of[j] = dp_create(c, S[j]); c->dp_cnt++; }
+	}
+}
 static void dp_leave(ig_ctx *c, int j)
 {
 	const int s = c->dp_of[j];
@@ -457,9 +476,10 @@ static void dp_update(ig_ctx *c, const std::vector<double> &ind_h)   // update_D
 		dp_leave(c, j);
 		cum[0] = c->cfg.alpha_dpm / (gen + 1) / gen;                  // gen_post_prob, DPMM.c:369
 		int n = 1;
-		const int gi = gen < 1 ? 1 : (gen > 50 ? 50 : gen);
+		// num * dgeom(value, G_j), DPMM.c:373: from the per-cluster table for G in 1..50; the reference's mode-3 initial G is
+		// not capped (mcmc.c:329-331), so a larger G (possible until its first accepted proposal) is evaluated directly
 		for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++)
-			cum[n] = cum[n - 1] + c->dp[p].num * c->dp_w[(size_t)p * 51 + gi];             // num * dgeom(value, G_j), DPMM.c:373
+			cum[n] = cum[n - 1] + c->dp[p].num * dp_dgeom(c, p, gen);
 		const int pick = pick_weighted(cum, n, st.uniform());
 		if (pick == 0) {                                              // sample_poster, DPMM.c:395: Beta(G, 2)
 			c->S_h[j] = draw_beta(st, (double)gen, 2.0);
@@ -486,7 +506,11 @@ static ZQArgs zq_args(ig_ctx *c)
 	a.fmode = c->geo.fmode;
 	a.hpair = (c->geo.fmode == 1) ? c->hpair : nullptr;
 	a.ftab = c->ftab; a.pfk = c->pfk;
+#ifdef IG_Z16
+	a.k_mant = 0x007fff80u; a.k_one = 0x3f800040u;
+#else
 	a.k_mant = 0x007fffffu; a.k_one = 0x3f800000u;
+#endif
 	return a;
 }
 
@@ -822,7 +846,9 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 			c->launches++;
 			cnt_step++;
 		}
-		if (cnt_step == cf.nstep_check_empty_cluster) {                // mcmc.c:227-234
+		// mcmc_POP_no_admixture (mcmc.c:90-131) never calls check_empty_cluster: a surplus cluster in mode 0 simply stays
+		// empty (its one-hot column sums to 0) and the chain finishes; every other driver checks (mcmc.c:227-234)
+		if (cf.mode != 0 && cnt_step == cf.nstep_check_empty_cluster) {
 			DevScalars h;
 			CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
 			CK(cudaStreamSynchronize(c->stream));
@@ -985,6 +1011,33 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 		for (int i = 0; i < g.N; i++) for (int j = 0; j < 2 * g.K; j++) ((double *)host)[(size_t)i * 2 * g.K + j] = r[(size_t)i * g.REC + g.K + 3 + j];
 		return IG_OK;
 	}
+	case 104: {   /* Dirichlet-process step: for every individual j, the weights gen_post_prob (DPMM.c:361-377) would hand to
+		         disc_unif with j taken out of its cluster and everybody else where they are: double [N][N+1],
+		         [j][0] = alpha / ((G_j + 1) G_j) (new cluster), [j][1..] = num_c * dgeom(S_c, G_j) in list (value) order, 0 beyond */
+		if (!(c->cfg.mode == 3 && c->cfg.prior_flag == 1)) return fail(IG_ERR_ARG, "DP weights exist in mode 3 with the DP prior only");
+		if ((st = need(bytes, (size_t)g.N * (g.N + 1) * 8, "DPWEIGHTS")) != IG_OK) return st;
+		if ((int)c->dp_of.size() != g.N) return fail(IG_ERR_STATE, "initialise the chain (or set S) first");
+		std::vector<double> r((size_t)c->Npad * g.REC);
+		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		double *w = (double *)host;
+		memset(w, 0, bytes);
+		for (int j = 0; j < g.N; j++) {
+			const int gen = (int)r[(size_t)j * g.REC + g.K + 2];
+			double *wj = w + (size_t)j * (g.N + 1);
+			wj[0] = c->cfg.alpha_dpm / (gen + 1) / gen;
+			int n = 1;
+			for (int p = c->dp_head; p >= 0; p = c->dp[p].next) {
+				const int num = c->dp[p].num - (c->dp_of[j] == p ? 1 : 0);
+				if (num == 0) continue;                                   // j's own singleton disappears when j leaves (delete, DPMM.c:280)
+				wj[n++] = num * dp_dgeom(c, p, gen);
+			}
+		}
+		return IG_OK;
+	}
+	case 105:     /* number of Dirichlet-process clusters, int64 */
+		if ((st = need(bytes, 8, "DPCLUSTERS")) != IG_OK) return st;
+		*(int64_t *)host = c->dp_cnt;
+		return IG_OK;
 	case 101: {   /* debug: launch geometry int32[8] = TL, nchunks, nblk, subs_per_blk, R, smem, KP, A */
 		if ((st = need(bytes, 32, "GEOMETRY")) != IG_OK) return st;
 		int32_t *o = (int32_t *)host;
@@ -1077,6 +1130,7 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 	case IG_STATE_S:
 		if ((st = need(bytes, (size_t)c->ns * 8, "S")) != IG_OK) return st;
 		CK(cudaMemcpy(c->S, host, bytes, cudaMemcpyHostToDevice));
+		if (c->cfg.ploid == 2 && c->cfg.mode == 3 && c->cfg.prior_flag == 1) dp_from_values(c, (const double *)host);   // the host-side clusters follow
 		return IG_OK;
 	case IG_STATE_STATE:
 		if ((st = need(bytes, (size_t)g.K * 4, "STATE")) != IG_OK) return st;

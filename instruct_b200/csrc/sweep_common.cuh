@@ -82,7 +82,11 @@ __device__ __forceinline__ float lg2_fast(float x)           // MUFU.LG2; |abs e
 
 constexpr float BIG126 = 8.507059173023462e37f;          // 2^126
 constexpr float U_SCALE = 8.507059173023462e37f;         // (f - 1 + 2^-24) * 2^126, f in [1,2)
+#ifdef IG_Z16
+constexpr float U_OFFS = -8.507059173023462e37f;         // 16-bit draw: the half step sits in the mantissa (bit 6), so the offset is -2^126
+#else
 constexpr float U_OFFS = -8.5070586659632355e37f;        // (-1 + 2^-24) * 2^126
+#endif
 
 struct RegConst { uint32_t mant, one; };                 // 0x007fffff, 0x3f800000 held in registers
 

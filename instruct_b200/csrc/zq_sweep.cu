@@ -74,9 +74,28 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 	const uint32_t x0 = __byte_perm((uint32_t)xw, 0u, 0x4410), x1 = __byte_perm((uint32_t)xw, 0u, 0x4432);
 	const float row0f = fmaf(as_dn(x0), (float)(KP * 4), rowbf), row1f = fmaf(as_dn(x1), (float)(KP * 4), rowbf);
 	const uint32_t row0 = __float_as_uint(row0f), row1 = __float_as_uint(row1f);
+#if defined(IG_ABL_HOM)
+	const bool het = false;
+#elif defined(IG_ABL_HET)
+	const bool het = true;
+#else
 	const bool het = (x0 != x1);
+#endif
 	// ---- cumulative weights w_k = sum_{m<=k} Q_im P_m,l,x (mcmc.c:1141-1149)
 	float p0[KP], p1[KP], c0[KP], c1[KP];
+#ifdef IG_ABL_HOM
+	// ABLATION (timing only, wrong chain): every genotype treated as a homozygote -- one row, one prefix
+#pragma unroll
+	for (int v = 0; v < KP / 4; v++) {
+		const float4 t0 = lds_f4(row0 + 16 * v);
+		p0[4 * v] = t0.x; p0[4 * v + 1] = t0.y; p0[4 * v + 2] = t0.z; p0[4 * v + 3] = t0.w;
+	}
+	c0[0] = q[0] * p0[0];
+#pragma unroll
+	for (int k = 1; k < KP; k++) c0[k] = fmaf(q[k], p0[k], c0[k - 1]);
+#pragma unroll
+	for (int k = 0; k < KP; k++) { c1[k] = c0[k]; p1[k] = p0[k]; }
+#else
 #pragma unroll
 	for (int v = 0; v < KP / 4; v++) {
 		const float4 t0 = lds_f4(row0 + 16 * v), t1 = lds_f4(row1 + 16 * v);
@@ -87,10 +106,15 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 	c1[0] = q[0] * p1[0];
 #pragma unroll
 	for (int k = 1; k < KP; k++) { c0[k] = fmaf(q[k], p0[k], c0[k - 1]); c1[k] = fmaf(q[k], p1[k], c1[k - 1]); }
+#endif
 	// ---- old-Z piece of update_G's ratio (log_ld_indv, mcmc.c:1752-1759): only same-z
 	//      homozygotes depend on g.  (The 2^-(g-1) count of same-z heterozygotes on the old
 	//      Z is the previous pass's nsh_new; indiv_epilogue carries it over.)
+#if defined(IG_ABL_NOD) || defined(IG_ABL_HET)
+	if (false) {
+#else
 	if (!TF0 && FM != 2) {
+#endif
 		const uint32_t zo0 = __byte_perm(zw, 0u, H ? 0x4442 : 0x4440), zo1 = __byte_perm(zw, 0u, H ? 0x4443 : 0x4441);
 		const float fo = lds_f(__float_as_uint(fmaf(as_dn(zo0), 4.0f, row0f)));
 		const float fe = (zo0 == zo1 && !het) ? fo : 1.0f;                // h + 1 * (1 - h) == 1 exactly
@@ -112,15 +136,23 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 	const float pa0f = fmaf(zf0, as_dn(4u), row0f), pa1f = fmaf(zf1, as_dn(4u), row1f);           // &P[l][x][z]
 	// ---- n[l][a][k] tally for the next update_P (mcmc.c:815-845) and the individual's
 	//      ancestry counts (mcmc.c:1176-1194): shared-memory RED
+#ifndef IG_ABL_NOTALLY
 	red_inc(__float_as_uint(fmaf(pa0f, (float)(1 << LR), t.hist_bias)));
 	red_inc(__float_as_uint(fmaf(pa1f, (float)(1 << LR), t.hist_bias)));
+#endif
+#ifndef IG_ABL_NOCNT
 	red_inc(__float_as_uint(fmaf(zf0, as_dn(4u * ZQ_THREADS), t.cnt_t)));
 	red_inc(__float_as_uint(fmaf(zf1, as_dn(4u * ZQ_THREADS), t.cnt_t)));
+#endif
 	// ---- new-Z likelihood pieces (cal_lkh and the accepted-G selection)
 	float f0, f1;
 	bool same_n;
 	if (TF0) { f0 = c0[KP - 1]; f1 = c1[KP - 1]; same_n = true; }                                 // mcmc.c:1739-1749
+#if defined(IG_ABL_NOLIK)
+	else { f0 = f1 = 1.0f; same_n = (zf0 == zf1); }
+#else
 	else { f0 = lds_f(__float_as_uint(pa0f)); f1 = lds_f(__float_as_uint(pa1f)); same_n = (zf0 == zf1); }
+#endif
 	const bool sh_n = same_n && !het;
 	if (FM == 2) {
 		float fac = f1;
@@ -134,9 +166,16 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 		}
 		acc.mA += lg2_fast(f0 * fac);
 	} else {
+#if defined(IG_ABL_NOLIK)
+		acc.nsh_new += (same_n && het) ? 1 : 0;
+#elif defined(IG_ABL_HET)
+		acc.mA += lg2_fast(f0 * f1);
+		acc.nsh_new += same_n ? 1 : 0;
+#else
 		acc.mA += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_g, t.h_g) : f1));
 		acc.mB += lg2_fast(f0 * (sh_n ? fmaf(f0, t.omh_p, t.h_p) : f1));
 		acc.nsh_new += (same_n && het) ? 1 : 0;
+#endif
 	}
 	return __float_as_uint(fmaf(zf1, as_dn(256u), zf0 * as_dn(1u)));                              // z0 | z1 << 8
 }
@@ -148,6 +187,37 @@ __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&
                                            uint32_t mt_global, uint32_t ig_global, uint32_t iter, const ZQArgs &a, const float (&q)[KP], const Thr &t,
                                            Acc &acc, const RegConst &kc)
 {
+#ifdef IG_Z16
+	// 16 random bits per allele copy: one Philox block serves FOUR genotypes.  Copy 0 of a genotype takes bits 22..7 of
+	// its word as they lie (the mantissa of uniform_big), copy 1 the other sixteen, rotated into the same place by one PRMT.
+#pragma unroll
+	for (int ph = 0; ph < 2; ++ph) {
+		const u32x4 rnd = philox4x32<ROUNDS>(u32x4{mt_global, ig_global, iter, TAG_Z16 | (uint32_t)ph}, a.key0, a.key1);
+		const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+		for (int qq = 0; qq < 2; ++qq) {
+			const int pr = 2 * ph + qq;
+			uint32_t pair[2];
+#pragma unroll
+			for (int h2 = 0; h2 < 2; ++h2) {
+				const int j = 2 * pr + h2;
+				const uint32_t ra = rr[2 * qq + h2], rb = __byte_perm(ra, 0u, 0x1032);
+				const float rowbf = fmaf((float)j, rowstridef, rowb0f);
+				if (CHECK) {
+					pair[h2] = h2 ? (zwo[pr] >> 16) : (zwo[pr] & 0xFFFFu);
+					if (xw[j] >= 0) {
+						if (h2) pair[h2] = genotype<KP, TF0, LR, 1, FM>(xw[j], zwo[pr], ra, rb, rowbf, q, t, acc, kc);
+						else pair[h2] = genotype<KP, TF0, LR, 0, FM>(xw[j], zwo[pr], ra, rb, rowbf, q, t, acc, kc);
+					}
+				} else {
+					if (h2) pair[h2] = genotype<KP, TF0, LR, 1, FM>(xw[j], zwo[pr], ra, rb, rowbf, q, t, acc, kc);
+					else pair[h2] = genotype<KP, TF0, LR, 0, FM>(xw[j], zwo[pr], ra, rb, rowbf, q, t, acc, kc);
+				}
+			}
+			zwn[pr] = __byte_perm(pair[0], pair[1], 0x5410);
+		}
+	}
+#else
 #pragma unroll
 	for (int pr = 0; pr < 4; ++pr) {
 		const u32x4 rnd = philox4x32<ROUNDS>(u32x4{mt_global, ig_global, iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
@@ -171,6 +241,7 @@ __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&
 		}
 		zwn[pr] = __byte_perm(pair[0], pair[1], 0x5410);
 	}
+#endif
 }
 
 // --------------------------------------------------------------------------------------

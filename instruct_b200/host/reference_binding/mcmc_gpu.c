@@ -22,6 +22,8 @@
 #include "check_converg.h"
 #include "mcmc.h"
 
+extern int GR_flag;     /* InStruct.c:32: with -g 0 the caller never runs allocate_convg (InStruct.c:181), so *cvg is uninitialised stack */
+
 /* SEQDATA.seqdata[i][l][c] (int; -9 = missing, data_interface.c:497,538; ploid 4: ascending distinct alleles padded with
  * -1, data_interface.c:617-650)  ->  int16 [L][N][ploid], any negative value = not an allele */
 static int16_t *pack_store(SEQDATA d)
@@ -47,6 +49,8 @@ CHAIN mcmc_updating(SEQDATA data, INIT initial, int chn, CONVG *cvg)
 	const int N = data.totalsize, K = data.popnum;
 	const int dip = data.ploid == 2, mode = data.mode;
 	int j;
+	const int have_cvg = (GR_flag == 1 && cvg != NULL);
+	double u_hi, u_lo;
 
 	memset(&chain, 0, sizeof chain);
 	memset(&cfg, 0, sizeof cfg);
@@ -95,15 +99,17 @@ CHAIN mcmc_updating(SEQDATA data, INIT initial, int chn, CONVG *cvg)
 	cfg.alpha_dpm = data.alpha_dpm; cfg.nstep_check_empty_cluster = data.nstep_check_empty_cluster;
 	cfg.print_iter = data.print_iter; cfg.print_freq = data.print_freq; cfg.autopoly = data.autopoly;
 	cfg.update = initial.update; cfg.burnin = initial.burnin; cfg.thinning = initial.thinning;
-	cfg.ckrep = cvg ? cvg->ckrep : 0;
+	cfg.ckrep = have_cvg ? cvg->ckrep : 0;
 	cfg.shard_size = N; cfg.shard_count = 1;
 	/* the chain's Philox key from the reference's own stream (-s seed1 seed2 seed3 seeds it, InStruct.c:430): the run
 	 * stays a function of the three seeds, and every chain draws a different key */
-	cfg.seed = ((uint64_t)(ran1() * 4294967296.0) << 32) | (uint64_t)(ran1() * 4294967296.0);
+	u_hi = ran1();                                          /* two statements: the order of the two draws is part of the seed */
+	u_lo = ran1();
+	cfg.seed = ((uint64_t)(u_hi * 4294967296.0) << 32) | (uint64_t)(u_lo * 4294967296.0);
 
 	x = pack_store(data);
 	st = ig_mcmc_updating(&cfg, x, data.allelenum, chn, (dip && (mode == 2 || mode == 4)) || data.ploid == 4 ? initial.initd[chn] : NULL, &r,
-	                      cvg ? &cvg->convg_ld[chn * cvg->ckrep] : NULL);          /* mcmc.c:223-224 */
+	                      have_cvg ? &cvg->convg_ld[chn * cvg->ckrep] : NULL);     /* mcmc.c:223-224 */
 	free(x);
 	if (st < 0) nrerror((char *)ig_last_error());          /* the reference's own error convention (nrutil.c:9-16): message, exit(1) */
 	chain.steps = (long)r.steps; chain.step = (long)r.step;

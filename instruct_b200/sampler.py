@@ -287,6 +287,7 @@ class Sampler:
             _lib.STATE_ITER: ((1,), np.int64), _lib.STATE_LLPARTS: ((Nl, 4), np.float64),
             _lib.STATE_GEOMETRY: ((8,), np.int32), _lib.STATE_FPROP: ((self.ns,), np.float64),
             _lib.STATE_FK: ((N, 2, K), np.float64),
+            _lib.STATE_DPWEIGHTS: ((N, N + 1), np.float64), _lib.STATE_DPCLUSTERS: ((1,), np.int64),
             _lib.STATE_P2: ((K, L, A), np.float64), _lib.STATE_TALLY2: ((K, L, A), np.int32),
         }[sid]
 

@@ -781,6 +781,22 @@ void orc_update_DP(orc_model *m)
 }
 int orc_dp_nclusters(const orc_model *m) { return m->dp_cnt; }
 
+/* TEST HOOK (no reference counterpart): rebuild the cluster list from self_rates[] -- individuals with the same value
+ * share a cluster -- so that one orc_update_DP scan can start from an injected clustering.  Built with the same
+ * dp_create as the sampler, so the list order is the value order the reference's find/insert keeps (DPMM.c:202-263). */
+void orc_dp_from_values(orc_model *m)
+{
+	int j, p;
+	dp_reset(m);
+	for (j = 0; j < m->N; j++) {
+		double v = m->self_rates[j];
+		for (p = m->dp_head; p >= 0; p = m->dp_next[p]) if (m->dp_value[p] == v) break;
+		if (p >= 0) { m->dp_num[p]++; m->dp_of[j] = p; }
+		else { m->dp_of[j] = dp_create(m, v); m->dp_cnt++; }
+		m->dp_sval[j] = v;
+	}
+}
+
 /* ------------------------------------------------------------------ sweeps / chains --- */
 
 /* one sweep in the reference's order: mcmc.c:152-155 (mode 1), :210-215 (mode 2), :336-348 (mode 3) */

@@ -88,6 +88,7 @@ void orc_cal_lkh(orc_model *m);
 void orc_init_DP(orc_model *m);
 void orc_update_DP(orc_model *m);
 int orc_dp_nclusters(const orc_model *m);
+void orc_dp_from_values(orc_model *m);   /* test hook: clusters = groups of equal self_rates[] */
 void orc_sweeps(orc_model *m, int n);
 
 /* whole chain = the reference's mcmc_POP_selfing (mode 2) / mcmc_INDV_selfing (mode 3) */

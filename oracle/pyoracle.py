@@ -102,6 +102,8 @@ def oracle_lib():
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_update_ZQ.argtypes = [C.c_void_p, C.c_int]
         L.orc_dp_nclusters.argtypes = [C.c_void_p]
+        L.orc_dp_from_values.argtypes = [C.c_void_p]
+        L.orc_dp_from_values.restype = None
         L.orc_sweeps.argtypes = [C.c_void_p, C.c_int]
         L.orc_chain_new.restype = C.c_void_p
         L.orc_chain_new.argtypes = [C.c_void_p, C.c_int]
@@ -261,6 +263,13 @@ class Oracle:
 
     def dp_nclusters(self):
         return self.lib.orc_dp_nclusters(self.h)
+
+    def dp_from_values(self):
+        """test hook: rebuild the Dirichlet-process clusters from self_rates (equal values share a cluster)"""
+        self.lib.orc_dp_from_values(self.h)
+
+    def dgeom(self, s, g):
+        return self.lib.orc_dgeom(float(s), int(g))
 
     def sweeps(self, n):
         self.lib.orc_sweeps(self.h, n)

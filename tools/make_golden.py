@@ -15,6 +15,8 @@ Fixtures
                       the reference's own mcmc_updating()            (whole-chain pin)
   posterior_c1.npz    config-1 shaped data (K=2 N=200 L=10), posterior means of S, Q, log-lik
                       from R independent reference chains            (parity level 3)
+  posterior_mode3_prior{0,1}.npz  BASELINE configs[2] in small: selfing rate per individual under the uniform and the
+                      Dirichlet-process prior; posterior means from R reference chains, and the number of DP clusters
   tetra_chain.npz     autotetraploid: genotype catalogues, float tables on an injected state and
                       the CHAIN moments of one short chain through mcmc_POP_tetra_selfing
   posterior_tetra.npz autotetraploid posterior means from R independent reference chains
@@ -208,7 +210,48 @@ def posterior_inbreeding_fixture(mode, R=10):
                         Q=np.array(Qm).astype(np.float32), LL=np.array(LL), pop=d.pop, update=5000, burnin=2000, thinning=10)
 
 
+def posterior_mode3_fixture(prior, R=10):
+    """Mode 3 (mcmc_INDV_selfing, mcmc.c:297-383): selfing rate per individual under the uniform prior (update_S_IND,
+    mcmc.c:864) or the Dirichlet-process prior (update_DP, DPMM.c:165) -- BASELINE configs[2] in small.  CHAIN moments of R
+    chains through the reference's own driver; for the DP prior also the number of clusters, from R runs stepped through
+    the reference's own update functions in the driver's order (refh_sweeps), since CHAIN does not carry it."""
+    K = 2
+    d = make_dataset(N=200, L=10, K=K, A=8, miss=0.0, seed=1003, pure=True, s_atoms=[0.05, 0.5, 0.9])
+    upd, burn, thin = 5000, 2000, 10
+    S, Qm, LL, G, NC = [], [], [], [], []
+    for rep in range(R):
+        r = Reference(d.x, d.allelenum, K, mode=3, prior_flag=prior, alpha_dpm=2.0)
+        r.setseeds(13 + 7 * rep, 4 + 3 * rep, 1972 + 11 * rep)
+        c = r.mcmc_updating(update=upd, burnin=burn, thinning=thin, ckrep=5, nstep_check_empty=20)
+        o = np.argsort(c["qq"][d.pop == 0].mean(axis=0))[::-1]
+        S.append(c["self_rates"]); Qm.append(c["qq"][:, o]); LL.append(c["totallkh"]); G.append(c["gen"])
+        print(f"mode-3 prior {prior} rep", rep, c["totallkh"], c["self_rates"][:4], flush=True)
+        if prior == 1:
+            r2 = Reference(d.x, d.allelenum, K, mode=3, prior_flag=1, alpha_dpm=2.0)
+            r2.setseeds(17 + 5 * rep, 9 + 2 * rep, 1900 + 13 * rep)
+            rng = np.random.default_rng(50 + rep)
+            r2.init_DP()                                             # mcmc.c:318-324
+            s0 = r2.get_self()
+            r2.set_gen(np.minimum(rng.geometric(1.0 - np.clip(s0, 1e-9, 1 - 1e-9)), 50).astype(np.int32))   # mcmc.c:326-331
+            r2.set_alpha(10.0 * rng.random())                        # initial_chn, mcmc.c:479
+            r2.update_ZQ(1)
+            r2.sweeps(burn)
+            nc = []
+            for _ in range((upd - burn) // thin):
+                r2.sweeps(thin)
+                nc.append(r2.dp_nclusters())
+            NC.append(np.mean(nc))
+            print("   clusters", NC[-1], flush=True)
+    np.savez_compressed(os.path.join(OUT, f"posterior_mode3_prior{prior}.npz"), x=d.x, allelenum=d.allelenum, K=K, S=np.array(S),
+                        Q=np.array(Qm).astype(np.float32), LL=np.array(LL), G=np.array(G).astype(np.float32), NC=np.array(NC),
+                        S_true=d.S_true, pop=d.pop, update=upd, burnin=burn, thinning=thin, alpha_dpm=2.0)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mode3":
+        posterior_mode3_fixture(0)
+        posterior_mode3_fixture(1)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mode0":
         chain_fixture(0, 0)
         posterior_mode0_fixture()
@@ -243,6 +286,8 @@ if __name__ == "__main__":
     chain_fixture(5, 0)
     posterior_inbreeding_fixture(4)
     posterior_inbreeding_fixture(5)
+    posterior_mode3_fixture(0)
+    posterior_mode3_fixture(1)
     posterior_fixture()
     posterior_mode1_fixture()
     tetra_fixtures()
