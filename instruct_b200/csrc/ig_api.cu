@@ -26,6 +26,7 @@ static double wall_ms()
 }
 #include "philox.cuh"
 #include "samplers.cuh"
+#include "sweep_common.cuh"
 
 
 // --------------------------------------------------------------------------------------
@@ -150,6 +151,7 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 
 static void free_all(ig_ctx *c)
 {
+	cudaFree(c->Es); cudaFree(c->Hs); cudaFree(c->Zs); cudaFree(c->Pc); cudaFree(c->Pcnext);
 	cudaFree(c->Xt); cudaFree(c->Zt); cudaFree(c->P); cudaFree(c->P64); cudaFree(c->n); cudaFree(c->allelenum);
 	cudaFree(c->ind); cudaFree(c->Qf); cudaFree(c->gprop); cudaFree(c->gpair); cudaFree(c->S); cudaFree(c->state);
 	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->pnsh); cudaFree(c->nhet); cudaFree(c->nsh); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
@@ -187,11 +189,19 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] > amax) amax = c->allelenum_h[l];
 	if (amax > 32000) return fail(IG_ERR_ARG, "allelenum_max %d does not fit the int16 genotype store", amax);
 	g.A = amax < 2 ? 2 : amax;
-	CK(zq_configure(g, c->cfg.device));
+	g.snp = 0;
+	if (snp_eligible(g, c->cfg.mode, c->cfg.type_freq)) CK(snp_configure(g, c->cfg.device));
+	else CK(zq_configure(g, c->cfg.device));
 	const size_t tiles = (size_t)g.LT * g.Nloc * TILE * 2;
 	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
 	CK(dalloc(&c->Xt, tiles));
-	CK(dalloc(&c->Zt, tiles));
+	if (g.snp) {
+		const size_t ne = (size_t)g.nchunks * g.Nloc * g.TL;
+		CK(dalloc(&c->Es, ne));
+		CK(dalloc(&c->Zs, ne));
+		CK(dalloc(&c->Hs, (size_t)g.nchunks * g.Nloc));
+		CK(dalloc(&c->Pc, snp_pc_floats(g)));
+	} else CK(dalloc(&c->Zt, tiles));
 	CK(dalloc(&c->P, pn));
 	CK(dalloc(&c->n, pn));
 	if (c->cfg.print_freq) CK(dalloc(&c->P64, (size_t)g.K * g.L * g.A));
@@ -237,6 +247,7 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	CK(launch_het_counts(c->Xt, nullptr, c->nhet, nullptr, g, c->stream));
 	CK(cudaMemsetAsync(c->nsh, 0, (size_t)g.Nloc * sizeof(int32_t), c->stream));
 	c->launches += 2;
+	if (g.snp) { CK(launch_snp_tile(c->Xt, c->Es, c->Hs, g, c->stream)); c->launches++; }
 	CK(cudaStreamSynchronize(c->stream));
 	c->loaded = true;
 	return IG_OK;
@@ -318,6 +329,7 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 		CK(cudaEventCreateWithFlags(&c->ev_zq, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_p, cudaEventDisableTiming));
 		CK(dalloc(&c->Pnext, (size_t)c->geo.Lpad * c->geo.A * c->geo.KP));
+		if (c->geo.snp) CK(dalloc(&c->Pcnext, snp_pc_floats(c->geo)));
 	}
 	return IG_OK;
 }
@@ -506,11 +518,7 @@ static ZQArgs zq_args(ig_ctx *c)
 	a.fmode = c->geo.fmode;
 	a.hpair = (c->geo.fmode == 1) ? c->hpair : nullptr;
 	a.ftab = c->ftab; a.pfk = c->pfk;
-#ifdef IG_Z16
-	a.k_mant = 0x007fff80u; a.k_one = 0x3f800040u;
-#else
-	a.k_mant = 0x007fffffu; a.k_one = 0x3f800000u;
-#endif
+	a.k_mant = U16_MANT; a.k_one = U16_ONE;         // 16 random bits per allele copy (sweep_common.cuh)
 	return a;
 }
 
@@ -519,12 +527,13 @@ static ig_status phase_update_P(ig_ctx *c)
 	if (c->early_p) {                       // drawn behind the previous sweep's kernel on the side stream
 		CK(cudaStreamWaitEvent(c->stream, c->ev_p, 0));
 		std::swap(c->P, c->Pnext);
+		std::swap(c->Pc, c->Pcnext);
 		c->early_p = false;
 		return IG_OK;
 	}
 	ig_status st = exchange_tally(c);
 	if (st != IG_OK) return st;
-	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, c->iter_dev, 0};
+	PArgs a{c->n, c->P, c->P64, c->allelenum, c->geo, c->iter, c->key0, c->key1, c->iter_dev, 0, 0, c->Pc, c->geo.TL};
 	CK(launch_p_dirichlet(a, c->stream));
 	c->launches++;
 	return IG_OK;
@@ -560,7 +569,12 @@ static ig_status phase_zq(ig_ctx *c, int init)
 	if (init) { a.type_freq = 1; a.fmode = 0; a.hpair = nullptr; }     // uniform initial assignment: no likelihood is kept
 	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
 	if (timed) CK(cudaEventRecord(c->ev[c->ev_used], c->stream));
-	CK(launch_zq_sweep(a, c->rounds, c->stream));
+	if (c->geo.snp) {
+		SnpArgs sa{c->Es, c->Zs, c->Hs, c->Pc, c->n, c->Qf, c->gpair, c->pcnt, c->plog, c->pnsh, c->geo, c->iter, c->key0, c->key1,
+		           c->iter_dev, U16_MANT, U16_ONE};
+		CK(launch_zq_snp(sa, c->rounds, c->stream));
+		c->zt_stale = true;
+	} else CK(launch_zq_sweep(a, c->rounds, c->stream));
 	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
 	if (!init && c->comm && c->stream2 && c->more_follow) {
 		// Sharded chain: n is complete once this kernel ends, and nothing else of this sweep reads it.
@@ -570,7 +584,7 @@ static ig_status phase_zq(ig_ctx *c, int init)
 		CK(cudaEventRecord(c->ev_zq, c->stream));
 		CK(cudaStreamWaitEvent(c->stream2, c->ev_zq, 0));
 		NCK(g_nccl.AllReduce(c->n, c->n, (size_t)g.Lpad * g.A * g.KP, ncclInt32, ncclSum, c->comm, c->stream2));
-		PArgs pa{c->n, c->Pnext, c->P64, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0};
+		PArgs pa{c->n, c->Pnext, c->P64, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0, 0, c->Pcnext, c->geo.TL};
 		CK(launch_p_dirichlet(pa, c->stream2));
 		CK(cudaEventRecord(c->ev_p, c->stream2));
 		c->launches++;
@@ -697,7 +711,11 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 		CK(launch_fill_f32(c->P, 1.0f, pn, c->stream));
 		CK(launch_fill_q_uniform(c->Qf, g, c->stream));
 		CK(cudaMemsetAsync(c->n, 0, pn * sizeof(int32_t), c->stream));
-		CK(cudaMemsetAsync(c->Zt, 0, (size_t)g.LT * g.Nloc * TILE * 2, c->stream));
+		if (g.snp) {
+			CK(launch_fill_f32(c->Pc, 1.0f, snp_pc_floats(g), c->stream));
+			CK(cudaMemsetAsync(c->Zs, 0, (size_t)g.nchunks * g.Nloc * g.TL * sizeof(uint16_t), c->stream));
+			c->zt_stale = true;
+		} else CK(cudaMemsetAsync(c->Zt, 0, (size_t)g.LT * g.Nloc * TILE * 2, c->stream));
 		c->launches += 3;
 	}
 	ig_status st = phase_zq(c, 1);
@@ -885,6 +903,31 @@ extern "C" ig_status ig_mcmc_updating(const ig_config *cfg, const int16_t *x_hos
 // --------------------------------------------------------------------------------------
 // state hooks (parity tests): canonical host layouts <-> device layouts
 // --------------------------------------------------------------------------------------
+// biallelic path: the micro-tiled Z the hooks read is a view of the class-sorted Z, rebuilt when it is behind
+static ig_status ensure_zt(ig_ctx *c)
+{
+	const Geometry &g = c->geo;
+	if (!g.snp) return IG_OK;
+	if (!c->Zt) { ig_alloc_stream = c->stream; CK(dalloc(&c->Zt, (size_t)g.LT * g.Nloc * TILE * 2)); c->zt_stale = true; }
+	if (c->zt_stale) {
+		CK(launch_snp_z_convert(c->Es, c->Zs, c->Zt, g, 0, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		c->zt_stale = false;
+	}
+	return IG_OK;
+}
+
+// Host <-> device copies of the state hooks: on the context's stream and complete on return.  A plain cudaMemcpy runs on the
+// legacy default stream, which is not ordered with the (non-blocking) context stream, and a host-to-device copy from
+// pageable memory may return before its DMA has landed: a kernel launched on the context stream right after it could
+// read the old contents (seen: the chunk-ordered copy of P built from a P that had not arrived yet).
+static cudaError_t copy_sync(ig_ctx *c, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+	cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	return e;
+}
+
 static ig_status need(size_t have, size_t want, const char *what)
 {
 	if (have != want) return fail(IG_ERR_ARG, "%s: expected %zu bytes, got %zu", what, want, have);
@@ -910,6 +953,7 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 		const size_t el = (size_t)g.L * g.Nloc * 2;
 		const size_t want = el * (id == IG_STATE_X ? 2 : 1);
 		if ((st = need(bytes, want, "X/Z")) != IG_OK) return st;
+		if (id == IG_STATE_Z && (st = ensure_zt(c)) != IG_OK) return st;
 		void *tmp = nullptr;
 		CK(cudaMalloc(&tmp, want));
 		cudaError_t e = (id == IG_STATE_X) ? launch_untile_x(c->Xt, (int16_t *)tmp, g, c->stream) : launch_untile_z(c->Zt, (int8_t *)tmp, g, c->stream);
@@ -930,7 +974,7 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 	case IG_STATE_Q: {
 		if ((st = need(bytes, (size_t)g.N * g.K * 8, "Q")) != IG_OK) return st;
 		std::vector<double> r((size_t)c->Npad * g.REC);
-		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
 		double *q = (double *)host;
 		for (int i = 0; i < g.N; i++) for (int k = 0; k < g.K; k++) q[(size_t)i * g.K + k] = r[(size_t)i * g.REC + k];
 		return IG_OK;
@@ -938,7 +982,7 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 	case IG_STATE_G:
 	case IG_STATE_INDVLKH: {
 		std::vector<double> r((size_t)c->Npad * g.REC);
-		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
 		if (id == IG_STATE_G) {
 			if ((st = need(bytes, (size_t)g.N * 4, "G")) != IG_OK) return st;
 			for (int i = 0; i < g.N; i++) ((int32_t *)host)[i] = (int32_t)r[(size_t)i * g.REC + g.K + 2];
@@ -955,12 +999,12 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 		if ((st = need(bytes, el * (id == IG_STATE_P ? 8 : 4), "P/TALLY")) != IG_OK) return st;
 		if (id == IG_STATE_P) {
 			std::vector<float> p(pn);
-			CK(cudaMemcpy(p.data(), c->P, pn * 4, cudaMemcpyDeviceToHost));
+			CK(copy_sync(c, p.data(), c->P, pn * 4, cudaMemcpyDeviceToHost));
 			for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int a = 0; a < g.A; a++)
 				((double *)host)[((size_t)k * g.L + l) * g.A + a] = (double)p[((size_t)l * g.A + a) * g.KP + k];
 		} else {
 			std::vector<int32_t> p(pn);
-			CK(cudaMemcpy(p.data(), c->n, pn * 4, cudaMemcpyDeviceToHost));
+			CK(copy_sync(c, p.data(), c->n, pn * 4, cudaMemcpyDeviceToHost));
 			for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int a = 0; a < g.A; a++)
 				((int32_t *)host)[((size_t)k * g.L + l) * g.A + a] = p[((size_t)l * g.A + a) * g.KP + k];
 		}
@@ -970,25 +1014,25 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 	case IG_STATE_TOTALLKH: {
 		if ((st = need(bytes, 8, "scalar")) != IG_OK) return st;
 		DevScalars h;
-		CK(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, &h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
 		*(double *)host = (id == IG_STATE_ALPHA) ? h.alpha : h.totallkh;
 		return IG_OK;
 	}
 	case IG_STATE_S:
 		if ((st = need(bytes, (size_t)c->ns * 8, "S")) != IG_OK) return st;
-		CK(cudaMemcpy(host, c->S, bytes, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, host, c->S, bytes, cudaMemcpyDeviceToHost));
 		return IG_OK;
 	case IG_STATE_STATE:
 		if ((st = need(bytes, (size_t)g.K * 4, "STATE")) != IG_OK) return st;
-		CK(cudaMemcpy(host, c->state, bytes, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, host, c->state, bytes, cudaMemcpyDeviceToHost));
 		return IG_OK;
 	case IG_STATE_CNT:
 		if ((st = need(bytes, (size_t)g.Nloc * g.K * 4, "CNT")) != IG_OK) return st;
-		CK(cudaMemcpy(host, c->cnt, bytes, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, host, c->cnt, bytes, cudaMemcpyDeviceToHost));
 		return IG_OK;
 	case IG_STATE_GPROP:
 		if ((st = need(bytes, (size_t)g.N * 4, "GPROP")) != IG_OK) return st;
-		CK(cudaMemcpy(host, c->gprop, bytes, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, host, c->gprop, bytes, cudaMemcpyDeviceToHost));
 		return IG_OK;
 	case IG_STATE_ITER:
 		if ((st = need(bytes, 8, "ITER")) != IG_OK) return st;
@@ -996,18 +1040,18 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 		return IG_OK;
 	case 100:     /* debug: per-individual (d_old, c_new, a_new, b_new) of the last zq pass, double [Nloc][4] */
 		if ((st = need(bytes, (size_t)g.Nloc * 32, "LLPARTS")) != IG_OK) return st;
-		CK(cudaMemcpy(host, c->llparts, bytes, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, host, c->llparts, bytes, cudaMemcpyDeviceToHost));
 		return IG_OK;
 	case 102:     /* debug: proposed inbreeding coefficients of the last sweep, double [K] (mode 4) or [N] (mode 5) */
 		if (!c->fprop) return fail(IG_ERR_ARG, "FPROP exists in modes 4 and 5 only");
 		if ((st = need(bytes, (size_t)c->ns * 8, "FPROP")) != IG_OK) return st;
-		CK(cudaMemcpy(host, c->fprop, bytes, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, host, c->fprop, bytes, cudaMemcpyDeviceToHost));
 		return IG_OK;
 	case 103: {   /* debug, mode 4: per-individual old-Z and new-Z differences per population, double [N][2][K] (nats) */
 		if (g.fmode != 2) return fail(IG_ERR_ARG, "FK exists in mode 4 only");
 		if ((st = need(bytes, (size_t)g.N * 2 * g.K * 8, "FK")) != IG_OK) return st;
 		std::vector<double> r((size_t)c->Npad * g.REC);
-		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
 		for (int i = 0; i < g.N; i++) for (int j = 0; j < 2 * g.K; j++) ((double *)host)[(size_t)i * 2 * g.K + j] = r[(size_t)i * g.REC + g.K + 3 + j];
 		return IG_OK;
 	}
@@ -1018,7 +1062,7 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 		if ((st = need(bytes, (size_t)g.N * (g.N + 1) * 8, "DPWEIGHTS")) != IG_OK) return st;
 		if ((int)c->dp_of.size() != g.N) return fail(IG_ERR_STATE, "initialise the chain (or set S) first");
 		std::vector<double> r((size_t)c->Npad * g.REC);
-		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
 		double *w = (double *)host;
 		memset(w, 0, bytes);
 		for (int j = 0; j < g.N; j++) {
@@ -1066,12 +1110,14 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 	case IG_STATE_Z: {
 		const size_t want = (size_t)g.L * g.Nloc * 2;
 		if ((st = need(bytes, want, "Z")) != IG_OK) return st;
+		if ((st = ensure_zt(c)) != IG_OK) return st;
 		void *tmp = nullptr;
 		CK(cudaMalloc(&tmp, want));
 		cudaError_t e = cudaMemcpyAsync(tmp, host, want, cudaMemcpyHostToDevice, c->stream);
 		if (e == cudaSuccess) e = launch_tile_z((const int8_t *)tmp, c->Zt, g, c->stream);
 		if (e == cudaSuccess) e = launch_tally(c->Xt, c->Zt, c->n, g, c->stream);    // n always mirrors Z
 		if (e == cudaSuccess) e = launch_het_counts(c->Xt, c->Zt, nullptr, c->nsh, g, c->stream);   // and so does nsh
+		if (e == cudaSuccess && g.snp) e = launch_snp_z_convert(c->Es, c->Zs, c->Zt, g, 1, c->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		cudaFree(tmp);
 		CK(e);
@@ -1080,14 +1126,14 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 	case IG_STATE_Q: {
 		if ((st = need(bytes, (size_t)g.N * g.K * 8, "Q")) != IG_OK) return st;
 		std::vector<double> r((size_t)c->Npad * g.REC);
-		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
 		const double *q = (const double *)host;
 		for (int i = 0; i < g.N; i++) {
 			double slq = 0;
 			for (int k = 0; k < g.K; k++) { r[(size_t)i * g.REC + k] = q[(size_t)i * g.K + k]; slq += log(q[(size_t)i * g.K + k]); }
 			r[(size_t)i * g.REC + g.K + 1] = slq;
 		}
-		CK(cudaMemcpy(c->ind, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+		CK(copy_sync(c, c->ind, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
 		CK(launch_qf_from_ind(c->ind, c->Qf, g, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 		return IG_OK;
@@ -1095,7 +1141,7 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 	case IG_STATE_G:
 	case IG_STATE_INDVLKH: {
 		std::vector<double> r((size_t)c->Npad * g.REC);
-		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
 		if (id == IG_STATE_G) {
 			if ((st = need(bytes, (size_t)g.N * 4, "G")) != IG_OK) return st;
 			for (int i = 0; i < g.N; i++) r[(size_t)i * g.REC + g.K + 2] = (double)((const int32_t *)host)[i];
@@ -1103,11 +1149,11 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 			if ((st = need(bytes, (size_t)g.N * 8, "INDVLKH")) != IG_OK) return st;
 			for (int i = 0; i < g.N; i++) r[(size_t)i * g.REC + g.K] = ((const double *)host)[i];
 		}
-		CK(cudaMemcpy(c->ind, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+		CK(copy_sync(c, c->ind, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
 		if (id == IG_STATE_G && c->cfg.mode == 0 && c->cfg.ploid == 2) {       // mode 0: G carries the cluster labels zz; n mirrors them
 			std::vector<double> r2(r);
 			for (int i = 0; i < g.N; i++) for (int k = 0; k < g.K; k++) r2[(size_t)i * g.REC + k] = (k == ((const int32_t *)host)[i]) ? 1.0 : 0.0;
-			CK(cudaMemcpy(c->ind, r2.data(), r2.size() * 8, cudaMemcpyHostToDevice));
+			CK(copy_sync(c, c->ind, r2.data(), r2.size() * 8, cudaMemcpyHostToDevice));
 			if ((st = na_retally(c)) != IG_OK) return st;
 			CK(cudaStreamSynchronize(c->stream));
 		}
@@ -1119,31 +1165,32 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 		std::vector<float> p(pn, 0.0f);
 		for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int a = 0; a < g.A; a++)
 			p[((size_t)l * g.A + a) * g.KP + k] = (float)((const double *)host)[((size_t)k * g.L + l) * g.A + a];
-		CK(cudaMemcpy(c->P, p.data(), pn * 4, cudaMemcpyHostToDevice));
+		CK(copy_sync(c, c->P, p.data(), pn * 4, cudaMemcpyHostToDevice));
+		if (g.snp) { CK(launch_snp_pc_from_p(c->P, c->Pc, g, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
 		return IG_OK;
 	}
 	case IG_STATE_ALPHA: {
 		if ((st = need(bytes, 8, "ALPHA")) != IG_OK) return st;
-		CK(cudaMemcpy(&c->sc->alpha, host, 8, cudaMemcpyHostToDevice));
+		CK(copy_sync(c, &c->sc->alpha, host, 8, cudaMemcpyHostToDevice));
 		return IG_OK;
 	}
 	case IG_STATE_S:
 		if ((st = need(bytes, (size_t)c->ns * 8, "S")) != IG_OK) return st;
-		CK(cudaMemcpy(c->S, host, bytes, cudaMemcpyHostToDevice));
+		CK(copy_sync(c, c->S, host, bytes, cudaMemcpyHostToDevice));
 		if (c->cfg.ploid == 2 && c->cfg.mode == 3 && c->cfg.prior_flag == 1) dp_from_values(c, (const double *)host);   // the host-side clusters follow
 		return IG_OK;
 	case IG_STATE_STATE:
 		if ((st = need(bytes, (size_t)g.K * 4, "STATE")) != IG_OK) return st;
-		CK(cudaMemcpy(c->state, host, bytes, cudaMemcpyHostToDevice));
+		CK(copy_sync(c, c->state, host, bytes, cudaMemcpyHostToDevice));
 		return IG_OK;
 	case IG_STATE_GPROP: {      /* also refreshes the (g, g') pairs the sweep kernel reads */
 		if ((st = need(bytes, (size_t)g.N * 4, "GPROP")) != IG_OK) return st;
-		CK(cudaMemcpy(c->gprop, host, bytes, cudaMemcpyHostToDevice));
+		CK(copy_sync(c, c->gprop, host, bytes, cudaMemcpyHostToDevice));
 		std::vector<double> r((size_t)c->Npad * g.REC);
-		CK(cudaMemcpy(r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
+		CK(copy_sync(c, r.data(), c->ind, r.size() * 8, cudaMemcpyDeviceToHost));
 		std::vector<int2> gp(g.Nloc);
 		for (int il = 0; il < g.Nloc; il++) gp[il] = make_int2((int)r[(size_t)(g.i0 + il) * g.REC + g.K + 2], ((const int32_t *)host)[g.i0 + il]);
-		CK(cudaMemcpy(c->gpair, gp.data(), gp.size() * sizeof(int2), cudaMemcpyHostToDevice));
+		CK(copy_sync(c, c->gpair, gp.data(), gp.size() * sizeof(int2), cudaMemcpyHostToDevice));
 		return IG_OK;
 	}
 	case IG_STATE_ITER:
@@ -1163,6 +1210,7 @@ extern "C" ig_status ig_loglik(ig_ctx *c, const int32_t *gen, double *out)
 	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
 	CK(cudaSetDevice(c->cfg.device));
 	const Geometry &g = c->geo;
+	{ ig_status stz = ensure_zt(c); if (stz != IG_OK) return stz; }
 	int32_t *gd = nullptr;
 	double *od = nullptr;
 	CK(cudaMalloc((void **)&gd, (size_t)g.Nloc * 4));
@@ -1199,7 +1247,7 @@ extern "C" ig_status ig_alpha_logratio(ig_ctx *c, double ralpha, double *out)
 	// sweep uses, on a scratch copy of the scalars so that alpha itself is not advanced
 	DevScalars keep;
 	CK(cudaStreamSynchronize(c->stream));
-	CK(cudaMemcpy(&keep, c->sc, sizeof(keep), cudaMemcpyDeviceToHost));
+	CK(copy_sync(c, &keep, c->sc, sizeof(keep), cudaMemcpyDeviceToHost));
 	PostArgs a{c->ind, c->sc, c->gpart, c->geo, 0xFFFFFFFFu, c->key0, c->key1, nullptr, c->cfg.mode, c->cfg.back_refl,
 	           c->S, c->fprop, c->state, c->state2};
 	CK(launch_post_sweep(a, c->stream));
@@ -1207,7 +1255,7 @@ extern "C" ig_status ig_alpha_logratio(ig_ctx *c, double ralpha, double *out)
 	CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	*out = (ralpha - keep.alpha) * h.sumlogq;
-	CK(cudaMemcpy(c->sc, &keep, sizeof(keep), cudaMemcpyHostToDevice));
+	CK(copy_sync(c, c->sc, &keep, sizeof(keep), cudaMemcpyHostToDevice));
 	return IG_OK;
 }
 

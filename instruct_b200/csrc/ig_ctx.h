@@ -38,7 +38,12 @@ struct ig_ctx {
 	int rounds = 7;
 	// device buffers
 	int16_t *Xt = nullptr;
-	int8_t *Zt = nullptr;
+	int8_t *Zt = nullptr;           // micro-tiled Z; on the biallelic path only the state hooks' view (allocated on demand)
+	// biallelic path (zq_snp.cu): class-sorted store, Z in the same order, chunk-ordered P
+	uint32_t *Es = nullptr, *Hs = nullptr;
+	uint16_t *Zs = nullptr;
+	float *Pc = nullptr, *Pcnext = nullptr;
+	bool zt_stale = false;          // Zs is ahead of Zt
 	float *P = nullptr;
 	double *P64 = nullptr;
 	int32_t *n = nullptr;

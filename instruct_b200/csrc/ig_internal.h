@@ -11,6 +11,7 @@ namespace ig {
 constexpr int TILE = 8;          // loci per micro-tile (one 128-bit Z vector, two 128-bit X vectors)
 constexpr int ZQ_THREADS = 256;  // individuals per CTA pass
 constexpr int ZQ_MIN_CTAS = 2;   // resident CTAs per SM the sweep kernel is compiled and sized for
+constexpr int SNP_THREADS = 512; // zq_snp.cu: 16 warps, one CTA per SM
 constexpr int MAX_K = 16;
 constexpr int SC_MAX_CTAS = 592;   // cooperative scalar-update kernels: at most 4 CTAs per SM
 constexpr float P_FLOOR = 1e-18f;   // keeps f0*f1 a normal fp32 number in the product accumulators
@@ -49,6 +50,7 @@ struct Geometry {
 	int nblk;                // individual blocks (grid.y)
 	int subs_per_blk;        // 256-individual passes per CTA
 	int R;                   // smem histogram replicas
+	int snp;                 // 1: the biallelic path (zq_snp.cu): TL = compile-time chunk length, subs_per_blk = individuals per CTA
 	int fmode;               // 0: selfing generations (modes 1-3), 1: inbreeding coefficient per individual (mode 5), 2: per population (mode 4)
 	size_t zq_smem;          // dynamic shared memory bytes of zq_sweep
 	int tab_stage;           // ploid 4, PASS B: the chunk's genotype-frequency tables and the code -> index bytes are staged in shared memory
@@ -81,6 +83,37 @@ struct ZQArgs {
 cudaError_t launch_zq_sweep(const ZQArgs &a, int rounds, cudaStream_t s);
 cudaError_t zq_configure(Geometry &g, int device);
 
+// ---- the biallelic path (zq_snp.cu) ---------------------------------------------------
+struct SnpArgs {
+	const uint32_t *Es;      // [nchunks][Nloc][TL] class-sorted store entries (x0 TL + l) | (x1 TL + l) << 16, missing: 0x80000000 | l
+	uint16_t *Zs;            // [nchunks][Nloc][TL] z0 | z1 << 8 in the same order
+	const uint32_t *Hs;      // [nchunks][Nloc]     homozygotes | heterozygotes << 16
+	const float *Pc;         // [nchunks][4 KP TL]  chunk-ordered P: float4 planes [k/4][x][l], then words [k][x][l]
+	int32_t *n;              // [Lpad][2][KP]
+	const float *Qf;
+	const int2 *gpair;
+	uint16_t *pcnt; double *plog; uint16_t *pnsh;     // the partials of ZQArgs
+	Geometry geo;
+	uint32_t iter, key0, key1;
+	const uint32_t *iter_dev;
+	uint32_t k_mant, k_one;
+};
+cudaError_t launch_zq_snp(const SnpArgs &a, int rounds, cudaStream_t s);
+bool snp_eligible(const Geometry &g, int mode, int type_freq);
+cudaError_t snp_configure(Geometry &g, int device);
+size_t snp_pc_floats(const Geometry &g);
+cudaError_t launch_snp_tile(const int16_t *Xt, uint32_t *Es, uint32_t *Hs, Geometry g, cudaStream_t s);
+cudaError_t launch_snp_z_convert(const uint32_t *Es, uint16_t *Zs, int8_t *Zt, Geometry g, int to_sorted, cudaStream_t s);
+cudaError_t launch_snp_pc_from_p(const float *P, float *Pc, Geometry g, cudaStream_t s);
+// one element of the chunk-ordered P
+__host__ __device__ inline void snp_pc_store(float *Pc, int tlc, int KP, int l, int x, int k, float v)
+{
+	float *b = Pc + (size_t)(l / tlc) * 4 * KP * tlc;
+	const int ll = l % tlc;
+	b[((size_t)(k / 4) * 2 * tlc + (size_t)x * tlc + ll) * 4 + (k % 4)] = v;
+	b[(size_t)2 * KP * tlc + ((size_t)k * 2 + x) * tlc + ll] = v;
+}
+
 struct EpiArgs {
 	const uint16_t *pcnt; const double *plog; const uint16_t *pnsh;
 	const int32_t *nhet;     // [Nloc] usable heterozygous genotypes (data only; computed at load)
@@ -110,6 +143,8 @@ struct PArgs {
 	const uint32_t *iter_dev;
 	int mono_ok;             // 1: a locus with one allele gets P = 1 (update_P_auto has no allelenum > 1 guard, poly_geno.c:425)
 	int sub;                 // 1: the second subgenome of the allotetraploid model (its own random stream)
+	float *Pc;               // biallelic path: the chunk-ordered copy of P the sweep kernel stages (null otherwise)
+	int tlc;
 };
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s);
 

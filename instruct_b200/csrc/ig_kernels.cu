@@ -43,7 +43,12 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 	const size_t base = (size_t)l * g.A * g.KP + k;
 	const int Al = (l < g.L) ? a.allelenum[l] : 0;
 	if (k >= g.K || Al <= 1) {
-		for (int al = 0; al < g.A; al++) { a.P[base + (size_t)al * g.KP] = (a.mono_ok && k < g.K && Al == 1 && al == 0) ? 1.0f : 0.0f; a.n[base + (size_t)al * g.KP] = 0; }
+		for (int al = 0; al < g.A; al++) {
+			const float v = (a.mono_ok && k < g.K && Al == 1 && al == 0) ? 1.0f : 0.0f;
+			a.P[base + (size_t)al * g.KP] = v;
+			if (a.Pc) snp_pc_store(a.Pc, a.tlc, g.KP, l, al, k, v);
+			a.n[base + (size_t)al * g.KP] = 0;
+		}
 		return;
 	}
 	Stream st((uint32_t)l, (uint32_t)k + 256u * (uint32_t)a.sub, iter, TAG_P, a.key0, a.key1);
@@ -54,7 +59,9 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 		for (int al = 0; al < Al; al++) { gam[al] = draw_gamma(st, (double)a.n[base + (size_t)al * g.KP] + 1.0); sum += gam[al]; }
 		for (int al = 0; al < g.A; al++) {
 			const double p = (al < Al) ? gam[al] / sum : 0.0;
-			a.P[base + (size_t)al * g.KP] = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;
+			const float pv = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;
+			a.P[base + (size_t)al * g.KP] = pv;
+			if (a.Pc) snp_pc_store(a.Pc, a.tlc, g.KP, l, al, k, pv);
 			if (a.P64) a.P64[((size_t)k * g.L + l) * g.A + al] = p;
 			a.n[base + (size_t)al * g.KP] = 0;
 		}

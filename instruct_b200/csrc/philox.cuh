@@ -69,6 +69,7 @@ enum : uint32_t {
 	TAG_DP = 11u << 16,     // host-side Dirichlet-process step    (DPMM.c:124-199)
 	TAG_GENO = 12u << 16,   // tetraploid dosage resolution        (poly_geno.c:520)
 	TAG_TETRA = 13u << 16,  // tetraploid selfing-rate MH          (poly_geno.c:584)
+	TAG_ZS = 15u << 16,     // ancestry draw of the biallelic path (zq_snp.cu): block (chunk step, individual), draw number = lane
 	TAG_Z16 = 14u << 16,    // ancestry draw, 16 random bits per allele copy (one block per four genotypes)
 };
 

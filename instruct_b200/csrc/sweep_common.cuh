@@ -82,11 +82,9 @@ __device__ __forceinline__ float lg2_fast(float x)           // MUFU.LG2; |abs e
 
 constexpr float BIG126 = 8.507059173023462e37f;          // 2^126
 constexpr float U_SCALE = 8.507059173023462e37f;         // (f - 1 + 2^-24) * 2^126, f in [1,2)
-#ifdef IG_Z16
-constexpr float U_OFFS = -8.507059173023462e37f;         // 16-bit draw: the half step sits in the mantissa (bit 6), so the offset is -2^126
-#else
 constexpr float U_OFFS = -8.5070586659632355e37f;        // (-1 + 2^-24) * 2^126
-#endif
+constexpr float U_OFFS16 = -8.507059173023462e37f;       // 16-bit draw: the half step sits in the mantissa (bit 6), so the offset is -2^126
+constexpr uint32_t U16_MANT = 0x007fff80u, U16_ONE = 0x3f800040u;   // RegConst of the 16-bit draw: mantissa bits 22..7, half step in bit 6
 
 struct RegConst { uint32_t mant, one; };                 // 0x007fffff, 0x3f800000 held in registers
 
@@ -98,6 +96,19 @@ __device__ __forceinline__ float uniform_big(uint32_t r, const RegConst &k)
 	uint32_t b;
 	asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(b) : "r"(r), "r"(k.mant), "r"(k.one));     // (r & mant) | one
 	return fmaf(__uint_as_float(b), U_SCALE, U_OFFS);
+}
+
+// The bulk ancestry draw takes SIXTEEN random bits per allele copy, so that one Philox4x32 block serves four genotypes
+// (eight copies): u = (r16 + 0.5) / 65536 scaled by 2^126.  Copy 0 of a genotype uses bits 22..7 of its word where they
+// lie -- they are the mantissa -- and copy 1 the other sixteen, rotated into place by one PRMT (__byte_perm(r, 0, 0x1032)).
+// k = {U16_MANT, U16_ONE}: (r & mant) | one = 1.r16|1000000b, i.e. 1 + u exactly.  A draw probability is therefore exact
+// to 2^-16; where in a weight interval the 65536 grid points fall varies from locus to locus and individual to
+// individual, so nothing is systematically favoured (chi-square tests against the exact conditional in tests/).
+__device__ __forceinline__ float uniform_big16(uint32_t r, const RegConst &k)
+{
+	uint32_t b;
+	asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(b) : "r"(r), "r"(k.mant), "r"(k.one));
+	return fmaf(__uint_as_float(b), U_SCALE, U_OFFS16);
 }
 
 // index of the first cumulative weight that exceeds t, as a FLOAT in {0..KP-1}:

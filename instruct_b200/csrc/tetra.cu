@@ -1343,10 +1343,10 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	const size_t tn = (size_t)t->Lq * g.K * t->Gmax;
 	CK(dalloc0(&t->Xq, tiles)); CK(dalloc0(&t->Zq, tiles)); CK(dalloc0(&t->Gq, tiles));
 	CK(dalloc0(&t->cats, (size_t)t->ncat)); CK(dalloc0(&t->codes, codes.size())); CK(dalloc0(&t->c2i, c2i.size())); CK(dalloc0(&t->loc_cat, (size_t)t->Lq));
-	CK(cudaMemcpy(t->cats, t->cat_h, sizeof(TetraCat) * t->ncat, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(t->codes, codes.data(), codes.size() * 4, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(t->c2i, c2i.data(), c2i.size(), cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(t->loc_cat, loc_cat.data(), loc_cat.size() * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpyAsync(t->cats, t->cat_h, sizeof(TetraCat) * t->ncat, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpyAsync(t->codes, codes.data(), codes.size() * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpyAsync(t->c2i, c2i.data(), c2i.size(), cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpyAsync(t->loc_cat, loc_cat.data(), loc_cat.size() * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
 	CK(dalloc0(&t->exf, tn)); CK(dalloc0(&t->tabC, tn)); CK(dalloc0(&t->tabP, tn));
 	CK(dalloc0(&t->Sprop, (size_t)MAX_K)); CK(dalloc0(&t->dstat, (size_t)MAX_K)); CK(dalloc0(&t->accepted, (size_t)MAX_K));
 	CK(dalloc0(&t->dfix, (size_t)MAX_K)); CK(dalloc0(&t->lpart, (size_t)g.nchunks * 2 * g.Nloc));
@@ -1695,7 +1695,7 @@ ig_status tetra_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes,
 	}
 	case IG_STATE_SPROP:
 		if (bytes != (size_t)g.K * 8) return fail(IG_ERR_ARG, "SPROP: expected %zu bytes", (size_t)g.K * 8);
-		CK(cudaMemcpy(t->Sprop, host, bytes, cudaMemcpyHostToDevice));
+		CK(cudaMemcpyAsync(t->Sprop, host, bytes, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
 		return IG_OK;
 	case IG_STATE_P2: {
 		if (!t->allo) return fail(IG_ERR_ARG, "P2: allotetraploid model only");
@@ -1704,7 +1704,7 @@ ig_status tetra_set_state(ig_ctx *c, int32_t id, const void *host, size_t bytes,
 		std::vector<float> p(pn, 0.0f);
 		for (int k = 0; k < g.K; k++) for (int l = 0; l < g.L; l++) for (int al = 0; al < g.A; al++)
 			p[((size_t)l * g.A + al) * g.KP + k] = (float)((const double *)host)[((size_t)k * g.L + l) * g.A + al];
-		CK(cudaMemcpy(t->P2, p.data(), pn * 4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpyAsync(t->P2, p.data(), pn * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
 		return IG_OK;
 	}
 	case IG_STATE_TABLES: {

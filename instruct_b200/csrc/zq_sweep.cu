@@ -131,8 +131,8 @@ __device__ __forceinline__ uint32_t genotype(int xw, uint32_t zw, uint32_t r0, u
 		}
 	}
 	// ---- categorical draws (disc_unif, random.c:403-430)
-	const float zf0 = pick_category<KP>(c0, uniform_big(r0, kc));
-	const float zf1 = pick_category<KP>(c1, uniform_big(r1, kc));
+	const float zf0 = pick_category<KP>(c0, uniform_big16(r0, kc));
+	const float zf1 = pick_category<KP>(c1, uniform_big16(r1, kc));
 	const float pa0f = fmaf(zf0, as_dn(4u), row0f), pa1f = fmaf(zf1, as_dn(4u), row1f);           // &P[l][x][z]
 	// ---- n[l][a][k] tally for the next update_P (mcmc.c:815-845) and the individual's
 	//      ancestry counts (mcmc.c:1176-1194): shared-memory RED
@@ -187,7 +187,6 @@ __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&
                                            uint32_t mt_global, uint32_t ig_global, uint32_t iter, const ZQArgs &a, const float (&q)[KP], const Thr &t,
                                            Acc &acc, const RegConst &kc)
 {
-#ifdef IG_Z16
 	// 16 random bits per allele copy: one Philox block serves FOUR genotypes.  Copy 0 of a genotype takes bits 22..7 of
 	// its word as they lie (the mantissa of uniform_big), copy 1 the other sixteen, rotated into the same place by one PRMT.
 #pragma unroll
@@ -217,31 +216,6 @@ __device__ __forceinline__ void micro_tile(const int (&xw)[8], const uint32_t (&
 			zwn[pr] = __byte_perm(pair[0], pair[1], 0x5410);
 		}
 	}
-#else
-#pragma unroll
-	for (int pr = 0; pr < 4; ++pr) {
-		const u32x4 rnd = philox4x32<ROUNDS>(u32x4{mt_global, ig_global, iter, TAG_Z | (uint32_t)pr}, a.key0, a.key1);
-		const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-		uint32_t pair[2];
-#pragma unroll
-		for (int h2 = 0; h2 < 2; ++h2) {
-			const int j = 2 * pr + h2;
-			const float rowbf = fmaf((float)j, rowstridef, rowb0f);
-			if (CHECK) {
-				pair[h2] = h2 ? (zwo[pr] >> 16) : (zwo[pr] & 0xFFFFu);
-				// the tiler stores a genotype with ANY missing copy as (-9,-9): one sign test
-				if (xw[j] >= 0) {
-					if (h2) pair[h2] = genotype<KP, TF0, LR, 1, FM>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
-					else pair[h2] = genotype<KP, TF0, LR, 0, FM>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
-				}
-			} else {
-				if (h2) pair[h2] = genotype<KP, TF0, LR, 1, FM>(xw[j], zwo[pr], rr[2], rr[3], rowbf, q, t, acc, kc);
-				else pair[h2] = genotype<KP, TF0, LR, 0, FM>(xw[j], zwo[pr], rr[0], rr[1], rowbf, q, t, acc, kc);
-			}
-		}
-		zwn[pr] = __byte_perm(pair[0], pair[1], 0x5410);
-	}
-#endif
 }
 
 // --------------------------------------------------------------------------------------

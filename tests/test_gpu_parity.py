@@ -58,6 +58,9 @@ SHAPES = [
     (64, 130, 8, 2, 0.1),       # KP=8, SNP, several micro-tiles
     (70, 21, 12, 3, 0.02),      # KP=16
     (530, 9, 3, 12, 0.3),       # many alleles, heavy missingness, several individual passes
+    (70, 1300, 8, 2, 0.05),     # biallelic path (zq_snp.cu), 1024-locus chunks: one full chunk and a partial one
+    (45, 600, 3, 2, 0.02),      # biallelic path, KP=4, one partial 1024-locus chunk
+    (40, 300, 7, 2, 0.5),       # biallelic path, 256-locus chunks, half of the genotypes missing
 ]
 
 
@@ -153,10 +156,12 @@ def test_standalone_loglik_proposal_alpha():
     s.close()
 
 
-def test_z_draw_matches_exact_conditional():
+@pytest.mark.parametrize("K,A", [(5, 4), (6, 2), (3, 2)])
+def test_z_draw_matches_exact_conditional(K, A):
     """Chi-square of the categorical draw (update_ZQ, mcmc.c:1139-1153) against the oracle's
-    exact P(z = k) = Q_ik P_k,l,x / sum, pooled over repeated sweeps of a fixed state."""
-    N, L, K, A = 32, 8, 5, 4
+    exact P(z = k) = Q_ik P_k,l,x / sum, pooled over repeated sweeps of a fixed state.  (K, A) = (5, 4): the generic
+    kernel; A = 2: the biallelic path.  Both take 16 random bits per allele copy."""
+    N, L = 32, 8
     d, sd = _mk(N, L, K, A, 0.0, seed=6)
     s = Sampler(sd)
     o = Oracle(d.x, d.allelenum, K)
