@@ -234,6 +234,129 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def _barrier_time(dist, dev):
+    import torch
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    return time.perf_counter()
+
+
+def measure_e2e(args, x, an, K, N, mode, ploid, tetra, nloc, srank, count, chain, gsz, grp, rank, world, local, dist, copies_total):
+    """One chain through the public API from HOST buffers, at N GPUs.  N = 1: ``mcmc_updating()`` (the drop-in call).
+    N > 1: what the sharded drop-in does on every rank -- context for its shard, H2D of the shard, communicator, the chain,
+    CHAIN back on every rank.  Timed between barriers; the slowest rank counts."""
+    import numpy as np
+    import torch
+    from instruct_b200 import Init, Sampler, SeqData, mcmc_updating
+    from instruct_b200.shard import broadcast_unique_id
+
+    dev = torch.device("cuda", local)
+    xh = torch.empty(x.shape, dtype=torch.int16, pin_memory=True)
+    xh.copy_(x)
+    anh = an.cpu().numpy()
+    torch.cuda.synchronize()
+    upd = args.e2e_sweeps or 4 * (args.steps + args.warmup)
+    burn = max(1, args.warmup)
+    sd_h = SeqData(xh.numpy(), anh, K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0, alpha_dpm=2.0,
+                   nstep_check_empty_cluster=10 ** 9, autopoly=0 if args.workload in ALLO else 1)
+    times, ch = [], None
+    for _ in range(3):
+        t0 = _barrier_time(dist, dev)
+        if world == 1:
+            ch = mcmc_updating(sd_h, Init(update=upd, burnin=burn, thinning=1), 0, None, seed=args.seed, device=local)
+        else:
+            sm = Sampler(sd_h, update=upd, burnin=burn, thinning=1, seed=args.seed, device=local, shard_rank=srank, shard_count=count,
+                         totalsize=N, rng_rounds=args.rng_rounds)
+            uid = broadcast_unique_id(Sampler.unique_id, rank, src=chain * gsz, group=grp)
+            sm.comm_init(uid)
+            ch, _ = sm.run_chain(chain, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
+            sm.close()
+        t1 = time.perf_counter()
+        dt = t1 - t0
+        if dist is not None:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0].item())
+        times.append(dt)
+    med = sorted(times)[1]
+    h2d = xh.numel() * 2 + anh.size * 4
+    d2h = 8 * (N * (2 * K + 3) + 2 * K + 2)
+    del xh
+    return {"value": copies_total * upd / med, "unit": "copy-updates/s", "h2d_bytes_per_step": h2d / upd, "d2h_bytes_per_step": d2h / upd,
+            "sweeps": upd, "seconds": med, "seconds_each_call": times, "statistic": "median of three calls",
+            "retained_samples": int(ch.step), "posterior_mean_loglik": float(ch.totallkh), "n_gpus": world,
+            "note": ("one ig_mcmc_updating() call: create + H2D of the pinned genotype store + all sweeps + D2H of CHAIN" if world == 1 else
+                     "per rank: create + H2D of its pinned shard + NCCL communicator + all sweeps of the sharded chain + D2H of CHAIN; "
+                     "between barriers, slowest rank; h2d_bytes_per_step is per rank")}
+
+
+def check_shard_parity(args, K, mode, srank, count, chain, gsz, grp, rank, local, dist):
+    """A 30-sweep chain on a small slice, sharded over this run's ranks and unsharded on one GPU, compared bit for bit
+    (posterior moments of Q, S, G, the log-likelihood trace).  True / False on rank 0."""
+    import numpy as np
+    import torch
+    from instruct_b200 import Sampler, SeqData
+    from instruct_b200.shard import broadcast_unique_id, shard_bounds
+    from instruct_b200.synth import make_dataset
+
+    Ns, Ls = 64 * count + 7, 777                       # ragged on purpose
+    d = make_dataset(N=Ns, L=Ls, K=K, A=2, miss=0.02, seed=99)
+    b, e = shard_bounds(Ns, count, srank)
+    kw = dict(update=30, burnin=10, thinning=2, ckrep=5, seed=4242, device=local)
+    sd_s = SeqData(np.ascontiguousarray(d.x[:, b:e, :]), d.allelenum, K, mode=mode if mode in (1, 2, 3) else 2)
+    sm = Sampler(sd_s, shard_rank=srank, shard_count=count, totalsize=Ns, **kw)
+    sm.comm_init(broadcast_unique_id(Sampler.unique_id, rank, src=chain * gsz, group=grp))
+    initd = np.linspace(0.2, 0.8, K)
+    ch_s, cv_s = sm.run_chain(0, initd=initd)
+    sm.close()
+    ok = True
+    if srank == 0:
+        s1 = Sampler(SeqData(d.x, d.allelenum, K, mode=sd_s.mode), **kw)
+        ch_1, cv_1 = s1.run_chain(0, initd=initd)
+        s1.close()
+        ok = (ch_s.totallkh == ch_1.totallkh and np.array_equal(ch_s.qq, ch_1.qq) and np.array_equal(ch_s.self_rates, ch_1.self_rates)
+              and np.array_equal(ch_s.gen, ch_1.gen) and np.array_equal(ch_s.indvlkh, ch_1.indvlkh) and np.array_equal(cv_s, cv_1))
+    t = torch.tensor([1 if ok else 0], device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t[0].item()))
+
+
+def measure_chains(args, N, L, K, A, miss, mode, tetra, ploid, rank, world, local, dist):
+    """The other way the path shards: one independent chain per GPU on the whole data set, no communication.  Same
+    workload, same step count, timed between barriers on the slowest rank."""
+    import numpy as np
+    import torch
+    from instruct_b200 import Sampler, SeqData
+    from instruct_b200.synth import make_dataset_torch, make_tetra_dataset_torch
+
+    dev = torch.device("cuda", local)
+    if tetra:
+        x, an = make_tetra_dataset_torch(N, L, K, A=A, miss=miss, seed=4 + rank, device=dev)
+        usable = float((x[:, :, 0] >= 0).sum().item())
+    else:
+        x, an = make_dataset_torch(N, L, K, A=A, miss=miss, seed=4 + rank, device=dev)
+        usable = float((~(x < 0).any(dim=2)).sum().item())
+    torch.cuda.synchronize()
+    shape_only = np.lib.stride_tricks.as_strided(np.zeros(1, dtype=np.int16), shape=(L, N, ploid), strides=(0, 0, 0))
+    sd = SeqData(shape_only, np.zeros(L, dtype=np.int32), K, ploid=ploid, mode=mode, autopoly=0 if args.workload in ALLO else 1)
+    s = Sampler(sd, seed=args.seed, device=local, rng_rounds=args.rng_rounds, x_device_ptr=x.data_ptr(), allelenum_device_ptr=an.data_ptr())
+    s.chain_init(rank, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
+    s.sweep(args.warmup)
+    s.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = s.time_sweeps(args.steps)
+    t = torch.tensor([ms, ploid * usable], device=dev, dtype=torch.float64)
+    mx = t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    s.close()
+    ms = float(mx[0].item())
+    return {"parallelism": "chains x%d (one independent chain per GPU, no communication)" % world, "ms_per_step": ms / args.steps,
+            "value": float(t[1].item()) * args.steps / (ms * 1e-3), "unit": "copy-updates/s", "scaling": "weak"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -343,32 +466,21 @@ def run_ours(args):
 
     geo = s.geometry()
     s.close()                                      # the timed context is done: release its buffers before the end-to-end call
-    # ---- e2e: the drop-in call with HOST buffers (H2D of the store + D2H of the moments inside)
+    # ---- e2e: the drop-in call with HOST buffers.  Every rank holds its shard of the genotype store in pinned host memory;
+    # the timed region is create + H2D of the store + (N > 1: communicator) + the whole chain + D2H of CHAIN, between
+    # barriers, max over ranks.  Three calls, the MEDIAN is reported and all three are kept in the line.
     e2e = None
-    if rank == 0 and not args.no_e2e:
-        from instruct_b200 import Init, mcmc_updating
-        xh = torch.empty(x.shape, dtype=torch.int16, pin_memory=True)
-        xh.copy_(x)
-        torch.cuda.synchronize()
-        sd_h = SeqData(xh.numpy(), an.cpu().numpy(), K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0,
-                       alpha_dpm=2.0, nstep_check_empty_cluster=10 ** 9, autopoly=0 if args.workload in ALLO else 1)
-        upd = args.steps + args.warmup
-        # the call is made three times and the fastest one reported: cudaMalloc / cudaFree of the multi-GB buffers
-        # stall for hundreds of ms now and then on these boxes (IG_TRACE=1 shows the stages), both times are kept
-        times = []
-        for _ in range(3):
-            t0 = time.perf_counter()
-            ch = mcmc_updating(sd_h, Init(update=upd, burnin=args.warmup if args.warmup > 0 else 1, thinning=1), 0, None,
-                               seed=args.seed, device=local)
-            times.append(time.perf_counter() - t0)
-        dt = min(times)
-        h2d = xh.numel() * 2 + an.numel() * 4
-        d2h = 8 * (nloc * (2 * K + 3) + 2 * K + 2)
-        e2e = {"value": copies_local * upd / dt, "unit": "copy-updates/s", "h2d_bytes_per_step": h2d / upd,
-               "d2h_bytes_per_step": d2h / upd, "sweeps": upd, "seconds": dt, "seconds_each_call": times,
-               "retained_samples": int(ch.step), "posterior_mean_loglik": float(ch.totallkh),
-               "note": "one ig_mcmc_updating() call: create + H2D of the pinned genotype store + all sweeps + D2H of CHAIN"}
-        del xh
+    if not args.no_e2e and (world == 1 or shard_ind):
+        e2e = measure_e2e(args, x, an, K, N, mode, ploid, tetra, nloc, srank, count, chain_of_rank, gsz, grp, rank, world, local, dist,
+                          copies_total)
+    shard_parity = None
+    if world > 1 and shard_ind and not tetra:
+        shard_parity = check_shard_parity(args, K, mode, srank, count, chain_of_rank, gsz, grp, rank, local, dist)
+    chains_rec = None
+    if world > 1 and shard_ind and gsz == world and not args.no_chains:
+        del x
+        torch.cuda.empty_cache()
+        chains_rec = measure_chains(args, N, L, K, A, miss, mode, tetra, ploid, rank, world, local, dist)
 
     if rank == 0:
         cb = None
@@ -391,6 +503,7 @@ def run_ours(args):
                          "graph_replay": (not inline_profile) and world == 1 and not tetra and args.workload != "c3", "ms_per_step_direct_launch": ms_direct / args.steps},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None,
             "e2e": e2e, "gpu_launches": int(k1 - k0), "clocks": clk,
+            "shard_parity": shard_parity, "chains": chains_rec,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -411,6 +524,8 @@ def main():
     ap.add_argument("--N", type=int, default=0)
     ap.add_argument("--L", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-chains", action="store_true", help="N > 1: skip the chain-partitioned sub-record")
+    ap.add_argument("--e2e-sweeps", type=int, default=0, help="sweeps of the end-to-end chain (default 4 x (steps + warmup))")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -175,6 +175,10 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->ev_zq) cudaEventDestroy(c->ev_zq);
 	if (c->ev_p) cudaEventDestroy(c->ev_p);
 	cudaFree(c->Pnext);
+	cudaFree(c->g8_dev);
+	if (c->g8_host) cudaFreeHost(c->g8_host);
+	if (c->S_pin) cudaFreeHost(c->S_pin);
+	if (c->ev_g) cudaEventDestroy(c->ev_g);
 	tetra_destroy(c);
 	free_all(c);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -477,14 +481,14 @@ static void dp_init(ig_ctx *c)                         // init_DP, DPMM.c:124-16
 		}
 	}
 }
-static void dp_update(ig_ctx *c, const std::vector<double> &ind_h)   // update_DP, DPMM.c:165-199
+static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165-199; gen8[j] = G_j
 {
 	const Geometry &g = c->geo;
 	const int N = g.N;
 	std::vector<double> cum(N + 1);
 	for (int j = 0; j < N; j++) {
 		Stream st((uint32_t)j, 0u, c->iter, TAG_DP, c->key0, c->key1);
-		const int gen = (int)ind_h[(size_t)j * g.REC + g.K + 2];
+		const int gen = (int)gen8[j];
 		dp_leave(c, j);
 		cum[0] = c->cfg.alpha_dpm / (gen + 1) / gen;                  // gen_post_prob, DPMM.c:369
 		int n = 1;
@@ -547,11 +551,25 @@ static ig_status phase_update_S(ig_ctx *c)
 	// log_ld_noselfing_indv (mcmc.c:1869)
 	if (c->cfg.mode <= 1) return IG_OK;
 	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1) {
-		c->ind_h.resize((size_t)c->Npad * g.REC);
-		CK(cudaMemcpyAsync(c->ind_h.data(), c->ind, c->ind_h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-		CK(cudaStreamSynchronize(c->stream));
-		dp_update(c, c->ind_h);
-		CK(cudaMemcpyAsync(c->S, c->S_h.data(), (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		if (!c->g8_dev) {
+			ig_alloc_stream = c->stream;
+			CK(dalloc(&c->g8_dev, (size_t)g.N));
+			CK(cudaHostAlloc((void **)&c->g8_host, (size_t)g.N, cudaHostAllocDefault));
+			CK(cudaHostAlloc((void **)&c->S_pin, (size_t)g.N * sizeof(double), cudaHostAllocDefault));
+			CK(cudaEventCreateWithFlags(&c->ev_g, cudaEventDisableTiming));
+		}
+		if (!c->g8_inflight) {                               // first sweep, or a hook touched the state since the last one
+			CK(launch_pack_g(c->ind, c->g8_dev, g, c->stream));
+			CK(cudaMemcpyAsync(c->g8_host, c->g8_dev, (size_t)g.N, cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaEventRecord(c->ev_g, c->stream));
+			c->launches++;
+		}
+		CK(cudaEventSynchronize(c->ev_g));
+		c->g8_inflight = false;
+		dp_update(c, c->g8_host);
+		// the previous sweep's copy out of S_pin has long completed: pre_sweep consumed S before the epilogue whose G we just read
+		memcpy(c->S_pin, c->S_h.data(), (size_t)g.N * sizeof(double));
+		CK(cudaMemcpyAsync(c->S, c->S_pin, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	}
 	// UPMCMC.state is read by every CTA and written by one: double-buffered
 	PreArgs a{c->ind, c->S, c->state, c->state2, c->gprop, c->gpair, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1,
@@ -595,7 +613,18 @@ static ig_status phase_zq(ig_ctx *c, int init)
 	CK(launch_epilogue(e, c->stream));
 	c->launches += 2;
 	if (c->geo.fmode == 2 && !init) { CK(launch_fk_epilogue(e, c->stream)); c->launches++; }
-	return exchange_individuals(c);
+	ig_status stx = exchange_individuals(c);
+	if (stx != IG_OK) return stx;
+	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1 && c->g8_dev && c->more_follow && !c->iter_dev) {
+		// the next sweep's Dirichlet-process scan needs this G: send it now, the host reads it while post_sweep and the
+		// next p_dirichlet run
+		CK(launch_pack_g(c->ind, c->g8_dev, c->geo, c->stream));
+		CK(cudaMemcpyAsync(c->g8_host, c->g8_dev, (size_t)c->geo.N, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaEventRecord(c->ev_g, c->stream));
+		c->launches++;
+		c->g8_inflight = true;
+	}
+	return IG_OK;
 }
 
 static ig_status phase_alpha(ig_ctx *c)
@@ -687,6 +716,7 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	c->key0 = (uint32_t)c->cfg.seed ^ (0x9E3779B9u * (uint32_t)(chain_id + 1));
 	c->key1 = (uint32_t)(c->cfg.seed >> 32) ^ (0x85EBCA6Bu * (uint32_t)(chain_id + 1));
 	c->iter = 0;
+	c->g8_inflight = false;
 	if (c->stream2) CK(cudaStreamSynchronize(c->stream2));
 	c->early_p = false;
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // the chain's RNG key is baked into the captured arguments
@@ -780,6 +810,7 @@ extern "C" ig_status ig_run_phase(ig_ctx *c, int32_t mask)
 	ig_status st;
 	if (c->tetra) return tetra_run_phase(c, mask);
 	c->dev_iter_valid = false;
+	c->g8_inflight = false;
 	if (mask & IG_PHASE_UPDATE_P) if ((st = phase_update_P(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_UPDATE_S) if ((st = phase_update_S(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_ZQ) if ((st = phase_zq(c, 0)) != IG_OK) return st;
@@ -833,7 +864,7 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 	out->step = 0;
 	out->flag_empty_cluster = 0;
 	long cnt_step = 0;
-	MomArgs m{c->ind, c->S, c->sc, c->P, c->mom, g, c->ns, 0, -1, cf.print_freq};
+	MomArgs m{c->ind, c->S, c->sc, c->P, c->mom, g, c->ns, 0, -1, cf.print_freq, cf.print_freq ? c->P64 : nullptr};
 	const long print_every = cf.update >= 100 ? cf.update / 100 : 1;   // print_info, mcmc.c:1273 (guards the /0 of App. B #7)
 	for (long step = 0; step < cf.update; step++) {
 		c->more_follow = step + 1 < cf.update;
@@ -1101,6 +1132,7 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 	const Geometry &g = c->geo;
 	ig_status st;
 	CK(cudaStreamSynchronize(c->stream));
+	c->g8_inflight = false;
 	if (c->tetra) {
 		bool handled = false;
 		st = tetra_set_state(c, id, host, bytes, &handled);

@@ -82,6 +82,13 @@ struct ig_ctx {
 	std::vector<double> dp_w;     // [slot][51] dgeom(value, g), g = 1..50
 	std::vector<int> dp_of;
 	int dp_head = -1, dp_free = -1, dp_cnt = 0;
+	// DP prior: the scan reads only G (one byte each, <= 50) and writes only S.  G is packed and copied to pinned host memory
+	// right behind the epilogue of the PREVIOUS sweep, so the host scan overlaps post_sweep and the next p_dirichlet;
+	// S goes back from pinned memory on the stream.  (Round 1 copied the whole record array both ways, synchronously.)
+	uint8_t *g8_dev = nullptr, *g8_host = nullptr;   // [N]
+	double *S_pin = nullptr;                         // [N] pinned
+	cudaEvent_t ev_g = nullptr;
+	bool g8_inflight = false;                        // a copy of the current G is on its way (or has arrived) in g8_host
 	// NCCL
 	ncclComm_t comm = nullptr;
 	// sharded chains: the tally all-reduce and the NEXT sweep's P draw run on a side stream behind

@@ -170,6 +170,7 @@ cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
 struct MomArgs {
 	const double *ind; const double *S; const DevScalars *sc; const float *P; Moments m;
 	Geometry geo; int ns; long step; int convg_slot; int print_freq;
+	const double *P64;       // print_freq: the allele frequencies in double, [K][L][A], as p_dirichlet drew them (the fp32 sweep copy is floored and rounded)
 };
 cudaError_t launch_moments(const MomArgs &a, cudaStream_t s);
 cudaError_t launch_moments_reset(const MomArgs &a, cudaStream_t s);
@@ -190,5 +191,6 @@ cudaError_t launch_init_chain(double *ind, double *S, int32_t *state, DevScalars
                               uint32_t key0, uint32_t key1, cudaStream_t s);
 cudaError_t launch_proposal_ll(const double *ind, const double *S, double *out, Geometry g, cudaStream_t s);
 cudaError_t launch_qf_from_ind(const double *ind, float *Qf, Geometry g, cudaStream_t s);
+cudaError_t launch_pack_g(const double *ind, uint8_t *g8, Geometry g, cudaStream_t s);     // G of every individual as one byte (DP host step)
 
 }  // namespace ig

@@ -126,14 +126,18 @@ __device__ __forceinline__ double trans_prob(int from, int to)
 }
 
 // --------------------------------------------------------------------------------------
-// Deterministic grid-wide sums for the scalar updates.  The kernels below are launched
-// cooperatively (all CTAs resident).  Each CTA reduces its threads' values with a fixed
-// shuffle/shared tree and writes one partial per value; after grid.sync() every CTA adds
-// the partials in CTA order.  Fixed launch shape => fixed summation order => bit-identical
-// on every rank of a sharded chain and for every GPU count.  Partials are double-buffered
-// so one grid.sync() per reduction suffices.
+// Deterministic sums over all individuals for the scalar updates.  update_S_POP is K sequential Metropolis steps, each
+// needing a sum over all N individuals (proposal(), mcmc.c:1630), update_alpha one: K + 2 reductions with a barrier each.
+// They run in ONE thread-block cluster of SC_CTAS CTAs (hardware cluster barrier, partial sums exchanged through
+// distributed shared memory): every CTA reduces its threads' values with a fixed shuffle / shared tree, publishes one
+// partial per value in its own shared memory, and after the cluster barrier adds the SC_CTAS partials in rank order.
+// Fixed launch shape => fixed summation order => bit-identical on every rank of a sharded chain and for every GPU count.
+// (Round 1 used a cooperative grid with grid.sync() and partials in global memory: 47 us per sweep at N = 10^4, and a
+// function-static occupancy cache that two contexts on different devices raced on; the cluster needs neither.)
 // --------------------------------------------------------------------------------------
-constexpr int SC_THREADS = 256;
+constexpr int SC_CTAS = 8;                      // portable cluster size
+constexpr int SC_THREADS = 512;
+constexpr int SC_WARPS = SC_THREADS / 32;
 constexpr int SC_MAXV = 20;                     // values reduced at once (K + 2 <= 18)
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -143,36 +147,40 @@ __device__ __forceinline__ double warp_sum(double v)
 	return v;
 }
 
-// reduce nv per-thread values over the whole grid; result in out[0..nv) for every thread
-__device__ void grid_sum(cg::grid_group &grid, const double *v, int nv, double *out, double *gpart, int &phase, double *sh /*[SC_MAXV][8]*/)
+struct ScShared {
+	double warp[SC_MAXV][SC_WARPS];
+	double part[2][SC_MAXV];                    // this CTA's partials, double-buffered by reduction parity
+	double total[SC_MAXV];
+};
+
+// reduce nv per-thread values over the whole cluster; the result lands in out[0..nv) for every thread
+__device__ void cluster_sum(cg::cluster_group &cl, const double *v, int nv, double *out, ScShared &sh, int &phase)
 {
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int j = 0; j < nv; j++) {
 		const double w = warp_sum(v[j]);
-		if (lane == 0) sh[j * 8 + wid] = w;
+		if (lane == 0) sh.warp[j][wid] = w;
 	}
 	__syncthreads();
-	double *buf = gpart + (size_t)(phase & 1) * gridDim.x * SC_MAXV;
 	if (tid < nv) {
 		double t = 0.0;
-		for (int w = 0; w < SC_THREADS / 32; w++) t += sh[tid * 8 + w];
-		buf[(size_t)blockIdx.x * SC_MAXV + tid] = t;
+		for (int w = 0; w < SC_WARPS; w++) t += sh.warp[tid][w];
+		sh.part[phase & 1][tid] = t;
 	}
-	__threadfence();
-	grid.sync();
+	cl.sync();                                   // every CTA's partials are written and visible cluster-wide
 	if (tid < nv) {
 		double t = 0.0;
-		for (unsigned b = 0; b < gridDim.x; b++) t += buf[(size_t)b * SC_MAXV + tid];
-		sh[SC_MAXV * 8 + tid] = t;
+		for (unsigned r = 0; r < SC_CTAS; r++) t += cl.map_shared_rank(&sh.part[phase & 1][0], r)[tid];
+		sh.total[tid] = t;
 	}
 	__syncthreads();
-	for (int j = 0; j < nv; j++) out[j] = sh[SC_MAXV * 8 + j];
-	__syncthreads();
+	for (int j = 0; j < nv; j++) out[j] = sh.total[j];
+	cl.sync();                                   // nobody leaves the kernel, or rewrites its partials, while a peer still reads them
 	phase++;
 }
 
 // --------------------------------------------------------------------------------------
-// pre_sweep (cooperative grid, one thread per individual, grid-stride beyond that):
+// pre_sweep (one cluster of SC_CTAS x SC_THREADS threads, striding over the individuals):
 // selfing-rate update, then the generation proposals of update_G.
 //   mode 2: update_S_POP (mcmc.c:913-983): K sequential MH steps, each a grid-wide sum of
 //           log( s_i^(G_i-1) (1-s_i) ), s_i = sum_k Q_ik S_k  (proposal, mcmc.c:1630)
@@ -181,10 +189,10 @@ __device__ void grid_sum(cg::grid_group &grid, const double *v, int nv, double *
 // Every rank of a sharded chain runs this redundantly on the all-gathered (Q, G): identical
 // inputs and a fixed reduction order give identical S everywhere, so no broadcast is needed.
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
+__global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 {
-	cg::grid_group grid = cg::this_grid();
-	__shared__ double sh[SC_MAXV * 8 + SC_MAXV];
+	cg::cluster_group cl = cg::this_cluster();
+	__shared__ ScShared sh;
 	__shared__ double Ssh[MAX_K];
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x;
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 			for (int k = 0; k < K; k++) s += rec[k] * Sl[k];
 			part += log_geom(s, (int)rec[K + 2]);
 		}
-		grid_sum(grid, &part, 1, &cur, a.gpart, phase, sh);
+		cluster_sum(cl, &part, 1, &cur, sh, phase);
 		int accepts = 0;
 		for (int j = 0; j < K; j++) {
 			Stream st((uint32_t)j, 0u, iter, TAG_SPOP, a.key0, a.key1);
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 				part += log_geom(s, (int)rec[K + 2]);
 			}
 			double pl;
-			grid_sum(grid, &part, 1, &pl, a.gpart, phase, sh);
+			cluster_sum(cl, &part, 1, &pl, sh, phase);
 			// every thread of every CTA takes the same decision from the same numbers
 			double ratio = exp(pl - cur);
 			if (a.back_refl == 0) ratio *= trans_prob(cs, new_state) / trans_prob(new_state, cs);
@@ -336,46 +344,34 @@ __global__ void __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
 	}
 }
 
-static int coop_grid(const void *kernel, int n_items, int device)
-{
-	int per_sm = 1, sms = 148;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SC_THREADS, 0);
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-	int want = (n_items + SC_THREADS - 1) / SC_THREADS;
-	int cap = per_sm * sms;
-	if (cap > SC_MAX_CTAS) cap = SC_MAX_CTAS;
-	if (want < 1) want = 1;
-	return want < cap ? want : cap;
-}
-
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
 {
-	static int grid_cache_n = -1, grid_cache = 0;
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (grid_cache_n != a.geo.N) { grid_cache = coop_grid((const void *)pre_sweep_kernel, a.geo.N, dev); grid_cache_n = a.geo.N; }
-	void *args[] = {(void *)&a};
-	return cudaLaunchCooperativeKernel((const void *)pre_sweep_kernel, dim3(grid_cache), dim3(SC_THREADS), args, 0, s);
+	pre_sweep_kernel<<<SC_CTAS, SC_THREADS, 0, s>>>(a);
+	return cudaGetLastError();
 }
 
 // --------------------------------------------------------------------------------------
-// indiv_epilogue: CTA = 32 individuals (lanes) x 8 chunk groups (warps).  Warp w adds the
-// partials of chunks w, w+8, ... (coalesced across the 32 individuals), warp 0 then adds the
-// 8 group sums in group order, takes the update_G accept decision (mcmc.c:1085-1089), draws
+// indiv_epilogue: CTA = 8 individuals x 32 chunk groups (a shard of 1250 individuals gets 157 CTAs; with the 32 x 8 shape
+// of round 1 it got 40 and took 85 us on 148 SMs).  Thread row w adds the partials of chunks w, w+32, ... , the group sums
+// are added in group order, then one thread per individual takes the update_G accept decision (mcmc.c:1085-1089), draws
 // Q_i ~ Dirichlet(cnt_i + alpha) (mcmc.c:1196-1198) and writes the individual's record
 // (Q, indvlkh, sum_k log q, G) into the all-gatherable array.  The summation order depends
 // only on the chunk decomposition, which depends only on (L, K, A): shard-invariant.
 // --------------------------------------------------------------------------------------
-constexpr int EPI_GROUPS = 8;       // chunk groups (warps) per CTA
-__global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const EpiArgs a)
+constexpr int EPI_IPB = 8;          // individuals per CTA
+constexpr int EPI_GROUPS = 32;      // chunk groups per CTA
+__global__ void __launch_bounds__(EPI_IPB * EPI_GROUPS) indiv_epilogue_kernel(const EpiArgs a)
 {
-	__shared__ int cnt_sh[EPI_GROUPS][MAX_K][32];
-	__shared__ double ll_sh[EPI_GROUPS][3][32];
-	__shared__ int nsh_sh[EPI_GROUPS][32];
-	__shared__ double gq_sh[MAX_K][32];
+	__shared__ int cnt_sh[EPI_GROUPS][MAX_K][EPI_IPB];
+	__shared__ double ll_sh[EPI_GROUPS][3][EPI_IPB];
+	__shared__ int nsh_sh[EPI_GROUPS][EPI_IPB];
+	__shared__ double gq_sh[MAX_K][EPI_IPB];
+	__shared__ int cntt_sh[MAX_K][EPI_IPB];
+	__shared__ double llt_sh[3][EPI_IPB];
+	__shared__ int nsht_sh[EPI_IPB];
 	const Geometry &g = a.geo;
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int il = blockIdx.x * 32 + lane;
+	const int lane = threadIdx.x % EPI_IPB, w = threadIdx.x / EPI_IPB;
+	const int il = blockIdx.x * EPI_IPB + lane;
 	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	const int K = g.K, KP = g.KP;
 	const bool live = il < g.Nloc;
@@ -408,31 +404,34 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 	ll_sh[w][0][lane] = d_old; ll_sh[w][1][lane] = a_new; ll_sh[w][2][lane] = b_new;
 	nsh_sh[w][lane] = nsh_new;
 	__syncthreads();
-	// ---- Q_i ~ Dirichlet(cnt_i + alpha) (mcmc.c:1195-1197): the K gamma draws of an individual are the long pole
-	//      of this kernel (double-precision Marsaglia-Tsang), so warp k draws population k's gamma for the CTA's 32
-	//      individuals, each (individual, population) on its own Philox stream; warp 0 then normalises
+	// ---- group sums in group order (the order depends only on the chunk decomposition: shard-invariant), spread over
+	//      the CTA: thread (k, individual) adds population k's counts and draws its gamma of Q_i ~ Dirichlet(cnt_i + alpha)
+	//      (mcmc.c:1195-1197; double-precision Marsaglia-Tsang, own Philox stream per (individual, population)); three more
+	//      thread rows add the likelihood pieces, one the heterozygote count
 	const int ig_global = g.i0 + il;
-	if (live)
-		for (int k = w; k < K; k += EPI_GROUPS) {
+	if (live) {
+		if (w < K) {
 			int ck = 0;
-			for (int ww = 0; ww < EPI_GROUPS; ww++) ck += cnt_sh[ww][k][lane];
-			Stream sq((uint32_t)ig_global, (uint32_t)k, iter, TAG_Q, a.key0, a.key1);
-			gq_sh[k][lane] = draw_gamma(sq, (double)ck + a.sc->alpha);
-		}
-	if (w == 0 && live) {
-		d_old = a_new = b_new = 0.0;
-		nsh_new = 0;
-#pragma unroll
-		for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
-		for (int ww = 0; ww < EPI_GROUPS; ww++) {
-#pragma unroll
-			for (int k = 0; k < MAX_K; k++) cnt[k] += cnt_sh[ww][k][lane];
-			d_old += ll_sh[ww][0][lane]; a_new += ll_sh[ww][1][lane]; b_new += ll_sh[ww][2][lane];
-			nsh_new += nsh_sh[ww][lane];
+			for (int ww = 0; ww < EPI_GROUPS; ww++) ck += cnt_sh[ww][w][lane];
+			cntt_sh[w][lane] = ck;
+			Stream sq((uint32_t)ig_global, (uint32_t)w, iter, TAG_Q, a.key0, a.key1);
+			gq_sh[w][lane] = draw_gamma(sq, (double)ck + a.sc->alpha);
+		} else if (w >= MAX_K && w < MAX_K + 3) {
+			double t = 0.0;
+			for (int ww = 0; ww < EPI_GROUPS; ww++) t += ll_sh[ww][w - MAX_K][lane];
+			llt_sh[w - MAX_K][lane] = t;
+		} else if (w == MAX_K + 3) {
+			int t = 0;
+			for (int ww = 0; ww < EPI_GROUPS; ww++) t += nsh_sh[ww][lane];
+			nsht_sh[lane] = t;
 		}
 	}
 	__syncthreads();
 	if (w != 0 || !live) return;
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++) cnt[k] = (k < K) ? cntt_sh[k][lane] : 0;
+	d_old = llt_sh[0][lane]; a_new = llt_sh[1][lane]; b_new = llt_sh[2][lane];
+	nsh_new = nsht_sh[lane];
 	// heterozygotes contribute ln 2 each (genofreq, mcmc.c:1700); the count is data only
 	const double c_new = (double)a.nhet[il] * LN2_D;
 	double *rec = a.ind + (size_t)ig_global * g.REC;
@@ -485,7 +484,7 @@ __global__ void __launch_bounds__(32 * EPI_GROUPS) indiv_epilogue_kernel(const E
 }
 cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s)
 {
-	indiv_epilogue_kernel<<<(a.geo.Nloc + 31) / 32, 32 * EPI_GROUPS, 0, s>>>(a);
+	indiv_epilogue_kernel<<<(a.geo.Nloc + EPI_IPB - 1) / EPI_IPB, EPI_IPB * EPI_GROUPS, 0, s>>>(a);
 	return cudaGetLastError();
 }
 
@@ -513,15 +512,15 @@ cudaError_t launch_fk_epilogue(const EpiArgs &a, cudaStream_t s)
 }
 
 // --------------------------------------------------------------------------------------
-// post_sweep (cooperative grid): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
+// post_sweep (one cluster, as pre_sweep): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
 // (update_alpha, mcmc.c:1244-1263, in log form: (alpha'-alpha) * sum log q), and the
 // column sums of Q for check_empty_cluster (mcmc.c:1954-1961) -- one grid-wide sum of
 // K + 2 values.
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a)
+__global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a)
 {
-	cg::grid_group grid = cg::this_grid();
-	__shared__ double sh[SC_MAXV * 8 + SC_MAXV];
+	cg::cluster_group cl = cg::this_cluster();
+	__shared__ ScShared sh;
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x, K = g.K, REC = g.REC;
 	const int gstride = gridDim.x * SC_THREADS;
@@ -537,7 +536,7 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 		for (int k = 0; k < MAX_K; k++) if (k < K) v[2 + k] += rec[k];
 	}
 	int phase = 0;
-	grid_sum(grid, v, K + 2, tot, a.gpart, phase, sh);
+	cluster_sum(cl, v, K + 2, tot, sh, phase);
 	if (a.mode == 5)                                        // the accepted F of every individual, from the (all-gathered) records
 		for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) a.S[i] = a.ind[(size_t)i * REC + K + 2];
 	if (a.mode == 4 && iter != 0xFFFFFFFFu) {
@@ -559,7 +558,7 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 #pragma unroll
 			for (int k = 0; k < MAX_K; k++) if (k < K) dv[k] += rec[k];
 		}
-		grid_sum(grid, dv, K, dt, a.gpart, phase, sh);
+		cluster_sum(cl, dv, K, dt, sh, phase);
 		bool acc[MAX_K];
 		int naccept = 0;
 		for (int k = 0; k < K; k++) {
@@ -579,7 +578,7 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 			rec[K] = l;
 			lv += l;
 		}
-		grid_sum(grid, &lv, 1, &lt, a.gpart, phase, sh);
+		cluster_sum(cl, &lv, 1, &lt, sh, phase);
 		tot[0] = lt;
 		if (blockIdx.x == 0 && tid == 0) {
 			for (int k = 0; k < K; k++) if (acc[k]) { a.S[k] = Fp[k]; if (a.back_refl == 0) a.state[k] = ns_[k]; }
@@ -612,12 +611,8 @@ __global__ void __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a
 }
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s)
 {
-	static int grid_cache_n = -1, grid_cache = 0;
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (grid_cache_n != a.geo.N) { grid_cache = coop_grid((const void *)post_sweep_kernel, a.geo.N, dev); grid_cache_n = a.geo.N; }
-	void *args[] = {(void *)&a};
-	return cudaLaunchCooperativeKernel((const void *)post_sweep_kernel, dim3(grid_cache), dim3(SC_THREADS), args, 0, s);
+	post_sweep_kernel<<<SC_CTAS, SC_THREADS, 0, s>>>(a);
+	return cudaGetLastError();
 }
 
 // --------------------------------------------------------------------------------------
@@ -659,7 +654,7 @@ __global__ void moments_kernel(const MomArgs a)
 		const long tot = (long)K * g.L * g.A;
 		for (long e = t; e < tot; e += (long)gridDim.x * blockDim.x) {
 			const int al = (int)(e % g.A), l = (int)((e / g.A) % g.L), k = (int)(e / ((long)g.A * g.L));
-			const double p = (double)a.P[((size_t)l * g.A + al) * g.KP + k];
+			const double p = a.P64 ? a.P64[e] : (double)a.P[((size_t)l * g.A + al) * g.KP + k];
 			run_mean(a.m.freq + e, p, step);
 			run_mean(a.m.freq2 + e, p * p, step);
 		}
@@ -879,6 +874,20 @@ __global__ void qf_from_ind_kernel(const double *ind, float *Qf, Geometry g)
 cudaError_t launch_qf_from_ind(const double *ind, float *Qf, Geometry g, cudaStream_t s)
 {
 	qf_from_ind_kernel<<<nblocks((size_t)g.Nloc * g.KP, 256), 256, 0, s>>>(ind, Qf, g);
+	return cudaGetLastError();
+}
+
+// the host-side Dirichlet-process step reads nothing but G (1..50)
+__global__ void pack_g_kernel(const double *ind, uint8_t *g8, Geometry g)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= g.N) return;
+	const double v = ind[(size_t)i * g.REC + g.K + 2];
+	g8[i] = (uint8_t)(v < 1.0 ? 1 : (v > 255.0 ? 255 : (int)v));
+}
+cudaError_t launch_pack_g(const double *ind, uint8_t *g8, Geometry g, cudaStream_t s)
+{
+	pack_g_kernel<<<(g.N + 255) / 256, 256, 0, s>>>(ind, g8, g);
 	return cudaGetLastError();
 }
 

@@ -120,9 +120,9 @@ template <int KP>
 __device__ __forceinline__ float pick_category(const float (&c)[KP], float ub)
 {
 #ifdef IG_PICK_BSEARCH
-	// EXPERIMENT (not built by default): the cumulative weights are non-decreasing, so the
-	// count #{k : t > c_k} is a three-level compare / select search for KP = 8 -- identical decisions, fewer issue slots
-	// (static SASS count in profiles/r1_zq_sweep_bsearch_sass.txt), but on the half-rate ALU pipe.  To be measured.
+	// The cumulative weights are non-decreasing, so the count #{k : t > c_k} is a three-level compare / select search for
+	// KP = 8 -- identical decisions, fewer issue slots, but on the half-rate ALU pipe.  Defined by zq_sweep.cu only (measured
+	// there: profiles/r2_zq_levers.md); the tetraploid passes and zq_snp.cu keep the saturating-FFMA form.
 	if (KP == 8) {
 		const float t = (ub * 1.1754943508222875e-38f) * c[KP - 1];          // 2^-126: a power of two, so t > c_k decides exactly as above
 		const bool p2 = t > c[3];

@@ -395,7 +395,12 @@ bool snp_eligible(const Geometry &g, int mode, int type_freq)
 #ifdef IG_FAST_BUILD
 	if (g.KP != 8) return false;
 #endif
-	if (getenv("IG_NO_SNP_PATH")) return false;
+	// Opt-in (IG_SNP_PATH=1): at config 4 this kernel runs 4.14 ms per launch against 3.95 ms for zq_sweep with the same
+	// 16-bit draw -- the class-pure rows cost 84 / 81 warp instructions per 32 genotypes as designed (generic: 116), but the
+	// per-step, per-pair and per-individual work that the lanes-are-loci decomposition adds (Philox per lane and step,
+	// cross-lane reductions per individual and chunk, rows at the class boundaries) takes 26 more per row
+	// (profiles/r2_zq_snp_ncu.md).  Kept, tested and measured; not the default.
+	if (!getenv("IG_SNP_PATH")) return false;
 	return g.A == 2 && (g.KP == 8 || g.KP == 4) && g.fmode == 0 && type_freq == 1 && mode >= 1 && mode <= 3;
 }
 

@@ -25,6 +25,9 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+// the K <= 8 categorical search as three compare/select levels: measured at config 4 together with the 16-bit draw,
+// 3.99 -> 3.95 ms per launch (alone, on the 23-bit draw, it lost 1.5 %: profiles/r2_zq_levers.md)
+#define IG_PICK_BSEARCH 1
 #include "ig_internal.h"
 #include "philox.cuh"
 #include "sweep_common.cuh"

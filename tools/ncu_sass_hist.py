@@ -14,7 +14,10 @@ for r in rows[hi + 1:]:
     src = r[ci["Source"]].strip()
     m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", src)
     op = m.group(2) if m else src[:10]
-    n = int(r[ci["Instructions Executed"]] or 0)
+    try:
+        n = int(r[ci["Instructions Executed"]] or 0)
+    except ValueError:
+        continue                                   # a second kernel's header row
     ops[op] += n; tot += n
     for h in hdr:
         if h.startswith("stall_") and "Not Issued" not in h:
