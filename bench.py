@@ -260,7 +260,7 @@ def measure_e2e(args, x, an, K, N, mode, ploid, tetra, nloc, srank, count, chain
     burn = max(1, args.warmup)
     sd_h = SeqData(xh.numpy(), anh, K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0, alpha_dpm=2.0,
                    nstep_check_empty_cluster=10 ** 9, autopoly=0 if args.workload in ALLO else 1)
-    times, ch = [], None
+    times, ch, comm_s = [], None, []
     for _ in range(3):
         t0 = _barrier_time(dist, dev)
         if world == 1:
@@ -268,8 +268,10 @@ def measure_e2e(args, x, an, K, N, mode, ploid, tetra, nloc, srank, count, chain
         else:
             sm = Sampler(sd_h, update=upd, burnin=burn, thinning=1, seed=args.seed, device=local, shard_rank=srank, shard_count=count,
                          totalsize=N, rng_rounds=args.rng_rounds)
+            tc = time.perf_counter()
             uid = broadcast_unique_id(Sampler.unique_id, rank, src=chain * gsz, group=grp)
             sm.comm_init(uid)
+            comm_s.append(time.perf_counter() - tc)
             ch, _ = sm.run_chain(chain, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
             sm.close()
         t1 = time.perf_counter()
@@ -286,8 +288,10 @@ def measure_e2e(args, x, an, K, N, mode, ploid, tetra, nloc, srank, count, chain
     return {"value": copies_total * upd / med, "unit": "copy-updates/s", "h2d_bytes_per_step": h2d / upd, "d2h_bytes_per_step": d2h / upd,
             "sweeps": upd, "seconds": med, "seconds_each_call": times, "statistic": "median of three calls",
             "retained_samples": int(ch.step), "posterior_mean_loglik": float(ch.totallkh), "n_gpus": world,
+            "comm_init_seconds_each_call": comm_s if comm_s else None,
             "note": ("one ig_mcmc_updating() call: create + H2D of the pinned genotype store + all sweeps + D2H of CHAIN" if world == 1 else
-                     "per rank: create + H2D of its pinned shard + NCCL communicator + all sweeps of the sharded chain + D2H of CHAIN; "
+                     "per rank: create + H2D of its pinned shard + NCCL communicator (a new one per call: comm_init_seconds_each_call, this "
+                     "rank's share of the time; a multi-chain run creates it once) + all sweeps of the sharded chain + D2H of CHAIN; "
                      "between barriers, slowest rank; h2d_bytes_per_step is per rank")}
 
 
@@ -409,6 +413,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         usable = float((~(x < 0).any(dim=2)).sum().item())
     copies_local = float(ploid) * usable
+    store_gb = (x.numel() * 2 + x.numel() * (2 if tetra else 1)) / 1e9
     # the genotype store is passed by device pointer (inputs resident in HBM); this SeqData only
     # carries the flags and the (L, Nloc, ploid) shape, through a zero-strided placeholder
     shape_only = np.lib.stride_tricks.as_strided(np.zeros(1, dtype=np.int16), shape=(L, nloc, ploid), strides=(0, 0, 0))
@@ -494,7 +499,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: K={K} N={N} L={L} A={A} " + (("allotetraploid" if args.workload in ALLO else "autotetraploid") if tetra else f"diploid mode {mode}") + f" miss={miss}",
                        "parallelism": ("individual-sharded x%d" % world) if (shard_ind and gsz == world) else
                                       (("%d chains x %d GPUs each (individual-sharded)" % (world // gsz, gsz)) if shard_ind else ("chains x%d" % world)),
-                       "l2": "inputs (%.2f GB per GPU) larger than L2" % ((x.numel() * 2 + x.numel() * (2 if tetra else 1)) / 1e9),
+                       "l2": "inputs (%.2f GB per GPU) larger than L2" % store_gb,
                        "geometry": geo, "rng": f"philox4x32-{args.rng_rounds or 7} (Z draw), philox4x32-10 (all other draws)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload, N, L) if world == 1 else None, "kernel": "tetra_zs + tetra_geno (the two passes of one sweep)" if tetra else "zq_sweep", "launches_timed": nz, "avg_launch_ms": zq_avg_ms,

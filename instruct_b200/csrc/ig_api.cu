@@ -60,6 +60,7 @@ struct NcclApi {
 	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
 	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;     // optional (NCCL >= 2.18)
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -81,6 +82,7 @@ static ig_status nccl_load()
 	SYM(AllGather, "ncclAllGather");
 	SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
+	*(void **)(&g_nccl.CommSplit) = dlsym(h, "ncclCommSplit");
 	g_nccl.h = h;
 	return IG_OK;
 }
@@ -89,6 +91,9 @@ static ig_status nccl_load()
 		ncclResult_t r_ = (call);                                                               \
 		if (r_ != ncclSuccess) return fail(IG_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r_)); \
 	} while (0)
+
+constexpr int PT_POINTS = 7, PT_SWEEPS = 64;        // IG_PHASE_TRACE: events per sweep, sweeps traced
+static void ptrace_report(ig_ctx *c);
 
 extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 {
@@ -141,6 +146,10 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	c->key1 = (uint32_t)(cfg->seed >> 32);
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(IG_ERR_CUDA, "stream creation failed"); }
 	ig_alloc_stream = c->stream;
+	if (getenv("IG_PHASE_TRACE")) {
+		c->ptrace.resize((size_t)PT_POINTS * PT_SWEEPS);
+		for (auto &e : c->ptrace) cudaEventCreate(&e);
+	}
 	if (cfg->ploid == 4) {
 		ig_status st = tetra_create(c);
 		if (st != IG_OK) { cudaStreamDestroy(c->stream); delete c; return st; }
@@ -168,6 +177,9 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->cfg.device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	ptrace_report(c);
+	for (auto e : c->ptrace) cudaEventDestroy(e);
+	if (c->comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm2);
 	if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
 	for (auto e : c->ev) cudaEventDestroy(e);
 	if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -226,6 +238,8 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	CK(dalloc(&c->initd_dev, (size_t)MAX_K));
 	CK(dalloc(&c->scratch, (size_t)64));
 	CK(dalloc(&c->gpart, (size_t)2 * SC_MAX_CTAS * 20));
+	c->grid_pre = scalar_grid(0, g.N, c->cfg.device);
+	c->grid_post = scalar_grid(1, g.N, c->cfg.device);
 	CK(dalloc(&c->state2, (size_t)MAX_K));
 	if (c->cfg.mode == 0) { ig_status st0 = na_alloc(c); if (st0 != IG_OK) return st0; }
 	if (g.fmode) {
@@ -328,6 +342,10 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 	ncclUniqueId id;
 	memcpy(&id, id128, 128);
 	NCK(g_nccl.CommInitRank(&c->comm, c->cfg.shard_count, id, c->cfg.shard_rank));
+	// (measured at 2 GPUs: no difference -- the all-gather does not queue behind the tally all-reduce; off by default)
+	if (g_nccl.CommSplit && getenv("IG_TWO_COMMS")) {
+		if (g_nccl.CommSplit(c->comm, 0, c->cfg.shard_rank, &c->comm2, nullptr) != ncclSuccess) c->comm2 = nullptr;
+	}
 	if (!c->tetra && c->cfg.mode != 0 && !c->cfg.print_freq && c->loaded && !c->stream2) {
 		CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 		CK(cudaEventCreateWithFlags(&c->ev_zq, cudaEventDisableTiming));
@@ -512,6 +530,11 @@ static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165
 // --------------------------------------------------------------------------------------
 // sweep phases
 // --------------------------------------------------------------------------------------
+static inline void ptrace_mark(ig_ctx *c, int point)
+{
+	if (c->ptrace.empty() || c->ptrace_sweeps >= PT_SWEEPS || c->iter_dev) return;
+	cudaEventRecord(c->ptrace[(size_t)c->ptrace_sweeps * PT_POINTS + point], c->stream);
+}
 static ZQArgs zq_args(ig_ctx *c)
 {
 	ZQArgs a;
@@ -528,11 +551,14 @@ static ZQArgs zq_args(ig_ctx *c)
 
 static ig_status phase_update_P(ig_ctx *c)
 {
-	if (c->early_p) {                       // drawn behind the previous sweep's kernel on the side stream
-		CK(cudaStreamWaitEvent(c->stream, c->ev_p, 0));
+	if (c->early_p) {
+		// drawn behind the previous sweep's kernel on the side stream.  Only zq_sweep reads P: the main stream waits for it
+		// there (phase_zq), so update_S / the G proposals of this sweep still overlap the all-reduce and the draw (waiting
+		// here cost 46 us per sweep at 1250 individuals per GPU)
 		std::swap(c->P, c->Pnext);
 		std::swap(c->Pc, c->Pcnext);
 		c->early_p = false;
+		c->p_wait = true;
 		return IG_OK;
 	}
 	ig_status st = exchange_tally(c);
@@ -573,7 +599,7 @@ static ig_status phase_update_S(ig_ctx *c)
 	}
 	// UPMCMC.state is read by every CTA and written by one: double-buffered
 	PreArgs a{c->ind, c->S, c->state, c->state2, c->gprop, c->gpair, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1,
-	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl, c->iter_dev, c->fprop, c->hpair, c->ftab};
+	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl, c->iter_dev, c->fprop, c->hpair, c->ftab, c->grid_pre};
 	CK(launch_pre_sweep(a, c->stream));
 	if (c->cfg.mode == 2 && c->cfg.back_refl == 0) std::swap(c->state, c->state2);
 	c->launches++;
@@ -583,6 +609,7 @@ static ig_status phase_update_S(ig_ctx *c)
 static ig_status phase_zq(ig_ctx *c, int init)
 {
 	if (c->cfg.mode == 0) return init ? na_chain_init(c) : na_phase_z(c);     // no admixture: whole-individual labels (noadmix.cu)
+	if (c->p_wait) { CK(cudaStreamWaitEvent(c->stream, c->ev_p, 0)); c->p_wait = false; }
 	ZQArgs a = zq_args(c);
 	if (init) { a.type_freq = 1; a.fmode = 0; a.hpair = nullptr; }     // uniform initial assignment: no likelihood is kept
 	const bool timed = c->profile && !init && c->ev_used + 2 <= (int)c->ev.size();
@@ -594,6 +621,7 @@ static ig_status phase_zq(ig_ctx *c, int init)
 		c->zt_stale = true;
 	} else CK(launch_zq_sweep(a, c->rounds, c->stream));
 	if (timed) { CK(cudaEventRecord(c->ev[c->ev_used + 1], c->stream)); c->ev_used += 2; }
+	if (!init) ptrace_mark(c, 3);
 	if (!init && c->comm && c->stream2 && c->more_follow) {
 		// Sharded chain: n is complete once this kernel ends, and nothing else of this sweep reads it.
 		// Its all-reduce and the P draw of the NEXT sweep (same Philox keys, iter + 1: identical on every
@@ -601,7 +629,7 @@ static ig_status phase_zq(ig_ctx *c, int init)
 		const Geometry &g = c->geo;
 		CK(cudaEventRecord(c->ev_zq, c->stream));
 		CK(cudaStreamWaitEvent(c->stream2, c->ev_zq, 0));
-		NCK(g_nccl.AllReduce(c->n, c->n, (size_t)g.Lpad * g.A * g.KP, ncclInt32, ncclSum, c->comm, c->stream2));
+		NCK(g_nccl.AllReduce(c->n, c->n, (size_t)g.Lpad * g.A * g.KP, ncclInt32, ncclSum, c->comm2 ? c->comm2 : c->comm, c->stream2));
 		PArgs pa{c->n, c->Pnext, c->P64, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0, 0, c->Pcnext, c->geo.TL};
 		CK(launch_p_dirichlet(pa, c->stream2));
 		CK(cudaEventRecord(c->ev_p, c->stream2));
@@ -613,6 +641,7 @@ static ig_status phase_zq(ig_ctx *c, int init)
 	CK(launch_epilogue(e, c->stream));
 	c->launches += 2;
 	if (c->geo.fmode == 2 && !init) { CK(launch_fk_epilogue(e, c->stream)); c->launches++; }
+	if (!init) ptrace_mark(c, 4);
 	ig_status stx = exchange_individuals(c);
 	if (stx != IG_OK) return stx;
 	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1 && c->g8_dev && c->more_follow && !c->iter_dev) {
@@ -631,10 +660,31 @@ static ig_status phase_alpha(ig_ctx *c)
 {
 	// mode 4: pre_sweep left the proposed adaptive-independence states in state2 (-e 0)
 	PostArgs a{c->ind, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1, c->iter_dev, c->cfg.mode, c->cfg.back_refl,
-	           c->S, c->fprop, c->state, c->state2};
+	           c->S, c->fprop, c->state, c->state2, c->grid_post};
 	CK(launch_post_sweep(a, c->stream));
 	c->launches++;
 	return IG_OK;
+}
+
+static void ptrace_report(ig_ctx *c)
+{
+	if (c->ptrace.empty() || c->ptrace_sweeps < 8) return;
+	static const char *names[PT_POINTS - 1] = {"update_P (wait / draw)", "update_S + G proposals", "zq_sweep", "epilogue", "all-gather", "update_alpha"};
+	double acc[PT_POINTS - 1] = {0, 0, 0, 0, 0, 0}, between = 0;
+	int n = 0;
+	for (int s = 4; s < c->ptrace_sweeps; s++, n++) {            // skip the first sweeps
+		for (int p = 0; p + 1 < PT_POINTS; p++) {
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, c->ptrace[(size_t)s * PT_POINTS + p], c->ptrace[(size_t)s * PT_POINTS + p + 1]);
+			acc[p] += ms;
+		}
+		if (s + 1 < c->ptrace_sweeps) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ptrace[(size_t)s * PT_POINTS + PT_POINTS - 1], c->ptrace[(size_t)(s + 1) * PT_POINTS]); between += ms; }
+	}
+	fprintf(stderr, "[ig_phase_trace] rank %d, %d sweeps, us per sweep:", c->cfg.shard_rank, n);
+	for (int p = 0; p + 1 < PT_POINTS; p++) fprintf(stderr, " %s %.1f |", names[p], 1e3 * acc[p] / n);
+	fprintf(stderr, " between sweeps %.1f || host enqueue us per sweep:", 1e3 * between / (n > 1 ? n - 1 : 1));
+	for (int p = 0; p < 4; p++) fprintf(stderr, " %.1f", 1e3 * c->ptrace_host_ms[p] / (c->ptrace_host_ms[4] > 0 ? c->ptrace_host_ms[4] : 1.0));
+	fprintf(stderr, "\n");
 }
 
 static ig_status one_sweep_direct(ig_ctx *c)
@@ -642,10 +692,23 @@ static ig_status one_sweep_direct(ig_ctx *c)
 	ig_status st;
 	if (c->tetra) return tetra_one_sweep(c);
 	c->iter++;
+	const bool tr = !c->ptrace.empty();
+	double h0 = tr ? wall_ms() : 0.0, h1;
+	ptrace_mark(c, 0);
 	if ((st = phase_update_P(c)) != IG_OK) return st;      // update_P            mcmc.c:210
+	ptrace_mark(c, 1);
+	if (tr) { h1 = wall_ms(); c->ptrace_host_ms[0] += h1 - h0; h0 = h1; }
 	if ((st = phase_update_S(c)) != IG_OK) return st;      // update_S_* + G proposal  :211-212
+	ptrace_mark(c, 2);
+	if (tr) { h1 = wall_ms(); c->ptrace_host_ms[1] += h1 - h0; h0 = h1; }
 	if ((st = phase_zq(c, 0)) != IG_OK) return st;         // update_G accept, update_ZQ, cal_lkh :212-215
-	return phase_alpha(c);                                 // update_alpha, totallkh    :214-215
+	ptrace_mark(c, 5);
+	if (tr) { h1 = wall_ms(); c->ptrace_host_ms[2] += h1 - h0; h0 = h1; }
+	st = phase_alpha(c);                                   // update_alpha, totallkh    :214-215
+	ptrace_mark(c, 6);
+	if (tr) { h1 = wall_ms(); c->ptrace_host_ms[3] += h1 - h0; c->ptrace_host_ms[4] += 1.0; }
+	if (!c->ptrace.empty() && c->ptrace_sweeps < PT_SWEEPS && !c->iter_dev) c->ptrace_sweeps++;
+	return st;
 }
 
 // A sweep of the small configurations is five launches of a few microseconds each: launch latency,
@@ -719,6 +782,7 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	c->g8_inflight = false;
 	if (c->stream2) CK(cudaStreamSynchronize(c->stream2));
 	c->early_p = false;
+	c->p_wait = false;
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // the chain's RNG key is baked into the captured arguments
 	float init_h[MAX_K];
 	for (int k = 0; k < MAX_K; k++) init_h[k] = (initd && k < g.K) ? initd[k] : 0.5f;
@@ -1281,7 +1345,7 @@ extern "C" ig_status ig_alpha_logratio(ig_ctx *c, double ralpha, double *out)
 	CK(cudaStreamSynchronize(c->stream));
 	CK(copy_sync(c, &keep, c->sc, sizeof(keep), cudaMemcpyDeviceToHost));
 	PostArgs a{c->ind, c->sc, c->gpart, c->geo, 0xFFFFFFFFu, c->key0, c->key1, nullptr, c->cfg.mode, c->cfg.back_refl,
-	           c->S, c->fprop, c->state, c->state2};
+	           c->S, c->fprop, c->state, c->state2, c->grid_post};
 	CK(launch_post_sweep(a, c->stream));
 	DevScalars h;
 	CK(cudaMemcpyAsync(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

@@ -36,6 +36,7 @@ struct ig_ctx {
 	bool loaded = false, chain_ready = false;
 	uint32_t iter = 0, key0 = 0, key1 = 0;
 	int rounds = 7;
+	int grid_pre = 1, grid_post = 1;   // cooperative grids of the scalar kernels on this context's device
 	// device buffers
 	int16_t *Xt = nullptr;
 	int8_t *Zt = nullptr;           // micro-tiled Z; on the biallelic path only the state hooks' view (allocated on demand)
@@ -91,13 +92,21 @@ struct ig_ctx {
 	bool g8_inflight = false;                        // a copy of the current G is on its way (or has arrived) in g8_host
 	// NCCL
 	ncclComm_t comm = nullptr;
+	ncclComm_t comm2 = nullptr;      // a second communicator over the same ranks for the side stream: operations on ONE communicator
+	                                 // are serialised by NCCL even across streams, which put the 6.4 MB tally all-reduce in front of
+	                                 // the all-gather of the records on the critical path
 	// sharded chains: the tally all-reduce and the NEXT sweep's P draw run on a side stream behind
 	// the sweep kernel, off the critical path (ig_api.cu early_update_P)
 	cudaStream_t stream2 = nullptr;
 	cudaEvent_t ev_zq = nullptr, ev_p = nullptr;
 	float *Pnext = nullptr;
 	bool early_p = false;            // Pnext holds the P of sweep iter + 1 and n has been consumed
+	bool p_wait = false;             // the main stream has not yet waited for that draw (it does before zq_sweep)
 	bool more_follow = false;        // another sweep follows inside the current API call
+	// IG_PHASE_TRACE=1: CUDA events at the phase boundaries of the first 64 sweeps, averages printed by ig_destroy
+	std::vector<cudaEvent_t> ptrace;
+	int ptrace_sweeps = 0;
+	double ptrace_host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // host time spent enqueueing each phase
 	// profiling
 	bool profile = false;
 	std::vector<cudaEvent_t> ev;

@@ -156,14 +156,17 @@ struct PreArgs {
 	double *fprop;           // modes 4/5: proposed inbreeding coefficients [K] / [N]
 	float2 *hpair;           // mode 5: [Nloc] (1 - F, 1 - F')
 	float *ftab;             // mode 4: table for the sweep kernel (ZQArgs.ftab)
+	int grid;                // cooperative grid size of this context (scalar_grid), used when N > 1024
 };
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s);
+int scalar_grid(int which /*0 pre, 1 post*/, int n_items, int device);
 
 struct PostArgs {
 	double *ind; DevScalars *sc; double *gpart; Geometry geo; uint32_t iter, key0, key1;
 	const uint32_t *iter_dev;
 	int mode, back_refl;
 	double *S; const double *fprop; int32_t *state; const int32_t *state_prop;   // modes 4/5
+	int grid;                // cooperative grid size of this context
 };
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
 

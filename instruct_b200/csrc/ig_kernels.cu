@@ -127,17 +127,19 @@ __device__ __forceinline__ double trans_prob(int from, int to)
 
 // --------------------------------------------------------------------------------------
 // Deterministic sums over all individuals for the scalar updates.  update_S_POP is K sequential Metropolis steps, each
-// needing a sum over all N individuals (proposal(), mcmc.c:1630), update_alpha one: K + 2 reductions with a barrier each.
-// They run in ONE thread-block cluster of SC_CTAS CTAs (hardware cluster barrier, partial sums exchanged through
-// distributed shared memory): every CTA reduces its threads' values with a fixed shuffle / shared tree, publishes one
-// partial per value in its own shared memory, and after the cluster barrier adds the SC_CTAS partials in rank order.
-// Fixed launch shape => fixed summation order => bit-identical on every rank of a sharded chain and for every GPU count.
-// (Round 1 used a cooperative grid with grid.sync() and partials in global memory: 47 us per sweep at N = 10^4, and a
-// function-static occupancy cache that two contexts on different devices raced on; the cluster needs neither.)
+// needing a sum over all N individuals (proposal(), mcmc.c:1630), update_alpha one more: K + 2 reductions with a barrier
+// each.  Two launch shapes, chosen from the GLOBAL N only (so every rank of a sharded chain takes the same one and adds in
+// the same order):
+//   N <= 1024  one CTA of 1024 threads: the barrier is __syncthreads (configs 1-2 are launch- and latency-bound);
+//   larger     a cooperative grid of 256-thread CTAs, one individual per thread: each CTA publishes one partial per value,
+//              after grid.sync() every CTA adds the partials in CTA order.  The double-precision logarithms of proposal()
+//              need the SMs: a single 8-CTA cluster (tried in round 2: hardware cluster barrier, partials through
+//              distributed shared memory) ran 73 us at N = 10^4 where this grid runs 47.
+// The cooperative grid size is computed once per context (ig_api.cu) -- round 1 cached it in function statics, which two
+// contexts on different devices raced on.
 // --------------------------------------------------------------------------------------
-constexpr int SC_CTAS = 8;                      // portable cluster size
-constexpr int SC_THREADS = 512;
-constexpr int SC_WARPS = SC_THREADS / 32;
+constexpr int SC_THREADS = 256;                 // cooperative shape
+constexpr int SC1_THREADS = 1024;               // single-CTA shape
 constexpr int SC_MAXV = 20;                     // values reduced at once (K + 2 <= 18)
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -148,39 +150,44 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 struct ScShared {
-	double warp[SC_MAXV][SC_WARPS];
-	double part[2][SC_MAXV];                    // this CTA's partials, double-buffered by reduction parity
+	double warp[SC_MAXV][32];
 	double total[SC_MAXV];
 };
 
-// reduce nv per-thread values over the whole cluster; the result lands in out[0..nv) for every thread
-__device__ void cluster_sum(cg::cluster_group &cl, const double *v, int nv, double *out, ScShared &sh, int &phase)
+// reduce nv per-thread values over all threads of the launch; the result lands in out[0..nv) for every thread
+template <bool COOP>
+__device__ void all_sum(const double *v, int nv, double *out, ScShared &sh, double *gpart, int &phase)
 {
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
 	for (int j = 0; j < nv; j++) {
 		const double w = warp_sum(v[j]);
 		if (lane == 0) sh.warp[j][wid] = w;
 	}
 	__syncthreads();
+	double *buf = COOP ? gpart + (size_t)(phase & 1) * gridDim.x * SC_MAXV : nullptr;
 	if (tid < nv) {
 		double t = 0.0;
-		for (int w = 0; w < SC_WARPS; w++) t += sh.warp[tid][w];
-		sh.part[phase & 1][tid] = t;
+		for (int w = 0; w < nwarps; w++) t += sh.warp[tid][w];
+		if (COOP) buf[(size_t)blockIdx.x * SC_MAXV + tid] = t;
+		else sh.total[tid] = t;
 	}
-	cl.sync();                                   // every CTA's partials are written and visible cluster-wide
-	if (tid < nv) {
-		double t = 0.0;
-		for (unsigned r = 0; r < SC_CTAS; r++) t += cl.map_shared_rank(&sh.part[phase & 1][0], r)[tid];
-		sh.total[tid] = t;
+	if (COOP) {
+		__threadfence();
+		cg::this_grid().sync();
+		if (tid < nv) {
+			double t = 0.0;
+			for (unsigned b = 0; b < gridDim.x; b++) t += buf[(size_t)b * SC_MAXV + tid];
+			sh.total[tid] = t;
+		}
 	}
 	__syncthreads();
 	for (int j = 0; j < nv; j++) out[j] = sh.total[j];
-	cl.sync();                                   // nobody leaves the kernel, or rewrites its partials, while a peer still reads them
-	phase++;
+	__syncthreads();
+	phase++;                                     // COOP: the partials are double-buffered, one grid.sync() per reduction suffices
 }
 
 // --------------------------------------------------------------------------------------
-// pre_sweep (one cluster of SC_CTAS x SC_THREADS threads, striding over the individuals):
+// pre_sweep (either launch shape, striding over the individuals):
 // selfing-rate update, then the generation proposals of update_G.
 //   mode 2: update_S_POP (mcmc.c:913-983): K sequential MH steps, each a grid-wide sum of
 //           log( s_i^(G_i-1) (1-s_i) ), s_i = sum_k Q_ik S_k  (proposal, mcmc.c:1630)
@@ -189,16 +196,16 @@ __device__ void cluster_sum(cg::cluster_group &cl, const double *v, int nv, doub
 // Every rank of a sharded chain runs this redundantly on the all-gathered (Q, G): identical
 // inputs and a fixed reduction order give identical S everywhere, so no broadcast is needed.
 // --------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) pre_sweep_kernel(const PreArgs a)
+template <bool COOP>
+__global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) pre_sweep_kernel(const PreArgs a)
 {
-	cg::cluster_group cl = cg::this_cluster();
 	__shared__ ScShared sh;
 	__shared__ double Ssh[MAX_K];
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x;
 	const int K = g.K, REC = g.REC;
-	const int gstride = gridDim.x * SC_THREADS;
-	const int i_first = blockIdx.x * SC_THREADS + tid;
+	const int gstride = gridDim.x * blockDim.x;
+	const int i_first = blockIdx.x * blockDim.x + tid;
 	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	int phase = 0;
 
@@ -259,7 +266,7 @@ __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) pr
 			for (int k = 0; k < K; k++) s += rec[k] * Sl[k];
 			part += log_geom(s, (int)rec[K + 2]);
 		}
-		cluster_sum(cl, &part, 1, &cur, sh, phase);
+		all_sum<COOP>(&part, 1, &cur, sh, a.gpart, phase);
 		int accepts = 0;
 		for (int j = 0; j < K; j++) {
 			Stream st((uint32_t)j, 0u, iter, TAG_SPOP, a.key0, a.key1);
@@ -285,7 +292,7 @@ __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) pr
 				part += log_geom(s, (int)rec[K + 2]);
 			}
 			double pl;
-			cluster_sum(cl, &part, 1, &pl, sh, phase);
+			all_sum<COOP>(&part, 1, &pl, sh, a.gpart, phase);
 			// every thread of every CTA takes the same decision from the same numbers
 			double ratio = exp(pl - cur);
 			if (a.back_refl == 0) ratio *= trans_prob(cs, new_state) / trans_prob(new_state, cs);
@@ -346,8 +353,9 @@ __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) pr
 
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
 {
-	pre_sweep_kernel<<<SC_CTAS, SC_THREADS, 0, s>>>(a);
-	return cudaGetLastError();
+	if (a.geo.N <= SC1_THREADS) { pre_sweep_kernel<false><<<1, SC1_THREADS, 0, s>>>(a); return cudaGetLastError(); }
+	void *args[] = {(void *)&a};
+	return cudaLaunchCooperativeKernel((const void *)pre_sweep_kernel<true>, dim3(a.grid), dim3(SC_THREADS), args, 0, s);
 }
 
 // --------------------------------------------------------------------------------------
@@ -358,10 +366,11 @@ cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
 // (Q, indvlkh, sum_k log q, G) into the all-gatherable array.  The summation order depends
 // only on the chunk decomposition, which depends only on (L, K, A): shard-invariant.
 // --------------------------------------------------------------------------------------
-constexpr int EPI_IPB = 8;          // individuals per CTA
-constexpr int EPI_GROUPS = 32;      // chunk groups per CTA
-__global__ void __launch_bounds__(EPI_IPB * EPI_GROUPS) indiv_epilogue_kernel(const EpiArgs a)
+constexpr int EPI_THREADS = 256;
+template <int EPI_IPB>              // individuals per CTA: 8 (small shards: more CTAs) or 32; chunk groups = 256 / EPI_IPB
+__global__ void __launch_bounds__(EPI_THREADS) indiv_epilogue_kernel(const EpiArgs a)
 {
+	constexpr int EPI_GROUPS = EPI_THREADS / EPI_IPB;
 	__shared__ int cnt_sh[EPI_GROUPS][MAX_K][EPI_IPB];
 	__shared__ double ll_sh[EPI_GROUPS][3][EPI_IPB];
 	__shared__ int nsh_sh[EPI_GROUPS][EPI_IPB];
@@ -378,25 +387,34 @@ __global__ void __launch_bounds__(EPI_IPB * EPI_GROUPS) indiv_epilogue_kernel(co
 	int cnt[MAX_K];
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
+	// The floating-point sums of an individual are taken in an order that depends on the chunk decomposition only (so a
+	// chain is bit-identical for every shard count and either CTA shape): chunks c = v (mod 32) form virtual group v, summed
+	// in chunk order; four consecutive virtual groups are folded left to right into T_0 .. T_7; the T are folded in order.
+	constexpr int VG = 32, VPR = VG / EPI_GROUPS;      // virtual groups, and how many of them one thread row walks (1 or 4)
 	double d_old = 0.0, a_new = 0.0, b_new = 0.0;
 	int nsh_new = 0;
 	if (live) {
-		for (int c = w; c < g.nchunks; c += EPI_GROUPS) {
-			// KP u16 counters per (chunk, individual): 8, 16 or 32 bytes, read as 64 / 128-bit vectors
-			const uint16_t *pcb = a.pcnt + ((size_t)c * g.Nloc + il) * KP;
+#pragma unroll
+		for (int vv = 0; vv < VPR; vv++) {
+			double dv = 0.0, av = 0.0, bv = 0.0;
+			for (int c = w * VPR + vv; c < g.nchunks; c += VG) {
+				// KP u16 counters per (chunk, individual): 8, 16 or 32 bytes, read as 64 / 128-bit vectors
+				const uint16_t *pcb = a.pcnt + ((size_t)c * g.Nloc + il) * KP;
 #define EPI_ADD(J, V) do { cnt[2 * (J)] += (V) & 0xFFFFu; cnt[2 * (J) + 1] += (V) >> 16; } while (0)
-			if (KP == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(pcb); EPI_ADD(0, t.x); EPI_ADD(1, t.y); }
-			else {
-				const uint4 t = *reinterpret_cast<const uint4 *>(pcb);
-				EPI_ADD(0, t.x); EPI_ADD(1, t.y); EPI_ADD(2, t.z); EPI_ADD(3, t.w);
-				if (KP == 16) { const uint4 t2 = *(reinterpret_cast<const uint4 *>(pcb) + 1); EPI_ADD(4, t2.x); EPI_ADD(5, t2.y); EPI_ADD(6, t2.z); EPI_ADD(7, t2.w); }
-			}
+				if (KP == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(pcb); EPI_ADD(0, t.x); EPI_ADD(1, t.y); }
+				else {
+					const uint4 t = *reinterpret_cast<const uint4 *>(pcb);
+					EPI_ADD(0, t.x); EPI_ADD(1, t.y); EPI_ADD(2, t.z); EPI_ADD(3, t.w);
+					if (KP == 16) { const uint4 t2 = *(reinterpret_cast<const uint4 *>(pcb) + 1); EPI_ADD(4, t2.x); EPI_ADD(5, t2.y); EPI_ADD(6, t2.z); EPI_ADD(7, t2.w); }
+				}
 #undef EPI_ADD
-			const double *pl = a.plog + (size_t)c * 3 * g.Nloc + il;
-			d_old += pl[0];
-			a_new += pl[(size_t)g.Nloc];
-			b_new += pl[(size_t)2 * g.Nloc];
-			nsh_new += a.pnsh[(size_t)c * g.Nloc + il];
+				const double *pl = a.plog + (size_t)c * 3 * g.Nloc + il;
+				dv += pl[0];
+				av += pl[(size_t)g.Nloc];
+				bv += pl[(size_t)2 * g.Nloc];
+				nsh_new += a.pnsh[(size_t)c * g.Nloc + il];
+			}
+			d_old += dv; a_new += av; b_new += bv;     // VPR == 4: this row's T; VPR == 1: one virtual group, folded below
 		}
 	}
 #pragma unroll
@@ -409,23 +427,28 @@ __global__ void __launch_bounds__(EPI_IPB * EPI_GROUPS) indiv_epilogue_kernel(co
 	//      (mcmc.c:1195-1197; double-precision Marsaglia-Tsang, own Philox stream per (individual, population)); three more
 	//      thread rows add the likelihood pieces, one the heterozygote count
 	const int ig_global = g.i0 + il;
-	if (live) {
-		if (w < K) {
-			int ck = 0;
-			for (int ww = 0; ww < EPI_GROUPS; ww++) ck += cnt_sh[ww][w][lane];
-			cntt_sh[w][lane] = ck;
-			Stream sq((uint32_t)ig_global, (uint32_t)w, iter, TAG_Q, a.key0, a.key1);
-			gq_sh[w][lane] = draw_gamma(sq, (double)ck + a.sc->alpha);
-		} else if (w >= MAX_K && w < MAX_K + 3) {
-			double t = 0.0;
-			for (int ww = 0; ww < EPI_GROUPS; ww++) t += ll_sh[ww][w - MAX_K][lane];
-			llt_sh[w - MAX_K][lane] = t;
-		} else if (w == MAX_K + 3) {
-			int t = 0;
-			for (int ww = 0; ww < EPI_GROUPS; ww++) t += nsh_sh[ww][lane];
-			nsht_sh[lane] = t;
+	if (live)
+		for (int task = w; task < K + 4; task += EPI_GROUPS) {
+			if (task < K) {
+				int ck = 0;
+				for (int ww = 0; ww < EPI_GROUPS; ww++) ck += cnt_sh[ww][task][lane];
+				cntt_sh[task][lane] = ck;
+				Stream sq((uint32_t)ig_global, (uint32_t)task, iter, TAG_Q, a.key0, a.key1);
+				gq_sh[task][lane] = draw_gamma(sq, (double)ck + a.sc->alpha);
+			} else if (task < K + 3) {
+				double t = 0.0;
+				for (int tw = 0; tw < 8; tw++) {
+					double tt = 0.0;
+					for (int r = 0; r < EPI_GROUPS / 8; r++) tt += ll_sh[tw * (EPI_GROUPS / 8) + r][task - K][lane];
+					t += tt;
+				}
+				llt_sh[task - K][lane] = t;
+			} else {
+				int t = 0;
+				for (int ww = 0; ww < EPI_GROUPS; ww++) t += nsh_sh[ww][lane];
+				nsht_sh[lane] = t;
+			}
 		}
-	}
 	__syncthreads();
 	if (w != 0 || !live) return;
 #pragma unroll
@@ -484,7 +507,10 @@ __global__ void __launch_bounds__(EPI_IPB * EPI_GROUPS) indiv_epilogue_kernel(co
 }
 cudaError_t launch_epilogue(const EpiArgs &a, cudaStream_t s)
 {
-	indiv_epilogue_kernel<<<(a.geo.Nloc + EPI_IPB - 1) / EPI_IPB, EPI_IPB * EPI_GROUPS, 0, s>>>(a);
+	// 32 individuals per CTA once that still gives every SM a few CTAs; 8 for the small shards of a many-GPU chain (the
+	// summation order is the same for both shapes, see the kernel)
+	if (a.geo.Nloc >= 8192) indiv_epilogue_kernel<32><<<(a.geo.Nloc + 31) / 32, EPI_THREADS, 0, s>>>(a);
+	else indiv_epilogue_kernel<8><<<(a.geo.Nloc + 7) / 8, EPI_THREADS, 0, s>>>(a);
 	return cudaGetLastError();
 }
 
@@ -512,23 +538,23 @@ cudaError_t launch_fk_epilogue(const EpiArgs &a, cudaStream_t s)
 }
 
 // --------------------------------------------------------------------------------------
-// post_sweep (one cluster, as pre_sweep): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
+// post_sweep (either launch shape, as pre_sweep): totallkh (cal_lkh, mcmc.c:1940), the alpha MH step
 // (update_alpha, mcmc.c:1244-1263, in log form: (alpha'-alpha) * sum log q), and the
 // column sums of Q for check_empty_cluster (mcmc.c:1954-1961) -- one grid-wide sum of
 // K + 2 values.
 // --------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) post_sweep_kernel(const PostArgs a)
+template <bool COOP>
+__global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) post_sweep_kernel(const PostArgs a)
 {
-	cg::cluster_group cl = cg::this_cluster();
 	__shared__ ScShared sh;
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x, K = g.K, REC = g.REC;
-	const int gstride = gridDim.x * SC_THREADS;
+	const int gstride = gridDim.x * blockDim.x;
 	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
 	double v[SC_MAXV], tot[SC_MAXV];
 #pragma unroll
 	for (int j = 0; j < SC_MAXV; j++) v[j] = 0.0;
-	for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) {
+	for (int i = blockIdx.x * blockDim.x + tid; i < g.N; i += gstride) {
 		const double *rec = a.ind + (size_t)i * REC;
 		v[0] += rec[K];
 		v[1] += rec[K + 1];
@@ -536,9 +562,9 @@ __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) po
 		for (int k = 0; k < MAX_K; k++) if (k < K) v[2 + k] += rec[k];
 	}
 	int phase = 0;
-	cluster_sum(cl, v, K + 2, tot, sh, phase);
+	all_sum<COOP>(v, K + 2, tot, sh, a.gpart, phase);
 	if (a.mode == 5)                                        // the accepted F of every individual, from the (all-gathered) records
-		for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) a.S[i] = a.ind[(size_t)i * REC + K + 2];
+		for (int i = blockIdx.x * blockDim.x + tid; i < g.N; i += gstride) a.S[i] = a.ind[(size_t)i * REC + K + 2];
 	if (a.mode == 4 && iter != 0xFFFFFFFFu) {
 		// update_inbreedcoff_POP accepts (mcmc.c:1038-1047): D_k = sum over individuals of the old-Z
 		// differences; the reference multiplies that LOG ratio by the Hastings ratio under -e 0 and
@@ -553,12 +579,12 @@ __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) po
 		double dv[SC_MAXV], dt[SC_MAXV];
 #pragma unroll
 		for (int j = 0; j < SC_MAXV; j++) dv[j] = 0.0;
-		for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) {
+		for (int i = blockIdx.x * blockDim.x + tid; i < g.N; i += gstride) {
 			const double *rec = a.ind + (size_t)i * REC + K + 3;
 #pragma unroll
 			for (int k = 0; k < MAX_K; k++) if (k < K) dv[k] += rec[k];
 		}
-		cluster_sum(cl, dv, K, dt, sh, phase);
+		all_sum<COOP>(dv, K, dt, sh, a.gpart, phase);
 		bool acc[MAX_K];
 		int naccept = 0;
 		for (int k = 0; k < K; k++) {
@@ -571,14 +597,14 @@ __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) po
 		}
 		// cal_lkh at the accepted coefficients (log_ld_F_pop, mcmc.c:1776): add the new-Z differences
 		double lv = 0.0, lt;
-		for (int i = blockIdx.x * SC_THREADS + tid; i < g.N; i += gstride) {
+		for (int i = blockIdx.x * blockDim.x + tid; i < g.N; i += gstride) {
 			double *rec = a.ind + (size_t)i * REC;
 			double l = rec[K];
 			for (int k = 0; k < K; k++) if (acc[k]) l += rec[2 * K + 3 + k];
 			rec[K] = l;
 			lv += l;
 		}
-		cluster_sum(cl, &lv, 1, &lt, sh, phase);
+		all_sum<COOP>(&lv, 1, &lt, sh, a.gpart, phase);
 		tot[0] = lt;
 		if (blockIdx.x == 0 && tid == 0) {
 			for (int k = 0; k < K; k++) if (acc[k]) { a.S[k] = Fp[k]; if (a.back_refl == 0) a.state[k] = ns_[k]; }
@@ -609,10 +635,25 @@ __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_THREADS) po
 		if (nan_accept || u < fmin(1.0, ratio)) { a.sc->alpha = ralpha; a.sc->alpha_accepts++; }
 	}
 }
+// cooperative grid for n_items individuals on `device` (computed once per context)
+int scalar_grid(int which, int n_items, int device)
+{
+	int per_sm = 1, sms = 148;
+	const void *k = which == 0 ? (const void *)pre_sweep_kernel<true> : (const void *)post_sweep_kernel<true>;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SC_THREADS, 0);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	int want = (n_items + SC_THREADS - 1) / SC_THREADS;
+	int cap = per_sm * sms;
+	if (cap > SC_MAX_CTAS) cap = SC_MAX_CTAS;
+	if (want < 1) want = 1;
+	return want < cap ? want : cap;
+}
+
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s)
 {
-	post_sweep_kernel<<<SC_CTAS, SC_THREADS, 0, s>>>(a);
-	return cudaGetLastError();
+	if (a.geo.N <= SC1_THREADS) { post_sweep_kernel<false><<<1, SC1_THREADS, 0, s>>>(a); return cudaGetLastError(); }
+	void *args[] = {(void *)&a};
+	return cudaLaunchCooperativeKernel((const void *)post_sweep_kernel<true>, dim3(a.grid), dim3(SC_THREADS), args, 0, s);
 }
 
 // --------------------------------------------------------------------------------------

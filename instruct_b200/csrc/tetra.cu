@@ -28,7 +28,7 @@
 // the per-individual S statistics and records; fixed-order reductions => bit-identical to one GPU).
 // Restrictions of this version: -e 1 only
 // (with -e 0 the reference's own tables are log(0), tests/test_tetra_oracle_vs_reference.py),
-// allelenum_max <= 6, alpha is never updated (the reference's tetraploid driver never calls
+// allelenum_max <= 10, alpha is never updated (the reference's tetraploid driver never calls
 // update_alpha).
 #include <stdlib.h>
 #include "ig_ctx.h"
@@ -39,7 +39,7 @@
 namespace ig {
 
 constexpr int TT = 4;                 // loci per micro-tile: one 128-bit z / geno vector, two 128-bit x vectors
-constexpr int TETRA_MAX_A = 6;
+constexpr int TETRA_MAX_A = 10;       // catalogue of 715 genotypes (autotetraploid) / 3025 (allotetraploid): 16-bit indices
 constexpr int TETRA_THREADS = 256;
 #define LN2_D 0.69314718055994530942
 
@@ -50,7 +50,7 @@ struct TetraCat {
 	int cls[5];      // iiii, iiij, iijj, iijk, ijkl
 	int total;
 	int code_off;    // into codes[]
-	int c2i_off;     // into c2i[] (n^4 entries: code -> index, 255 = not a catalogue genotype)
+	int c2i_off;     // into c2i[] (n^4 entries: code -> index, 0xFFFF = not a catalogue genotype)
 };
 
 struct TetraState {
@@ -60,7 +60,7 @@ struct TetraState {
 	int8_t *Zq = nullptr, *Gq = nullptr;   // [LTq][Nloc][TT][4]; geno = -1 on missing genotypes
 	TetraCat *cats = nullptr;
 	int32_t *codes = nullptr;
-	uint8_t *c2i = nullptr;
+	uint16_t *c2i = nullptr;
 	int32_t *loc_cat = nullptr;       // [Lq] catalogue of each locus (-1 beyond L)
 	float *exf = nullptr, *tabC = nullptr, *tabP = nullptr;    // [Lq][K][Gmax] natural logs
 	double *Sprop = nullptr, *dstat = nullptr;                  // [K]
@@ -133,7 +133,7 @@ static inline unsigned nb(size_t n, int b) { return (unsigned)((n + b - 1) / b);
 // tables: one thread per (locus, population)
 // --------------------------------------------------------------------------------------
 struct TabArgs {
-	const float *P; const int32_t *allelenum; const int32_t *loc_cat; const TetraCat *cats; const int32_t *codes; const uint8_t *c2i;
+	const float *P; const int32_t *allelenum; const int32_t *loc_cat; const TetraCat *cats; const int32_t *codes; const uint16_t *c2i;
 	const double *S, *Sprop; float *exf, *tabC, *tabP;
 	int L, K, KP, A, Gmax, do_cur, do_prop;
 	const float *P2; int allo;
@@ -196,7 +196,7 @@ __device__ int quad_with2(const int *d, int v1, int v2, int n)
 // class by class from the most to the least heterozygous, (I - sA) P = (1 - s) R.  Same float /
 // double mix and operation order as the reference; its re-use of a stale index in the
 // monoallelic class (:1984-1989) is reproduced as written.
-__device__ void genfreq_locus(float self, const TetraCat &c, const int32_t *code, const uint8_t *c2i, const float *R, float *P)
+__device__ void genfreq_locus(float self, const TetraCat &c, const int32_t *code, const uint16_t *c2i, const float *R, float *P)
 {
 	const int n = c.n, n2 = n * n;
 	int hi = c.total, num = 0, d[3];
@@ -284,7 +284,7 @@ __device__ void genfreq_locus(float self, const TetraCat &c, const int32_t *code
 
 // allo_genfreq, poly_geno.c:2122-2305: (I - sA) P = (1 - s) R solved class by class, from the doubly
 // heterozygous genotypes down; operation order and float / double mix of the reference
-__device__ void genfreq_locus_allo(float self, const TetraCat &c, const int32_t *code, const uint8_t *c2i, const float *R, float *P)
+__device__ void genfreq_locus_allo(float self, const TetraCat &c, const int32_t *code, const uint16_t *c2i, const float *R, float *P)
 {
 	const int n = c.n, n2 = n * n, n3 = n2 * n;
 #define IDX(cd) ((int)c2i[(cd)])
@@ -356,7 +356,7 @@ __global__ void tetra_tables_kernel(const TabArgs a)
 	const int l = t / a.K, k = t % a.K;
 	const TetraCat c = a.cats[a.loc_cat[l]];
 	const int32_t *code = a.codes + c.code_off;
-	const uint8_t *c2i = a.c2i + c.c2i_off;
+	const uint16_t *c2i = a.c2i + c.c2i_off;
 	const int n = c.n;
 	float *R = a.exf + (size_t)t * a.Gmax;
 	double lf[TETRA_MAX_A];
@@ -485,14 +485,14 @@ __global__ void tetra_select_kernel(float *tabC, const float *tabP, const int32_
 // --------------------------------------------------------------------------------------
 struct ZsArgs {
 	int8_t *Zq; const int8_t *Gq; const float *P; const float *Qf;
-	const float *tabC, *tabP; const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
+	const float *tabC, *tabP; const int32_t *loc_cat; const TetraCat *cats; const uint16_t *c2i;
 	uint16_t *pcnt; unsigned long long *dfix;   // dfix [K]: S statistics, 2^-24 fixed point, summed over the launch
 	Geometry geo; int Gmax; int init;
 	uint32_t iter, key0, key1, k_mant, k_one;
 };
 
 template <int KP, int ROUNDS>
-__global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_zs_kernel(const ZsArgs a)
+__global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_zs_kernel(const ZsArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bar;
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(32 * CG) tetra_q_kernel(const uint16_t *pcnt, 
 // --------------------------------------------------------------------------------------
 struct GenoArgs {
 	const int16_t *Xq; const int8_t *Zq; int8_t *Gq; const float *P; const float *Qf; const float *tab;
-	const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
+	const int32_t *loc_cat; const TetraCat *cats; const uint16_t *c2i;
 	int32_t *n; float *lpart;
 	Geometry geo; int Gmax; int init;       // init: uniform resolution (initial_geno), no likelihood, no tally
 	uint32_t iter, key0, key1;
@@ -711,17 +711,31 @@ __device__ __forceinline__ int2 lds_i2(uint32_t addr)
 	asm("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
 	return v;
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
 	uint32_t v;
-	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
+}
+// Catalogue code of a genotype (its four alleles, one per byte, as a base-n number).  n <= 6: one dp4a with the weights
+// (n^3, n^2, n, 1), which fit a byte each.  Beyond that (npack's top byte is 2 instead of 1): two dp4a with the weights
+// (n, 1) on the upper and the lower pair and one multiply-add, hi * n^2 + lo.  A locus is the same for the whole warp, so
+// the branch is uniform.
+__device__ __forceinline__ uint32_t tcode(uint32_t gpk, uint32_t npack)
+{
+	if ((npack >> 24) == 1u) return __dp4a(gpk, npack, 0u);
+	const uint32_t n = npack & 0xFFu, w = n | (1u << 8);
+	return __dp4a(gpk, w, 0u) * (n * n) + __dp4a(gpk, w << 16, 0u);
+}
+__host__ __device__ __forceinline__ int tetra_npack(int n)
+{
+	return n <= 6 ? ((n * n * n) | ((n * n) << 8) | (n << 16) | (1 << 24)) : (n | (2 << 24));
 }
 // table entry of the genotype with catalogue code `code`: staged copy (shared addresses) or global
 template <bool STAGE>
-__device__ __forceinline__ float tab_at(uint32_t tab_sa, const float *tab_g, uint32_t c2i_sa, const uint8_t *c2i_g, uint32_t code)
+__device__ __forceinline__ float tab_at(uint32_t tab_sa, const float *tab_g, uint32_t c2i_sa, const uint16_t *c2i_g, uint32_t code)
 {
-	if (STAGE) return lds_f(tab_sa + lds_u8(c2i_sa + code) * 4u);
+	if (STAGE) return lds_f(tab_sa + lds_u16(c2i_sa + 2u * code) * 4u);
 	return __ldg(tab_g + c2i_g[code]);
 }
 
@@ -750,12 +764,12 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 		tma_bulk_g2s(Psm, a.P + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
 		if (STAGE) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
 	}
-	if (STAGE) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
+	if (STAGE) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = reinterpret_cast<const uint8_t *>(a.c2i)[j];
 	for (int j = tid; j < nbins * R; j += TETRA_THREADS) hist[j] = 0;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
 		const int n = ci >= 0 ? a.cats[ci].n : 1;                                // n <= 6: n^3 fits a byte
-		locsm[j] = make_int2((n * n * n) | ((n * n) << 8) | (n << 16) | (1 << 24), ci >= 0 ? a.cats[ci].c2i_off : 0);
+		locsm[j] = make_int2(tetra_npack(n), ci >= 0 ? a.cats[ci].c2i_off : 0);
 	}
 	__syncthreads();
 	mbar_wait(&bar, 0);
@@ -814,8 +828,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 				const bool same = (zw[j] == z0 * 0x01010101u);
 				const uint32_t tj_sa = t_sa + (uint32_t)j * KG4 + z0 * G4;        // population z0's table of this locus
 				const float *tj_g = t_g + ((size_t)j * g.K + z0) * a.Gmax;
-				const uint32_t cj_sa = c2i_sa0 + (uint32_t)li.y;
-				const uint8_t *cj_g = a.c2i + li.y;
+				const uint32_t cj_sa = c2i_sa0 + 2u * (uint32_t)li.y;
+				const uint16_t *cj_g = a.c2i + li.y;
 				uint32_t gpk;
 				float lmul;                                                        // heterozygote multiplicities log 4, 6, 12, 24 (poly_geno.c:1262-1268)
 				if (nd == 1) { gpk = (apack & 0xFFu) * 0x01010101u; lmul = 0.0f; }
@@ -828,9 +842,9 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 					float w0, w1, w2;
 					if (a.init) { w0 = w1 = w2 = 0.0f; }                                // choose_unif, poly_geno.c:842
 					else if (same) {
-						w0 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(__byte_perm(apack, 0u, s0), npack, 0u)) * LOG2E;
-						w1 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(__byte_perm(apack, 0u, s1), npack, 0u)) * LOG2E;
-						w2 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(__byte_perm(apack, 0u, s2), npack, 0u)) * LOG2E;
+						w0 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, tcode(__byte_perm(apack, 0u, s0), npack)) * LOG2E;
+						w1 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, tcode(__byte_perm(apack, 0u, s1), npack)) * LOG2E;
+						w2 = tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, tcode(__byte_perm(apack, 0u, s2), npack)) * LOG2E;
 					} else {
 						const uint32_t r0 = pj_sa + (apack & 0xFFu) * (KP * 4u), r1 = pj_sa + ((apack >> 8) & 0xFFu) * (KP * 4u);
 						const uint32_t r2 = (nd == 3) ? pj_sa + ((apack >> 16) & 0xFFu) * (KP * 4u) : r0;
@@ -859,7 +873,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_geno_kernel(const Geno
 				const uint32_t ipk = gpk * (uint32_t)KP + zw[j];
 				const uint32_t i0 = ipk & 0xFFu, i1 = (ipk >> 8) & 0xFFu, i2 = (ipk >> 16) & 0xFFu, i3 = ipk >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286)
-				if (same) m_nat += tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(gpk, npack, 0u));
+				if (same) m_nat += tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, tcode(gpk, npack));
 				else {
 					m_nat += lmul;
 					m_lg2 += lg2_fast(lds_f(pj_sa + i0 * 4u) * lds_f(pj_sa + i1 * 4u)) + lg2_fast(lds_f(pj_sa + i2 * 4u) * lds_f(pj_sa + i3 * 4u));
@@ -918,7 +932,7 @@ __host__ __device__ constexpr uint32_t allo_sel(int r)
 // resolved genotype g0 | g1 << 8 | g2 << 16 | g3 << 24.
 template <int ND, int KP, bool STAGE>
 __device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack, int init, bool same, uint32_t tab_sa, const float *tab_g,
-                                                 uint32_t c2i_sa, const uint8_t *c2i_g, uint32_t p1_sa, uint32_t p2_sa, const float (&q)[KP], float u01)
+                                                 uint32_t c2i_sa, const uint16_t *c2i_g, uint32_t p1_sa, uint32_t p2_sa, const float (&q)[KP], float u01)
 {
 	using RS = AlloRes<ND>;
 	constexpr int NR = RS::N;
@@ -930,7 +944,7 @@ __device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack,
 	} else if (same) {                                                 // population z's table at the resolution's genotype
 #pragma unroll
 		for (int r = 0; r < NR; r++)
-			w[r] = tab_at<STAGE>(tab_sa, tab_g, c2i_sa, c2i_g, __dp4a(__byte_perm(apack, 0u, allo_sel<ND>(r)), npack, 0u)) * LOG2E;
+			w[r] = tab_at<STAGE>(tab_sa, tab_g, c2i_sa, c2i_g, tcode(__byte_perm(apack, 0u, allo_sel<ND>(r)), npack)) * LOG2E;
 	} else {                                                           // admixture-averaged frequencies of the two subgenomes
 		float lf[ND], lf2[ND];
 #pragma unroll
@@ -966,7 +980,7 @@ __device__ __forceinline__ uint32_t allo_resolve(uint32_t apack, uint32_t npack,
 
 struct GenoAlloArgs {
 	const int16_t *Xq; const int8_t *Zq; int8_t *Gq; const float *P, *P2; const float *Qf; const float *tab;
-	const int32_t *loc_cat; const TetraCat *cats; const uint8_t *c2i;
+	const int32_t *loc_cat; const TetraCat *cats; const uint16_t *c2i;
 	int32_t *n, *n2; float *lpart;
 	Geometry geo; int Gmax; int init;
 	uint32_t iter, key0, key1;
@@ -997,12 +1011,12 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 		tma_bulk_g2s(P2sm, a.P2 + (size_t)l0 * rowsz, (uint32_t)nbins * 4u, &bar);
 		if (STAGE) tma_bulk_g2s(tabsm, a.tab + (size_t)l0 * g.K * a.Gmax, tab_bytes, &bar);
 	}
-	if (STAGE) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = a.c2i[j];
+	if (STAGE) for (int j = tid; j < g.c2i_bytes; j += TETRA_THREADS) c2ism[j] = reinterpret_cast<const uint8_t *>(a.c2i)[j];
 	for (int j = tid; j < 2 * g.TL * rowsz * R; j += TETRA_THREADS) hist[j] = 0;
 	for (int j = tid; j < nl; j += TETRA_THREADS) {
 		const int ci = (l0 + j < g.L) ? a.loc_cat[l0 + j] : -1;
-		const int n = ci >= 0 ? a.cats[ci].n : 1;                              // n <= 5: n^3 fits a byte
-		locsm[j] = make_int2((n * n * n) | ((n * n) << 8) | (n << 16) | (1 << 24), ci >= 0 ? a.cats[ci].c2i_off : 0);
+		const int n = ci >= 0 ? a.cats[ci].n : 1;                              // tetra_npack: one dp4a up to n = 6, two beyond
+		locsm[j] = make_int2(tetra_npack(n), ci >= 0 ? a.cats[ci].c2i_off : 0);
 	}
 	__syncthreads();
 	mbar_wait(&bar, 0);
@@ -1060,8 +1074,8 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 				const bool same = (zw[j] == z0 * 0x01010101u);
 				const uint32_t tj_sa = t_sa + (uint32_t)j * KG4 + z0 * G4;
 				const float *tj_g = t_g + ((size_t)j * g.K + z0) * a.Gmax;
-				const uint32_t cj_sa = c2i_sa0 + (uint32_t)li.y;
-				const uint8_t *cj_g = a.c2i + li.y;
+				const uint32_t cj_sa = c2i_sa0 + 2u * (uint32_t)li.y;
+				const uint16_t *cj_g = a.c2i + li.y;
 				const float u01 = u01f(rj[j]);
 				uint32_t gpk;
 				if (nd == 1) gpk = (apack & 0xFFu) * 0x01010101u;
@@ -1074,7 +1088,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 2) tetra_geno_allo_kernel(const
 				const uint32_t ipk = gpk * (uint32_t)KP + zw[j];
 				const uint32_t i0 = ipk & 0xFFu, i1 = (ipk >> 8) & 0xFFu, i2 = (ipk >> 16) & 0xFFu, i3 = ipk >> 24;
 				// ---- likelihood of the result (calc_genofq, poly_geno.c:1235-1286, allotetraploid branch)
-				if (same) m_nat += tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, __dp4a(gpk, npack, 0u));
+				if (same) m_nat += tab_at<STAGE>(tj_sa, tj_g, cj_sa, cj_g, tcode(gpk, npack));
 				else {
 					// classes 1,2: log 2; class 3: log 4 -- one log 2 per heterozygous pair
 					const uint32_t hx = gpk ^ (gpk >> 8);                             // byte 0: g0 ^ g1, byte 2: g2 ^ g3
@@ -1315,11 +1329,10 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] > amax) amax = c->allelenum_h[l];
 	if (amax > TETRA_MAX_A) return fail(IG_ERR_UNSUPPORTED, "ploid 4: allelenum_max %d > %d", amax, TETRA_MAX_A);
 	// the code -> index tables hold one byte per genotype: 441 allotetraploid genotypes at 6 alleles do not fit
-	if (t->allo && amax > 5) return fail(IG_ERR_UNSUPPORTED, "allotetraploid: allelenum_max %d > 5", amax);
 	g.A = amax < 2 ? 2 : amax;
 	// catalogues, one per distinct allele count
 	std::vector<int> codes;
-	std::vector<uint8_t> c2i;
+	std::vector<uint16_t> c2i;
 	std::vector<int32_t> loc_cat(t->Lq, -1);
 	t->ncat = 0; t->Gmax = 1;
 	for (int n = 1; n <= amax; n++) {
@@ -1332,12 +1345,12 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 		if (t->allo) build_catalogue_allo(n, cd, cat.cls); else build_catalogue(n, cd, cat.cls);
 		cat.total = (int)cd.size();
 		if (cat.total > t->Gmax) t->Gmax = cat.total;
-		c2i.resize(c2i.size() + (size_t)n * n * n * n, 255);
-		for (int gi = 0; gi < cat.total; gi++) { codes.push_back(cd[gi]); c2i[cat.c2i_off + cd[gi]] = (uint8_t)gi; }
+		c2i.resize(c2i.size() + (size_t)n * n * n * n, 0xFFFFu);
+		for (int gi = 0; gi < cat.total; gi++) { codes.push_back(cd[gi]); c2i[cat.c2i_off + cd[gi]] = (uint16_t)gi; }
 		for (int l = 0; l < g.L; l++) if (c->allelenum_h[l] == n) loc_cat[l] = t->ncat;
 		t->ncat++;
 	}
-	CK(tetra_configure(g, c->cfg.device, t->allo, t->Gmax, (int)c2i.size()));
+	CK(tetra_configure(g, c->cfg.device, t->allo, t->Gmax, (int)(c2i.size() * sizeof(uint16_t))));
 	const size_t tiles = (size_t)t->LTq * g.Nloc * TT * 4;
 	const size_t pn = (size_t)g.Lpad * g.A * g.KP;
 	const size_t tn = (size_t)t->Lq * g.K * t->Gmax;
@@ -1345,7 +1358,7 @@ ig_status tetra_load(ig_ctx *c, const int16_t *x_dev)
 	CK(dalloc0(&t->cats, (size_t)t->ncat)); CK(dalloc0(&t->codes, codes.size())); CK(dalloc0(&t->c2i, c2i.size())); CK(dalloc0(&t->loc_cat, (size_t)t->Lq));
 	CK(cudaMemcpyAsync(t->cats, t->cat_h, sizeof(TetraCat) * t->ncat, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpyAsync(t->codes, codes.data(), codes.size() * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
-	CK(cudaMemcpyAsync(t->c2i, c2i.data(), c2i.size(), cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpyAsync(t->c2i, c2i.data(), c2i.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpyAsync(t->loc_cat, loc_cat.data(), loc_cat.size() * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
 	CK(dalloc0(&t->exf, tn)); CK(dalloc0(&t->tabC, tn)); CK(dalloc0(&t->tabP, tn));
 	CK(dalloc0(&t->Sprop, (size_t)MAX_K)); CK(dalloc0(&t->dstat, (size_t)MAX_K)); CK(dalloc0(&t->accepted, (size_t)MAX_K));

@@ -23,7 +23,9 @@ SHAPES = [
     (70, 13, 3, 4, 0.05),     # KP=4, ragged L
     (300, 9, 6, 4, 0.02),     # config-5 shape in small: K=6 (KP=8), several individual passes
     (40, 22, 2, 2, 0.1),      # biallelic: no tri / quadri classes
-    (33, 8, 5, 6, 0.0),       # largest supported catalogue (126 genotypes)
+    (33, 8, 5, 6, 0.0),       # largest catalogue whose code is one dp4a (126 genotypes)
+    (40, 6, 3, 8, 0.02),      # 330 genotypes: 16-bit catalogue indices, two-dp4a codes
+    (36, 5, 2, 10, 0.0),      # microsatellite-like, the limit: 715 genotypes
     (50, 12, 2, 3, 0.3),      # heavy missingness
 ]
 

@@ -30,7 +30,9 @@ SHAPES = [
     (70, 13, 3, 4, 0.05),     # KP=4, ragged L
     (300, 9, 6, 4, 0.02),     # config-5 shape in small: K=6 (KP=8), several individual passes
     (40, 22, 2, 2, 0.1),      # biallelic: only the 7-way resolution
-    (33, 8, 5, 5, 0.0),       # largest supported catalogue (225 genotypes)
+    (33, 8, 5, 5, 0.0),       # largest catalogue an 8-bit index held (225 genotypes)
+    (40, 6, 3, 7, 0.02),      # 784 genotypes: 16-bit catalogue indices, two-dp4a codes
+    (30, 4, 2, 10, 0.0),      # the limit: 3025 genotypes
     (50, 12, 2, 3, 0.3),      # heavy missingness
 ]
 

@@ -21,7 +21,7 @@ def _random_freq(rng, K, L, allelenum, Amax):
     return f
 
 
-@pytest.mark.parametrize("A,K", [(2, 2), (3, 3), (4, 3), (6, 2)])
+@pytest.mark.parametrize("A,K", [(2, 2), (3, 3), (4, 3), (6, 2), (8, 2), (10, 2)])
 def test_catalogue_and_tables_bit_exact(A, K):
     d = make_tetra_dataset(N=30, L=9, K=K, A=A, miss=0.05, seed=A)
     o = TetraOracle(d.x, d.nd, d.allelenum, K)
@@ -46,7 +46,7 @@ def test_catalogue_and_tables_bit_exact(A, K):
         assert (gf[:, l, :n] <= 0).all()
 
 
-@pytest.mark.parametrize("A,K,miss,back_refl", [(4, 3, 0.05, 1), (3, 2, 0.0, 1), (2, 2, 0.1, 1), (5, 2, 0.02, 0)])
+@pytest.mark.parametrize("A,K,miss,back_refl", [(4, 3, 0.05, 1), (3, 2, 0.0, 1), (2, 2, 0.1, 1), (5, 2, 0.02, 0), (9, 2, 0.02, 1)])
 def test_whole_chain_bit_exact(A, K, miss, back_refl):
     d = make_tetra_dataset(N=36, L=10, K=K, A=A, miss=miss, seed=10 + A)
     o = TetraOracle(d.x, d.nd, d.allelenum, K, back_refl=back_refl)
@@ -65,7 +65,7 @@ def test_whole_chain_bit_exact(A, K, miss, back_refl):
 
 # ---- allotetraploid (-p 4 -ap 0): two subgenomes, freq / freq2 ----------
 
-@pytest.mark.parametrize("A,K", [(2, 2), (3, 3), (4, 3), (5, 2)])
+@pytest.mark.parametrize("A,K", [(2, 2), (3, 3), (4, 3), (5, 2), (8, 2), (10, 2)])
 def test_allo_catalogue_and_tables_bit_exact(A, K):
     d = make_tetra_dataset(N=30, L=9, K=K, A=A, miss=0.05, seed=20 + A)
     o = TetraOracle(d.x, d.nd, d.allelenum, K, autopoly=0)
@@ -91,7 +91,7 @@ def test_allo_catalogue_and_tables_bit_exact(A, K):
         np.testing.assert_allclose(np.exp(gf[:, l, :n].astype(np.float64)).sum(axis=1), 1.0, atol=2e-5)
 
 
-@pytest.mark.parametrize("A,K,miss,back_refl", [(4, 3, 0.05, 1), (3, 2, 0.0, 1), (2, 2, 0.1, 1), (5, 2, 0.02, 1)])
+@pytest.mark.parametrize("A,K,miss,back_refl", [(4, 3, 0.05, 1), (3, 2, 0.0, 1), (2, 2, 0.1, 1), (5, 2, 0.02, 1), (8, 2, 0.02, 1)])
 def test_allo_whole_chain_bit_exact(A, K, miss, back_refl):
     d = make_tetra_dataset(N=36, L=10, K=K, A=A, miss=miss, seed=30 + A)
     o = TetraOracle(d.x, d.nd, d.allelenum, K, back_refl=back_refl, autopoly=0)
