@@ -168,6 +168,12 @@ ig_status ig_comm_init(ig_ctx *ctx, const void *id128);      /* uses cfg.shard_r
 ig_status ig_run_chain(ig_ctx *ctx, int32_t chain_id, const float *initd,
                        ig_chain_result *out, double *convg_ld);
 
+/* The first ckrep retained draws of the POPULATION rates of the last ig_run_chain -- selfing rates (mode 2, ploid 4) or
+ * inbreeding coefficients (mode 4) -- double [ckrep][K], same retained sweeps as convg_ld; *rows = how many are filled.
+ * The reference checks convergence on the log-likelihood only (chain_converg / GelmanRubin, check_converg.c:44-153); with
+ * this the caller can run the same statistic per parameter (`inbreed` does). */
+ig_status ig_get_rate_trace(ig_ctx *ctx, double *out, size_t bytes, int32_t *rows);
+
 /* mcmc_updating() in one call: create + load (host buffers, H2D inside) + run + destroy. */
 ig_status ig_mcmc_updating(const ig_config *cfg, const int16_t *x_host, const int32_t *allelenum_host,
                            int32_t chain_id, const float *initd, ig_chain_result *out, double *convg_ld);

@@ -30,7 +30,7 @@ EXPORTS = [
     "ig_version", "ig_last_error", "ig_device_count", "ig_create", "ig_destroy", "ig_load_genotypes",
     "ig_load_genotypes_device", "ig_comm_unique_id", "ig_comm_init", "ig_run_chain", "ig_mcmc_updating",
     "ig_chain_init", "ig_sweep", "ig_sync", "ig_time_sweeps", "ig_run_phase", "ig_get_state", "ig_set_state", "ig_loglik",
-    "ig_proposal_loglik", "ig_alpha_logratio", "ig_profile", "ig_profile_read", "ig_algorithmic_bytes",
+    "ig_proposal_loglik", "ig_alpha_logratio", "ig_profile", "ig_profile_read", "ig_algorithmic_bytes", "ig_get_rate_trace",
 ]
 
 
@@ -101,6 +101,7 @@ def load():
     L.ig_profile.argtypes = [vp, i32]
     L.ig_profile_read.argtypes = [vp, vp, vp, vp]
     L.ig_algorithmic_bytes.argtypes = [vp, vp, vp]
+    L.ig_get_rate_trace.argtypes = [vp, vp, C.c_size_t, vp]
     _lib = L
     return L
 

@@ -169,7 +169,7 @@ static void free_all(ig_ctx *c)
 	cudaFree(c->logP); cudaFree(c->na_pll);
 	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
 	cudaFree(c->mom.self2); cudaFree(c->mom.gen); cudaFree(c->mom.gen2); cudaFree(c->mom.freq); cudaFree(c->mom.freq2);
-	cudaFree(c->mom.convg);
+	cudaFree(c->mom.convg); cudaFree(c->mom.convg_S);
 }
 
 extern "C" void ig_destroy(ig_ctx *c)
@@ -499,13 +499,35 @@ static void dp_init(ig_ctx *c)                         // init_DP, DPMM.c:124-16
 		}
 	}
 }
+// The scan is sequential over the individuals (DPMM.c:175-197) and sits on the host's critical path every sweep; one
+// Philox4x32-10 block per individual was a third of it.  The scan's uniforms come from xoshiro256** seeded per sweep by
+// one Philox block of (sweep, TAG_DP) -- still a pure function of (seed, chain, sweep), still the same on every rank; the
+// (rare) Beta(G, 2) draw of a new cluster keeps its own Philox stream keyed by the individual.
+struct Xoshiro {
+	uint64_t s[4];
+	static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+	inline uint64_t next()
+	{
+		const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+		s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+		return r;
+	}
+	inline double uniform() { return ((double)(next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+};
 static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165-199; gen8[j] = G_j
 {
 	const Geometry &g = c->geo;
 	const int N = g.N;
-	std::vector<double> cum(N + 1);
+	std::vector<double> &cum = c->dp_cum;
+	if ((int)cum.size() < N + 1) cum.resize(N + 1);
+	Xoshiro rng;
+	{
+		const u32x4 a = philox4x32<10>(u32x4{0u, 0u, c->iter, TAG_DP}, c->key0, c->key1), b = philox4x32<10>(u32x4{1u, 0u, c->iter, TAG_DP}, c->key0, c->key1);
+		rng.s[0] = ((uint64_t)a.x << 32) | a.y; rng.s[1] = ((uint64_t)a.z << 32) | a.w;
+		rng.s[2] = ((uint64_t)b.x << 32) | b.y; rng.s[3] = (((uint64_t)b.z << 32) | b.w) | 1u;
+		for (int w = 0; w < 8; w++) rng.next();
+	}
 	for (int j = 0; j < N; j++) {
-		Stream st((uint32_t)j, 0u, c->iter, TAG_DP, c->key0, c->key1);
 		const int gen = (int)gen8[j];
 		dp_leave(c, j);
 		cum[0] = c->cfg.alpha_dpm / (gen + 1) / gen;                  // gen_post_prob, DPMM.c:369
@@ -514,8 +536,9 @@ static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165
 		// not capped (mcmc.c:329-331), so a larger G (possible until its first accepted proposal) is evaluated directly
 		for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++)
 			cum[n] = cum[n - 1] + c->dp[p].num * dp_dgeom(c, p, gen);
-		const int pick = pick_weighted(cum, n, st.uniform());
+		const int pick = pick_weighted(cum, n, rng.uniform());
 		if (pick == 0) {                                              // sample_poster, DPMM.c:395: Beta(G, 2)
+			Stream st((uint32_t)j, 1u, c->iter, TAG_DP, c->key0, c->key1);
 			c->S_h[j] = draw_beta(st, (double)gen, 2.0);
 			c->dp_of[j] = dp_create(c, c->S_h[j]);
 			c->dp_cnt++;
@@ -928,6 +951,12 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 	out->step = 0;
 	out->flag_empty_cluster = 0;
 	long cnt_step = 0;
+	c->trace_rows = 0;
+	if (c->ns == g.K && c->ns > 0 && cf.ckrep > 0) {                   // population rates: keep their trace beside the log-likelihood's
+		ig_alloc_stream = c->stream;
+		if (!c->mom.convg_S) CK(dalloc(&c->mom.convg_S, (size_t)cf.ckrep * g.K));
+		else CK(cudaMemsetAsync(c->mom.convg_S, 0, (size_t)cf.ckrep * g.K * sizeof(double), c->stream));
+	}
 	MomArgs m{c->ind, c->S, c->sc, c->P, c->mom, g, c->ns, 0, -1, cf.print_freq, cf.print_freq ? c->P64 : nullptr};
 	const long print_every = cf.update >= 100 ? cf.update / 100 : 1;   // print_info, mcmc.c:1273 (guards the /0 of App. B #7)
 	for (long step = 0; step < cf.update; step++) {
@@ -972,9 +1001,24 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 		}
 	}
 	out->step = cnt_step;
+	c->trace_rows = (int)(cnt_step < cf.ckrep ? cnt_step : cf.ckrep);
 	st = download_result(c, out, convg_ld, cnt_step);
 	if (st != IG_OK) return st;
 	return out->flag_empty_cluster ? IG_EMPTY_CLUSTER : IG_OK;
+}
+
+extern "C" ig_status ig_get_rate_trace(ig_ctx *c, double *out, size_t bytes, int32_t *rows)
+{
+	if (!c || !out) return fail(IG_ERR_ARG, "null argument");
+	const Geometry &g = c->geo;
+	if (!c->mom.convg_S) return fail(IG_ERR_STATE, "no rate trace: it exists for population rates (modes 2, 4, ploid 4) with ckrep > 0, after ig_run_chain");
+	const size_t want = (size_t)c->cfg.ckrep * g.K * sizeof(double);
+	if (bytes != want) return fail(IG_ERR_ARG, "rate trace: expected %zu bytes, got %zu", want, bytes);
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaMemcpyAsync(out, c->mom.convg_S, want, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	if (rows) *rows = c->trace_rows;
+	return IG_OK;
 }
 
 extern "C" ig_status ig_mcmc_updating(const ig_config *cfg, const int16_t *x_host, const int32_t *allelenum_host,

@@ -36,6 +36,7 @@ struct ig_ctx {
 	bool loaded = false, chain_ready = false;
 	uint32_t iter = 0, key0 = 0, key1 = 0;
 	int rounds = 7;
+	int trace_rows = 0;        // retained sweeps held by the traces of the last ig_run_chain (<= ckrep)
 	int grid_pre = 1, grid_post = 1;   // cooperative grids of the scalar kernels on this context's device
 	// device buffers
 	int16_t *Xt = nullptr;
@@ -82,6 +83,7 @@ struct ig_ctx {
 	std::vector<DpCluster> dp;
 	std::vector<double> dp_w;     // [slot][51] dgeom(value, g), g = 1..50
 	std::vector<int> dp_of;
+	std::vector<double> dp_cum;   // scratch of the scan
 	int dp_head = -1, dp_free = -1, dp_cnt = 0;
 	// DP prior: the scan reads only G (one byte each, <= 50) and writes only S.  G is packed and copied to pinned host memory
 	// right behind the epilogue of the PREVIOUS sweep, so the host scan overlaps post_sweep and the next p_dirichlet;

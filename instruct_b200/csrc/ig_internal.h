@@ -38,6 +38,7 @@ struct Moments {
 	double *gen, *gen2;
 	double *freq, *freq2;   // [K][L][A] (print_freq)
 	double *convg;     // [ckrep]
+	double *convg_S;   // [ckrep][K] the population rates (selfing rates / inbreeding coefficients) of the same retained sweeps, or null
 };
 
 struct Geometry {

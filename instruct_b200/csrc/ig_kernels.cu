@@ -684,6 +684,7 @@ __global__ void moments_kernel(const MomArgs a)
 		const double s = a.S[t];
 		run_mean(a.m.self + t, s, step);
 		run_mean(a.m.self2 + t, s * s, step);
+		if (a.convg_slot >= 0 && a.m.convg_S) a.m.convg_S[(size_t)a.convg_slot * a.ns + t] = s;
 	}
 	if (t == 0) {
 		const double tl = a.sc->totallkh;

@@ -34,6 +34,7 @@
 static double siglevel = 0.900, alpha_dpm = 10, max_mem = 1.0e9;
 static int nloci = 100, popnum = 2, totalsize = 100, ploid = 2, thinning = 10, ckrep = 20, GR_flag = 1, chainnum = 2;
 static long updatenum = 1000000, burnin = 500000;
+static int gr_params = 0;       /* --gr-params 1: also append the per-parameter Gelman-Rubin lines to the -o file (not in the reference's format) */
 static const char *missingdata = "-9", *datafilename, *outfilename, *initialfilename, *convgfilename;
 static int label = 1, popdata = 1, prior_flag = 0, back_refl = 1, type_freq = 1, nstep_check_empty_cluster = 20;
 static int n_extra_col = 0, markername_flag = 0, print_iter = 1, print_freq = 0, n_small = 1, n_large = 0, inf_K = 0;
@@ -57,7 +58,7 @@ static void parse_args(int argc, char **argv)
 	    "[-f prior_flag] [-v mode] [-h alpha_dpm] [-e back_refl] [-y type_freq] [-j nstep_check_empty_cluster] "
 	    "[-x extra_columns] [-w markername] [-cf convgfilename] [-pi print_iter] [-pf print_freq]  [-ik inf_K] "
 	    "[-kv n_small n_large] [-df distr_fmt] [-ap autopoly] [-af data_fmt] [-mm max_mem] "
-	    "[--gpus N] [--shard chains|individuals] [--ref-compat-gr] [--quiet-data] "
+	    "[--gpus N] [--shard chains|individuals] [--ref-compat-gr] [--gr-params 0|1] [--quiet-data] "
 	    "[--save-store file] [--load-store file] [--pack-only]\n";
 	int i;
 	if (argc == 2 && strcmp(argv[1], "-h") == 0) { fprintf(stdout, "%s", synopsis); exit(1); }
@@ -68,6 +69,7 @@ static void parse_args(int argc, char **argv)
 		else if (ARG("-o")) outfilename = argv[i + 1];
 		else if (ARG("-i")) initialfilename = argv[i + 1];
 		else if (ARG("-cf")) convgfilename = argv[i + 1];
+		else if (ARG("--gr-params")) gr_params = atoi(argv[i + 1]);
 		else if (ARG("-L")) nloci = atoi(argv[i + 1]);
 		else if (ARG("-N")) totalsize = atoi(argv[i + 1]);
 		else if (ARG("-K")) popnum = atoi(argv[i + 1]);
@@ -166,6 +168,7 @@ typedef struct {
 	const init_t *init;
 	chain_out *out;         /* [chainnum] */
 	double *convg;          /* [chainnum][ckrep] */
+	double *convgS;         /* [chainnum][ckrep][K] population-rate traces (modes 2, 4, ploid 4), or NULL */
 	unsigned char nccl_id[128];
 	int status;
 	char err[512];
@@ -233,6 +236,10 @@ static void *worker(void *arg)
 			attempt++;
 		}
 		if (w->status < 0) break;
+		if (w->convgS && (w->rank == 0 || w->nrank == 1)) {
+			int32_t rows = 0;
+			if (ig_get_rate_trace(ctx, w->convgS + (size_t)chn * ckrep * K, (size_t)ckrep * K * sizeof(double), &rows) != IG_OK) w->convgS = NULL;
+		}
 		if (r.step != r.steps) { w->status = IG_ERR_STATE; snprintf(w->err, sizeof w->err, "The number of iterations attained is not the same as counted"); break; }
 		o->totallkh = r.totallkh; o->totallkh2 = r.totallkh2; o->done = 1;
 		if (w->rank == 0 || w->nrank == 1) fprintf(stdout, "\n\nChain %d is finished running.\n", chn + 1);
@@ -251,7 +258,7 @@ static double run_for_K(const gs_store *gsp, int K, wr_run *runp, const wr_data 
 	const wr_data wd = *wdp;
 	init_t init;
 	chain_out *outs;
-	double *convg = NULL, dic_min = 0;
+	double *convg = NULL, *convgS = NULL, dic_min = 0;
 	worker_t *ws;
 	pthread_t *th;
 	int g, chn, N = gs.totalsize, ns;
@@ -265,11 +272,12 @@ static double run_for_K(const gs_store *gsp, int K, wr_run *runp, const wr_data 
 	outs = (chain_out *)calloc((size_t)chainnum, sizeof(chain_out));
 	for (chn = 0; chn < chainnum; chn++) alloc_out(&outs[chn], N, K, ns, nfreq);
 	if (GR_flag) convg = (double *)calloc((size_t)chainnum * ckrep, sizeof(double));
+	if (GR_flag && ns == K && (ploid == 4 || mode == 2 || mode == 4)) convgS = (double *)calloc((size_t)chainnum * ckrep * K, sizeof(double));
 	ws = (worker_t *)calloc((size_t)n_gpus, sizeof(worker_t));
 	th = (pthread_t *)calloc((size_t)n_gpus, sizeof(pthread_t));
 	for (g = 0; g < n_gpus; g++) {
 		ws[g].gpu = g; ws[g].rank = g; ws[g].nrank = shard_individuals ? n_gpus : 1;
-		ws[g].gs = &gs; ws[g].init = &init; ws[g].convg = convg;
+		ws[g].gs = &gs; ws[g].init = &init; ws[g].convg = convg; ws[g].convgS = convgS;
 		/* sharded ranks all compute the full moments; only rank 0's copy is kept */
 		if (shard_individuals && g > 0) {
 			ws[g].out = (chain_out *)calloc((size_t)chainnum, sizeof(chain_out));
@@ -300,7 +308,15 @@ static double run_for_K(const gs_store *gsp, int K, wr_run *runp, const wr_data 
 	}
 	if (GR_flag == 1 && wr_convergence(outfilename, convg, chainnum, ckrep, convgfilename, ref_compat_gr) < 0)
 		die("ERROR: Cannot open output file!\n");
-	free(ws); free(th); free(outs); free(convg);
+	if (GR_flag == 1 && convgS && chainnum > 1) {
+		/* per-parameter convergence: the reference's statistic (check_converg.c:100-153) on the
+		 * trace of every population rate, clusters of chain c matched to chain 0's by the overlap of their posterior mean Q */
+		const double **qq = (const double **)calloc((size_t)chainnum, sizeof(double *));
+		for (chn = 0; chn < chainnum; chn++) qq[chn] = outs[chn].qq;
+		wr_rate_convergence(gr_params ? outfilename : NULL, convgS, qq, chainnum, ckrep, K, N, (ploid == 2 && mode == 4) ? "inbreeding coefficient" : "selfing rate");
+		free(qq);
+	}
+	free(ws); free(th); free(outs); free(convg); free(convgS);
 	return dic_min;
 }
 

@@ -310,3 +310,37 @@ int wr_convergence(const char *path, const double *convg_ld, int n_chain, int ck
 	}
 	return flag;
 }
+
+int wr_rate_convergence(const char *path, const double *tr, const double *const *qq, int n_chain, int ckrep, int K, int N, const char *what)
+{
+	int c, a, b, i, j, flag = 0;
+	int *perm = (int *)calloc((size_t)n_chain * K, sizeof(int));          /* perm[c][a] = cluster of chain c matched to cluster a of chain 0 */
+	double *ov = (double *)calloc((size_t)K * K, sizeof(double)), *one = (double *)calloc((size_t)n_chain * ckrep, sizeof(double));
+	FILE *f = path ? fopen(path, "a+") : NULL;
+	for (a = 0; a < K; a++) perm[a] = a;
+	for (c = 1; c < n_chain; c++) {
+		char *ua = (char *)calloc((size_t)K, 1), *ub = (char *)calloc((size_t)K, 1);
+		for (a = 0; a < K * K; a++) ov[a] = 0;
+		for (i = 0; i < N; i++)
+			for (a = 0; a < K; a++)
+				for (b = 0; b < K; b++) ov[a * K + b] += qq[0][(size_t)i * K + a] * qq[c][(size_t)i * K + b];
+		for (j = 0; j < K; j++) {                                         /* greedy assignment, best remaining pair first */
+			int ba = -1, bb = -1;
+			for (a = 0; a < K; a++) if (!ua[a]) for (b = 0; b < K; b++) if (!ub[b] && (ba < 0 || ov[a * K + b] > ov[ba * K + bb])) { ba = a; bb = b; }
+			perm[c * K + ba] = bb; ua[ba] = 1; ub[bb] = 1;
+		}
+		free(ua); free(ub);
+	}
+	for (a = 0; a < K; a++) {
+		double gr;
+		for (c = 0; c < n_chain; c++)
+			for (j = 0; j < ckrep; j++) one[(size_t)c * ckrep + j] = tr[((size_t)c * ckrep + j) * K + perm[c * K + a]];
+		gr = wr_gelman_rubin(one, n_chain, ckrep);
+		fprintf(stdout, "The Gelman-Rubin statistics of the %s of cluster %d is %f\n", what, a + 1, gr);
+		if (f) fprintf(f, "The Gelman-Rubin statistics for the convergence of the %s of cluster %d is %f.\n", what, a + 1, gr);
+		if (gr > 1.1) flag = 1;
+	}
+	if (f) fclose(f);
+	free(perm); free(ov); free(one);
+	return flag;
+}

@@ -29,4 +29,10 @@ int wr_chain(const char *path, const wr_run *r, const wr_data *d, const wr_chain
 double wr_gelman_rubin(const double *traces, int n_chain, int n);
 int wr_convergence(const char *path, const double *convg_ld, int n_chain, int ckrep, const char *convgfile, int ref_compat);
 
+/* Gelman-Rubin per population rate on the first ckrep retained draws of every chain (tr: [n_chain][ckrep][K]).  Clusters are
+ * matched across chains first (label switching): cluster b of chain c goes with the cluster a of chain 0 it shares most
+ * posterior membership with, sum_i qq_0[i][a] * qq_c[i][b], greedily from the best pair down.  Printed to stdout, and
+ * appended to `path` when it is not NULL.  Returns 1 when some statistic exceeds 1.1. */
+int wr_rate_convergence(const char *path, const double *tr, const double *const *qq, int n_chain, int ckrep, int K, int N, const char *what);
+
 #endif

@@ -36,6 +36,9 @@ def test_cli_matches_reference_program(tmp_path):
         assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
         assert "THE JOB IS SUCCESSFULLY FINISHED" in p.stdout
         outs[name] = open(out, "rb").read()
+        if name == "gpu":      # per-parameter convergence (stdout only: the result file keeps the reference's format)
+            gr = [float(v) for v in re.findall(r"Gelman-Rubin statistics of the selfing rate of cluster \d+ is (-?\d+\.\d+)", p.stdout)]
+            assert len(gr) == 2 and all(0.8 < v < 2.5 for v in gr), p.stdout[-1500:]
     # ---- banner: identical bytes apart from the echoed command line
     def banner(t):
         t = t[: t.index(b"Chain#1")]
