@@ -178,6 +178,10 @@ ig_status ig_get_rate_trace(ig_ctx *ctx, double *out, size_t bytes, int32_t *row
 ig_status ig_mcmc_updating(const ig_config *cfg, const int16_t *x_host, const int32_t *allelenum_host,
                            int32_t chain_id, const float *initd, ig_chain_result *out, double *convg_ld);
 
+/* Device buffers freed by ig_destroy() are kept by the library and reused by the next context (one mcmc_updating() call
+ * per chain would otherwise pay cudaMalloc / cudaFree of several GB every time); this returns them to the driver. */
+ig_status ig_release_cache(void);
+
 /* ---- finer-grained control (benchmarks, tests) --------------------------------------- */
 ig_status ig_chain_init(ig_ctx *ctx, int32_t chain_id, const float *initd);
 ig_status ig_sweep(ig_ctx *ctx, int32_t nsweeps);            /* asynchronous; see ig_sync */

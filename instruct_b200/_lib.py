@@ -30,7 +30,7 @@ EXPORTS = [
     "ig_version", "ig_last_error", "ig_device_count", "ig_create", "ig_destroy", "ig_load_genotypes",
     "ig_load_genotypes_device", "ig_comm_unique_id", "ig_comm_init", "ig_run_chain", "ig_mcmc_updating",
     "ig_chain_init", "ig_sweep", "ig_sync", "ig_time_sweeps", "ig_run_phase", "ig_get_state", "ig_set_state", "ig_loglik",
-    "ig_proposal_loglik", "ig_alpha_logratio", "ig_profile", "ig_profile_read", "ig_algorithmic_bytes", "ig_get_rate_trace",
+    "ig_proposal_loglik", "ig_alpha_logratio", "ig_profile", "ig_profile_read", "ig_algorithmic_bytes", "ig_get_rate_trace", "ig_release_cache",
 ]
 
 

@@ -527,15 +527,21 @@ static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165
 		rng.s[2] = ((uint64_t)b.x << 32) | b.y; rng.s[3] = (((uint64_t)b.z << 32) | b.w) | 1u;
 		for (int w = 0; w < 8; w++) rng.next();
 	}
+	std::vector<int> &node = c->dp_node;
+	if ((int)node.size() < N + 1) node.resize(N + 1);
 	for (int j = 0; j < N; j++) {
 		const int gen = (int)gen8[j];
 		dp_leave(c, j);
 		cum[0] = c->cfg.alpha_dpm / (gen + 1) / gen;                  // gen_post_prob, DPMM.c:369
 		int n = 1;
 		// num * dgeom(value, G_j), DPMM.c:373: from the per-cluster table for G in 1..50; the reference's mode-3 initial G is
-		// not capped (mcmc.c:329-331), so a larger G (possible until its first accepted proposal) is evaluated directly
-		for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++)
-			cum[n] = cum[n - 1] + c->dp[p].num * dp_dgeom(c, p, gen);
+		// not capped (mcmc.c:329-331), so a larger G (possible until its first accepted proposal) is evaluated directly.
+		// One walk over the value-ordered list: cumulative weights and the slot of every position.
+		if (gen >= 1 && gen <= 50) {
+			const double *w = c->dp_w.data() + gen;
+			for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++) { cum[n] = cum[n - 1] + c->dp[p].num * w[(size_t)p * 51]; node[n] = p; }
+		} else
+			for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++) { cum[n] = cum[n - 1] + c->dp[p].num * dp_dgeom(c, p, gen); node[n] = p; }
 		const int pick = pick_weighted(cum, n, rng.uniform());
 		if (pick == 0) {                                              // sample_poster, DPMM.c:395: Beta(G, 2)
 			Stream st((uint32_t)j, 1u, c->iter, TAG_DP, c->key0, c->key1);
@@ -543,8 +549,7 @@ static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165
 			c->dp_of[j] = dp_create(c, c->S_h[j]);
 			c->dp_cnt++;
 		} else {
-			int p = c->dp_head;
-			for (int k = 1; k < pick; k++) p = c->dp[p].next;
+			const int p = node[pick];
 			c->dp[p].num++; c->dp_of[j] = p; c->S_h[j] = c->dp[p].value;
 		}
 	}

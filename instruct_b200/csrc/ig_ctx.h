@@ -13,6 +13,12 @@
 
 #include "ig_internal.h"
 
+// every device allocation of the library goes through the caching allocator of ig_pool.cu
+cudaError_t ig_pool_malloc(void **p, size_t bytes);
+cudaError_t ig_pool_free(void *p);
+#define cudaMalloc(p, n) ig_pool_malloc((void **)(p), (n))
+#define cudaFree(p) ig_pool_free((void *)(p))
+
 ig_status ig_fail(ig_status st, const char *fmt, ...);
 #define fail ig_fail
 #define CK(call)                                                                                           \
@@ -84,6 +90,7 @@ struct ig_ctx {
 	std::vector<double> dp_w;     // [slot][51] dgeom(value, g), g = 1..50
 	std::vector<int> dp_of;
 	std::vector<double> dp_cum;   // scratch of the scan
+	std::vector<int> dp_node;
 	int dp_head = -1, dp_free = -1, dp_cnt = 0;
 	// DP prior: the scan reads only G (one byte each, <= 50) and writes only S.  G is packed and copied to pinned host memory
 	// right behind the epilogue of the PREVIOUS sweep, so the host scan overlaps post_sweep and the next p_dirichlet;

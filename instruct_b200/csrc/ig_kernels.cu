@@ -368,7 +368,7 @@ cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
 // --------------------------------------------------------------------------------------
 constexpr int EPI_THREADS = 256;
 template <int EPI_IPB>              // individuals per CTA: 8 (small shards: more CTAs) or 32; chunk groups = 256 / EPI_IPB
-__global__ void __launch_bounds__(EPI_THREADS) indiv_epilogue_kernel(const EpiArgs a)
+__global__ void __launch_bounds__(EPI_THREADS, EPI_IPB == 32 ? 3 : 2) indiv_epilogue_kernel(const EpiArgs a)
 {
 	constexpr int EPI_GROUPS = EPI_THREADS / EPI_IPB;
 	__shared__ int cnt_sh[EPI_GROUPS][MAX_K][EPI_IPB];
@@ -389,15 +389,19 @@ __global__ void __launch_bounds__(EPI_THREADS) indiv_epilogue_kernel(const EpiAr
 	for (int k = 0; k < MAX_K; k++) cnt[k] = 0;
 	// The floating-point sums of an individual are taken in an order that depends on the chunk decomposition only (so a
 	// chain is bit-identical for every shard count and either CTA shape): chunks c = v (mod 32) form virtual group v, summed
-	// in chunk order; four consecutive virtual groups are folded left to right into T_0 .. T_7; the T are folded in order.
+	// in chunk order; T_t = ((s_t + s_t+8) + s_t+16) + s_t+24 for t = 0 .. 7; the T are folded in order.  The 8-row shape
+	// walks its four virtual groups in ONE loop with four accumulator sets, the 32-row shape has one group per row.
 	constexpr int VG = 32, VPR = VG / EPI_GROUPS;      // virtual groups, and how many of them one thread row walks (1 or 4)
-	double d_old = 0.0, a_new = 0.0, b_new = 0.0;
+	double dv[VPR], av[VPR], bv[VPR];
+#pragma unroll
+	for (int vv = 0; vv < VPR; vv++) dv[vv] = av[vv] = bv[vv] = 0.0;
 	int nsh_new = 0;
 	if (live) {
+		for (int c0 = w; c0 < g.nchunks; c0 += VG) {
 #pragma unroll
-		for (int vv = 0; vv < VPR; vv++) {
-			double dv = 0.0, av = 0.0, bv = 0.0;
-			for (int c = w * VPR + vv; c < g.nchunks; c += VG) {
+			for (int vv = 0; vv < VPR; vv++) {
+				const int c = c0 + vv * EPI_GROUPS;
+				if (c >= g.nchunks) break;
 				// KP u16 counters per (chunk, individual): 8, 16 or 32 bytes, read as 64 / 128-bit vectors
 				const uint16_t *pcb = a.pcnt + ((size_t)c * g.Nloc + il) * KP;
 #define EPI_ADD(J, V) do { cnt[2 * (J)] += (V) & 0xFFFFu; cnt[2 * (J) + 1] += (V) >> 16; } while (0)
@@ -409,14 +413,16 @@ __global__ void __launch_bounds__(EPI_THREADS) indiv_epilogue_kernel(const EpiAr
 				}
 #undef EPI_ADD
 				const double *pl = a.plog + (size_t)c * 3 * g.Nloc + il;
-				dv += pl[0];
-				av += pl[(size_t)g.Nloc];
-				bv += pl[(size_t)2 * g.Nloc];
+				dv[vv] += pl[0];
+				av[vv] += pl[(size_t)g.Nloc];
+				bv[vv] += pl[(size_t)2 * g.Nloc];
 				nsh_new += a.pnsh[(size_t)c * g.Nloc + il];
 			}
-			d_old += dv; a_new += av; b_new += bv;     // VPR == 4: this row's T; VPR == 1: one virtual group, folded below
 		}
 	}
+	double d_old = dv[0], a_new = av[0], b_new = bv[0];     // VPR == 4: this row's T; VPR == 1: one virtual group, folded below
+#pragma unroll
+	for (int vv = 1; vv < VPR; vv++) { d_old += dv[vv]; a_new += av[vv]; b_new += bv[vv]; }
 #pragma unroll
 	for (int k = 0; k < MAX_K; k++) cnt_sh[w][k][lane] = cnt[k];
 	ll_sh[w][0][lane] = d_old; ll_sh[w][1][lane] = a_new; ll_sh[w][2][lane] = b_new;
@@ -438,8 +444,8 @@ __global__ void __launch_bounds__(EPI_THREADS) indiv_epilogue_kernel(const EpiAr
 			} else if (task < K + 3) {
 				double t = 0.0;
 				for (int tw = 0; tw < 8; tw++) {
-					double tt = 0.0;
-					for (int r = 0; r < EPI_GROUPS / 8; r++) tt += ll_sh[tw * (EPI_GROUPS / 8) + r][task - K][lane];
+					double tt = ll_sh[tw][task - K][lane];
+					for (int r = 1; r < EPI_GROUPS / 8; r++) tt += ll_sh[tw + 8 * r][task - K][lane];
 					t += tt;
 				}
 				llt_sh[task - K][lane] = t;

@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_zs_kernel(const ZsArgs
 	const int sub0 = blockIdx.y * g.subs_per_blk, sub1 = min(sub0 + g.subs_per_blk, nsub_total);
 	const uint32_t psm = smem_addr(Psm);
 	const RegConst kc{a.k_mant, a.k_one};
+	const RegConst kc16{U16_MANT, U16_ONE};
 	const float cnt_t = as_dn(smem_addr(cntsm) + (uint32_t)tid * 4u);
 
 	for (int sub = sub0; sub < sub1; ++sub) {
@@ -544,6 +545,10 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_zs_kernel(const ZsArgs
 			const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
 			const uint32_t zo[4] = {(uint32_t)zv.x, (uint32_t)zv.y, (uint32_t)zv.z, (uint32_t)zv.w};
 			uint32_t zn[4];
+			// 16 random bits per allele copy (sweep_common.cuh): two Philox blocks serve the micro-tile's 16 copies
+			const u32x4 rndA = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z16 | 0u}, a.key0, a.key1);
+			const u32x4 rndB = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z16 | 1u}, a.key0, a.key1);
+			const uint32_t rw[8] = {rndA.x, rndA.y, rndA.z, rndA.w, rndB.x, rndB.y, rndB.z, rndB.w};
 #pragma unroll
 			for (int j = 0; j < TT; ++j) {
 				zn[j] = zo[j];
@@ -563,8 +568,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_zs_kernel(const ZsArgs
 					}
 				}
 				// ---- new z: one categorical draw per copy, weights Q_ik P_k,l,geno_c (poly_geno.c:766-779)
-				const u32x4 rnd = philox4x32<ROUNDS>(u32x4{(uint32_t)(mt0 + mt), ig_global, a.iter, TAG_Z | (uint32_t)j}, a.key0, a.key1);
-				const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+				const uint32_t rr[4] = {rw[2 * j], __byte_perm(rw[2 * j], 0u, 0x1032), rw[2 * j + 1], __byte_perm(rw[2 * j + 1], 0u, 0x1032)};
 				const float rowbf = as_dn(psm + (uint32_t)(lj * rowsz) * 4u);
 				uint32_t packed = 0;
 #pragma unroll
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(TETRA_THREADS, 3) tetra_zs_kernel(const ZsArgs
 					cw[0] = q[0] * p[0];
 #pragma unroll
 					for (int k = 1; k < KP; k++) cw[k] = fmaf(q[k], p[k], cw[k - 1]);
-					const float zf = pick_category<KP>(cw, uniform_big(rr[cidx], kc));
+					const float zf = pick_category<KP>(cw, uniform_big16(rr[cidx], kc16));
 					red_inc(__float_as_uint(fmaf(zf, as_dn(4u * TETRA_THREADS), cnt_t)));
 					packed |= __float_as_uint(zf * as_dn(1u)) << (8 * cidx);
 				}
