@@ -326,6 +326,45 @@ def check_shard_parity(args, K, mode, srank, count, chain, gsz, grp, rank, local
     return bool(int(t[0].item()))
 
 
+def measure_concurrent_chains(args, x, an, K, N, L, mode, ploid, local, copies, C=8):
+    """Small data sets (configs 1-2) are launch- and latency-bound: one chain's sweep leaves most SMs idle.  BASELINE's
+    config 2 is 8 chains; here C chains run CONCURRENTLY on the one GPU, each on its own context and stream from its own
+    host thread (what `inbreed --chains-per-gpu` does), and the aggregate rate is reported."""
+    import threading
+    import numpy as np
+    from instruct_b200 import Sampler, SeqData
+
+    shape_only = np.lib.stride_tricks.as_strided(np.zeros(1, dtype=np.int16), shape=(L, N, ploid), strides=(0, 0, 0))
+    sd = SeqData(shape_only, np.zeros(L, dtype=np.int32), K, ploid=ploid, mode=mode, prior_flag=1 if args.workload == "c3" else 0, alpha_dpm=2.0)
+    ss = []
+    for c in range(C):
+        s = Sampler(sd, seed=args.seed, device=local, rng_rounds=args.rng_rounds, x_device_ptr=x.data_ptr(), allelenum_device_ptr=an.data_ptr())
+        s.chain_init(c, initd=np.linspace(0.2, 0.8, K) if mode == 2 else None)
+        s.sweep(args.warmup)
+        s.sync()
+        ss.append(s)
+    bar = threading.Barrier(C + 1)
+    def work(s):
+        bar.wait()
+        s.sweep(args.steps)
+        s.sync()
+        bar.wait()
+    th = [threading.Thread(target=work, args=(s,)) for s in ss]
+    for t in th:
+        t.start()
+    bar.wait()
+    t0 = time.perf_counter()
+    bar.wait()
+    dt = time.perf_counter() - t0
+    for t in th:
+        t.join()
+    for s in ss:
+        s.close()
+    return {"chains": C, "sweeps_per_chain": args.steps, "seconds": dt, "us_per_sweep_per_chain": 1e6 * dt / (args.steps * C),
+            "value": copies * C * args.steps / dt, "unit": "copy-updates/s",
+            "note": "C independent chains in flight on ONE GPU (own context, stream and host thread each); wall clock between barriers"}
+
+
 def measure_chains(args, N, L, K, A, miss, mode, tetra, ploid, rank, world, local, dist):
     """The other way the path shards: one independent chain per GPU on the whole data set, no communication.  Same
     workload, same step count, timed between barriers on the slowest rank."""
@@ -478,6 +517,9 @@ def run_ours(args):
     if not args.no_e2e and (world == 1 or shard_ind):
         e2e = measure_e2e(args, x, an, K, N, mode, ploid, tetra, nloc, srank, count, chain_of_rank, gsz, grp, rank, world, local, dist,
                           copies_total)
+    conc = None
+    if world == 1 and not tetra and N * L <= 2_000_000 and not args.no_concurrent:
+        conc = measure_concurrent_chains(args, x, an, K, N, L, mode, ploid, local, copies_local)
     shard_parity = None
     if world > 1 and shard_ind and not tetra:
         shard_parity = check_shard_parity(args, K, mode, srank, count, chain_of_rank, gsz, grp, rank, local, dist)
@@ -508,7 +550,7 @@ def run_ours(args):
                          "graph_replay": (not inline_profile) and world == 1 and not tetra and args.workload != "c3", "ms_per_step_direct_launch": ms_direct / args.steps},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None,
             "e2e": e2e, "gpu_launches": int(k1 - k0), "clocks": clk,
-            "shard_parity": shard_parity, "chains": chains_rec,
+            "shard_parity": shard_parity, "chains": chains_rec, "concurrent_chains": conc,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -529,6 +571,7 @@ def main():
     ap.add_argument("--N", type=int, default=0)
     ap.add_argument("--L", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-concurrent", action="store_true", help="small workloads: skip the concurrent-chains sub-record")
     ap.add_argument("--no-chains", action="store_true", help="N > 1: skip the chain-partitioned sub-record")
     ap.add_argument("--e2e-sweeps", type=int, default=0, help="sweeps of the end-to-end chain (default 4 x (steps + warmup))")
     ap.add_argument("--no-cpu", action="store_true")

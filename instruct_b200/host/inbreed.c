@@ -41,6 +41,9 @@ static int n_extra_col = 0, markername_flag = 0, print_iter = 1, print_freq = 0,
 static int distr_fmt = 1, autopoly = 1, data_fmt = 0, mode = 1;
 static long seeds[3] = {13, 4, 1972};               /* random.c:10-12 */
 static int n_gpus = 1, shard_individuals = 0, ref_compat_gr = 0, quiet_data = 0, pack_only = 0;
+static int chains_per_gpu = 0;    /* --chains-per-gpu C: chains run concurrently on one GPU (0 = choose: several for small data sets, whose sweeps
+                                   * are launch- and latency-bound and leave most of the SMs idle; 1 for HBM-sized ones) */
+static int n_workers = 1;
 static const char *save_store = NULL, *load_store = NULL;
 
 static void die(const char *msg)                    /* nrerror's output convention, nrutil.c:9-16 */
@@ -58,7 +61,7 @@ static void parse_args(int argc, char **argv)
 	    "[-f prior_flag] [-v mode] [-h alpha_dpm] [-e back_refl] [-y type_freq] [-j nstep_check_empty_cluster] "
 	    "[-x extra_columns] [-w markername] [-cf convgfilename] [-pi print_iter] [-pf print_freq]  [-ik inf_K] "
 	    "[-kv n_small n_large] [-df distr_fmt] [-ap autopoly] [-af data_fmt] [-mm max_mem] "
-	    "[--gpus N] [--shard chains|individuals] [--ref-compat-gr] [--gr-params 0|1] [--quiet-data] "
+	    "[--gpus N] [--shard chains|individuals] [--chains-per-gpu C] [--ref-compat-gr] [--gr-params 0|1] [--quiet-data] "
 	    "[--save-store file] [--load-store file] [--pack-only]\n";
 	int i;
 	if (argc == 2 && strcmp(argv[1], "-h") == 0) { fprintf(stdout, "%s", synopsis); exit(1); }
@@ -102,6 +105,7 @@ static void parse_args(int argc, char **argv)
 		else if (ARG("-j")) nstep_check_empty_cluster = atoi(argv[i + 1]);
 		else if (strcmp(argv[i], "-s") == 0 && i + 3 < argc) { seeds[0] = atol(argv[i + 1]); seeds[1] = atol(argv[i + 2]); seeds[2] = atol(argv[i + 3]); }
 		else if (ARG("--gpus")) n_gpus = atoi(argv[i + 1]);
+		else if (ARG("--chains-per-gpu")) chains_per_gpu = atoi(argv[i + 1]);
 		else if (ARG("--shard")) shard_individuals = (strcmp(argv[i + 1], "individuals") == 0);
 		else if (strcmp(argv[i], "--ref-compat-gr") == 0) ref_compat_gr = 1;
 		else if (strcmp(argv[i], "--quiet-data") == 0) quiet_data = 1;
@@ -223,7 +227,7 @@ static void *worker(void *arg)
 		chain_out *o = &w->out[chn];
 		ig_chain_result r;
 		int attempt = 0;
-		if (w->nrank == 1 && chn % n_gpus != w->rank) continue;     /* chains mode: chain c on GPU c mod N */
+		if (w->nrank == 1 && chn % n_workers != w->rank) continue;  /* chains mode: chain c on worker c mod W, worker w on GPU w mod N */
 		memset(&r, 0, sizeof r);
 		r.indvlkh = o->indvlkh; r.qq = o->qq; r.qq2 = o->qq2; r.self_rates = o->self; r.self_rates2 = o->self2;
 		r.gen = o->gen; r.gen2 = o->gen2; r.freq = o->freq; r.freq2 = o->freq2;
@@ -273,10 +277,21 @@ static double run_for_K(const gs_store *gsp, int K, wr_run *runp, const wr_data 
 	for (chn = 0; chn < chainnum; chn++) alloc_out(&outs[chn], N, K, ns, nfreq);
 	if (GR_flag) convg = (double *)calloc((size_t)chainnum * ckrep, sizeof(double));
 	if (GR_flag && ns == K && (ploid == 4 || mode == 2 || mode == 4)) convgS = (double *)calloc((size_t)chainnum * ckrep * K, sizeof(double));
-	ws = (worker_t *)calloc((size_t)n_gpus, sizeof(worker_t));
-	th = (pthread_t *)calloc((size_t)n_gpus, sizeof(pthread_t));
-	for (g = 0; g < n_gpus; g++) {
-		ws[g].gpu = g; ws[g].rank = g; ws[g].nrank = shard_individuals ? n_gpus : 1;
+	/* chains mode: n_workers = GPUs x chains per GPU host threads, each with its own context (its own copy of the store, its
+	 * own stream), so that several chains' sweeps are in flight on one GPU; sharded mode: one worker per GPU */
+	n_workers = n_gpus;
+	if (!shard_individuals) {
+		int cpg = chains_per_gpu;
+		if (cpg <= 0) cpg = ((double)gs.totalsize * gs.locinum <= 2.0e6 && print_iter == 0) ? 8 : 1;   /* progress lines of concurrent chains would interleave */
+		if (cpg > 16) cpg = 16;
+		n_workers = n_gpus * cpg;
+		if (n_workers > chainnum) n_workers = chainnum;
+		if (n_workers < 1) n_workers = 1;
+	}
+	ws = (worker_t *)calloc((size_t)n_workers, sizeof(worker_t));
+	th = (pthread_t *)calloc((size_t)n_workers, sizeof(pthread_t));
+	for (g = 0; g < n_workers; g++) {
+		ws[g].gpu = g % n_gpus; ws[g].rank = g; ws[g].nrank = shard_individuals ? n_gpus : 1;
 		ws[g].gs = &gs; ws[g].init = &init; ws[g].convg = convg; ws[g].convgS = convgS;
 		/* sharded ranks all compute the full moments; only rank 0's copy is kept */
 		if (shard_individuals && g > 0) {
@@ -289,9 +304,9 @@ static double run_for_K(const gs_store *gsp, int K, wr_run *runp, const wr_data 
 		if (ig_comm_unique_id(ws[0].nccl_id) != IG_OK) die(ig_last_error());
 		for (g = 1; g < n_gpus; g++) memcpy(ws[g].nccl_id, ws[0].nccl_id, 128);
 	}
-	for (g = 0; g < n_gpus; g++) pthread_create(&th[g], NULL, worker, &ws[g]);
-	for (g = 0; g < n_gpus; g++) pthread_join(th[g], NULL);
-	for (g = 0; g < n_gpus; g++) if (ws[g].status < 0) die(ws[g].err);
+	for (g = 0; g < n_workers; g++) pthread_create(&th[g], NULL, worker, &ws[g]);
+	for (g = 0; g < n_workers; g++) pthread_join(th[g], NULL);
+	for (g = 0; g < n_workers; g++) if (ws[g].status < 0) die(ws[g].err);
 
 	for (chn = 0; chn < chainnum; chn++) {               /* chain_stat in chain order, InStruct.c:191 */
 		wr_chain_t c;
