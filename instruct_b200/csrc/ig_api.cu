@@ -527,31 +527,62 @@ static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165
 		rng.s[2] = ((uint64_t)b.x << 32) | b.y; rng.s[3] = (((uint64_t)b.z << 32) | b.w) | 1u;
 		for (int w = 0; w < 8; w++) rng.next();
 	}
-	std::vector<int> &node = c->dp_node;
-	if ((int)node.size() < N + 1) node.resize(N + 1);
+	// T[g] = sum over clusters of num_c * dgeom(S_c, g), kept current as individuals leave and join (two 50-element vector
+	// updates per individual), so the total weight of an individual with G = g is alpha/((g+1)g) + T[g] without a pass over
+	// the clusters; the pick then walks the value-ordered list only as far as the chosen cluster.  Rebuilt from scratch at
+	// the start of every scan, so rounding cannot drift; if rounding leaves the threshold beyond the last cumulative weight,
+	// the last cluster is taken (as disc_unif does, random.c:425-429).
+	double T[51];
+	for (int gg = 0; gg <= 50; gg++) T[gg] = 0.0;
+	for (int p = c->dp_head; p >= 0; p = c->dp[p].next) {
+		const double *w = &c->dp_w[(size_t)p * 51];
+		const double num = c->dp[p].num;
+		for (int gg = 1; gg <= 50; gg++) T[gg] += num * w[gg];
+	}
 	for (int j = 0; j < N; j++) {
 		const int gen = (int)gen8[j];
+		{
+			const double *w = &c->dp_w[(size_t)c->dp_of[j] * 51];
+			for (int gg = 1; gg <= 50; gg++) T[gg] -= w[gg];
+		}
 		dp_leave(c, j);
-		cum[0] = c->cfg.alpha_dpm / (gen + 1) / gen;                  // gen_post_prob, DPMM.c:369
-		int n = 1;
-		// num * dgeom(value, G_j), DPMM.c:373: from the per-cluster table for G in 1..50; the reference's mode-3 initial G is
-		// not capped (mcmc.c:329-331), so a larger G (possible until its first accepted proposal) is evaluated directly.
-		// One walk over the value-ordered list: cumulative weights and the slot of every position.
+		const double w0 = c->cfg.alpha_dpm / (gen + 1) / gen;         // gen_post_prob, DPMM.c:369: a new cluster
+		int p = -1;
+		const double u = rng.uniform();
 		if (gen >= 1 && gen <= 50) {
-			const double *w = c->dp_w.data() + gen;
-			for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++) { cum[n] = cum[n - 1] + c->dp[p].num * w[(size_t)p * 51]; node[n] = p; }
-		} else
-			for (int p = c->dp_head; p >= 0; p = c->dp[p].next, n++) { cum[n] = cum[n - 1] + c->dp[p].num * dp_dgeom(c, p, gen); node[n] = p; }
-		const int pick = pick_weighted(cum, n, rng.uniform());
-		if (pick == 0) {                                              // sample_poster, DPMM.c:395: Beta(G, 2)
+			// num * dgeom(value, G_j), DPMM.c:373, from the per-cluster tables
+			const double t = u * (w0 + T[gen]);
+			if (t > w0) {
+				double cum = w0;
+				int last = -1;
+				for (int q = c->dp_head; q >= 0; q = c->dp[q].next) {
+					cum += c->dp[q].num * c->dp_w[(size_t)q * 51 + gen];
+					last = q;
+					if (t <= cum) break;
+				}
+				p = last;                                             // none left (one individual, no cluster): p stays -1 -> new cluster
+			}
+		} else {
+			// the reference's mode-3 initial G is not capped (mcmc.c:329-331): a G beyond the tables is evaluated directly
+			double tot = w0;
+			for (int q = c->dp_head; q >= 0; q = c->dp[q].next) tot += c->dp[q].num * dp_dgeom(c, q, gen);
+			const double t = u * tot;
+			if (t > w0) {
+				double cum = w0;
+				for (int q = c->dp_head; q >= 0; q = c->dp[q].next) { cum += c->dp[q].num * dp_dgeom(c, q, gen); p = q; if (t <= cum) break; }
+			}
+		}
+		if (p < 0) {                                                  // sample_poster, DPMM.c:395: Beta(G, 2)
 			Stream st((uint32_t)j, 1u, c->iter, TAG_DP, c->key0, c->key1);
 			c->S_h[j] = draw_beta(st, (double)gen, 2.0);
-			c->dp_of[j] = dp_create(c, c->S_h[j]);
+			p = dp_create(c, c->S_h[j]);
+			c->dp_of[j] = p;
 			c->dp_cnt++;
 		} else {
-			const int p = node[pick];
 			c->dp[p].num++; c->dp_of[j] = p; c->S_h[j] = c->dp[p].value;
 		}
+		const double *w = &c->dp_w[(size_t)p * 51];
+		for (int gg = 1; gg <= 50; gg++) T[gg] += w[gg];
 	}
 }
 
@@ -618,9 +649,12 @@ static ig_status phase_update_S(ig_ctx *c)
 			CK(cudaEventRecord(c->ev_g, c->stream));
 			c->launches++;
 		}
+		const double tw0 = c->ptrace.empty() ? 0.0 : wall_ms();
 		CK(cudaEventSynchronize(c->ev_g));
 		c->g8_inflight = false;
+		const double tw1 = c->ptrace.empty() ? 0.0 : wall_ms();
 		dp_update(c, c->g8_host);
+		if (!c->ptrace.empty()) { c->ptrace_host_ms[5] += tw1 - tw0; c->ptrace_host_ms[6] += wall_ms() - tw1; }
 		// the previous sweep's copy out of S_pin has long completed: pre_sweep consumed S before the epilogue whose G we just read
 		memcpy(c->S_pin, c->S_h.data(), (size_t)g.N * sizeof(double));
 		CK(cudaMemcpyAsync(c->S, c->S_pin, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -712,6 +746,7 @@ static void ptrace_report(ig_ctx *c)
 	for (int p = 0; p + 1 < PT_POINTS; p++) fprintf(stderr, " %s %.1f |", names[p], 1e3 * acc[p] / n);
 	fprintf(stderr, " between sweeps %.1f || host enqueue us per sweep:", 1e3 * between / (n > 1 ? n - 1 : 1));
 	for (int p = 0; p < 4; p++) fprintf(stderr, " %.1f", 1e3 * c->ptrace_host_ms[p] / (c->ptrace_host_ms[4] > 0 ? c->ptrace_host_ms[4] : 1.0));
+	if (c->ptrace_host_ms[6] > 0) fprintf(stderr, " (DP prior: wait for G %.1f, scan %.1f)", 1e3 * c->ptrace_host_ms[5] / c->ptrace_host_ms[4], 1e3 * c->ptrace_host_ms[6] / c->ptrace_host_ms[4]);
 	fprintf(stderr, "\n");
 }
 

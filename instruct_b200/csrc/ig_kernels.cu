@@ -354,6 +354,10 @@ __global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) pre_sweep_ker
 cudaError_t launch_pre_sweep(const PreArgs &a, cudaStream_t s)
 {
 	if (a.geo.N <= SC1_THREADS) { pre_sweep_kernel<false><<<1, SC1_THREADS, 0, s>>>(a); return cudaGetLastError(); }
+	if (a.mode != 2) {       // only update_S_POP has sums over the individuals: the other modes are independent per individual -- a plain grid
+		pre_sweep_kernel<false><<<(a.geo.N + SC1_THREADS - 1) / SC1_THREADS, SC1_THREADS, 0, s>>>(a);
+		return cudaGetLastError();
+	}
 	void *args[] = {(void *)&a};
 	return cudaLaunchCooperativeKernel((const void *)pre_sweep_kernel<true>, dim3(a.grid), dim3(SC_THREADS), args, 0, s);
 }
