@@ -92,7 +92,14 @@ static ig_status nccl_load()
 		if (r_ != ncclSuccess) return fail(IG_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r_)); \
 	} while (0)
 
+constexpr int FX_POST = 32, LOCAL_MAX_K = 10;      // layout of ig_ctx::fx: the post-sweep sums, then 2^K subset sums of (value, counts)
 constexpr int PT_POINTS = 7, PT_SWEEPS = 64;        // IG_PHASE_TRACE: events per sweep, sweeps traced
+static bool getenv_once(const char *name)
+{
+	// (a handful of debugging switches; looked up per call -- getenv is a short list walk, not on any device-side path)
+	const char *v = getenv(name);
+	return v && *v && *v != '0';
+}
 static void ptrace_report(ig_ctx *c);
 
 extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
@@ -164,7 +171,7 @@ static void free_all(ig_ctx *c)
 	cudaFree(c->Xt); cudaFree(c->Zt); cudaFree(c->P); cudaFree(c->P64); cudaFree(c->n); cudaFree(c->allelenum);
 	cudaFree(c->ind); cudaFree(c->Qf); cudaFree(c->gprop); cudaFree(c->gpair); cudaFree(c->S); cudaFree(c->state);
 	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->pnsh); cudaFree(c->nhet); cudaFree(c->nsh); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
-	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2);
+	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2); cudaFree(c->S2); cudaFree(c->fx);
 	cudaFree(c->fprop); cudaFree(c->hpair); cudaFree(c->ftab); cudaFree(c->pfk);
 	cudaFree(c->logP); cudaFree(c->na_pll);
 	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
@@ -241,6 +248,8 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	c->grid_pre = scalar_grid(0, g.N, c->cfg.device);
 	c->grid_post = scalar_grid(1, g.N, c->cfg.device);
 	CK(dalloc(&c->state2, (size_t)MAX_K));
+	CK(dalloc(&c->S2, (size_t)MAX_K));
+	CK(dalloc(&c->fx, (size_t)FX_POST + 2 * ((size_t)1 << LOCAL_MAX_K)));
 	if (c->cfg.mode == 0) { ig_status st0 = na_alloc(c); if (st0 != IG_OK) return st0; }
 	if (g.fmode) {
 		CK(dalloc(&c->fprop, (size_t)(c->ns > g.K ? c->ns : g.K)));
@@ -249,13 +258,13 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 		if (g.fmode == 2) CK(dalloc(&c->pfk, (size_t)g.nchunks * g.Nloc * 2 * g.KP));
 	}
 	CK(dalloc(&c->mom.tot, 2));
-	CK(dalloc(&c->mom.indvlkh, (size_t)g.N));
-	CK(dalloc(&c->mom.qq, (size_t)g.N * g.K));
-	CK(dalloc(&c->mom.qq2, (size_t)g.N * g.K));
+	CK(dalloc(&c->mom.indvlkh, (size_t)c->Npad));
+	CK(dalloc(&c->mom.qq, (size_t)c->Npad * g.K));
+	CK(dalloc(&c->mom.qq2, (size_t)c->Npad * g.K));
 	CK(dalloc(&c->mom.self, (size_t)c->ns));
 	CK(dalloc(&c->mom.self2, (size_t)c->ns));
-	CK(dalloc(&c->mom.gen, (size_t)g.N));
-	CK(dalloc(&c->mom.gen2, (size_t)g.N));
+	CK(dalloc(&c->mom.gen, (size_t)c->Npad));
+	CK(dalloc(&c->mom.gen2, (size_t)c->Npad));
 	CK(dalloc(&c->mom.convg, (size_t)(c->cfg.ckrep > 0 ? c->cfg.ckrep : 1)));
 	if (c->cfg.print_freq) {
 		CK(dalloc(&c->mom.freq, (size_t)g.K * g.L * g.A));
@@ -334,14 +343,16 @@ extern "C" ig_status ig_comm_unique_id(void *id128)
 extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 {
 	if (!c || !id128) return fail(IG_ERR_ARG, "null argument");
-	if (c->cfg.shard_count <= 1) return IG_OK;
+	// IG_COMM_SINGLE=1: a one-rank communicator, so that the whole sharded code path (side-stream P draw, local scalar
+	// updates, gathers) can be exercised -- and compared with the plain path -- on one GPU (tests/test_gpu_local_scalars.py)
+	if (c->cfg.shard_count <= 1 && !getenv_once("IG_COMM_SINGLE")) return IG_OK;
 	ig_status st = nccl_load();
 	if (st != IG_OK) return st;
 	CK(cudaSetDevice(c->cfg.device));
 	ig_alloc_stream = c->stream;
 	ncclUniqueId id;
 	memcpy(&id, id128, 128);
-	NCK(g_nccl.CommInitRank(&c->comm, c->cfg.shard_count, id, c->cfg.shard_rank));
+	NCK(g_nccl.CommInitRank(&c->comm, c->cfg.shard_count > 1 ? c->cfg.shard_count : 1, id, c->cfg.shard_count > 1 ? c->cfg.shard_rank : 0));
 	// (measured at 2 GPUs: no difference -- the all-gather does not queue behind the tally all-reduce; off by default)
 	if (g_nccl.CommSplit && getenv("IG_TWO_COMMS")) {
 		if (g_nccl.CommSplit(c->comm, 0, c->cfg.shard_rank, &c->comm2, nullptr) != ncclSuccess) c->comm2 = nullptr;
@@ -353,6 +364,9 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 		CK(dalloc(&c->Pnext, (size_t)c->geo.Lpad * c->geo.A * c->geo.KP));
 		if (c->geo.snp) CK(dalloc(&c->Pcnext, snp_pc_floats(c->geo)));
 	}
+	// modes 1 and 2 keep the records local (IG_GATHER_RECORDS=1: the all-gather path of round 1, kept for comparison)
+	c->local_scalars = !c->tetra && c->loaded && (c->cfg.mode == 1 || c->cfg.mode == 2) && c->geo.fmode == 0 &&
+	                   c->geo.K <= LOCAL_MAX_K && !getenv("IG_GATHER_RECORDS");
 	return IG_OK;
 }
 
@@ -400,6 +414,17 @@ static ig_status exchange_individuals(ig_ctx *c)
 	const size_t cnt = (size_t)c->shard_cap * g.REC;
 	NCK(g_nccl.AllGather(c->ind + (size_t)g.i0 * g.REC, c->ind, cnt, ncclDouble, c->comm, c->stream));
 	return IG_OK;
+}
+
+// A sharded chain with local scalar updates leaves other ranks' records stale between sweeps; whatever reads or edits the
+// records from outside a sweep (state hooks, phase hooks, stand-alone evaluators) gathers them first.  Collective: in that
+// mode every rank has to make the same hook calls (they already must for the phase hooks).
+static ig_status ensure_records(ig_ctx *c)
+{
+	c->tree_ready = false;
+	if (!c->comm || !c->ind_stale) return IG_OK;
+	c->ind_stale = false;
+	return exchange_individuals(c);
 }
 
 // --------------------------------------------------------------------------------------
@@ -659,6 +684,25 @@ static ig_status phase_update_S(ig_ctx *c)
 		memcpy(c->S_pin, c->S_h.data(), (size_t)g.N * sizeof(double));
 		CK(cudaMemcpyAsync(c->S, c->S_pin, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	}
+	if (c->local_now) {
+		// update_S_POP + the G proposals on the local records: subset sums (unless they were taken behind the previous
+		// sweep's post sums and travelled with that all-reduce), one int64 all-reduce, the K decisions
+		TreeArgs t{c->ind, c->S, c->state, c->geo, c->iter, c->key0, c->key1, c->cfg.back_refl, c->fx + FX_POST,
+		           c->S2, c->state2, c->gprop, c->gpair, c->sc};
+		if (!c->tree_ready) {
+			const size_t nt = 2 * ((size_t)1 << g.K);
+			CK(cudaMemsetAsync(c->fx + FX_POST, 0, nt * sizeof(unsigned long long), c->stream));
+			CK(launch_spop_tree(t, c->stream));
+			NCK(g_nccl.AllReduce(c->fx + FX_POST, c->fx + FX_POST, nt, ncclInt64, ncclSum, c->comm, c->stream));
+			c->launches++;
+		}
+		c->tree_ready = false;
+		CK(launch_spop_decide(t, c->stream));
+		std::swap(c->S, c->S2);
+		if (c->cfg.back_refl == 0) std::swap(c->state, c->state2);
+		c->launches++;
+		return IG_OK;
+	}
 	// UPMCMC.state is read by every CTA and written by one: double-buffered
 	PreArgs a{c->ind, c->S, c->state, c->state2, c->gprop, c->gpair, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1,
 	          c->cfg.mode, c->cfg.prior_flag, c->cfg.back_refl, c->iter_dev, c->fprop, c->hpair, c->ftab, c->grid_pre};
@@ -704,8 +748,11 @@ static ig_status phase_zq(ig_ctx *c, int init)
 	c->launches += 2;
 	if (c->geo.fmode == 2 && !init) { CK(launch_fk_epilogue(e, c->stream)); c->launches++; }
 	if (!init) ptrace_mark(c, 4);
-	ig_status stx = exchange_individuals(c);
-	if (stx != IG_OK) return stx;
+	if (c->local_now) c->ind_stale = true;                  // the records stay on their rank
+	else {
+		ig_status stx = exchange_individuals(c);
+		if (stx != IG_OK) return stx;
+	}
 	if (c->cfg.mode == 3 && c->cfg.prior_flag == 1 && c->g8_dev && c->more_follow && !c->iter_dev) {
 		// the next sweep's Dirichlet-process scan needs this G: send it now, the host reads it while post_sweep and the
 		// next p_dirichlet run
@@ -723,6 +770,27 @@ static ig_status phase_alpha(ig_ctx *c)
 	// mode 4: pre_sweep left the proposed adaptive-independence states in state2 (-e 0)
 	PostArgs a{c->ind, c->sc, c->gpart, c->geo, c->iter, c->key0, c->key1, c->iter_dev, c->cfg.mode, c->cfg.back_refl,
 	           c->S, c->fprop, c->state, c->state2, c->grid_post};
+	if (c->local_now) {
+		// local sums -> all-reduce -> tail.  When another sweep follows, ITS subset sums of update_S_POP are taken now (S, Q
+		// and G are final for this sweep; the proposals are a function of S and the next sweep's Philox streams) and ride
+		// the same all-reduce: one exchange of a few KB per sweep.
+		const Geometry &g = c->geo;
+		const bool ahead = c->more_follow && c->cfg.mode == 2 && !getenv_once("IG_NO_TREE_AHEAD");
+		const size_t nt = ahead ? 2 * ((size_t)1 << g.K) : 0;
+		CK(cudaMemsetAsync(c->fx, 0, (FX_POST + nt) * sizeof(unsigned long long), c->stream));
+		CK(launch_post_local(a, c->fx, c->stream));
+		if (ahead) {
+			TreeArgs t{c->ind, c->S, c->state, c->geo, c->iter + 1, c->key0, c->key1, c->cfg.back_refl, c->fx + FX_POST,
+			           nullptr, nullptr, nullptr, nullptr, nullptr};
+			CK(launch_spop_tree(t, c->stream));
+			c->launches++;
+		}
+		NCK(g_nccl.AllReduce(c->fx, c->fx, ahead ? FX_POST + nt : (size_t)(g.K + 4), ncclInt64, ncclSum, c->comm, c->stream));
+		CK(launch_post_final(a, c->fx, c->stream));
+		c->tree_ready = ahead;
+		c->launches += 2;
+		return IG_OK;
+	}
 	CK(launch_post_sweep(a, c->stream));
 	c->launches++;
 	return IG_OK;
@@ -755,6 +823,9 @@ static ig_status one_sweep_direct(ig_ctx *c)
 	ig_status st;
 	if (c->tetra) return tetra_one_sweep(c);
 	c->iter++;
+	c->local_now = c->comm && c->local_scalars;
+	if (!c->local_now) c->tree_ready = false;
+	struct LocalGuard { ig_ctx *c; ~LocalGuard() { c->local_now = false; } } local_guard{c};
 	const bool tr = !c->ptrace.empty();
 	double h0 = tr ? wall_ms() : 0.0, h1;
 	ptrace_mark(c, 0);
@@ -846,6 +917,8 @@ extern "C" ig_status ig_chain_init(ig_ctx *c, int32_t chain_id, const float *ini
 	if (c->stream2) CK(cudaStreamSynchronize(c->stream2));
 	c->early_p = false;
 	c->p_wait = false;
+	c->tree_ready = false;
+	c->ind_stale = false;
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // the chain's RNG key is baked into the captured arguments
 	float init_h[MAX_K];
 	for (int k = 0; k < MAX_K; k++) init_h[k] = (initd && k < g.K) ? initd[k] : 0.5f;
@@ -938,6 +1011,7 @@ extern "C" ig_status ig_run_phase(ig_ctx *c, int32_t mask)
 	if (c->tetra) return tetra_run_phase(c, mask);
 	c->dev_iter_valid = false;
 	c->g8_inflight = false;
+	if ((st = ensure_records(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_UPDATE_P) if ((st = phase_update_P(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_UPDATE_S) if ((st = phase_update_S(c)) != IG_OK) return st;
 	if (mask & IG_PHASE_ZQ) if ((st = phase_zq(c, 0)) != IG_OK) return st;
@@ -953,6 +1027,17 @@ static ig_status download_result(ig_ctx *c, ig_chain_result *out, double *convg_
 {
 	const Geometry &g = c->geo;
 	double tot[2];
+	if (c->mom_local) {
+		// every rank advanced the moments of its own individuals: one all-gather per array, at the chain's end
+		ig_status st;
+		const size_t cap = (size_t)c->shard_cap;
+		if ((st = ig_allgather_double(c, c->mom.indvlkh, cap)) != IG_OK) return st;
+		if ((st = ig_allgather_double(c, c->mom.gen, cap)) != IG_OK) return st;
+		if ((st = ig_allgather_double(c, c->mom.gen2, cap)) != IG_OK) return st;
+		if ((st = ig_allgather_double(c, c->mom.qq, cap * g.K)) != IG_OK) return st;
+		if ((st = ig_allgather_double(c, c->mom.qq2, cap * g.K)) != IG_OK) return st;
+		c->mom_local = false;
+	}
 	CK(cudaMemcpyAsync(tot, c->mom.tot, sizeof(tot), cudaMemcpyDeviceToHost, c->stream));
 #define DL(dst, src, n) \
 	if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream))
@@ -997,7 +1082,10 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 		if (!c->mom.convg_S) CK(dalloc(&c->mom.convg_S, (size_t)cf.ckrep * g.K));
 		else CK(cudaMemsetAsync(c->mom.convg_S, 0, (size_t)cf.ckrep * g.K * sizeof(double), c->stream));
 	}
-	MomArgs m{c->ind, c->S, c->sc, c->P, c->mom, g, c->ns, 0, -1, cf.print_freq, cf.print_freq ? c->P64 : nullptr};
+	// records local to their rank: each rank advances the moments of its own individuals, gathered once by download_result
+	c->mom_local = c->comm && c->local_scalars;
+	MomArgs m{c->ind, c->S, c->sc, c->P, c->mom, g, c->ns, 0, -1, cf.print_freq, cf.print_freq ? c->P64 : nullptr,
+	          c->mom_local ? g.i0 : 0, c->mom_local ? g.Nloc : g.N};
 	const long print_every = cf.update >= 100 ? cf.update / 100 : 1;   // print_info, mcmc.c:1273 (guards the /0 of App. B #7)
 	for (long step = 0; step < cf.update; step++) {
 		c->more_follow = step + 1 < cf.update;
@@ -1023,6 +1111,7 @@ extern "C" ig_status ig_run_chain(ig_ctx *c, int32_t chain_id, const float *init
 		if (step >= cf.burnin && (step + 1 - cf.burnin) % cf.thinning == 0) {    // mcmc.c:220-226
 			m.step = cnt_step;
 			m.P = c->P;
+			m.S = c->S;
 			m.convg_slot = (cnt_step < cf.ckrep) ? (int)cnt_step : -1;
 			CK(launch_moments(m, c->stream));
 			c->launches++;
@@ -1120,6 +1209,7 @@ extern "C" ig_status ig_get_state(ig_ctx *c, int32_t id, void *host, size_t byte
 	CK(cudaSetDevice(c->cfg.device));
 	const Geometry &g = c->geo;
 	ig_status st;
+	if ((st = ensure_records(c)) != IG_OK) return st;
 	CK(cudaStreamSynchronize(c->stream));
 	if (c->tetra) {
 		bool handled = false;
@@ -1279,6 +1369,7 @@ extern "C" ig_status ig_set_state(ig_ctx *c, int32_t id, const void *host, size_
 	CK(cudaSetDevice(c->cfg.device));
 	const Geometry &g = c->geo;
 	ig_status st;
+	if ((st = ensure_records(c)) != IG_OK) return st;
 	CK(cudaStreamSynchronize(c->stream));
 	c->g8_inflight = false;
 	if (c->tetra) {
@@ -1411,6 +1502,7 @@ extern "C" ig_status ig_proposal_loglik(ig_ctx *c, const double *S, double *out)
 	if (!c->loaded) return fail(IG_ERR_STATE, "load genotypes first");
 	if (c->cfg.mode != 2) return fail(IG_ERR_ARG, "proposal() is the mode-2 likelihood (mcmc.c:1630)");
 	CK(cudaSetDevice(c->cfg.device));
+	{ ig_status str = ensure_records(c); if (str != IG_OK) return str; }
 	CK(cudaMemcpyAsync(c->scratch, S, (size_t)c->geo.K * 8, cudaMemcpyHostToDevice, c->stream));
 	CK(launch_proposal_ll(c->ind, c->scratch, c->scratch + 32, c->geo, c->stream));
 	CK(cudaMemcpyAsync(out, c->scratch + 32, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1426,6 +1518,7 @@ extern "C" ig_status ig_alpha_logratio(ig_ctx *c, double ralpha, double *out)
 	// sum log q is maintained per individual in the record; reduce it with the same kernel the
 	// sweep uses, on a scratch copy of the scalars so that alpha itself is not advanced
 	DevScalars keep;
+	{ ig_status str = ensure_records(c); if (str != IG_OK) return str; }
 	CK(cudaStreamSynchronize(c->stream));
 	CK(copy_sync(c, &keep, c->sc, sizeof(keep), cudaMemcpyDeviceToHost));
 	PostArgs a{c->ind, c->sc, c->gpart, c->geo, 0xFFFFFFFFu, c->key0, c->key1, nullptr, c->cfg.mode, c->cfg.back_refl,

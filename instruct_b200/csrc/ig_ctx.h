@@ -112,6 +112,16 @@ struct ig_ctx {
 	bool early_p = false;            // Pnext holds the P of sweep iter + 1 and n has been consumed
 	bool p_wait = false;             // the main stream has not yet waited for that draw (it does before zq_sweep)
 	bool more_follow = false;        // another sweep follows inside the current API call
+	// Local scalar updates (modes 1-2, K <= 10): a sharded chain keeps each individual's record on its own rank only; the
+	// sums update_S_POP / update_alpha / cal_lkh need are fixed-point int64 sums of the local individuals, all-reduced
+	// (ig_kernels.cu spop_tree_kernel).  The records are gathered on demand (state hooks) and the moments at the chain's end.
+	bool local_scalars = false;      // this context runs its sweeps that way
+	bool local_now = false;          // ... and is inside such a sweep (the phase hooks always use the gathered path)
+	bool ind_stale = false;          // other ranks' records in `ind` are older than the last sweep
+	bool mom_local = false;          // the running moments of other ranks' individuals live on those ranks
+	bool tree_ready = false;         // fx holds the all-reduced subset sums for sweep iter + 1 (computed behind the previous post_sweep)
+	unsigned long long *fx = nullptr;   // [32] post sums | [2^K][2] subset sums
+	double *S2 = nullptr;            // double buffer of S (every CTA of the decide kernel reads S, CTA 0 writes it)
 	// IG_PHASE_TRACE=1: CUDA events at the phase boundaries of the first 64 sweeps, averages printed by ig_destroy
 	std::vector<cudaEvent_t> ptrace;
 	int ptrace_sweeps = 0;

@@ -170,11 +170,25 @@ struct PostArgs {
 	int grid;                // cooperative grid size of this context
 };
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
+// the same in two halves around an int64 all-reduce (sharded chains with local records): acc[K + 4]
+cudaError_t launch_post_local(const PostArgs &a, unsigned long long *acc, cudaStream_t s);
+cudaError_t launch_post_final(const PostArgs &a, const unsigned long long *acc, cudaStream_t s);
+
+// update_S_POP of a sharded chain on the local records: proposal() summed for all 2^K subsets of replaced rates
+// (acc[2^K][2]: fixed-point sum, -inf / NaN counts), and, after the all-reduce, the K decisions + the local G proposals
+struct TreeArgs {
+	const double *ind; const double *S; const int32_t *state; Geometry geo; uint32_t iter, key0, key1; int back_refl;
+	unsigned long long *acc;
+	double *S_out; int32_t *state_out; int32_t *gprop; int2 *gpair; DevScalars *sc;      // decide only
+};
+cudaError_t launch_spop_tree(const TreeArgs &a, cudaStream_t s);
+cudaError_t launch_spop_decide(const TreeArgs &a, cudaStream_t s);
 
 struct MomArgs {
 	const double *ind; const double *S; const DevScalars *sc; const float *P; Moments m;
 	Geometry geo; int ns; long step; int convg_slot; int print_freq;
 	const double *P64;       // print_freq: the allele frequencies in double, [K][L][A], as p_dirichlet drew them (the fp32 sweep copy is floored and rounded)
+	int i_lo, n_ind;         // individuals whose moments this launch advances: all N, or the shard's own when the records are local
 };
 cudaError_t launch_moments(const MomArgs &a, cudaStream_t s);
 cudaError_t launch_moments_reset(const MomArgs &a, cudaStream_t s);

@@ -142,31 +142,36 @@ constexpr int SC_THREADS = 256;                 // cooperative shape
 constexpr int SC1_THREADS = 1024;               // single-CTA shape
 constexpr int SC_MAXV = 20;                     // values reduced at once (K + 2 <= 18)
 
-__device__ __forceinline__ double warp_sum(double v)
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
 {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
 	return v;
 }
 
-struct ScShared {
-	double warp[SC_MAXV][32];
-	double total[SC_MAXV];
+template <typename T>
+struct ScSharedT {
+	T warp[SC_MAXV][32];
+	T total[SC_MAXV];
 };
+typedef ScSharedT<double> ScShared;
 
-// reduce nv per-thread values over all threads of the launch; the result lands in out[0..nv) for every thread
-template <bool COOP>
-__device__ void all_sum(const double *v, int nv, double *out, ScShared &sh, double *gpart, int &phase)
+// reduce nv per-thread values over all threads of the launch; the result lands in out[0..nv) for every thread.
+// T = double: fixed shape, fixed order.  T = long long: the fixed-point sums below, exact in any order.
+template <bool COOP, typename T>
+__device__ void all_sum(const T *v, int nv, T *out, ScSharedT<T> &sh, double *gpart_, int &phase)
 {
+	T *gpart = reinterpret_cast<T *>(gpart_);
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
 	for (int j = 0; j < nv; j++) {
-		const double w = warp_sum(v[j]);
+		const T w = warp_sum(v[j]);
 		if (lane == 0) sh.warp[j][wid] = w;
 	}
 	__syncthreads();
-	double *buf = COOP ? gpart + (size_t)(phase & 1) * gridDim.x * SC_MAXV : nullptr;
+	T *buf = COOP ? gpart + (size_t)(phase & 1) * gridDim.x * SC_MAXV : nullptr;
 	if (tid < nv) {
-		double t = 0.0;
+		T t = 0;
 		for (int w = 0; w < nwarps; w++) t += sh.warp[tid][w];
 		if (COOP) buf[(size_t)blockIdx.x * SC_MAXV + tid] = t;
 		else sh.total[tid] = t;
@@ -175,7 +180,7 @@ __device__ void all_sum(const double *v, int nv, double *out, ScShared &sh, doub
 		__threadfence();
 		cg::this_grid().sync();
 		if (tid < nv) {
-			double t = 0.0;
+			T t = 0;
 			for (unsigned b = 0; b < gridDim.x; b++) t += buf[(size_t)b * SC_MAXV + tid];
 			sh.total[tid] = t;
 		}
@@ -184,6 +189,76 @@ __device__ void all_sum(const double *v, int nv, double *out, ScShared &sh, doub
 	for (int j = 0; j < nv; j++) out[j] = sh.total[j];
 	__syncthreads();
 	phase++;                                     // COOP: the partials are double-buffered, one grid.sync() per reduction suffices
+}
+
+// --------------------------------------------------------------------------------------
+// Fixed-point sums.  The sums over individuals that DECIDE something (the K Metropolis steps of update_S_POP, the alpha
+// step) or that are reported (totallkh, the column sums of Q) are taken over integers: every term is rounded once to a
+// multiple of 2^-s and the integers are added -- exact in any order, so the result is the same for every grid shape and for
+// every split of the individuals over GPUs.  That is what lets a sharded chain add its LOCAL individuals and all-reduce a
+// few int64 instead of all-gathering every individual's record to every rank (ig_api.cu, local scalar updates), and stay
+// bit-identical to the one-GPU chain.  -inf and NaN terms (log 0: a selfing rate of exactly 0 or 1, a q that underflowed)
+// are carried as counts (low / high half of a second integer), because the reference's accept rules depend on them
+// (MIN2(1, NaN) == 1, mcmc.h:10).  Ranges: |sum| < 2^63 / scale: 8.6e9 for the log-scale sums, 5.5e11 for totallkh,
+// 8.4e6 individuals for the column sums.
+// --------------------------------------------------------------------------------------
+constexpr double FX_LL = 1073741824.0;            // 2^30: log( s^(g-1) (1-s) ) terms of proposal()
+constexpr double FX_LKH = 16777216.0;             // 2^24: indvlkh (|.| ~ L)
+constexpr double FX_SLQ = 268435456.0;            // 2^28: sum_k log q_ik
+constexpr double FX_Q = 1099511627776.0;          // 2^40: q_ik in [0, 1]
+__device__ __forceinline__ void fx_add(long long &acc, long long &cnt, double x, double scale)
+{
+	if (x != x) cnt += 1ll << 32;
+	else if (x == INFINITY || x == -INFINITY) cnt += (x < 0.0) ? 1ll : (1ll << 32);      // +inf cannot arise from these terms; were it to, it poisons the sum like a NaN
+	else acc += __double2ll_rn(x * scale);
+}
+__device__ __forceinline__ double fx_val(long long acc, long long cnt, double scale)
+{
+	if (cnt >> 32) return NAN;
+	if (cnt) return -INFINITY;
+	return (double)acc * (1.0 / scale);
+}
+// s_i = sum_k q_ik S_k, one fixed sequence of FMAs wherever it is evaluated
+__device__ __forceinline__ double mix_rate(const double *rec, const double *Sv, int K)
+{
+	double s = 0.0;
+	for (int k = 0; k < K; k++) s = fma(rec[k], Sv[k], s);
+	return s;
+}
+
+// one Metropolis step of update_S_POP (mcmc.c:913-983), split so that the sequential kernel and the subset-sum kernels of the
+// sharded chain consume the step's Philox stream identically: the proposal first ...
+__device__ __forceinline__ void spop_propose(double sj, int cs, int back_refl, Stream &st, double &prop, int &new_state)
+{
+	new_state = 1;
+	if (back_refl == 1) {                           // mcmc.c:939-945
+		prop = sj + (st.uniform() * 2.0 * 0.05 - 0.05);
+		if (prop <= 0.0) prop = -prop;
+		else if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
+	} else {                                        // adpt_indp, mcmc.c:1461-1520
+		const double u = st.uniform();
+		if (cs == 0) { if (u < 0.5) { prop = 0.0; new_state = 0; } else { prop = st.uniform(); new_state = 1; } }
+		else if (cs == 2) { if (u < 0.5) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
+		else { if (u <= 0.05) { prop = 0.0; new_state = 0; } else if (u >= 0.95) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
+	}
+}
+// ... then the accept from proposal() at the current and the proposed rates
+__device__ __forceinline__ bool spop_accept(double cur, double pl, int cs, int new_state, int back_refl, Stream &st)
+{
+	double ratio = exp(pl - cur);
+	if (back_refl == 0) ratio *= trans_prob(cs, new_state) / trans_prob(new_state, cs);
+	const double u = st.uniform();
+	// MIN2(1, NaN) == 1 in the reference (mcmc.h:10): a NaN ratio accepts
+	return (ratio != ratio) || (u < fmin(1.0, ratio));
+}
+// generation proposal of update_G (mcmc.c:1062-1084) for individual i (global index) at selfing rate s
+__device__ __forceinline__ int g_propose(double s, int i, uint32_t iter, uint32_t key0, uint32_t key1)
+{
+	const int stt = sel_state(s);
+	if (stt != 1) return (stt == 0) ? 1 : 50;
+	Stream st((uint32_t)i, 0u, iter, TAG_GPROP, key0, key1);
+	const double v = floor(log(st.uniform()) / log(s)) + 1.0;    // rgeom(1 - s), random.c:311-321
+	return (v < 1.0) ? 1 : (v > 50.0 ? 50 : (int)v);
 }
 
 // --------------------------------------------------------------------------------------
@@ -255,70 +330,50 @@ __global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) pre_sweep_ker
 		return;
 	}
 	if (a.mode == 2) {
+		ScSharedT<long long> &shl = reinterpret_cast<ScSharedT<long long> &>(sh);
 		if (tid < K) Ssh[tid] = a.S[tid];
 		__syncthreads();
-		double Sl[MAX_K];
-		for (int k = 0; k < K; k++) Sl[k] = Ssh[k];
-		double cur, part = 0.0;
+		double Sl[MAX_K], Sp[MAX_K];
+		for (int k = 0; k < K; k++) Sl[k] = Sp[k] = Ssh[k];
+		long long part[2] = {0, 0}, tot[2];
 		for (int i = i_first; i < g.N; i += gstride) {
 			const double *rec = a.ind + (size_t)i * REC;
-			double s = 0.0;
-			for (int k = 0; k < K; k++) s += rec[k] * Sl[k];
-			part += log_geom(s, (int)rec[K + 2]);
+			fx_add(part[0], part[1], log_geom(mix_rate(rec, Sl, K), (int)rec[K + 2]), FX_LL);
 		}
-		all_sum<COOP>(&part, 1, &cur, sh, a.gpart, phase);
+		all_sum<COOP>(part, 2, tot, shl, a.gpart, phase);
+		double cur = fx_val(tot[0], tot[1], FX_LL);
 		int accepts = 0;
 		for (int j = 0; j < K; j++) {
 			Stream st((uint32_t)j, 0u, iter, TAG_SPOP, a.key0, a.key1);
 			double prop;
-			int new_state = 1;
+			int new_state;
 			const int cs = (a.back_refl == 0) ? a.state_in[j] : 1;
-			const double sj = Sl[j];
-			if (a.back_refl == 1) {                         // mcmc.c:939-945
-				prop = sj + (st.uniform() * 2.0 * 0.05 - 0.05);
-				if (prop <= 0.0) prop = -prop;
-				else if (prop >= 1.0) prop = 1.0 - (prop - 1.0);
-			} else {                                        // adpt_indp, mcmc.c:1461-1520
-				const double u = st.uniform();
-				if (cs == 0) { if (u < 0.5) { prop = 0.0; new_state = 0; } else { prop = st.uniform(); new_state = 1; } }
-				else if (cs == 2) { if (u < 0.5) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
-				else { if (u <= 0.05) { prop = 0.0; new_state = 0; } else if (u >= 0.95) { prop = 1.0; new_state = 2; } else { prop = st.uniform(); new_state = 1; } }
-			}
-			part = 0.0;
+			spop_propose(Sl[j], cs, a.back_refl, st, prop, new_state);
+			Sp[j] = prop;
+			part[0] = part[1] = 0;
 			for (int i = i_first; i < g.N; i += gstride) {
 				const double *rec = a.ind + (size_t)i * REC;
-				double s = 0.0;
-				for (int k = 0; k < K; k++) s += rec[k] * ((k == j) ? prop : Sl[k]);
-				part += log_geom(s, (int)rec[K + 2]);
+				fx_add(part[0], part[1], log_geom(mix_rate(rec, Sp, K), (int)rec[K + 2]), FX_LL);
 			}
-			double pl;
-			all_sum<COOP>(&part, 1, &pl, sh, a.gpart, phase);
+			all_sum<COOP>(part, 2, tot, shl, a.gpart, phase);
+			const double pl = fx_val(tot[0], tot[1], FX_LL);
 			// every thread of every CTA takes the same decision from the same numbers
-			double ratio = exp(pl - cur);
-			if (a.back_refl == 0) ratio *= trans_prob(cs, new_state) / trans_prob(new_state, cs);
-			const double u = st.uniform();
-			// MIN2(1, NaN) == 1 in the reference (mcmc.h:10): a NaN ratio accepts
-			const bool acc = (ratio != ratio) || (u < fmin(1.0, ratio));
+			const bool acc = spop_accept(cur, pl, cs, new_state, a.back_refl, st);
 			if (acc) {
 				cur = pl;
 				Sl[j] = prop;
 				accepts++;
 				if (blockIdx.x == 0 && tid == 0) { a.S[j] = prop; if (a.back_refl == 0) a.state_out[j] = new_state; }
-			} else if (blockIdx.x == 0 && tid == 0 && a.back_refl == 0) a.state_out[j] = cs;
+			} else {
+				Sp[j] = Sl[j];
+				if (blockIdx.x == 0 && tid == 0 && a.back_refl == 0) a.state_out[j] = cs;
+			}
 		}
 		if (blockIdx.x == 0 && tid == 0) { a.sc->cur_prop_ll = cur; a.sc->s_accepts += accepts; }
 		// ---- generation proposals with the UPDATED S (update_G follows update_S_POP, mcmc.c:211-212)
 		for (int i = i_first; i < g.N; i += gstride) {
 			const double *rec = a.ind + (size_t)i * REC;
-			double s = 0.0;
-			for (int k = 0; k < K; k++) s += rec[k] * Sl[k];
-			const int stt = sel_state(s);
-			int gp;
-			if (stt == 1) {
-				Stream st((uint32_t)i, 0u, iter, TAG_GPROP, a.key0, a.key1);
-				const double v = floor(log(st.uniform()) / log(s)) + 1.0;    // rgeom(1 - s), random.c:311-321
-				gp = (v < 1.0) ? 1 : (v > 50.0 ? 50 : (int)v);
-			} else gp = (stt == 0) ? 1 : 50;
+			const int gp = g_propose(mix_rate(rec, Sl, K), i, iter, a.key0, a.key1);
 			a.gprop[i] = gp;
 			const int il = i - g.i0;
 			if (il >= 0 && il < g.Nloc) a.gpair[il] = make_int2((int)rec[K + 2], gp);
@@ -553,6 +608,25 @@ cudaError_t launch_fk_epilogue(const EpiArgs &a, cudaStream_t s)
 // column sums of Q for check_empty_cluster (mcmc.c:1954-1961) -- one grid-wide sum of
 // K + 2 values.
 // --------------------------------------------------------------------------------------
+// the K + 2 sums of post_sweep in fixed point: v[0] totallkh, v[1] sum log q, v[2 + k] column k of Q, v[K + 2] / v[K + 3]
+// the -inf / NaN counts of the first two
+__device__ __forceinline__ void post_terms(const double *rec, int K, long long *v)
+{
+	fx_add(v[0], v[K + 2], rec[K], FX_LKH);
+	fx_add(v[1], v[K + 3], rec[K + 1], FX_SLQ);
+#pragma unroll
+	for (int k = 0; k < MAX_K; k++)
+		if (k < K) v[2 + k] += __double2ll_rn(rec[k] * FX_Q);
+}
+__device__ __forceinline__ void post_totals(const long long *t, int K, double *tot)
+{
+	tot[0] = fx_val(t[0], t[K + 2], FX_LKH);
+	tot[1] = fx_val(t[1], t[K + 3], FX_SLQ);
+	for (int k = 0; k < K; k++) tot[2 + k] = (double)t[2 + k] * (1.0 / FX_Q);
+}
+
+__device__ void post_finish(const PostArgs &a, const double *tot, uint32_t iter);
+
 template <bool COOP>
 __global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) post_sweep_kernel(const PostArgs a)
 {
@@ -561,18 +635,17 @@ __global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) post_sweep_ke
 	const int tid = threadIdx.x, K = g.K, REC = g.REC;
 	const int gstride = gridDim.x * blockDim.x;
 	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
-	double v[SC_MAXV], tot[SC_MAXV];
-#pragma unroll
-	for (int j = 0; j < SC_MAXV; j++) v[j] = 0.0;
-	for (int i = blockIdx.x * blockDim.x + tid; i < g.N; i += gstride) {
-		const double *rec = a.ind + (size_t)i * REC;
-		v[0] += rec[K];
-		v[1] += rec[K + 1];
-#pragma unroll
-		for (int k = 0; k < MAX_K; k++) if (k < K) v[2 + k] += rec[k];
-	}
+	double tot[SC_MAXV];
 	int phase = 0;
-	all_sum<COOP>(v, K + 2, tot, sh, a.gpart, phase);
+	{
+		ScSharedT<long long> &shl = reinterpret_cast<ScSharedT<long long> &>(sh);
+		long long v[SC_MAXV], t[SC_MAXV];
+#pragma unroll
+		for (int j = 0; j < SC_MAXV; j++) v[j] = 0;
+		for (int i = blockIdx.x * blockDim.x + tid; i < g.N; i += gstride) post_terms(a.ind + (size_t)i * REC, K, v);
+		all_sum<COOP>(v, K + 4, t, shl, a.gpart, phase);
+		post_totals(t, K, tot);
+	}
 	if (a.mode == 5)                                        // the accepted F of every individual, from the (all-gathered) records
 		for (int i = blockIdx.x * blockDim.x + tid; i < g.N; i += gstride) a.S[i] = a.ind[(size_t)i * REC + K + 2];
 	if (a.mode == 4 && iter != 0xFFFFFFFFu) {
@@ -622,6 +695,13 @@ __global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) post_sweep_ke
 		}
 	}
 	if (blockIdx.x != 0 || tid != 0) return;
+	post_finish(a, tot, iter);
+}
+
+// the single-thread tail of post_sweep: publish the totals, then update_alpha
+__device__ void post_finish(const PostArgs &a, const double *tot, uint32_t iter)
+{
+	const int K = a.geo.K;
 	const double slq = tot[1];
 	a.sc->totallkh = tot[0];
 	a.sc->sumlogq = slq;
@@ -645,6 +725,144 @@ __global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) post_sweep_ke
 		if (nan_accept || u < fmin(1.0, ratio)) { a.sc->alpha = ralpha; a.sc->alpha_accepts++; }
 	}
 }
+// --------------------------------------------------------------------------------------
+// Local scalar updates of a sharded chain (modes 1 and 2; ig_api.cu local_scalars).  A rank holds the records of its own
+// individuals only.  update_S_POP is K sequential Metropolis steps, but step j's proposal does not depend on the outcome of
+// the earlier steps (it perturbs S_j, which only step j changes) -- only the sums do, through WHICH of S_0 .. S_j-1 were
+// replaced.  So the sum of proposal() is taken for every subset B of replaced populations at once (2^K sums over the local
+// individuals, one launch), ONE int64 all-reduce makes them global and exact, and a single thread per CTA then walks the K
+// decisions through the table: cur = sum[B], proposed = sum[B | 1 << j].  Same Philox streams, same fixed-point sums as the
+// sequential kernel: bit-identical S.
+// --------------------------------------------------------------------------------------
+constexpr int TREE_THREADS = 256;
+__global__ void __launch_bounds__(TREE_THREADS) spop_tree_kernel(const TreeArgs a)
+{
+	__shared__ double Sc[MAX_K];
+	__shared__ long long wsum[2][TREE_THREADS / 32];
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x, K = g.K;
+	const unsigned B = blockIdx.y;
+	if (tid < K) {
+		double sv = a.S[tid];
+		if ((B >> tid) & 1u) {
+			Stream st((uint32_t)tid, 0u, a.iter, TAG_SPOP, a.key0, a.key1);
+			int ns;
+			spop_propose(sv, (a.back_refl == 0) ? a.state[tid] : 1, a.back_refl, st, sv, ns);
+		}
+		Sc[tid] = sv;
+	}
+	__syncthreads();
+	double Sv[MAX_K];
+	for (int k = 0; k < K; k++) Sv[k] = Sc[k];
+	long long v = 0, cn = 0;
+	const int il = blockIdx.x * TREE_THREADS + tid;
+	if (il < g.Nloc) {
+		const double *rec = a.ind + (size_t)(g.i0 + il) * g.REC;
+		fx_add(v, cn, log_geom(mix_rate(rec, Sv, K), (int)rec[K + 2]), FX_LL);
+	}
+	v = warp_sum(v); cn = warp_sum(cn);
+	if ((tid & 31) == 0) { wsum[0][tid >> 5] = v; wsum[1][tid >> 5] = cn; }
+	__syncthreads();
+	if (tid < 2) {
+		long long t = 0;
+		for (int w = 0; w < TREE_THREADS / 32; w++) t += wsum[tid][w];
+		if (t) atomicAdd(a.acc + 2 * (size_t)B + tid, (unsigned long long)t);
+	}
+}
+__global__ void __launch_bounds__(TREE_THREADS) spop_decide_kernel(const TreeArgs a)
+{
+	__shared__ double Sn[MAX_K];
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x, K = g.K;
+	if (tid == 0) {
+		const long long *acc = reinterpret_cast<const long long *>(a.acc);
+		unsigned B = 0;
+		double cur = fx_val(acc[0], acc[1], FX_LL);
+		int accepts = 0;
+		for (int j = 0; j < K; j++) {
+			Stream st((uint32_t)j, 0u, a.iter, TAG_SPOP, a.key0, a.key1);
+			const double sj = a.S[j];
+			const int cs = (a.back_refl == 0) ? a.state[j] : 1;
+			double prop;
+			int new_state;
+			spop_propose(sj, cs, a.back_refl, st, prop, new_state);
+			const unsigned Bp = B | (1u << j);
+			const double pl = fx_val(acc[2 * (size_t)Bp], acc[2 * (size_t)Bp + 1], FX_LL);
+			const bool ok = spop_accept(cur, pl, cs, new_state, a.back_refl, st);
+			if (ok) { B = Bp; cur = pl; accepts++; }
+			Sn[j] = ok ? prop : sj;
+			if (blockIdx.x == 0) {
+				a.S_out[j] = Sn[j];
+				if (a.back_refl == 0) a.state_out[j] = ok ? new_state : cs;
+			}
+		}
+		if (blockIdx.x == 0) { a.sc->cur_prop_ll = cur; a.sc->s_accepts += accepts; }
+	}
+	__syncthreads();
+	double Sv[MAX_K];
+	for (int k = 0; k < K; k++) Sv[k] = Sn[k];
+	const int il = blockIdx.x * TREE_THREADS + tid;
+	if (il >= g.Nloc) return;
+	const int i = g.i0 + il;
+	const double *rec = a.ind + (size_t)i * g.REC;
+	const int gp = g_propose(mix_rate(rec, Sv, K), i, a.iter, a.key0, a.key1);
+	a.gprop[i] = gp;
+	a.gpair[il] = make_int2((int)rec[K + 2], gp);
+}
+cudaError_t launch_spop_tree(const TreeArgs &a, cudaStream_t s)
+{
+	const dim3 grid((a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS, 1u << a.geo.K);
+	spop_tree_kernel<<<grid, TREE_THREADS, 0, s>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_spop_decide(const TreeArgs &a, cudaStream_t s)
+{
+	spop_decide_kernel<<<(a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+// post_sweep in two halves around an int64 all-reduce: the local individuals' K + 4 fixed-point sums, then the tail
+__global__ void __launch_bounds__(TREE_THREADS) post_local_kernel(const PostArgs a, unsigned long long *acc)
+{
+	__shared__ long long wsum[SC_MAXV][TREE_THREADS / 32];
+	const Geometry &g = a.geo;
+	const int tid = threadIdx.x, K = g.K;
+	long long v[SC_MAXV];
+#pragma unroll
+	for (int j = 0; j < SC_MAXV; j++) v[j] = 0;
+	for (int il = blockIdx.x * TREE_THREADS + tid; il < g.Nloc; il += gridDim.x * TREE_THREADS)
+		post_terms(a.ind + (size_t)(g.i0 + il) * g.REC, K, v);
+	for (int j = 0; j < K + 4; j++) {
+		const long long w = warp_sum(v[j]);
+		if ((tid & 31) == 0) wsum[j][tid >> 5] = w;
+	}
+	__syncthreads();
+	if (tid < K + 4) {
+		long long t = 0;
+		for (int w = 0; w < TREE_THREADS / 32; w++) t += wsum[tid][w];
+		if (t) atomicAdd(acc + tid, (unsigned long long)t);
+	}
+}
+__global__ void post_final_kernel(const PostArgs a, const unsigned long long *acc)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	double tot[SC_MAXV];
+	post_totals(reinterpret_cast<const long long *>(acc), a.geo.K, tot);
+	post_finish(a, tot, a.iter);
+}
+cudaError_t launch_post_local(const PostArgs &a, unsigned long long *acc, cudaStream_t s)
+{
+	int grid = (a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS;
+	if (grid > 592) grid = 592;
+	post_local_kernel<<<grid, TREE_THREADS, 0, s>>>(a, acc);
+	return cudaGetLastError();
+}
+cudaError_t launch_post_final(const PostArgs &a, const unsigned long long *acc, cudaStream_t s)
+{
+	post_final_kernel<<<1, 32, 0, s>>>(a, acc);
+	return cudaGetLastError();
+}
+
 // cooperative grid for n_items individuals on `device` (computed once per context)
 int scalar_grid(int which, int n_items, int device)
 {
@@ -678,11 +896,12 @@ __global__ void moments_kernel(const MomArgs a)
 	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	const int K = g.K, REC = g.REC;
 	const long step = a.step;
-	if (t < (long)g.N * K) {
-		const int i = (int)(t / K), k = (int)(t % K);
+	if (t < (long)a.n_ind * K) {
+		const int i = a.i_lo + (int)(t / K), k = (int)(t % K);
 		const double q = a.ind[(size_t)i * REC + k];
-		run_mean(a.m.qq + t, q, step);
-		run_mean(a.m.qq2 + t, q * q, step);
+		const size_t e = (size_t)i * K + k;
+		run_mean(a.m.qq + e, q, step);
+		run_mean(a.m.qq2 + e, q * q, step);
 		if (k == 0) {
 			const double lk = a.ind[(size_t)i * REC + K], gen = a.ind[(size_t)i * REC + K + 2];
 			run_mean(a.m.indvlkh + i, lk, step);
@@ -714,8 +933,9 @@ __global__ void moments_kernel(const MomArgs a)
 }
 cudaError_t launch_moments(const MomArgs &a, cudaStream_t s)
 {
-	long n = (long)a.geo.N * a.geo.K;
+	long n = (long)a.n_ind * a.geo.K;
 	if (a.ns > n) n = a.ns;
+	if (n < 1) n = 1;
 	moments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
 	return cudaGetLastError();
 }

@@ -77,7 +77,7 @@ def test_mode5_fused_pieces(N, L, K, A, miss):
     want = np.where(took, ll_new_p, ll_new)
     assert np.max(np.abs(lk - want) / np.maximum(np.abs(want), 1.0)) <= RTOL
     tot = s.get(_lib.STATE_TOTALLKH)[0]
-    assert abs(tot - lk.sum()) <= 1e-9 * abs(tot)
+    assert abs(tot - lk.sum()) <= 1e-9 * abs(tot) + len(lk) * 2.0 ** -24     # totallkh is a 2^-24 fixed-point sum
     s.close()
 
 
@@ -121,7 +121,7 @@ def test_mode4_fused_pieces(N, L, K, A, miss, back_refl):
     if ok:
         assert np.max(np.abs(lk - want) / np.maximum(np.abs(want), 1.0)) <= RTOL
         tot = s.get(_lib.STATE_TOTALLKH)[0]
-        assert abs(tot - lk.sum()) <= 1e-9 * abs(tot)
+        assert abs(tot - lk.sum()) <= 1e-9 * abs(tot) + len(lk) * 2.0 ** -24     # totallkh is a 2^-24 fixed-point sum
     s.close()
 
 
