@@ -93,7 +93,7 @@ static ig_status nccl_load()
 	} while (0)
 
 constexpr int FX_POST = 32, LOCAL_MAX_K = 10;      // layout of ig_ctx::fx: the post-sweep sums, then 2^K subset sums of (value, counts)
-constexpr int PT_POINTS = 7, PT_SWEEPS = 64;        // IG_PHASE_TRACE: events per sweep, sweeps traced
+constexpr int PT_POINTS = 8, PT_SWEEPS = 64;        // IG_PHASE_TRACE: events per sweep, sweeps traced
 static bool getenv_once(const char *name)
 {
 	// (a handful of debugging switches; looked up per call -- getenv is a short list walk, not on any device-side path)
@@ -101,6 +101,7 @@ static bool getenv_once(const char *name)
 	return v && *v && *v != '0';
 }
 static void ptrace_report(ig_ctx *c);
+static void peer_teardown(ig_ctx *c);
 
 extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 {
@@ -199,6 +200,7 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->S_pin) cudaFreeHost(c->S_pin);
 	if (c->ev_g) cudaEventDestroy(c->ev_g);
 	tetra_destroy(c);
+	peer_teardown(c);
 	free_all(c);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -340,6 +342,62 @@ extern "C" ig_status ig_comm_unique_id(void *id128)
 	return IG_OK;
 }
 
+// Map every rank's exchange buffer into every rank (CUDA IPC; the 64-byte handles travel through the communicator that was
+// just created).  All ranks end up with px == true or all with px == false (then the sums go through ncclAllReduce).
+static void peer_teardown(ig_ctx *c)
+{
+	for (void *p : c->px_mapped) if (p) cudaIpcCloseMemHandle(p);
+	c->px_mapped.clear();
+	if (c->px_peers) { cudaFree(c->px_peers); c->px_peers = nullptr; }
+	// The exported buffer of a multi-rank chain is NOT freed: freeing memory that another process still has mapped is undefined
+	// and there is no cheap point at which every peer is known to have closed it (a barrier here would hang on a dead peer).
+	// It is a few hundred KB per context, returned when the process exits.
+	if (c->px_buf && c->cfg.shard_count <= 1) (cudaFree)(c->px_buf);
+	c->px_buf = nullptr;
+	c->px = false;
+}
+static ig_status peer_setup(ig_ctx *c)
+{
+	const int W = c->cfg.shard_count > 1 ? c->cfg.shard_count : 1, me = W > 1 ? c->cfg.shard_rank : 0;
+	const size_t bytes = px_buffer_words(W) * sizeof(unsigned long long);
+	int bad = 0;
+	if ((cudaMalloc)((void **)&c->px_buf, bytes) != cudaSuccess) { cudaGetLastError(); c->px_buf = nullptr; bad = 1; }
+	if (!bad) { CK(cudaMemsetAsync(c->px_buf, 0, bytes, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+	std::vector<cudaIpcMemHandle_t> hs((size_t)W);
+	memset(hs.data(), 0, hs.size() * sizeof(cudaIpcMemHandle_t));
+	if (!bad && W > 1 && cudaIpcGetMemHandle(&hs[(size_t)me], c->px_buf) != cudaSuccess) { cudaGetLastError(); bad = 1; }
+	char *hd = nullptr;
+	CK(dalloc(&hd, (size_t)W * sizeof(cudaIpcMemHandle_t) + 16));
+	CK(cudaMemcpyAsync(hd + (size_t)me * sizeof(cudaIpcMemHandle_t), &hs[(size_t)me], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice, c->stream));
+	NCK(g_nccl.AllGather(hd + (size_t)me * sizeof(cudaIpcMemHandle_t), hd, sizeof(cudaIpcMemHandle_t), ncclChar, c->comm, c->stream));
+	CK(cudaMemcpyAsync(hs.data(), hd, (size_t)W * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	std::vector<unsigned long long *> peers((size_t)W, nullptr);
+	c->px_mapped.assign((size_t)W, nullptr);
+	for (int r = 0; r < W && !bad; r++) {
+		if (r == me) { peers[(size_t)r] = c->px_buf; continue; }
+		void *p = nullptr;
+		if (cudaIpcOpenMemHandle(&p, hs[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); bad = 1; break; }
+		c->px_mapped[(size_t)r] = p;
+		peers[(size_t)r] = (unsigned long long *)p;
+	}
+	// agree (and make sure every rank's zero fill is complete before anyone stores into a peer): sum of the failures
+	int32_t *flag_dev = reinterpret_cast<int32_t *>(hd + (size_t)W * sizeof(cudaIpcMemHandle_t));
+	CK(cudaMemcpyAsync(flag_dev, &bad, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	NCK(g_nccl.AllReduce(flag_dev, flag_dev, 1, ncclInt32, ncclSum, c->comm, c->stream));
+	int32_t nbad = 0;
+	CK(cudaMemcpyAsync(&nbad, flag_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(hd);
+	if (nbad) { peer_teardown(c); return IG_OK; }
+	CK(dalloc(&c->px_peers, (size_t)W));
+	CK(cudaMemcpyAsync(c->px_peers, peers.data(), (size_t)W * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->px_seq = 0;
+	c->px = true;
+	return IG_OK;
+}
+
 extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 {
 	if (!c || !id128) return fail(IG_ERR_ARG, "null argument");
@@ -366,7 +424,9 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 	}
 	// modes 1 and 2 keep the records local (IG_GATHER_RECORDS=1: the all-gather path of round 1, kept for comparison)
 	c->local_scalars = !c->tetra && c->loaded && (c->cfg.mode == 1 || c->cfg.mode == 2) && c->geo.fmode == 0 &&
-	                   c->geo.K <= LOCAL_MAX_K && !getenv("IG_GATHER_RECORDS");
+	                   c->geo.K <= LOCAL_MAX_K && !getenv_once("IG_GATHER_RECORDS");
+	// ... and all-reduce their sums over peer memory (IG_NCCL_SCALARS=1: through ncclAllReduce, for comparison)
+	if (c->local_scalars && !c->px_buf && !getenv_once("IG_NCCL_SCALARS")) return peer_setup(c);
 	return IG_OK;
 }
 
@@ -611,6 +671,22 @@ static void dp_update(ig_ctx *c, const uint8_t *gen8)   // update_DP, DPMM.c:165
 	}
 }
 
+// int64 all-reduce of fx[off .. off + n) on the main stream: peer-memory kernel (optionally with the post-sweep tail fused) or NCCL
+static ig_status allreduce_fx(ig_ctx *c, size_t off, size_t n, const PostArgs *tail)
+{
+	if (c->px) {
+		PeerArgs x{c->px_peers, c->cfg.shard_count > 1 ? c->cfg.shard_count : 1, c->cfg.shard_count > 1 ? c->cfg.shard_rank : 0,
+		           ++c->px_seq, (int)n, c->fx + off, tail ? 1 : 0};
+		PostArgs none{};
+		CK(launch_peer_allreduce(x, tail ? *tail : none, c->stream));
+		c->launches++;
+		return IG_OK;
+	}
+	NCK(g_nccl.AllReduce(c->fx + off, c->fx + off, n, ncclInt64, ncclSum, c->comm, c->stream));
+	if (tail) { CK(launch_post_final(*tail, c->fx, c->stream)); c->launches++; }
+	return IG_OK;
+}
+
 // --------------------------------------------------------------------------------------
 // sweep phases
 // --------------------------------------------------------------------------------------
@@ -693,8 +769,9 @@ static ig_status phase_update_S(ig_ctx *c)
 			const size_t nt = 2 * ((size_t)1 << g.K);
 			CK(cudaMemsetAsync(c->fx + FX_POST, 0, nt * sizeof(unsigned long long), c->stream));
 			CK(launch_spop_tree(t, c->stream));
-			NCK(g_nccl.AllReduce(c->fx + FX_POST, c->fx + FX_POST, nt, ncclInt64, ncclSum, c->comm, c->stream));
 			c->launches++;
+			ig_status sta = allreduce_fx(c, FX_POST, nt, nullptr);
+			if (sta != IG_OK) return sta;
 		}
 		c->tree_ready = false;
 		CK(launch_spop_decide(t, c->stream));
@@ -785,12 +862,14 @@ static ig_status phase_alpha(ig_ctx *c)
 			CK(launch_spop_tree(t, c->stream));
 			c->launches++;
 		}
-		NCK(g_nccl.AllReduce(c->fx, c->fx, ahead ? FX_POST + nt : (size_t)(g.K + 4), ncclInt64, ncclSum, c->comm, c->stream));
-		CK(launch_post_final(a, c->fx, c->stream));
+		ptrace_mark(c, 6);
+		ig_status sta = allreduce_fx(c, 0, ahead ? FX_POST + nt : (size_t)(g.K + 4), &a);
+		if (sta != IG_OK) return sta;
 		c->tree_ready = ahead;
-		c->launches += 2;
+		c->launches++;
 		return IG_OK;
 	}
+	ptrace_mark(c, 6);
 	CK(launch_post_sweep(a, c->stream));
 	c->launches++;
 	return IG_OK;
@@ -799,8 +878,8 @@ static ig_status phase_alpha(ig_ctx *c)
 static void ptrace_report(ig_ctx *c)
 {
 	if (c->ptrace.empty() || c->ptrace_sweeps < 8) return;
-	static const char *names[PT_POINTS - 1] = {"update_P (wait / draw)", "update_S + G proposals", "zq_sweep", "epilogue", "all-gather", "update_alpha"};
-	double acc[PT_POINTS - 1] = {0, 0, 0, 0, 0, 0}, between = 0;
+	static const char *names[PT_POINTS - 1] = {"update_P (wait / draw)", "update_S + G proposals", "zq_sweep", "epilogue", "all-gather", "local sums", "exchange + update_alpha"};
+	double acc[PT_POINTS - 1] = {0, 0, 0, 0, 0, 0, 0}, between = 0;
 	int n = 0;
 	for (int s = 4; s < c->ptrace_sweeps; s++, n++) {            // skip the first sweeps
 		for (int p = 0; p + 1 < PT_POINTS; p++) {
@@ -839,7 +918,7 @@ static ig_status one_sweep_direct(ig_ctx *c)
 	ptrace_mark(c, 5);
 	if (tr) { h1 = wall_ms(); c->ptrace_host_ms[2] += h1 - h0; h0 = h1; }
 	st = phase_alpha(c);                                   // update_alpha, totallkh    :214-215
-	ptrace_mark(c, 6);
+	ptrace_mark(c, 7);
 	if (tr) { h1 = wall_ms(); c->ptrace_host_ms[3] += h1 - h0; c->ptrace_host_ms[4] += 1.0; }
 	if (!c->ptrace.empty() && c->ptrace_sweeps < PT_SWEEPS && !c->iter_dev) c->ptrace_sweeps++;
 	return st;

@@ -122,6 +122,12 @@ struct ig_ctx {
 	bool tree_ready = false;         // fx holds the all-reduced subset sums for sweep iter + 1 (computed behind the previous post_sweep)
 	unsigned long long *fx = nullptr;   // [32] post sums | [2^K][2] subset sums
 	double *S2 = nullptr;            // double buffer of S (every CTA of the decide kernel reads S, CTA 0 writes it)
+	// ... all-reduced over NVLink peer memory (peer_allreduce_kernel) when every rank could map every rank's buffer
+	unsigned long long *px_buf = nullptr;             // this rank's buffer (a plain cudaMalloc: it is exported through CUDA IPC)
+	std::vector<void *> px_mapped;                    // the peers' buffers as opened here (to close them)
+	unsigned long long **px_peers = nullptr;          // device array [W]
+	unsigned long long px_seq = 0;
+	bool px = false;
 	// IG_PHASE_TRACE=1: CUDA events at the phase boundaries of the first 64 sweeps, averages printed by ig_destroy
 	std::vector<cudaEvent_t> ptrace;
 	int ptrace_sweeps = 0;

@@ -182,6 +182,22 @@ struct TreeArgs {
 	double *S_out; int32_t *state_out; int32_t *gprop; int2 *gpair; DevScalars *sc;      // decide only
 };
 cudaError_t launch_spop_tree(const TreeArgs &a, cudaStream_t s);
+
+// All-reduce of the few KB of int64 sums over NVLink peer memory, fused with the post-sweep tail (ig_kernels.cu
+// peer_allreduce_kernel).  Every rank owns one buffer that all ranks of the chain have mapped (CUDA IPC):
+//   words [2 parities][W ranks][PX_WORDS] : rank r's contribution to the all-reduce of that parity, written BY rank r
+//   words [2 parities][W ranks]           : rank r's sequence number, written by rank r after its data
+constexpr int PX_WORDS = 32 + 2 * 1024;
+static inline size_t px_buffer_words(int W) { return (size_t)2 * W * PX_WORDS + (size_t)2 * W; }
+struct PeerArgs {
+	unsigned long long *const *peers;    // device array [W]: every rank's buffer as mapped here (own buffer at [me])
+	int W, me;
+	unsigned long long seq;              // 1, 2, 3, ... : the same on every rank for the same all-reduce
+	int nwords;
+	unsigned long long *acc;             // in: local sums; out: global sums
+	int do_final;                        // run the post-sweep tail (post_finish) on the summed totals at acc[0 .. K + 4)
+};
+cudaError_t launch_peer_allreduce(const PeerArgs &x, const PostArgs &a, cudaStream_t s);
 cudaError_t launch_spop_decide(const TreeArgs &a, cudaStream_t s);
 
 struct MomArgs {

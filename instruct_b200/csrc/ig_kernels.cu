@@ -243,13 +243,16 @@ __device__ __forceinline__ void spop_propose(double sj, int cs, int back_refl, S
 	}
 }
 // ... then the accept from proposal() at the current and the proposed rates
-__device__ __forceinline__ bool spop_accept(double cur, double pl, int cs, int new_state, int back_refl, Stream &st)
+__device__ __forceinline__ bool spop_accept_u(double cur, double pl, int cs, int new_state, int back_refl, double u)
 {
 	double ratio = exp(pl - cur);
 	if (back_refl == 0) ratio *= trans_prob(cs, new_state) / trans_prob(new_state, cs);
-	const double u = st.uniform();
 	// MIN2(1, NaN) == 1 in the reference (mcmc.h:10): a NaN ratio accepts
 	return (ratio != ratio) || (u < fmin(1.0, ratio));
+}
+__device__ __forceinline__ bool spop_accept(double cur, double pl, int cs, int new_state, int back_refl, Stream &st)
+{
+	return spop_accept_u(cur, pl, cs, new_state, back_refl, st.uniform());
 }
 // generation proposal of update_G (mcmc.c:1062-1084) for individual i (global index) at selfing rate s
 __device__ __forceinline__ int g_propose(double s, int i, uint32_t iter, uint32_t key0, uint32_t key1)
@@ -771,29 +774,42 @@ __global__ void __launch_bounds__(TREE_THREADS) spop_tree_kernel(const TreeArgs 
 }
 __global__ void __launch_bounds__(TREE_THREADS) spop_decide_kernel(const TreeArgs a)
 {
-	__shared__ double Sn[MAX_K];
+	// every CTA repeats the K decisions (they are a function of the all-reduced table and the step's Philox streams), then
+	// proposes G for its own 256 individuals.  The table goes to shared memory first and thread j prepares step j's proposal,
+	// so the sequential walk of thread 0 is K times (two shared loads, one exp, one compare) -- it was 11 us of dependent
+	// global loads and Philox set-ups when one thread did everything.
+	extern __shared__ long long tab[];                    // [2^K][2]
+	__shared__ double Sn[MAX_K], prop_s[MAX_K], Sold[MAX_K];
+	__shared__ int cs_s[MAX_K], ns_s[MAX_K];
+	__shared__ double u_s[MAX_K];
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x, K = g.K;
+	const long long *acc = reinterpret_cast<const long long *>(a.acc);
+	for (int t = tid; t < (2 << K); t += TREE_THREADS) tab[t] = acc[t];
+	if (tid < K) {
+		Stream st((uint32_t)tid, 0u, a.iter, TAG_SPOP, a.key0, a.key1);
+		const double sj = a.S[tid];
+		const int cs = (a.back_refl == 0) ? a.state[tid] : 1;
+		double prop;
+		int new_state;
+		spop_propose(sj, cs, a.back_refl, st, prop, new_state);
+		Sold[tid] = sj; prop_s[tid] = prop; cs_s[tid] = cs; ns_s[tid] = new_state;
+		u_s[tid] = st.uniform();                          // the step's accept draw: next in the same stream (spop_accept's order)
+	}
+	__syncthreads();
 	if (tid == 0) {
-		const long long *acc = reinterpret_cast<const long long *>(a.acc);
 		unsigned B = 0;
-		double cur = fx_val(acc[0], acc[1], FX_LL);
+		double cur = fx_val(tab[0], tab[1], FX_LL);
 		int accepts = 0;
 		for (int j = 0; j < K; j++) {
-			Stream st((uint32_t)j, 0u, a.iter, TAG_SPOP, a.key0, a.key1);
-			const double sj = a.S[j];
-			const int cs = (a.back_refl == 0) ? a.state[j] : 1;
-			double prop;
-			int new_state;
-			spop_propose(sj, cs, a.back_refl, st, prop, new_state);
 			const unsigned Bp = B | (1u << j);
-			const double pl = fx_val(acc[2 * (size_t)Bp], acc[2 * (size_t)Bp + 1], FX_LL);
-			const bool ok = spop_accept(cur, pl, cs, new_state, a.back_refl, st);
+			const double pl = fx_val(tab[2 * Bp], tab[2 * Bp + 1], FX_LL);
+			const bool ok = spop_accept_u(cur, pl, cs_s[j], ns_s[j], a.back_refl, u_s[j]);
 			if (ok) { B = Bp; cur = pl; accepts++; }
-			Sn[j] = ok ? prop : sj;
+			Sn[j] = ok ? prop_s[j] : Sold[j];
 			if (blockIdx.x == 0) {
 				a.S_out[j] = Sn[j];
-				if (a.back_refl == 0) a.state_out[j] = ok ? new_state : cs;
+				if (a.back_refl == 0) a.state_out[j] = ok ? ns_s[j] : cs_s[j];
 			}
 		}
 		if (blockIdx.x == 0) { a.sc->cur_prop_ll = cur; a.sc->s_accepts += accepts; }
@@ -817,7 +833,7 @@ cudaError_t launch_spop_tree(const TreeArgs &a, cudaStream_t s)
 }
 cudaError_t launch_spop_decide(const TreeArgs &a, cudaStream_t s)
 {
-	spop_decide_kernel<<<(a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, s>>>(a);
+	spop_decide_kernel<<<(a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, (size_t)(2 << a.geo.K) * sizeof(long long), s>>>(a);
 	return cudaGetLastError();
 }
 
@@ -860,6 +876,58 @@ cudaError_t launch_post_local(const PostArgs &a, unsigned long long *acc, cudaSt
 cudaError_t launch_post_final(const PostArgs &a, const unsigned long long *acc, cudaStream_t s)
 {
 	post_final_kernel<<<1, 32, 0, s>>>(a, acc);
+	return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// peer_allreduce: the exchange of a sharded sweep as ONE kernel over NVLink peer memory.  One CTA: (1) stores this rank's
+// local sums into its slot of EVERY rank's buffer (plain stores through the IPC mappings; a few KB to each of W - 1 peers
+// over NVSwitch), system-scope fence, then its sequence number behind them; (2) spins on its own buffer until every
+// rank's sequence number has arrived; (3) adds the W slots -- integers, so any order gives the same bits -- and (4) runs the
+// tail of post_sweep (totallkh, update_alpha) on the totals when asked to.  An NCCL all-reduce of the same 4 KB costs ~30 us
+// of protocol latency per sweep at 8 GPUs; this is one launch and two NVLink one-way trips.  Buffers alternate by the
+// parity of the sequence number: a rank can be at most one all-reduce ahead of the slowest (it needs everyone's number to
+// leave), so the slots it overwrites are never ones a peer still has to read.
+// --------------------------------------------------------------------------------------
+constexpr int PX_THREADS = 512;
+__global__ void __launch_bounds__(PX_THREADS) peer_allreduce_kernel(const PeerArgs x, const PostArgs a)
+{
+	const int tid = threadIdx.x, W = x.W;
+	const int par = (int)(x.seq & 1ull);
+	const size_t slot = ((size_t)par * W + x.me) * PX_WORDS;
+	const size_t flags = (size_t)2 * W * PX_WORDS + (size_t)par * W;
+	for (int r = 0; r < W; r++) {
+		volatile unsigned long long *dst = x.peers[r] + slot;
+		for (int w = tid; w < x.nwords; w += PX_THREADS) dst[w] = x.acc[w];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (tid < W) *(volatile unsigned long long *)(x.peers[tid] + flags + x.me) = x.seq;
+	unsigned long long *mine = x.peers[x.me];
+	if (tid < W) {
+		volatile unsigned long long *f = mine + flags + tid;
+		const long long t0 = clock64();
+		while (*f != x.seq)
+			if (clock64() - t0 > (1ll << 34)) __trap();        // ~9 s: a peer died; fail the context loudly instead of hanging the GPU
+	}
+	__threadfence_system();
+	__syncthreads();
+	for (int w = tid; w < x.nwords; w += PX_THREADS) {
+		unsigned long long sum = 0;
+		for (int r = 0; r < W; r++) sum += *(volatile unsigned long long *)(mine + ((size_t)par * W + r) * PX_WORDS + w);
+		x.acc[w] = sum;
+	}
+	if (!x.do_final) return;
+	__threadfence();
+	__syncthreads();
+	if (tid != 0) return;
+	double tot[SC_MAXV];
+	post_totals(reinterpret_cast<const long long *>(x.acc), a.geo.K, tot);
+	post_finish(a, tot, a.iter);
+}
+cudaError_t launch_peer_allreduce(const PeerArgs &x, const PostArgs &a, cudaStream_t s)
+{
+	peer_allreduce_kernel<<<1, PX_THREADS, 0, s>>>(x, a);
 	return cudaGetLastError();
 }
 

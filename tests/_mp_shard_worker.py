@@ -97,18 +97,34 @@ def gpu_mode():
     s.comm_init(broadcast_unique_id(Sampler.unique_id, rank))
     ch, cv = s.run_chain(0, initd=[0.2, 0.4, 0.6, 0.8])
     zloc = s.get(_lib.STATE_Z)
+    # the records live on their own rank during the sweeps (local scalar updates): a state hook gathers them, and the
+    # sweeps after it must not use anything computed ahead of the hook
+    qall = s.get(_lib.STATE_Q); gall = s.get(_lib.STATE_G)
+    s.sweep(6)
+    qall2 = s.get(_lib.STATE_Q); sall2 = s.get(_lib.STATE_S)
     s.close()
     ok = True
     if rank == 0:
         s1 = Sampler(SeqData(d.x, d.allelenum, K), device=local, **kw)
         c1, cv1 = s1.run_chain(0, initd=[0.2, 0.4, 0.6, 0.8])
         z1 = s1.get(_lib.STATE_Z)
+        q1 = s1.get(_lib.STATE_Q); g1 = s1.get(_lib.STATE_G)
+        s1.sweep(6)
+        q12 = s1.get(_lib.STATE_Q); s12 = s1.get(_lib.STATE_S)
         s1.close()
         b, e = shard_bounds(d.N, world, 0)
         for name in ("qq", "qq2", "self_rates", "self_rates2", "gen", "gen2", "indvlkh"):
             ok &= bool(np.array_equal(getattr(ch, name), getattr(c1, name)))
         ok &= ch.totallkh == c1.totallkh and ch.totallkh2 == c1.totallkh2 and bool(np.array_equal(cv, cv1))
         ok &= bool(np.array_equal(zloc, z1[:, b:e, :]))
+        ok &= bool(np.array_equal(qall, q1)) and bool(np.array_equal(gall, g1))
+        ok &= bool(np.array_equal(qall2, q12)) and bool(np.array_equal(sall2, s12))
+    ok &= _diploid_variant(rank, world, local, mode=2, back_refl=0, K=3)      # adaptive-independence proposals (-e 0): states double-buffered
+    ok &= _diploid_variant(rank, world, local, mode=1, back_refl=1, K=5)      # no selfing: post-sweep sums only
+    ok &= _diploid_variant(rank, world, local, mode=3, back_refl=1, K=3)      # individual rates: the all-gather path
+    os.environ["IG_NCCL_SCALARS"] = "1"                                       # the same sums through ncclAllReduce instead of peer memory
+    ok &= _diploid_variant(rank, world, local, mode=2, back_refl=1, K=4)
+    del os.environ["IG_NCCL_SCALARS"]
     ok &= _tetra_sharded(rank, world, local, 1)
     ok &= _tetra_sharded(rank, world, local, 0)
     flag = torch.tensor([1 if ok else 0], device="cuda")
@@ -116,6 +132,29 @@ def gpu_mode():
     if rank == 0:
         print("GPU_SHARD_OK" if int(flag.item()) == 1 else "GPU_SHARD_MISMATCH")
     dist.destroy_process_group()
+
+
+def _diploid_variant(rank, world, local, mode, back_refl, K):
+    from instruct_b200 import Sampler, SeqData
+    d = make_dataset(N=401, L=90, K=min(K, 4), A=3, miss=0.03, seed=10 + mode)
+    kw = dict(update=24, burnin=9, thinning=2, ckrep=4, seed=5)
+    initd = np.linspace(0.2, 0.8, K) if mode == 2 else None
+    xs = shard_genotypes(d.x, world, rank)
+    s = Sampler(SeqData(xs, d.allelenum, K, mode=mode, back_refl=back_refl), device=local, shard_rank=rank, shard_count=world, totalsize=d.N, **kw)
+    s.comm_init(broadcast_unique_id(Sampler.unique_id, rank))
+    ch, cv = s.run_chain(0, initd=initd)
+    s.close()
+    ok = True
+    if rank == 0:
+        s1 = Sampler(SeqData(d.x, d.allelenum, K, mode=mode, back_refl=back_refl), device=local, **kw)
+        c1, cv1 = s1.run_chain(0, initd=initd)
+        s1.close()
+        for name in ("qq", "qq2", "self_rates", "self_rates2", "gen", "gen2", "indvlkh"):
+            ok &= bool(np.array_equal(getattr(ch, name), getattr(c1, name)))
+        ok &= ch.totallkh == c1.totallkh and ch.totallkh2 == c1.totallkh2 and bool(np.array_equal(cv, cv1))
+        if not ok:
+            print(f"variant mode={mode} back_refl={back_refl} differs", flush=True)
+    return ok
 
 
 def _tetra_sharded(rank, world, local, autopoly):
