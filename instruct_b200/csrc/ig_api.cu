@@ -152,7 +152,11 @@ extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 	c->rounds = (cfg->rng_rounds == 10) ? 10 : 7;
 	c->key0 = (uint32_t)cfg->seed;
 	c->key1 = (uint32_t)(cfg->seed >> 32);
-	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(IG_ERR_CUDA, "stream creation failed"); }
+	// the chain's stream gets the highest priority, the side stream of a sharded chain (tally all-reduce + next P draw) the lowest:
+	// its 6000 short CTAs otherwise take SM slots from the few small kernels on the sweep's critical path
+	int prio_least = 0, prio_greatest = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+	if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { delete c; return fail(IG_ERR_CUDA, "stream creation failed"); }
 	ig_alloc_stream = c->stream;
 	if (getenv("IG_PHASE_TRACE")) {
 		c->ptrace.resize((size_t)PT_POINTS * PT_SWEEPS);
@@ -172,7 +176,7 @@ static void free_all(ig_ctx *c)
 	cudaFree(c->Xt); cudaFree(c->Zt); cudaFree(c->P); cudaFree(c->P64); cudaFree(c->n); cudaFree(c->allelenum);
 	cudaFree(c->ind); cudaFree(c->Qf); cudaFree(c->gprop); cudaFree(c->gpair); cudaFree(c->S); cudaFree(c->state);
 	cudaFree(c->sc); cudaFree(c->pcnt); cudaFree(c->plog); cudaFree(c->pnsh); cudaFree(c->nhet); cudaFree(c->nsh); cudaFree(c->cnt); cudaFree(c->llparts); cudaFree(c->initd_dev);
-	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2); cudaFree(c->S2); cudaFree(c->fx);
+	cudaFree(c->scratch); cudaFree(c->gpart); cudaFree(c->state2); cudaFree(c->S2); cudaFree(c->fx); cudaFree(c->fxg);
 	cudaFree(c->fprop); cudaFree(c->hpair); cudaFree(c->ftab); cudaFree(c->pfk);
 	cudaFree(c->logP); cudaFree(c->na_pll);
 	cudaFree(c->mom.tot); cudaFree(c->mom.indvlkh); cudaFree(c->mom.qq); cudaFree(c->mom.qq2); cudaFree(c->mom.self);
@@ -252,6 +256,7 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 	CK(dalloc(&c->state2, (size_t)MAX_K));
 	CK(dalloc(&c->S2, (size_t)MAX_K));
 	CK(dalloc(&c->fx, (size_t)FX_POST + 2 * ((size_t)1 << LOCAL_MAX_K)));
+	CK(dalloc(&c->fxg, (size_t)FX_POST + 2 * ((size_t)1 << LOCAL_MAX_K)));
 	if (c->cfg.mode == 0) { ig_status st0 = na_alloc(c); if (st0 != IG_OK) return st0; }
 	if (g.fmode) {
 		CK(dalloc(&c->fprop, (size_t)(c->ns > g.K ? c->ns : g.K)));
@@ -416,7 +421,9 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 		if (g_nccl.CommSplit(c->comm, 0, c->cfg.shard_rank, &c->comm2, nullptr) != ncclSuccess) c->comm2 = nullptr;
 	}
 	if (!c->tetra && c->cfg.mode != 0 && !c->cfg.print_freq && c->loaded && !c->stream2) {
-		CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+		int prio_least = 0, prio_greatest = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+		CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_least));
 		CK(cudaEventCreateWithFlags(&c->ev_zq, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_p, cudaEventDisableTiming));
 		CK(dalloc(&c->Pnext, (size_t)c->geo.Lpad * c->geo.A * c->geo.KP));
@@ -676,14 +683,15 @@ static ig_status allreduce_fx(ig_ctx *c, size_t off, size_t n, const PostArgs *t
 {
 	if (c->px) {
 		PeerArgs x{c->px_peers, c->cfg.shard_count > 1 ? c->cfg.shard_count : 1, c->cfg.shard_count > 1 ? c->cfg.shard_rank : 0,
-		           ++c->px_seq, (int)n, c->fx + off, tail ? 1 : 0};
+		           ++c->px_seq, (int)n, c->fx + off, c->fxg + off, tail ? 1 : 0};
 		PostArgs none{};
 		CK(launch_peer_allreduce(x, tail ? *tail : none, c->stream));
 		c->launches++;
 		return IG_OK;
 	}
-	NCK(g_nccl.AllReduce(c->fx + off, c->fx + off, n, ncclInt64, ncclSum, c->comm, c->stream));
-	if (tail) { CK(launch_post_final(*tail, c->fx, c->stream)); c->launches++; }
+	NCK(g_nccl.AllReduce(c->fx + off, c->fxg + off, n, ncclInt64, ncclSum, c->comm, c->stream));
+	CK(cudaMemsetAsync(c->fx + off, 0, n * sizeof(unsigned long long), c->stream));       // the accumulators go back empty
+	if (tail) { CK(launch_post_final(*tail, c->fxg, c->stream)); c->launches++; }
 	return IG_OK;
 }
 
@@ -766,13 +774,12 @@ static ig_status phase_update_S(ig_ctx *c)
 		TreeArgs t{c->ind, c->S, c->state, c->geo, c->iter, c->key0, c->key1, c->cfg.back_refl, c->fx + FX_POST,
 		           c->S2, c->state2, c->gprop, c->gpair, c->sc};
 		if (!c->tree_ready) {
-			const size_t nt = 2 * ((size_t)1 << g.K);
-			CK(cudaMemsetAsync(c->fx + FX_POST, 0, nt * sizeof(unsigned long long), c->stream));
-			CK(launch_spop_tree(t, c->stream));
+			CK(launch_local_sums(&t, nullptr, nullptr, c->stream));
 			c->launches++;
-			ig_status sta = allreduce_fx(c, FX_POST, nt, nullptr);
+			ig_status sta = allreduce_fx(c, FX_POST, 2 * ((size_t)1 << g.K), nullptr);
 			if (sta != IG_OK) return sta;
 		}
+		t.acc = c->fxg + FX_POST;                            // the decisions read the all-reduced table
 		c->tree_ready = false;
 		CK(launch_spop_decide(t, c->stream));
 		std::swap(c->S, c->S2);
@@ -854,14 +861,9 @@ static ig_status phase_alpha(ig_ctx *c)
 		const Geometry &g = c->geo;
 		const bool ahead = c->more_follow && c->cfg.mode == 2 && !getenv_once("IG_NO_TREE_AHEAD");
 		const size_t nt = ahead ? 2 * ((size_t)1 << g.K) : 0;
-		CK(cudaMemsetAsync(c->fx, 0, (FX_POST + nt) * sizeof(unsigned long long), c->stream));
-		CK(launch_post_local(a, c->fx, c->stream));
-		if (ahead) {
-			TreeArgs t{c->ind, c->S, c->state, c->geo, c->iter + 1, c->key0, c->key1, c->cfg.back_refl, c->fx + FX_POST,
-			           nullptr, nullptr, nullptr, nullptr, nullptr};
-			CK(launch_spop_tree(t, c->stream));
-			c->launches++;
-		}
+		TreeArgs t{c->ind, c->S, c->state, c->geo, c->iter + 1, c->key0, c->key1, c->cfg.back_refl, c->fx + FX_POST,
+		           nullptr, nullptr, nullptr, nullptr, nullptr};
+		CK(launch_local_sums(ahead ? &t : nullptr, &a, c->fx, c->stream));
 		ptrace_mark(c, 6);
 		ig_status sta = allreduce_fx(c, 0, ahead ? FX_POST + nt : (size_t)(g.K + 4), &a);
 		if (sta != IG_OK) return sta;

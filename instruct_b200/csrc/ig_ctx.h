@@ -120,7 +120,8 @@ struct ig_ctx {
 	bool ind_stale = false;          // other ranks' records in `ind` are older than the last sweep
 	bool mom_local = false;          // the running moments of other ranks' individuals live on those ranks
 	bool tree_ready = false;         // fx holds the all-reduced subset sums for sweep iter + 1 (computed behind the previous post_sweep)
-	unsigned long long *fx = nullptr;   // [32] post sums | [2^K][2] subset sums
+	unsigned long long *fx = nullptr;   // local accumulators: [32] post sums | [2^K][2] subset sums; zero between uses (whoever consumes them clears them)
+	unsigned long long *fxg = nullptr;  // the same layout, summed over the ranks
 	double *S2 = nullptr;            // double buffer of S (every CTA of the decide kernel reads S, CTA 0 writes it)
 	// ... all-reduced over NVLink peer memory (peer_allreduce_kernel) when every rank could map every rank's buffer
 	unsigned long long *px_buf = nullptr;             // this rank's buffer (a plain cudaMalloc: it is exported through CUDA IPC)

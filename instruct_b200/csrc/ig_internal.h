@@ -171,7 +171,6 @@ struct PostArgs {
 };
 cudaError_t launch_post_sweep(const PostArgs &a, cudaStream_t s);
 // the same in two halves around an int64 all-reduce (sharded chains with local records): acc[K + 4]
-cudaError_t launch_post_local(const PostArgs &a, unsigned long long *acc, cudaStream_t s);
 cudaError_t launch_post_final(const PostArgs &a, const unsigned long long *acc, cudaStream_t s);
 
 // update_S_POP of a sharded chain on the local records: proposal() summed for all 2^K subsets of replaced rates
@@ -181,7 +180,6 @@ struct TreeArgs {
 	unsigned long long *acc;
 	double *S_out; int32_t *state_out; int32_t *gprop; int2 *gpair; DevScalars *sc;      // decide only
 };
-cudaError_t launch_spop_tree(const TreeArgs &a, cudaStream_t s);
 
 // All-reduce of the few KB of int64 sums over NVLink peer memory, fused with the post-sweep tail (ig_kernels.cu
 // peer_allreduce_kernel).  Every rank owns one buffer that all ranks of the chain have mapped (CUDA IPC):
@@ -194,10 +192,12 @@ struct PeerArgs {
 	int W, me;
 	unsigned long long seq;              // 1, 2, 3, ... : the same on every rank for the same all-reduce
 	int nwords;
-	unsigned long long *acc;             // in: local sums; out: global sums
-	int do_final;                        // run the post-sweep tail (post_finish) on the summed totals at acc[0 .. K + 4)
+	unsigned long long *acc;             // in: local sums (left zeroed)
+	unsigned long long *out;             // global sums
+	int do_final;                        // run the post-sweep tail (post_finish) on the summed totals at out[0 .. K + 4)
 };
 cudaError_t launch_peer_allreduce(const PeerArgs &x, const PostArgs &a, cudaStream_t s);
+cudaError_t launch_local_sums(const TreeArgs *tree, const PostArgs *post, unsigned long long *post_acc, cudaStream_t s);   // either may be null
 cudaError_t launch_spop_decide(const TreeArgs &a, cudaStream_t s);
 
 struct MomArgs {

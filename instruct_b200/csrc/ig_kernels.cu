@@ -738,13 +738,12 @@ __device__ void post_finish(const PostArgs &a, const double *tot, uint32_t iter)
 // sequential kernel: bit-identical S.
 // --------------------------------------------------------------------------------------
 constexpr int TREE_THREADS = 256;
-__global__ void __launch_bounds__(TREE_THREADS) spop_tree_kernel(const TreeArgs a)
+__device__ __forceinline__ void spop_tree_body(const TreeArgs &a, const unsigned B)
 {
 	__shared__ double Sc[MAX_K];
 	__shared__ long long wsum[2][TREE_THREADS / 32];
 	const Geometry &g = a.geo;
 	const int tid = threadIdx.x, K = g.K;
-	const unsigned B = blockIdx.y;
 	if (tid < K) {
 		double sv = a.S[tid];
 		if ((B >> tid) & 1u) {
@@ -825,12 +824,6 @@ __global__ void __launch_bounds__(TREE_THREADS) spop_decide_kernel(const TreeArg
 	a.gprop[i] = gp;
 	a.gpair[il] = make_int2((int)rec[K + 2], gp);
 }
-cudaError_t launch_spop_tree(const TreeArgs &a, cudaStream_t s)
-{
-	const dim3 grid((a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS, 1u << a.geo.K);
-	spop_tree_kernel<<<grid, TREE_THREADS, 0, s>>>(a);
-	return cudaGetLastError();
-}
 cudaError_t launch_spop_decide(const TreeArgs &a, cudaStream_t s)
 {
 	spop_decide_kernel<<<(a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, (size_t)(2 << a.geo.K) * sizeof(long long), s>>>(a);
@@ -838,7 +831,7 @@ cudaError_t launch_spop_decide(const TreeArgs &a, cudaStream_t s)
 }
 
 // post_sweep in two halves around an int64 all-reduce: the local individuals' K + 4 fixed-point sums, then the tail
-__global__ void __launch_bounds__(TREE_THREADS) post_local_kernel(const PostArgs a, unsigned long long *acc)
+__device__ __forceinline__ void post_local_body(const PostArgs &a, unsigned long long *acc)
 {
 	__shared__ long long wsum[SC_MAXV][TREE_THREADS / 32];
 	const Geometry &g = a.geo;
@@ -859,19 +852,30 @@ __global__ void __launch_bounds__(TREE_THREADS) post_local_kernel(const PostArgs
 		if (t) atomicAdd(acc + tid, (unsigned long long)t);
 	}
 }
+// one launch for all local sums of a sweep: rows [0, n_tree) of the grid are the subset sums of the NEXT update_S_POP (t),
+// the last row the post-sweep sums of this sweep (a) -- either part may be absent
+__global__ void __launch_bounds__(TREE_THREADS) local_sums_kernel(const TreeArgs t, const PostArgs a, unsigned long long *post_acc, int n_tree)
+{
+	if ((int)blockIdx.y < n_tree) spop_tree_body(t, blockIdx.y);
+	else post_local_body(a, post_acc);
+}
+cudaError_t launch_local_sums(const TreeArgs *t, const PostArgs *a, unsigned long long *post_acc, cudaStream_t s)
+{
+	const Geometry &g = t ? t->geo : a->geo;
+	const int n_tree = t ? (1 << g.K) : 0;
+	const dim3 grid((g.Nloc + TREE_THREADS - 1) / TREE_THREADS, n_tree + (a ? 1 : 0));
+	TreeArgs tz{};
+	PostArgs az{};
+	local_sums_kernel<<<grid, TREE_THREADS, 0, s>>>(t ? *t : tz, a ? *a : az, post_acc, n_tree);
+	return cudaGetLastError();
+}
+
 __global__ void post_final_kernel(const PostArgs a, const unsigned long long *acc)
 {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	double tot[SC_MAXV];
 	post_totals(reinterpret_cast<const long long *>(acc), a.geo.K, tot);
 	post_finish(a, tot, a.iter);
-}
-cudaError_t launch_post_local(const PostArgs &a, unsigned long long *acc, cudaStream_t s)
-{
-	int grid = (a.geo.Nloc + TREE_THREADS - 1) / TREE_THREADS;
-	if (grid > 592) grid = 592;
-	post_local_kernel<<<grid, TREE_THREADS, 0, s>>>(a, acc);
-	return cudaGetLastError();
 }
 cudaError_t launch_post_final(const PostArgs &a, const unsigned long long *acc, cudaStream_t s)
 {
@@ -896,9 +900,10 @@ __global__ void __launch_bounds__(PX_THREADS) peer_allreduce_kernel(const PeerAr
 	const int par = (int)(x.seq & 1ull);
 	const size_t slot = ((size_t)par * W + x.me) * PX_WORDS;
 	const size_t flags = (size_t)2 * W * PX_WORDS + (size_t)par * W;
-	for (int r = 0; r < W; r++) {
-		volatile unsigned long long *dst = x.peers[r] + slot;
-		for (int w = tid; w < x.nwords; w += PX_THREADS) dst[w] = x.acc[w];
+	for (int w = tid; w < x.nwords; w += PX_THREADS) {
+		const unsigned long long v = x.acc[w];
+		x.acc[w] = 0;                                          // the local accumulators are handed back empty: no memset per sweep
+		for (int r = 0; r < W; r++) *(volatile unsigned long long *)(x.peers[r] + slot + w) = v;
 	}
 	__threadfence_system();
 	__syncthreads();
@@ -915,14 +920,14 @@ __global__ void __launch_bounds__(PX_THREADS) peer_allreduce_kernel(const PeerAr
 	for (int w = tid; w < x.nwords; w += PX_THREADS) {
 		unsigned long long sum = 0;
 		for (int r = 0; r < W; r++) sum += *(volatile unsigned long long *)(mine + ((size_t)par * W + r) * PX_WORDS + w);
-		x.acc[w] = sum;
+		x.out[w] = sum;
 	}
 	if (!x.do_final) return;
 	__threadfence();
 	__syncthreads();
 	if (tid != 0) return;
 	double tot[SC_MAXV];
-	post_totals(reinterpret_cast<const long long *>(x.acc), a.geo.K, tot);
+	post_totals(reinterpret_cast<const long long *>(x.out), a.geo.K, tot);
 	post_finish(a, tot, a.iter);
 }
 cudaError_t launch_peer_allreduce(const PeerArgs &x, const PostArgs &a, cudaStream_t s)
