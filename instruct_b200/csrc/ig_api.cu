@@ -14,6 +14,7 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <algorithm>
 
 #include <time.h>
 #include "ig_ctx.h"
@@ -63,6 +64,7 @@ struct NcclApi {
 	ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;     // optional (NCCL >= 2.18)
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -80,6 +82,7 @@ static ig_status nccl_load()
 	SYM(CommDestroy, "ncclCommDestroy");
 	SYM(AllReduce, "ncclAllReduce");
 	SYM(AllGather, "ncclAllGather");
+	SYM(ReduceScatter, "ncclReduceScatter");
 	SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
 	*(void **)(&g_nccl.CommSplit) = dlsym(h, "ncclCommSplit");
@@ -199,6 +202,7 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->ev_zq) cudaEventDestroy(c->ev_zq);
 	if (c->ev_p) cudaEventDestroy(c->ev_p);
 	cudaFree(c->Pnext);
+	cudaFree(c->nred);
 	cudaFree(c->g8_dev);
 	if (c->g8_host) cudaFreeHost(c->g8_host);
 	if (c->S_pin) cudaFreeHost(c->S_pin);
@@ -231,8 +235,12 @@ static ig_status finish_load(ig_ctx *c, const int16_t *x_dev_canon)
 		CK(dalloc(&c->Hs, (size_t)g.nchunks * g.Nloc));
 		CK(dalloc(&c->Pc, snp_pc_floats(g)));
 	} else CK(dalloc(&c->Zt, tiles));
-	CK(dalloc(&c->P, pn));
-	CK(dalloc(&c->n, pn));
+	// a sharded chain reduce-scatters the tally by whole loci and all-gathers P (phase_zq): room for W equal blocks of loci
+	const int Wl = c->cfg.shard_count > 1 ? c->cfg.shard_count : 1;
+	c->p_lr = (g.Lpad + Wl - 1) / Wl;
+	const size_t pn_alloc = (size_t)Wl * c->p_lr * g.A * g.KP;
+	CK(dalloc(&c->P, pn_alloc));
+	CK(dalloc(&c->n, pn_alloc));
 	if (c->cfg.print_freq) CK(dalloc(&c->P64, (size_t)g.K * g.L * g.A));
 	CK(dalloc(&c->ind, (size_t)c->Npad * g.REC));
 	CK(dalloc(&c->Qf, (size_t)g.Nloc * g.KP));
@@ -426,7 +434,9 @@ extern "C" ig_status ig_comm_init(ig_ctx *c, const void *id128)
 		CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_least));
 		CK(cudaEventCreateWithFlags(&c->ev_zq, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_p, cudaEventDisableTiming));
-		CK(dalloc(&c->Pnext, (size_t)c->geo.Lpad * c->geo.A * c->geo.KP));
+		const int Wl = c->cfg.shard_count > 1 ? c->cfg.shard_count : 1;
+		CK(dalloc(&c->Pnext, (size_t)Wl * c->p_lr * c->geo.A * c->geo.KP));
+		if (!c->geo.snp && g_nccl.ReduceScatter && !getenv_once("IG_P_ALLREDUCE")) CK(dalloc(&c->nred, (size_t)c->p_lr * c->geo.A * c->geo.KP));
 		if (c->geo.snp) CK(dalloc(&c->Pcnext, snp_pc_floats(c->geo)));
 	}
 	// modes 1 and 2 keep the records local (IG_GATHER_RECORDS=1: the all-gather path of round 1, kept for comparison)
@@ -819,9 +829,24 @@ static ig_status phase_zq(ig_ctx *c, int init)
 		const Geometry &g = c->geo;
 		CK(cudaEventRecord(c->ev_zq, c->stream));
 		CK(cudaStreamWaitEvent(c->stream2, c->ev_zq, 0));
-		NCK(g_nccl.AllReduce(c->n, c->n, (size_t)g.Lpad * g.A * g.KP, ncclInt32, ncclSum, c->comm2 ? c->comm2 : c->comm, c->stream2));
-		PArgs pa{c->n, c->Pnext, c->P64, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0, 0, c->Pcnext, c->geo.TL};
-		CK(launch_p_dirichlet(pa, c->stream2));
+		ncclComm_t cm = c->comm2 ? c->comm2 : c->comm;
+		if (c->nred) {
+			// every rank needs all of P but not all of n: the tally is reduce-SCATTERED by blocks of loci, each rank draws the
+			// Dirichlets of its block (1/W of the 43 us the full draw takes at config 4) and P is all-gathered -- the same
+			// bytes on the wire as the all-reduce, W times less double-precision work behind it
+			const int W = c->cfg.shard_count > 1 ? c->cfg.shard_count : 1, me = W > 1 ? c->cfg.shard_rank : 0;
+			const size_t cnt = (size_t)c->p_lr * g.A * g.KP;
+			NCK(g_nccl.ReduceScatter(c->n, c->nred, cnt, ncclInt32, ncclSum, cm, c->stream2));
+			CK(cudaMemsetAsync(c->n, 0, (size_t)g.Lpad * g.A * g.KP * sizeof(int32_t), c->stream2));     // p_dirichlet used to clear it
+			PArgs pa{c->nred - (size_t)me * cnt, c->Pnext, nullptr, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0, 0,
+			         nullptr, c->geo.TL, me * c->p_lr, c->p_lr};
+			CK(launch_p_dirichlet(pa, c->stream2));
+			NCK(g_nccl.AllGather(c->Pnext + (size_t)me * cnt, c->Pnext, cnt, ncclFloat, cm, c->stream2));
+		} else {
+			NCK(g_nccl.AllReduce(c->n, c->n, (size_t)g.Lpad * g.A * g.KP, ncclInt32, ncclSum, cm, c->stream2));
+			PArgs pa{c->n, c->Pnext, c->P64, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0, 0, c->Pcnext, c->geo.TL};
+			CK(launch_p_dirichlet(pa, c->stream2));
+		}
 		CK(cudaEventRecord(c->ev_p, c->stream2));
 		c->launches++;
 		c->early_p = true;
@@ -882,6 +907,7 @@ static void ptrace_report(ig_ctx *c)
 	if (c->ptrace.empty() || c->ptrace_sweeps < 8) return;
 	static const char *names[PT_POINTS - 1] = {"update_P (wait / draw)", "update_S + G proposals", "zq_sweep", "epilogue", "all-gather", "local sums", "exchange + update_alpha"};
 	double acc[PT_POINTS - 1] = {0, 0, 0, 0, 0, 0, 0}, between = 0;
+	std::vector<float> gaps;             // between consecutive sweeps: the median (the caller's own pauses -- a barrier, a sync -- are not the sweep's)
 	int n = 0;
 	for (int s = 4; s < c->ptrace_sweeps; s++, n++) {            // skip the first sweeps
 		for (int p = 0; p + 1 < PT_POINTS; p++) {
@@ -889,11 +915,12 @@ static void ptrace_report(ig_ctx *c)
 			cudaEventElapsedTime(&ms, c->ptrace[(size_t)s * PT_POINTS + p], c->ptrace[(size_t)s * PT_POINTS + p + 1]);
 			acc[p] += ms;
 		}
-		if (s + 1 < c->ptrace_sweeps) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ptrace[(size_t)s * PT_POINTS + PT_POINTS - 1], c->ptrace[(size_t)(s + 1) * PT_POINTS]); between += ms; }
+		if (s + 1 < c->ptrace_sweeps) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ptrace[(size_t)s * PT_POINTS + PT_POINTS - 1], c->ptrace[(size_t)(s + 1) * PT_POINTS]); gaps.push_back(ms); }
 	}
 	fprintf(stderr, "[ig_phase_trace] rank %d, %d sweeps, us per sweep:", c->cfg.shard_rank, n);
 	for (int p = 0; p + 1 < PT_POINTS; p++) fprintf(stderr, " %s %.1f |", names[p], 1e3 * acc[p] / n);
-	fprintf(stderr, " between sweeps %.1f || host enqueue us per sweep:", 1e3 * between / (n > 1 ? n - 1 : 1));
+	if (!gaps.empty()) { std::sort(gaps.begin(), gaps.end()); between = gaps[gaps.size() / 2]; }
+	fprintf(stderr, " between sweeps (median) %.1f || host enqueue us per sweep:", 1e3 * between);
 	for (int p = 0; p < 4; p++) fprintf(stderr, " %.1f", 1e3 * c->ptrace_host_ms[p] / (c->ptrace_host_ms[4] > 0 ? c->ptrace_host_ms[4] : 1.0));
 	if (c->ptrace_host_ms[6] > 0) fprintf(stderr, " (DP prior: wait for G %.1f, scan %.1f)", 1e3 * c->ptrace_host_ms[5] / c->ptrace_host_ms[4], 1e3 * c->ptrace_host_ms[6] / c->ptrace_host_ms[4]);
 	fprintf(stderr, "\n");

@@ -109,6 +109,8 @@ struct ig_ctx {
 	cudaStream_t stream2 = nullptr;
 	cudaEvent_t ev_zq = nullptr, ev_p = nullptr;
 	float *Pnext = nullptr;
+	int32_t *nred = nullptr;         // this rank's block of the reduce-scattered tally (p_lr loci); null: all-reduce + full draw on every rank
+	int p_lr = 0;                    // loci per rank of that split: ceil(Lpad / W)
 	bool early_p = false;            // Pnext holds the P of sweep iter + 1 and n has been consumed
 	bool p_wait = false;             // the main stream has not yet waited for that draw (it does before zq_sweep)
 	bool more_follow = false;        // another sweep follows inside the current API call

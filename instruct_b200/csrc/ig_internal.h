@@ -146,6 +146,7 @@ struct PArgs {
 	int sub;                 // 1: the second subgenome of the allotetraploid model (its own random stream)
 	float *Pc;               // biallelic path: the chunk-ordered copy of P the sweep kernel stages (null otherwise)
 	int tlc;
+	int l0, nl;              // nl > 0: draw loci [l0, l0 + nl) only (a sharded chain draws 1/W of the loci per rank and all-gathers P)
 };
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s);
 

@@ -38,8 +38,9 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 	const Geometry &g = a.geo;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t iter = a.iter_dev ? *a.iter_dev : a.iter;
-	if (t >= g.Lpad * g.KP) return;
-	const int l = t / g.KP, k = t % g.KP;
+	if (t >= (a.nl > 0 ? a.nl : g.Lpad) * g.KP) return;
+	const int l = a.l0 + t / g.KP, k = t % g.KP;
+	if (l >= g.Lpad) return;
 	const size_t base = (size_t)l * g.A * g.KP + k;
 	const int Al = (l < g.L) ? a.allelenum[l] : 0;
 	if (k >= g.K || Al <= 1) {
@@ -78,7 +79,7 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 }
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s)
 {
-	const int total = a.geo.Lpad * a.geo.KP;
+	const int total = (a.nl > 0 ? a.nl : a.geo.Lpad) * a.geo.KP;
 	p_dirichlet_kernel<<<(total + 127) / 128, 128, 0, s>>>(a);
 	return cudaGetLastError();
 }
