@@ -194,6 +194,8 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	ptrace_report(c);
 	for (auto e : c->ptrace) cudaEventDestroy(e);
+	if (c->stream2) cudaStreamSynchronize(c->stream2);
+	peer_teardown(c);                // before the communicator goes (its barrier) and before Pnext is freed (it may point into the arena)
 	if (c->comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm2);
 	if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
 	for (auto e : c->ev) cudaEventDestroy(e);
@@ -208,7 +210,6 @@ extern "C" void ig_destroy(ig_ctx *c)
 	if (c->S_pin) cudaFreeHost(c->S_pin);
 	if (c->ev_g) cudaEventDestroy(c->ev_g);
 	tetra_destroy(c);
-	peer_teardown(c);
 	free_all(c);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -359,20 +360,39 @@ extern "C" ig_status ig_comm_unique_id(void *id128)
 // just created).  All ranks end up with px == true or all with px == false (then the sums go through ncclAllReduce).
 static void peer_teardown(ig_ctx *c)
 {
+	const bool had = c->px_buf != nullptr;
+	if (c->p_peer) { c->P = c->Pnext = nullptr; c->n = nullptr; c->p_peer = false; }      // they lived in the arena
 	for (void *p : c->px_mapped) if (p) cudaIpcCloseMemHandle(p);
 	c->px_mapped.clear();
 	if (c->px_peers) { cudaFree(c->px_peers); c->px_peers = nullptr; }
-	// The exported buffer of a multi-rank chain is NOT freed: freeing memory that another process still has mapped is undefined
-	// and there is no cheap point at which every peer is known to have closed it (a barrier here would hang on a dead peer).
-	// It is a few hundred KB per context, returned when the process exits.
-	if (c->px_buf && c->cfg.shard_count <= 1) (cudaFree)(c->px_buf);
+	// Freeing memory that another process still has mapped is undefined: every rank closes its mappings first, then all meet
+	// in a barrier on the communicator (which every rank destroys right after this, in the same ig_destroy), then free.
+	// A one-rank arena was never exported.
+	bool may_free = had && c->cfg.shard_count <= 1;
+	if (had && c->cfg.shard_count > 1 && c->comm && c->px) {
+		int32_t *f = nullptr;
+		if (ig_pool_malloc((void **)&f, 16) == cudaSuccess) {
+			cudaMemsetAsync(f, 0, 16, c->stream);
+			const bool ok = g_nccl.AllReduce(f, f, 1, ncclInt32, ncclSum, c->comm, c->stream) == ncclSuccess &&
+			                cudaStreamSynchronize(c->stream) == cudaSuccess;
+			ig_pool_free(f);
+			may_free = ok;
+		}
+	}
+	if (may_free) (cudaFree)(c->px_buf);              // otherwise left to process exit (setup failed half-way, or a peer is gone)
 	c->px_buf = nullptr;
 	c->px = false;
 }
 static ig_status peer_setup(ig_ctx *c)
 {
 	const int W = c->cfg.shard_count > 1 ? c->cfg.shard_count : 1, me = W > 1 ? c->cfg.shard_rank : 0;
-	const size_t bytes = px_buffer_words(W) * sizeof(unsigned long long);
+	// the arena: the scalar exchange buffer, then (when the tally -> P exchange goes over peer memory too) n and both P buffers
+	const Geometry &g = c->geo;
+	const bool want_p = c->stream2 && !g.snp && !getenv_once("IG_P_NCCL");
+	const size_t pn_bytes = (size_t)W * c->p_lr * g.A * g.KP * 4;
+	auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+	const size_t sc_bytes = up(px_buffer_words(W) * sizeof(unsigned long long));
+	const size_t bytes = sc_bytes + (want_p ? 3 * up(pn_bytes) : 0);
 	int bad = 0;
 	if ((cudaMalloc)((void **)&c->px_buf, bytes) != cudaSuccess) { cudaGetLastError(); c->px_buf = nullptr; bad = 1; }
 	if (!bad) { CK(cudaMemsetAsync(c->px_buf, 0, bytes, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
@@ -408,6 +428,21 @@ static ig_status peer_setup(ig_ctx *c)
 	CK(cudaStreamSynchronize(c->stream));
 	c->px_seq = 0;
 	c->px = true;
+	if (want_p) {
+		// n, P and Pnext move into the arena (their contents are written by ig_chain_init and by every sweep; nothing to copy)
+		c->px_n_off = sc_bytes;
+		c->px_p_off[0] = sc_bytes + up(pn_bytes);
+		c->px_p_off[1] = sc_bytes + 2 * up(pn_bytes);
+		cudaFree(c->n); cudaFree(c->P); cudaFree(c->Pnext); cudaFree(c->nred);
+		c->nred = nullptr;
+		char *base = reinterpret_cast<char *>(c->px_buf);
+		c->n = reinterpret_cast<int32_t *>(base + c->px_n_off);
+		c->P = reinterpret_cast<float *>(base + c->px_p_off[0]);
+		c->Pnext = reinterpret_cast<float *>(base + c->px_p_off[1]);
+		c->p_par = 0;
+		c->pp_seq = 0;
+		c->p_peer = true;
+	}
 	return IG_OK;
 }
 
@@ -734,6 +769,7 @@ static ig_status phase_update_P(ig_ctx *c)
 		// there (phase_zq), so update_S / the G proposals of this sweep still overlap the all-reduce and the draw (waiting
 		// here cost 46 us per sweep at 1250 individuals per GPU)
 		std::swap(c->P, c->Pnext);
+		c->p_par ^= 1;
 		std::swap(c->Pc, c->Pcnext);
 		c->early_p = false;
 		c->p_wait = true;
@@ -830,7 +866,20 @@ static ig_status phase_zq(ig_ctx *c, int init)
 		CK(cudaEventRecord(c->ev_zq, c->stream));
 		CK(cudaStreamWaitEvent(c->stream2, c->ev_zq, 0));
 		ncclComm_t cm = c->comm2 ? c->comm2 : c->comm;
-		if (c->nred) {
+		if (c->p_peer) {
+			// the whole tally -> P exchange over peer memory, no NCCL: "my tally is final" to every rank and wait for theirs; pull
+			// my block of loci from every rank's n, draw its Dirichlets, push the block into every rank's next-P buffer; "my
+			// block is in your buffer" and wait for theirs -- which also tells me every rank is done reading my n: clear it
+			const int W = c->cfg.shard_count > 1 ? c->cfg.shard_count : 1, me = W > 1 ? c->cfg.shard_rank : 0;
+			PeerPArgs x{c->px_peers, W, me, ++c->pp_seq, c->px_n_off, c->px_p_off[c->p_par ^ 1]};
+			PArgs pa{c->n, c->Pnext, nullptr, c->allelenum, c->geo, c->iter + 1, c->key0, c->key1, nullptr, 0, 0,
+			         nullptr, c->geo.TL, me * c->p_lr, c->p_lr};
+			CK(launch_p_peer_signal(x, 0, c->stream2));
+			CK(launch_p_peer_draw(pa, x, c->stream2));
+			CK(launch_p_peer_signal(x, 1, c->stream2));
+			CK(cudaMemsetAsync(c->n, 0, (size_t)g.Lpad * g.A * g.KP * sizeof(int32_t), c->stream2));
+			c->launches += 2;
+		} else if (c->nred) {
 			// every rank needs all of P but not all of n: the tally is reduce-SCATTERED by blocks of loci, each rank draws the
 			// Dirichlets of its block (1/W of the 43 us the full draw takes at config 4) and P is all-gathered -- the same
 			// bytes on the wire as the all-reduce, W times less double-precision work behind it

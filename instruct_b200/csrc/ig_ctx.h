@@ -131,6 +131,11 @@ struct ig_ctx {
 	unsigned long long **px_peers = nullptr;          // device array [W]
 	unsigned long long px_seq = 0;
 	bool px = false;
+	// ... and the tally -> P exchange over the same arena (p_peer_*): n and both P buffers live in it
+	bool p_peer = false;
+	size_t px_n_off = 0, px_p_off[2] = {0, 0};       // byte offsets inside every rank's arena
+	int p_par = 0;                                    // which P buffer c->P is (toggles with the P / Pnext swap; in lockstep on all ranks)
+	unsigned long long pp_seq = 0;
 	// IG_PHASE_TRACE=1: CUDA events at the phase boundaries of the first 64 sweeps, averages printed by ig_destroy
 	std::vector<cudaEvent_t> ptrace;
 	int ptrace_sweeps = 0;

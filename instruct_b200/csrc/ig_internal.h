@@ -187,7 +187,22 @@ struct TreeArgs {
 //   words [2 parities][W ranks][PX_WORDS] : rank r's contribution to the all-reduce of that parity, written BY rank r
 //   words [2 parities][W ranks]           : rank r's sequence number, written by rank r after its data
 constexpr int PX_WORDS = 32 + 2 * 1024;
-static inline size_t px_buffer_words(int W) { return (size_t)2 * W * PX_WORDS + (size_t)2 * W; }
+//   words [2][W]                          : sequence numbers of the tally / P exchange below ("my tally is final", "my block of P is in your buffer")
+static inline size_t px_buffer_words(int W) { return (size_t)2 * W * PX_WORDS + (size_t)4 * W; }
+__host__ __device__ static inline size_t px_pflag_word(int W, int which) { return (size_t)2 * W * PX_WORDS + (size_t)(2 + which) * W; }
+
+// The tally -> P exchange of a sharded sweep over peer memory (ig_kernels.cu p_peer_*): the arena every rank exports also
+// holds its tally n and both P buffers.  Rank r owns loci block r: it PULLS that block of every rank's n over NVLink and adds
+// (the reduce-scatter), draws the block's Dirichlets, and PUSHES the result into every rank's next-P buffer (the all-gather)
+// -- one kernel between two single-CTA flag kernels.
+struct PeerPArgs {
+	unsigned long long *const *peers;    // device array [W] of arena bases
+	int W, me;
+	unsigned long long seq;
+	size_t n_off, p_off;                 // byte offsets of n and of the P buffer being written, inside every arena
+};
+cudaError_t launch_p_peer_signal(const PeerPArgs &x, int which, cudaStream_t s);      // publish seq in flag array `which`, wait for all ranks'
+cudaError_t launch_p_peer_draw(const PArgs &a, const PeerPArgs &x, cudaStream_t s);   // a.l0 / a.nl: this rank's block
 struct PeerArgs {
 	unsigned long long *const *peers;    // device array [W]: every rank's buffer as mapped here (own buffer at [me])
 	int W, me;

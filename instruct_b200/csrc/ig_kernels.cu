@@ -33,7 +33,23 @@ namespace ig {
 // p_dirichlet: P[k][l][.] ~ Dirichlet(n[k][l][.] + 1)  (update_P, mcmc.c:846-857, lambda = 1).
 // One thread per (locus, population); writes fp32 P[l][a][k] and clears n for the next sweep.
 // --------------------------------------------------------------------------------------
-__global__ void p_dirichlet_kernel(const PArgs a)
+// PEER: the tally is the sum of every rank's n over NVLink and P goes into every rank's buffer (PeerPArgs); n is not cleared
+template <bool PEER>
+__device__ __forceinline__ int tally_at(const PArgs &a, const PeerPArgs &x, size_t e)
+{
+	if (!PEER) return a.n[e];
+	int v = 0;
+	for (int r = 0; r < x.W; r++) v += reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(x.peers[r]) + x.n_off)[e];
+	return v;
+}
+template <bool PEER>
+__device__ __forceinline__ void p_store(const PArgs &a, const PeerPArgs &x, size_t e, float v)
+{
+	if (!PEER) { a.P[e] = v; return; }
+	for (int r = 0; r < x.W; r++) reinterpret_cast<float *>(reinterpret_cast<char *>(x.peers[r]) + x.p_off)[e] = v;
+}
+template <bool PEER>
+__global__ void p_dirichlet_kernel(const PArgs a, const PeerPArgs x)
 {
 	const Geometry &g = a.geo;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,9 +62,9 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 	if (k >= g.K || Al <= 1) {
 		for (int al = 0; al < g.A; al++) {
 			const float v = (a.mono_ok && k < g.K && Al == 1 && al == 0) ? 1.0f : 0.0f;
-			a.P[base + (size_t)al * g.KP] = v;
+			p_store<PEER>(a, x, base + (size_t)al * g.KP, v);
 			if (a.Pc) snp_pc_store(a.Pc, a.tlc, g.KP, l, al, k, v);
-			a.n[base + (size_t)al * g.KP] = 0;
+			if (!PEER) a.n[base + (size_t)al * g.KP] = 0;
 		}
 		return;
 	}
@@ -57,30 +73,57 @@ __global__ void p_dirichlet_kernel(const PArgs a)
 	double gam[64];
 	// allelenum_max is small (2 for SNPs, tens for microsatellites); larger loci spill to a second pass
 	if (Al <= 64) {
-		for (int al = 0; al < Al; al++) { gam[al] = draw_gamma(st, (double)a.n[base + (size_t)al * g.KP] + 1.0); sum += gam[al]; }
+		for (int al = 0; al < Al; al++) { gam[al] = draw_gamma(st, (double)tally_at<PEER>(a, x, base + (size_t)al * g.KP) + 1.0); sum += gam[al]; }
 		for (int al = 0; al < g.A; al++) {
 			const double p = (al < Al) ? gam[al] / sum : 0.0;
 			const float pv = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;
-			a.P[base + (size_t)al * g.KP] = pv;
+			p_store<PEER>(a, x, base + (size_t)al * g.KP, pv);
 			if (a.Pc) snp_pc_store(a.Pc, a.tlc, g.KP, l, al, k, pv);
 			if (a.P64) a.P64[((size_t)k * g.L + l) * g.A + al] = p;
-			a.n[base + (size_t)al * g.KP] = 0;
+			if (!PEER) a.n[base + (size_t)al * g.KP] = 0;
 		}
 	} else {
-		for (int al = 0; al < Al; al++) sum += draw_gamma(st, (double)a.n[base + (size_t)al * g.KP] + 1.0);
+		for (int al = 0; al < Al; al++) sum += draw_gamma(st, (double)tally_at<PEER>(a, x, base + (size_t)al * g.KP) + 1.0);
 		Stream st2((uint32_t)l, (uint32_t)k + 256u * (uint32_t)a.sub, iter, TAG_P, a.key0, a.key1);     // replay the same stream
 		for (int al = 0; al < g.A; al++) {
-			const double p = (al < Al) ? draw_gamma(st2, (double)a.n[base + (size_t)al * g.KP] + 1.0) / sum : 0.0;
-			a.P[base + (size_t)al * g.KP] = (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f;
+			const double p = (al < Al) ? draw_gamma(st2, (double)tally_at<PEER>(a, x, base + (size_t)al * g.KP) + 1.0) / sum : 0.0;
+			p_store<PEER>(a, x, base + (size_t)al * g.KP, (al < Al) ? fmaxf((float)p, P_FLOOR) : 0.0f);
 			if (a.P64) a.P64[((size_t)k * g.L + l) * g.A + al] = p;
-			a.n[base + (size_t)al * g.KP] = 0;
+			if (!PEER) a.n[base + (size_t)al * g.KP] = 0;
 		}
 	}
 }
 cudaError_t launch_p_dirichlet(const PArgs &a, cudaStream_t s)
 {
 	const int total = (a.nl > 0 ? a.nl : a.geo.Lpad) * a.geo.KP;
-	p_dirichlet_kernel<<<(total + 127) / 128, 128, 0, s>>>(a);
+	p_dirichlet_kernel<false><<<(total + 127) / 128, 128, 0, s>>>(a, PeerPArgs{});
+	return cudaGetLastError();
+}
+cudaError_t launch_p_peer_draw(const PArgs &a, const PeerPArgs &x, cudaStream_t s)
+{
+	const int total = a.nl * a.geo.KP;
+	p_dirichlet_kernel<true><<<(total + 127) / 128, 128, 0, s>>>(a, x);
+	return cudaGetLastError();
+}
+// one CTA: (after a system-scope fence, so that everything this rank stored before -- its tally, its block of P in the
+// peers' buffers -- is visible) publish the sequence number in every rank's flag array, then wait for every rank's number
+__global__ void p_peer_signal_kernel(const PeerPArgs x, int which)
+{
+	const int tid = threadIdx.x;
+	const size_t flags = px_pflag_word(x.W, which);
+	__threadfence_system();
+	if (tid < x.W) {
+		*(volatile unsigned long long *)(x.peers[tid] + flags + x.me) = x.seq;
+		volatile unsigned long long *f = x.peers[x.me] + flags + tid;
+		const long long t0 = clock64();
+		while (*f < x.seq)
+			if (clock64() - t0 > (1ll << 34)) __trap();
+	}
+	__threadfence_system();
+}
+cudaError_t launch_p_peer_signal(const PeerPArgs &x, int which, cudaStream_t s)
+{
+	p_peer_signal_kernel<<<1, 32, 0, s>>>(x, which);
 	return cudaGetLastError();
 }
 

@@ -125,6 +125,9 @@ def gpu_mode():
     os.environ["IG_NCCL_SCALARS"] = "1"                                       # the same sums through ncclAllReduce instead of peer memory
     ok &= _diploid_variant(rank, world, local, mode=2, back_refl=1, K=4)
     del os.environ["IG_NCCL_SCALARS"]
+    os.environ["IG_P_NCCL"] = "1"                                             # tally reduce-scattered / P all-gathered by NCCL instead of the peer kernels
+    ok &= _diploid_variant(rank, world, local, mode=2, back_refl=1, K=4)
+    del os.environ["IG_P_NCCL"]
     ok &= _tetra_sharded(rank, world, local, 1)
     ok &= _tetra_sharded(rank, world, local, 0)
     flag = torch.tensor([1 if ok else 0], device="cuda")

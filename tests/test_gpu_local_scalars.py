@@ -50,7 +50,9 @@ def test_local_scalar_updates_reproduce_the_plain_chain(mode, back_refl, K, N, L
     # default: sums all-reduced by the peer-memory kernel; then through ncclAllReduce; without taking the next sweep's subset
     # sums ahead; and the round-1 path (records all-gathered, sequential update_S_POP on every rank)
     for env in ({"IG_COMM_SINGLE": "1"}, {"IG_COMM_SINGLE": "1", "IG_NCCL_SCALARS": "1"}, {"IG_COMM_SINGLE": "1", "IG_NO_TREE_AHEAD": "1"},
-                {"IG_COMM_SINGLE": "1", "IG_GATHER_RECORDS": "1"}):
+                {"IG_COMM_SINGLE": "1", "IG_GATHER_RECORDS": "1"},
+                # the tally -> P exchange: default over peer memory; through ncclReduceScatter / ncclAllGather; through ncclAllReduce
+                {"IG_COMM_SINGLE": "1", "IG_P_NCCL": "1"}, {"IG_COMM_SINGLE": "1", "IG_P_NCCL": "1", "IG_P_ALLREDUCE": "1"}):
         got = _chain(d, K, mode, back_refl, env, **kw)
         for name in FIELDS:
             assert np.array_equal(getattr(got[0], name), getattr(ref[0], name)), (env, name)
