@@ -15,6 +15,7 @@
 #include <utility>
 #include <vector>
 #include <algorithm>
+#include <unistd.h>
 
 #include <time.h>
 #include "ig_ctx.h"
@@ -104,7 +105,7 @@ static bool getenv_once(const char *name)
 	return v && *v && *v != '0';
 }
 static void ptrace_report(ig_ctx *c);
-static void peer_teardown(ig_ctx *c);
+static void peer_teardown(ig_ctx *c, bool collective);
 
 extern "C" ig_status ig_create(const ig_config *cfg, ig_ctx **out)
 {
@@ -195,7 +196,7 @@ extern "C" void ig_destroy(ig_ctx *c)
 	ptrace_report(c);
 	for (auto e : c->ptrace) cudaEventDestroy(e);
 	if (c->stream2) cudaStreamSynchronize(c->stream2);
-	peer_teardown(c);                // before the communicator goes (its barrier) and before Pnext is freed (it may point into the arena)
+	peer_teardown(c, c->px);         // before the communicator goes (its barrier) and before Pnext is freed (it may point into the arena)
 	if (c->comm2 && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm2);
 	if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
 	for (auto e : c->ev) cudaEventDestroy(e);
@@ -358,28 +359,27 @@ extern "C" ig_status ig_comm_unique_id(void *id128)
 
 // Map every rank's exchange buffer into every rank (CUDA IPC; the 64-byte handles travel through the communicator that was
 // just created).  All ranks end up with px == true or all with px == false (then the sums go through ncclAllReduce).
-static void peer_teardown(ig_ctx *c)
+static void peer_teardown(ig_ctx *c, bool collective)
 {
-	const bool had = c->px_buf != nullptr;
 	if (c->p_peer) { c->P = c->Pnext = nullptr; c->n = nullptr; c->p_peer = false; }      // they lived in the arena
 	for (void *p : c->px_mapped) if (p) cudaIpcCloseMemHandle(p);
 	c->px_mapped.clear();
 	if (c->px_peers) { cudaFree(c->px_peers); c->px_peers = nullptr; }
 	// Freeing memory that another process still has mapped is undefined: every rank closes its mappings first, then all meet
-	// in a barrier on the communicator (which every rank destroys right after this, in the same ig_destroy), then free.
+	// in a barrier on the communicator, then free.  `collective`: every rank of the communicator is inside this call (the
+	// agreed failure branch of peer_setup; ig_destroy of a context whose set-up succeeded -- which is all ranks or none).
 	// A one-rank arena was never exported.
-	bool may_free = had && c->cfg.shard_count <= 1;
-	if (had && c->cfg.shard_count > 1 && c->comm && c->px) {
+	bool may_free = c->cfg.shard_count <= 1;
+	if (c->cfg.shard_count > 1 && collective && c->comm) {
 		int32_t *f = nullptr;
 		if (ig_pool_malloc((void **)&f, 16) == cudaSuccess) {
 			cudaMemsetAsync(f, 0, 16, c->stream);
-			const bool ok = g_nccl.AllReduce(f, f, 1, ncclInt32, ncclSum, c->comm, c->stream) == ncclSuccess &&
-			                cudaStreamSynchronize(c->stream) == cudaSuccess;
+			may_free = g_nccl.AllReduce(f, f, 1, ncclInt32, ncclSum, c->comm, c->stream) == ncclSuccess &&
+			           cudaStreamSynchronize(c->stream) == cudaSuccess;
 			ig_pool_free(f);
-			may_free = ok;
 		}
 	}
-	if (may_free) (cudaFree)(c->px_buf);              // otherwise left to process exit (setup failed half-way, or a peer is gone)
+	if (c->px_buf && may_free) (cudaFree)(c->px_buf);     // otherwise left to process exit (a peer is gone)
 	c->px_buf = nullptr;
 	c->px = false;
 }
@@ -396,33 +396,38 @@ static ig_status peer_setup(ig_ctx *c)
 	int bad = 0;
 	if ((cudaMalloc)((void **)&c->px_buf, bytes) != cudaSuccess) { cudaGetLastError(); c->px_buf = nullptr; bad = 1; }
 	if (!bad) { CK(cudaMemsetAsync(c->px_buf, 0, bytes, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-	std::vector<cudaIpcMemHandle_t> hs((size_t)W);
-	memset(hs.data(), 0, hs.size() * sizeof(cudaIpcMemHandle_t));
-	if (!bad && W > 1 && cudaIpcGetMemHandle(&hs[(size_t)me], c->px_buf) != cudaSuccess) { cudaGetLastError(); bad = 1; }
+	// what every rank tells the others: the IPC handle of its arena and its process id.  CUDA IPC maps memory of OTHER
+	// processes; ranks that are threads of one process (the `inbreed` CLI's --shard individuals) keep the NCCL exchanges.
+	struct PeerBlob { cudaIpcMemHandle_t h; long long pid; long long pad; };
+	std::vector<PeerBlob> hs((size_t)W);
+	memset(hs.data(), 0, hs.size() * sizeof(PeerBlob));
+	hs[(size_t)me].pid = (long long)getpid();
+	if (!bad && W > 1 && cudaIpcGetMemHandle(&hs[(size_t)me].h, c->px_buf) != cudaSuccess) { cudaGetLastError(); bad = 1; }
 	char *hd = nullptr;
-	CK(dalloc(&hd, (size_t)W * sizeof(cudaIpcMemHandle_t) + 16));
-	CK(cudaMemcpyAsync(hd + (size_t)me * sizeof(cudaIpcMemHandle_t), &hs[(size_t)me], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice, c->stream));
-	NCK(g_nccl.AllGather(hd + (size_t)me * sizeof(cudaIpcMemHandle_t), hd, sizeof(cudaIpcMemHandle_t), ncclChar, c->comm, c->stream));
-	CK(cudaMemcpyAsync(hs.data(), hd, (size_t)W * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(dalloc(&hd, (size_t)W * sizeof(PeerBlob) + 16));
+	CK(cudaMemcpyAsync(hd + (size_t)me * sizeof(PeerBlob), &hs[(size_t)me], sizeof(PeerBlob), cudaMemcpyHostToDevice, c->stream));
+	NCK(g_nccl.AllGather(hd + (size_t)me * sizeof(PeerBlob), hd, sizeof(PeerBlob), ncclChar, c->comm, c->stream));
+	CK(cudaMemcpyAsync(hs.data(), hd, (size_t)W * sizeof(PeerBlob), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	std::vector<unsigned long long *> peers((size_t)W, nullptr);
 	c->px_mapped.assign((size_t)W, nullptr);
+	for (int r = 0; r < W; r++) if (r != me && hs[(size_t)r].pid == hs[(size_t)me].pid) bad = 1;
 	for (int r = 0; r < W && !bad; r++) {
 		if (r == me) { peers[(size_t)r] = c->px_buf; continue; }
 		void *p = nullptr;
-		if (cudaIpcOpenMemHandle(&p, hs[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); bad = 1; break; }
+		if (cudaIpcOpenMemHandle(&p, hs[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); bad = 1; break; }
 		c->px_mapped[(size_t)r] = p;
 		peers[(size_t)r] = (unsigned long long *)p;
 	}
 	// agree (and make sure every rank's zero fill is complete before anyone stores into a peer): sum of the failures
-	int32_t *flag_dev = reinterpret_cast<int32_t *>(hd + (size_t)W * sizeof(cudaIpcMemHandle_t));
+	int32_t *flag_dev = reinterpret_cast<int32_t *>(hd + (size_t)W * sizeof(PeerBlob));
 	CK(cudaMemcpyAsync(flag_dev, &bad, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
 	NCK(g_nccl.AllReduce(flag_dev, flag_dev, 1, ncclInt32, ncclSum, c->comm, c->stream));
 	int32_t nbad = 0;
 	CK(cudaMemcpyAsync(&nbad, flag_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	cudaFree(hd);
-	if (nbad) { peer_teardown(c); return IG_OK; }
+	if (nbad) { peer_teardown(c, true); return IG_OK; }
 	CK(dalloc(&c->px_peers, (size_t)W));
 	CK(cudaMemcpyAsync(c->px_peers, peers.data(), (size_t)W * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaStreamSynchronize(c->stream));

@@ -117,7 +117,7 @@ __global__ void p_peer_signal_kernel(const PeerPArgs x, int which)
 		volatile unsigned long long *f = x.peers[x.me] + flags + tid;
 		const long long t0 = clock64();
 		while (*f < x.seq)
-			if (clock64() - t0 > (1ll << 34)) __trap();
+			if (clock64() - t0 > (1ll << 36)) __trap();
 	}
 	__threadfence_system();
 }
@@ -957,7 +957,7 @@ __global__ void __launch_bounds__(PX_THREADS) peer_allreduce_kernel(const PeerAr
 		volatile unsigned long long *f = mine + flags + tid;
 		const long long t0 = clock64();
 		while (*f != x.seq)
-			if (clock64() - t0 > (1ll << 34)) __trap();        // ~9 s: a peer died; fail the context loudly instead of hanging the GPU
+			if (clock64() - t0 > (1ll << 36)) __trap();        // ~35 s: a peer died; fail the context loudly instead of hanging the GPU
 	}
 	__threadfence_system();
 	__syncthreads();
