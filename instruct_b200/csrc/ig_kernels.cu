@@ -12,6 +12,12 @@
 //     indiv_epilogue(N threads)         G accept, Q | Z,alpha, indvlkh     mcmc.c:1085-1089,1196-1198,1931
 //     post_sweep    (1 CTA)             alpha | Q, totallkh, column sums   mcmc.c:1244-1263,1940,1954-1961
 //     moments       (N*K threads)       store_chn                         mcmc.c:1320-1456
+// A chain sharded over GPUs by individuals (modes 1-2) replaces pre_sweep / post_sweep by sums over its LOCAL individuals
+// and two kernels that exchange over NVLink peer memory (no NCCL call inside a sweep):
+//     local_sums      2^K subset sums of the next update_S_POP + the post-sweep sums, fixed point
+//     peer_allreduce  all-reduce of those few KB through every rank's exported arena, fused with the update_alpha tail
+//     spop_decide     the K Metropolis decisions from the summed table, G proposals of the local individuals
+//     p_dirichlet<PEER>  pulls its block of every rank's tally, draws, pushes P to every rank (side stream)
 //
 // update_G reads the OLD Z and update_ZQ never reads G, so both can ride one pass over the
 // genotype store: the pass reads x (int16) and old z (int8), writes new z (int8) -- the
@@ -315,8 +321,9 @@ __device__ __forceinline__ int g_propose(double s, int i, uint32_t iter, uint32_
 //           log( s_i^(G_i-1) (1-s_i) ), s_i = sum_k Q_ik S_k  (proposal, mcmc.c:1630)
 //   mode 3, uniform prior: update_S_IND (mcmc.c:864-886), independent per individual
 //   mode 3, DP prior: S was written by the host step (ig_api.cu) before this launch
-// Every rank of a sharded chain runs this redundantly on the all-gathered (Q, G): identical
-// inputs and a fixed reduction order give identical S everywhere, so no broadcast is needed.
+// A sharded chain in mode 3 / 4 / 5 runs this redundantly on every rank over the all-gathered (Q, G): identical inputs and
+// exact (fixed-point) sums give identical S everywhere, so no broadcast is needed.  Modes 1-2 take the local path below
+// (local_sums_kernel / spop_decide_kernel) instead.
 // --------------------------------------------------------------------------------------
 template <bool COOP>
 __global__ void __launch_bounds__(COOP ? SC_THREADS : SC1_THREADS) pre_sweep_kernel(const PreArgs a)
