@@ -49,14 +49,15 @@ ALLO = {"c5a", "tiny5a"}
 
 
 def measured_traffic(workload, N, L):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json),
-    valid for the workload's default shape only."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if workload in t and (N, L) == WORKLOADS[workload][:2]:
-            return float(t[workload]["bytes"])
-    except Exception:
-        pass
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the current build
+    (profiles/r2_traffic.json; round 1's file if that is missing), valid for the workload's default shape only."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if workload in t and (N, L) == WORKLOADS[workload][:2]:
+                return float(t[workload]["bytes"])
+        except Exception:
+            pass
     return None
 
 
